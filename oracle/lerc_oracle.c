@@ -1,0 +1,909 @@
+/*
+ * lerc_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.  See lerc_oracle.h for scope and parity status.
+ *
+ * Untyped building blocks of the Lerc2 restatement (header, Fletcher-32, RLE, fixed-width bit
+ * stuffing, canonical Huffman) followed by the 8 typed instantiations of lerc_oracle_typed.inc and
+ * the lo_* API.  Every function names the reference file:line whose behaviour it restates
+ * (paths relative to /root/reference/src/LercLib).
+ */
+#include "lerc_oracle.h"
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <limits.h>
+#include <float.h>
+
+typedef uint8_t u8;
+typedef uint32_t u32;
+typedef uint64_t u64;
+
+static const int kTypeSize[8] = {1, 1, 2, 2, 4, 4, 4, 8};
+
+/* ------------------------------------------------------------------------------------------- */
+/* header                                                                        Lerc2.cpp:710-917 */
+
+typedef struct {
+  int version;
+  u32 checksum;
+  int nRows, nCols, nDepth, numValid, mbSize, blobSize, dt, nBlobsMore;
+  u8 passNoData, isInt, res3, res4;
+  double maxZErr, zMin, zMax, noData, noDataOrig;
+} lo_hdr;
+
+static int hdr_bytes(int v) {
+  return 6 + 4 + (v >= 3 ? 4 : 0) + 4 * (v >= 4 ? 7 : 6) + (v >= 6 ? 8 : 0) + 8 * (v >= 6 ? 5 : 3);
+}
+
+static void put_i32(u8** p, int v) { memcpy(*p, &v, 4); *p += 4; }
+static void put_f64(u8** p, double v) { memcpy(*p, &v, 8); *p += 8; }
+static int get_i32(const u8** p) { int v; memcpy(&v, *p, 4); *p += 4; return v; }
+static double get_f64(const u8** p) { double v; memcpy(&v, *p, 8); *p += 8; return v; }
+
+/* Lerc2.cpp:724-786.  The checksum slot is left 0; finish_blob() fills it. */
+static void hdr_write(u8* p, const lo_hdr* h) {
+  memcpy(p, "Lerc2 ", 6); p += 6;
+  put_i32(&p, h->version);
+  if (h->version >= 3) put_i32(&p, 0);
+  put_i32(&p, h->nRows); put_i32(&p, h->nCols);
+  if (h->version >= 4) put_i32(&p, h->nDepth);
+  put_i32(&p, h->numValid); put_i32(&p, h->mbSize); put_i32(&p, h->blobSize); put_i32(&p, h->dt);
+  if (h->version >= 6) {
+    put_i32(&p, h->nBlobsMore);
+    *p++ = h->passNoData; *p++ = h->isInt; *p++ = h->res3; *p++ = h->res4;
+  }
+  put_f64(&p, h->maxZErr); put_f64(&p, h->zMin); put_f64(&p, h->zMax);
+  if (h->version >= 6) { put_f64(&p, h->noData); put_f64(&p, h->noDataOrig); }
+}
+
+/* Lerc2.cpp:790-917 incl. the dimension guards at :877-911.  Returns header length or 0. */
+static int hdr_read(const u8* p, size_t avail, lo_hdr* h) {
+  memset(h, 0, sizeof *h);
+  if (avail < 10 || memcmp(p, "Lerc2 ", 6)) return 0;
+  const u8* q = p + 6;
+  h->version = get_i32(&q);
+  if (h->version < 0 || h->version > 6) return 0;
+  int need = hdr_bytes(h->version);
+  if (avail < (size_t)need) return 0;
+  if (h->version >= 3) h->checksum = (u32)get_i32(&q);
+  h->nRows = get_i32(&q); h->nCols = get_i32(&q);
+  h->nDepth = h->version >= 4 ? get_i32(&q) : 1;
+  h->numValid = get_i32(&q); h->mbSize = get_i32(&q); h->blobSize = get_i32(&q);
+  int dt = get_i32(&q);
+  if (h->version >= 6) {
+    h->nBlobsMore = get_i32(&q);
+    h->passNoData = *q++; h->isInt = *q++; h->res3 = *q++; h->res4 = *q++;
+  }
+  h->maxZErr = get_f64(&q); h->zMin = get_f64(&q); h->zMax = get_f64(&q);
+  if (h->version >= 6) { h->noData = get_f64(&q); h->noDataOrig = get_f64(&q); }
+  if (h->nRows <= 0 || h->nCols <= 0 || h->nDepth <= 0 || h->numValid < 0 || h->mbSize <= 0 || h->blobSize <= 0 ||
+      dt < 0 || dt > LO_DOUBLE)
+    return 0;
+  h->dt = dt;
+  u64 nPix = (u64)h->nRows * (u64)h->nCols, lim = (u64)INT_MAX, bpp = (u64)kTypeSize[dt];
+  if (nPix > lim || (u64)h->numValid > nPix) return 0;
+  if (h->mbSize > 32 || bpp * (u64)h->nDepth > lim || bpp * (u64)h->nDepth * nPix > lim) return 0;
+  return need;
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* Fletcher-32 over big-endian 16-bit words                                    Lerc2.cpp:1037-1064 */
+
+uint32_t lo_fletcher32(const uint8_t* b, int len) {
+  u32 s1 = 0xffff, s2 = 0xffff;
+  int words = len / 2;
+  while (words > 0) {
+    int chunk = words > 359 ? 359 : words;   /* 359 words keep both sums below 2^32 before folding */
+    words -= chunk;
+    for (int i = 0; i < chunk; i++, b += 2) {
+      s1 += ((u32)b[0] << 8) + b[1];
+      s2 += s1;
+    }
+    s1 = (s1 & 0xffff) + (s1 >> 16);
+    s2 = (s2 & 0xffff) + (s2 >> 16);
+  }
+  if (len & 1) { s1 += (u32)b[0] << 8; s2 += s1; }
+  s1 = (s1 & 0xffff) + (s1 >> 16);
+  s2 = (s2 & 0xffff) + (s2 >> 16);
+  return (s2 << 16) | s1;
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* byte RLE of the bit mask                                                         RLE.cpp:32-331 */
+/* Restated as a run tokenizer: a maximal run of equal bytes becomes a "repeat" token iff it is at
+ * least 5 long and starts more than 5 bytes before the end of the array (RLE.cpp:74-79); everything
+ * else is literal.  Both token kinds are cut into pieces of at most 32767 (RLE.cpp:98-107).
+ * Token = int16 count (LE) then: count>0 -> that many literal bytes; count<0 -> one byte repeated
+ * -count times; -32768 terminates (RLE.cpp:250). */
+
+typedef struct { u8* dst; size_t n; } rle_sink;
+
+static void rle_put(rle_sink* s, int count, const u8* bytes, size_t nBytes) {
+  if (s->dst) {
+    int16_t c = (int16_t)count;
+    s->dst[s->n] = (u8)(c & 0xff);
+    s->dst[s->n + 1] = (u8)((c >> 8) & 0xff);
+    if (nBytes) memcpy(s->dst + s->n + 2, bytes, nBytes);
+  }
+  s->n += 2 + nBytes;
+}
+
+static void rle_literals(rle_sink* s, const u8* src, size_t a, size_t b) {
+  while (a < b) {
+    size_t c = b - a > 32767 ? 32767 : b - a;
+    rle_put(s, (int)c, src + a, c);
+    a += c;
+  }
+}
+
+static size_t rle_run(const u8* src, size_t n, u8* dst) {
+  rle_sink s = {dst, 0};
+  if (!src || n == 0) return 0;
+  size_t pos = 0, lit = 0;
+  while (pos < n) {
+    size_t run = 1;
+    while (pos + run < n && src[pos + run] == src[pos]) run++;
+    if (run >= 5 && pos + 5 < n) {
+      rle_literals(&s, src, lit, pos);
+      size_t left = run;
+      while (left) {
+        size_t c = left > 32767 ? 32767 : left;
+        rle_put(&s, -(int)c, src + pos, 1);
+        left -= c;
+      }
+      lit = pos + run;
+    }
+    pos += run;
+  }
+  rle_literals(&s, src, lit, n);
+  rle_put(&s, -32768, NULL, 0);
+  return s.n;
+}
+
+size_t lo_rle_size(const uint8_t* src, size_t n) { return rle_run(src, n, NULL); }
+size_t lo_rle_encode(const uint8_t* src, size_t n, uint8_t* dst) { return rle_run(src, n, dst); }
+
+/* RLE.cpp:298-331.  1 on success. */
+int lo_rle_decode(const uint8_t* src, size_t srcLen, uint8_t* dst, size_t dstLen) {
+  if (!src || !dst || srcLen < 2) return 0;
+  size_t ip = 0, op = 0;
+  for (;;) {
+    if (ip + 2 > srcLen) return 0;
+    int16_t c = (int16_t)(src[ip] | (src[ip + 1] << 8));
+    ip += 2;
+    if (c == -32768) return 1;
+    size_t cnt = (size_t)(c <= 0 ? -c : c), take = c > 0 ? cnt : 1;
+    if (ip + take + 2 > srcLen || op + cnt > dstLen) return 0;
+    if (c > 0) memcpy(dst + op, src + ip, cnt);
+    else memset(dst + op, src[ip], cnt);
+    ip += take; op += cnt;
+  }
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* fixed-width bit stuffing, v3+ layout                                    BitStuffer2.cpp:35-287 */
+
+static int bit_length(u32 v) { int n = 0; while (n < 32 && (v >> n)) n++; return n; }
+static int count_field_bytes(u32 n) { return n < 256 ? 1 : (n < 65536 ? 2 : 4); }
+static size_t packed_bytes(u32 n, int nb) { return (size_t)(((u64)n * (u64)nb + 7) >> 3); }
+
+/* value i occupies stream bits [i*nb, (i+1)*nb), bit k of the stream = bit (k&7) of byte k>>3.
+ * This equals the reference's LE-uint32, LSB-first words with the unused tail bytes dropped
+ * (BitStuffer2.cpp:432-472). */
+static void pack_lsb(u8* dst, const u32* v, u32 n, int nb) {
+  size_t len = packed_bytes(n, nb);
+  memset(dst, 0, len);
+  u64 bit = 0;
+  for (u32 i = 0; i < n; i++, bit += (u64)nb) {
+    u64 x = (u64)v[i] << (bit & 7);
+    for (size_t k = bit >> 3; x; k++, x >>= 8) dst[k] |= (u8)x;
+  }
+}
+
+static void unpack_lsb(const u8* src, u32* v, u32 n, int nb) {
+  size_t len = packed_bytes(n, nb);
+  u64 bit = 0;
+  u32 mask = nb == 32 ? 0xffffffffu : ((1u << nb) - 1);
+  for (u32 i = 0; i < n; i++, bit += (u64)nb) {
+    u64 x = 0;
+    size_t k0 = bit >> 3;
+    for (int k = 0; k < 5 && k0 + k < len; k++) x |= (u64)src[k0 + k] << (8 * k);
+    v[i] = (u32)(x >> (bit & 7)) & mask;
+  }
+}
+
+static u8* put_count(u8* p, u32 n, int nBytes) {
+  if (nBytes == 1) *p = (u8)n;
+  else if (nBytes == 2) { uint16_t s = (uint16_t)n; memcpy(p, &s, 2); }
+  else memcpy(p, &n, 4);
+  return p + nBytes;
+}
+
+static u32 simple_size(u32 n, u32 maxElem) {   /* BitStuffer2.h:68-74 */
+  return 1 + (u32)count_field_bytes(n) + (u32)packed_bytes(n, bit_length(maxElem));
+}
+
+/* BitStuffer2.cpp:35-75 */
+static u8* encode_simple(u8* p, const u32* v, u32 n) {
+  u32 mx = 0;
+  for (u32 i = 0; i < n; i++) if (v[i] > mx) mx = v[i];
+  int nb = bit_length(mx), cb = count_field_bytes(n);
+  *p++ = (u8)(nb | ((cb == 4 ? 0 : 3 - cb) << 6));
+  p = put_count(p, n, cb);
+  if (nb > 0) { pack_lsb(p, v, n, nb); p += packed_bytes(n, nb); }
+  return p;
+}
+
+static int cmp_u32(const void* a, const void* b) {
+  u32 x = *(const u32*)a, y = *(const u32*)b;
+  return x < y ? -1 : (x > y ? 1 : 0);
+}
+
+/* distinct sorted values of v[] into lut[] (including the leading one); returns their count */
+static u32 distinct_sorted(const u32* v, u32 n, u32* lut) {
+  memcpy(lut, v, n * sizeof(u32));
+  qsort(lut, n, sizeof(u32), cmp_u32);
+  u32 m = 0;
+  for (u32 i = 0; i < n; i++) if (i == 0 || lut[i] != lut[i - 1]) lut[m++] = lut[i];
+  return m;
+}
+
+/* BitStuffer2.cpp:262-287: size of the cheaper of {simple, LUT}; *useLut says which. */
+static u32 lut_or_simple_size(const u32* v, u32 n, u32* scratch, int* useLut) {
+  u32 m = distinct_sorted(v, n, scratch);
+  u32 nLut = m - 1;
+  int nb = bit_length(scratch[m - 1]), nbIdx = bit_length(nLut), cb = count_field_bytes(n);
+  u32 simple = 1 + (u32)cb + (u32)packed_bytes(n, nb);
+  u32 lut = 1 + (u32)cb + 1 + (u32)packed_bytes(nLut, nb) + (u32)packed_bytes(n, nbIdx);
+  *useLut = lut < simple;
+  return lut < simple ? lut : simple;
+}
+
+/* BitStuffer2.cpp:79-153.  v[] must contain a 0 (the block minimum).  NULL on failure. */
+static u8* encode_lut(u8* p, const u32* v, u32 n, u32* scratch, u32* idxScratch) {
+  u32 m = distinct_sorted(v, n, scratch);
+  if (m < 2 || m > 255 || scratch[0] != 0) return NULL;
+  u32 nLut = m - 1;
+  int nb = bit_length(scratch[m - 1]), nbIdx = bit_length(nLut), cb = count_field_bytes(n);
+  if (nb <= 0 || nb >= 32) return NULL;
+  for (u32 i = 0; i < n; i++) {     /* rank of v[i] among the distinct values */
+    u32 lo = 0, hi = m - 1;
+    while (lo < hi) { u32 mid = (lo + hi) / 2; if (scratch[mid] < v[i]) lo = mid + 1; else hi = mid; }
+    idxScratch[i] = lo;
+  }
+  *p++ = (u8)(nb | (1 << 5) | ((cb == 4 ? 0 : 3 - cb) << 6));
+  p = put_count(p, n, cb);
+  *p++ = (u8)(nLut + 1);
+  pack_lsb(p, scratch + 1, nLut, nb); p += packed_bytes(nLut, nb);
+  pack_lsb(p, idxScratch, n, nbIdx);  p += packed_bytes(n, nbIdx);
+  return p;
+}
+
+/* BitStuffer2.cpp:159-258 (v3+ branch).  Returns bytes consumed, 0 on malformed input.
+ * v[] must hold maxCount entries. */
+static size_t decode_bitstuffed(const u8* p, size_t avail, u32* v, u32 maxCount, u32* nOut) {
+  const u8* p0 = p;
+  if (avail < 1) return 0;
+  u8 b = *p++; avail--;
+  int code = b >> 6, cb = code == 0 ? 4 : 3 - code, lut = (b >> 5) & 1, nb = b & 31;
+  if (cb <= 0 || avail < (size_t)cb) return 0;
+  u32 n = 0;
+  if (cb == 1) n = *p; else if (cb == 2) { uint16_t s; memcpy(&s, p, 2); n = s; } else memcpy(&n, p, 4);
+  p += cb; avail -= cb;
+  if (n > maxCount) return 0;
+  if (!lut) {
+    if (nb > 0) {
+      if (n == 0) return 0;
+      size_t len = packed_bytes(n, nb);
+      if (avail < len) return 0;
+      unpack_lsb(p, v, n, nb); p += len;
+    } else memset(v, 0, n * sizeof(u32));
+  } else {
+    if (nb == 0 || avail < 1) return 0;
+    int nLut = (int)*p++ - 1; avail--;
+    if (nLut < 1 || n == 0) return 0;
+    u32 table[256];
+    size_t len = packed_bytes((u32)nLut, nb);
+    if (avail < len) return 0;
+    table[0] = 0;
+    unpack_lsb(p, table + 1, (u32)nLut, nb); p += len; avail -= len;
+    int nbIdx = bit_length((u32)nLut);
+    len = packed_bytes(n, nbIdx);
+    if (avail < len) return 0;
+    unpack_lsb(p, v, n, nbIdx); p += len;
+    for (u32 i = 0; i < n; i++) { if (v[i] > (u32)nLut) return 0; v[i] = table[v[i]]; }
+  }
+  *nOut = n;
+  return (size_t)(p - p0);
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* canonical Huffman over a 256-bin histogram                                  Huffman.cpp:35-572 */
+
+typedef struct { int weight; int leaf; int kid0, kid1; } hnode;   /* weight = -count (Huffman.h:90) */
+
+/* The reference keeps its nodes in std::priority_queue<Node, vector<Node>, less<Node>>
+ * (Huffman.cpp:40).  Which of several equal-weight nodes surfaces first is decided by the binary
+ * heap's sift order, and that decides the code lengths, so the two libstdc++ sift routines
+ * (bits/stl_heap.h: __push_heap, __adjust_heap) are restated here on an index heap. */
+static void heap_sift_up(int* heap, const hnode* nd, int hole, int top, int val) {
+  int parent = (hole - 1) / 2;
+  while (hole > top && nd[heap[parent]].weight < nd[val].weight) {
+    heap[hole] = heap[parent];
+    hole = parent;
+    parent = (hole - 1) / 2;
+  }
+  heap[hole] = val;
+}
+
+static void heap_push(int* heap, int* n, const hnode* nd, int val) {
+  heap[*n] = val; (*n)++;
+  heap_sift_up(heap, nd, *n - 1, 0, val);
+}
+
+static int heap_pop(int* heap, int* n, const hnode* nd) {
+  int top = heap[0];
+  int len = --(*n);
+  if (len > 0) {
+    int val = heap[len], hole = 0, kid = 0;
+    while (kid < (len - 1) / 2) {
+      kid = 2 * (kid + 1);
+      if (nd[heap[kid]].weight < nd[heap[kid - 1]].weight) kid--;
+      heap[hole] = heap[kid];
+      hole = kid;
+    }
+    if ((len & 1) == 0 && kid == (len - 2) / 2) {
+      kid = 2 * (kid + 1);
+      heap[hole] = heap[kid - 1];
+      hole = kid - 1;
+    }
+    heap_sift_up(heap, nd, hole, 0, val);
+  }
+  return top;
+}
+
+static int assign_depths(const hnode* nd, int root, int depth, uint16_t* len) {
+  if (nd[root].leaf >= 0) { len[nd[root].leaf] = (uint16_t)depth; return 1; }
+  if (depth == 32) return 0;                               /* Huffman.h:91 */
+  return assign_depths(nd, nd[root].kid0, depth + 1, len) && assign_depths(nd, nd[root].kid1, depth + 1, len);
+}
+
+typedef struct { int key; int sym; } canon_key;
+static int cmp_canon(const void* a, const void* b) {
+  int x = ((const canon_key*)a)->key, y = ((const canon_key*)b)->key;
+  return x > y ? -1 : (x < y ? 1 : 0);
+}
+
+/* Huffman.cpp:35-81 + :541-572.  1 on success (>= 2 used symbols, no code longer than 32). */
+int lo_huffman_lengths(const int* histo, int n, uint16_t* len, uint32_t* code) {
+  hnode nd[512]; int heap[256], hn = 0, nn = 0;
+  if (n > 256) return 0;
+  for (int i = 0; i < n; i++) { len[i] = 0; code[i] = 0; }
+  for (int i = 0; i < n; i++)
+    if (histo[i] > 0) { nd[nn].weight = -histo[i]; nd[nn].leaf = i; nd[nn].kid0 = nd[nn].kid1 = -1; heap_push(heap, &hn, nd, nn); nn++; }
+  if (hn < 2) return 0;
+  while (hn > 1) {
+    int a = heap_pop(heap, &hn, nd), b = heap_pop(heap, &hn, nd);
+    nd[nn].weight = nd[a].weight + nd[b].weight; nd[nn].leaf = -1; nd[nn].kid0 = a; nd[nn].kid1 = b;
+    heap_push(heap, &hn, nd, nn); nn++;
+  }
+  if (!assign_depths(nd, heap[0], 0, len)) return 0;
+  /* canonical codes: longest first, smaller symbol first within a length, code shrinks by >> */
+  canon_key keys[256]; int nk = 0;
+  for (int i = 0; i < n; i++) if (len[i] > 0) { keys[nk].key = len[i] * n - i; keys[nk].sym = i; nk++; }
+  qsort(keys, nk, sizeof(canon_key), cmp_canon);
+  int curLen = len[keys[0].sym]; u32 c = 0;
+  for (int k = 0; k < nk; k++) {
+    int s = keys[k].sym, d = curLen - len[s];
+    c >>= d; curLen -= d;
+    code[s] = c++;
+  }
+  return 1;
+}
+
+static int wrap(int i, int size) { return i < size ? i : i - size; }
+
+/* Huffman.cpp:383-438: the stored index range, possibly wrapping past `size`. */
+static int huff_range(const uint16_t* len, int size, int* i0, int* i1, int* maxLen) {
+  int a = 0, b = size - 1;
+  while (a < size && len[a] == 0) a++;
+  while (b >= 0 && len[b] == 0) b--;
+  if (b + 1 <= a) return 0;
+  *i0 = a; *i1 = b + 1;
+  int bestStart = 0, bestLen = 0, j = 0;
+  while (j < size) {
+    while (j < size && len[j] > 0) j++;
+    int k0 = j;
+    while (j < size && len[j] == 0) j++;
+    if (j - k0 > bestLen) { bestStart = k0; bestLen = j - k0; }
+  }
+  if (size - bestLen < *i1 - *i0) { *i0 = bestStart + bestLen; *i1 = bestStart + size; }
+  if (*i1 <= *i0) return 0;
+  int mx = 0;
+  for (int i = *i0; i < *i1; i++) { int l = len[wrap(i, size)]; if (l > mx) mx = l; }
+  if (mx <= 0 || mx > 32) return 0;
+  *maxLen = mx;
+  return 1;
+}
+
+/* Huffman.cpp:357-379 */
+static int huff_table_bytes(const uint16_t* len, int size, int* nBytes) {
+  int i0, i1, maxLen;
+  if (!huff_range(len, size, &i0, &i1, &maxLen)) return 0;
+  int sum = 0;
+  for (int i = i0; i < i1; i++) sum += len[wrap(i, size)];
+  *nBytes = 16 + (int)simple_size((u32)(i1 - i0), (u32)maxLen) + 4 * ((((sum + 7) >> 3) + 3) >> 2);
+  return 1;
+}
+
+/* Huffman.cpp:85-111; total bits >= 2^31 is reported as "not available" (see DESIGN.md). */
+static int huff_total_bytes(const int* histo, const uint16_t* len, int size, int* nBytes) {
+  int tb;
+  if (!huff_table_bytes(len, size, &tb)) return 0;
+  int64_t bits = 0, elems = 0;
+  for (int i = 0; i < size; i++) if (histo[i] > 0) { bits += (int64_t)histo[i] * len[i]; elems += histo[i]; }
+  if (elems == 0 || bits >= ((int64_t)1 << 31)) return 0;
+  int64_t words = ((((bits + 7) >> 3) + 3) >> 2) + 1;
+  int64_t total = tb + 4 * words;
+  if (total > INT_MAX) return 0;
+  *nBytes = (int)total;
+  return 1;
+}
+
+/* MSB-first bit writer into little-endian uint32 words                        Huffman.h:218-255 */
+typedef struct { u8* base; u64 bitPos; } msb_writer;
+static void msb_put(msb_writer* w, u32 val, int nBits) {
+  for (int k = nBits - 1; k >= 0; k--, w->bitPos++) {
+    if ((val >> k) & 1) {
+      u64 word = w->bitPos >> 5; int bit = 31 - (int)(w->bitPos & 31);   /* bit index inside the LE word */
+      w->base[word * 4 + (bit >> 3)] |= (u8)(1u << (bit & 7));
+    }
+  }
+}
+static int msb_get(const u8* base, u64 bitPos) {
+  u64 word = bitPos >> 5; int bit = 31 - (int)(bitPos & 31);
+  return (base[word * 4 + (bit >> 3)] >> (bit & 7)) & 1;
+}
+
+/* Huffman.cpp:126-166 + :442-467.  Destination must be zero-filled.  Returns bytes written. */
+static size_t huff_write_table(u8* p, const uint16_t* len, const u32* code, int size) {
+  u8* p0 = p;
+  int i0, i1, maxLen;
+  if (!huff_range(len, size, &i0, &i1, &maxLen)) return 0;
+  put_i32(&p, 4); put_i32(&p, size); put_i32(&p, i0); put_i32(&p, i1);
+  u32 lens[512];
+  for (int i = i0; i < i1; i++) lens[i - i0] = len[wrap(i, size)];
+  p = encode_simple(p, lens, (u32)(i1 - i0));
+  msb_writer w = {p, 0};
+  for (int i = i0; i < i1; i++) { int k = wrap(i, size); if (len[k] > 0) msb_put(&w, code[k], len[k]); }
+  p += 4 * ((w.bitPos + 31) >> 5);
+  return (size_t)(p - p0);
+}
+
+/* Huffman.cpp:170-234 + :471-537.  Returns bytes consumed or 0. */
+static size_t huff_read_table(const u8* p, size_t avail, uint16_t* len, u32* code, int* sizeOut) {
+  const u8* p0 = p;
+  if (avail < 16) return 0;
+  int ver = get_i32(&p), size = get_i32(&p), i0 = get_i32(&p), i1 = get_i32(&p);
+  avail -= 16;
+  if (ver < 2 || i0 >= i1 || i0 < 0 || size < 0 || size > 256) return 0;
+  if (wrap(i0, size) >= size || wrap(i1 - 1, size) >= size || i1 - i0 > 512) return 0;
+  u32 lens[512], n = 0;
+  size_t used = decode_bitstuffed(p, avail, lens, (u32)(i1 - i0), &n);
+  if (!used || n != (u32)(i1 - i0)) return 0;
+  p += used; avail -= used;
+  for (int i = 0; i < size; i++) { len[i] = 0; code[i] = 0; }
+  u64 bits = 0;
+  for (int i = i0; i < i1; i++) {
+    int k = wrap(i, size);
+    if (lens[i - i0] > 32) return 0;
+    len[k] = (uint16_t)lens[i - i0];
+    bits += len[k];
+  }
+  size_t bytes = 4 * (size_t)((bits + 31) >> 5);
+  if (avail < bytes) return 0;
+  u64 pos = 0;
+  for (int i = i0; i < i1; i++) {
+    int k = wrap(i, size);
+    u32 c = 0;
+    for (int b = 0; b < len[k]; b++) c = (c << 1) | (u32)msb_get(p, pos++);
+    code[k] = c;
+  }
+  p += bytes;
+  *sizeOut = size;
+  return (size_t)(p - p0);
+}
+
+/* prefix-code decoder as a binary trie over the explicit (length, code) pairs of the table */
+typedef struct { int16_t kid[2]; int16_t sym; } trie_node;
+typedef struct { trie_node n[1024]; int used; } trie;
+
+static int trie_build(trie* t, const uint16_t* len, const u32* code, int size) {
+  t->used = 1; t->n[0].kid[0] = t->n[0].kid[1] = -1; t->n[0].sym = -1;
+  int any = 0;
+  for (int s = 0; s < size; s++) {
+    if (!len[s]) continue;
+    any = 1;
+    int cur = 0;
+    for (int b = len[s] - 1; b >= 0; b--) {
+      int bit = (code[s] >> b) & 1;
+      if (t->n[cur].sym >= 0) return 0;                 /* not prefix free */
+      if (t->n[cur].kid[bit] < 0) {
+        if (t->used >= 1024) return 0;
+        int nn = t->used++;
+        t->n[nn].kid[0] = t->n[nn].kid[1] = -1; t->n[nn].sym = -1;
+        t->n[cur].kid[bit] = (int16_t)nn;
+      }
+      cur = t->n[cur].kid[bit];
+    }
+    if (t->n[cur].kid[0] >= 0 || t->n[cur].kid[1] >= 0 || t->n[cur].sym >= 0) return 0;
+    t->n[cur].sym = (int16_t)s;
+  }
+  return any;
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* shared helpers of the typed code                                                               */
+
+static int mask_bit(const u8* bits, int64_t k) { return (bits[k >> 3] & (0x80 >> (k & 7))) != 0; }
+
+/* BitMask.cpp:100-119 */
+static int64_t mask_count(const u8* bits, int64_t nPix) {
+  int64_t c = 0;
+  for (int64_t k = 0; k < nPix; k++) c += mask_bit(bits, k);
+  return c;
+}
+
+/* Lerc2.h:457-542: smallest type that stores the block offset exactly; returns the 2-bit code. */
+static int fits_int(double z, double lo, double hi) { return z >= lo && z <= hi && z == floor(z); }
+static int reduce_offset_type(double z, int dt, int* dtUsed) {
+  int tc = 0;
+  switch (dt) {
+    case LO_SHORT:  tc = fits_int(z, -128, 127) ? 2 : (fits_int(z, 0, 255) ? 1 : 0); *dtUsed = dt - tc; break;
+    case LO_USHORT: tc = fits_int(z, 0, 255) ? 1 : 0; *dtUsed = dt - 2 * tc; break;
+    case LO_INT:    tc = fits_int(z, 0, 255) ? 3 : (fits_int(z, -32768, 32767) ? 2 : (fits_int(z, 0, 65535) ? 1 : 0)); *dtUsed = dt - tc; break;
+    case LO_UINT:   tc = fits_int(z, 0, 255) ? 2 : (fits_int(z, 0, 65535) ? 1 : 0); *dtUsed = dt - 2 * tc; break;
+    case LO_FLOAT:  tc = fits_int(z, 0, 255) ? 2 : (fits_int(z, -32768, 32767) ? 1 : 0); *dtUsed = tc == 0 ? dt : (tc == 1 ? LO_SHORT : LO_BYTE); break;
+    case LO_DOUBLE:
+      tc = fits_int(z, -32768, 32767) ? 3 : (fits_int(z, (double)INT_MIN, (double)INT_MAX) ? 2 : ((z >= -FLT_MAX && z <= FLT_MAX && (double)(float)z == z) ? 1 : 0));
+      *dtUsed = tc == 0 ? dt : dt - 2 * tc + 1; break;
+    default: *dtUsed = dt; break;
+  }
+  return tc;
+}
+
+static int offset_type_from_code(int dt, int tc) {      /* Lerc2.h:528-542 */
+  int r;
+  switch (dt) {
+    case LO_SHORT: case LO_INT: r = dt - tc; break;
+    case LO_USHORT: case LO_UINT: r = dt - 2 * tc; break;
+    case LO_FLOAT: r = tc == 0 ? dt : (tc == 1 ? LO_SHORT : LO_BYTE); break;
+    case LO_DOUBLE: r = tc == 0 ? dt : dt - 2 * tc + 1; break;
+    default: r = dt; break;
+  }
+  return (r >= LO_CHAR && r <= LO_DOUBLE) ? r : LO_UNDEFINED;
+}
+
+static u8* write_offset(u8* p, double z, int dtUsed) {   /* Lerc2.h:546-613 */
+  switch (dtUsed) {
+    case LO_CHAR:   { int8_t v = (int8_t)z; memcpy(p, &v, 1); return p + 1; }
+    case LO_BYTE:   { u8 v = (u8)z; memcpy(p, &v, 1); return p + 1; }
+    case LO_SHORT:  { int16_t v = (int16_t)z; memcpy(p, &v, 2); return p + 2; }
+    case LO_USHORT: { uint16_t v = (uint16_t)z; memcpy(p, &v, 2); return p + 2; }
+    case LO_INT:    { int32_t v = (int32_t)z; memcpy(p, &v, 4); return p + 4; }
+    case LO_UINT:   { u32 v = (u32)z; memcpy(p, &v, 4); return p + 4; }
+    case LO_FLOAT:  { float v = (float)z; memcpy(p, &v, 4); return p + 4; }
+    default:        { memcpy(p, &z, 8); return p + 8; }
+  }
+}
+
+static double read_offset(const u8* p, int dtUsed) {     /* Lerc2.h:617-681 */
+  switch (dtUsed) {
+    case LO_CHAR:   { int8_t v; memcpy(&v, p, 1); return v; }
+    case LO_BYTE:   { return *p; }
+    case LO_SHORT:  { int16_t v; memcpy(&v, p, 2); return v; }
+    case LO_USHORT: { uint16_t v; memcpy(&v, p, 2); return v; }
+    case LO_INT:    { int32_t v; memcpy(&v, p, 4); return v; }
+    case LO_UINT:   { u32 v; memcpy(&v, p, 4); return v; }
+    case LO_FLOAT:  { float v; memcpy(&v, p, 4); return v; }
+    default:        { double v; memcpy(&v, p, 8); return v; }
+  }
+}
+
+static u32 max_val_to_quantize(int dt) { return dt <= LO_USHORT ? (1u << 15) - 1 : (1u << 30) - 1; }  /* Lerc2.h:685-703 */
+
+/* per-band encoder/decoder state shared between the typed functions (the role of class Lerc2) */
+typedef struct {
+  lo_hdr hd;
+  u8* bits;              /* bit mask, (nPix+7)/8 bytes, MSB first */
+  int haveBits;          /* decoder: a mask from a previous band may be reused (Lerc2.cpp:1002) */
+  double* zMinVec; double* zMaxVec;   /* per depth */
+  int minMaxSet;         /* Lerc.cpp:749-751 */
+  int encodeMask, oneSweep, imageMode;
+  u32 maxQ;
+  uint16_t hLen[256]; u32 hCode[256]; int haveHuff;
+} band_state;
+
+enum { IEM_TILING = 0, IEM_DELTA_HUFFMAN = 1, IEM_HUFFMAN = 2, IEM_DELTA_DELTA_HUFFMAN = 3 };
+
+static int try_huffman_int(const lo_hdr* h) { return h->version >= 2 && (h->dt == LO_BYTE || h->dt == LO_CHAR) && h->maxZErr == 0.5; }
+static int try_huffman_flt(const lo_hdr* h) { return h->version >= 6 && (h->dt == LO_FLOAT || h->dt == LO_DOUBLE) && h->maxZErr == 0; }
+
+/* Lerc2.cpp:1012-1030 */
+static int finish_blob(u8* blob, const u8* end, const lo_hdr* h) {
+  if ((size_t)(end - blob) != (size_t)h->blobSize) return 0;
+  if (h->version >= 3) {
+    u32 cs = lo_fletcher32(blob + 14, h->blobSize - 14);
+    memcpy(blob + 10, &cs, 4);
+  }
+  return 1;
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* typed instantiations                                                                           */
+
+static int read_band_header(const u8* p, size_t avail, lo_hdr* h, int* hasMask);
+
+#define T int8_t
+#define TN(x) x##_i8
+#define T_CODE LO_CHAR
+#define T_IS_FLT 0
+#include "lerc_oracle_typed.inc"
+#undef T
+#undef TN
+#undef T_CODE
+#undef T_IS_FLT
+
+#define T uint8_t
+#define TN(x) x##_u8
+#define T_CODE LO_BYTE
+#define T_IS_FLT 0
+#include "lerc_oracle_typed.inc"
+#undef T
+#undef TN
+#undef T_CODE
+#undef T_IS_FLT
+
+#define T int16_t
+#define TN(x) x##_i16
+#define T_CODE LO_SHORT
+#define T_IS_FLT 0
+#include "lerc_oracle_typed.inc"
+#undef T
+#undef TN
+#undef T_CODE
+#undef T_IS_FLT
+
+#define T uint16_t
+#define TN(x) x##_u16
+#define T_CODE LO_USHORT
+#define T_IS_FLT 0
+#include "lerc_oracle_typed.inc"
+#undef T
+#undef TN
+#undef T_CODE
+#undef T_IS_FLT
+
+#define T int32_t
+#define TN(x) x##_i32
+#define T_CODE LO_INT
+#define T_IS_FLT 0
+#include "lerc_oracle_typed.inc"
+#undef T
+#undef TN
+#undef T_CODE
+#undef T_IS_FLT
+
+#define T uint32_t
+#define TN(x) x##_u32
+#define T_CODE LO_UINT
+#define T_IS_FLT 0
+#include "lerc_oracle_typed.inc"
+#undef T
+#undef TN
+#undef T_CODE
+#undef T_IS_FLT
+
+#define T float
+#define TN(x) x##_f32
+#define T_CODE LO_FLOAT
+#define T_IS_FLT 1
+#include "lerc_oracle_typed.inc"
+#undef T
+#undef TN
+#undef T_CODE
+#undef T_IS_FLT
+
+#define T double
+#define TN(x) x##_f64
+#define T_CODE LO_DOUBLE
+#define T_IS_FLT 1
+#include "lerc_oracle_typed.inc"
+#undef T
+#undef TN
+#undef T_CODE
+#undef T_IS_FLT
+
+/* ------------------------------------------------------------------------------------------- */
+/* API                                                                  Lerc_c_api_impl.cpp:33-305 */
+
+typedef unsigned (*enc_fn)(const void*, int, int, int, int, int, const u8*, double, u8*, unsigned, unsigned*, unsigned*);
+typedef unsigned (*dec_fn)(const u8*, unsigned, int, u8*, int, int, int, int, void*);
+static const enc_fn kEnc[8] = {encode_bands_i8, encode_bands_u8, encode_bands_i16, encode_bands_u16,
+                               encode_bands_i32, encode_bands_u32, encode_bands_f32, encode_bands_f64};
+static const dec_fn kDec[8] = {decode_bands_i8, decode_bands_u8, decode_bands_i16, decode_bands_u16,
+                               decode_bands_i32, decode_bands_u32, decode_bands_f32, decode_bands_f64};
+
+static int dims_ok(int nDepth, int nCols, int nRows, int elemSize) {     /* Lerc.cpp:1622-1639 */
+  if (nDepth <= 0 || nCols <= 0 || nRows <= 0) return 0;
+  u64 nPix = (u64)nRows * (u64)nCols, lim = (u64)INT_MAX, b = (u64)elemSize;
+  return !(nPix > lim || b * (u64)nDepth > lim || b * (u64)nDepth * nPix > lim);
+}
+
+static unsigned encode_common(const void* data, int version, unsigned dt, int nDepth, int nCols, int nRows, int nBands,
+                              int nMasks, const u8* validBytes, double maxZErr, u8* out, unsigned outSize,
+                              unsigned* nWritten, unsigned* nNeeded, int sizeOnly) {
+  if (!data || dt >= LO_UNDEFINED || nDepth <= 0 || nCols <= 0 || nRows <= 0 || nBands <= 0 || maxZErr < 0) return LO_WRONG_PARAM;
+  if (!sizeOnly && (!out || !outSize)) return LO_WRONG_PARAM;
+  if (!(nMasks == 0 || nMasks == 1 || nMasks == nBands) || (nMasks > 0 && !validBytes)) return LO_WRONG_PARAM;
+  if (!(version == -1 || version == 6)) return LO_WRONG_PARAM;     /* older writers: out of scope, see header */
+  if (!dims_ok(nDepth, nCols, nRows, kTypeSize[dt])) return LO_DIMS_TOO_LARGE;
+  if (!sizeOnly) memset(out, 0, outSize);                          /* Lerc.cpp:374 */
+  return kEnc[dt](data, nDepth, nCols, nRows, nBands, nMasks, validBytes, maxZErr, sizeOnly ? NULL : out, outSize, nWritten, nNeeded);
+}
+
+unsigned lo_computeCompressedSizeForVersion(const void* data, int version, unsigned dt, int nDepth, int nCols, int nRows,
+                                            int nBands, int nMasks, const unsigned char* validBytes, double maxZErr, unsigned* numBytes) {
+  if (!numBytes) return LO_WRONG_PARAM;
+  *numBytes = 0;
+  unsigned w = 0;
+  return encode_common(data, version, dt, nDepth, nCols, nRows, nBands, nMasks, validBytes, maxZErr, NULL, 0, &w, numBytes, 1);
+}
+unsigned lo_computeCompressedSize(const void* data, unsigned dt, int nDepth, int nCols, int nRows, int nBands, int nMasks,
+                                  const unsigned char* validBytes, double maxZErr, unsigned* numBytes) {
+  return lo_computeCompressedSizeForVersion(data, -1, dt, nDepth, nCols, nRows, nBands, nMasks, validBytes, maxZErr, numBytes);
+}
+unsigned lo_encodeForVersion(const void* data, int version, unsigned dt, int nDepth, int nCols, int nRows, int nBands,
+                             int nMasks, const unsigned char* validBytes, double maxZErr, unsigned char* out, unsigned outSize,
+                             unsigned* nWritten) {
+  if (!nWritten) return LO_WRONG_PARAM;
+  *nWritten = 0;
+  unsigned need = 0;
+  return encode_common(data, version, dt, nDepth, nCols, nRows, nBands, nMasks, validBytes, maxZErr, out, outSize, nWritten, &need, 0);
+}
+unsigned lo_encode(const void* data, unsigned dt, int nDepth, int nCols, int nRows, int nBands, int nMasks,
+                   const unsigned char* validBytes, double maxZErr, unsigned char* out, unsigned outSize, unsigned* nWritten) {
+  return lo_encodeForVersion(data, -1, dt, nDepth, nCols, nRows, nBands, nMasks, validBytes, maxZErr, out, outSize, nWritten);
+}
+
+/* the multi-band header walk of Lerc::GetLercInfo                                Lerc.cpp:92-182 */
+typedef struct {
+  int version, nDepth, nCols, nRows, numValid, nBands, nMasks, dt, nUsesNoData;
+  unsigned blobSize;
+  double zMin, zMax, maxZErr;
+} lo_info;
+
+static int read_band_header(const u8* p, size_t avail, lo_hdr* h, int* hasMask) {   /* Lerc2.cpp:495-510 */
+  int n = hdr_read(p, avail, h);
+  if (!n || avail - (size_t)n < 4) return 0;
+  int nm; memcpy(&nm, p + n, 4);
+  if (nm < 0) return 0;
+  *hasMask = nm > 0;
+  return 1;
+}
+
+/* ranges of one band into mins/maxs[iBand*nDepth ...]                Lerc.cpp:1014-1042, Lerc2.cpp:514-573 */
+static unsigned band_ranges(const u8* p, size_t avail, int iBand, const lo_hdr* h, double* mins, double* maxs, size_t nElem) {
+  int nDepth = h->nDepth;
+  if (nElem < ((size_t)iBand + 1) * (size_t)nDepth) return LO_BUFFER_TOO_SMALL;
+  if (nDepth == 1) { mins[iBand] = h->zMin; maxs[iBand] = h->zMax; return LO_OK; }
+  if (h->passNoData) return LO_HAS_NODATA;
+  if (h->version < 4) return LO_FAILED;
+  double* mn = mins + (size_t)iBand * nDepth; double* mx = maxs + (size_t)iBand * nDepth;
+  if (h->numValid == 0) { for (int i = 0; i < nDepth; i++) mn[i] = mx[i] = 0; return LO_OK; }
+  if (h->zMin == h->zMax) { for (int i = 0; i < nDepth; i++) mn[i] = mx[i] = h->zMin; return LO_OK; }
+  size_t off = (size_t)hdr_bytes(h->version);
+  if (avail < off + 4) return LO_FAILED;
+  int nm; memcpy(&nm, p + off, 4);
+  off += 4;
+  if (nm < 0 || avail < off + (size_t)nm) return LO_FAILED;
+  off += (size_t)nm;
+  size_t ts = (size_t)kTypeSize[h->dt], len = ts * (size_t)nDepth;
+  if (avail < off + 2 * len) return LO_FAILED;
+  for (int i = 0; i < nDepth; i++) {
+    mn[i] = read_offset(p + off + ts * (size_t)i, h->dt);
+    mx[i] = read_offset(p + off + len + ts * (size_t)i, h->dt);
+  }
+  return LO_OK;
+}
+
+static unsigned blob_info(const u8* blob, unsigned blobSize, lo_info* li, double* mins, double* maxs, size_t nElem) {
+  memset(li, 0, sizeof *li);
+  lo_hdr h; int hasMask = 0, nMasks = 0;
+  if (!read_band_header(blob, blobSize, &h, &hasMask)) return LO_FAILED;     /* (no Lerc1 in the oracle) */
+  li->version = h.version; li->nDepth = h.nDepth; li->nCols = h.nCols; li->nRows = h.nRows;
+  li->numValid = h.numValid; li->blobSize = (unsigned)h.blobSize; li->dt = h.dt;
+  li->zMin = h.zMin; li->zMax = h.zMax; li->maxZErr = h.maxZErr; li->nUsesNoData = h.passNoData ? 1 : 0;
+  int tryNext = h.version <= 5 || h.nBlobsMore > 0;
+  if (hasMask || h.numValid == 0) nMasks = 1;
+  if (mins && maxs) { unsigned e = band_ranges(blob, blobSize, 0, &h, mins, maxs, nElem); if (e) return e; }
+  li->nBands = 1;
+  if (li->blobSize > blobSize) return LO_FAILED;
+  lo_hdr g;
+  while (tryNext && read_band_header(blob + li->blobSize, blobSize - li->blobSize, &g, &hasMask)) {
+    if (g.nDepth != li->nDepth || g.nCols != li->nCols || g.nRows != li->nRows || g.dt != li->dt) return LO_FAILED;
+    tryNext = g.version <= 5 || g.nBlobsMore > 0;
+    if (g.passNoData) li->nUsesNoData++;
+    if (hasMask || g.numValid != li->numValid) nMasks = 2;
+    if ((u64)li->blobSize + (u64)g.blobSize > (u64)UINT_MAX) return LO_FAILED;
+    if ((u64)li->blobSize + (u64)g.blobSize > (u64)blobSize) return LO_FAILED;
+    if (g.zMin < li->zMin) li->zMin = g.zMin;
+    if (g.zMax > li->zMax) li->zMax = g.zMax;
+    if (g.maxZErr > li->maxZErr) li->maxZErr = g.maxZErr;
+    if (mins && maxs) {
+      unsigned e = band_ranges(blob + li->blobSize, blobSize - li->blobSize, li->nBands, &g, mins, maxs, nElem);
+      if (e) return e;
+    }
+    li->blobSize += (unsigned)g.blobSize;
+    li->nBands++;
+  }
+  li->nMasks = nMasks > 1 ? li->nBands : nMasks;
+  if (li->nUsesNoData > 0) li->nUsesNoData = li->nBands;
+  return LO_OK;
+}
+
+unsigned lo_getBlobInfo(const unsigned char* blob, unsigned blobSize, unsigned* infoArray, double* dataRangeArray,
+                        int infoArraySize, int dataRangeArraySize) {
+  if (!blob || !blobSize || (!infoArray && !dataRangeArray) || (infoArraySize <= 0 && dataRangeArraySize <= 0)) return LO_WRONG_PARAM;
+  lo_info li;
+  unsigned e = blob_info(blob, blobSize, &li, NULL, NULL, 0);
+  if (e) return e;
+  if (infoArray) {
+    unsigned v[11] = {(unsigned)li.version, (unsigned)li.dt, (unsigned)li.nDepth, (unsigned)li.nCols, (unsigned)li.nRows,
+                      (unsigned)li.nBands, (unsigned)li.numValid, li.blobSize, (unsigned)li.nMasks, (unsigned)li.nDepth,
+                      (unsigned)li.nUsesNoData};
+    for (int i = 0; i < infoArraySize; i++) infoArray[i] = i < 11 ? v[i] : 0;
+  }
+  if (dataRangeArray) {
+    int noData = li.nDepth > 1 && li.nUsesNoData > 0;
+    double v[3] = {noData ? -1 : li.zMin, noData ? -1 : li.zMax, li.maxZErr};
+    for (int i = 0; i < dataRangeArraySize; i++) dataRangeArray[i] = i < 3 ? v[i] : 0;
+  }
+  return LO_OK;
+}
+
+unsigned lo_getDataRanges(const unsigned char* blob, unsigned blobSize, int nDepth, int nBands, double* mins, double* maxs) {
+  if (!blob || !blobSize || !mins || !maxs || nDepth <= 0 || nBands <= 0) return LO_WRONG_PARAM;
+  lo_info li;
+  return blob_info(blob, blobSize, &li, mins, maxs, (size_t)nDepth * (size_t)nBands);
+}
+
+unsigned lo_decode(const unsigned char* blob, unsigned blobSize, int nMasks, unsigned char* validBytes, int nDepth,
+                   int nCols, int nRows, int nBands, unsigned dt, void* data) {
+  if (!blob || !blobSize || !data || dt >= LO_UNDEFINED || nDepth <= 0 || nCols <= 0 || nRows <= 0 || nBands <= 0) return LO_WRONG_PARAM;
+  if (!(nMasks == 0 || nMasks == 1 || nMasks == nBands) || (nMasks > 0 && !validBytes)) return LO_WRONG_PARAM;
+  if (!dims_ok(nDepth, nCols, nRows, kTypeSize[dt])) return LO_DIMS_TOO_LARGE;
+  lo_info li;
+  unsigned e = blob_info(blob, blobSize, &li, NULL, NULL, 0);
+  if (e) return e;
+  if (nMasks < li.nMasks || nBands > li.nBands) return LO_WRONG_PARAM;    /* Lerc.cpp:423-428 */
+  if (li.nUsesNoData && nDepth > 1) return LO_HAS_NODATA;                  /* Lerc.cpp:431-434; _4D out of scope */
+  if ((unsigned)li.dt != dt) return LO_FAILED;   /* deviation: the reference reinterprets; see DESIGN.md */
+  return kDec[dt](blob, blobSize, nMasks, validBytes, nDepth, nCols, nRows, nBands, data);
+}
+
+unsigned lo_decodeToDouble(const unsigned char* blob, unsigned blobSize, int nMasks, unsigned char* validBytes, int nDepth,
+                           int nCols, int nRows, int nBands, double* data) {       /* Lerc_c_api_impl.cpp:256-304 */
+  if (!blob || !blobSize || !data || nDepth <= 0 || nCols <= 0 || nRows <= 0 || nBands <= 0) return LO_WRONG_PARAM;
+  if (!(nMasks == 0 || nMasks == 1 || nMasks == nBands) || (nMasks > 0 && !validBytes)) return LO_WRONG_PARAM;
+  lo_info li;
+  unsigned e = blob_info(blob, blobSize, &li, NULL, NULL, 0);
+  if (e) return e;
+  if (li.nDepth != nDepth || li.nCols != nCols || li.nRows != nRows || li.nBands != nBands) return LO_FAILED;
+  size_t n = (size_t)nDepth * (size_t)nCols * (size_t)nRows * (size_t)nBands;
+  if (li.dt == LO_DOUBLE) return lo_decode(blob, blobSize, nMasks, validBytes, nDepth, nCols, nRows, nBands, LO_DOUBLE, data);
+  u8* tmp = (u8*)data + n * (8 - (size_t)kTypeSize[li.dt]);   /* decode into the tail, widen front to back */
+  e = lo_decode(blob, blobSize, nMasks, validBytes, nDepth, nCols, nRows, nBands, (unsigned)li.dt, tmp);
+  if (e) return e;
+  for (size_t k = 0; k < n; k++) data[k] = read_offset(tmp + k * (size_t)kTypeSize[li.dt], li.dt);
+  return LO_OK;
+}

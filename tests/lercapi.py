@@ -1,0 +1,161 @@
+"""ctypes view of the Lerc C API (include/Lerc_c_api.h) for ANY library exporting it.
+
+Used by the tests, bench.py and __graft_entry__.smoke() to drive three libraries through the
+very same calls: the product (lerc_b200/libLerc.so.4, CUDA), the oracle restatement
+(oracle/_build/liblerc_oracle.so, plain C, exports the same 12 symbols with an `lo_` prefix)
+and the unmodified reference (oracle/_ref/libLerc_ref.so).
+Mirrors the call sequence of the reference's own wrapper, OtherLanguages/Python/lerc/_lerc.py:277-790.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+DT_NP = [np.int8, np.uint8, np.int16, np.uint16, np.int32, np.uint32, np.float32, np.float64]
+DT_CODE = {np.dtype(t): i for i, t in enumerate(DT_NP)}
+
+ERR = {0: "Ok", 1: "Failed", 2: "WrongParam", 3: "BufferTooSmall", 4: "NaN", 5: "HasNoData", 6: "DimensionsTooLarge"}
+
+
+class LercLib:
+    def __init__(self, path, prefix="lerc_"):
+        self.path = path
+        self.lib = C.CDLL(path)
+        self.prefix = prefix
+        u, i, d, p = C.c_uint, C.c_int, C.c_double, C.c_void_p
+        sig = {
+            "computeCompressedSize": [p, u, i, i, i, i, i, p, d, p],
+            "encode": [p, u, i, i, i, i, i, p, d, p, u, p],
+            "computeCompressedSizeForVersion": [p, i, u, i, i, i, i, i, p, d, p],
+            "encodeForVersion": [p, i, u, i, i, i, i, i, p, d, p, u, p],
+            "getBlobInfo": [p, u, p, p, i, i],
+            "getDataRanges": [p, u, i, i, p, p],
+            "decode": [p, u, i, p, i, i, i, i, u, p],
+            "decodeToDouble": [p, u, i, p, i, i, i, i, p],
+            "computeCompressedSize_4D": [p, u, i, i, i, i, i, p, d, p, p, p],
+            "encode_4D": [p, u, i, i, i, i, i, p, d, p, u, p, p, p],
+            "decode_4D": [p, u, i, p, i, i, i, i, u, p, p, p],
+            "decodeToDouble_4D": [p, u, i, p, i, i, i, i, p, p, p],
+        }
+        self.f = {}
+        for name, args in sig.items():
+            fn = getattr(self.lib, prefix + name, None)
+            if fn is None:
+                continue
+            fn.argtypes = args
+            fn.restype = C.c_uint
+            self.f[name] = fn
+
+    # ---- helpers -------------------------------------------------------------------------
+    @staticmethod
+    def _shape(arr, n_depth, n_bands):
+        """arr layout: [nBands?][nRows][nCols][nDepth?]"""
+        a = np.ascontiguousarray(arr)
+        sh = list(a.shape)
+        if n_depth > 1:
+            assert sh[-1] == n_depth
+            sh = sh[:-1]
+        if n_bands > 1:
+            assert sh[0] == n_bands
+            sh = sh[1:]
+        assert len(sh) == 2, sh
+        return a, sh[0], sh[1]
+
+    def compute_size(self, arr, max_z_err, n_depth=1, n_bands=1, mask=None, version=None):
+        a, n_rows, n_cols = self._shape(arr, n_depth, n_bands)
+        n_masks, mp = self._mask(mask, n_bands, n_rows, n_cols)
+        n = C.c_uint(0)
+        if version is None:
+            st = self.f["computeCompressedSize"](a.ctypes.data, DT_CODE[a.dtype], n_depth, n_cols, n_rows, n_bands,
+                                                 n_masks, mp, max_z_err, C.addressof(n))
+        else:
+            st = self.f["computeCompressedSizeForVersion"](a.ctypes.data, version, DT_CODE[a.dtype], n_depth, n_cols,
+                                                           n_rows, n_bands, n_masks, mp, max_z_err, C.addressof(n))
+        return st, n.value
+
+    @staticmethod
+    def _mask(mask, n_bands, n_rows, n_cols):
+        if mask is None:
+            return 0, None
+        m = np.ascontiguousarray(mask, dtype=np.uint8)
+        n_masks = 1 if m.ndim == 2 else m.shape[0]
+        assert m.size == n_masks * n_rows * n_cols
+        LercLib._keep = m
+        return n_masks, m.ctypes.data
+
+    def encode(self, arr, max_z_err, n_depth=1, n_bands=1, mask=None, buf_size=None, version=None):
+        """returns (status, blob bytes, whole zero-filled output buffer as np.uint8)"""
+        a, n_rows, n_cols = self._shape(arr, n_depth, n_bands)
+        n_masks, mp = self._mask(mask, n_bands, n_rows, n_cols)
+        if buf_size is None:
+            buf_size = int(a.nbytes * 1.1) + 4096 + (n_rows * n_cols * n_bands) // 4
+        out = np.full(buf_size, 0xAB, dtype=np.uint8)  # the API must zero-fill it (Lerc.cpp:374)
+        n = C.c_uint(0)
+        if version is None:
+            st = self.f["encode"](a.ctypes.data, DT_CODE[a.dtype], n_depth, n_cols, n_rows, n_bands, n_masks, mp,
+                                  max_z_err, out.ctypes.data, buf_size, C.addressof(n))
+        else:
+            st = self.f["encodeForVersion"](a.ctypes.data, version, DT_CODE[a.dtype], n_depth, n_cols, n_rows, n_bands,
+                                            n_masks, mp, max_z_err, out.ctypes.data, buf_size, C.addressof(n))
+        return st, out[: n.value].tobytes(), out
+
+    def blob_info(self, blob):
+        b = np.frombuffer(blob, dtype=np.uint8)
+        info = np.zeros(11, dtype=np.uint32)
+        rng = np.zeros(3, dtype=np.float64)
+        st = self.f["getBlobInfo"](b.ctypes.data, b.size, info.ctypes.data, rng.ctypes.data, 11, 3)
+        keys = ["version", "dataType", "nDepth", "nCols", "nRows", "nBands", "nValidPixels", "blobSize", "nMasks",
+                "nDepth2", "nUsesNoDataValue"]
+        d = {k: int(v) for k, v in zip(keys, info)}
+        d.update(zMin=float(rng[0]), zMax=float(rng[1]), maxZErrUsed=float(rng[2]))
+        return st, d
+
+    def data_ranges(self, blob, n_depth, n_bands):
+        b = np.frombuffer(blob, dtype=np.uint8)
+        mins = np.zeros(n_depth * n_bands)
+        maxs = np.zeros(n_depth * n_bands)
+        st = self.f["getDataRanges"](b.ctypes.data, b.size, n_depth, n_bands, mins.ctypes.data, maxs.ctypes.data)
+        return st, mins, maxs
+
+    def decode(self, blob, n_masks=None, info=None, to_double=False):
+        """returns (status, data array [nBands][nRows][nCols][nDepth], mask array or None)"""
+        b = np.frombuffer(blob, dtype=np.uint8)
+        if info is None:
+            st, info = self.blob_info(blob)
+            if st:
+                return st, None, None
+        nb, nr, nc, nd = info["nBands"], info["nRows"], info["nCols"], info["nDepth"]
+        if n_masks is None:
+            n_masks = info["nMasks"]
+        dt = info["dataType"]
+        data = np.full((nb, nr, nc, nd), 0x5A, dtype=np.float64 if to_double else DT_NP[dt])
+        mask = np.full((n_masks, nr, nc), 7, dtype=np.uint8) if n_masks > 0 else None
+        mp = mask.ctypes.data if mask is not None else None
+        if to_double:
+            st = self.f["decodeToDouble"](b.ctypes.data, b.size, n_masks, mp, nd, nc, nr, nb, data.ctypes.data)
+        else:
+            st = self.f["decode"](b.ctypes.data, b.size, n_masks, mp, nd, nc, nr, nb, dt, data.ctypes.data)
+        return st, data, mask
+
+
+def _first(*paths):
+    for p in paths:
+        if os.path.exists(p):
+            return p
+    return None
+
+
+def ref_lib():
+    p = _first(os.path.join(ROOT, "oracle", "_ref", "libLerc_ref.so"))
+    return LercLib(p) if p else None
+
+
+def oracle_lib():
+    p = _first(os.path.join(ROOT, "oracle", "_build", "liblerc_oracle.so"))
+    return LercLib(p, prefix="lo_") if p else None
+
+
+def product_lib():
+    p = _first(os.path.join(ROOT, "lerc_b200", "libLerc.so.4"))
+    return LercLib(p) if p else None
