@@ -1,0 +1,109 @@
+// lerc_context.cpp -- CUDA plumbing behind the stateless C API: a pool of contexts (one stream, one
+// growable device arena, pinned staging) so that concurrent callers never share scratch memory
+// (the reference is re-entrant with all state on the caller's stack, SURVEY.md 8b "Threading").
+#include "lerc_internal.h"
+#include <cstdio>
+#include <cstdlib>
+#include <mutex>
+
+namespace lerc {
+
+bool cudaOk(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return true;
+  if (std::getenv("LERC_B200_VERBOSE"))
+    std::fprintf(stderr, "[lerc_b200] CUDA error in %s: %s\n", what, cudaGetErrorString(e));
+  cudaGetLastError();   // clear the sticky-free error state
+  return false;
+}
+
+// ---- arena ----------------------------------------------------------------------------------
+void* Arena::alloc(size_t bytes, size_t align) {
+  size_t off = (used + align - 1) / align * align;
+  if (off + bytes > cap) {
+    // Grow by replacing the block.  Pointers handed out earlier in this call stay valid because the
+    // old block is only retired (freed at releaseContext), never reused.
+    size_t want = cap ? cap * 2 : ((size_t)64 << 20);
+    while (want < bytes + align) want *= 2;
+    uint8_t* nb = nullptr;
+    if (!cudaOk(cudaMalloc(&nb, want), "cudaMalloc(arena)")) return nullptr;
+    if (base) retired.push_back(base);
+    base = nb; cap = want; used = 0;
+    off = 0;
+  }
+  used = off + bytes;
+  return base + off;
+}
+
+void Arena::reset() {
+  used = 0;
+  for (uint8_t* p : retired) cudaFree(p);
+  retired.clear();
+}
+
+void* Context::pinnedAlloc(size_t bytes) {
+  size_t off = (pinnedUsed + 63) / 64 * 64;
+  if (off + bytes > pinnedCap) return nullptr;
+  pinnedUsed = off + bytes;
+  return pinned + off;
+}
+
+// ---- pool -----------------------------------------------------------------------------------
+namespace {
+std::mutex gMutex;
+std::vector<Context*> gFree;
+Stats gStats = {0, 0, 0, 0, 0};
+bool gNoDevice = false;
+}  // namespace
+
+Stats& globalStats() { return gStats; }
+
+Context* acquireContext() {
+  {
+    std::lock_guard<std::mutex> lock(gMutex);
+    if (gNoDevice) return nullptr;
+    if (!gFree.empty()) { Context* c = gFree.back(); gFree.pop_back(); cudaSetDevice(c->device); return c; }
+  }
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    // No usable CUDA device: the product has no CPU fallback by design; every call fails loudly.
+    std::lock_guard<std::mutex> lock(gMutex);
+    gNoDevice = true;
+    std::fprintf(stderr, "[lerc_b200] no CUDA device available: this library has no CPU fallback\n");
+    cudaGetLastError();
+    return nullptr;
+  }
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+    std::lock_guard<std::mutex> lock(gMutex);
+    gNoDevice = true;
+    std::fprintf(stderr, "[lerc_b200] no CUDA device available: this library has no CPU fallback\n");
+    cudaGetLastError();
+    return nullptr;
+  }
+  Context* c = new Context();
+  c->device = dev;
+  if (!cudaOk(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate")) { delete c; return nullptr; }
+  c->pinnedCap = (size_t)1 << 20;
+  if (!cudaOk(cudaMallocHost(&c->pinned, c->pinnedCap), "cudaMallocHost")) { cudaStreamDestroy(c->stream); delete c; return nullptr; }
+  return c;
+}
+
+void releaseContext(Context* c) {
+  if (!c) return;
+  c->arena.reset();
+  c->pinnedUsed = 0;
+  std::lock_guard<std::mutex> lock(gMutex);
+  gStats.kernelLaunches += c->kernelLaunches;
+  c->kernelLaunches = 0;
+  gFree.push_back(c);
+}
+
+PtrKind classifyPointer(const void* p) {
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) { cudaGetLastError(); return PTR_HOST_PAGEABLE; }
+  if (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged) return PTR_DEVICE;
+  if (attr.type == cudaMemoryTypeHost) return PTR_HOST_PINNED;
+  return PTR_HOST_PAGEABLE;
+}
+
+}  // namespace lerc

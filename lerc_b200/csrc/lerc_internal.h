@@ -1,0 +1,145 @@
+// lerc_internal.h -- declarations shared by the host side and the CUDA translation units of lerc_b200.
+//
+// Layering:
+//   lerc_capi.cpp      C ABI (include/Lerc_c_api.h, include/lerc_b200.h): argument checks, pointer
+//                      classification (host / pinned / device), band loop
+//   lerc_format.cpp    pure host: Lerc2 header read/write, multi-band header walk, Huffman code
+//                      table construction and (de)serialisation
+//   lerc_encode.cu     band encoder: statistics, micro-block sizing/packing, Huffman, one-sweep
+//   lerc_decode.cu     band decoder: block boundary discovery, unpack/dequantise, Huffman, one-sweep
+//   lerc_mask.cu       validity mask kernels (byte<->bit, RLE), Fletcher-32, small utilities
+//
+// Reference citations are relative to /root/reference/src/LercLib.
+#pragma once
+#include <cstdint>
+#include <cstddef>
+#include <vector>
+#include <cuda_runtime.h>
+
+namespace lerc {
+
+enum ErrCode : unsigned { Ok = 0, Failed, WrongParam, BufferTooSmall, NaNFound, HasNoData, DimensionsTooLarge };
+enum DataType : int { DT_Char = 0, DT_Byte, DT_Short, DT_UShort, DT_Int, DT_UInt, DT_Float, DT_Double, DT_Undefined };
+enum ImageEncodeMode : int { IEM_Tiling = 0, IEM_DeltaHuffman = 1, IEM_Huffman = 2, IEM_DeltaDeltaHuffman = 3 };
+
+inline int typeSize(int dt) { static const int s[8] = {1, 1, 2, 2, 4, 4, 4, 8}; return (dt >= 0 && dt < 8) ? s[dt] : 0; }
+
+// ---------------------------------------------------------------------------------------------
+// Lerc2 band header (Lerc2.h:102-131, Lerc2.cpp:710-917)
+struct HeaderInfo {
+  int version = 6;
+  uint32_t checksum = 0;
+  int nRows = 0, nCols = 0, nDepth = 1, numValidPixel = 0, microBlockSize = 8, blobSize = 0, dt = DT_Undefined, nBlobsMore = 0;
+  uint8_t bPassNoDataValues = 0, bIsInt = 0, bReserved3 = 0, bReserved4 = 0;
+  double maxZError = 0, zMin = 0, zMax = 0, noDataVal = 0, noDataValOrig = 0;
+
+  bool tryHuffmanInt() const { return version >= 2 && (dt == DT_Byte || dt == DT_Char) && maxZError == 0.5; }
+  bool tryHuffmanFlt() const { return version >= 6 && (dt == DT_Float || dt == DT_Double) && maxZError == 0; }
+};
+
+int headerBytes(int version);                                        // 58 / 62 / 66 / 90
+void writeHeader(uint8_t* dst, const HeaderInfo& hd);                // checksum slot written as hd.checksum
+bool readHeader(const uint8_t* src, size_t avail, HeaderInfo& hd);   // incl. the guards of Lerc2.cpp:877-911
+
+// A blob that may live in host or device memory; fetch() brings small pieces to the host.
+struct ByteSource {
+  const uint8_t* base = nullptr;
+  size_t size = 0;
+  bool onDevice = false;
+  bool fetch(size_t off, size_t len, void* dst) const;
+};
+
+struct BlobInfo {     // Lerc.h:99-116
+  int version = 0, nDepth = 0, nCols = 0, nRows = 0, numValidPixel = 0, nBands = 0, nMasks = 0, dt = 0, nUsesNoDataValue = 0;
+  uint32_t blobSize = 0;
+  double zMin = 0, zMax = 0, maxZError = 0;
+};
+// Lerc::GetLercInfo (Lerc.cpp:92-182), Lerc2 blobs only.
+ErrCode getBlobInfo(const ByteSource& src, BlobInfo& info, double* mins, double* maxs, size_t nElem);
+
+// ---------------------------------------------------------------------------------------------
+// canonical Huffman code table for the 8-bit path (Huffman.cpp)
+struct HuffmanTable {
+  uint16_t len[256];
+  uint32_t code[256];
+  bool buildFromHistogram(const int* histo);              // Huffman.cpp:35-81 + :541-572
+  bool range(int& i0, int& i1, int& maxLen) const;        // Huffman.cpp:383-438
+  bool tableBytes(int& nBytes) const;                     // Huffman.cpp:357-379
+  bool totalBytes(const int* histo, int& nBytes) const;   // Huffman.cpp:85-111
+  size_t write(uint8_t* dst) const;                       // Huffman.cpp:126-166; dst zero-filled; returns bytes
+  size_t read(const uint8_t* src, size_t avail);          // Huffman.cpp:170-234; returns bytes consumed or 0
+};
+
+// ---------------------------------------------------------------------------------------------
+// CUDA context: one stream + a growable device arena + pinned staging, pooled per concurrent call.
+struct Arena {
+  uint8_t* base = nullptr;
+  size_t cap = 0, used = 0;
+  std::vector<uint8_t*> retired;   // blocks replaced by a bigger one during this call; freed at release
+  void* alloc(size_t bytes, size_t align = 256);
+  void reset();
+};
+
+struct Context {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  Arena arena;              // device scratch, bump-allocated per API call
+  uint8_t* pinned = nullptr;   // pinned host staging for small control transfers
+  size_t pinnedCap = 0;
+  uint8_t* pinnedBig = nullptr; size_t pinnedBigCap = 0;   // staging for pageable host payloads
+  uint64_t kernelLaunches = 0; // counted for lerc_b200_stats()
+  void* pinnedAlloc(size_t bytes);   // returns a region of `pinned` (bump, reset per call)
+  size_t pinnedUsed = 0;
+};
+
+Context* acquireContext();            // thread-safe; creates stream/arena on first use; nullptr if no CUDA device
+void releaseContext(Context* ctx);
+bool cudaOk(cudaError_t e, const char* what);   // logs and returns false on error
+
+enum PtrKind { PTR_HOST_PAGEABLE, PTR_HOST_PINNED, PTR_DEVICE };
+PtrKind classifyPointer(const void* p);
+
+// ---------------------------------------------------------------------------------------------
+// band-level device work.  All pointers named d* are device pointers valid on ctx->stream.
+
+struct BandMaskState {      // validity of the band being coded and of the previous band (Lerc.cpp:659-741)
+  uint8_t* dBits = nullptr;       // MSB-first bit mask, (nPix+7)/8 bytes (BitMask.h:48-67); valid even if all pixels are valid
+  uint8_t* dPrevBits = nullptr;
+  int numValid = 0;
+  bool havePrev = false;
+};
+
+struct EncodeBandArgs {
+  int dt, nDepth, nCols, nRows;
+  const void* dData;              // this band's pixels on the device
+  const uint8_t* dValidBytes;     // this band's byte mask on the device, or nullptr
+  double maxZErr;
+  int iBand, nBands, nMasks;
+  bool anyMaskModified;           // in/out across bands (Lerc.cpp:714-720)
+  uint8_t* dOut;                  // device output buffer (whole multi-band blob), may be nullptr for size-only
+  size_t outCapacity;             // bytes available in dOut from outOffset
+  size_t outOffset;               // where this band's blob starts
+};
+
+// Encodes (or only sizes, if a.dOut == nullptr) one band.  Returns Ok and the band blob size.
+ErrCode encodeBand(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t& bandBytes);
+
+struct DecodeBandArgs {
+  int dt, nDepth, nCols, nRows;
+  const uint8_t* dBlob;           // device pointer to this band's blob
+  size_t avail;                   // bytes available from dBlob
+  HeaderInfo hd;                  // already parsed on the host
+  const uint8_t* hBlob;           // the same band blob in host memory when the caller's blob is a host buffer, else nullptr
+  void* dData;                    // device output for this band
+  uint8_t* dValidBytes;           // device byte mask output for this band or nullptr
+};
+ErrCode decodeBand(Context* ctx, DecodeBandArgs& a, BandMaskState& ms);
+
+// misc device utilities (lerc_mask.cu)
+void launchConvertToDouble(Context* ctx, const void* dSrc, int dt, size_t n, double* dDst);   // in-place safe back-to-front
+
+// library statistics for bench.py / tests (lerc_b200.h)
+struct Stats { uint64_t kernelLaunches, encodeCalls, decodeCalls, fastPathEncodes, fastPathDecodes; };
+Stats& globalStats();
+
+}  // namespace lerc

@@ -1,0 +1,257 @@
+// lerc_mask.cu -- validity-mask kernels (byte mask <-> MSB-first bit mask, NaN folding, byte RLE),
+// Fletcher-32 and a few small utilities.  Reference citations relative to /root/reference/src/LercLib.
+#include "lerc_device.cuh"
+#include "lerc_kernels.h"
+
+namespace lerc {
+
+// ------------------------------------------------------------------------------------------------
+// byte mask (+ NaN test for float types) -> bit mask                 Lerc.cpp:959-975, :1420-1468
+// One thread produces one mask byte (8 pixels).  Pad bits of the last byte stay 1 (SetAllValid then
+// clear, Lerc.cpp:967-972).  counters[0] += number of valid pixels; counters[1] |= flags.
+template <class T>
+__global__ void k_mask_build(const T* __restrict__ data, const uint8_t* __restrict__ bytes, long long nPix, int nDepth,
+                             uint8_t* __restrict__ bits, int* __restrict__ counters) {
+  const long long nBytes = (nPix + 7) >> 3;
+  int valid = 0, flags = 0;
+  for (long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x; b < nBytes; b += (long long)gridDim.x * blockDim.x) {
+    unsigned out = 0;
+    for (int j = 0; j < 8; j++) {
+      const long long k = b * 8 + j;
+      bool v = true;
+      if (k < nPix) {
+        if (bytes) v = bytes[k] != 0;
+        if (PixelTraits<T>::isFloat && v) {
+          int bad = 0;
+          const T* px = data + k * nDepth;
+          for (int m = 0; m < nDepth; m++) bad += isNaNVal(px[m]) ? 1 : 0;
+          if (bad == nDepth) { v = false; flags |= MASKF_MODIFIED; }
+          else if (bad > 0) flags |= MASKF_MIXED_NAN;
+        }
+        valid += v ? 1 : 0;
+      }
+      out |= (v ? 1u : 0u) << (7 - j);
+    }
+    bits[b] = (uint8_t)out;
+  }
+  valid = warpSum(valid);
+  flags = __reduce_or_sync(FULL, flags);
+  if ((threadIdx.x & 31) == 0) {
+    if (valid) atomicAdd(&counters[0], valid);
+    if (flags) atomicOr(&counters[1], flags);
+  }
+}
+
+template <class T>
+void launchMaskBuild(Context* ctx, const void* dData, const uint8_t* dBytes, long long nPix, int nDepth, uint8_t* dBits, int* dCounters) {
+  const long long nBytes = (nPix + 7) >> 3;
+  int grid = (int)std::min<long long>((nBytes + 255) / 256, 148 * 16);
+  LERC_LAUNCH(ctx, k_mask_build<T>, grid, 256, 0, (const T*)dData, dBytes, nPix, nDepth, dBits, dCounters);
+}
+#define INST(T) template void launchMaskBuild<T>(Context*, const void*, const uint8_t*, long long, int, uint8_t*, int*);
+INST(int8_t) INST(uint8_t) INST(int16_t) INST(uint16_t) INST(int32_t) INST(uint32_t) INST(float) INST(double)
+#undef INST
+
+// bit mask -> byte mask (Lerc.cpp:979-995)
+__global__ void k_bits_to_bytes(const uint8_t* __restrict__ bits, long long nPix, uint8_t* __restrict__ bytes) {
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < nPix; k += (long long)gridDim.x * blockDim.x)
+    bytes[k] = maskBit(bits, k) ? 1 : 0;
+}
+void launchBitsToBytes(Context* ctx, const uint8_t* dBits, long long nPix, uint8_t* dBytes) {
+  int grid = (int)std::min<long long>((nPix + 255) / 256, 148 * 32);
+  LERC_LAUNCH(ctx, k_bits_to_bytes, grid, 256, 0, dBits, nPix, dBytes);
+}
+
+__global__ void k_fill_bytes(uint8_t* p, long long n, uint8_t v) {
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) p[k] = v;
+}
+
+// masks of consecutive bands equal?  (Lerc.cpp:999-1010; compared as validity, see DESIGN.md "Deviations")
+__global__ void k_bits_differ(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, long long nPix, int* __restrict__ flag) {
+  const long long nBytes = (nPix + 7) >> 3;
+  int diff = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nBytes; i += (long long)gridDim.x * blockDim.x) {
+    unsigned x = a[i] ^ b[i];
+    if (i == nBytes - 1 && (nPix & 7)) x &= 0xffu << (8 - (nPix & 7));     // ignore pad bits
+    diff |= x ? 1 : 0;
+  }
+  if (__any_sync(FULL, diff) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+void launchBitsDiffer(Context* ctx, const uint8_t* a, const uint8_t* b, long long nPix, int* dFlag) {
+  const long long nBytes = (nPix + 7) >> 3;
+  int grid = (int)std::min<long long>((nBytes + 255) / 256, 148 * 8);
+  LERC_LAUNCH(ctx, k_bits_differ, grid, 256, 0, a, b, nPix, dFlag);
+}
+
+// number of valid pixels in each run of 1024 pixels (128 mask bytes); one warp per chunk
+__global__ void k_chunk_valid_counts(const uint8_t* __restrict__ bits, long long nPix, int nChunks, uint32_t* __restrict__ counts) {
+  const int lane = threadIdx.x & 31;
+  for (int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); c < nChunks; c += gridDim.x * (blockDim.x >> 5)) {
+    int n = 0;
+    for (int j = 0; j < 4; j++) {
+      const long long byteIdx = (long long)c * 128 + lane * 4 + j, k0 = byteIdx * 8;
+      if (k0 < nPix) {
+        unsigned b = bits[byteIdx];
+        if (k0 + 8 > nPix) b &= 0xffu << (8 - (nPix - k0));
+        n += __popc(b);
+      }
+    }
+    n = warpSum(n);
+    if (lane == 0) counts[c] = (uint32_t)n;
+  }
+}
+void launchChunkValidCounts(Context* ctx, const uint8_t* dBits, long long nPix, int nChunks, uint32_t* dCounts) {
+  int grid = std::min((nChunks + 7) / 8, 148 * 8);
+  LERC_LAUNCH(ctx, k_chunk_valid_counts, grid, 256, 0, dBits, nPix, nChunks, dCounts);
+}
+
+// ------------------------------------------------------------------------------------------------
+// byte RLE of the bit mask                                                          RLE.cpp:32-331
+// Token stream: int16 count; count > 0: that many literal bytes follow; count < 0: one byte follows,
+// repeated -count times; -32768 ends the stream.  A maximal run of equal bytes is coded as a repeat
+// iff it is >= 5 long and starts more than 5 bytes before the end of the array (RLE.cpp:74-79); all
+// counts are capped at 32767 (RLE.cpp:98-107).  One warp walks the runs; lanes measure run lengths
+// with ballots and copy literal stretches cooperatively.  dst == nullptr only sizes.
+__global__ void k_rle_encode(const uint8_t* __restrict__ src, long long n, uint8_t* __restrict__ dst, uint32_t* __restrict__ sizeOut) {
+  const int lane = threadIdx.x;
+  long long pos = 0, lit = 0, out = 0;
+  auto putCount = [&](int c) {
+    if (dst && lane == 0) { dst[out] = (uint8_t)(c & 0xff); dst[out + 1] = (uint8_t)((c >> 8) & 0xff); }
+    out += 2;
+  };
+  auto flushLiterals = [&](long long a, long long b) {
+    while (a < b) {
+      const long long c = (b - a > 32767) ? 32767 : (b - a);
+      putCount((int)c);
+      if (dst) for (long long i = lane; i < c; i += 32) dst[out + i] = src[a + i];
+      out += c; a += c;
+    }
+  };
+  while (pos < n) {
+    const uint8_t v = src[pos];
+    long long run = 1;
+    for (;;) {                                   // extend the run 32 bytes at a time
+      const long long i = pos + run + lane;
+      const unsigned m = __ballot_sync(FULL, i < n && src[i] == v);
+      const int ones = (m == FULL) ? 32 : (__ffs(~m) - 1);
+      run += ones;
+      if (ones < 32) break;
+    }
+    if (run >= 5 && pos + 5 < n) {
+      flushLiterals(lit, pos);
+      long long left = run;
+      while (left) {
+        const long long c = left > 32767 ? 32767 : left;
+        putCount(-(int)c);
+        if (dst && lane == 0) dst[out] = v;
+        out += 1; left -= c;
+      }
+      lit = pos + run;
+    }
+    pos += run;
+  }
+  flushLiterals(lit, n);
+  putCount(-32768);
+  if (lane == 0) *sizeOut = (uint32_t)out;
+}
+void launchRleEncode(Context* ctx, const uint8_t* dSrc, long long n, uint8_t* dDst, uint32_t* dSize) {
+  LERC_LAUNCH(ctx, k_rle_encode, 1, 32, 0, dSrc, n, dDst, dSize);
+}
+
+// RLE.cpp:298-331.  status[0] = 1 on success, 0 on malformed input.
+__global__ void k_rle_decode(const uint8_t* __restrict__ src, long long srcLen, uint8_t* __restrict__ dst, long long dstLen, int* __restrict__ status) {
+  const int lane = threadIdx.x;
+  long long ip = 0, op = 0;
+  int ok = 1;
+  for (;;) {
+    if (ip + 2 > srcLen) { ok = 0; break; }
+    const int c = (int)(int16_t)(src[ip] | (src[ip + 1] << 8));
+    ip += 2;
+    if (c == -32768) break;
+    const long long cnt = c <= 0 ? -c : c, take = c > 0 ? cnt : 1;
+    if (ip + take + 2 > srcLen || op + cnt > dstLen) { ok = 0; break; }
+    if (c > 0) for (long long i = lane; i < cnt; i += 32) dst[op + i] = src[ip + i];
+    else { const uint8_t v = src[ip]; for (long long i = lane; i < cnt; i += 32) dst[op + i] = v; }
+    ip += take; op += cnt;
+  }
+  if (lane == 0) *status = ok;
+}
+void launchRleDecode(Context* ctx, const uint8_t* dSrc, long long srcLen, uint8_t* dDst, long long dstLen, int* dStatus) {
+  LERC_LAUNCH(ctx, k_rle_decode, 1, 32, 0, dSrc, srcLen, dDst, dstLen, dStatus);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fletcher-32 over big-endian 16-bit words                                     Lerc2.cpp:1037-1064
+// With w_i (i = 0..m-1) the words of the region (odd tail byte padded with a low zero byte):
+//   sum1 = 0xffff + SUM w_i ;  sum2 = 0xffff*(m+1) + SUM (m - i) * w_i      (both mod 65535, 0 -> 65535)
+// (SURVEY.md Appendix B.9).  A byte at region offset r contributes c = b << (r even ? 8 : 0) to word
+// r/2, so any partition of the bytes can accumulate  A = SUM c  and  D = SUM (r/2 mod 65535) * c
+// independently; sum2 = 0xffff*(m+1) + m*A - D.  Each thread folds its partials mod 65535 before
+// the block/global adds, so the 64-bit accumulators cannot overflow.
+__global__ void k_fletcher_partial(const uint8_t* __restrict__ region, long long len, unsigned long long* __restrict__ acc) {
+  unsigned long long A = 0, D = 0;
+  const long long nVec = (len + 15) >> 4;          // 16 region bytes per step (unaligned-safe byte loads via 4 x u32 when possible)
+  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nVec; v += (long long)gridDim.x * blockDim.x) {
+    const long long r0 = v << 4;
+    unsigned long long a = 0, d = 0;
+    const unsigned wbase = (unsigned)((r0 >> 1) % 65535);
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+      const long long r = r0 + j;
+      if (r < len) {
+        const unsigned c = (unsigned)region[r] << ((j & 1) ? 0 : 8);       // r0 is even, so parity of r == parity of j
+        a += c;
+        d += (unsigned long long)(wbase + (j >> 1)) * c;
+      }
+    }
+    A += a; D += d % 65535ull;
+  }
+  A %= 65535ull; D %= 65535ull;
+  for (int m = 16; m; m >>= 1) { A += __shfl_xor_sync(FULL, A, m); D += __shfl_xor_sync(FULL, D, m); }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(&acc[0], A); atomicAdd(&acc[1], D); }
+}
+
+// acc -> checksum; either stored at dst (encode) or compared with `expect` (decode: status |= 2 on mismatch)
+__global__ void k_fletcher_finish(const unsigned long long* __restrict__ acc, long long len, uint8_t* dst, uint32_t expect, int* status) {
+  const unsigned long long M = 65535ull;
+  const unsigned long long m = (unsigned long long)((len + 1) >> 1);
+  const unsigned long long A = acc[0] % M, D = acc[1] % M;
+  unsigned long long s1 = (0xffffull + A) % M;
+  unsigned long long s2 = ((0xffffull % M) * ((m + 1) % M) + (m % M) * A + (M - D)) % M;
+  if (s1 == 0) s1 = M;
+  if (s2 == 0) s2 = M;
+  const uint32_t cs = (uint32_t)((s2 << 16) | s1);
+  if (dst) { dst[0] = (uint8_t)cs; dst[1] = (uint8_t)(cs >> 8); dst[2] = (uint8_t)(cs >> 16); dst[3] = (uint8_t)(cs >> 24); }
+  else if (cs != expect) atomicOr(status, 2);
+}
+
+void launchFletcher(Context* ctx, const uint8_t* dRegion, long long len, unsigned long long* dAcc /*2, zeroed*/,
+                    uint8_t* dStoreAt, uint32_t expect, int* dStatus) {
+  const long long nVec = (len + 15) >> 4;
+  int grid = (int)std::min<long long>((nVec + 255) / 256, 148 * 8);
+  if (grid < 1) grid = 1;
+  LERC_LAUNCH(ctx, k_fletcher_partial, grid, 256, 0, dRegion, len, dAcc);
+  LERC_LAUNCH(ctx, k_fletcher_finish, 1, 1, 0, dAcc, len, dStoreAt, expect, dStatus);
+}
+
+// ------------------------------------------------------------------------------------------------
+template <class T>
+__global__ void k_to_double(const T* __restrict__ src, size_t n, double* __restrict__ dst) {
+  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) dst[k] = (double)src[k];
+}
+void launchConvertToDouble(Context* ctx, const void* dSrc, int dt, size_t n, double* dDst) {
+  int grid = (int)std::min<size_t>((n + 255) / 256, 148 * 32);
+  if (grid < 1) grid = 1;
+  switch (dt) {
+    case DT_Char:   LERC_LAUNCH(ctx, k_to_double<int8_t>,   grid, 256, 0, (const int8_t*)dSrc, n, dDst); break;
+    case DT_Byte:   LERC_LAUNCH(ctx, k_to_double<uint8_t>,  grid, 256, 0, (const uint8_t*)dSrc, n, dDst); break;
+    case DT_Short:  LERC_LAUNCH(ctx, k_to_double<int16_t>,  grid, 256, 0, (const int16_t*)dSrc, n, dDst); break;
+    case DT_UShort: LERC_LAUNCH(ctx, k_to_double<uint16_t>, grid, 256, 0, (const uint16_t*)dSrc, n, dDst); break;
+    case DT_Int:    LERC_LAUNCH(ctx, k_to_double<int32_t>,  grid, 256, 0, (const int32_t*)dSrc, n, dDst); break;
+    case DT_UInt:   LERC_LAUNCH(ctx, k_to_double<uint32_t>, grid, 256, 0, (const uint32_t*)dSrc, n, dDst); break;
+    case DT_Float:  LERC_LAUNCH(ctx, k_to_double<float>,    grid, 256, 0, (const float*)dSrc, n, dDst); break;
+    default: break;
+  }
+}
+
+}  // namespace lerc

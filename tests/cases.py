@@ -1,0 +1,95 @@
+"""Seeded synthetic rasters shared by the oracle-pinning tests (CPU) and the CUDA parity tests (GPU).
+
+Each case is (name, array, maxZErr, kwargs for LercLib.encode).  The generators follow SURVEY.md 8(d):
+smooth sinusoid fields plus noise for the float configs, clipped integer versions of the same for the
+integer types, plus the distributions that flip an image-global decision of the encoder
+(all-integer floats, pre-rounded floats, constant images, uniform noise, masks, NaNs, LUT-friendly data).
+"""
+import numpy as np
+
+
+def smooth_field(h, w, phase=0.0):
+    yy, xx = np.mgrid[0:h, 0:w]
+    return 1000 + 300 * np.sin(xx / 97 + phase) * np.cos(yy / 131) + 50 * np.sin(xx / 13 + yy / 17 + phase)
+
+
+def c2_raster(h, w, seed=1234, phase=0.0):
+    """BASELINE config 2/3/5 generator: float32 terrain-like field with N(0, 0.5) noise."""
+    rng = np.random.default_rng(seed)
+    return (smooth_field(h, w, phase) + rng.normal(0, 0.5, (h, w))).astype(np.float32)
+
+
+def c4_raster(h, w, seed=7, sigma=2.0):
+    """BASELINE config 4 generator: uint8, nDepth=3 (bluemarble-like)."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w]
+    r = 128 + 100 * np.sin(xx / 53) * np.cos(yy / 71)
+    g = 128 + 90 * np.sin(xx / 31 + 1) * np.cos(yy / 47)
+    b = 100 + 80 * np.cos(xx / 91) * np.sin(yy / 23)
+    img = np.stack([r, g, b], axis=-1) + rng.normal(0, sigma, (h, w, 3))
+    return np.clip(img, 0, 255).astype(np.uint8)
+
+
+def all_cases(h=257, w=300, seed=1):
+    rng = np.random.default_rng(seed)
+    smooth = smooth_field(h, w)
+    f32 = (smooth + rng.normal(0, 0.5, (h, w))).astype(np.float32)
+    cases = []
+
+    def add(name, arr, mz, **kw):
+        cases.append((name, arr, mz, kw))
+
+    add("f32_noisy_0.01", f32, 0.01)
+    add("f32_noisy_0.001", f32, 0.001)
+    add("f32_noisy_1", f32, 1.0)
+    add("f32_noisy_100", f32, 100.0)
+    add("f64_noisy_0.01", f32.astype(np.float64) + 1e-7, 0.01)
+    add("f32_rounded_0.1", np.round(f32, 1), 0.01)
+    add("f32_allint", np.round(f32), 0.01)
+    add("f32_allint_3.7", np.round(f32), 3.7)
+    add("f32_const", np.full((h, w), 3.25, np.float32), 0.01)
+    add("f32_zero", np.zeros((h, w), np.float32), 0.01)
+    add("f32_negzero_min", np.where(rng.random((h, w)) < 0.01, np.float32(-0.0), np.abs(f32)).astype(np.float32), 0.01)
+    add("f32_huge_range", (f32 * np.float32(1e6)).astype(np.float32), 1e-4)
+    for dt in [np.int8, np.uint8, np.int16, np.uint16, np.int32, np.uint32]:
+        info = np.iinfo(dt)
+        name = np.dtype(dt).name
+        a = np.clip(smooth / 8 + rng.normal(0, 2, (h, w)), info.min, info.max).astype(dt)
+        add(f"{name}_smooth_lossless", a, 0)
+        add(f"{name}_smooth_lossy2", a, 2)
+        add(f"{name}_uniform_lossless", rng.integers(info.min, int(info.max) + 1, (h, w), dtype=np.int64).astype(dt), 0)
+    mask = (rng.random((h, w)) > 0.3).astype(np.uint8)
+    mask2 = np.ones((h, w), np.uint8)
+    mask2[50:120, 30:200] = 0
+    add("f32_masked_random", f32, 0.01, mask=mask)
+    add("f32_masked_rect", f32, 0.01, mask=mask2)
+    add("u8_masked_rect", np.clip(smooth / 8, 0, 255).astype(np.uint8), 0, mask=mask2)
+    add("u8_masked_random", np.clip(smooth / 8, 0, 255).astype(np.uint8), 0, mask=mask)
+    add("f32_all_masked", f32, 0.01, mask=np.zeros((h, w), np.uint8))
+    rgb = c4_raster(h, w, seed=7)
+    add("u8_depth3_lossless", rgb, 0, n_depth=3)
+    add("u8_depth3_lossless_masked", rgb, 0, n_depth=3, mask=mask2)
+    add("i8_depth3_lossless", (rgb.astype(np.int16) - 128).astype(np.int8), 0, n_depth=3)
+    add("u16_depth3_lossless", rgb.astype(np.uint16) * 7, 0, n_depth=3)
+    add("i32_depth3_lossless", rgb.astype(np.int32) * 1000 - 5000, 0, n_depth=3)
+    add("f32_depth3_0.01", rgb.astype(np.float32) * np.float32(1.37), 0.01, n_depth=3)
+    bands = np.stack([f32, f32 * 2, f32 + 5])
+    add("f32_3bands", bands, 0.01, n_bands=3)
+    add("f32_3bands_3masks", bands, 0.01, n_bands=3, mask=np.stack([mask, mask2, mask]))
+    add("f32_3bands_1mask", bands, 0.01, n_bands=3, mask=mask2)
+    fn = f32.copy()
+    fn[10:20, 10:50] = np.nan
+    add("f32_nan", fn, 0.01)
+    add("f32_nan_3bands", np.stack([f32, fn, f32]), 0.01, n_bands=3)
+    add("f32_stepped_lut", (np.floor(smooth / 40) * 40).astype(np.float32), 0.01)
+    add("u8_classes_lut", (rng.integers(0, 4, (h, w)) * 60).astype(np.uint8), 0)
+    cls = np.repeat(np.repeat(rng.integers(0, 5, (h // 4 + 1, w // 4 + 1)), 4, 0), 4, 1)[:h, :w]
+    add("u16_class_blocks_lut", (cls * 1000).astype(np.uint16), 0)
+    add("i16_class_blocks_lut", (cls * 1000 - 2000).astype(np.int16), 0)
+    add("f32_lossless_raw", f32, 0)
+    add("f64_lossless_raw", f32.astype(np.float64) * 1.0000001, 0)
+    add("f32_tiny_3x5", f32[:3, :5].copy(), 0.01)
+    add("u8_tiny_1x1", np.array([[7]], np.uint8), 0)
+    add("f32_8x8", f32[:8, :8].copy(), 0.01)
+    add("i16_smooth_low_bitrate", (smooth / 300).astype(np.int16), 0)   # < 1.5 bpp -> 16x16 blocks
+    return cases

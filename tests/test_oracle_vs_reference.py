@@ -1,0 +1,155 @@
+"""CPU tests (-m "not gpu"): pin the plain-C oracle (oracle/lerc_oracle.c) to the reference.
+
+ (a) golden fixtures: the reference's shipped blobs + the JS sanity blob decode to exactly what the
+     reference decoded (tests/golden/*.npz, made by tests/golden/make_golden.py);
+ (b) synthetic rasters: the oracle's blob and decoded pixels hash to the reference's (synthetic_ref.npz);
+ (c) when oracle/_ref/libLerc_ref.so is present (always in the build container), byte-for-byte against it.
+"""
+import hashlib
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from cases import all_cases
+from lercapi import ROOT, oracle_lib, ref_lib
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+FPL_CASES = {"f32_lossless_raw", "f64_lossless_raw"}   # reference uses the FPL codec here: sizes differ by design
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    if oracle_lib() is None:
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")])
+    lib = oracle_lib()
+    assert lib is not None
+    return lib
+
+
+@pytest.mark.parametrize("name", ["california_400_400_1_float", "bluemarble_256_256_3_byte", "js_sanity_30_20_3_byte"])
+def test_golden_decode(oracle, name):
+    blob = open(os.path.join(GOLD, name + ".lerc2"), "rb").read()
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    st, info = oracle.blob_info(blob)
+    assert st == 0
+    want = dict(zip([str(k) for k in g["info_keys"]], g["info"]))
+    for k, v in want.items():
+        assert float(info[k]) == float(v), (k, info[k], v)
+    st, data, mask = oracle.decode(blob)
+    assert st == 0
+    assert np.array_equal(data.view(np.uint8), g["data"].view(np.uint8))      # bit-exact, floats included
+    if g["mask"].size:
+        assert np.array_equal(mask, g["mask"])
+    st, mins, maxs = oracle.data_ranges(blob, info["nDepth"], info["nBands"])
+    assert st == 0 and np.array_equal(mins, g["mins"]) and np.array_equal(maxs, g["maxs"])
+
+
+def test_js_sanity_expectations(oracle):
+    """the assertions of OtherLanguages/js/tests/sanity.mjs:27-40"""
+    blob = open(os.path.join(GOLD, "js_sanity_30_20_3_byte.lerc2"), "rb").read()
+    st, info = oracle.blob_info(blob)
+    assert (info["nCols"], info["nRows"], info["nDepth"], info["dataType"]) == (30, 20, 3, 1)
+    st, data, _ = oracle.decode(blob)
+    assert data.reshape(-1)[:6].tolist() == [13, 57, 68, 14, 59, 80]
+    px = data[0]
+    assert [int(px[..., d].min()) for d in range(3)] == [0, 30, 60] and int(px.max()) == 89
+
+
+def test_stored_checksums(oracle):
+    """free known-answer test: the Fletcher-32 values stored in the shipped blobs"""
+    import ctypes
+    f = oracle.lib.lo_fletcher32
+    f.restype = ctypes.c_uint32
+    f.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    for name, size in [("california_400_400_1_float", 176451), ("bluemarble_256_256_3_byte", 18747)]:
+        blob = np.frombuffer(open(os.path.join(GOLD, name + ".lerc2"), "rb").read(), np.uint8)
+        stored = int(np.frombuffer(blob[10:14].tobytes(), np.uint32)[0])
+        assert f(blob[14:].ctypes.data, size - 14) == stored
+
+
+def test_synthetic_hashes(oracle):
+    g = np.load(os.path.join(GOLD, "synthetic_ref.npz"))
+    want = {str(n): (int(s), str(e), str(d)) for n, s, e, d in zip(g["names"], g["sizes"], g["enc"], g["dec"])}
+    checked = 0
+    for name, arr, mz, kw in all_cases():
+        if name not in want:
+            continue
+        st, blob, buf = oracle.encode(arr, mz, **kw)
+        assert st == 0, name
+        assert not buf[len(blob):].any(), f"{name}: output buffer not zero-filled past the blob"
+        st, data, mask = oracle.decode(blob)
+        assert st == 0, name
+        if name not in FPL_CASES:
+            assert len(blob) == want[name][0], name
+            assert hashlib.sha256(blob).hexdigest() == want[name][1], f"{name}: blob differs from the reference's"
+            h = hashlib.sha256(data.tobytes())
+            if mask is not None:
+                h.update(mask.tobytes())
+            assert h.hexdigest() == want[name][2], f"{name}: decoded pixels differ from the reference's"
+        else:     # lossless float without FPL: must still round-trip exactly
+            assert np.array_equal(data.reshape(arr.shape).view(np.uint8), np.ascontiguousarray(arr).view(np.uint8))
+        st2, n = oracle.compute_size(arr, mz, **kw)
+        assert st2 == 0 and n == len(blob), name
+        checked += 1
+    assert checked >= 50
+
+
+def test_against_reference_library(oracle):
+    ref = ref_lib()
+    if ref is None:
+        pytest.skip("oracle/_ref/libLerc_ref.so not built (no /root/reference on this machine)")
+    for name, arr, mz, kw in all_cases():
+        s1, b1, _ = ref.encode(arr, mz, **kw)
+        s2, b2, _ = oracle.encode(arr, mz, **kw)
+        assert s1 == s2, name
+        if s1 != 0:
+            continue
+        if name not in FPL_CASES:
+            assert b1 == b2, name
+        for blob in (b1, b2):
+            if name in FPL_CASES and blob is b1:
+                continue              # FPL blobs are outside the oracle's scope
+            t1, d1, m1 = ref.decode(blob)
+            t2, d2, m2 = oracle.decode(blob)
+            assert t1 == 0 and t2 == 0, name
+            assert np.array_equal(d1.view(np.uint8), d2.view(np.uint8)) and np.array_equal(m1, m2), name
+
+
+def test_error_codes(oracle):
+    a = np.zeros((4, 4), np.float32)
+    assert oracle.encode(a, -1.0)[0] == 2                       # WrongParam: maxZErr < 0 (Lerc_c_api_impl.cpp:82)
+    st, blob, _ = oracle.encode(a + 1, 0.01, buf_size=50)
+    assert st == 3                                              # BufferTooSmall (Lerc.cpp:764)
+    nan = np.full((4, 4, 2), 1.0, np.float32); nan[0, 0, 0] = np.nan
+    assert oracle.encode(nan, 0.01, n_depth=2)[0] == 4          # NaN: mixed NaN at one pixel, no noData value (Lerc.cpp:1481)
+    st, blob, _ = oracle.encode(a + 1, 0.01)
+    bad = bytearray(blob); bad[-1] ^= 0xFF
+    assert oracle.decode(bytes(bad))[0] == 1                    # checksum mismatch -> Failed (Lerc2.cpp:599)
+    assert oracle.decode(blob[:-3])[0] == 1                     # truncated
+
+
+def test_rle_against_reference_tokens(oracle):
+    """RLE restated as a run tokenizer: round-trips and hits the documented corner cases"""
+    import ctypes
+    lib = oracle.lib
+    lib.lo_rle_size.restype = ctypes.c_size_t
+    lib.lo_rle_encode.restype = ctypes.c_size_t
+    lib.lo_rle_size.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
+    lib.lo_rle_encode.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
+    lib.lo_rle_decode.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t]
+    rng = np.random.default_rng(3)
+    samples = [np.zeros(5, np.uint8), np.zeros(6, np.uint8), np.zeros(70000, np.uint8), rng.integers(0, 3, 5000).astype(np.uint8),
+               np.repeat(rng.integers(0, 255, 400), rng.integers(1, 12, 400)).astype(np.uint8), np.array([9], np.uint8),
+               np.concatenate([rng.integers(0, 255, 40000), np.zeros(40000)]).astype(np.uint8)]
+    for s in samples:
+        n = lib.lo_rle_size(s.ctypes.data, s.size)
+        out = np.zeros(n + 8, np.uint8)
+        assert lib.lo_rle_encode(s.ctypes.data, s.size, out.ctypes.data) == n
+        back = np.full(s.size, 0x55, np.uint8)
+        assert lib.lo_rle_decode(out.ctypes.data, n, back.ctypes.data, s.size) == 1
+        assert np.array_equal(back, s)
+    # a 5-run at the very end stays literal, a 6-run becomes a repeat token (RLE.cpp:74-79)
+    five = np.zeros(5, np.uint8); six = np.zeros(6, np.uint8)
+    assert lib.lo_rle_size(five.ctypes.data, 5) == 2 + 5 + 2 and lib.lo_rle_size(six.ctypes.data, 6) == 3 + 2
