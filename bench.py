@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""bench.py -- LERC encode+decode throughput of lerc_b200 on B200 (driver contract, task section 4).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c4]
+
+One "step" = lerc_encode + lerc_decode of one synthetic raster of BASELINE.json configs[1]
+(4096x4096 float32, 1 band, maxZError = 0.01; generator tests/cases.py:c2_raster).
+  value   Gpixels/s with the raster / blob / output resident in HBM (device pointers through the C ABI,
+          timed with CUDA events on the stream the kernels run on)
+  e2e     the same calls with pinned HOST buffers: H2D of the raster, D2H of the blob, H2D of the blob,
+          D2H of the pixels are inside the timed region
+  roofline  dominant kernel: algorithmic bytes / its CUDA-event duration vs MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the unmodified reference (oracle/_ref/libLerc_ref.so) on the host cores, bounded sample
+With N > 1 (torchrun) every rank codes its own raster (independent objects, weak scaling, no data-path
+collective); rank 0 reports units of all ranks / max-over-ranks time.
+--impl reference times the reference's CPU implementation on the host cores and prints the same JSON line.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WORKLOADS = {
+    # name: (rows, cols, nDepth, dtype code, maxZErr, description)
+    "c2": (4096, 4096, 1, 6, 0.01, "4096x4096 float32 1-band encode+decode maxZError=0.01"),
+    "c4": (8192, 8192, 3, 1, 0.0, "8192x8192 nDepth=3 uint8 lossless (Huffman path)"),
+}
+
+
+def make_raster(workload, seed):
+    from cases import c2_raster, c4_raster
+    rows, cols, depth, dt, mz, _ = WORKLOADS[workload]
+    if workload == "c2":
+        return c2_raster(rows, cols, seed=seed, phase=0.1 * (seed % 7))
+    return c4_raster(rows, cols, seed=seed)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p))["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region"""
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = []
+        for i, n in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
+            if any(len(r) > 2 + i and r[2 + i].lower().startswith("active") for r in self.rows):
+                reasons.append(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference_run(workload, seconds_budget=20.0, threads=None):
+    """The reference's own CPU implementation on the host cores (bounded sample)."""
+    from lercapi import oracle_lib, ref_lib
+    lib, kind = ref_lib(), "reference"
+    if lib is None:
+        lib, kind = oracle_lib(), "port"
+    assert lib is not None, "neither oracle/_ref/libLerc_ref.so nor oracle/_build/liblerc_oracle.so present"
+    rows, cols, depth, dt, mz, desc = WORKLOADS[workload]
+    # bounded sample: a horizontal strip of the workload raster per thread (the library is single-threaded and
+    # re-entrant: one independent call per core)
+    threads = threads or os.cpu_count() or 1
+    strip_rows = min(rows, 1024 if workload == "c2" else 512)
+    img = make_raster(workload, 1234)[:strip_rows]
+    n_px = strip_rows * cols
+
+    def one(out):
+        t0 = time.perf_counter()
+        st, blob, _ = lib.encode(img, mz, n_depth=depth)
+        assert st == 0
+        st, dec, _ = lib.decode(blob)
+        assert st == 0
+        out.append(time.perf_counter() - t0)
+
+    one([])   # warm-up (page in the library, touch the buffers)
+    single = []
+    one(single)
+    reps = max(1, int(seconds_budget / max(single[0], 1e-3) / 2))
+    reps = min(reps, 8)
+    t0 = time.perf_counter()
+    res = []
+    th = [threading.Thread(target=lambda: [one(res) for _ in range(reps)]) for _ in range(threads)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    wall = time.perf_counter() - t0
+    gpx_all = threads * reps * n_px / wall / 1e9
+    gpx_one = n_px / single[0] / 1e9
+    return {"value": gpx_all, "unit": "Gpixels/s", "cores": threads, "kind": kind, "single_thread_value": gpx_one,
+            "sample": f"{strip_rows}x{cols} strip of the workload raster, {reps} encode+decode calls on each of {threads} threads ({wall:.1f} s wall)"}, wall / (threads * reps) * 1e3
+
+
+# ---------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    rows, cols, depth, dt, mz, desc = WORKLOADS[args.workload]
+    n_px = rows * cols
+    peak_gbs, peak_src = peaks()
+    warm = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        base, ms = cpu_reference_run(args.workload, seconds_budget=max(10.0, 2.0 * args.steps))
+        line = {"impl": "reference", "metric": "Gpixels/s encode+decode", "value": base["value"], "unit": "Gpixels/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64" if dt >= 6 else "int32", "data": "synthetic", "config": {"workload": desc, "sample": base["sample"]},
+                "cpu_baseline": base, "e2e": {"value": base["value"], "unit": "Gpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    import lerc_b200
+    from lercapi import DT_NP, product_lib
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device: lerc_b200 has no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = product_lib()
+    assert lib is not None, "lerc_b200/libLerc.so.4 missing: run python __graft_entry__.py"
+    enc, dec = lib.f["encode"], lib.f["decode"]
+    ts = np.dtype(DT_NP[dt]).itemsize
+    raw_bytes = n_px * depth * ts
+
+    # rotating buffer sets: successive steps touch different inputs/outputs, > 126 MB L2 between reuses
+    NBUF = 4
+    host_imgs = [make_raster(args.workload, 1234 + rank * 16 + i) for i in range(NBUF)]
+    d_imgs = [torch.from_numpy(h).cuda() for h in host_imgs]
+    cap = raw_bytes + raw_bytes // 8 + 4096
+    d_blobs = [torch.empty(cap, dtype=torch.uint8, device="cuda") for _ in range(NBUF)]
+    d_decs = [torch.empty_like(d) for d in d_imgs]
+    n_written = C.c_uint(0)
+    stream = torch.cuda.current_stream()
+    lerc_b200.set_stream(stream.cuda_stream, True)
+
+    def step_device(i):
+        k = i % NBUF
+        st = enc(d_imgs[k].data_ptr(), dt, depth, cols, rows, 1, 0, None, mz, d_blobs[k].data_ptr(), cap, C.addressof(n_written))
+        assert st == 0, f"lerc_encode status {st}"
+        nb = n_written.value
+        st = dec(d_blobs[k].data_ptr(), nb, 0, None, depth, cols, rows, 1, dt, d_decs[k].data_ptr())
+        assert st == 0, f"lerc_decode status {st}"
+        return nb
+
+    # ---- device-resident timing ------------------------------------------------------------------
+    for i in range(warm):
+        blob_bytes = step_device(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = lerc_b200.stats()[0]
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for i in range(args.steps):
+        ev[i][0].record(stream)
+        step_device(warm + i)
+        ev[i][1].record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches = lerc_b200.stats()[0] - launches0
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    clocks = sampler.stop()
+    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max = float(t.item())
+    ms_per_step = dev_ms_max / args.steps
+    value = world * n_px / (ms_per_step * 1e-3) / 1e9
+
+    # correctness guard inside the bench: the decoded raster respects maxZError (reference slack 1.1x, Lerc.cpp:1137)
+    k = (warm + args.steps - 1) % NBUF
+    err = float((d_decs[k].double() - d_imgs[k].double()).abs().max().item())
+    assert err <= max(mz, 0.5 if dt < 6 else 0) * 1.1 + 1e-12, f"round trip error {err} exceeds maxZError {mz}"
+
+    # ---- per-kernel roofline (separate instrumented pass, CUDA events around every launch) ------------
+    lerc_b200.kernel_times(reset=True)
+    lerc_b200.profile(True)
+    PROF = max(3, min(args.steps, 10))
+    for i in range(PROF):
+        step_device(i)
+    torch.cuda.synchronize()
+    lerc_b200.profile(False)
+    kt = lerc_b200.kernel_times(reset=True)
+    total_k = sum(v[1] for v in kt.values()) or 1.0
+    top = max(kt.items(), key=lambda kv: kv[1][1])
+    top_name, (top_cnt, top_ms) = top
+    per_launch_ms = top_ms / top_cnt
+    # algorithmic bytes of one launch of the dominant kernel: the encode-side block
+    # kernels read the raster once (count pass) or read it and write the blob (write pass); decode reads the
+    # blob and writes the raster
+    algo = {"count": raw_bytes, "write": raw_bytes + blob_bytes, "decode": raw_bytes + blob_bytes}
+    if "k_tiles_decode" in top_name or "decode" in top_name:
+        algo_bytes, which = algo["decode"], "blob read + raster write"
+    elif "true" in top_name:
+        algo_bytes, which = algo["write"], "raster read + blob write"
+    else:
+        algo_bytes, which = algo["count"], "raster read"
+    achieved = algo_bytes / (per_launch_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": top_name, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes, "algorithmic_bytes_are": which,
+                "kernel_ms_per_launch": per_launch_ms, "kernel_share_of_step": top_ms / total_k,
+                "step_roofline_frac": (2 * (raw_bytes + blob_bytes)) / (ms_per_step * 1e-3) / 1e9 / peak_gbs,
+                "kernels": {n: {"launches_per_step": c / PROF, "ms_per_step": m / PROF} for n, (c, m) in sorted(kt.items(), key=lambda kv: -kv[1][1])[:8]}}
+
+    # ---- end to end: pinned host buffers through the same C ABI ----------------------------------------
+    lerc_b200.set_stream(0, False)
+    h_in = [torch.from_numpy(h).pin_memory() for h in host_imgs[:2]]
+    h_blob = torch.empty(cap, dtype=torch.uint8).pin_memory()
+    h_out = torch.empty_like(h_in[0]).pin_memory()
+
+    def step_host(i):
+        src = h_in[i % 2]
+        st = enc(src.data_ptr(), dt, depth, cols, rows, 1, 0, None, mz, h_blob.data_ptr(), cap, C.addressof(n_written))
+        assert st == 0
+        st = dec(h_blob.data_ptr(), n_written.value, 0, None, depth, cols, rows, 1, dt, h_out.data_ptr())
+        assert st == 0
+        return n_written.value
+
+    for i in range(warm):
+        step_host(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    E2E = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for i in range(E2E):
+        nb = step_host(i)
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / E2E
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e = {"value": world * n_px / float(t.item()) / 1e9, "unit": "Gpixels/s", "ms_per_step": float(t.item()) * 1e3,
+           "h2d_bytes_per_step": raw_bytes + nb, "d2h_bytes_per_step": cap + raw_bytes, "timer": "host wall clock around the synchronous C-API calls"}
+    assert np.abs(h_out.numpy().astype(np.float64) - h_in[(E2E - 1) % 2].numpy().astype(np.float64)).max() <= max(mz, 0.5 if dt < 6 else 0) * 1.1 + 1e-12
+
+    if rank == 0:
+        cpu = None
+        if world >= 1 and not args.no_cpu_baseline and args.gpus == 1:
+            cpu, _ = cpu_reference_run(args.workload, seconds_budget=15.0)
+        line = {"metric": "Gpixels/s encode+decode float32 @ maxZError=0.01; achieved HBM GB/s vs peak" if args.workload == "c2" else "Gpixels/s encode+decode",
+                "value": value, "unit": "Gpixels/s", "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms_per_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64" if dt >= 6 else "int32", "data": "synthetic",
+                "config": {"workload": desc, "generator": "tests/cases.py", "blob_bytes": blob_bytes, "compression_ratio": raw_bytes / blob_bytes,
+                           "l2": f"{NBUF} rotating raster/blob/output sets ({NBUF * (2 * raw_bytes + blob_bytes) // 2**20} MiB touched between reuses) > 126 MB L2",
+                           "sharding": "one independent raster per rank, no data-path collective" if world > 1 else "single GPU"},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -30,6 +30,11 @@ LERC_B200_API void lerc_b200_set_stream(void* cudaStream, int enable);
  * out[3] = encodes that took the fused all-valid fast path, out[4] = decodes that did. */
 LERC_B200_API void lerc_b200_get_stats(unsigned long long* out, int n);
 
+/* Per-kernel timing: while enabled, every kernel launch of this library is bracketed by a CUDA event pair on
+ * its stream.  lerc_b200_get_profile() writes lines "name<TAB>launches<TAB>total_ms" into buf. */
+LERC_B200_API void lerc_b200_profile(int enable);
+LERC_B200_API void lerc_b200_get_profile(char* buf, int bufLen, int reset);
+
 LERC_B200_API const char* lerc_b200_version(void);
 
 #ifdef __cplusplus

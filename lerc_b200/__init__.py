@@ -16,7 +16,7 @@ REQUIRED_SYMBOLS = [
     "lerc_computeCompressedSize", "lerc_encode", "lerc_computeCompressedSizeForVersion", "lerc_encodeForVersion",
     "lerc_getBlobInfo", "lerc_getDataRanges", "lerc_decode", "lerc_decodeToDouble",
     "lerc_computeCompressedSize_4D", "lerc_encode_4D", "lerc_decode_4D", "lerc_decodeToDouble_4D",
-    "lerc_b200_set_stream", "lerc_b200_get_stats", "lerc_b200_version",
+    "lerc_b200_set_stream", "lerc_b200_get_stats", "lerc_b200_version", "lerc_b200_profile", "lerc_b200_get_profile",
 ]
 
 
@@ -46,3 +46,19 @@ def set_stream(cuda_stream_ptr, enable=True):
     """Route this thread's lerc_* calls onto the given cudaStream_t (integer handle, e.g.
     torch.cuda.current_stream().cuda_stream)."""
     _lib.lerc_b200_set_stream(ctypes.c_void_p(cuda_stream_ptr), 1 if enable else 0)
+
+
+def profile(enable=True):
+    """Bracket every kernel launch with CUDA events (see kernel_times())."""
+    _lib.lerc_b200_profile(1 if enable else 0)
+
+
+def kernel_times(reset=True):
+    """{kernel name: (launches, total milliseconds)} accumulated while profile(True) was on."""
+    buf = ctypes.create_string_buffer(1 << 16)
+    _lib.lerc_b200_get_profile(buf, len(buf), 1 if reset else 0)
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, cnt, ms = line.split("\t")
+        out[name] = (int(cnt), float(ms))
+    return out

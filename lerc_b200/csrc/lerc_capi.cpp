@@ -318,6 +318,9 @@ void lerc_b200_get_stats(unsigned long long* out, int n) {
   for (int i = 0; i < n; i++) out[i] = i < 5 ? v[i] : 0;
 }
 
+void lerc_b200_profile(int enable) { gProfileEnabled = enable != 0; }
+void lerc_b200_get_profile(char* buf, int bufLen, int reset) { profileReport(buf, bufLen, reset != 0); }
+
 const char* lerc_b200_version(void) { return "lerc_b200 0.1 (Lerc2 v6 writer, v3-v6 reader; CUDA sm_100a)"; }
 
 }  // extern "C"

@@ -5,6 +5,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <mutex>
+#include <map>
+#include <string>
+#include <cstring>
 
 namespace lerc {
 
@@ -57,6 +60,22 @@ bool gNoDevice = false;
 
 Stats& globalStats() { return gStats; }
 
+bool gProfileEnabled = false;
+namespace { std::map<std::string, std::pair<double, unsigned long long>> gProfile; }
+
+cudaEvent_t Context::takeEvent() {
+  if (!eventPool.empty()) { cudaEvent_t e = eventPool.back(); eventPool.pop_back(); return e; }
+  cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+
+void profileReport(char* buf, int bufLen, bool reset) {
+  std::lock_guard<std::mutex> lock(gMutex);
+  std::string out;
+  for (auto& kv : gProfile) { char line[256]; std::snprintf(line, sizeof line, "%s\t%llu\t%.6f\n", kv.first.c_str(), kv.second.second, kv.second.first); out += line; }
+  if (buf && bufLen > 0) { std::strncpy(buf, out.c_str(), (size_t)bufLen - 1); buf[bufLen - 1] = 0; }
+  if (reset) gProfile.clear();
+}
+
 Context* acquireContext() {
   {
     std::lock_guard<std::mutex> lock(gMutex);
@@ -93,6 +112,15 @@ void releaseContext(Context* c) {
   c->arena.reset();
   c->pinnedUsed = 0;
   std::lock_guard<std::mutex> lock(gMutex);
+  if (!c->profRecs.empty()) {
+    cudaEventSynchronize(c->profRecs.back().b);
+    for (auto& r : c->profRecs) {
+      float ms = 0; cudaEventElapsedTime(&ms, r.a, r.b);
+      auto& slot = gProfile[r.name]; slot.first += ms; slot.second += 1;
+      c->eventPool.push_back(r.a); c->eventPool.push_back(r.b);
+    }
+    c->profRecs.clear();
+  }
   gStats.kernelLaunches += c->kernelLaunches;
   c->kernelLaunches = 0;
   gFree.push_back(c);

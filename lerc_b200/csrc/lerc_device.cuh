@@ -8,7 +8,8 @@
 namespace lerc {
 
 #define LERC_LAUNCH(ctx, kernel, grid, block, smem, ...)                                   \
-  do { kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__); (ctx)->kernelLaunches++; } while (0)
+  do { LaunchScope scope_((ctx), #kernel);                                                  \
+       kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__); (ctx)->kernelLaunches++; } while (0)
 
 constexpr unsigned FULL = 0xffffffffu;
 

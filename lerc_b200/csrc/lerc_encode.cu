@@ -21,6 +21,7 @@ namespace lerc {
 // prefix sums (CUB; plumbing, not a hot kernel)
 
 void exclusiveScanU32(Context* ctx, const uint32_t* dIn, uint32_t* dOut, size_t n) {
+  LaunchScope scope(ctx, "cub::ExclusiveSum<u32>");
   size_t tmpBytes = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, dIn, dOut, (int)(n + 1), ctx->stream);
   void* tmp = ctx->arena.alloc(tmpBytes ? tmpBytes : 16);
@@ -28,6 +29,7 @@ void exclusiveScanU32(Context* ctx, const uint32_t* dIn, uint32_t* dOut, size_t 
   ctx->kernelLaunches += 2;
 }
 void exclusiveScanU64(Context* ctx, const unsigned long long* dIn, unsigned long long* dOut, size_t n) {
+  LaunchScope scope(ctx, "cub::ExclusiveSum<u64>");
   size_t tmpBytes = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, dIn, dOut, (int)(n + 1), ctx->stream);
   void* tmp = ctx->arena.alloc(tmpBytes ? tmpBytes : 16);

@@ -90,7 +90,21 @@ struct Context {
   uint64_t kernelLaunches = 0; // counted for lerc_b200_stats()
   void* pinnedAlloc(size_t bytes);   // returns a region of `pinned` (bump, reset per call)
   size_t pinnedUsed = 0;
+  // optional per-kernel timing (lerc_b200_profile): event pairs recorded around every launch
+  struct ProfRec { const char* name; cudaEvent_t a, b; };
+  std::vector<ProfRec> profRecs;
+  std::vector<cudaEvent_t> eventPool;
+  cudaEvent_t takeEvent();
 };
+
+extern bool gProfileEnabled;
+// RAII: records an event pair around the launches issued while it is alive (only when profiling is on)
+struct LaunchScope {
+  Context* ctx; cudaEvent_t a = nullptr; const char* name;
+  LaunchScope(Context* c, const char* n) : ctx(c), name(n) { if (gProfileEnabled) { a = ctx->takeEvent(); cudaEventRecord(a, ctx->stream); } }
+  ~LaunchScope() { if (a) { cudaEvent_t b = ctx->takeEvent(); cudaEventRecord(b, ctx->stream); ctx->profRecs.push_back({name, a, b}); } }
+};
+void profileReport(char* buf, int bufLen, bool reset);
 
 Context* acquireContext();            // thread-safe; creates stream/arena on first use; nullptr if no CUDA device
 void releaseContext(Context* ctx);
