@@ -316,9 +316,52 @@ __global__ void k_huffman_decode_seq(HuffDecArgs a) {
   if (!ok) atomicOr(a.status, DECF_BAD_STREAM);
 }
 
+}  // namespace lerc
+#include "lerc_decode_fast.cuh"
+namespace lerc {
+
 // =================================================================================================
 // band orchestration (host)
 namespace {
+
+int smCount() {
+  static int n = 0;
+  if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 1; }
+  return n;
+}
+
+// Launches the single-kernel decoder (lerc_decode_fast.cuh) on the micro-block stream.  Returns false when the
+// stream's shape is outside what it handles (nothing launched).
+template <class T>
+bool launchDecodeFast(Context* ctx, const HeaderInfo& hd, const uint8_t* dStream, size_t streamLen, void* dData, int* dStatus) {
+  if (hd.nDepth != 1 || hd.microBlockSize != 8 || hd.version < 3 || (long long)hd.numValidPixel != (long long)hd.nCols * hd.nRows) return false;
+  if (streamLen == 0 || streamLen >= 0xfff00000ull || std::getenv("LERC_B200_NO_FAST")) return false;
+  const int nSub = (int)((streamLen + FD_SUB - 1) / FD_SUB);
+  const int subPerReg = (nSub + smCount() - 1) / smCount();
+  const int nReg = (nSub + subPerReg - 1) / subPerReg;
+  const size_t smem = fastDecodeSmemBytes<T>(subPerReg, nReg);
+  if (smem + 1024 > 227 * 1024) return false;
+  uint8_t* scratch = (uint8_t*)ctx->arena.alloc((size_t)nReg * FD_ENT * sizeof(FdEntry) + (size_t)nReg * 4 + 16);
+  if (!scratch) return false;
+  FastDecArgs fa;
+  fa.stream = dStream; fa.streamLen = streamLen;
+  fa.nRows = hd.nRows; fa.nCols = hd.nCols; fa.nTx = (hd.nCols + 7) / 8; fa.nTy = (hd.nRows + 7) / 8; fa.dt = hd.dt; fa.version = hd.version;
+  fa.invScale = 2 * hd.maxZError; fa.zMax = hd.zMax; fa.data = dData;
+  fa.nSub = nSub; fa.subPerReg = subPerReg; fa.nReg = nReg; fa.maxU = 1 + 64 * (int)sizeof(T);
+  fa.barrier = (unsigned int*)scratch; fa.regN = (int*)(scratch + 16); fa.regTab = (FdEntry*)(scratch + 16 + (size_t)nReg * 4);
+  fa.status = dStatus;
+  cudaMemsetAsync(scratch, 0, 16, ctx->stream);
+  static size_t attrSmem = 0;
+  if (smem > attrSmem) {
+    if (!cudaOk(cudaFuncSetAttribute(k_decode_fused<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attribute")) return false;
+    attrSmem = smem;
+  }
+  void* params[] = {&fa};
+  LaunchScope scope(ctx, "k_decode_fused<T>");
+  if (!cudaOk(cudaLaunchCooperativeKernel((const void*)k_decode_fused<T>, dim3(nReg), dim3(FD_WARPS * 32), params, smem, ctx->stream), "launch k_decode_fused")) return false;
+  ctx->kernelLaunches++;
+  return true;
+}
 
 template <class T>
 ErrCode decodeBandT(Context* ctx, DecodeBandArgs& a, BandMaskState& ms) {
@@ -362,7 +405,12 @@ ErrCode decodeBandT(Context* ctx, DecodeBandArgs& a, BandMaskState& ms) {
   const bool rleUsed = nm > 0;
   if (a.dValidBytes) launchBitsToBytes(ctx, ms.dBits, nPix, a.dValidBytes);           // Lerc.cpp:481, :979-995
 
-  cudaMemsetAsync(a.dData, 0, (size_t)nPix * nDepth * sizeof(T), st);                 // Lerc2.cpp:609
+  // Lerc2.cpp:609 zero-fills the output; when every pixel is valid and coded by the micro-block stream each one is
+  // overwritten, so the fill is deferred until the fused decoder is known not to apply.
+  const bool mayFast = nDepth == 1 && hd.numValidPixel == nPix && hd.microBlockSize == 8 && hd.version >= 3 && hd.zMin != hd.zMax;
+  bool zeroFilled = false;
+  auto zeroFill = [&]() { if (!zeroFilled) { cudaMemsetAsync(a.dData, 0, (size_t)nPix * nDepth * sizeof(T), st); zeroFilled = true; } };
+  if (!mayFast) zeroFill();
 
   auto finish = [&]() -> ErrCode {
     int hStatus[2] = {0, 1};
@@ -404,6 +452,7 @@ ErrCode decodeBandT(Context* ctx, DecodeBandArgs& a, BandMaskState& ms) {
   if (!src.fetch(pos, std::min<size_t>(2, (size_t)hd.blobSize - pos), flags)) return Failed;
   pos += 1;
   if (flags[0]) {                                                                       // one sweep
+    zeroFill();
     const size_t len = (size_t)nDepth * sizeof(T);
     // numValidPixel of the header is trusted here only after comparing with the mask popcount on the device path below
     if (hd.numValidPixel == nPix) {
@@ -430,6 +479,7 @@ ErrCode decodeBandT(Context* ctx, DecodeBandArgs& a, BandMaskState& ms) {
     pos += 1;
     if (mode > 3 || (mode > 2 && hd.version < 6) || (mode > 1 && hd.version < 4)) return Failed;
     if (mode != IEM_Tiling) {
+      zeroFill();
       if constexpr (sizeof(T) == 1) {
         if (!(hd.tryHuffmanInt() && (mode == IEM_DeltaHuffman || (hd.version >= 4 && mode == IEM_Huffman)))) return Failed;
         std::vector<uint8_t> tb(std::min<size_t>(2048, (size_t)hd.blobSize - pos));
@@ -449,7 +499,15 @@ ErrCode decodeBandT(Context* ctx, DecodeBandArgs& a, BandMaskState& ms) {
       } else return Failed;                      // FPL lossless-float blobs (mode 3): not implemented (DESIGN.md "Deviations")
     }
   }
-  // micro-block stream
+  // micro-block stream: single-kernel speculative decoder first (lerc_decode_fast.cuh)
+  if (mayFast && launchDecodeFast<T>(ctx, hd, blob + pos, (size_t)hd.blobSize - pos, a.dData, dStatus)) {
+    int hs = 0;
+    if (!cudaOk(cudaMemcpyAsync(&hs, dStatus, 4, cudaMemcpyDeviceToHost, st), "D2H") || !cudaOk(cudaStreamSynchronize(st), "sync")) return Failed;
+    if (!(hs & DECF_FALLBACK)) { if (hs == 0) globalStats().fastPathDecodes++; return hs == 0 ? Ok : Failed; }
+    if (hs & ~DECF_FALLBACK) return Failed;                     // e.g. checksum mismatch
+    cudaMemsetAsync(dStatus, 0, 4, st);
+  }
+  zeroFill();
   DecTileArgs ta; std::memset(&ta, 0, sizeof ta);
   ta.stream = blob + pos; ta.streamLen = (unsigned long long)((size_t)hd.blobSize - pos);
   ta.bits = ms.dBits; ta.nRows = hd.nRows; ta.nCols = hd.nCols; ta.nDepth = nDepth; ta.mb = hd.microBlockSize;

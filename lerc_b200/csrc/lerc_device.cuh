@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cfloat>
 #include <climits>
+#include <cstring>
 
 namespace lerc {
 
@@ -58,6 +59,17 @@ template <> __device__ __forceinline__ double   fromKey<double>(unsigned long lo
   return __longlong_as_double((long long)((k >> 63) ? (k & 0x7fffffffffffffffull) : ~k));
 }
 
+// host-side inverse of toKey (same formulas)
+template <class T> inline T fromKeyHost(typename PixelTraits<T>::Key k);
+template <> inline int8_t   fromKeyHost<int8_t>(uint32_t k)   { return (int8_t)(int32_t)(k ^ 0x80000000u); }
+template <> inline int16_t  fromKeyHost<int16_t>(uint32_t k)  { return (int16_t)(int32_t)(k ^ 0x80000000u); }
+template <> inline int32_t  fromKeyHost<int32_t>(uint32_t k)  { return (int32_t)(k ^ 0x80000000u); }
+template <> inline uint8_t  fromKeyHost<uint8_t>(uint32_t k)  { return (uint8_t)k; }
+template <> inline uint16_t fromKeyHost<uint16_t>(uint32_t k) { return (uint16_t)k; }
+template <> inline uint32_t fromKeyHost<uint32_t>(uint32_t k) { return k; }
+template <> inline float    fromKeyHost<float>(uint32_t k)    { uint32_t b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k; float f; memcpy(&f, &b, 4); return f; }
+template <> inline double   fromKeyHost<double>(unsigned long long k) { unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k; double d; memcpy(&d, &b, 8); return d; }
+
 template <class T> __device__ __forceinline__ bool isNaNVal(T) { return false; }
 template <> __device__ __forceinline__ bool isNaNVal<float>(float v) { return v != v; }
 template <> __device__ __forceinline__ bool isNaNVal<double>(double v) { return v != v; }
@@ -75,6 +87,11 @@ __device__ __forceinline__ uint32_t packedBytes(uint32_t n, int nb) { return (ui
 __device__ __forceinline__ double blockMaxVal(double zMin, double zMax, double maxZErr) {     // Lerc2.h:337-341
   double fac = __ddiv_rn(1.0, __dmul_rn(2.0, maxZErr));
   return __dmul_rn(__dsub_rn(zMax, zMin), fac);
+}
+// (unsigned int)(v + 0.5) as the reference's x86-64 build evaluates it (cvttsd2si to 64 bits, low word): NaN -> 0
+__device__ __forceinline__ uint32_t roundToUInt(double v) {
+  const double t = __dadd_rn(v, 0.5);
+  return t == t ? (uint32_t)t : 0u;
 }
 __device__ __forceinline__ uint32_t quantizeOne(double x, double zMin, double scale) {       // Lerc2.h:369-373
   return (uint32_t)__dadd_rn(__dmul_rn(__dsub_rn(x, zMin), scale), 0.5);

@@ -262,7 +262,7 @@ __device__ inline BlockChoice sizeBlock(const TileArgs& a, int n, double zMin, d
   if ((a.maxZErr == 0 && zMax > zMin) || (a.maxZErr > 0 && (mv = blockMaxVal(zMin, zMax, a.maxZErr)) > (double)a.maxQ)) { c.nBytes = raw; return c; }
   c.tc = reduceOffsetType(zMin, dtZ, c.dtUsed);
   int nBytes = 1 + dtSize(c.dtUsed);
-  c.maxElem = (uint32_t)__dadd_rn(mv, 0.5);
+  c.maxElem = roundToUInt(mv);
   bool useLut = false;
   if (c.maxElem > 0) {
     c.nb = bitLength(c.maxElem);
@@ -286,7 +286,7 @@ __device__ inline BlockChoice sizeBlock(const TileArgs& a, int n, double zMin, d
 __device__ inline bool needQuantize(const TileArgs& a, int n, double zMin, double zMax) {     // Lerc2.h:345-353
   if (n == 0 || a.maxZErr == 0) return false;
   const double mv = blockMaxVal(zMin, zMax, a.maxZErr);
-  return !(mv > (double)a.maxQ || (uint32_t)__dadd_rn(mv, 0.5) == 0);
+  return !(mv > (double)a.maxQ || roundToUInt(mv) == 0);
 }
 
 // Lerc2.cpp:1949-2021.  Returns the number of bytes emitted (== choice.nBytes).
@@ -589,10 +589,129 @@ __global__ void k_one_sweep_gather(const T* __restrict__ data, const uint8_t* __
   }
 }
 
+}  // namespace lerc
+#include "lerc_encode_fast.cuh"
+namespace lerc {
+
 // =================================================================================================
 // band orchestration (host)
 
 namespace {
+
+template <class V> bool d2h(Context* ctx, V* hostDst, const void* dSrc, size_t count);
+
+// Single-pass encoder (lerc_encode_fast.cuh).  Returns true when the band was written (or a definite error is
+// in `err`); false when one of its assumptions did not hold and the general encoder must run instead.
+template <class T>
+bool encodeBandFast(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t& bandBytes, ErrCode& err) {
+  constexpr bool isFlt = PixelTraits<T>::isFloat;
+  using K = typename PixelTraits<T>::Key;
+  if (sizeof(T) == 1 || a.nDepth != 1 || a.dValidBytes || a.anyMaskModified || !a.dOut) return false;
+  if (std::getenv("LERC_B200_NO_FAST")) return false;
+  double maxZErr = a.maxZErr;
+  if (isFlt) { if (!(maxZErr > 0)) return false; }                    // float lossless: FPL / raw decisions stay in the general path
+  else maxZErr = std::max(0.5, std::floor(maxZErr));                   // Lerc2.cpp:219
+  const long long nPix = (long long)a.nCols * a.nRows;
+  const size_t nBits = (size_t)((nPix + 7) >> 3);
+  cudaStream_t st = ctx->stream;
+  const int nTx = (a.nCols + 7) / 8, nTy = (a.nRows + 7) / 8;
+  const long long nBlocks = (long long)nTx * nTy;
+  constexpr int TB = FAST_TB;
+  const long long nTiles = (nBlocks + TB - 1) / TB;
+  if (nTiles > 0x7fffffffLL) return false;
+  const size_t dataStart = (size_t)headerBytes(6) + 4 + 2 * sizeof(T) + 1;
+  if (a.outCapacity < dataStart + 1) return false;                     // let the general path report BufferTooSmall exactly
+
+  const size_t stateBytes = sizeof(FastEncResult) + 9 * 8 + (size_t)nTiles * 8;
+  uint8_t* dState = (uint8_t*)ctx->arena.alloc(stateBytes);
+  struct HostRes { FastEncResult r; unsigned long long raise[9]; };
+  HostRes* hRes = (HostRes*)ctx->pinnedAlloc(sizeof(HostRes));
+  if (!dState || !hRes) return false;
+  FastEncResult* dRes = (FastEncResult*)dState;
+  unsigned long long* dRaise = (unsigned long long*)(dState + sizeof(FastEncResult));
+  cudaMemsetAsync(dState, 0, stateBytes, st);
+
+  // float data already on a coarser decimal grid (Lerc2.cpp:226-231, :1233-1339): test the first row only; if a
+  // candidate survives it the general path does the full scan
+  RaiseArgs ra; ra.n = 0;
+  if (isFlt) {
+    static const double kErr[9] = {1, 0.5, 0.1, 0.05, 0.01, 0.005, 0.001, 0.0005, 0.0001};
+    static const double kFac[9] = {1, 2, 10, 20, 100, 200, 1000, 2000, 10000};
+    for (int i = 0; i < 9; i++) if (kErr[i] / 2 > maxZErr) { ra.fac[ra.n] = kFac[i]; ra.n++; }
+    if (ra.n > 0) {
+      int grid = (int)std::min<long long>((a.nCols + 255) / 256, 148);
+      LERC_LAUNCH(ctx, k_try_raise<T>, grid, 256, 0, (const T*)a.dData, (const uint8_t*)nullptr, 0LL, (long long)a.nCols, 1, ra, dRaise);
+    }
+  }
+
+  FastEncArgs fa;
+  fa.data = a.dData; fa.nRows = a.nRows; fa.nCols = a.nCols; fa.nTx = nTx; fa.nTy = nTy; fa.dt = PixelTraits<T>::code;
+  fa.maxZErr = maxZErr; fa.scale = 1.0 / (2.0 * maxZErr); fa.maxQ = fa.dt <= DT_UShort ? (1u << 15) - 1 : (1u << 30) - 1;         // Lerc2.h:685-703
+  fa.intLossless = (!isFlt && maxZErr == 0.5) ? 1 : 0;
+  uint8_t* blob = a.dOut + a.outOffset;
+  fa.stream = blob + dataStart; fa.streamCap = a.outCapacity - dataStart; fa.regionOff = (long long)dataStart - 14;
+  fa.tileState = (unsigned long long*)(dState + sizeof(FastEncResult) + 9 * 8); fa.res = dRes;
+  constexpr int MAXB = 1 + 64 * (int)sizeof(T);
+  const size_t smem = (size_t)((TB * MAXB + 15) / 16 + 3) * 16;
+  static bool attrSet = false;
+  if (!attrSet) { cudaFuncSetAttribute(k_encode_fused<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attrSet = true; }
+  LERC_LAUNCH(ctx, k_encode_fused<T>, (unsigned)nTiles, 256, smem, fa);
+  if (!cudaOk(cudaMemcpyAsync(hRes, dState, sizeof(HostRes), cudaMemcpyDeviceToHost, st), "D2H fast result")) { err = Failed; return true; }
+  if (!cudaOk(cudaStreamSynchronize(st), "sync")) { err = Failed; return true; }
+
+  // ---- were the assumptions right?
+  const FastEncResult& r = hRes->r;
+  if (r.flags & (FASTF_NAN | FASTF_LUT)) return false;
+  const K minKey = (K)~r.negMinKey, maxKey = (K)r.maxKey;
+  const T lo = fromKeyHost<T>(minKey), hi = fromKeyHost<T>(maxKey);
+  const double zMin = (double)lo, zMax = (double)hi;
+  if (zMin == zMax) return false;                                        // constant image: no stream at all
+  HeaderInfo hd;
+  if (isFlt) {
+    if ((lo == (T)0 && std::signbit(lo)) || (hi == (T)0 && !std::signbit(hi))) return false;   // sign of a zero extreme depends on scan order (general path)
+    bool allInt = !(r.flags & FASTF_NOT_INT);
+    const double lim = sizeof(T) == 4 ? 8388608.0 : 9007199254740992.0;
+    allInt = allInt && zMin >= -lim && zMin <= lim && zMax >= -lim && zMax <= lim;             // Lerc.cpp:1490-1500
+    if (allInt) { if (std::max(0.5, std::floor(maxZErr)) != maxZErr) return false; hd.bIsInt = 1; }
+    for (int c = 0; c < ra.n; c++) {                                      // PruneCandidates on row 0 (Lerc2.cpp:1322-1339)
+      double m; std::memcpy(&m, &hRes->raise[c], 8);
+      if (!(m / ra.fac[c] > maxZErr / 2)) return false;                   // a candidate survived: full scan needed
+    }
+  }
+  const unsigned long long nData = r.totalBytes;
+  const size_t oneSweepBytes = sizeof(T) * (size_t)nPix;
+  if ((double)nData * 8 < (double)nPix * 1.5 && nData < 4 * oneSweepBytes && (a.nRows > 8 || a.nCols > 8)) return false;   // 16x16 retry (Lerc2.cpp:333-357)
+  if (oneSweepBytes <= nData) return false;                              // one sweep raw wins (Lerc2.cpp:364-373)
+  const unsigned long long total = dataStart + nData;
+  if (total > (unsigned long long)INT_MAX) { err = Failed; return true; }
+  bandBytes = (uint32_t)total;
+  if (total > a.outCapacity || (r.flags & FASTF_OVERFLOW)) { err = BufferTooSmall; return true; }   // Lerc.cpp:764-765
+
+  // ---- header, mask length, ranges, flag byte; checksum from the kernel's partial sums (Lerc2.cpp:1012-1064)
+  hd.version = 6; hd.nRows = a.nRows; hd.nCols = a.nCols; hd.nDepth = 1; hd.dt = PixelTraits<T>::code;
+  hd.nBlobsMore = a.nBands - 1 - a.iBand; hd.numValidPixel = (int)nPix; hd.microBlockSize = 8;
+  hd.blobSize = (int)total; hd.maxZError = maxZErr; hd.zMin = zMin; hd.zMax = zMax;
+  PrefixBytes pb; std::memset(&pb, 0, sizeof pb);
+  writeHeader(pb.b, hd);
+  size_t p = (size_t)headerBytes(6) + 4;                                  // mask byte count 0
+  std::memcpy(pb.b + p, &lo, sizeof(T)); p += sizeof(T);
+  std::memcpy(pb.b + p, &hi, sizeof(T)); p += sizeof(T);
+  pb.b[p++] = 0;                                                          // not one sweep
+  pb.n = (int)p;
+  unsigned long long A = 0, D = 0;
+  for (int i = 0; i < FAST_SLOTS; i++) { A += r.fletA[i]; D = (D + r.fletD[i]) % 65535ull; }
+  fletcherHostPartial(pb.b + 14, 0, (long long)p - 14, A, D);
+  hd.checksum = fletcherFinish(A, D, (long long)total - 14);
+  std::memcpy(pb.b + 10, &hd.checksum, 4);
+  LERC_LAUNCH(ctx, k_write_prefix, 1, 128, 0, blob, pb);
+
+  // validity bookkeeping the band loop expects (Lerc.cpp:659-741): this band is all valid
+  ms.numValid = (int)nPix;
+  if (a.nBands > 1 && a.iBand < a.nBands - 1) { cudaMemsetAsync(ms.dPrevBits, 0xff, nBits, st); ms.havePrev = true; }
+  globalStats().fastPathEncodes++;
+  err = cudaOk(cudaGetLastError(), "encodeBandFast") ? Ok : Failed;
+  return true;
+}
 
 template <class V> bool d2h(Context* ctx, V* hostDst, const void* dSrc, size_t count) {
   if (!cudaOk(cudaMemcpyAsync(hostDst, dSrc, count * sizeof(V), cudaMemcpyDeviceToHost, ctx->stream), "D2H")) return false;
@@ -607,6 +726,14 @@ ErrCode encodeBandT(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
   const int nDepth = a.nDepth;
   cudaStream_t st = ctx->stream;
   bandBytes = 0;
+  {
+    ErrCode fe = Ok;
+    const size_t arenaMark = ctx->arena.used, pinnedMark = ctx->pinnedUsed;
+    if (encodeBandFast<T>(ctx, a, ms, bandBytes, fe)) return fe;
+    if (ctx->arena.retired.empty()) ctx->arena.used = arenaMark;
+    ctx->pinnedUsed = pinnedMark;
+    bandBytes = 0;
+  }
 
   HeaderInfo hd;
   hd.version = 6; hd.nRows = a.nRows; hd.nCols = a.nCols; hd.nDepth = nDepth; hd.dt = PixelTraits<T>::code;

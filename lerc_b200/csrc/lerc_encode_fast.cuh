@@ -1,0 +1,425 @@
+// lerc_encode_fast.cuh -- single-pass fused Lerc2 band encoder for the common raster shape:
+// every pixel valid, nDepth == 1, 8x8 micro-blocks, 16/32/64-bit pixel types (included by lerc_encode.cu).
+//
+// One kernel reads the raster ONCE and writes the finished micro-block stream ONCE:
+//   per CTA tile = TILE_BLOCKS consecutive micro-blocks in stream order (Lerc2.cpp:1507-1521)
+//     8 lanes per micro-block, one lane per block row (8 pixels in registers, 128-bit global loads)
+//     block min/max by 3 xor-shuffles in order-preserving key space   (GetValidDataAndStats, Lerc2.cpp:1717-1799)
+//     block coding choice + byte length                               (NumBytesTile, Lerc2.h:416-453)
+//     CTA exclusive scan of the lengths, decoupled look-back across tiles for the global byte offset
+//     fp64 quantisation without contraction                           (Quantize, Lerc2.h:357-376)
+//     each block row packs to w*numBits bits in registers (funnel shifts), OR-ed into a shared-memory staging
+//     image of the tile's output bytes                                (WriteTile Lerc2.cpp:1949-2021, BitStuffer2.cpp:35-75, :432-472)
+//     staging -> HBM with 128-bit stores aligned to the global address, Fletcher-32 partial sums of exactly
+//     those bytes                                                     (Lerc2.cpp:1037-1064)
+//   image-global facts (min/max, NaN, all-integer, LUT candidates) fall out of the same pass.
+// The kernel is speculative about the image-global decisions the reference takes before block coding
+// (Lerc2.cpp:179-381): it assumes "no NaN, maxZError as given, 8x8 tiling wins, no LUT block".  The host checks
+// the facts afterwards and re-runs the general multi-pass encoder (encodeBandT) when any assumption failed, so
+// the bytes are always those of the reference.
+#pragma once
+
+namespace lerc {
+
+enum { FASTF_NAN = 1, FASTF_NOT_INT = 2, FASTF_LUT = 4, FASTF_OVERFLOW = 8 };
+constexpr int FAST_SLOTS = 32;
+
+struct FastEncResult {                 // device, zero-initialised per call
+  unsigned long long totalBytes;       // length of the micro-block stream
+  unsigned long long negMinKey;        // ~min key (so that zero-init works with atomicMax)
+  unsigned long long maxKey;
+  unsigned int flags, ticket;
+  unsigned long long fletA[FAST_SLOTS], fletD[FAST_SLOTS];
+};
+
+struct FastEncArgs {
+  const void* data; int nRows, nCols, nTx, nTy, dt;
+  double maxZErr, scale; uint32_t maxQ;   // scale = 1 / (2 * maxZErr), computed on the host exactly like Lerc2.h:339
+  int intLossless;                     // integer type && maxZErr == 0.5
+  uint8_t* stream;                     // where the micro-block stream starts (blob + dataStart)
+  unsigned long long streamCap;        // bytes available from `stream`
+  long long regionOff;                 // checksum-region offset of stream[0] (= dataStart - 14)
+  unsigned long long* tileState;       // [nTiles], zero-initialised
+  FastEncResult* res;
+};
+
+// ---- helpers -----------------------------------------------------------------------------------
+template <class K> __device__ __forceinline__ K shflXorK(K v, int m);
+template <> __device__ __forceinline__ uint32_t shflXorK<uint32_t>(uint32_t v, int m) { return __shfl_xor_sync(FULL, v, m); }
+template <> __device__ __forceinline__ unsigned long long shflXorK<unsigned long long>(unsigned long long v, int m) { return __shfl_xor_sync(FULL, v, m); }
+
+// OR the bit string R (little-endian words, nbits long) into the zeroed staging words at bit offset bitOff.
+template <int NW>
+__device__ __forceinline__ void orBits(uint32_t* __restrict__ stage, uint32_t bitOff, const uint32_t (&R)[NW], int nbits) {
+  const uint32_t w0 = bitOff >> 5, sh = bitOff & 31;
+  const int nw = (int)((sh + (uint32_t)nbits + 31) >> 5);
+  uint32_t prev = 0;
+#pragma unroll
+  for (int j = 0; j <= NW; j++) {
+    const uint32_t cur = j < NW ? R[j] : 0u;
+    const uint32_t o = __funnelshift_l(prev, cur, sh);
+    if (j < nw && o) atomicOr(&stage[w0 + j], o);
+    prev = cur;
+  }
+}
+
+// 8 values of nb bits (1..30) each -> 256-bit little-endian bit string, value k at bit k*nb (BitStuffer2.cpp:432-472)
+__device__ __forceinline__ void packRow8(const uint32_t (&q)[8], int nb, uint32_t (&R)[8]) {
+  const unsigned long long p0 = q[0] | ((unsigned long long)q[1] << nb), p1 = q[2] | ((unsigned long long)q[3] << nb);
+  const unsigned long long p2 = q[4] | ((unsigned long long)q[5] << nb), p3 = q[6] | ((unsigned long long)q[7] << nb);
+  const int s2 = 2 * nb;                                   // 2..60
+  const unsigned long long h0lo = p0 | (p1 << s2), h0hi = p1 >> (64 - s2);
+  const unsigned long long h1lo = p2 | (p3 << s2), h1hi = p3 >> (64 - s2);
+  const int s4 = 4 * nb;                                   // 4..120
+  unsigned long long r0, r1, r2, r3;
+  if (s4 < 64) { r0 = h0lo | (h1lo << s4); r1 = h1lo >> (64 - s4); r2 = 0; r3 = 0; }
+  else {
+    const int t = s4 - 64;
+    r0 = h0lo; r1 = h0hi | (h1lo << t);
+    r2 = (t ? (h1lo >> (64 - t)) : 0ull) | (h1hi << t);
+    r3 = t ? (h1hi >> (64 - t)) : 0ull;
+  }
+  R[0] = (uint32_t)r0; R[1] = (uint32_t)(r0 >> 32); R[2] = (uint32_t)r1; R[3] = (uint32_t)(r1 >> 32);
+  R[4] = (uint32_t)r2; R[5] = (uint32_t)(r2 >> 32); R[6] = (uint32_t)r3; R[7] = (uint32_t)(r3 >> 32);
+}
+
+// raw bits of w values of T, value k at bit k*8*sizeof(T)
+template <class T>
+__device__ __forceinline__ void rawRowBits(const T (&v)[8], int w, uint32_t (&R)[16]) {
+#pragma unroll
+  for (int j = 0; j < 16; j++) R[j] = 0;
+  if (sizeof(T) == 8) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) if (k < w) { unsigned long long b; memcpy(&b, &v[k], 8); R[2 * k] = (uint32_t)b; R[2 * k + 1] = (uint32_t)(b >> 32); }
+  } else if (sizeof(T) == 4) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) if (k < w) { uint32_t b; memcpy(&b, &v[k], 4); R[k] = b; }
+  } else if (sizeof(T) == 2) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) if (k < w) { uint16_t b; memcpy(&b, &v[k], 2); R[k >> 1] |= (uint32_t)b << (16 * (k & 1)); }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; k++) if (k < w) { uint8_t b; memcpy(&b, &v[k], 1); R[k >> 2] |= (uint32_t)b << (8 * (k & 3)); }
+  }
+}
+
+// 8 pixels of one block row; columns >= w repeat the first pixel (neutral for min/max).
+template <class T>
+__device__ __forceinline__ void loadRow8(const T* __restrict__ p, int w, bool vec, T (&v)[8]) {
+  if (vec) {                                          // w == 8 and 16-byte aligned
+    if (sizeof(T) == 4) {
+      const uint4 a = __ldg((const uint4*)p), b = __ldg((const uint4*)p + 1);
+      const uint32_t u[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int k = 0; k < 8; k++) memcpy(&v[k], &u[k], 4);
+    } else if (sizeof(T) == 2) {
+      const uint4 a = __ldg((const uint4*)p);
+      const uint32_t u[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+      for (int k = 0; k < 8; k++) { const uint16_t h = (uint16_t)(u[k >> 1] >> (16 * (k & 1))); memcpy(&v[k], &h, 2); }
+    } else if (sizeof(T) == 8) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const uint4 a = __ldg((const uint4*)p + k);
+        const unsigned long long lo = a.x | ((unsigned long long)a.y << 32), hi = a.z | ((unsigned long long)a.w << 32);
+        memcpy(&v[2 * k], &lo, 8); memcpy(&v[2 * k + 1], &hi, 8);
+      }
+    } else {
+      const uint2 a = __ldg((const uint2*)p);
+      const uint32_t u[2] = {a.x, a.y};
+#pragma unroll
+      for (int k = 0; k < 8; k++) { const uint8_t h = (uint8_t)(u[k >> 2] >> (8 * (k & 3))); memcpy(&v[k], &h, 1); }
+    }
+  } else {
+    const T first = __ldg(p);
+#pragma unroll
+    for (int k = 0; k < 8; k++) v[k] = k < w ? __ldg(p + k) : first;
+  }
+}
+
+// ---- the kernel --------------------------------------------------------------------------------
+// 256 threads = 8 warps x 4 micro-blocks = 32 blocks per CTA tile; tile index = blockIdx.x (tiles are
+// dispatched in index order, which the look-back relies on, as CUB's single-pass scan does).
+constexpr int FAST_TB = 32;
+
+template <class T>
+__global__ void __launch_bounds__(256) k_encode_fused(FastEncArgs a) {
+  using K = typename PixelTraits<T>::Key;
+  constexpr bool isFlt = PixelTraits<T>::isFloat;
+  constexpr int DT = PixelTraits<T>::code;
+  constexpr int TB = FAST_TB;
+  constexpr int MAXB = 1 + 64 * (int)sizeof(T);                 // longest block: raw (Lerc2.h:427)
+  constexpr int NQ = (TB * MAXB + 15) / 16 + 3;                 // staging uint4s: 16 zero bytes | tile output | zero tail
+  extern __shared__ __align__(16) uint32_t stageRaw[];
+  uint32_t* stage = stageRaw + 4;                               // tile-local byte 0 of the output
+  __shared__ uint32_t sLen[TB];
+  __shared__ unsigned long long sTileOff;
+  __shared__ unsigned long long sKMin[8], sKMax[8], sFA[8], sFD[8];
+  __shared__ unsigned int sFlg[8];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, sb = lane >> 3, r = lane & 7;
+  const unsigned int tile = blockIdx.x;
+  // snapshots of the image-global facts so far (read early, used at the very end to skip useless atomics)
+  const unsigned int flagsSeen = *(volatile unsigned int*)&a.res->flags;
+  const unsigned long long negMinSeen = *(volatile unsigned long long*)&a.res->negMinKey, maxSeen = *(volatile unsigned long long*)&a.res->maxKey;
+  for (int i = tid; i < NQ; i += 256) ((uint4*)stageRaw)[i] = make_uint4(0, 0, 0, 0);
+
+  const int nBlocks = a.nTx * a.nTy;
+  const T* data = (const T*)a.data;
+  const bool vecOk = ((a.nCols * (int)sizeof(T)) % 16 == 0) && (((uintptr_t)data & 15) == 0);
+
+  // ---- load one block row per lane, block statistics (GetValidDataAndStats, Lerc2.cpp:1717-1799)
+  const int b = warp * 4 + sb, blk = (int)tile * TB + b;
+  const bool act = blk < nBlocks;
+  const int ty = act ? blk / a.nTx : 0, tx = act ? blk - ty * a.nTx : 0;
+  const int i0 = ty * 8, j0 = tx * 8;
+  const int h = act ? min(8, a.nRows - i0) : 0, w = min(8, a.nCols - j0), n = h * w;
+  const bool rowAct = r < h;
+  T v[8];
+  K kmin = keyMaxValue<K>(), kmax = 0;
+  int same = 0;
+  unsigned int myFlags = 0;
+  if (rowAct) {
+    loadRow8<T>(data + (size_t)(i0 + r) * a.nCols + j0, w, vecOk && w == 8, v);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const K key = toKey(v[k]);
+      kmin = key < kmin ? key : kmin; kmax = key > kmax ? key : kmax;
+      if (k > 0) same += (k < w && v[k] == v[k - 1]) ? 1 : 0;
+    }
+    if (isFlt && !(flagsSeen & FASTF_NOT_INT)) {                        // all-integer test (Lerc.h:248), until someone found a fraction
+      bool ni = false;
+#pragma unroll
+      for (int k = 0; k < 8; k++) ni |= sizeof(T) == 4 ? ((float)v[k] != truncf((float)v[k])) : ((double)v[k] != trunc((double)v[k]));
+      if (ni) myFlags |= FASTF_NOT_INT;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; k++) v[k] = (T)0;
+  }
+  {  // previous pixel of a row's first pixel: last pixel of the row above; 0 for the block's first pixel (Lerc2.cpp:1729)
+    T last = v[0];
+#pragma unroll
+    for (int k = 1; k < 8; k++) if (k < w) last = v[k];
+    T up;
+    if (sizeof(T) == 8) { unsigned long long bb; memcpy(&bb, &last, 8); bb = __shfl_up_sync(FULL, bb, 1, 8); memcpy(&up, &bb, 8); }
+    else { uint32_t bb = 0; memcpy(&bb, &last, sizeof(T)); bb = __shfl_up_sync(FULL, bb, 1, 8); memcpy(&up, &bb, sizeof(T)); }
+    if (r == 0) up = (T)0;
+    if (rowAct) same += (v[0] == up) ? 1 : 0;
+  }
+#pragma unroll
+  for (int m = 1; m < 8; m <<= 1) {
+    const K omin = shflXorK<K>(kmin, m), omax = shflXorK<K>(kmax, m);
+    kmin = omin < kmin ? omin : kmin; kmax = omax > kmax ? omax : kmax;
+    same += __shfl_xor_sync(FULL, same, m);
+  }
+  const T lo = fromKey<T>(kmin), hi = fromKey<T>(kmax);
+  const double zMin = (double)lo, zMax = (double)hi;
+  if (isFlt && act && (isNaNVal(lo) || isNaNVal(hi))) myFlags |= FASTF_NAN;
+  // LUT coding is a candidate (Lerc2.cpp:1794-1795): not handled here, the host falls back
+  if (act && n > 4 && (zMax > __dadd_rn(zMin, __dmul_rn(3.0, a.maxZErr))) && (2 * same > n)) myFlags |= FASTF_LUT;
+
+  // ---- coding choice + length (NumBytesTile, Lerc2.h:416-453; tryLut == false)
+  int mode = BEM_RAW, nb = 0, tc = 0, dtUsed = DT, nBytes = 0;
+  uint32_t maxElem = 0;
+  if (act) {
+    const int raw = 1 + n * (int)sizeof(T);
+    if (zMin == 0 && zMax == 0) { nBytes = 1; mode = BEM_ZERO; }
+    else {
+      const double mv = __dmul_rn(__dsub_rn(zMax, zMin), a.scale);
+      if (mv > (double)a.maxQ) nBytes = raw;
+      else {
+        tc = reduceOffsetType(zMin, DT, dtUsed);
+        int nbt = 1 + dtSize(dtUsed);
+        maxElem = roundToUInt(mv);
+        if (maxElem > 0) { nb = bitLength(maxElem); nbt += 2 + (int)packedBytes(n, nb); }
+        if (nbt < raw) { mode = BEM_SIMPLE; nBytes = nbt; } else nBytes = raw;
+      }
+    }
+  }
+  if (r == 0) sLen[b] = (uint32_t)nBytes;
+  __syncthreads();                                                      // staging zeroed, block lengths visible
+
+  // ---- tile-local byte offsets: every warp scans the 32 lengths itself
+  uint32_t inc = sLen[lane];
+  {
+    const uint32_t x = inc;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) { const uint32_t o = __shfl_up_sync(FULL, inc, s); if (lane >= s) inc += o; }
+    inc -= x;                                                           // exclusive
+  }
+  const uint32_t tileBytes = __shfl_sync(FULL, inc, 31) + __shfl_sync(FULL, sLen[lane], 31);
+  const uint32_t byte0 = __shfl_sync(FULL, inc, b);
+  constexpr unsigned long long ST_A = 1ull << 62, ST_P = 2ull << 62, VAL = (1ull << 62) - 1;
+  volatile unsigned long long* st = a.tileState;
+  if (tid == 0) st[tile] = (tile == 0 ? ST_P : ST_A) | (unsigned long long)tileBytes;   // publish before packing
+
+  // ---- quantise (Lerc2.h:357-376), pack, OR into the staging image (WriteTile, Lerc2.cpp:1949-2021)
+  if (rowAct) {
+    const uint8_t flag = (uint8_t)((((j0 >> 3) & 15) << 2) & 0x38);     // version 6, no depth delta (Lerc2.cpp:1955-1958)
+    if (mode == BEM_ZERO) { if (r == 0) { const uint32_t H[1] = {(uint32_t)(flag | 2)}; orBits<1>(stage, byte0 * 8, H, 8); } }
+    else if (mode == BEM_RAW) {
+      if (r == 0) { const uint32_t H[1] = {(uint32_t)flag}; orBits<1>(stage, byte0 * 8, H, 8); }
+      uint32_t R[16]; rawRowBits<T>(v, w, R);
+      const uint32_t bitOff = (byte0 + 1 + (uint32_t)(r * w) * (uint32_t)sizeof(T)) * 8;
+      if (sizeof(T) == 8) orBits<16>(stage, bitOff, R, w * 64);
+      else { uint32_t R8[8];
+#pragma unroll
+             for (int j = 0; j < 8; j++) R8[j] = R[j];
+             orBits<8>(stage, bitOff, R8, w * 8 * (int)sizeof(T)); }
+    } else {
+      const int osz = dtSize(dtUsed);
+      if (r == 0) {                                                     // flag | offset | [numBits byte | count]
+        const unsigned long long ob = offsetBits(zMin, dtUsed);
+        unsigned long long lo64 = (unsigned long long)(flag | (maxElem == 0 ? 3 : 1) | (tc << 6)) | (ob << 8);
+        unsigned long long hi64 = osz == 8 ? (ob >> 56) : 0;
+        int nbytes = 1 + osz;                                           // 2, 3, 5 or 9
+        if (maxElem > 0) {
+          const unsigned long long two = (unsigned long long)(nb | (2 << 6)) | ((unsigned long long)n << 8);   // count < 256: one byte, code 2
+          if (nbytes < 8) lo64 |= two << (8 * nbytes); else hi64 |= two << (8 * (nbytes - 8));
+          nbytes += 2;
+        }
+        const uint32_t H[3] = {(uint32_t)lo64, (uint32_t)(lo64 >> 32), (uint32_t)hi64};
+        orBits<3>(stage, byte0 * 8, H, nbytes * 8);
+      }
+      if (maxElem > 0) {
+        uint32_t q[8];
+        bool done = false;
+        if constexpr (!isFlt) {
+          if (a.intLossless) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) q[k] = k < w ? (uint32_t)((long long)v[k] - (long long)lo) : 0u;
+            done = true;
+          }
+        }
+        if (!done) {
+#pragma unroll
+          for (int k = 0; k < 8; k++) q[k] = k < w ? quantizeOne((double)v[k], zMin, a.scale) : 0u;
+        }
+        uint32_t R[8];
+        packRow8(q, nb, R);
+        orBits<8>(stage, (byte0 + (uint32_t)(osz + 3)) * 8 + (uint32_t)(r * w * nb), R, w * nb);
+      }
+    }
+  }
+
+  // ---- image-global facts of this warp
+  {
+    K gMin = act ? kmin : keyMaxValue<K>(), gMax = act ? kmax : (K)0;
+#pragma unroll
+    for (int m = 8; m < 32; m <<= 1) {
+      const K omin = shflXorK<K>(gMin, m), omax = shflXorK<K>(gMax, m);
+      gMin = omin < gMin ? omin : gMin; gMax = omax > gMax ? omax : gMax;
+    }
+    myFlags = __reduce_or_sync(FULL, myFlags);
+    if (lane == 0) { sKMin[warp] = (unsigned long long)gMin; sKMax[warp] = (unsigned long long)gMax; sFlg[warp] = myFlags; }
+  }
+
+  // ---- decoupled look-back (warp 0) for the tile's global byte offset
+  if (warp == 0) {
+    unsigned long long excl = 0;
+    if (tile > 0) {
+      long long base = (long long)tile - 1;
+      for (;;) {
+        const long long idx = base - lane;
+        unsigned long long s = ST_P;                                    // virtual tiles before 0: prefix 0
+        if (idx >= 0) { do { s = st[idx]; } while ((s >> 62) == 0); }
+        const unsigned isP = __ballot_sync(FULL, (s >> 62) == 2);
+        const int firstP = isP ? __ffs(isP) - 1 : 32;
+        unsigned long long contrib = (lane <= firstP && idx >= 0) ? (s & VAL) : 0;
+#pragma unroll
+        for (int m = 16; m; m >>= 1) contrib += __shfl_xor_sync(FULL, contrib, m);
+        excl += contrib;
+        if (isP) break;
+        base -= 32;
+      }
+      if (lane == 0) st[tile] = ST_P | (excl + tileBytes);
+    }
+    if (lane == 0) {
+      sTileOff = excl;
+      if ((long long)(tile + 1) * TB >= nBlocks) a.res->totalBytes = excl + tileBytes;
+    }
+  }
+  __syncthreads();
+
+  // ---- staging -> HBM in 16-byte chunks aligned to the GLOBAL address (the staging image is re-aligned with
+  // funnel shifts), Fletcher-32 partial sums of the same words (bytes outside the tile are zero in the image)
+  const unsigned long long tileOff = sTileOff;
+  unsigned long long fa = 0, fd = 0;
+  if (tileOff + tileBytes <= a.streamCap) {
+    uint8_t* gTile = a.stream + tileOff;
+    const int pad = (int)((uintptr_t)gTile & 15);
+    const int nChunks = (pad + (int)tileBytes + 15) >> 4;
+    const int bs8 = ((-pad) & 3) * 8;
+    for (int cI = tid; cI < nChunks; cI += 256) {
+      const int s0 = cI * 16 - pad;                                     // tile-local byte of the chunk's first byte (>= -15)
+      const int wi = s0 >> 2;                                           // floor
+      uint32_t x[5];
+#pragma unroll
+      for (int k = 0; k < 5; k++) x[k] = stage[wi + k];
+      uint32_t o[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) o[k] = __funnelshift_r(x[k], x[k + 1], bs8);
+      if (s0 >= 0 && s0 + 16 <= (int)tileBytes) *(uint4*)(gTile + s0) = make_uint4(o[0], o[1], o[2], o[3]);
+      else {
+#pragma unroll
+        for (int j = 0; j < 16; j++) if (s0 + j >= 0 && s0 + j < (int)tileBytes) gTile[s0 + j] = (uint8_t)(o[j >> 2] >> (8 * (j & 3)));
+      }
+      // big-endian 16-bit words at even region offsets (Lerc2.cpp:1037-1064)
+      const long long r0 = a.regionOff + (long long)tileOff + s0;
+      const unsigned par = (unsigned)(r0 & 1);
+      const uint32_t w0 = (uint32_t)(((r0 - par) >> 1) % 65535);
+      uint32_t S = 0, S1 = 0, prev = 0;
+#pragma unroll
+      for (int k = 0; k < 5; k++) {
+        const uint32_t cur = k < 4 ? o[k] : 0u;
+        const uint32_t y = __funnelshift_l(prev, cur, par * 8);        // bytes shifted up by one when the chunk starts at an odd offset
+        const uint32_t pw = __byte_perm(y, 0, 0x2301);                  // low half = first BE word, high half = second
+        const uint32_t wlo = pw & 0xffffu, whi = pw >> 16;
+        S += wlo + whi; S1 += (uint32_t)(2 * k) * (wlo + whi) + whi;
+        prev = cur;
+      }
+      fa += S; fd += (unsigned long long)w0 * S + S1;
+    }
+  } else if (tid == 0) atomicOr(&a.res->flags, FASTF_OVERFLOW);
+  fa %= 65535ull; fd %= 65535ull;
+#pragma unroll
+  for (int m = 16; m; m >>= 1) { fa += __shfl_xor_sync(FULL, fa, m); fd += __shfl_xor_sync(FULL, fd, m); }
+  if (lane == 0) { sFA[warp] = fa; sFD[warp] = fd; }
+  __syncthreads();
+  if (tid == 0) {
+    unsigned long long A = 0, D = 0, kMin = ~0ull, kMax = 0; unsigned int fl = 0;
+    for (int i = 0; i < 8; i++) { A += sFA[i]; D += sFD[i]; kMin = sKMin[i] < kMin ? sKMin[i] : kMin; kMax = sKMax[i] > kMax ? sKMax[i] : kMax; fl |= sFlg[i]; }
+    if (A | D) { atomicAdd(&a.res->fletA[tile % FAST_SLOTS], A); atomicAdd(&a.res->fletD[tile % FAST_SLOTS], D % 65535ull); }
+    if (kMax >= kMin) {
+      if (~kMin > negMinSeen) atomicMax(&a.res->negMinKey, ~kMin);
+      if (kMax > maxSeen) atomicMax(&a.res->maxKey, kMax);
+    }
+    if (fl & ~flagsSeen) atomicOr(&a.res->flags, fl);
+  }
+}
+
+// small blob prefix (header, mask length, ranges, flag bytes) written from kernel parameters
+struct PrefixBytes { uint8_t b[128]; int n; };
+__global__ void k_write_prefix(uint8_t* dst, PrefixBytes p) { if ((int)threadIdx.x < p.n) dst[threadIdx.x] = p.b[threadIdx.x]; }
+
+// Fletcher-32 from the partial sums A = SUM c, D = SUM (wordIndex mod 65535) * c over the checksum region of
+// length len (see k_fletcher_partial in lerc_mask.cu for the derivation).
+inline uint32_t fletcherFinish(unsigned long long A, unsigned long long D, long long len) {
+  const unsigned long long M = 65535ull, m = (unsigned long long)((len + 1) >> 1);
+  A %= M; D %= M;
+  unsigned long long s1 = (0xffffull + A) % M;
+  unsigned long long s2 = ((0xffffull % M) * ((m + 1) % M) + (m % M) * A + (M - D)) % M;
+  if (s1 == 0) s1 = M;
+  if (s2 == 0) s2 = M;
+  return (uint32_t)((s2 << 16) | s1);
+}
+inline void fletcherHostPartial(const uint8_t* bytes, long long r0, long long n, unsigned long long& A, unsigned long long& D) {
+  for (long long i = 0; i < n; i++) {
+    const long long r = r0 + i;
+    const unsigned long long c = (unsigned long long)bytes[i] << ((r & 1) ? 0 : 8);
+    A += c; D = (D + ((unsigned long long)((r >> 1) % 65535) * c) % 65535ull) % 65535ull;
+  }
+}
+
+}  // namespace lerc

@@ -188,27 +188,39 @@ void launchRleDecode(Context* ctx, const uint8_t* dSrc, long long srcLen, uint8_
 // r/2, so any partition of the bytes can accumulate  A = SUM c  and  D = SUM (r/2 mod 65535) * c
 // independently; sum2 = 0xffff*(m+1) + m*A - D.  Each thread folds its partials mod 65535 before
 // the block/global adds, so the 64-bit accumulators cannot overflow.
+// 16 region bytes per thread step, big-endian 16-bit words formed with byte permutes.
+// acc[0] += SUM c, acc[1] += SUM (wordIndex mod 65535) * c (mod 65535) over region bytes [0, len)
 __global__ void k_fletcher_partial(const uint8_t* __restrict__ region, long long len, unsigned long long* __restrict__ acc) {
-  unsigned long long A = 0, D = 0;
-  const long long nVec = (len + 15) >> 4;          // 16 region bytes per step (unaligned-safe byte loads via 4 x u32 when possible)
-  for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < nVec; v += (long long)gridDim.x * blockDim.x) {
-    const long long r0 = v << 4;
-    unsigned long long a = 0, d = 0;
-    const unsigned wbase = (unsigned)((r0 >> 1) % 65535);
+  const int d = (int)((uintptr_t)region & 15);
+  const uint4* g0 = (const uint4*)(region - d);
+  const long long nChunks = (len + d + 15) >> 4;
+  unsigned long long fa = 0, fd = 0;
+  for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < nChunks; c += (long long)gridDim.x * blockDim.x) {
+    uint4 x = __ldg(g0 + c);
+    uint32_t o[4] = {x.x, x.y, x.z, x.w};
+    const long long r0 = c * 16 - d;                               // region offset of the chunk's first byte
+    if (r0 < 0 || r0 + 16 > len) {
 #pragma unroll
-    for (int j = 0; j < 16; j++) {
-      const long long r = r0 + j;
-      if (r < len) {
-        const unsigned c = (unsigned)region[r] << ((j & 1) ? 0 : 8);       // r0 is even, so parity of r == parity of j
-        a += c;
-        d += (unsigned long long)(wbase + (j >> 1)) * c;
-      }
+      for (int j = 0; j < 16; j++) if (r0 + j < 0 || r0 + j >= len) o[j >> 2] &= ~(0xffu << (8 * (j & 3)));
     }
-    A += a; D += d % 65535ull;
+    const unsigned par = (unsigned)(r0 & 1);
+    const uint32_t w0 = (uint32_t)((((r0 - (long long)par) >> 1) % 65535 + 65535) % 65535);
+    uint32_t S = 0, S1 = 0, prev = 0;
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+      const uint32_t cur = k < 4 ? o[k] : 0u;
+      const uint32_t y = __funnelshift_l(prev, cur, par * 8);
+      const uint32_t pw = __byte_perm(y, 0, 0x2301);
+      const uint32_t wlo = pw & 0xffffu, whi = pw >> 16;
+      S += wlo + whi; S1 += (uint32_t)(2 * k) * (wlo + whi) + whi;
+      prev = cur;
+    }
+    fa += S; fd += ((unsigned long long)w0 * S + S1) % 65535ull;
   }
-  A %= 65535ull; D %= 65535ull;
-  for (int m = 16; m; m >>= 1) { A += __shfl_xor_sync(FULL, A, m); D += __shfl_xor_sync(FULL, D, m); }
-  if ((threadIdx.x & 31) == 0) { atomicAdd(&acc[0], A); atomicAdd(&acc[1], D); }
+  fa %= 65535ull; fd %= 65535ull;
+#pragma unroll
+  for (int m = 16; m; m >>= 1) { fa += __shfl_xor_sync(FULL, fa, m); fd += __shfl_xor_sync(FULL, fd, m); }
+  if ((threadIdx.x & 31) == 0 && (fa | fd)) { atomicAdd(&acc[0], fa); atomicAdd(&acc[1], fd % 65535ull); }
 }
 
 // acc -> checksum; either stored at dst (encode) or compared with `expect` (decode: status |= 2 on mismatch)
@@ -227,7 +239,7 @@ __global__ void k_fletcher_finish(const unsigned long long* __restrict__ acc, lo
 
 void launchFletcher(Context* ctx, const uint8_t* dRegion, long long len, unsigned long long* dAcc /*2, zeroed*/,
                     uint8_t* dStoreAt, uint32_t expect, int* dStatus) {
-  const long long nVec = (len + 15) >> 4;
+  const long long nVec = (len + 30) >> 4;
   int grid = (int)std::min<long long>((nVec + 255) / 256, 148 * 8);
   if (grid < 1) grid = 1;
   LERC_LAUNCH(ctx, k_fletcher_partial, grid, 256, 0, dRegion, len, dAcc);

@@ -1,0 +1,91 @@
+"""GPU tests of the fused single-pass paths (lerc_encode_fast.cuh / lerc_decode_fast.cuh): they must be taken for
+the shapes they are built for, and their bytes / pixels must equal the oracle's."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from cases import c2_raster, smooth_field
+from lercapi import ROOT, oracle_lib, product_lib
+
+sys.path.insert(0, ROOT)
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def libs():
+    prod, orc = product_lib(), oracle_lib()
+    assert prod is not None and orc is not None
+    return prod, orc
+
+
+def _shapes():
+    return [(8, 8), (64, 64), (257, 300), (300, 517), (1024, 1024), (5, 1000), (1000, 5), (513, 2049)]
+
+
+@pytest.mark.parametrize("shape", _shapes(), ids=lambda s: f"{s[0]}x{s[1]}")
+@pytest.mark.parametrize("dtype,mz", [(np.float32, 0.01), (np.float32, 1.0), (np.float64, 0.001), (np.int16, 0), (np.uint16, 2),
+                                      (np.int32, 0), (np.uint32, 3)], ids=lambda v: str(getattr(v, "__name__", v)))
+def test_fast_encode_and_decode_match_oracle(libs, shape, dtype, mz):
+    import lerc_b200
+    prod, orc = libs
+    h, w = shape
+    rng = np.random.default_rng(h * 7919 + w)
+    base = smooth_field(h, w) + rng.normal(0, 0.5, (h, w))
+    if np.issubdtype(dtype, np.integer):
+        info = np.iinfo(dtype)
+        arr = np.clip(base * 3 - (2000 if info.min < 0 else 0), info.min, info.max).astype(dtype)
+    else:
+        arr = base.astype(dtype)
+    s_o, b_o, _ = orc.encode(arr, mz)
+    before = lerc_b200.stats()
+    s_p, b_p, _ = prod.encode(arr, mz)
+    mid = lerc_b200.stats()
+    assert s_o == 0 and s_p == 0
+    assert b_p == b_o, f"len {len(b_p)} vs {len(b_o)}"
+    assert mid[3] == before[3] + 1, "single-pass encoder was not taken"
+    t_o, d_o, m_o = orc.decode(b_o)
+    t_p, d_p, m_p = prod.decode(b_o)
+    after = lerc_b200.stats()
+    assert t_p == 0 and np.array_equal(d_p.view(np.uint8), d_o.view(np.uint8))
+    assert np.array_equal(m_p, m_o)
+    assert after[4] == mid[4] + 1, "single-kernel decoder was not taken"
+
+
+def test_fast_encode_falls_back_when_assumptions_fail(libs):
+    """NaN, all-integer floats, pre-rounded floats, LUT-friendly data, low bit rate, incompressible data: the
+    single-pass result is discarded and the general encoder produces the reference's bytes."""
+    prod, orc = libs
+    h, w = 128, 256
+    rng = np.random.default_rng(5)
+    f32 = (smooth_field(h, w) + rng.normal(0, 0.5, (h, w))).astype(np.float32)
+    nan = f32.copy(); nan[3, 4] = np.nan
+    neg0 = np.abs(f32); neg0[5, 5] = -0.0; neg0[9, 9] = 0.0
+    cases = [("nan", nan, 0.01), ("allint", np.round(f32), 0.01), ("rounded", np.round(f32, 1), 0.01),
+             ("stepped", (np.floor(smooth_field(h, w) / 40) * 40).astype(np.float32), 0.01),
+             ("lowrate", (smooth_field(h, w) / 300).astype(np.int16), 0),
+             ("noise", rng.integers(-2**31, 2**31 - 1, (h, w)).astype(np.int32), 0),
+             ("const", np.full((h, w), 2.5, np.float32), 0.01), ("negzero", neg0.astype(np.float32), 0.01),
+             ("allint_mz1", np.round(f32), 1.0), ("inf", np.where(f32 > 1290, np.float32(np.inf), f32).astype(np.float32), 0.01)]
+    for name, arr, mz in cases:
+        s_o, b_o, _ = orc.encode(arr, mz)
+        s_p, b_p, _ = prod.encode(arr, mz)
+        assert s_p == s_o, name
+        if s_o == 0:
+            assert b_p == b_o, name
+
+
+def test_fast_multiband_and_buffer_too_small(libs):
+    prod, orc = libs
+    bands = np.stack([c2_raster(128, 256, seed=s) for s in (1, 2, 3)])
+    s_o, b_o, _ = orc.encode(bands, 0.01, n_bands=3)
+    s_p, b_p, _ = prod.encode(bands, 0.01, n_bands=3)
+    assert s_p == 0 and b_p == b_o
+    t_p, d_p, _ = prod.decode(b_o)
+    t_o, d_o, _ = orc.decode(b_o)
+    assert t_p == 0 and np.array_equal(d_p.view(np.uint8), d_o.view(np.uint8))
+    st, _, _ = prod.encode(bands[0], 0.01, buf_size=len(b_o) // 3 - 100)
+    assert st == 3
+    st, _, _ = prod.encode(bands[0], 0.01, buf_size=200)
+    assert st == 3
