@@ -341,7 +341,7 @@ bool launchDecodeFast(Context* ctx, const HeaderInfo& hd, const uint8_t* dStream
   const int nReg = (nSub + subPerReg - 1) / subPerReg;
   const size_t smem = fastDecodeSmemBytes<T>(subPerReg, nReg);
   if (smem + 1024 > 227 * 1024) return false;
-  uint8_t* scratch = (uint8_t*)ctx->arena.alloc((size_t)nReg * FD_ENT * sizeof(FdEntry) + (size_t)nReg * 4 + 16);
+  uint8_t* scratch = (uint8_t*)ctx->arena.alloc((size_t)nReg * FD_ENT * sizeof(FdEntry) + (size_t)nReg * 4 + 16 + (size_t)nSub * 16);
   if (!scratch) return false;
   FastDecArgs fa;
   fa.stream = dStream; fa.streamLen = streamLen;
@@ -349,6 +349,7 @@ bool launchDecodeFast(Context* ctx, const HeaderInfo& hd, const uint8_t* dStream
   fa.invScale = 2 * hd.maxZError; fa.zMax = hd.zMax; fa.data = dData;
   fa.nSub = nSub; fa.subPerReg = subPerReg; fa.nReg = nReg; fa.maxU = 1 + 64 * (int)sizeof(T);
   fa.barrier = (unsigned int*)scratch; fa.regN = (int*)(scratch + 16); fa.regTab = (FdEntry*)(scratch + 16 + (size_t)nReg * 4);
+  fa.ckList = (uint16_t*)(scratch + 16 + (size_t)nReg * 4 + (size_t)nReg * FD_ENT * sizeof(FdEntry));
   fa.status = dStatus;
   cudaMemsetAsync(scratch, 0, 16, ctx->stream);
   static size_t attrSmem = 0;
@@ -503,8 +504,9 @@ ErrCode decodeBandT(Context* ctx, DecodeBandArgs& a, BandMaskState& ms) {
   if (mayFast && launchDecodeFast<T>(ctx, hd, blob + pos, (size_t)hd.blobSize - pos, a.dData, dStatus)) {
     int hs = 0;
     if (!cudaOk(cudaMemcpyAsync(&hs, dStatus, 4, cudaMemcpyDeviceToHost, st), "D2H") || !cudaOk(cudaStreamSynchronize(st), "sync")) return Failed;
-    if (!(hs & DECF_FALLBACK)) { if (hs == 0) globalStats().fastPathDecodes++; return hs == 0 ? Ok : Failed; }
-    if (hs & ~DECF_FALLBACK) return Failed;                     // e.g. checksum mismatch
+    if (hs && std::getenv("LERC_B200_VERBOSE")) std::fprintf(stderr, "[lerc_b200] fused decoder status %d\n", hs);
+    if (!(hs & DECF_FALLBACK)) { if (hs == 0) globalStats().fastPathDecodes++; return (hs & 7) == 0 ? Ok : Failed; }
+    if (hs & 7) return Failed;                                  // e.g. checksum mismatch (bits above DECF_FALLBACK say why the fused decoder gave up)
     cudaMemsetAsync(dStatus, 0, 4, st);
   }
   zeroFill();

@@ -4,7 +4,7 @@ from lercapi import oracle_lib, product_lib
 from cases import c2_raster
 import lerc_b200
 prod, orc = product_lib(), oracle_lib()
-for shape in [(8, 8), (64, 64), (257, 300), (1024, 1024)]:
+for shape in [(65, 2049), (257, 300), (513, 2049), (513, 2050), (1024, 1024), (4096, 4096)]:
     img = c2_raster(*shape)
     s, b, _ = orc.encode(img, 0.01)
     s0 = lerc_b200.stats()
