@@ -185,6 +185,7 @@ lerc_status decodeImpl(const unsigned char* pBlob, unsigned blobSize, int nMasks
     DecodeBandArgs a;
     a.dt = (int)dataType; a.nDepth = nDepth; a.nCols = nCols; a.nRows = nRows;
     a.dBlob = dBlob + pos; a.avail = blobSize - pos; a.hd = hd; a.hBlob = kBlob != PTR_DEVICE ? pBlob + pos : nullptr;
+    a.src = &src; a.srcOff = pos;
     a.dData = direct ? (void*)((uint8_t*)pData + nElem * ts * (size_t)b) : dBandScratch;
     const bool wantMask = b < nMasks;
     a.dValidBytes = wantMask ? (kMask == PTR_DEVICE ? pValidBytes + nPix * (size_t)b : dMaskScratch) : nullptr;

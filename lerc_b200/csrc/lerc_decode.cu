@@ -330,38 +330,41 @@ int smCount() {
   return n;
 }
 
-// Launches the single-kernel decoder (lerc_decode_fast.cuh) on the micro-block stream.  Returns false when the
+// Launches the speculative parallel decoder (lerc_decode_fast.cuh) on the micro-block stream.  Returns false when the
 // stream's shape is outside what it handles (nothing launched).
 template <class T>
 bool launchDecodeFast(Context* ctx, const HeaderInfo& hd, const uint8_t* dStream, size_t streamLen, void* dData, int* dStatus) {
   if (hd.nDepth != 1 || hd.microBlockSize != 8 || hd.version < 3 || (long long)hd.numValidPixel != (long long)hd.nCols * hd.nRows) return false;
   if (streamLen == 0 || streamLen >= 0xfff00000ull || std::getenv("LERC_B200_NO_FAST")) return false;
   const int nSub = (int)((streamLen + FD_SUB - 1) / FD_SUB);
-  const int subPerReg = (nSub + smCount() - 1) / smCount();
+  const int regTarget = smCount();
+  const int subPerReg = (nSub + regTarget - 1) / regTarget;
   const int nReg = (nSub + subPerReg - 1) / subPerReg;
-  const size_t smem = fastDecodeSmemBytes<T>(subPerReg, nReg);
-  if (smem + 1024 > 227 * 1024) return false;
-  uint8_t* scratch = (uint8_t*)ctx->arena.alloc((size_t)nReg * FD_ENT * sizeof(FdEntry) + (size_t)nReg * 4 + 16 + (size_t)nSub * 16);
+  const size_t smemB = fastDecodeBlocksSmem<T>(subPerReg, nReg), smemW = (size_t)subPerReg * FD_CAND * sizeof(FdEntry);
+  if (smemB + 1024 > 227 * 1024 || smemW + 1024 > 227 * 1024) return false;
+  const size_t szCand = (size_t)nSub * FD_CAND * sizeof(FdCand), szN = ((size_t)nSub + 255) & ~(size_t)255, szLens = (size_t)nSub * FD_CAND * 256,
+               szSub = (size_t)nSub * FD_CAND * sizeof(FdEntry), szReg = (size_t)nReg * FD_CAND * sizeof(FdEntry);
+  uint8_t* scratch = (uint8_t*)ctx->arena.alloc(szLens + szCand + szSub + szReg + szN + 256);
   if (!scratch) return false;
   FastDecArgs fa;
   fa.stream = dStream; fa.streamLen = streamLen;
   fa.nRows = hd.nRows; fa.nCols = hd.nCols; fa.nTx = (hd.nCols + 7) / 8; fa.nTy = (hd.nRows + 7) / 8; fa.dt = hd.dt; fa.version = hd.version;
   fa.invScale = 2 * hd.maxZError; fa.zMax = hd.zMax; fa.data = dData;
-  fa.nSub = nSub; fa.subPerReg = subPerReg; fa.nReg = nReg; fa.maxU = 1 + 64 * (int)sizeof(T);
-  fa.barrier = (unsigned int*)scratch; fa.regN = (int*)(scratch + 16); fa.regTab = (FdEntry*)(scratch + 16 + (size_t)nReg * 4);
-  fa.ckList = (uint16_t*)(scratch + 16 + (size_t)nReg * 4 + (size_t)nReg * FD_ENT * sizeof(FdEntry));
+  fa.nSub = nSub; fa.subPerReg = subPerReg; fa.nReg = nReg;
+  uint8_t* sp = scratch;
+  fa.lens = sp; sp += szLens;
+  fa.cand = (FdCand*)sp; sp += szCand;
+  fa.subTab = (FdEntry*)sp; sp += szSub;
+  fa.regTab = (FdEntry*)sp; sp += szReg;
+  fa.nCand = sp;
   fa.status = dStatus;
-  cudaMemsetAsync(scratch, 0, 16, ctx->stream);
-  static size_t attrSmem = 0;
-  if (smem > attrSmem) {
-    if (!cudaOk(cudaFuncSetAttribute(k_decode_fused<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attribute")) return false;
-    attrSmem = smem;
-  }
-  void* params[] = {&fa};
-  LaunchScope scope(ctx, "k_decode_fused<T>");
-  if (!cudaOk(cudaLaunchCooperativeKernel((const void*)k_decode_fused<T>, dim3(nReg), dim3(FD_WARPS * 32), params, smem, ctx->stream), "launch k_decode_fused")) return false;
-  ctx->kernelLaunches++;
-  return true;
+  static size_t attrB = 0, attrW = 0;
+  if (smemB > attrB) { if (!cudaOk(cudaFuncSetAttribute(k_dec_blocks<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB), "smem attribute")) return false; attrB = smemB; }
+  if (smemW > attrW && smemW > 48 * 1024) { if (!cudaOk(cudaFuncSetAttribute(k_dec_walk<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemW), "smem attribute")) return false; attrW = smemW; }
+  LERC_LAUNCH(ctx, k_dec_candidates<T>, (nSub + 7) / 8, 256, 0, fa);
+  LERC_LAUNCH(ctx, k_dec_walk<T>, nReg, 512, smemW, fa);
+  LERC_LAUNCH(ctx, k_dec_blocks<T>, nReg, FD_DWARPS * 32, smemB, fa);
+  return cudaOk(cudaGetLastError(), "launch fast decode");
 }
 
 template <class T>
@@ -373,7 +376,12 @@ ErrCode decodeBandT(Context* ctx, DecodeBandArgs& a, BandMaskState& ms) {
   const int nDepth = hd.nDepth;
   if (a.avail < (size_t)hd.blobSize) return Failed;
   const uint8_t* blob = a.dBlob;
-  ByteSource src; src.base = a.hBlob ? a.hBlob : a.dBlob; src.size = (size_t)hd.blobSize; src.onDevice = a.hBlob == nullptr;
+  // reads of this band's blob on the host go through the caller's ByteSource (host pointer, or device pointer + cache)
+  struct BandView { const ByteSource* s; size_t off, size;
+                    bool fetch(size_t o, size_t len, void* dst) const { return o <= size && len <= size - o && s->fetch(off + o, len, dst); } };
+  ByteSource own;
+  if (!a.src) { own.base = a.hBlob ? a.hBlob : a.dBlob; own.size = (size_t)hd.blobSize; own.onDevice = a.hBlob == nullptr; }
+  const BandView src{a.src ? a.src : &own, a.src ? a.srcOff : 0, (size_t)hd.blobSize};
 
   int* dStatus = (int*)ctx->arena.alloc(16);
   if (!dStatus) return Failed;

@@ -85,7 +85,14 @@ bool readHeader(const uint8_t* src, size_t avail, HeaderInfo& h) {
 bool ByteSource::fetch(size_t off, size_t len, void* dst) const {
   if (off > size || len > size - off) return false;
   if (!onDevice) { std::memcpy(dst, base + off, len); return true; }
-  return cudaMemcpy(dst, base + off, len, cudaMemcpyDeviceToHost) == cudaSuccess;
+  if (len > sizeof cache) return cudaMemcpy(dst, base + off, len, cudaMemcpyDeviceToHost) == cudaSuccess;
+  if (!(off >= cacheOff && off + len <= cacheOff + cacheLen)) {
+    const size_t take = size - off < sizeof cache ? size - off : sizeof cache;
+    if (cudaMemcpy(cache, base + off, take, cudaMemcpyDeviceToHost) != cudaSuccess) { cacheLen = 0; return false; }
+    cacheOff = off; cacheLen = take;
+  }
+  std::memcpy(dst, cache + (off - cacheOff), len);
+  return true;
 }
 
 namespace {

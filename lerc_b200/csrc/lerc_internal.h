@@ -47,6 +47,10 @@ struct ByteSource {
   size_t size = 0;
   bool onDevice = false;
   bool fetch(size_t off, size_t len, void* dst) const;
+  // device blobs: a small host copy of the bytes around the last fetch, so that the handful of header / mask length /
+  // range / flag reads of one band cost one device-to-host copy (valid for the duration of one API call only)
+  mutable uint8_t cache[512];
+  mutable size_t cacheOff = 0, cacheLen = 0;
 };
 
 struct BlobInfo {     // Lerc.h:99-116
@@ -144,6 +148,7 @@ struct DecodeBandArgs {
   size_t avail;                   // bytes available from dBlob
   HeaderInfo hd;                  // already parsed on the host
   const uint8_t* hBlob;           // the same band blob in host memory when the caller's blob is a host buffer, else nullptr
+  const ByteSource* src = nullptr; size_t srcOff = 0;   // the caller's view of the whole blob and this band's offset in it
   void* dData;                    // device output for this band
   uint8_t* dValidBytes;           // device byte mask output for this band or nullptr
 };

@@ -190,7 +190,7 @@ void launchRleDecode(Context* ctx, const uint8_t* dSrc, long long srcLen, uint8_
 // the block/global adds, so the 64-bit accumulators cannot overflow.
 // 16 region bytes per thread step, big-endian 16-bit words formed with byte permutes.
 // acc[0] += SUM c, acc[1] += SUM (wordIndex mod 65535) * c (mod 65535) over region bytes [0, len)
-__global__ void k_fletcher_partial(const uint8_t* __restrict__ region, long long len, unsigned long long* __restrict__ acc) {
+__global__ void __launch_bounds__(256) k_fletcher_partial(const uint8_t* __restrict__ region, long long len, unsigned long long* __restrict__ acc) {
   const int d = (int)((uintptr_t)region & 15);
   const uint4* g0 = (const uint4*)(region - d);
   const long long nChunks = (len + d + 15) >> 4;
@@ -204,7 +204,7 @@ __global__ void k_fletcher_partial(const uint8_t* __restrict__ region, long long
       for (int j = 0; j < 16; j++) if (r0 + j < 0 || r0 + j >= len) o[j >> 2] &= ~(0xffu << (8 * (j & 3)));
     }
     const unsigned par = (unsigned)(r0 & 1);
-    const uint32_t w0 = (uint32_t)((((r0 - (long long)par) >> 1) % 65535 + 65535) % 65535);
+    const uint32_t w0 = (uint32_t)((unsigned long long)(r0 + 16) >> 1) % 65535u;   // word index of byte r0 + 16 - par ... minus 8 below
     uint32_t S = 0, S1 = 0, prev = 0;
 #pragma unroll
     for (int k = 0; k < 5; k++) {
@@ -215,12 +215,20 @@ __global__ void k_fletcher_partial(const uint8_t* __restrict__ region, long long
       S += wlo + whi; S1 += (uint32_t)(2 * k) * (wlo + whi) + whi;
       prev = cur;
     }
-    fa += S; fd += ((unsigned long long)w0 * S + S1) % 65535ull;
+    // words of this chunk have indices w0 - 8 + k (mod 65535), k = 0..9 (index base of byte r0 - par is (r0 - par) / 2 = (r0 + 16) / 2 - 8)
+    fa += S; fd += (unsigned long long)(w0 + 65535u - 8u) * S + S1;
   }
   fa %= 65535ull; fd %= 65535ull;
 #pragma unroll
   for (int m = 16; m; m >>= 1) { fa += __shfl_xor_sync(FULL, fa, m); fd += __shfl_xor_sync(FULL, fd, m); }
-  if ((threadIdx.x & 31) == 0 && (fa | fd)) { atomicAdd(&acc[0], fa); atomicAdd(&acc[1], fd % 65535ull); }
+  __shared__ unsigned long long sA[8], sD[8];
+  if ((threadIdx.x & 31) == 0) { sA[threadIdx.x >> 5] = fa; sD[threadIdx.x >> 5] = fd; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long A = 0, D = 0;
+    for (int i = 0; i < 8; i++) { A += sA[i]; D += sD[i]; }
+    if (A | D) { atomicAdd(&acc[0], A); atomicAdd(&acc[1], D % 65535ull); }
+  }
 }
 
 // acc -> checksum; either stored at dst (encode) or compared with `expect` (decode: status |= 2 on mismatch)
@@ -240,7 +248,7 @@ __global__ void k_fletcher_finish(const unsigned long long* __restrict__ acc, lo
 void launchFletcher(Context* ctx, const uint8_t* dRegion, long long len, unsigned long long* dAcc /*2, zeroed*/,
                     uint8_t* dStoreAt, uint32_t expect, int* dStatus) {
   const long long nVec = (len + 30) >> 4;
-  int grid = (int)std::min<long long>((nVec + 255) / 256, 148 * 8);
+  int grid = (int)std::min<long long>((nVec + 255) / 256, 148 * 32);
   if (grid < 1) grid = 1;
   LERC_LAUNCH(ctx, k_fletcher_partial, grid, 256, 0, dRegion, len, dAcc);
   LERC_LAUNCH(ctx, k_fletcher_finish, 1, 1, 0, dAcc, len, dStoreAt, expect, dStatus);
