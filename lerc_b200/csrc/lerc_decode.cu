@@ -337,7 +337,7 @@ bool launchDecodeFast(Context* ctx, const HeaderInfo& hd, const uint8_t* dStream
   if (hd.nDepth != 1 || hd.microBlockSize != 8 || hd.version < 3 || (long long)hd.numValidPixel != (long long)hd.nCols * hd.nRows) return false;
   if (streamLen == 0 || streamLen >= 0xfff00000ull || std::getenv("LERC_B200_NO_FAST")) return false;
   const int nSub = (int)((streamLen + FD_SUB - 1) / FD_SUB);
-  const int regTarget = smCount();
+  const int regTarget = 2 * smCount();                          // k_dec_blocks: two 512-thread CTAs per SM
   const int subPerReg = (nSub + regTarget - 1) / regTarget;
   const int nReg = (nSub + subPerReg - 1) / subPerReg;
   const size_t smemB = fastDecodeBlocksSmem<T>(subPerReg, nReg), smemW = (size_t)subPerReg * FD_CAND * sizeof(FdEntry);

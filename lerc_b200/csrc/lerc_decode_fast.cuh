@@ -276,11 +276,12 @@ __global__ void __launch_bounds__(512) k_dec_walk(FastDecArgs a) {
         uint32_t v[5];
 #pragma unroll
         for (int k = 0; k < 5; k++) v[k] = (w0 + 4 * k <= lastByte) ? __ldg(w + k) : 0u;
+        if (w0 + 384 <= lastByte) asm volatile("prefetch.global.L1 [%0];" :: "l"(w + 64));   // the chain advances < 256 bytes per hop: keep its next lines in L1
         FdWin x;
         x.lo = (unsigned long long)__funnelshift_r(v[0], v[1], sh) | ((unsigned long long)__funnelshift_r(v[1], v[2], sh) << 32);
         x.hi = (unsigned long long)__funnelshift_r(v[2], v[3], sh) | ((unsigned long long)__funnelshift_r(v[3], v[4], sh) << 32);
         int np;
-        const int len = fdHopLen<T>(x, nullptr, version, left - pos, tailRaw, np);
+        const int len = fdHopLen<T>(x, (left - pos >= 24) ? a.stream + start + pos : nullptr, version, left - pos, tailRaw, np);   // byte-wise parser (LUT blocks) reads the stream directly
         // lengths are recorded as bytes; 255 stands for the raw 8x8 block (the only unit that can be longer)
         const int code = len == 1 + 64 * (int)sizeof(T) ? 255 : len;
         if (len <= 0 || (code != 255 && len >= 255) || cnt >= FD_MAXHOP || (cnt > 0 && !fdFollows(pat, np, version))) { ok = false; break; }
@@ -319,7 +320,7 @@ __global__ void __launch_bounds__(512) k_dec_walk(FastDecArgs a) {
 // ================= kernel 3: resolve the true chain, decode the blocks ================================
 constexpr int FD_DWARPS = 16;
 template <class T>
-__global__ void __launch_bounds__(FD_DWARPS * 32) k_dec_blocks(FastDecArgs a) {
+__global__ void __launch_bounds__(FD_DWARPS * 32, 2) k_dec_blocks(FastDecArgs a) {
   constexpr int MAXU = 1 + 64 * (int)sizeof(T);
   constexpr int BUFB = ((FD_SUB + MAXU + 64 + 15) / 16) * 16;       // per-warp staging of one sub-chunk (+ look-ahead)
   extern __shared__ __align__(16) uint8_t smemD[];

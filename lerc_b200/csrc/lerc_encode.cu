@@ -617,8 +617,9 @@ bool encodeBandFast(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
   const int nTx = (a.nCols + 7) / 8, nTy = (a.nRows + 7) / 8;
   const long long nBlocks = (long long)nTx * nTy;
   constexpr int TB = FAST_TB;
-  const long long nTiles = (nBlocks + TB - 1) / TB;
+  const long long nTiles = (long long)((nTx + TB - 1) / TB) * nTy;      // tiles never wrap a block row
   if (nTiles > 0x7fffffffLL) return false;
+  (void)nBlocks;
   const size_t dataStart = (size_t)headerBytes(6) + 4 + 2 * sizeof(T) + 1;
   if (a.outCapacity < dataStart + 1) return false;                     // let the general path report BufferTooSmall exactly
 
@@ -646,16 +647,21 @@ bool encodeBandFast(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
 
   FastEncArgs fa;
   fa.data = a.dData; fa.nRows = a.nRows; fa.nCols = a.nCols; fa.nTx = nTx; fa.nTy = nTy; fa.dt = PixelTraits<T>::code;
-  fa.maxZErr = maxZErr; fa.scale = 1.0 / (2.0 * maxZErr); fa.maxQ = fa.dt <= DT_UShort ? (1u << 15) - 1 : (1u << 30) - 1;         // Lerc2.h:685-703
+  fa.maxZErr = maxZErr; fa.scale = 1.0 / (2.0 * maxZErr); fa.maxZErr3 = 3.0 * maxZErr; fa.maxQ = fa.dt <= DT_UShort ? (1u << 15) - 1 : (1u << 30) - 1;         // Lerc2.h:685-703
   fa.intLossless = (!isFlt && maxZErr == 0.5) ? 1 : 0;
   uint8_t* blob = a.dOut + a.outOffset;
   fa.stream = blob + dataStart; fa.streamCap = a.outCapacity - dataStart; fa.regionOff = (long long)dataStart - 14;
   fa.tileState = (unsigned long long*)(dState + sizeof(FastEncResult) + 9 * 8); fa.res = dRes;
   constexpr int MAXB = 1 + 64 * (int)sizeof(T);
-  const size_t smem = (size_t)((TB * MAXB + 15) / 16 + 3) * 16;
-  static bool attrSet = false;
-  if (!attrSet) { cudaFuncSetAttribute(k_encode_fused<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attrSet = true; }
-  LERC_LAUNCH(ctx, k_encode_fused<T>, (unsigned)nTiles, 256, smem, fa);
+  const size_t smem = (size_t)((TB * MAXB + 15) / 16 + 3) * 16 * 2 + 256 * 8 * sizeof(T);       // two staging images + the general path's pixel rows
+  static int ctasPerSm = 0;
+  if (!ctasPerSm) {
+    cudaFuncSetAttribute(k_encode_fused<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSm, k_encode_fused<T>, 256, smem) != cudaSuccess || ctasPerSm < 1) ctasPerSm = 1;
+  }
+  int dev = 0, sms = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long grid = std::min<long long>(nTiles, (long long)ctasPerSm * std::max(sms, 1));   // all CTAs co-resident (look-back)
+  LERC_LAUNCH(ctx, k_encode_fused<T>, (unsigned)grid, 256, smem, fa);
   if (!cudaOk(cudaMemcpyAsync(hRes, dState, sizeof(HostRes), cudaMemcpyDeviceToHost, st), "D2H fast result")) { err = Failed; return true; }
   if (!cudaOk(cudaStreamSynchronize(st), "sync")) { err = Failed; return true; }
 

@@ -34,7 +34,7 @@ struct FastEncResult {                 // device, zero-initialised per call
 
 struct FastEncArgs {
   const void* data; int nRows, nCols, nTx, nTy, dt;
-  double maxZErr, scale; uint32_t maxQ;   // scale = 1 / (2 * maxZErr), computed on the host exactly like Lerc2.h:339
+  double maxZErr, scale, maxZErr3; uint32_t maxQ;   // scale = 1 / (2 * maxZErr) (Lerc2.h:339), maxZErr3 = 3 * maxZErr (Lerc2.cpp:1794), both rounded on the host as the reference does
   int intLossless;                     // integer type && maxZErr == 0.5
   uint8_t* stream;                     // where the micro-block stream starts (blob + dataStart)
   unsigned long long streamCap;        // bytes available from `stream`
@@ -138,64 +138,33 @@ __device__ __forceinline__ void loadRow8(const T* __restrict__ p, int w, bool ve
 }
 
 // ---- the kernel --------------------------------------------------------------------------------
-// 256 threads = 8 warps x 4 micro-blocks = 32 blocks per CTA tile; tile index = blockIdx.x (tiles are
-// dispatched in index order, which the look-back relies on, as CUB's single-pass scan does).
+// Persistent CTAs (256 threads = 8 warps x 4 micro-blocks).  A tile = up to 32 consecutive blocks of ONE block row
+// (tiles never wrap, so a lane's pixel address needs no division); tiles are numbered in stream order and CTA c
+// works on tiles c, c + gridDim.x, ...  While tile i is coded, the pixels of tile i + 1 are already in flight
+// (register prefetch).  All CTAs are co-resident (the host sizes the grid by occupancy), which the look-back needs.
 constexpr int FAST_TB = 32;
 
 template <class T>
-__global__ void __launch_bounds__(256) k_encode_fused(FastEncArgs a) {
+struct FastRow { T v[8]; };
+
+// ---- general (any block shape / coding) per-lane pieces, kept out of line so that the hot path stays lean -------
+template <class T>
+__device__ __noinline__ void fastGenericChoice(const FastEncArgs& a, const T* __restrict__ v, int h, int w, int r, bool act,
+                                               int& nBytesOut, int& modeOut, int& nbOut, int& tcOut, int& dtUsedOut, uint32_t& maxElemOut,
+                                               double& zMinOut, T& loOut, unsigned int& flagsOut,
+                                               typename PixelTraits<T>::Key& kminOut, typename PixelTraits<T>::Key& kmaxOut) {
   using K = typename PixelTraits<T>::Key;
   constexpr bool isFlt = PixelTraits<T>::isFloat;
   constexpr int DT = PixelTraits<T>::code;
-  constexpr int TB = FAST_TB;
-  constexpr int MAXB = 1 + 64 * (int)sizeof(T);                 // longest block: raw (Lerc2.h:427)
-  constexpr int NQ = (TB * MAXB + 15) / 16 + 3;                 // staging uint4s: 16 zero bytes | tile output | zero tail
-  extern __shared__ __align__(16) uint32_t stageRaw[];
-  uint32_t* stage = stageRaw + 4;                               // tile-local byte 0 of the output
-  __shared__ uint32_t sLen[TB];
-  __shared__ unsigned long long sTileOff;
-  __shared__ unsigned long long sKMin[8], sKMax[8], sFA[8], sFD[8];
-  __shared__ unsigned int sFlg[8];
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, sb = lane >> 3, r = lane & 7;
-  const unsigned int tile = blockIdx.x;
-  // snapshots of the image-global facts so far (read early, used at the very end to skip useless atomics)
-  const unsigned int flagsSeen = *(volatile unsigned int*)&a.res->flags;
-  const unsigned long long negMinSeen = *(volatile unsigned long long*)&a.res->negMinKey, maxSeen = *(volatile unsigned long long*)&a.res->maxKey;
-  for (int i = tid; i < NQ; i += 256) ((uint4*)stageRaw)[i] = make_uint4(0, 0, 0, 0);
-
-  const int nBlocks = a.nTx * a.nTy;
-  const T* data = (const T*)a.data;
-  const bool vecOk = ((a.nCols * (int)sizeof(T)) % 16 == 0) && (((uintptr_t)data & 15) == 0);
-
-  // ---- load one block row per lane, block statistics (GetValidDataAndStats, Lerc2.cpp:1717-1799)
-  const int b = warp * 4 + sb, blk = (int)tile * TB + b;
-  const bool act = blk < nBlocks;
-  const int ty = act ? blk / a.nTx : 0, tx = act ? blk - ty * a.nTx : 0;
-  const int i0 = ty * 8, j0 = tx * 8;
-  const int h = act ? min(8, a.nRows - i0) : 0, w = min(8, a.nCols - j0), n = h * w;
-  const bool rowAct = r < h;
-  T v[8];
+  const bool rowAct = act && r < h;
   K kmin = keyMaxValue<K>(), kmax = 0;
   int same = 0;
-  unsigned int myFlags = 0;
   if (rowAct) {
-    loadRow8<T>(data + (size_t)(i0 + r) * a.nCols + j0, w, vecOk && w == 8, v);
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-      const K key = toKey(v[k]);
-      kmin = key < kmin ? key : kmin; kmax = key > kmax ? key : kmax;
+      if (k < w) { const K key = toKey(v[k]); kmin = key < kmin ? key : kmin; kmax = key > kmax ? key : kmax; }
       if (k > 0) same += (k < w && v[k] == v[k - 1]) ? 1 : 0;
     }
-    if (isFlt && !(flagsSeen & FASTF_NOT_INT)) {                        // all-integer test (Lerc.h:248), until someone found a fraction
-      bool ni = false;
-#pragma unroll
-      for (int k = 0; k < 8; k++) ni |= sizeof(T) == 4 ? ((float)v[k] != truncf((float)v[k])) : ((double)v[k] != trunc((double)v[k]));
-      if (ni) myFlags |= FASTF_NOT_INT;
-    }
-  } else {
-#pragma unroll
-    for (int k = 0; k < 8; k++) v[k] = (T)0;
   }
   {  // previous pixel of a row's first pixel: last pixel of the row above; 0 for the block's first pixel (Lerc2.cpp:1729)
     T last = v[0];
@@ -213,16 +182,18 @@ __global__ void __launch_bounds__(256) k_encode_fused(FastEncArgs a) {
     kmin = omin < kmin ? omin : kmin; kmax = omax > kmax ? omax : kmax;
     same += __shfl_xor_sync(FULL, same, m);
   }
+  kminOut = kmin; kmaxOut = kmax;
+  const int n = h * w;
   const T lo = fromKey<T>(kmin), hi = fromKey<T>(kmax);
   const double zMin = (double)lo, zMax = (double)hi;
-  if (isFlt && act && (isNaNVal(lo) || isNaNVal(hi))) myFlags |= FASTF_NAN;
-  // LUT coding is a candidate (Lerc2.cpp:1794-1795): not handled here, the host falls back
-  if (act && n > 4 && (zMax > __dadd_rn(zMin, __dmul_rn(3.0, a.maxZErr))) && (2 * same > n)) myFlags |= FASTF_LUT;
-
-  // ---- coding choice + length (NumBytesTile, Lerc2.h:416-453; tryLut == false)
+  zMinOut = zMin; loOut = lo;
+  unsigned int fl = 0;
+  if (isFlt && act && (isNaNVal(lo) || isNaNVal(hi))) fl |= FASTF_NAN;
+  if (act && n > 4 && (zMax > __dadd_rn(zMin, __dmul_rn(3.0, a.maxZErr))) && (2 * same > n)) fl |= FASTF_LUT;   // Lerc2.cpp:1794-1795
+  flagsOut = fl;
   int mode = BEM_RAW, nb = 0, tc = 0, dtUsed = DT, nBytes = 0;
   uint32_t maxElem = 0;
-  if (act) {
+  if (act) {                                                           // NumBytesTile, Lerc2.h:416-453; tryLut == false
     const int raw = 1 + n * (int)sizeof(T);
     if (zMin == 0 && zMax == 0) { nBytes = 1; mode = BEM_ZERO; }
     else {
@@ -237,160 +208,335 @@ __global__ void __launch_bounds__(256) k_encode_fused(FastEncArgs a) {
       }
     }
   }
-  if (r == 0) sLen[b] = (uint32_t)nBytes;
-  __syncthreads();                                                      // staging zeroed, block lengths visible
+  nBytesOut = nBytes; modeOut = mode; nbOut = nb; tcOut = tc; dtUsedOut = dtUsed; maxElemOut = maxElem;
+}
 
-  // ---- tile-local byte offsets: every warp scans the 32 lengths itself
-  uint32_t inc = sLen[lane];
-  {
-    const uint32_t x = inc;
+template <class T>
+__device__ __noinline__ void fastGenericEmit(const FastEncArgs& a, uint32_t* stage, const T* __restrict__ vs, int h, int w, int r, int j0, uint32_t byte0,
+                                             int mode, int nb, int tc, int dtUsed, uint32_t maxElem, double zMin, T lo) {
+  constexpr bool isFlt = PixelTraits<T>::isFloat;
+  if (r >= h) return;
+  T v[8];
 #pragma unroll
-    for (int s = 1; s < 32; s <<= 1) { const uint32_t o = __shfl_up_sync(FULL, inc, s); if (lane >= s) inc += o; }
-    inc -= x;                                                           // exclusive
+  for (int k = 0; k < 8; k++) v[k] = vs[k];
+  const int n = h * w;
+  const uint8_t flag = (uint8_t)((((j0 >> 3) & 15) << 2) & 0x38);       // version 6, no depth delta (Lerc2.cpp:1955-1958)
+  if (mode == BEM_ZERO) { if (r == 0) { const uint32_t H[1] = {(uint32_t)(flag | 2)}; orBits<1>(stage, byte0 * 8, H, 8); } return; }
+  if (mode == BEM_RAW) {
+    if (r == 0) { const uint32_t H[1] = {(uint32_t)flag}; orBits<1>(stage, byte0 * 8, H, 8); }
+    uint32_t R[16]; rawRowBits<T>(v, w, R);
+    const uint32_t bitOff = (byte0 + 1 + (uint32_t)(r * w) * (uint32_t)sizeof(T)) * 8;
+    if (sizeof(T) == 8) orBits<16>(stage, bitOff, R, w * 64);
+    else { uint32_t R8[8];
+#pragma unroll
+           for (int j = 0; j < 8; j++) R8[j] = R[j];
+           orBits<8>(stage, bitOff, R8, w * 8 * (int)sizeof(T)); }
+    return;
   }
-  const uint32_t tileBytes = __shfl_sync(FULL, inc, 31) + __shfl_sync(FULL, sLen[lane], 31);
-  const uint32_t byte0 = __shfl_sync(FULL, inc, b);
+  const int osz = dtSize(dtUsed);
+  if (r == 0) {                                                         // flag | offset | [numBits byte | count]
+    const unsigned long long ob = offsetBits(zMin, dtUsed);
+    unsigned long long lo64 = (unsigned long long)(flag | (maxElem == 0 ? 3 : 1) | (tc << 6)) | (ob << 8);
+    unsigned long long hi64 = osz == 8 ? (ob >> 56) : 0;
+    int nbytes = 1 + osz;                                               // 2, 3, 5 or 9
+    if (maxElem > 0) {
+      const unsigned long long two = (unsigned long long)(nb | (2 << 6)) | ((unsigned long long)n << 8);   // count < 256: one byte, code 2
+      if (nbytes < 8) lo64 |= two << (8 * nbytes); else hi64 |= two << (8 * (nbytes - 8));
+      nbytes += 2;
+    }
+    const uint32_t H[3] = {(uint32_t)lo64, (uint32_t)(lo64 >> 32), (uint32_t)hi64};
+    orBits<3>(stage, byte0 * 8, H, nbytes * 8);
+  }
+  if (maxElem == 0) return;
+  uint32_t q[8];
+  bool done = false;
+  if constexpr (!isFlt) {
+    if (a.intLossless) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) q[k] = k < w ? (uint32_t)((long long)v[k] - (long long)lo) : 0u;
+      done = true;
+    }
+  }
+  if (!done) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) q[k] = k < w ? quantizeOne((double)v[k], zMin, a.scale) : 0u;
+  }
+  uint32_t R[8];
+  packRow8(q, nb, R);
+  orBits<8>(stage, (byte0 + (uint32_t)(osz + 3)) * 8 + (uint32_t)(r * w * nb), R, w * nb);
+}
+
+template <class T>
+__global__ void __launch_bounds__(256, 4) k_encode_fused(FastEncArgs a) {
+  using K = typename PixelTraits<T>::Key;
+  constexpr bool isFlt = PixelTraits<T>::isFloat;
+  constexpr int DT = PixelTraits<T>::code;
+  constexpr int TB = FAST_TB;
+  constexpr int MAXB = 1 + 64 * (int)sizeof(T);                 // longest block: raw (Lerc2.h:427)
+  constexpr int NQ = (TB * MAXB + 15) / 16 + 3;                 // staging uint4s: 16 zero bytes | tile output | zero tail
+  extern __shared__ __align__(16) uint32_t stageRaw[];          // two staging images (tiles alternate) | T sRow[256][8] (general path)
+  T* sRow = (T*)(stageRaw + 2 * NQ * 4);
+  __shared__ uint32_t sLen[2][TB];
+  __shared__ unsigned long long sTileOff;
+  __shared__ unsigned long long sKMin[8], sKMax[8], sFA[8], sFD[8];
+  __shared__ unsigned int sFlg[8];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, sb = lane >> 3, r = lane & 7;
+  const unsigned int flagsSeen = *(volatile unsigned int*)&a.res->flags;
+  const unsigned long long negMinSeen = *(volatile unsigned long long*)&a.res->negMinKey, maxSeen = *(volatile unsigned long long*)&a.res->maxKey;
+  for (int i = tid; i < 2 * NQ; i += 256) ((uint4*)stageRaw)[i] = make_uint4(0, 0, 0, 0);
+
+  const T* data = (const T*)a.data;
+  const bool vecOk = ((a.nCols * (int)sizeof(T)) % 16 == 0) && (((uintptr_t)data & 15) == 0);
+  const int tpr = (a.nTx + TB - 1) / TB;                         // tiles per block row
+  const int nTiles = tpr * a.nTy;
+  const int b = warp * 4 + sb;
   constexpr unsigned long long ST_A = 1ull << 62, ST_P = 2ull << 62, VAL = (1ull << 62) - 1;
   volatile unsigned long long* st = a.tileState;
-  if (tid == 0) st[tile] = (tile == 0 ? ST_P : ST_A) | (unsigned long long)tileBytes;   // publish before packing
 
-  // ---- quantise (Lerc2.h:357-376), pack, OR into the staging image (WriteTile, Lerc2.cpp:1949-2021)
-  if (rowAct) {
-    const uint8_t flag = (uint8_t)((((j0 >> 3) & 15) << 2) & 0x38);     // version 6, no depth delta (Lerc2.cpp:1955-1958)
-    if (mode == BEM_ZERO) { if (r == 0) { const uint32_t H[1] = {(uint32_t)(flag | 2)}; orBits<1>(stage, byte0 * 8, H, 8); } }
-    else if (mode == BEM_RAW) {
-      if (r == 0) { const uint32_t H[1] = {(uint32_t)flag}; orBits<1>(stage, byte0 * 8, H, 8); }
-      uint32_t R[16]; rawRowBits<T>(v, w, R);
-      const uint32_t bitOff = (byte0 + 1 + (uint32_t)(r * w) * (uint32_t)sizeof(T)) * 8;
-      if (sizeof(T) == 8) orBits<16>(stage, bitOff, R, w * 64);
-      else { uint32_t R8[8];
+  // running image-global facts and checksum partials of this thread
+  K gMin = keyMaxValue<K>(), gMax = 0;
+  unsigned int myFlags = 0;
+  unsigned long long fa = 0, fd = 0;
+  bool overflow = false;
+  uint32_t prevBytes = 0;
+
+  // geometry + pixel row of a tile for this lane
+  auto tileGeom = [&](int tile, int tyT, int segT, int& ty, int& tx, int& h, int& w, bool& act) {
+    ty = tyT; tx = segT * TB + b;
+    act = tile < nTiles && tx < a.nTx;
+    h = act ? min(8, a.nRows - ty * 8) : 0; w = act ? min(8, a.nCols - tx * 8) : 0;
+  };
+  const int stepTy = (int)gridDim.x / tpr, stepSeg = (int)gridDim.x - stepTy * tpr;   // tile += gridDim.x in (block row, segment) form
+  FastRow<T> cur, nxt;
+  int ty, tx, h, w; bool act;
+  int tile = blockIdx.x;
+  int tyT = tile / tpr, segT = tile - tyT * tpr;
+  tileGeom(tile, tyT, segT, ty, tx, h, w, act);
 #pragma unroll
-             for (int j = 0; j < 8; j++) R8[j] = R[j];
-             orBits<8>(stage, bitOff, R8, w * 8 * (int)sizeof(T)); }
-    } else {
-      const int osz = dtSize(dtUsed);
-      if (r == 0) {                                                     // flag | offset | [numBits byte | count]
-        const unsigned long long ob = offsetBits(zMin, dtUsed);
-        unsigned long long lo64 = (unsigned long long)(flag | (maxElem == 0 ? 3 : 1) | (tc << 6)) | (ob << 8);
-        unsigned long long hi64 = osz == 8 ? (ob >> 56) : 0;
-        int nbytes = 1 + osz;                                           // 2, 3, 5 or 9
-        if (maxElem > 0) {
-          const unsigned long long two = (unsigned long long)(nb | (2 << 6)) | ((unsigned long long)n << 8);   // count < 256: one byte, code 2
-          if (nbytes < 8) lo64 |= two << (8 * nbytes); else hi64 |= two << (8 * (nbytes - 8));
-          nbytes += 2;
-        }
-        const uint32_t H[3] = {(uint32_t)lo64, (uint32_t)(lo64 >> 32), (uint32_t)hi64};
-        orBits<3>(stage, byte0 * 8, H, nbytes * 8);
+  for (int k = 0; k < 8; k++) cur.v[k] = (T)0;
+  if (act && r < h) loadRow8<T>(data + (size_t)(ty * 8 + r) * a.nCols + tx * 8, w, vecOk && w == 8, cur.v);
+  __syncthreads();                                               // staging zeroed
+
+  for (int it = 0; tile < nTiles; it++, tile += gridDim.x) {
+    uint32_t* stage = stageRaw + (size_t)(it & 1) * NQ * 4 + 4;  // tile-local byte 0 of this tile's output image
+    // ---- prefetch the next tile's pixels
+    int nty, ntx, nh, nw; bool nact;
+    tyT += stepTy; segT += stepSeg; if (segT >= tpr) { segT -= tpr; tyT++; }
+    tileGeom(tile + gridDim.x, tyT, segT, nty, ntx, nh, nw, nact);
+#pragma unroll
+    for (int k = 0; k < 8; k++) nxt.v[k] = (T)0;
+    if (nact && r < nh) loadRow8<T>(data + (size_t)(nty * 8 + r) * a.nCols + ntx * 8, nw, vecOk && nw == 8, nxt.v);
+
+    // ---- block statistics and coding choice
+    const int j0 = tx * 8, n = h * w;
+    int mode = BEM_SIMPLE, nb = 0, tc = 0, dtUsed = DT, nBytes = 0; uint32_t maxElem = 0; double zMin = 0; T lo = (T)0;
+    bool hot = false;
+    if (isFlt && sizeof(T) == 4) {
+      // hot path test for full 8x8 float blocks coded "bit-stuffed, offset as float/short/byte"
+      float fv[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) memcpy(&fv[k], &cur.v[k], 4);
+      float mn = fminf(fminf(fminf(fv[0], fv[1]), fminf(fv[2], fv[3])), fminf(fminf(fv[4], fv[5]), fminf(fv[6], fv[7])));
+      float mx = fmaxf(fmaxf(fmaxf(fv[0], fv[1]), fmaxf(fv[2], fv[3])), fmaxf(fmaxf(fv[4], fv[5]), fmaxf(fv[6], fv[7])));
+      float t0 = 0.f;                                              // NaN iff some value is NaN or +-Inf
+#pragma unroll
+      for (int k = 0; k < 8; k++) t0 = __fmaf_rn(fv[k], 0.f, t0);
+      int same = 0;
+#pragma unroll
+      for (int k = 1; k < 8; k++) same += (fv[k] == fv[k - 1]) ? 1 : 0;
+      const float up = __shfl_up_sync(FULL, fv[7], 1, 8);
+      same += (fv[0] == (r == 0 ? 0.f : up)) ? 1 : 0;
+      const bool full = act && h == 8 && w == 8;
+      uint32_t kmn = toKey(mn), kmx = toKey(mx);
+      int nonFinite = (t0 != t0) ? 1 : 0;
+#pragma unroll
+      for (int m = 1; m < 8; m <<= 1) {                              // 8-lane groups: xor shuffles stay inside the group
+        const uint32_t omn = __shfl_xor_sync(FULL, kmn, m), omx = __shfl_xor_sync(FULL, kmx, m);
+        kmn = omn < kmn ? omn : kmn; kmx = omx > kmx ? omx : kmx;
+        const int pk = __shfl_xor_sync(FULL, same | (nonFinite << 16), m);
+        same += pk & 0xffff; nonFinite |= pk >> 16;
       }
-      if (maxElem > 0) {
-        uint32_t q[8];
-        bool done = false;
-        if constexpr (!isFlt) {
-          if (a.intLossless) {
+      const bool finite = nonFinite == 0;
+      const float lof = fromKey<float>(kmn), hif = fromKey<float>(kmx);
+      const double zMn = (double)lof, zMx = (double)hif;
+      const double mv = __dmul_rn(__dsub_rn(zMx, zMn), a.scale);
+      const uint32_t me = roundToUInt(mv);
+      const int nbh = bitLength(me);
+      const bool lutCand = (zMx > __dadd_rn(zMn, a.maxZErr3)) && (2 * same > 64);
+      hot = full && finite && !(mv > (double)a.maxQ) && me > 0 && nbh <= 16 && !lutCand && !(lof == 0.f && hif == 0.f);
+      hot = __all_sync(FULL, hot || !act) && __any_sync(FULL, act);
+      if (hot && act) {
+        memcpy(&lo, &lof, 4); zMin = zMn; maxElem = me; nb = nbh;
+        // offset in the smallest type that holds it (Lerc2.h:457-542, float row)
+        const bool isInt = lof == truncf(lof);
+        tc = (isInt && lof >= 0.f && lof <= 255.f) ? 2 : ((isInt && lof >= -32768.f && lof <= 32767.f) ? 1 : 0);
+        dtUsed = tc == 0 ? DT_Float : (tc == 1 ? DT_Short : DT_Byte);
+        nBytes = 1 + (4 >> tc) + 2 + 8 * nb;
+        gMin = kmn < gMin ? (K)kmn : gMin; gMax = kmx > gMax ? (K)kmx : gMax;
+        if (!(flagsSeen & FASTF_NOT_INT) && !(myFlags & FASTF_NOT_INT)) {          // all-integer test (Lerc.h:248)
+          bool ni = false;
 #pragma unroll
-            for (int k = 0; k < 8; k++) q[k] = k < w ? (uint32_t)((long long)v[k] - (long long)lo) : 0u;
-            done = true;
+          for (int k = 0; k < 8; k++) ni |= fv[k] != truncf(fv[k]);
+          if (ni) myFlags |= FASTF_NOT_INT;
+        }
+      }
+    }
+    if (!hot) {
+      unsigned int fl = 0; K kmin, kmax;
+#pragma unroll
+      for (int k = 0; k < 8; k++) sRow[tid * 8 + k] = cur.v[k];
+      fastGenericChoice<T>(a, sRow + tid * 8, h, w, r, act, nBytes, mode, nb, tc, dtUsed, maxElem, zMin, lo, fl, kmin, kmax);
+      myFlags |= fl;
+      if (act) { gMin = kmin < gMin ? kmin : gMin; gMax = kmax > gMax ? kmax : gMax; }
+      if (isFlt && act && r < h && !(flagsSeen & FASTF_NOT_INT) && !(myFlags & FASTF_NOT_INT)) {
+        bool ni = false;
+#pragma unroll
+        for (int k = 0; k < 8; k++) ni |= k < w && (sizeof(T) == 4 ? ((float)cur.v[k] != truncf((float)cur.v[k])) : ((double)cur.v[k] != trunc((double)cur.v[k])));
+        if (ni) myFlags |= FASTF_NOT_INT;
+      }
+    }
+    if (r == 0) sLen[it & 1][b] = (uint32_t)nBytes;
+    __syncthreads();                                             // block lengths visible (and the previous tile's flush is over)
+    if (it > 0) {  // zero what the previous tile used of its image; that image is packed into again by the next tile
+      const int nz = (((int)prevBytes + 15) >> 4) + 3;
+      uint4* img = (uint4*)(stageRaw + (size_t)((it - 1) & 1) * NQ * 4);
+      for (int i = tid; i < nz && i < NQ; i += 256) img[i] = make_uint4(0, 0, 0, 0);
+    }
+
+    // ---- tile-local byte offsets: every warp scans the 32 lengths itself
+    const uint32_t myLen = sLen[it & 1][lane];
+    uint32_t inc = myLen;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) { const uint32_t o = __shfl_up_sync(FULL, inc, s); if (lane >= s) inc += o; }
+    const uint32_t tileBytes = __shfl_sync(FULL, inc, 31);
+    const uint32_t byte0 = __shfl_sync(FULL, inc - myLen, b);
+    if (tid == 0) st[tile] = (tile == 0 ? ST_P : ST_A) | (unsigned long long)tileBytes;   // publish before packing
+
+    // ---- quantise (Lerc2.h:357-376), pack, OR into the staging image (WriteTile, Lerc2.cpp:1949-2021)
+    if (hot) {
+      if (act) {
+        const int osz = 4 >> tc;
+        if (r == 0) {                                              // flag | offset | numBits byte | count
+          const uint32_t flag = (uint32_t)((((j0 >> 3) & 15) << 2) & 0x38);
+          const unsigned long long ob = offsetBits(zMin, dtUsed);
+          unsigned long long hd = (unsigned long long)(flag | 1 | (tc << 6)) | (ob << 8);
+          hd |= ((unsigned long long)(nb | (2 << 6)) | (64ull << 8)) << (8 * (1 + osz));
+          const uint32_t H[2] = {(uint32_t)hd, (uint32_t)(hd >> 32)};
+          orBits<2>(stage, byte0 * 8, H, (3 + osz) * 8);
+        }
+        float fv[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) memcpy(&fv[k], &cur.v[k], 4);
+        uint32_t q[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) q[k] = quantizeOne((double)fv[k], zMin, a.scale);
+        // 8 values of nb <= 16 bits -> 128 bits
+        const unsigned long long p0 = q[0] | ((unsigned long long)q[1] << nb), p1 = q[2] | ((unsigned long long)q[3] << nb);
+        const unsigned long long p2 = q[4] | ((unsigned long long)q[5] << nb), p3 = q[6] | ((unsigned long long)q[7] << nb);
+        const int s2 = 2 * nb, s4 = 4 * nb;
+        const unsigned long long h0 = p0 | (p1 << s2), h1 = p2 | (p3 << s2);      // 4 nb <= 64 bits each
+        const unsigned long long r0 = s4 == 64 ? h0 : (h0 | (h1 << s4)), r1 = s4 == 64 ? h1 : (h1 >> (64 - s4));
+        const uint32_t R[4] = {(uint32_t)r0, (uint32_t)(r0 >> 32), (uint32_t)r1, (uint32_t)(r1 >> 32)};
+        orBits<4>(stage, (byte0 + (uint32_t)(osz + 3) + (uint32_t)(r * nb)) * 8, R, 8 * nb);
+      }
+    } else if (act) {
+      fastGenericEmit<T>(a, stage, sRow + tid * 8, h, w, r, j0, byte0, mode, nb, tc, dtUsed, maxElem, zMin, lo);
+    }
+
+    // ---- decoupled look-back (warp 0) for the tile's global byte offset
+    if (warp == 0) {
+      unsigned long long excl = 0;
+      if (tile > 0) {
+        long long base = (long long)tile - 1;
+        for (;;) {
+          const long long idx = base - lane;
+          unsigned long long s = ST_P;                                  // virtual tiles before 0: prefix 0
+          if (idx >= 0) { do { s = st[idx]; } while ((s >> 62) == 0); }
+          const unsigned isP = __ballot_sync(FULL, (s >> 62) == 2);
+          const int firstP = isP ? __ffs(isP) - 1 : 32;
+          unsigned long long contrib = (lane <= firstP && idx >= 0) ? (s & VAL) : 0;
+#pragma unroll
+          for (int m = 16; m; m >>= 1) contrib += __shfl_xor_sync(FULL, contrib, m);
+          excl += contrib;
+          if (isP) break;
+          base -= 32;
+        }
+        if (lane == 0) st[tile] = ST_P | (excl + tileBytes);
+      }
+      if (lane == 0) {
+        sTileOff = excl;
+        if (tile == nTiles - 1) a.res->totalBytes = excl + tileBytes;
+      }
+    }
+    __syncthreads();                                             // staging image complete, tile offset known
+
+    // ---- staging -> HBM in 16-byte chunks aligned to the GLOBAL address (the staging image is re-aligned with
+    // funnel shifts), Fletcher-32 partial sums of the same words (bytes outside the tile are zero in the image);
+    // every chunk read is zeroed again for the tile after next
+    const unsigned long long tileOff = sTileOff;
+    {
+      uint8_t* gTile = a.stream + tileOff;
+      const bool fits = tileOff + tileBytes <= a.streamCap;
+      if (!fits) overflow = true;
+      const int pad = (int)((uintptr_t)gTile & 15);
+      const int nChunks = (pad + (int)tileBytes + 15) >> 4;
+      const int bs8 = ((-pad) & 3) * 8;
+      for (int cI = tid; cI < nChunks; cI += 256) {
+        const int s0 = cI * 16 - pad;                                     // tile-local byte of the chunk's first byte (>= -15)
+        const int wi = s0 >> 2;                                           // floor
+        uint32_t x[5];
+#pragma unroll
+        for (int k = 0; k < 5; k++) x[k] = stage[wi + k];
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) o[k] = __funnelshift_r(x[k], x[k + 1], bs8);
+        if (fits) {
+          if (s0 >= 0 && s0 + 16 <= (int)tileBytes) *(uint4*)(gTile + s0) = make_uint4(o[0], o[1], o[2], o[3]);
+          else {
+#pragma unroll
+            for (int j = 0; j < 16; j++) if (s0 + j >= 0 && s0 + j < (int)tileBytes) gTile[s0 + j] = (uint8_t)(o[j >> 2] >> (8 * (j & 3)));
           }
         }
-        if (!done) {
+        // big-endian 16-bit words at even region offsets (Lerc2.cpp:1037-1064)
+        const long long r0 = a.regionOff + (long long)tileOff + s0;
+        const unsigned par = (unsigned)(r0 & 1);
+        const uint32_t w0 = (uint32_t)((unsigned long long)(r0 + 16) >> 1) % 65535u + 65535u - 8u;   // word index of byte r0 - par (mod 65535)
+        uint32_t S = 0, S1 = 0, prev = 0;
 #pragma unroll
-          for (int k = 0; k < 8; k++) q[k] = k < w ? quantizeOne((double)v[k], zMin, a.scale) : 0u;
+        for (int k = 0; k < 5; k++) {
+          const uint32_t cw = k < 4 ? o[k] : 0u;
+          const uint32_t y = __funnelshift_l(prev, cw, par * 8);        // bytes shifted up by one when the chunk starts at an odd offset
+          const uint32_t pw = __byte_perm(y, 0, 0x2301);                // low half = first BE word, high half = second
+          const uint32_t wlo = pw & 0xffffu, whi = pw >> 16;
+          S += wlo + whi; S1 += (uint32_t)(2 * k) * (wlo + whi) + whi;
+          prev = cw;
         }
-        uint32_t R[8];
-        packRow8(q, nb, R);
-        orBits<8>(stage, (byte0 + (uint32_t)(osz + 3)) * 8 + (uint32_t)(r * w * nb), R, w * nb);
+        fa += S; fd += (unsigned long long)w0 * S + S1;
       }
     }
+    prevBytes = tileBytes;
+    // ---- next tile
+    cur = nxt; ty = nty; tx = ntx; h = nh; w = nw; act = nact;
   }
 
-  // ---- image-global facts of this warp
-  {
-    K gMin = act ? kmin : keyMaxValue<K>(), gMax = act ? kmax : (K)0;
+  // ---- image-global facts and checksum partials of this CTA
 #pragma unroll
-    for (int m = 8; m < 32; m <<= 1) {
-      const K omin = shflXorK<K>(gMin, m), omax = shflXorK<K>(gMax, m);
-      gMin = omin < gMin ? omin : gMin; gMax = omax > gMax ? omax : gMax;
-    }
-    myFlags = __reduce_or_sync(FULL, myFlags);
-    if (lane == 0) { sKMin[warp] = (unsigned long long)gMin; sKMax[warp] = (unsigned long long)gMax; sFlg[warp] = myFlags; }
+  for (int m = 1; m < 32; m <<= 1) {
+    const K omin = shflXorK<K>(gMin, m), omax = shflXorK<K>(gMax, m);
+    gMin = omin < gMin ? omin : gMin; gMax = omax > gMax ? omax : gMax;
   }
-
-  // ---- decoupled look-back (warp 0) for the tile's global byte offset
-  if (warp == 0) {
-    unsigned long long excl = 0;
-    if (tile > 0) {
-      long long base = (long long)tile - 1;
-      for (;;) {
-        const long long idx = base - lane;
-        unsigned long long s = ST_P;                                    // virtual tiles before 0: prefix 0
-        if (idx >= 0) { do { s = st[idx]; } while ((s >> 62) == 0); }
-        const unsigned isP = __ballot_sync(FULL, (s >> 62) == 2);
-        const int firstP = isP ? __ffs(isP) - 1 : 32;
-        unsigned long long contrib = (lane <= firstP && idx >= 0) ? (s & VAL) : 0;
-#pragma unroll
-        for (int m = 16; m; m >>= 1) contrib += __shfl_xor_sync(FULL, contrib, m);
-        excl += contrib;
-        if (isP) break;
-        base -= 32;
-      }
-      if (lane == 0) st[tile] = ST_P | (excl + tileBytes);
-    }
-    if (lane == 0) {
-      sTileOff = excl;
-      if ((long long)(tile + 1) * TB >= nBlocks) a.res->totalBytes = excl + tileBytes;
-    }
-  }
-  __syncthreads();
-
-  // ---- staging -> HBM in 16-byte chunks aligned to the GLOBAL address (the staging image is re-aligned with
-  // funnel shifts), Fletcher-32 partial sums of the same words (bytes outside the tile are zero in the image)
-  const unsigned long long tileOff = sTileOff;
-  unsigned long long fa = 0, fd = 0;
-  if (tileOff + tileBytes <= a.streamCap) {
-    uint8_t* gTile = a.stream + tileOff;
-    const int pad = (int)((uintptr_t)gTile & 15);
-    const int nChunks = (pad + (int)tileBytes + 15) >> 4;
-    const int bs8 = ((-pad) & 3) * 8;
-    for (int cI = tid; cI < nChunks; cI += 256) {
-      const int s0 = cI * 16 - pad;                                     // tile-local byte of the chunk's first byte (>= -15)
-      const int wi = s0 >> 2;                                           // floor
-      uint32_t x[5];
-#pragma unroll
-      for (int k = 0; k < 5; k++) x[k] = stage[wi + k];
-      uint32_t o[4];
-#pragma unroll
-      for (int k = 0; k < 4; k++) o[k] = __funnelshift_r(x[k], x[k + 1], bs8);
-      if (s0 >= 0 && s0 + 16 <= (int)tileBytes) *(uint4*)(gTile + s0) = make_uint4(o[0], o[1], o[2], o[3]);
-      else {
-#pragma unroll
-        for (int j = 0; j < 16; j++) if (s0 + j >= 0 && s0 + j < (int)tileBytes) gTile[s0 + j] = (uint8_t)(o[j >> 2] >> (8 * (j & 3)));
-      }
-      // big-endian 16-bit words at even region offsets (Lerc2.cpp:1037-1064)
-      const long long r0 = a.regionOff + (long long)tileOff + s0;
-      const unsigned par = (unsigned)(r0 & 1);
-      const uint32_t w0 = (uint32_t)(((r0 - par) >> 1) % 65535);
-      uint32_t S = 0, S1 = 0, prev = 0;
-#pragma unroll
-      for (int k = 0; k < 5; k++) {
-        const uint32_t cur = k < 4 ? o[k] : 0u;
-        const uint32_t y = __funnelshift_l(prev, cur, par * 8);        // bytes shifted up by one when the chunk starts at an odd offset
-        const uint32_t pw = __byte_perm(y, 0, 0x2301);                  // low half = first BE word, high half = second
-        const uint32_t wlo = pw & 0xffffu, whi = pw >> 16;
-        S += wlo + whi; S1 += (uint32_t)(2 * k) * (wlo + whi) + whi;
-        prev = cur;
-      }
-      fa += S; fd += (unsigned long long)w0 * S + S1;
-    }
-  } else if (tid == 0) atomicOr(&a.res->flags, FASTF_OVERFLOW);
+  if (overflow) myFlags |= FASTF_OVERFLOW;
+  myFlags = __reduce_or_sync(FULL, myFlags);
   fa %= 65535ull; fd %= 65535ull;
 #pragma unroll
   for (int m = 16; m; m >>= 1) { fa += __shfl_xor_sync(FULL, fa, m); fd += __shfl_xor_sync(FULL, fd, m); }
-  if (lane == 0) { sFA[warp] = fa; sFD[warp] = fd; }
+  if (lane == 0) { sKMin[warp] = (unsigned long long)gMin; sKMax[warp] = (unsigned long long)gMax; sFlg[warp] = myFlags; sFA[warp] = fa; sFD[warp] = fd; }
   __syncthreads();
   if (tid == 0) {
     unsigned long long A = 0, D = 0, kMin = ~0ull, kMax = 0; unsigned int fl = 0;
     for (int i = 0; i < 8; i++) { A += sFA[i]; D += sFD[i]; kMin = sKMin[i] < kMin ? sKMin[i] : kMin; kMax = sKMax[i] > kMax ? sKMax[i] : kMax; fl |= sFlg[i]; }
-    if (A | D) { atomicAdd(&a.res->fletA[tile % FAST_SLOTS], A); atomicAdd(&a.res->fletD[tile % FAST_SLOTS], D % 65535ull); }
+    if (A | D) { atomicAdd(&a.res->fletA[blockIdx.x % FAST_SLOTS], A); atomicAdd(&a.res->fletD[blockIdx.x % FAST_SLOTS], D % 65535ull); }
     if (kMax >= kMin) {
       if (~kMin > negMinSeen) atomicMax(&a.res->negMinKey, ~kMin);
       if (kMax > maxSeen) atomicMax(&a.res->maxKey, kMax);
