@@ -1,0 +1,64 @@
+"""Tile sharding and stream gathering for tiled rasters coded on several GPUs (BASELINE config 5: a 65536 x 65536
+raster as 256 x 256 tiles, every tile its own standard Lerc2 blob).
+
+Tiles are independent objects, so the codec needs no data-path collective: rank r codes the contiguous tile range
+shard_tiles(n_tiles, r, world).  Only the finished streams are exchanged: one fixed-size all-gather of the per-tile byte
+counts, an exclusive prefix sum for the global offsets, and one padded all-gather of the payloads (NCCL has no
+all-gather-v).  Works with any torch.distributed backend (nccl on GPUs, gloo in tests/test_tiles_gather.py).
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_tiles(n_tiles, rank, world):
+    """contiguous, ordered tile range [lo, hi) of `rank`; the first n_tiles % world ranks hold one tile more"""
+    base, extra = divmod(n_tiles, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def offsets_from_sizes(sizes):
+    """exclusive prefix sum: byte offset of every tile stream in the concatenated container (+ total as last entry)"""
+    sizes = torch.as_tensor(sizes, dtype=torch.int64)
+    out = torch.zeros(sizes.numel() + 1, dtype=torch.int64, device=sizes.device)
+    out[1:] = torch.cumsum(sizes, 0)
+    return out
+
+
+def gather_streams(local_blobs, n_tiles, group=None, device=None):
+    """local_blobs: the tile streams (bytes / uint8 tensors) of this rank's shard, in tile order.
+    Returns (container uint8 tensor with all n_tiles streams back to back in tile order, int64 offsets[n_tiles + 1])."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    lo, hi = shard_tiles(n_tiles, rank, world)
+    assert len(local_blobs) == hi - lo, (len(local_blobs), lo, hi)
+    if device is None:
+        device = local_blobs[0].device if (local_blobs and torch.is_tensor(local_blobs[0])) else torch.device("cpu")
+    blobs = [b if torch.is_tensor(b) else torch.frombuffer(bytearray(b), dtype=torch.uint8) for b in local_blobs]
+    blobs = [b.to(device) for b in blobs]
+    max_tiles = -(-n_tiles // world)
+    my_sizes = torch.zeros(max_tiles, dtype=torch.int64, device=device)
+    if blobs:
+        my_sizes[: len(blobs)] = torch.tensor([b.numel() for b in blobs], dtype=torch.int64, device=device)
+    if world == 1:
+        all_sizes = [my_sizes]
+    else:
+        all_sizes = [torch.empty_like(my_sizes) for _ in range(world)]
+        dist.all_gather(all_sizes, my_sizes, group=group)
+    # per-tile sizes in global tile order
+    sizes = torch.cat([all_sizes[r][: shard_tiles(n_tiles, r, world)[1] - shard_tiles(n_tiles, r, world)[0]] for r in range(world)])
+    offsets = offsets_from_sizes(sizes)
+    rank_bytes = [int(all_sizes[r].sum().item()) for r in range(world)]
+    pad = max(rank_bytes) if rank_bytes else 0
+    mine = torch.zeros(max(pad, 1), dtype=torch.uint8, device=device)
+    if blobs:
+        cat = torch.cat(blobs)
+        mine[: cat.numel()] = cat
+    if world == 1:
+        parts = [mine]
+    else:
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine, group=group)
+    container = torch.cat([parts[r][: rank_bytes[r]] for r in range(world)])
+    assert container.numel() == int(offsets[-1].item())
+    return container, offsets
