@@ -37,6 +37,9 @@ WORKLOADS = {
 }
 
 
+METRIC = {"c2": "Gpixels/s encode+decode float32 @ maxZError=0.01; achieved HBM GB/s vs peak", "c4": "Gpixels/s encode+decode uint8 nDepth=3 lossless"}
+
+
 def make_raster(workload, seed):
     from cases import c2_raster, c4_raster
     rows, cols, depth, dt, mz, _ = WORKLOADS[workload]
@@ -146,7 +149,7 @@ def main():
         if rank != 0:
             return
         base, ms = cpu_reference_run(args.workload, seconds_budget=max(10.0, 2.0 * args.steps))
-        line = {"impl": "reference", "metric": "Gpixels/s encode+decode", "value": base["value"], "unit": "Gpixels/s", "n_gpus": args.gpus,
+        line = {"impl": "reference", "metric": METRIC[args.workload], "value": base["value"], "unit": "Gpixels/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64" if dt >= 6 else "int32", "data": "synthetic", "config": {"workload": desc, "sample": base["sample"]},
                 "cpu_baseline": base, "e2e": {"value": base["value"], "unit": "Gpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -204,18 +207,30 @@ def main():
         dist.barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    t_s = time.perf_counter()
+    while len(sampler.rows) < 2 and time.perf_counter() - t_s < 3.0:      # nvidia-smi needs a moment to start; keep the GPU under the same load meanwhile
+        step_device(0)
+    torch.cuda.synchronize()
     launches0 = lerc_b200.stats()[0]
     torch.cuda.synchronize()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev_all = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    ev_all[0].record(stream)
     for i in range(args.steps):
         ev[i][0].record(stream)
         step_device(warm + i)
         ev[i][1].record(stream)
+    ev_all[1].record(stream)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     launches = lerc_b200.stats()[0] - launches0
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    t_s = time.perf_counter()
+    n_before = len(sampler.rows)
+    while len(sampler.rows) < n_before + 3 and time.perf_counter() - t_s < 1.0:   # the timed region is only milliseconds long: keep sampling under the same load
+        step_device(0)
+    torch.cuda.synchronize()
+    dev_ms = ev_all[0].elapsed_time(ev_all[1])          # one bracket around exactly K steps (host gaps between the calls included)
     if os.environ.get("BENCH_DEBUG"):
         print("per-step ms:", [round(a.elapsed_time(b), 3) for a, b in ev], "stats", lerc_b200.stats(), file=sys.stderr)
     clocks = sampler.stop()
@@ -314,7 +329,7 @@ def main():
         cpu = None
         if world >= 1 and not args.no_cpu_baseline and args.gpus == 1:
             cpu, _ = cpu_reference_run(args.workload, seconds_budget=15.0)
-        line = {"metric": "Gpixels/s encode+decode float32 @ maxZError=0.01; achieved HBM GB/s vs peak" if args.workload == "c2" else "Gpixels/s encode+decode",
+        line = {"metric": METRIC[args.workload],
                 "value": value, "unit": "Gpixels/s", "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64" if dt >= 6 else "int32", "data": "synthetic",
                 "config": {"workload": desc, "generator": "tests/cases.py", "blob_bytes": blob_bytes, "compression_ratio": raw_bytes / blob_bytes,
