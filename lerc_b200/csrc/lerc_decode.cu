@@ -337,14 +337,12 @@ bool launchDecodeFast(Context* ctx, const HeaderInfo& hd, const uint8_t* dStream
   if (hd.nDepth != 1 || hd.microBlockSize != 8 || hd.version < 3 || (long long)hd.numValidPixel != (long long)hd.nCols * hd.nRows) return false;
   if (streamLen == 0 || streamLen >= 0xfff00000ull || std::getenv("LERC_B200_NO_FAST")) return false;
   const int nSub = (int)((streamLen + FD_SUB - 1) / FD_SUB);
-  const int regTarget = 2 * smCount();                          // k_dec_blocks: two 512-thread CTAs per SM
-  const int subPerReg = (nSub + regTarget - 1) / regTarget;
+  const int subPerReg = FD_REG;
   const int nReg = (nSub + subPerReg - 1) / subPerReg;
-  const size_t smemB = fastDecodeBlocksSmem<T>(subPerReg, nReg), smemW = (size_t)subPerReg * FD_CAND * sizeof(FdEntry);
-  if (smemB + 1024 > 227 * 1024 || smemW + 1024 > 227 * 1024) return false;
-  const size_t szCand = (size_t)nSub * FD_CAND * sizeof(FdCand), szN = ((size_t)nSub + 255) & ~(size_t)255, szLens = (size_t)nSub * FD_CAND * 256,
-               szSub = (size_t)nSub * FD_CAND * sizeof(FdEntry), szReg = (size_t)nReg * FD_CAND * sizeof(FdEntry);
-  uint8_t* scratch = (uint8_t*)ctx->arena.alloc(szLens + szCand + szSub + szReg + szN + 256);
+  const size_t smemB = fastDecodeBlocksSmem<T>();
+  const size_t szCand = (size_t)nSub * FD_CAND * sizeof(FdCand), szN = ((size_t)nSub + 255) & ~(size_t)255, szLens = (size_t)nSub * FD_CAND * FD_LENS,
+               szSub = (size_t)nReg * FD_REG * FD_CAND * sizeof(FdEntry), szReg = (size_t)nReg * FD_CAND * sizeof(FdEntry), szEnt = ((size_t)(nReg + 1) * 8 + 255) & ~(size_t)255;
+  uint8_t* scratch = (uint8_t*)ctx->arena.alloc(szLens + szCand + szSub + szReg + szEnt + szN + 256);
   if (!scratch) return false;
   FastDecArgs fa;
   fa.stream = dStream; fa.streamLen = streamLen;
@@ -356,13 +354,14 @@ bool launchDecodeFast(Context* ctx, const HeaderInfo& hd, const uint8_t* dStream
   fa.cand = (FdCand*)sp; sp += szCand;
   fa.subTab = (FdEntry*)sp; sp += szSub;
   fa.regTab = (FdEntry*)sp; sp += szReg;
+  fa.regEntry = (uint32_t*)sp; sp += szEnt;
   fa.nCand = sp;
   fa.status = dStatus;
-  static size_t attrB = 0, attrW = 0;
-  if (smemB > attrB) { if (!cudaOk(cudaFuncSetAttribute(k_dec_blocks<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB), "smem attribute")) return false; attrB = smemB; }
-  if (smemW > attrW && smemW > 48 * 1024) { if (!cudaOk(cudaFuncSetAttribute(k_dec_walk<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemW), "smem attribute")) return false; attrW = smemW; }
+  static bool attrSet = false;
+  if (!attrSet) { if (!cudaOk(cudaFuncSetAttribute(k_dec_blocks<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB), "smem attribute")) return false; attrSet = true; }
   LERC_LAUNCH(ctx, k_dec_candidates<T>, (nSub + 7) / 8, 256, 0, fa);
-  LERC_LAUNCH(ctx, k_dec_walk<T>, nReg, 512, smemW, fa);
+  LERC_LAUNCH(ctx, k_dec_walk<T>, nReg, 256, 0, fa);
+  LERC_LAUNCH(ctx, k_dec_resolve, 1, 1024, 0, fa, fa.nTx * fa.nTy);
   LERC_LAUNCH(ctx, k_dec_blocks<T>, nReg, FD_DWARPS * 32, smemB, fa);
   return cudaOk(cudaGetLastError(), "launch fast decode");
 }

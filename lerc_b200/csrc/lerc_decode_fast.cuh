@@ -3,7 +3,7 @@
 //
 // The stream has no index: a block's length is only known from its own header bytes (ReadTile, Lerc2.cpp:2025-2230;
 // BitStuffer2::Decode, BitStuffer2.cpp:159-258), so the reference walks it serially.  Here the block boundaries are
-// found speculatively, in three kernels on one stream:
+// found speculatively, in four kernels on one stream:
 //   k_dec_candidates  the stream is cut into 4 KB sub-chunks, one warp each.  Every byte position in the first MAXU
 //                     bytes of a sub-chunk that parses as a block header is a candidate entry (32 positions per warp
 //                     step, staged in shared memory); candidates hop from header to header and die on the first
@@ -12,8 +12,8 @@
 //                     L2 (the checksum kernel has just read the blob), recording the unit lengths; result per
 //                     candidate: (entry, exit, #blocks).  Wrong candidates die or merge into the true chain.
 //                     The sub-chunk maps of a region (one CTA) are composed in shared memory -> region map.
-//   k_dec_blocks      every CTA composes the region maps from stream position 0 up to its own region, then its
-//                     sub-chunks' true entries; the recorded lengths of the matching candidate give every block's
+//   k_dec_resolve     one warp composes the region maps in stream order: true (position, block index) of every region.
+//   k_dec_blocks      every CTA (region) resolves its sub-chunks' true entries; the recorded lengths of the matching candidate give every block's
 //                     position, so the blocks decode in parallel: 8 lanes per micro-block, one lane per block row:
 //                     unpack numBits-wide values with funnel shifts, z = offset + q * 2 maxZError in fp64 without
 //                     contraction, min(z, zMax), cast, 128-bit stores.  Every block is re-parsed with its true size and
@@ -28,9 +28,11 @@ namespace lerc {
 
 enum { DECF_FALLBACK = 8 };
 constexpr int FD_SUB = 4096;          // sub-chunk bytes
-constexpr int FD_CAND = 8;            // surviving entry candidates kept per sub-chunk / region
-constexpr int FD_MAXHOP = 248;        // recorded unit lengths per candidate (multiple of 8)
+constexpr int FD_CAND = 16;           // surviving entry candidates kept per sub-chunk / region
+constexpr int FD_MAXHOP = 504;        // recorded unit lengths per candidate (multiple of 8)
+constexpr int FD_LENS = 512;          // bytes reserved per candidate for them
 constexpr uint32_t FD_DEAD = 0xffffffffu;
+constexpr int FD_REG = 16;            // sub-chunks per region (one CTA of k_dec_walk / k_dec_blocks)
 
 struct FdEntry { uint32_t entry, exit, count; };
 struct FdCand { uint16_t entry, pos, cnt, pat; };
@@ -42,9 +44,10 @@ struct FastDecArgs {
   void* data;
   int nSub, subPerReg, nReg;
   FdCand* cand; uint8_t* nCand;          // [nSub][FD_CAND], [nSub]
-  uint8_t* lens;                         // [nSub][FD_CAND][256] unit lengths of each candidate's chain
+  uint8_t* lens;                         // [nSub][FD_CAND][FD_LENS] unit lengths of each candidate's chain
   FdEntry* subTab;                       // [nSub][FD_CAND]
   FdEntry* regTab;                       // [nReg][FD_CAND]
+  uint32_t* regEntry;                    // [nReg + 1][2] true (position, block index) at the start of every region
   int* status;
 };
 
@@ -155,18 +158,46 @@ template <class T> __device__ __forceinline__ T fdCast(double z, double zMax) { 
 // ends the stream (tailRaw bytes).  LUT / wide-count units take the byte-wise parser through `bytes` (16+ readable
 // bytes) when it is not null, and end the chain otherwise.
 template <class T>
+__device__ __noinline__ int fdSlowLen(const uint8_t* bytes, int version) {
+  FdUnit u;
+  return fdParse<T>(bytes, version, 64, false, u) ? u.len : 0;
+}
+template <class T>
 __device__ __forceinline__ int fdHopLen(const FdWin& x, const uint8_t* bytes, int version, long long rest, int tailRaw, int& pat) {
   FdQuick q;
   int rc = fdQuick<T>(x, version, 64, false, q);
   pat = fdPattern((uint32_t)x.lo & 0xff, version);
   int len = q.len;
   if (rc < 0) {
-    FdUnit u;
-    if (bytes && fdParse<T>(bytes, version, 64, false, u)) { len = u.len; rc = 1; } else rc = 0;
+    len = bytes ? fdSlowLen<T>(bytes, version) : 0;
+    rc = len > 0 ? 1 : 0;
   }
   if (rc <= 0) return 0;
   if ((long long)len > rest) return (q.mode == 0 && rest == (long long)tailRaw) ? tailRaw : 0;
   return len;
+}
+
+// One block row of a LUT block / a block with a wide count field (byte-wise parser).  Returns the unit length,
+// 0 when malformed, -2 when a LUT index is out of range.
+template <class T>
+__device__ __noinline__ int fdDecodeSlowRow(const uint8_t* pp, int version, int cells, int r, int h, int w, double invScale, double zMax, T* out) {
+  FdUnit u;
+  if (!fdParse<T>(pp, version, cells, true, u)) return 0;
+  const int dtUsed = offsetTypeFromCode(PixelTraits<T>::code, u.tc);
+  const double offset = offsetFromBits(loadBytesLE(pp + 1, u.osz), dtUsed);
+  const int nbv = u.lut ? u.nbIdx : u.nb;
+  const uint32_t bit0 = (uint32_t)(r * w) * (uint32_t)nbv;
+  bool badIdx = false;
+  for (int kk = 0; kk < 8; kk++) {
+    uint32_t qq = 0;
+    if (kk < w && r < h && nbv > 0) qq = fdExtract(pp + u.pay, bit0 + (uint32_t)(kk * nbv), nbv);
+    if (u.lut) {
+      if (qq > (uint32_t)u.nLut) { badIdx = true; qq = 0; }
+      qq = qq == 0 ? 0u : fdExtract(pp + u.lutPay, (qq - 1) * (uint32_t)u.nb, u.nb);
+    }
+    out[kk] = fdCast<T>(__dadd_rn(offset, __dmul_rn((double)qq, invScale)), zMax);
+  }
+  return badIdx ? -2 : u.len;
 }
 
 // ================= kernel 1: entry candidates of every sub-chunk ===================================
@@ -243,9 +274,8 @@ __global__ void __launch_bounds__(256) k_dec_candidates(FastDecArgs a) {
 // ================= kernel 2: one lane per candidate walks to the end of its sub-chunk ================
 // CTA = region (subPerReg consecutive sub-chunks); afterwards warp 0 composes the region's sub-chunk maps.
 template <class T>
-__global__ void __launch_bounds__(512) k_dec_walk(FastDecArgs a) {
-  extern __shared__ __align__(16) uint8_t smemW[];
-  FdEntry* sTab = (FdEntry*)smemW;                                   // [subPerReg][FD_CAND]
+__global__ void __launch_bounds__(256) k_dec_walk(FastDecArgs a) {
+  __shared__ FdEntry sTab[FD_REG * FD_CAND];                        // [subPerReg <= FD_REG][FD_CAND]
   const int reg = blockIdx.x, tid = threadIdx.x;
   const int sub0 = reg * a.subPerReg, nLocal = max(0, min(a.nSub, sub0 + a.subPerReg) - sub0);
   const int version = a.version;
@@ -266,7 +296,7 @@ __global__ void __launch_bounds__(512) k_dec_walk(FastDecArgs a) {
       int pos = c.entry, cnt = 0, pat = 0;
       bool ok = true;
       unsigned long long acc = 0;
-      uint8_t* lens = a.lens + ((size_t)s * FD_CAND + j) * 256;
+      uint8_t* lens = a.lens + ((size_t)s * FD_CAND + j) * FD_LENS;
       while (pos < subEnd) {
         const unsigned long long gpos = start + (unsigned long long)pos + gd;
         const uint32_t* w = gw + (gpos >> 2);
@@ -304,7 +334,7 @@ __global__ void __launch_bounds__(512) k_dec_walk(FastDecArgs a) {
     FdEntry cur; cur.entry = FD_DEAD; cur.exit = 0; cur.count = 0;
     if (lane < FD_CAND && nLocal > 0) cur = sTab[lane];
     for (int ls = 1; ls < nLocal; ls++) {
-      if (cur.entry != FD_DEAD) {
+      if (cur.entry != FD_DEAD && (unsigned long long)cur.exit < a.streamLen) {      // a chain that reached the end of the stream is complete
         bool found = false;
         for (int e = 0; e < FD_CAND; e++) {
           const FdEntry t = sTab[ls * FD_CAND + e];
@@ -317,23 +347,96 @@ __global__ void __launch_bounds__(512) k_dec_walk(FastDecArgs a) {
   }
 }
 
-// ================= kernel 3: resolve the true chain, decode the blocks ================================
-constexpr int FD_DWARPS = 16;
+// ================= kernel 3: true entry of every region ==============================================
+// Region r's map sends each of its FD_CAND entry positions to (exit position, #blocks); the true chain starts at
+// (position 0, block 0) in region 0.  One CTA of 32 warps; warp w owns the consecutive regions [w*G, (w+1)*G):
+//   A  lanes 16..31 follow the 16 chains that start at the entries of the warp's first region through its G regions
+//      (the match of an exit position against the next region's entries is one __match_any_sync: lanes 0..15
+//      offer the entries, lanes 16..31 their current positions)              -> chunk map in shared memory
+//   B  one thread composes the 32 chunk maps serially                        -> true entry of every chunk
+//   C  every warp walks its regions again with the single true chain         -> regEntry[r] for every region
+static_assert(FD_CAND == 16, "k_dec_resolve pairs 16 entry lanes with 16 chain lanes");
+__global__ void __launch_bounds__(1024) k_dec_resolve(FastDecArgs a, int nBlocks) {
+  __shared__ uint32_t sEnt[32][FD_CAND], sExit[32][FD_CAND], sCnt[32][FD_CAND];
+  __shared__ uint32_t sChunkPos[33], sChunkBlk[33];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = (a.nReg + 31) / 32;
+  const int r0 = warp * G, r1 = min(a.nReg, r0 + G);
+  // ---- A
+  {
+    const int L = lane & 15;
+    uint32_t ent = FD_DEAD, pos = FD_DEAD, cnt = 0;
+    if (r0 < r1) { const FdEntry t = a.regTab[(size_t)r0 * FD_CAND + L]; ent = t.entry; pos = t.exit; cnt = t.count; }
+    bool alive = ent != FD_DEAD;
+    FdEntry nx; nx.entry = FD_DEAD; nx.exit = 0; nx.count = 0;
+    if (r0 + 1 < r1) nx = a.regTab[(size_t)(r0 + 1) * FD_CAND + L];
+    for (int r = r0 + 1; r < r1; r++) {
+      const FdEntry t = nx;                                          // lanes 0..15 and 16..31 hold the same 16 entries
+      if (r + 1 < r1) nx = a.regTab[(size_t)(r + 1) * FD_CAND + L];  // independent of the chains: overlaps the match
+      const bool chain = lane >= 16;
+      const bool active = chain && alive && (unsigned long long)pos < a.streamLen;   // a chain that reached the end of the stream is complete
+      // unique keys for lanes that must not match anything
+      const uint32_t key = chain ? (active ? pos : 0xfffffff0u - lane) : (t.entry != FD_DEAD ? t.entry : 0xffffffd0u - lane);
+      const unsigned m = __match_any_sync(FULL, key) & 0xffffu;
+      const int src = m ? __ffs(m) - 1 : 0;
+      const uint32_t nx = __shfl_sync(FULL, t.exit, src), nc = __shfl_sync(FULL, t.count, src);
+      if (active) { if (m) { pos = nx; cnt += nc; } else alive = false; }
+    }
+    if (lane >= 16) { sEnt[warp][L] = alive ? ent : FD_DEAD; sExit[warp][L] = pos; sCnt[warp][L] = cnt; }
+  }
+  __syncthreads();
+  // ---- B (warp 0: lanes 0..15 offer a chunk's entries, one ballot per chunk)
+  if (warp == 0) {
+    uint32_t pos = 0, blk = 0; bool dead = false;
+    for (int w = 0; w < 32; w++) {
+      if (lane == 0) { sChunkPos[w] = dead ? FD_DEAD : pos; sChunkBlk[w] = blk; }
+      if (w * G >= a.nReg || dead || blk >= (uint32_t)nBlocks) continue;
+      const uint32_t e = lane < FD_CAND ? sEnt[w][lane] : FD_DEAD;
+      const unsigned m = __ballot_sync(FULL, e != FD_DEAD && e == pos);
+      if (!m) { dead = true; continue; }
+      const int src = __ffs(m) - 1;
+      pos = sExit[w][src]; blk += sCnt[w][src];
+    }
+    if (lane == 0) {
+      sChunkPos[32] = dead ? FD_DEAD : pos; sChunkBlk[32] = blk;
+      a.regEntry[2 * a.nReg] = sChunkPos[32]; a.regEntry[2 * a.nReg + 1] = blk;
+      if (dead) atomicOr(a.status, DECF_FALLBACK | 32);
+      else if (blk < (uint32_t)nBlocks) atomicOr(a.status, DECF_FALLBACK | 4096);      // the chain must cover all blocks
+    }
+  }
+  __syncthreads();
+  // ---- C
+  {
+    uint32_t pos = sChunkPos[warp], blk = sChunkBlk[warp];
+    bool dead = pos == FD_DEAD;
+    FdEntry nx; nx.entry = FD_DEAD; nx.exit = 0; nx.count = 0;
+    if (lane < FD_CAND && r0 < r1) nx = a.regTab[(size_t)r0 * FD_CAND + lane];
+    for (int r = r0; r < r1; r++) {
+      const FdEntry t = nx;
+      nx.entry = FD_DEAD;
+      if (lane < FD_CAND && r + 1 < r1) nx = a.regTab[(size_t)(r + 1) * FD_CAND + lane];   // independent of the chain: overlaps the lookup
+      if (lane == 0) { a.regEntry[2 * r] = dead ? FD_DEAD : (blk >= (uint32_t)nBlocks ? FD_DEAD - 1 : pos); a.regEntry[2 * r + 1] = blk; }
+      if (dead || blk >= (uint32_t)nBlocks) continue;
+      const unsigned m = __ballot_sync(FULL, t.entry == pos && t.entry != FD_DEAD);
+      if (!m) { dead = true; continue; }
+      const int src = __ffs(m) - 1;
+      pos = __shfl_sync(FULL, t.exit, src); blk += __shfl_sync(FULL, t.count, src);
+    }
+  }
+}
+
+// ================= kernel 4: true entries of the region's sub-chunks, decode the blocks ================
+constexpr int FD_DWARPS = 8;
 template <class T>
-__global__ void __launch_bounds__(FD_DWARPS * 32, 2) k_dec_blocks(FastDecArgs a) {
+__global__ void __launch_bounds__(FD_DWARPS * 32) k_dec_blocks(FastDecArgs a) {
   constexpr int MAXU = 1 + 64 * (int)sizeof(T);
   constexpr int BUFB = ((FD_SUB + MAXU + 64 + 15) / 16) * 16;       // per-warp staging of one sub-chunk (+ look-ahead)
-  extern __shared__ __align__(16) uint8_t smemD[];
-  // layout: [FD_DWARPS][BUFB] stream staging | uint16 sPos[FD_DWARPS][256] | FdEntry sTab[subPerReg][FD_CAND] | FdEntry sReg[nReg][FD_CAND]
-  //         | uint32 sTrue[subPerReg + 1][3]
-  uint8_t* sp = smemD;
-  uint8_t* bufAll = sp; sp += (size_t)FD_DWARPS * BUFB;
-  uint16_t* sPosAll = (uint16_t*)sp; sp += (size_t)FD_DWARPS * 256 * 2;
-  FdEntry* sTab = (FdEntry*)sp; sp += (size_t)a.subPerReg * FD_CAND * sizeof(FdEntry);
-  FdEntry* sReg = (FdEntry*)sp; sp += (size_t)a.nReg * FD_CAND * sizeof(FdEntry);
-  uint32_t* sTrue = (uint32_t*)sp;
-  __shared__ uint32_t sRegEntry[2];
+  extern __shared__ __align__(16) uint8_t smemD[];                   // [FD_DWARPS][BUFB] stream staging
+  __shared__ uint16_t sPosAll[FD_DWARPS * FD_LENS];
+  __shared__ FdEntry sTab[FD_REG * FD_CAND];
+  __shared__ uint32_t sTrue[(FD_REG + 1) * 3];
   __shared__ int sWhy;
+  uint8_t* bufAll = smemD;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int reg = blockIdx.x;
@@ -341,33 +444,16 @@ __global__ void __launch_bounds__(FD_DWARPS * 32, 2) k_dec_blocks(FastDecArgs a)
   const int nBlocks = a.nTx * a.nTy;
   const int version = a.version;
   if (tid == 0) sWhy = 0;
-  for (int i = tid; i < a.nReg * FD_CAND; i += blockDim.x) sReg[i] = a.regTab[i];
   for (int i = tid; i < nLocal * FD_CAND; i += blockDim.x) sTab[i] = a.subTab[(size_t)sub0 * FD_CAND + i];
-  __syncthreads();
-
-  // ---- true entry of this region: compose the region maps from stream position 0
-  if (warp == 0) {
-    uint32_t pos = 0, blk = 0; bool bad = false;
-    for (int rg = 0; rg < reg && !bad; rg++) {
-      if (blk >= (uint32_t)nBlocks) break;
-      FdEntry t; t.entry = FD_DEAD; t.exit = 0; t.count = 0;
-      if (lane < FD_CAND) t = sReg[(size_t)rg * FD_CAND + lane];
-      const unsigned m = __ballot_sync(FULL, t.entry == pos && t.entry != FD_DEAD);
-      if (!m) { bad = true; break; }
-      const int src = __ffs(m) - 1;
-      pos = __shfl_sync(FULL, t.exit, src); blk += __shfl_sync(FULL, t.count, src);
-    }
-    if (lane == 0) { sRegEntry[0] = bad ? FD_DEAD : pos; sRegEntry[1] = blk; if (bad) sWhy |= 32; }
-  }
   __syncthreads();
   // ---- true entry (position, block index, candidate slot) of every sub-chunk of the region
   if (tid == 0) {
-    uint32_t pos = sRegEntry[0], blk = sRegEntry[1];
+    uint32_t pos = a.regEntry[2 * reg], blk = a.regEntry[2 * reg + 1];
     for (int ls = 0; ls <= nLocal; ls++) {
       sTrue[3 * ls] = pos; sTrue[3 * ls + 1] = blk; sTrue[3 * ls + 2] = 0;
       if (ls == nLocal) break;
       if (pos == FD_DEAD) { for (int k = ls; k <= nLocal; k++) { sTrue[3 * k] = FD_DEAD; sTrue[3 * k + 1] = blk; } break; }
-      if (blk >= (uint32_t)nBlocks) { for (int k = ls; k <= nLocal; k++) { sTrue[3 * k] = FD_DEAD - 1; sTrue[3 * k + 1] = blk; } break; }   // past the last block
+      if (pos == FD_DEAD - 1 || blk >= (uint32_t)nBlocks) { for (int k = ls; k <= nLocal; k++) { sTrue[3 * k] = FD_DEAD - 1; sTrue[3 * k + 1] = blk; } break; }   // past the last block
       bool found = false;
       for (int e = 0; e < FD_CAND; e++) {
         const FdEntry t = sTab[ls * FD_CAND + e];
@@ -383,7 +469,7 @@ __global__ void __launch_bounds__(FD_DWARPS * 32, 2) k_dec_blocks(FastDecArgs a)
   const bool vecOk = ((a.nCols * (int)sizeof(T)) % 16 == 0) && (((uintptr_t)data & 15) == 0);
   const int g = lane >> 3, r = lane & 7;
   uint8_t* buf = bufAll + (size_t)warp * BUFB;
-  uint16_t* sPos = sPosAll + (size_t)warp * 256;
+  uint16_t* sPos = sPosAll + warp * FD_LENS;
   for (int ls = warp; ls < nLocal; ls += FD_DWARPS) {
     const uint32_t pos0 = sTrue[3 * ls], blk0 = sTrue[3 * ls + 1], slot = sTrue[3 * ls + 2];
     if (pos0 >= FD_DEAD - 1) continue;                               // dead chain (reported through sWhy) or past the end
@@ -406,20 +492,25 @@ __global__ void __launch_bounds__(FD_DWARPS * 32, 2) k_dec_blocks(FastDecArgs a)
     }
     // block positions from the recorded unit lengths: sPos[i] = start of block i, sPos[cnt] = exit
     {
-      const uint8_t* lens = a.lens + ((size_t)s * FD_CAND + slot) * 256;
-      const unsigned long long l8 = lane * 8 < cnt ? *(const unsigned long long*)(lens + lane * 8) : 0ull;
-      uint32_t pre[8]; uint32_t sum = 0;
+      const uint8_t* lens = a.lens + ((size_t)s * FD_CAND + slot) * FD_LENS;
+      uint32_t run = pos0 - (uint32_t)s * FD_SUB;
+      for (int base = 0; base <= cnt; base += 256) {                 // 8 lengths per lane and round
+        const int i8 = base + lane * 8;
+        const unsigned long long l8 = i8 < cnt ? *(const unsigned long long*)(lens + i8) : 0ull;
+        uint32_t pre[8]; uint32_t sum = 0;
 #pragma unroll
-      for (int k = 0; k < 8; k++) {
-        const uint32_t c8 = (uint32_t)((l8 >> (8 * k)) & 0xff);
-        pre[k] = sum; sum += (lane * 8 + k < cnt) ? (c8 == 255 ? (uint32_t)MAXU : c8) : 0u;
+        for (int k = 0; k < 8; k++) {
+          const uint32_t c8 = (uint32_t)((l8 >> (8 * k)) & 0xff);
+          pre[k] = sum; sum += (i8 + k < cnt) ? (c8 == 255 ? (uint32_t)MAXU : c8) : 0u;
+        }
+        uint32_t inc = sum;
+#pragma unroll
+        for (int m = 1; m < 32; m <<= 1) { const uint32_t o = __shfl_up_sync(FULL, inc, m); if (lane >= m) inc += o; }
+        const uint32_t mine = run + inc - sum;
+#pragma unroll
+        for (int k = 0; k < 8; k++) if (i8 + k <= cnt) sPos[i8 + k] = (uint16_t)(mine + pre[k]);
+        run += __shfl_sync(FULL, inc, 31);
       }
-      uint32_t inc = sum;
-#pragma unroll
-      for (int m = 1; m < 32; m <<= 1) { const uint32_t o = __shfl_up_sync(FULL, inc, m); if (lane >= m) inc += o; }
-      const uint32_t base = (pos0 - (uint32_t)s * FD_SUB) + inc - sum;
-#pragma unroll
-      for (int k = 0; k < 8; k++) if (lane * 8 + k <= cnt && lane * 8 + k < 256) sPos[lane * 8 + k] = (uint16_t)(base + pre[k]);
     }
     __syncwarp();
     const uint8_t* sb = buf + d;
@@ -488,27 +579,9 @@ __global__ void __launch_bounds__(FD_DWARPS * 32, 2) k_dec_blocks(FastDecArgs a)
               for (int kk = 0; kk < 8; kk++) out[kk] = fdCast<T>(__dadd_rn(offset, __dmul_rn((double)qv[kk], a.invScale)), a.zMax);
             }
           }
-        } else {                                                     // LUT block or wide count field: byte-wise parser
-          FdUnit u;
-          if (!fdParse<T>(sb + p, version, cells, true, u) || u.len > MAXU) { fallback = true; why |= 8192; }
-          else {
-            len = u.len;
-            const uint8_t* pp = sb + p;
-            const int dtUsed = offsetTypeFromCode(PixelTraits<T>::code, u.tc);
-            const double offset = offsetFromBits(loadBytesLE(pp + 1, u.osz), dtUsed);
-            const int nbv = u.lut ? u.nbIdx : u.nb;
-            const uint32_t bit0 = (uint32_t)(r * w) * (uint32_t)nbv;
-#pragma unroll
-            for (int kk = 0; kk < 8; kk++) {
-              uint32_t qq = 0;
-              if (kk < w && r < h && nbv > 0) qq = fdExtract(pp + u.pay, bit0 + (uint32_t)(kk * nbv), nbv);
-              if (u.lut) {
-                if (qq > (uint32_t)u.nLut) { fallback = true; why |= 16384; qq = 0; }
-                qq = qq == 0 ? 0u : fdExtract(pp + u.lutPay, (qq - 1) * (uint32_t)u.nb, u.nb);
-              }
-              out[kk] = fdCast<T>(__dadd_rn(offset, __dmul_rn((double)qq, a.invScale)), a.zMax);
-            }
-          }
+        } else {                                                     // LUT block or wide count field: byte-wise parser, out of line
+          len = fdDecodeSlowRow<T>(sb + p, version, cells, r, h, w, a.invScale, a.zMax, out);
+          if (len <= 0 || len > MAXU) { fallback = true; why |= len == -2 ? 16384 : 8192; len = 0; }
         }
         // the block, parsed with its true size, must end where the recorded chain continues
         if (!fallback && p + len != pNext) { fallback = true; why |= 1024; }
@@ -538,18 +611,13 @@ __global__ void __launch_bounds__(FD_DWARPS * 32, 2) k_dec_blocks(FastDecArgs a)
     if (lane == 0 && fallback) atomicOr(a.status, DECF_FALLBACK | (int)why);
     __syncwarp();
   }
-  if (tid == 0) {
-    if (sWhy) atomicOr(a.status, DECF_FALLBACK | sWhy);
-    // the chain must cover all blocks
-    if (reg == a.nReg - 1 && sTrue[3 * nLocal] != FD_DEAD && sTrue[3 * nLocal + 1] < (uint32_t)nBlocks) atomicOr(a.status, DECF_FALLBACK | 4096);
-  }
+  if (tid == 0 && sWhy) atomicOr(a.status, DECF_FALLBACK | sWhy);
 }
 
-template <class T> inline size_t fastDecodeBlocksSmem(int subPerReg, int nReg) {
+template <class T> inline size_t fastDecodeBlocksSmem() {
   constexpr int MAXU = 1 + 64 * (int)sizeof(T);
   constexpr int BUFB = ((FD_SUB + MAXU + 64 + 15) / 16) * 16;
-  return (size_t)FD_DWARPS * BUFB + (size_t)FD_DWARPS * 256 * 2 + (size_t)subPerReg * FD_CAND * sizeof(FdEntry) + (size_t)nReg * FD_CAND * sizeof(FdEntry) +
-         (size_t)(subPerReg + 2) * 12 + 16;
+  return (size_t)FD_DWARPS * BUFB;
 }
 
 }  // namespace lerc
