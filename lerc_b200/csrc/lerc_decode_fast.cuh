@@ -351,8 +351,7 @@ __global__ void __launch_bounds__(256) k_dec_walk(FastDecArgs a) {
 // Region r's map sends each of its FD_CAND entry positions to (exit position, #blocks); the true chain starts at
 // (position 0, block 0) in region 0.  One CTA of 32 warps; warp w owns the consecutive regions [w*G, (w+1)*G):
 //   A  lanes 16..31 follow the 16 chains that start at the entries of the warp's first region through its G regions
-//      (the match of an exit position against the next region's entries is one __match_any_sync: lanes 0..15
-//      offer the entries, lanes 16..31 their current positions)              -> chunk map in shared memory
+//      (lanes 0..15 broadcast the next region's entries, every chain lane looks for its position) -> chunk map in shared memory
 //   B  one thread composes the 32 chunk maps serially                        -> true entry of every chunk
 //   C  every warp walks its regions again with the single true chain         -> regEntry[r] for every region
 static_assert(FD_CAND == 16, "k_dec_resolve pairs 16 entry lanes with 16 chain lanes");
@@ -375,12 +374,16 @@ __global__ void __launch_bounds__(1024) k_dec_resolve(FastDecArgs a, int nBlocks
       if (r + 1 < r1) nx = a.regTab[(size_t)(r + 1) * FD_CAND + L];  // independent of the chains: overlaps the match
       const bool chain = lane >= 16;
       const bool active = chain && alive && (unsigned long long)pos < a.streamLen;   // a chain that reached the end of the stream is complete
-      // unique keys for lanes that must not match anything
-      const uint32_t key = chain ? (active ? pos : 0xfffffff0u - lane) : (t.entry != FD_DEAD ? t.entry : 0xffffffd0u - lane);
-      const unsigned m = __match_any_sync(FULL, key) & 0xffffu;
-      const int src = m ? __ffs(m) - 1 : 0;
-      const uint32_t nx = __shfl_sync(FULL, t.exit, src), nc = __shfl_sync(FULL, t.count, src);
-      if (active) { if (m) { pos = nx; cnt += nc; } else alive = false; }
+      int hit = -1;
+#pragma unroll
+      for (int j = 0; j < FD_CAND; j++) {                           // 16 independent shuffles (entry lanes broadcast their entry)
+        const uint32_t e = __shfl_sync(FULL, t.entry, j);
+        if (e != FD_DEAD && e == pos) hit = j;
+      }
+      const bool m = hit >= 0;
+      const int src = m ? hit : 0;
+      const uint32_t nx2 = __shfl_sync(FULL, t.exit, src), nc = __shfl_sync(FULL, t.count, src);
+      if (active) { if (m) { pos = nx2; cnt += nc; } else alive = false; }
     }
     if (lane >= 16) { sEnt[warp][L] = alive ? ent : FD_DEAD; sExit[warp][L] = pos; sCnt[warp][L] = cnt; }
   }

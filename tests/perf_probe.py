@@ -46,4 +46,8 @@ probe("f32 4096^2 40% zero blocks", sea, 0.01)
 m = np.ones((4096, 4096), np.uint8); m[1000:2000, 500:3000] = 0
 probe("f32 4096^2 masked rect", f, 0.01, mask=m)
 big = c2_raster(16384, 16384)
-probe("f32 16384^2 mz0.001", big, 0.001, reps=2)
+probe("f32 16384^2 mz0.001", big, 0.001, reps=3)
+lerc_b200.profile(True)
+probe("f32 16384^2 mz0.001 (prof)", big, 0.001, reps=1)
+lerc_b200.profile(False)
+print({k: (v[0], round(v[1], 3)) for k, v in lerc_b200.kernel_times().items()})
