@@ -333,8 +333,11 @@ int smCount() {
 // Launches the speculative parallel decoder (lerc_decode_fast.cuh) on the micro-block stream.  Returns false when the
 // stream's shape is outside what it handles (nothing launched).
 template <class T>
-bool launchDecodeFast(Context* ctx, const HeaderInfo& hd, const uint8_t* dStream, size_t streamLen, void* dData, int* dStatus) {
-  if (hd.nDepth != 1 || hd.microBlockSize != 8 || hd.version < 3 || (long long)hd.numValidPixel != (long long)hd.nCols * hd.nRows) return false;
+bool launchDecodeFast(Context* ctx, const HeaderInfo& hd, const uint8_t* dStream, size_t streamLen, void* dData, int* dStatus,
+                      const uint8_t* dBits = nullptr, uint32_t* dBlockOff = nullptr) {
+  // dBlockOff == nullptr: every pixel valid, decode the pixels too; else (masked raster) only the block offsets are produced
+  const bool allValid = (long long)hd.numValidPixel == (long long)hd.nCols * hd.nRows;
+  if (hd.nDepth != 1 || hd.microBlockSize != 8 || hd.version < 3 || (dBlockOff == nullptr) != allValid) return false;
   if (streamLen == 0 || streamLen >= 0xfff00000ull || std::getenv("LERC_B200_NO_FAST")) return false;
   const int nSub = (int)((streamLen + FD_SUB - 1) / FD_SUB);
   const int subPerReg = FD_REG;
@@ -362,7 +365,8 @@ bool launchDecodeFast(Context* ctx, const HeaderInfo& hd, const uint8_t* dStream
   LERC_LAUNCH(ctx, k_dec_candidates<T>, (nSub + 7) / 8, 256, 0, fa);
   LERC_LAUNCH(ctx, k_dec_walk<T>, nReg, 256, 0, fa);
   LERC_LAUNCH(ctx, k_dec_resolve, 1, 1024, 0, fa, fa.nTx * fa.nTy);
-  LERC_LAUNCH(ctx, k_dec_blocks<T>, nReg, FD_DWARPS * 32, smemB, fa);
+  if (dBlockOff) LERC_LAUNCH(ctx, k_dec_offsets<T>, nReg, FD_DWARPS * 32, 0, fa, dBits, dBlockOff);
+  else LERC_LAUNCH(ctx, k_dec_blocks<T>, nReg, FD_DWARPS * 32, smemB, fa);
   return cudaOk(cudaGetLastError(), "launch fast decode");
 }
 
@@ -527,8 +531,21 @@ ErrCode decodeBandT(Context* ctx, DecodeBandArgs& a, BandMaskState& ms) {
   ta.blockOff = (uint32_t*)ctx->arena.alloc(4 * (nBlocks + 1));
   ta.data = a.dData; ta.status = dStatus;
   if (!ta.blockOff) return Failed;
-  LERC_LAUNCH(ctx, k_walk_units, 1, 128, 0, ta);
-  {   // a malformed chain must not reach the unpack kernel (its offsets would be garbage)
+  // block boundaries: speculative parallel discovery for masked nDepth == 1 rasters (lerc_decode_fast.cuh), else / on
+  // any inconsistency the exact serial walk
+  bool haveOffsets = false;
+  if (hd.numValidPixel != nPix && !ta.allValidImage && nDepth == 1 &&
+      launchDecodeFast<T>(ctx, hd, ta.stream, (size_t)ta.streamLen, nullptr, dStatus, ms.dBits, ta.blockOff)) {
+    int hs = 0;
+    if (!cudaOk(cudaMemcpyAsync(&hs, dStatus, 4, cudaMemcpyDeviceToHost, st), "D2H") || !cudaOk(cudaStreamSynchronize(st), "sync")) return Failed;
+    if (hs && std::getenv("LERC_B200_VERBOSE")) std::fprintf(stderr, "[lerc_b200] speculative block offsets status %d\n", hs);
+    if (hs & 7) return Failed;
+    if (!(hs & DECF_FALLBACK)) { haveOffsets = true; globalStats().fastPathDecodes++; }
+    else cudaMemsetAsync(dStatus, 0, 4, st);
+  }
+  if (!haveOffsets) {
+    LERC_LAUNCH(ctx, k_walk_units, 1, 128, 0, ta);
+    // a malformed chain must not reach the unpack kernel (its offsets would be garbage)
     int hs = 0;
     if (!cudaOk(cudaMemcpyAsync(&hs, dStatus, 4, cudaMemcpyDeviceToHost, st), "D2H") || !cudaOk(cudaStreamSynchronize(st), "sync")) return Failed;
     if (hs & DECF_BAD_STREAM) return Failed;

@@ -428,8 +428,108 @@ __global__ void __launch_bounds__(1024) k_dec_resolve(FastDecArgs a, int nBlocks
   }
 }
 
-// ================= kernel 4: true entries of the region's sub-chunks, decode the blocks ================
 constexpr int FD_DWARPS = 8;
+// ================= kernel 4b: block offsets only (masked rasters: the general block decoder does the pixels) =========
+// Same resolution as k_dec_blocks; instead of decoding, every block's stream offset is written to blockOff[] for
+// k_tiles_decode.  Bit-stuffed units describe their own length; a raw unit's length depends on the number of valid
+// pixels of its block, which the speculative walk assumed to be 64: checked here against the mask.
+template <class T>
+__global__ void __launch_bounds__(FD_DWARPS * 32) k_dec_offsets(FastDecArgs a, const uint8_t* __restrict__ bits, uint32_t* __restrict__ blockOff) {
+  constexpr int MAXU = 1 + 64 * (int)sizeof(T);
+  __shared__ uint16_t sPosAll[FD_DWARPS * FD_LENS];
+  __shared__ FdEntry sTab[FD_REG * FD_CAND];
+  __shared__ uint32_t sTrue[(FD_REG + 1) * 3];
+  __shared__ int sWhy;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int reg = blockIdx.x;
+  const int sub0 = reg * a.subPerReg, nLocal = max(0, min(a.nSub, sub0 + a.subPerReg) - sub0);
+  const int nBlocks = a.nTx * a.nTy;
+  const int version = a.version;
+  if (tid == 0) sWhy = 0;
+  for (int i = tid; i < nLocal * FD_CAND; i += blockDim.x) sTab[i] = a.subTab[(size_t)sub0 * FD_CAND + i];
+  __syncthreads();
+  // ---- true entry (position, block index, candidate slot) of every sub-chunk of the region
+  if (tid == 0) {
+    uint32_t pos = a.regEntry[2 * reg], blk = a.regEntry[2 * reg + 1];
+    for (int ls = 0; ls <= nLocal; ls++) {
+      sTrue[3 * ls] = pos; sTrue[3 * ls + 1] = blk; sTrue[3 * ls + 2] = 0;
+      if (ls == nLocal) break;
+      if (pos == FD_DEAD) { for (int k = ls; k <= nLocal; k++) { sTrue[3 * k] = FD_DEAD; sTrue[3 * k + 1] = blk; } break; }
+      if (pos == FD_DEAD - 1 || blk >= (uint32_t)nBlocks) { for (int k = ls; k <= nLocal; k++) { sTrue[3 * k] = FD_DEAD - 1; sTrue[3 * k + 1] = blk; } break; }   // past the last block
+      bool found = false;
+      for (int e = 0; e < FD_CAND; e++) {
+        const FdEntry t = sTab[ls * FD_CAND + e];
+        if (t.entry != FD_DEAD && t.entry == pos) { sTrue[3 * ls + 2] = (uint32_t)e; pos = t.exit; blk += t.count; found = true; break; }
+      }
+      if (!found) { sWhy |= 64; pos = FD_DEAD; }
+    }
+  }
+  __syncthreads();
+
+  const int tailRaw = 1 + (a.nRows - (a.nTy - 1) * 8) * (a.nCols - (a.nTx - 1) * 8) * (int)sizeof(T);
+  (void)tailRaw; (void)version;
+  uint16_t* sPos = sPosAll + warp * FD_LENS;
+  for (int ls = warp; ls < nLocal; ls += FD_DWARPS) {
+    const uint32_t pos0 = sTrue[3 * ls], blk0 = sTrue[3 * ls + 1], slot = sTrue[3 * ls + 2];
+    if (pos0 >= FD_DEAD - 1) continue;
+    const int s = sub0 + ls;
+    const uint32_t expectExit = sTrue[3 * ls + 3], expectBlk = sTrue[3 * ls + 4];
+    const FdEntry me = sTab[ls * FD_CAND + slot];
+    const int cnt = (int)me.count;
+    bool fallback = false; unsigned why = 0;
+    {
+      const uint8_t* lens = a.lens + ((size_t)s * FD_CAND + slot) * FD_LENS;
+      uint32_t run = pos0 - (uint32_t)s * FD_SUB;
+      for (int base = 0; base <= cnt; base += 256) {
+        const int i8 = base + lane * 8;
+        const unsigned long long l8 = i8 < cnt ? *(const unsigned long long*)(lens + i8) : 0ull;
+        uint32_t pre[8]; uint32_t sum = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          const uint32_t c8 = (uint32_t)((l8 >> (8 * k)) & 0xff);
+          pre[k] = sum; sum += (i8 + k < cnt) ? (c8 == 255 ? (uint32_t)MAXU : c8) : 0u;
+        }
+        uint32_t inc = sum;
+#pragma unroll
+        for (int m = 1; m < 32; m <<= 1) { const uint32_t o = __shfl_up_sync(FULL, inc, m); if (lane >= m) inc += o; }
+        const uint32_t mine = run + inc - sum;
+#pragma unroll
+        for (int k = 0; k < 8; k++) if (i8 + k <= cnt) sPos[i8 + k] = (uint16_t)(mine + pre[k]);
+        run += __shfl_sync(FULL, inc, 31);
+      }
+    }
+    __syncwarp();
+    for (int i = lane; i < cnt; i += 32) {
+      const uint32_t b = blk0 + (uint32_t)i;
+      if (b >= (uint32_t)nBlocks) break;
+      const uint32_t p = sPos[i], len = (uint32_t)sPos[i + 1] - p;
+      const unsigned long long gp = (unsigned long long)s * FD_SUB + p;
+      const unsigned flag = a.stream[gp];
+      if ((flag & 3) == 0) {                                           // raw: 1 + (valid pixels of the block) * sizeof(T) bytes
+        const int ty = (int)b / a.nTx, tx = (int)b - ty * a.nTx;
+        const int h = min(8, a.nRows - ty * 8), w = min(8, a.nCols - tx * 8);
+        int nv = 0;
+        for (int rr = 0; rr < h; rr++) {
+          const long long k0 = (long long)(ty * 8 + rr) * a.nCols + tx * 8;
+          for (int c = 0; c < w; c++) nv += maskBit(bits, k0 + c) ? 1 : 0;
+        }
+        if (len != 1u + (uint32_t)nv * (uint32_t)sizeof(T)) { fallback = true; why |= 1024; }
+      }
+      blockOff[b] = (uint32_t)gp;
+    }
+    const uint32_t blkEnd = blk0 + (uint32_t)cnt;
+    const bool haveNext = expectExit < FD_DEAD - 1;
+    if (haveNext ? (blkEnd != expectBlk || me.exit != expectExit) : (blkEnd < (uint32_t)nBlocks)) { fallback = true; why |= 2048; }
+    fallback = __any_sync(FULL, fallback);
+    why = __reduce_or_sync(FULL, why);
+    if (lane == 0 && fallback) atomicOr(a.status, DECF_FALLBACK | (int)why);
+    __syncwarp();
+  }
+  if (tid == 0 && sWhy) atomicOr(a.status, DECF_FALLBACK | sWhy);
+}
+
+// ================= kernel 4: true entries of the region's sub-chunks, decode the blocks ================
 template <class T>
 __global__ void __launch_bounds__(FD_DWARPS * 32) k_dec_blocks(FastDecArgs a) {
   constexpr int MAXU = 1 + 64 * (int)sizeof(T);

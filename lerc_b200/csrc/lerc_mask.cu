@@ -112,8 +112,26 @@ void launchChunkValidCounts(Context* ctx, const uint8_t* dBits, long long nPix, 
 // iff it is >= 5 long and starts more than 5 bytes before the end of the array (RLE.cpp:74-79); all
 // counts are capped at 32767 (RLE.cpp:98-107).  One warp walks the runs; lanes measure run lengths
 // with ballots and copy literal stretches cooperatively.  dst == nullptr only sizes.
-__global__ void k_rle_encode(const uint8_t* __restrict__ src, long long n, uint8_t* __restrict__ dst, uint32_t* __restrict__ sizeOut) {
+__global__ void __launch_bounds__(32) k_rle_encode(const uint8_t* __restrict__ src, long long n, uint8_t* __restrict__ dst, uint32_t* __restrict__ sizeOut) {
+  // The run scan is a serial dependency chain; it reads the mask through a 16 KB shared-memory window (refilled with
+  // independent 128-bit loads) so that a step costs a shared-memory access, not a DRAM round trip.
+  constexpr int WIN = 16384;
+  __shared__ __align__(16) uint8_t win[WIN + 16];
   const int lane = threadIdx.x;
+  long long wBase = 0; bool haveWin = false;               // window holds src[wBase, wBase + WIN); src + wBase is 16-byte aligned
+  const int mis = (int)((uintptr_t)src & 15);
+  auto fill = [&](long long i) {                          // make src[i] the first 16-byte chunk of the window
+    const long long a0 = ((i + mis) & ~15ll) - mis;       // src index (may be negative by < 16) whose address is 16-byte aligned
+    for (int c = lane; c < WIN / 16; c += 32) {
+      const long long s0 = a0 + (long long)c * 16;
+      uint4 x = make_uint4(0, 0, 0, 0);
+      if (s0 < n && s0 + 16 > 0) x = *(const uint4*)(src + s0);          // whole chunk lies inside the allocation granule of src
+      ((uint4*)win)[c] = x;
+    }
+    wBase = a0; haveWin = true;
+    __syncwarp();
+  };
+  auto rd = [&](long long i) -> unsigned { return win[i - wBase]; };
   long long pos = 0, lit = 0, out = 0;
   auto putCount = [&](int c) {
     if (dst && lane == 0) { dst[out] = (uint8_t)(c & 0xff); dst[out + 1] = (uint8_t)((c >> 8) & 0xff); }
@@ -128,11 +146,13 @@ __global__ void k_rle_encode(const uint8_t* __restrict__ src, long long n, uint8
     }
   };
   while (pos < n) {
-    const uint8_t v = src[pos];
+    if (!haveWin || pos < wBase || pos + 64 > wBase + WIN) fill(pos);
+    const unsigned v = rd(pos);
     long long run = 1;
     for (;;) {                                   // extend the run 32 bytes at a time
       const long long i = pos + run + lane;
-      const unsigned m = __ballot_sync(FULL, i < n && src[i] == v);
+      if (pos + run + 32 > wBase + WIN) { __syncwarp(); fill(pos + run); }
+      const unsigned m = __ballot_sync(FULL, i < n && rd(i) == v);
       const int ones = (m == FULL) ? 32 : (__ffs(~m) - 1);
       run += ones;
       if (ones < 32) break;
@@ -143,7 +163,7 @@ __global__ void k_rle_encode(const uint8_t* __restrict__ src, long long n, uint8
       while (left) {
         const long long c = left > 32767 ? 32767 : left;
         putCount(-(int)c);
-        if (dst && lane == 0) dst[out] = v;
+        if (dst && lane == 0) dst[out] = (uint8_t)v;
         out += 1; left -= c;
       }
       lit = pos + run;
@@ -159,19 +179,36 @@ void launchRleEncode(Context* ctx, const uint8_t* dSrc, long long n, uint8_t* dD
 }
 
 // RLE.cpp:298-331.  status[0] = 1 on success, 0 on malformed input.
-__global__ void k_rle_decode(const uint8_t* __restrict__ src, long long srcLen, uint8_t* __restrict__ dst, long long dstLen, int* __restrict__ status) {
+__global__ void __launch_bounds__(32) k_rle_decode(const uint8_t* __restrict__ src, long long srcLen, uint8_t* __restrict__ dst, long long dstLen, int* __restrict__ status) {
+  // token headers are a serial dependency chain: read them through a shared-memory window (see k_rle_encode)
+  constexpr int WIN = 8192;
+  __shared__ __align__(16) uint8_t win[WIN + 16];
   const int lane = threadIdx.x;
+  long long wBase = 0; bool haveWin = false;
+  const int mis = (int)((uintptr_t)src & 15);
+  auto fill = [&](long long i) {
+    const long long a0 = ((i + mis) & ~15ll) - mis;
+    for (int c = lane; c < WIN / 16; c += 32) {
+      const long long s0 = a0 + (long long)c * 16;
+      uint4 x = make_uint4(0, 0, 0, 0);
+      if (s0 < srcLen && s0 + 16 > 0) x = *(const uint4*)(src + s0);
+      ((uint4*)win)[c] = x;
+    }
+    wBase = a0; haveWin = true;
+    __syncwarp();
+  };
   long long ip = 0, op = 0;
   int ok = 1;
   for (;;) {
     if (ip + 2 > srcLen) { ok = 0; break; }
-    const int c = (int)(int16_t)(src[ip] | (src[ip + 1] << 8));
+    if (!haveWin || ip < wBase || ip + 4 > wBase + WIN) { __syncwarp(); fill(ip); }
+    const int c = (int)(int16_t)(win[ip - wBase] | (win[ip + 1 - wBase] << 8));
     ip += 2;
     if (c == -32768) break;
     const long long cnt = c <= 0 ? -c : c, take = c > 0 ? cnt : 1;
     if (ip + take + 2 > srcLen || op + cnt > dstLen) { ok = 0; break; }
     if (c > 0) for (long long i = lane; i < cnt; i += 32) dst[op + i] = src[ip + i];
-    else { const uint8_t v = src[ip]; for (long long i = lane; i < cnt; i += 32) dst[op + i] = v; }
+    else { const uint8_t v = win[ip - wBase]; for (long long i = lane; i < cnt; i += 32) dst[op + i] = v; }
     ip += take; op += cnt;
   }
   if (lane == 0) *status = ok;

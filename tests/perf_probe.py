@@ -45,6 +45,13 @@ sea = f.copy(); sea[:, :1500] = 0
 probe("f32 4096^2 40% zero blocks", sea, 0.01)
 m = np.ones((4096, 4096), np.uint8); m[1000:2000, 500:3000] = 0
 probe("f32 4096^2 masked rect", f, 0.01, mask=m)
+lerc_b200.kernel_times()
+lerc_b200.profile(True)
+probe("f32 4096^2 masked rect (prof)", f, 0.01, mask=m, reps=1)
+lerc_b200.profile(False)
+print({k: (v[0], round(v[1], 3)) for k, v in sorted(lerc_b200.kernel_times().items(), key=lambda kv: -kv[1][1])})
+mr = (rng.random((4096, 4096)) > 0.2).astype(np.uint8)
+probe("f32 4096^2 masked random 20%", f, 0.01, mask=mr)
 big = c2_raster(16384, 16384)
 probe("f32 16384^2 mz0.001", big, 0.001, reps=3)
 lerc_b200.profile(True)
