@@ -318,6 +318,8 @@ __global__ void k_huffman_decode_seq(HuffDecArgs a) {
 
 }  // namespace lerc
 #include "lerc_decode_fast.cuh"
+#include "lerc_huffman_fast.cuh"
+#include <cub/device/device_scan.cuh>
 namespace lerc {
 
 // =================================================================================================
@@ -368,6 +370,98 @@ bool launchDecodeFast(Context* ctx, const HeaderInfo& hd, const uint8_t* dStream
   if (dBlockOff) LERC_LAUNCH(ctx, k_dec_offsets<T>, nReg, FD_DWARPS * 32, 0, fa, dBits, dBlockOff);
   else LERC_LAUNCH(ctx, k_dec_blocks<T>, nReg, FD_DWARPS * 32, smemB, fa);
   return cudaOk(cudaGetLastError(), "launch fast decode");
+}
+
+// Parallel Huffman decode (lerc_huffman_fast.cuh) of an all-valid 8-bit band.  Returns 1 when the band was decoded,
+// 0 when the serial kernel must run instead (unexpected table / no convergence / anomaly on the true chain), -1 on a CUDA error.
+template <class T>
+int decodeHuffmanFast(Context* ctx, const HuffmanTable& t, const uint8_t* dStream, size_t streamLen, int H, int W, int D, bool delta, void* dData) {
+  if (std::getenv("LERC_B200_NO_FAST")) return 0;
+  cudaStream_t st = ctx->stream;
+  // ---- decode tables (host, 256 symbols)
+  HuffFastTables* hT = (HuffFastTables*)ctx->pinnedAlloc(sizeof(HuffFastTables));
+  if (!hT) return 0;
+  std::memset(hT, 0, sizeof *hT);
+  hT->minLen = 33; hT->maxLen = 0;
+  std::vector<std::pair<uint32_t, int>> byLen[33];
+  for (int s = 0; s < 256; s++) if (t.len[s]) {
+    if (t.len[s] > 32) return 0;
+    byLen[t.len[s]].push_back({t.code[s], s});
+    hT->minLen = std::min<int>(hT->minLen, t.len[s]); hT->maxLen = std::max<int>(hT->maxLen, t.len[s]);
+  }
+  if (hT->maxLen == 0) return 0;
+  int nSyms = 0;
+  for (int len = 1; len <= 32; len++) {
+    auto& v = byLen[len];
+    if (v.empty()) continue;
+    std::sort(v.begin(), v.end());
+    hT->first[len] = v[0].first; hT->count[len] = (uint32_t)v.size(); hT->offset[len] = (uint32_t)nSyms;
+    for (size_t i = 0; i < v.size(); i++) {
+      if (v[i].first != v[0].first + i || (len < 32 && (v[i].first >> len))) return 0;       // codes of one length must be consecutive (Huffman.cpp:541-572)
+      hT->syms[nSyms++] = (uint8_t)v[i].second;
+      if (len <= 12) for (uint32_t k = v[i].first << (12 - len); k < ((v[i].first + 1) << (12 - len)); k++) {
+        if (hT->lut[k]) return 0;                                                                // not prefix free
+        hT->lut[k] = (uint16_t)((len << 8) | v[i].second);
+      }
+    }
+  }
+  const unsigned long long nBits = (unsigned long long)(streamLen / 4) * 32;
+  if (nBits < 64) return 0;
+  const unsigned long long nSym = (unsigned long long)H * W * D;
+  const int nChunks = (int)((nBits + HF_CHUNK - 1) / HF_CHUNK);
+  HuffFastTables* dT = (HuffFastTables*)ctx->arena.alloc(sizeof(HuffFastTables));
+  unsigned long long* dArr = (unsigned long long*)ctx->arena.alloc((size_t)nChunks * 8 * 3);
+  uint32_t* dCount = (uint32_t*)ctx->arena.alloc((size_t)(nChunks + 1) * 4);
+  uint32_t* dBase = (uint32_t*)ctx->arena.alloc((size_t)(nChunks + 1) * 4);
+  int* dFlags = (int*)ctx->arena.alloc(16);
+  int* hFlags = (int*)ctx->pinnedAlloc(16);
+  if (!dT || !dArr || !dCount || !dBase || !dFlags || !hFlags) return 0;
+  cudaMemcpyAsync(dT, hT, sizeof(HuffFastTables), cudaMemcpyHostToDevice, st);
+  cudaMemsetAsync(dFlags, 0, 16, st);
+  cudaMemsetAsync(dCount + nChunks, 0, 4, st);
+  HuffFastArgs ha;
+  ha.stream = dStream; ha.nBits = nBits; ha.tab = dT; ha.nSym = nSym; ha.nChunks = nChunks;
+  ha.startA = dArr; ha.endA = dArr + nChunks; ha.endB = dArr + 2 * (size_t)nChunks; ha.count = dCount; ha.changed = dFlags; ha.bad = dFlags + 1;
+  const int grid = (nChunks + 255) / 256;
+  int iter = 0;
+  for (;; iter++) {
+    if (iter >= 64) return 0;                                        // does not synchronise: let the serial decoder handle it
+    if (iter > 0) cudaMemsetAsync(dFlags, 0, 4, st);
+    LERC_LAUNCH(ctx, k_huff_chunks, grid, 256, 0, ha, iter);
+    if (iter == 0) continue;
+    if (!cudaOk(cudaMemcpyAsync(hFlags, dFlags, 4, cudaMemcpyDeviceToHost, st), "D2H") || !cudaOk(cudaStreamSynchronize(st), "sync")) return -1;
+    if (!hFlags[0]) break;
+  }
+  const unsigned long long* dEndFinal = (iter & 1) ? ha.endB : ha.endA;   // written by the last iteration
+  {
+    LaunchScope scope(ctx, "cub::ExclusiveSum<u32>");
+    size_t tmpBytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmpBytes, dCount, dBase, nChunks + 1, st);
+    void* tmp = ctx->arena.alloc(tmpBytes ? tmpBytes : 16);
+    if (!tmp) return 0;
+    cub::DeviceScan::ExclusiveSum(tmp, tmpBytes, dCount, dBase, nChunks + 1, st);
+    ctx->kernelLaunches += 2;
+  }
+  uint32_t total = 0;
+  if (!cudaOk(cudaMemcpyAsync(hFlags, dBase + nChunks, 4, cudaMemcpyDeviceToHost, st), "D2H") || !cudaOk(cudaStreamSynchronize(st), "sync")) return -1;
+  total = (uint32_t)hFlags[0];
+  if ((unsigned long long)total < nSym || nSym > 0xffffffffull) return 0;     // stream holds fewer symbols than the band: the serial decoder reports the error
+  const int off = PixelTraits<T>::code == DT_Char ? 128 : 0;
+  uint8_t* dPlanes = nullptr;
+  if (delta) { dPlanes = (uint8_t*)ctx->arena.alloc((size_t)nSym + 16); if (!dPlanes) return 0; }
+  LERC_LAUNCH(ctx, k_huff_emit<T>, grid, 256, 0, ha, dEndFinal, dBase, delta ? dPlanes : (uint8_t*)dData);
+  if (!delta) {
+    if (off) LERC_LAUNCH(ctx, k_huff_values<T>, 148 * 8, 256, 0, (uint8_t*)dData, nSym, off);
+  } else {
+    uint8_t* dCol0 = (uint8_t*)ctx->arena.alloc((size_t)H * D + 16);
+    if (!dCol0) return 0;
+    LERC_LAUNCH(ctx, k_huff_col0, D, 256, 0, dPlanes, H, W, D, off, dCol0);
+    LERC_LAUNCH(ctx, k_huff_rows<T>, H, 256, 0, dPlanes, dCol0, H, W, D, off, (T*)dData);
+  }
+  if (!cudaOk(cudaMemcpyAsync(hFlags, dFlags, 8, cudaMemcpyDeviceToHost, st), "D2H") || !cudaOk(cudaStreamSynchronize(st), "sync")) return -1;
+  if (hFlags[1]) return 0;
+  globalStats().fastPathDecodes++;
+  return 1;
 }
 
 template <class T>
@@ -506,6 +600,11 @@ ErrCode decodeBandT(Context* ctx, DecodeBandArgs& a, BandMaskState& ms) {
         ha.allValidImage = hd.numValidPixel == nPix;
         std::memcpy(ha.len, t.len, sizeof ha.len); std::memcpy(ha.code, t.code, sizeof ha.code);
         ha.data = a.dData; ha.status = dStatus;
+        if (ha.allValidImage) {                         // parallel decoder first (lerc_huffman_fast.cuh)
+          const int rc = decodeHuffmanFast<T>(ctx, t, ha.stream, (size_t)ha.streamLen, hd.nRows, hd.nCols, nDepth, ha.delta != 0, a.dData);
+          if (rc < 0) return Failed;
+          if (rc > 0) return finish();
+        }
         LERC_LAUNCH(ctx, k_huffman_decode_seq<T>, 1, 32, 0, ha);
         return finish();
       } else return Failed;                      // FPL lossless-float blobs (mode 3): not implemented (DESIGN.md "Deviations")

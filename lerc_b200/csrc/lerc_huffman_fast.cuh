@@ -1,0 +1,174 @@
+// lerc_huffman_fast.cuh -- parallel decoder of the 8-bit Huffman image modes (IEM_Huffman / IEM_DeltaHuffman) for
+// rasters where every pixel is valid (included by lerc_decode.cu).
+//
+// The reference decodes ONE bit stream for the whole band serially (Lerc2::DecodeHuffman, Lerc2.cpp:2472-2606;
+// Huffman::DecodeOneValue, Huffman.h:144-214): codes are MSB-first in little-endian 32-bit words, at most 32 bits long,
+// canonical in the sense of Huffman.cpp:541-572 (codes of one length are consecutive integers).  Here:
+//   k_huff_chunks   the stream is cut into chunks of HF_CHUNK bits, one thread each.  Thread t decodes from its current
+//                   start bit to the end of its chunk and records where it stopped and how many symbols it saw.
+//                   Iteration 0 starts at the chunk boundary (usually mid-code); iteration i+1 starts where chunk t-1
+//                   stopped in iteration i.  Huffman codes self-synchronise within a few symbols, so after 2-4 iterations
+//                   nothing changes any more; then start[t] == end[t-1] for every t with start[0] = 0, i.e. the chain IS
+//                   the serial decode (exact, not heuristic).  Only chunks whose start moved are decoded again.
+//   (CUB scan)      symbol index of every chunk's first symbol
+//   k_huff_emit     every thread decodes its chunk once more and stores the symbols: straight into the raster for
+//                   IEM_Huffman (pixel-interleaved order, Lerc2.cpp:2590-2600), into a depth-planar delta image for
+//                   IEM_DeltaHuffman (Lerc2.cpp:2501-2522)
+//   k_huff_col0, k_huff_rows   undo the predictor of the delta image when all pixels are valid: column 0 is a running sum
+//                   down the rows (predictor = pixel above), every row a running sum along the row (predictor = left
+//                   neighbour), modulo 256, per depth plane.
+// Anything unexpected (no convergence, a bit pattern that is no code on the true chain, a short stream) makes the host
+// run the serial kernel (k_huffman_decode_seq), which decides about errors like the reference.
+#pragma once
+
+namespace lerc {
+
+constexpr int HF_CHUNK = 2048;         // bits per chunk
+
+struct HuffFastTables {                // device copy of the code book in decode form
+  uint16_t lut[4096];                  // 12 leading bits -> (len << 8) | symbol for codes of <= 12 bits, 0 = longer code
+  uint32_t first[33];                  // per length: smallest code
+  uint32_t count[33];                  // per length: number of codes
+  uint32_t offset[33];                 // per length: index of its first symbol in `syms`
+  uint8_t syms[256];                   // symbols sorted by (length, code)
+  int minLen, maxLen;
+};
+
+struct HuffFastArgs {
+  const uint8_t* stream; unsigned long long nBits;     // bit stream and the number of bits that may be read (whole words)
+  const HuffFastTables* tab;
+  unsigned long long nSym;                              // symbols the band holds
+  int nChunks;
+  unsigned long long* startA; unsigned long long* endA; unsigned long long* endB;   // [nChunks]
+  uint32_t* count;                                      // [nChunks + 1]
+  int* changed; int* bad;
+};
+
+// 32 bits starting at bit position p (MSB first inside little-endian words), stream pointer of any alignment
+__device__ __forceinline__ uint32_t hfPeek(const uint8_t* __restrict__ s, unsigned long long p) {
+  const unsigned long long byte = (p >> 5) * 4;
+  const uintptr_t ad = (uintptr_t)(s + byte);
+  const uint32_t* w = (const uint32_t*)(ad & ~(uintptr_t)3);
+  const uint32_t sh = (uint32_t)(ad & 3) * 8;
+  const uint32_t a = __ldg(w), b = __ldg(w + 1), c = __ldg(w + 2);
+  const uint32_t w0 = __funnelshift_r(a, b, sh), w1 = __funnelshift_r(b, c, sh);   // the two stream words
+  const uint32_t o = (uint32_t)(p & 31);
+  return __funnelshift_l(w1, w0, o);                                                // (w0 << o) | (w1 >> (32 - o))
+}
+
+// one symbol at bit position p: returns its length (0 = the 32 bits are no code) and the symbol
+__device__ __forceinline__ int hfDecodeOne(const HuffFastTables* __restrict__ t, const uint16_t* __restrict__ sLut, uint32_t bits32, int& sym) {
+  const uint32_t e = sLut[bits32 >> 20];
+  if (e) { sym = (int)(e & 0xff); return (int)(e >> 8); }
+  for (int len = max(13, t->minLen); len <= t->maxLen; len++) {
+    const uint32_t c = bits32 >> (32 - len);
+    const uint32_t d = c - t->first[len];
+    if (c >= t->first[len] && d < t->count[len]) { sym = t->syms[t->offset[len] + d]; return len; }
+  }
+  return 0;
+}
+
+// Iteration of the self-synchronising chunk decode.  iter 0: start at the chunk boundary.
+__global__ void __launch_bounds__(256) k_huff_chunks(HuffFastArgs a, int iter) {
+  __shared__ uint16_t sLut[4096];
+  for (int i = threadIdx.x; i < 4096; i += 256) sLut[i] = a.tab->lut[i];
+  __syncthreads();
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  if (t >= a.nChunks) return;
+  const unsigned long long* endPrev = (iter & 1) ? a.endA : a.endB;     // written by the previous iteration
+  unsigned long long* endCur = (iter & 1) ? a.endB : a.endA;
+  const unsigned long long chunkEnd = min((unsigned long long)(t + 1) * HF_CHUNK, a.nBits);
+  unsigned long long start;
+  if (iter == 0) start = (unsigned long long)t * HF_CHUNK;
+  else {
+    start = t == 0 ? 0ull : endPrev[t - 1];
+    if (start == a.startA[t]) { endCur[t] = endPrev[t]; return; }          // same start as before: same result
+  }
+  a.startA[t] = start;
+  unsigned long long p = start; uint32_t cnt = 0;
+  while (p < chunkEnd) {
+    if (p + 32 > a.nBits) { p = chunkEnd; break; }                         // inside the read-ahead padding
+    int sym; const int len = hfDecodeOne(a.tab, sLut, hfPeek(a.stream, p), sym);
+    p += len ? len : 1;                                                    // a speculative start may see a non-code: skip a bit
+    cnt += len ? 1 : 0;
+  }
+  endCur[t] = p; a.count[t] = cnt;
+  if (iter > 0) *a.changed = 1;
+}
+
+// Final pass: symbols into out (IEM_Huffman: raster order, value = symbol - offset) or into the planar delta image.
+template <class T>
+__global__ void __launch_bounds__(256) k_huff_emit(HuffFastArgs a, const unsigned long long* __restrict__ endFinal, const uint32_t* __restrict__ symBase, uint8_t* __restrict__ out) {
+  __shared__ uint16_t sLut[4096];
+  for (int i = threadIdx.x; i < 4096; i += 256) sLut[i] = a.tab->lut[i];
+  __syncthreads();
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  if (t >= a.nChunks) return;
+  const unsigned long long chunkEnd = min((unsigned long long)(t + 1) * HF_CHUNK, a.nBits);
+  unsigned long long p = t == 0 ? 0ull : endFinal[t - 1];
+  unsigned long long n = symBase[t];
+  while (p < chunkEnd && n < a.nSym) {
+    if (p + 32 > a.nBits) { atomicOr(a.bad, 1); break; }
+    int sym; const int len = hfDecodeOne(a.tab, sLut, hfPeek(a.stream, p), sym);
+    if (!len) { atomicOr(a.bad, 1); break; }                               // no code on the true chain: the serial decoder decides
+    out[n++] = (uint8_t)sym;
+    p += len;
+  }
+}
+
+// non-delta mode: symbol -> value in place (offset 128 for signed char, Lerc2.cpp:2320)
+template <class T>
+__global__ void k_huff_values(uint8_t* __restrict__ data, unsigned long long n, int off) {
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x)
+    data[i] = (uint8_t)(data[i] - off);
+}
+
+// delta mode, all pixels valid: running sums.  planes: delta image [D][H][W] of symbols.  col0[d][i] = value of pixel (i, 0).
+__global__ void __launch_bounds__(256) k_huff_col0(const uint8_t* __restrict__ planes, int H, int W, int D, int off, uint8_t* __restrict__ col0) {
+  // one CTA per depth plane: running sum of the first column down the rows (predictor of (i, 0) is (i-1, 0); of (0, 0): 0)
+  __shared__ uint32_t sSum[256];
+  const int d = blockIdx.x, tid = threadIdx.x;
+  const uint8_t* pl = planes + (size_t)d * H * W;
+  const int per = (H + 255) / 256;
+  const int i0 = tid * per, i1 = min(H, i0 + per);
+  uint32_t s = 0;
+  for (int i = i0; i < i1; i++) s += (uint32_t)(uint8_t)(pl[(size_t)i * W] - off);
+  sSum[tid] = s;
+  __syncthreads();
+  if (tid == 0) { uint32_t run = 0; for (int k = 0; k < 256; k++) { const uint32_t v = sSum[k]; sSum[k] = run; run += v; } }
+  __syncthreads();
+  uint32_t run = sSum[tid];
+  for (int i = i0; i < i1; i++) { run += (uint32_t)(uint8_t)(pl[(size_t)i * W] - off); col0[(size_t)d * H + i] = (uint8_t)run; }
+}
+
+// one CTA per image row: per depth plane a running sum along the row starting from col0, written pixel-interleaved
+template <class T>
+__global__ void __launch_bounds__(256) k_huff_rows(const uint8_t* __restrict__ planes, const uint8_t* __restrict__ col0, int H, int W, int D, int off, T* __restrict__ data) {
+  constexpr int SEG = 4096;                                   // pixels per pass
+  __shared__ uint32_t sSum[256];
+  __shared__ uint32_t sCarry;
+  const int i = blockIdx.x, tid = threadIdx.x;
+  for (int d = 0; d < D; d++) {
+    const uint8_t* row = planes + ((size_t)d * H + i) * W;
+    if (tid == 0) sCarry = col0[(size_t)d * H + i];           // value of pixel (i, 0)
+    __syncthreads();
+    for (int j0 = 0; j0 < W; j0 += SEG) {
+      const int per = SEG / 256;
+      const int a0 = j0 + tid * per, a1 = min(W, a0 + per);
+      uint32_t s = 0;
+      for (int j = a0; j < a1; j++) if (j > 0) s += (uint32_t)(uint8_t)(row[j] - off);
+      sSum[tid] = s;
+      __syncthreads();
+      if (tid == 0) { uint32_t run = sCarry; for (int k = 0; k < 256; k++) { const uint32_t v = sSum[k]; sSum[k] = run; run += v; } sCarry = run; }
+      __syncthreads();
+      uint32_t run = sSum[tid];
+      for (int j = a0; j < a1; j++) {
+        if (j > 0) run += (uint32_t)(uint8_t)(row[j] - off);
+        data[((size_t)i * W + j) * D + d] = (T)(uint8_t)run;
+      }
+      __syncthreads();
+    }
+  }
+}
+
+}  // namespace lerc
