@@ -21,7 +21,11 @@ extern "C" {
   #define LERC_B200_API
 #endif
 
-/* Use `cudaStream` (a cudaStream_t passed as void*) for all work issued by the calling thread's next
+/* Device pointers and ordering: without lerc_b200_set_stream the library works on a private NON-BLOCKING stream, so
+ * device buffers handed to lerc_* must be complete (synchronise the producing stream first); results are complete
+ * when the call returns.  With lerc_b200_set_stream the calls are ordered on the given stream like any other work.
+ *
+ * Use `cudaStream` (a cudaStream_t passed as void*) for all work issued by the calling thread's next
  * lerc_* calls when enable != 0; enable == 0 returns to the library's private non-blocking stream.
  * Thread-local.  The lerc_* calls still return only after their results are complete. */
 LERC_B200_API void lerc_b200_set_stream(void* cudaStream, int enable);

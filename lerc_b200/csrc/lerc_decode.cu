@@ -344,7 +344,7 @@ bool launchDecodeFast(Context* ctx, const HeaderInfo& hd, const uint8_t* dStream
   const int nSub = (int)((streamLen + FD_SUB - 1) / FD_SUB);
   const int subPerReg = FD_REG;
   const int nReg = (nSub + subPerReg - 1) / subPerReg;
-  const size_t smemB = fastDecodeBlocksSmem<T>();
+  const size_t smemB = fastDecodeBlocksSmem<T>(), smemW = fastDecodeWalkSmem<T>();
   const size_t szCand = (size_t)nSub * FD_CAND * sizeof(FdCand), szN = ((size_t)nSub + 255) & ~(size_t)255, szLens = (size_t)nSub * FD_CAND * FD_LENS,
                szSub = (size_t)nReg * FD_REG * FD_CAND * sizeof(FdEntry), szReg = (size_t)nReg * FD_CAND * sizeof(FdEntry), szEnt = ((size_t)(nReg + 1) * 8 + 255) & ~(size_t)255;
   uint8_t* scratch = (uint8_t*)ctx->arena.alloc(szLens + szCand + szSub + szReg + szEnt + szN + 256);
@@ -363,9 +363,13 @@ bool launchDecodeFast(Context* ctx, const HeaderInfo& hd, const uint8_t* dStream
   fa.nCand = sp;
   fa.status = dStatus;
   static bool attrSet = false;
-  if (!attrSet) { if (!cudaOk(cudaFuncSetAttribute(k_dec_blocks<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB), "smem attribute")) return false; attrSet = true; }
+  if (!attrSet) {
+    if (!cudaOk(cudaFuncSetAttribute(k_dec_blocks<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB), "smem attribute")) return false;
+    if (!cudaOk(cudaFuncSetAttribute(k_dec_walk<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemW), "smem attribute")) return false;
+    attrSet = true;
+  }
   LERC_LAUNCH(ctx, k_dec_candidates<T>, (nSub + 7) / 8, 256, 0, fa);
-  LERC_LAUNCH(ctx, k_dec_walk<T>, nReg, 256, 0, fa);
+  LERC_LAUNCH(ctx, k_dec_walk<T>, nReg, 256, smemW, fa);
   LERC_LAUNCH(ctx, k_dec_resolve, 1, 1024, 0, fa, fa.nTx * fa.nTy);
   if (dBlockOff) LERC_LAUNCH(ctx, k_dec_offsets<T>, nReg, FD_DWARPS * 32, 0, fa, dBits, dBlockOff);
   else LERC_LAUNCH(ctx, k_dec_blocks<T>, nReg, FD_DWARPS * 32, smemB, fa);

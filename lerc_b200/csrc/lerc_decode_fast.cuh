@@ -276,14 +276,29 @@ __global__ void __launch_bounds__(256) k_dec_candidates(FastDecArgs a) {
 template <class T>
 __global__ void __launch_bounds__(256) k_dec_walk(FastDecArgs a) {
   __shared__ FdEntry sTab[FD_REG * FD_CAND];                        // [subPerReg <= FD_REG][FD_CAND]
+  extern __shared__ __align__(16) uint8_t sReg[];                    // the region's bytes: FD_REG * FD_SUB + look-ahead
+  constexpr int MAXU = 1 + 64 * (int)sizeof(T);
+  constexpr int AHEAD = ((MAXU + 64 + 15) / 16) * 16;
   const int reg = blockIdx.x, tid = threadIdx.x;
   const int sub0 = reg * a.subPerReg, nLocal = max(0, min(a.nSub, sub0 + a.subPerReg) - sub0);
   const int version = a.version;
   const int tailRaw = 1 + (a.nRows - (a.nTy - 1) * 8) * (a.nCols - (a.nTx - 1) * 8) * (int)sizeof(T);
-  // aligned words of the stream: stream[p] lives in gw[(p + gd) >> 2] at byte (p + gd) & 3
-  const int gd = (int)((uintptr_t)a.stream & 3);
-  const uint32_t* gw = (const uint32_t*)(a.stream - gd);
-  const long long lastByte = (long long)a.streamLen + gd - 1;       // last stream byte, in gw byte coordinates
+  // ---- stage the region (the walks are dependent chains of header reads: shared-memory latency instead of L2 latency)
+  const unsigned long long regStart = (unsigned long long)sub0 * FD_SUB;
+  const uint8_t* g = a.stream + regStart;
+  const int d = (int)((uintptr_t)g & 15);
+  {
+    const uint8_t* g0 = g - d;
+    const long long avail = (long long)(a.streamLen - regStart) + d;
+    const int nChunks = (nLocal * FD_SUB + AHEAD + 16) / 16;
+    for (int i = tid; i < nChunks; i += blockDim.x) {
+      uint4 x = make_uint4(0, 0, 0, 0);
+      if ((long long)i * 16 < avail) x = __ldg((const uint4*)g0 + i);
+      ((uint4*)sReg)[i] = x;
+    }
+  }
+  __syncthreads();
+  const uint32_t* words = (const uint32_t*)sReg;
   for (int it = tid; it < nLocal * FD_CAND; it += blockDim.x) {
     const int ls = it / FD_CAND, j = it - ls * FD_CAND, s = sub0 + ls;
     FdEntry e; e.entry = FD_DEAD; e.exit = 0; e.count = 0;
@@ -292,26 +307,16 @@ __global__ void __launch_bounds__(256) k_dec_walk(FastDecArgs a) {
       const unsigned long long start = (unsigned long long)s * FD_SUB;
       const long long left = (long long)(a.streamLen - start);
       const int subEnd = (int)min((long long)FD_SUB, left);
+      const int base = d + ls * FD_SUB;                               // sReg[base + p] = stream[start + p]
       // restart from the entry so that every unit length of the chain is recorded
       int pos = c.entry, cnt = 0, pat = 0;
       bool ok = true;
       unsigned long long acc = 0;
       uint8_t* lens = a.lens + ((size_t)s * FD_CAND + j) * FD_LENS;
       while (pos < subEnd) {
-        const unsigned long long gpos = start + (unsigned long long)pos + gd;
-        const uint32_t* w = gw + (gpos >> 2);
-        const uint32_t sh = (uint32_t)(gpos & 3) * 8;
-        // 16-byte window from 5 aligned words; words past the stream's last byte are not touched
-        const long long w0 = (long long)(gpos >> 2) * 4;
-        uint32_t v[5];
-#pragma unroll
-        for (int k = 0; k < 5; k++) v[k] = (w0 + 4 * k <= lastByte) ? __ldg(w + k) : 0u;
-        if (w0 + 384 <= lastByte) asm volatile("prefetch.global.L1 [%0];" :: "l"(w + 64));   // the chain advances < 256 bytes per hop: keep its next lines in L1
-        FdWin x;
-        x.lo = (unsigned long long)__funnelshift_r(v[0], v[1], sh) | ((unsigned long long)__funnelshift_r(v[1], v[2], sh) << 32);
-        x.hi = (unsigned long long)__funnelshift_r(v[2], v[3], sh) | ((unsigned long long)__funnelshift_r(v[3], v[4], sh) << 32);
+        const FdWin x = fdWindow(words, (uint32_t)(base + pos));
         int np;
-        const int len = fdHopLen<T>(x, (left - pos >= 24) ? a.stream + start + pos : nullptr, version, left - pos, tailRaw, np);   // byte-wise parser (LUT blocks) reads the stream directly
+        const int len = fdHopLen<T>(x, (left - pos >= 24) ? sReg + base + pos : nullptr, version, left - pos, tailRaw, np);   // byte-wise parser (LUT blocks) reads the staged bytes
         // lengths are recorded as bytes; 255 stands for the raw 8x8 block (the only unit that can be longer)
         const int code = len == 1 + 64 * (int)sizeof(T) ? 255 : len;
         if (len <= 0 || (code != 255 && len >= 255) || cnt >= FD_MAXHOP || (cnt > 0 && !fdFollows(pat, np, version))) { ok = false; break; }
@@ -717,6 +722,10 @@ __global__ void __launch_bounds__(FD_DWARPS * 32) k_dec_blocks(FastDecArgs a) {
   if (tid == 0 && sWhy) atomicOr(a.status, DECF_FALLBACK | sWhy);
 }
 
+template <class T> inline size_t fastDecodeWalkSmem() {
+  constexpr int MAXU = 1 + 64 * (int)sizeof(T);
+  return (size_t)FD_REG * FD_SUB + ((MAXU + 64 + 15) / 16) * 16 + 32;
+}
 template <class T> inline size_t fastDecodeBlocksSmem() {
   constexpr int MAXU = 1 + 64 * (int)sizeof(T);
   constexpr int BUFB = ((FD_SUB + MAXU + 64 + 15) / 16) * 16;

@@ -52,6 +52,8 @@ def test_c3_band_properties_device_resident(libs):
     xx = torch.arange(n, device="cuda", dtype=torch.float32)
     img = (1000 + 300 * torch.sin(xx[None, :] / 97) * torch.cos(xx[:, None] / 131) + 50 * torch.sin(xx[None, :] / 13 + xx[:, None] / 17)
            + 0.5 * torch.randn(n, n, device="cuda")).contiguous()
+    # the library works on its own (non-blocking) stream unless lerc_b200_set_stream is used: the raster must be complete
+    torch.cuda.synchronize()
     cap = n * n * 4 + (1 << 20)
     blob = torch.empty(cap, dtype=torch.uint8, device="cuda")
     out = torch.empty_like(img)
