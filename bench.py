@@ -151,7 +151,7 @@ def main():
         base, ms = cpu_reference_run(args.workload, seconds_budget=max(10.0, 2.0 * args.steps))
         line = {"impl": "reference", "metric": METRIC[args.workload], "value": base["value"], "unit": "Gpixels/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f64" if dt >= 6 else "int32", "data": "synthetic", "config": {"workload": desc, "sample": base["sample"]},
+                "dtype": "f64" if dt >= 6 else "u8", "data": "synthetic", "config": {"workload": desc, "sample": base["sample"]},
                 "cpu_baseline": base, "e2e": {"value": base["value"], "unit": "Gpixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line))
@@ -271,6 +271,10 @@ def main():
         "k_tiles_decode": (raw_bytes + blob_bytes, "blob read + raster write (general path)"),
         "k_walk_units": (blob_bytes, "block stream (general path, serial walk)"),
         "k_huffman": (raw_bytes + blob_bytes, "raster read + bit stream written"),
+        "k_huff_chunks": (blob_bytes, "bit stream read once per synchronisation pass"),
+        "k_huff_emit": (raw_bytes + blob_bytes, "bit stream read + symbols written"),
+        "k_huff_rows": (2 * raw_bytes, "delta image read + raster written"),
+        "k_histograms": (raw_bytes, "raster read"),
     }
     algo_bytes, which = raw_bytes + blob_bytes, "raster + blob"
     for key, (ab, wh) in algo_table.items():
@@ -331,7 +335,7 @@ def main():
             cpu, _ = cpu_reference_run(args.workload, seconds_budget=15.0)
         line = {"metric": METRIC[args.workload],
                 "value": value, "unit": "Gpixels/s", "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms_per_step,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64" if dt >= 6 else "int32", "data": "synthetic",
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64" if dt >= 6 else "u8", "data": "synthetic",
                 "config": {"workload": desc, "generator": "tests/cases.py", "blob_bytes": blob_bytes, "compression_ratio": raw_bytes / blob_bytes,
                            "l2": f"{NBUF} rotating raster/blob/output sets ({NBUF * (2 * raw_bytes + blob_bytes) // 2**20} MiB touched between reuses) > 126 MB L2",
                            "sharding": "one independent raster per rank, no data-path collective" if world > 1 else "single GPU"},

@@ -43,6 +43,20 @@ void Arena::reset() {
   retired.clear();
 }
 
+void Context::forkSide() {
+  cudaEventRecord(evFork, stream);
+  cudaStreamWaitEvent(side, evFork, 0);
+  mainSaved = stream; stream = side;
+}
+void Context::backToMain() {
+  cudaEventRecord(evJoin, side);
+  stream = mainSaved; mainSaved = nullptr;
+  sidePending = true;
+}
+void Context::joinSide() {
+  if (sidePending) { cudaStreamWaitEvent(stream, evJoin, 0); sidePending = false; }
+}
+
 void* Context::pinnedAlloc(size_t bytes) {
   size_t off = (pinnedUsed + 63) / 64 * 64;
   if (off + bytes > pinnedCap) return nullptr;
@@ -102,6 +116,9 @@ Context* acquireContext() {
   Context* c = new Context();
   c->device = dev;
   if (!cudaOk(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate")) { delete c; return nullptr; }
+  if (!cudaOk(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking), "cudaStreamCreate") ||
+      !cudaOk(cudaEventCreateWithFlags(&c->evFork, cudaEventDisableTiming), "cudaEventCreate") ||
+      !cudaOk(cudaEventCreateWithFlags(&c->evJoin, cudaEventDisableTiming), "cudaEventCreate")) { delete c; return nullptr; }
   c->pinnedCap = (size_t)1 << 20;
   if (!cudaOk(cudaMallocHost(&c->pinned, c->pinnedCap), "cudaMallocHost")) { cudaStreamDestroy(c->stream); delete c; return nullptr; }
   return c;
@@ -109,6 +126,7 @@ Context* acquireContext() {
 
 void releaseContext(Context* c) {
   if (!c) return;
+  if (c->sidePending) { cudaStreamSynchronize(c->side); c->sidePending = false; }
   c->arena.reset();
   c->pinnedUsed = 0;
   std::lock_guard<std::mutex> lock(gMutex);

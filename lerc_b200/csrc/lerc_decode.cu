@@ -493,8 +493,10 @@ ErrCode decodeBandT(Context* ctx, DecodeBandArgs& a, BandMaskState& ms) {
     if (hd.blobSize < 14) return Failed;
     unsigned long long* dAcc = (unsigned long long*)ctx->arena.alloc(16);
     if (!dAcc) return Failed;
-    cudaMemsetAsync(dAcc, 0, 16, st);
+    ctx->forkSide();                                   // the checksum only reads the blob: it runs beside the decode kernels
+    cudaMemsetAsync(dAcc, 0, 16, ctx->stream);
     launchFletcher(ctx, blob + 14, (long long)hd.blobSize - 14, dAcc, nullptr, hd.checksum, dStatus);
+    ctx->backToMain();
   }
 
   // mask (Lerc2.cpp:961-1008)
@@ -524,6 +526,7 @@ ErrCode decodeBandT(Context* ctx, DecodeBandArgs& a, BandMaskState& ms) {
 
   auto finish = [&]() -> ErrCode {
     int hStatus[2] = {0, 1};
+    ctx->joinSide();
     if (!cudaOk(cudaMemcpyAsync(hStatus, dStatus, 8, cudaMemcpyDeviceToHost, st), "D2H status")) return Failed;
     if (!cudaOk(cudaStreamSynchronize(st), "sync")) return Failed;
     if (hStatus[0] != 0) return Failed;
@@ -617,6 +620,7 @@ ErrCode decodeBandT(Context* ctx, DecodeBandArgs& a, BandMaskState& ms) {
   // micro-block stream: single-kernel speculative decoder first (lerc_decode_fast.cuh)
   if (mayFast && launchDecodeFast<T>(ctx, hd, blob + pos, (size_t)hd.blobSize - pos, a.dData, dStatus)) {
     int hs = 0;
+    ctx->joinSide();
     if (!cudaOk(cudaMemcpyAsync(&hs, dStatus, 4, cudaMemcpyDeviceToHost, st), "D2H") || !cudaOk(cudaStreamSynchronize(st), "sync")) return Failed;
     if (hs && std::getenv("LERC_B200_VERBOSE")) std::fprintf(stderr, "[lerc_b200] fused decoder status %d\n", hs);
     if (!(hs & DECF_FALLBACK)) { if (hs == 0) globalStats().fastPathDecodes++; return (hs & 7) == 0 ? Ok : Failed; }
@@ -640,6 +644,7 @@ ErrCode decodeBandT(Context* ctx, DecodeBandArgs& a, BandMaskState& ms) {
   if (hd.numValidPixel != nPix && !ta.allValidImage && nDepth == 1 &&
       launchDecodeFast<T>(ctx, hd, ta.stream, (size_t)ta.streamLen, nullptr, dStatus, ms.dBits, ta.blockOff)) {
     int hs = 0;
+    ctx->joinSide();
     if (!cudaOk(cudaMemcpyAsync(&hs, dStatus, 4, cudaMemcpyDeviceToHost, st), "D2H") || !cudaOk(cudaStreamSynchronize(st), "sync")) return Failed;
     if (hs && std::getenv("LERC_B200_VERBOSE")) std::fprintf(stderr, "[lerc_b200] speculative block offsets status %d\n", hs);
     if (hs & 7) return Failed;
@@ -650,6 +655,7 @@ ErrCode decodeBandT(Context* ctx, DecodeBandArgs& a, BandMaskState& ms) {
     LERC_LAUNCH(ctx, k_walk_units, 1, 128, 0, ta);
     // a malformed chain must not reach the unpack kernel (its offsets would be garbage)
     int hs = 0;
+    ctx->joinSide();
     if (!cudaOk(cudaMemcpyAsync(&hs, dStatus, 4, cudaMemcpyDeviceToHost, st), "D2H") || !cudaOk(cudaStreamSynchronize(st), "sync")) return Failed;
     if (hs & DECF_BAD_STREAM) return Failed;
   }

@@ -644,7 +644,9 @@ bool encodeBandFast(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
     for (int i = 0; i < 9; i++) if (kErr[i] / 2 > maxZErr) { ra.fac[ra.n] = kFac[i]; ra.n++; }
     if (ra.n > 0) {
       int grid = (int)std::min<long long>((a.nCols + 255) / 256, 148);
+      ctx->forkSide();                                  // independent of the fused kernel: runs beside it
       LERC_LAUNCH(ctx, k_try_raise<T>, grid, 256, 0, (const T*)a.dData, (const uint8_t*)nullptr, 0LL, (long long)a.nCols, 1, ra, dRaise);
+      ctx->backToMain();
     }
   }
 
@@ -676,6 +678,7 @@ bool encodeBandFast(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
     const long long grid = std::min<long long>((nTiles + 7) / 8, (long long)ctasPerSm * std::max(sms, 1));   // all warps co-resident (look-back)
     LERC_LAUNCH(ctx, k_encode_warp<T>, (unsigned)grid, 256, smem, fa);
   }
+  ctx->joinSide();
   if (!cudaOk(cudaMemcpyAsync(hRes, dState, sizeof(HostRes), cudaMemcpyDeviceToHost, st), "D2H fast result")) { err = Failed; return true; }
   if (!cudaOk(cudaStreamSynchronize(st), "sync")) { err = Failed; return true; }
 

@@ -87,6 +87,15 @@ struct Arena {
 struct Context {
   int device = 0;
   cudaStream_t stream = nullptr;
+  // side stream for work that is independent of the main kernel chain (checksum of the blob on decode, the row-0
+  // maxZError test on encode): forkSide() makes it wait for everything issued on `stream` so far and switches `stream`
+  // to it; joinSide() switches back and makes `stream` wait for the side work.
+  cudaStream_t side = nullptr, mainSaved = nullptr;
+  cudaEvent_t evFork = nullptr, evJoin = nullptr;
+  bool sidePending = false;
+  void forkSide();
+  void backToMain();
+  void joinSide();
   Arena arena;              // device scratch, bump-allocated per API call
   uint8_t* pinned = nullptr;   // pinned host staging for small control transfers
   size_t pinnedCap = 0;
