@@ -661,13 +661,18 @@ bool encodeBandFast(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
   int dev = 0, sms = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (ctaTiles) {
     const size_t smem = (size_t)((FAST_TB * MAXB + 15) / 16 + 3) * 16 * 2 + 256 * 8 * sizeof(T);       // two staging images + the general path's pixel rows
-    static int ctasPerSm = 0;
-    if (!ctasPerSm) {
-      cudaFuncSetAttribute(k_encode_fused<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSm, k_encode_fused<T>, 256, smem) != cudaSuccess || ctasPerSm < 1) ctasPerSm = 1;
-    }
-    const long long grid = std::min<long long>(nTiles, (long long)ctasPerSm * std::max(sms, 1));   // all CTAs co-resident (look-back)
-    LERC_LAUNCH(ctx, k_encode_fused<T>, (unsigned)grid, 256, smem, fa);
+    static const int occ = [] { const char* e = std::getenv("LERC_B200_ENC_OCC"); const int v = e ? std::atoi(e) : 4; return (v == 5 || v == 6) ? v : 4; }();
+    auto launch = [&](auto kernel) {
+      static int ctasPerSm = 0;
+      if (!ctasPerSm) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSm, kernel, 256, smem) != cudaSuccess || ctasPerSm < 1) ctasPerSm = 1;
+      }
+      const long long grid = std::min<long long>(nTiles, (long long)ctasPerSm * std::max(sms, 1));   // all CTAs co-resident (look-back)
+      LaunchScope scope_(ctx, "k_encode_fused<T>");
+      kernel<<<(unsigned)grid, 256, smem, ctx->stream>>>(fa); ctx->kernelLaunches++;
+    };
+    if (occ == 6) launch(k_encode_fused<T, 6>); else if (occ == 5) launch(k_encode_fused<T, 5>); else launch(k_encode_fused<T, 4>);
   } else {
     const size_t smem = (size_t)((4 * MAXB + 15) / 16 + 3) * 16 * 8 + 256 * 8 * sizeof(T);               // one staging image per warp + the general path's pixel rows
     static int ctasPerSm = 0;

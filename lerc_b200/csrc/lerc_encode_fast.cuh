@@ -266,8 +266,8 @@ __device__ __noinline__ void fastGenericEmit(const FastEncArgs& a, uint32_t* sta
   orBits<8>(stage, (byte0 + (uint32_t)(osz + 3)) * 8 + (uint32_t)(r * w * nb), R, w * nb);
 }
 
-template <class T>
-__global__ void __launch_bounds__(256, 4) k_encode_fused(FastEncArgs a) {
+template <class T, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_encode_fused(FastEncArgs a) {
   using K = typename PixelTraits<T>::Key;
   constexpr bool isFlt = PixelTraits<T>::isFloat;
   constexpr int DT = PixelTraits<T>::code;
