@@ -313,6 +313,8 @@ __global__ void k_huffman_decode_seq(HuffDecArgs a) {
       for (int d = 0; d < a.D; d++) { const int s = nextSymbol(); if (!ok) break; data[k * a.D + d] = (T)(s - off); }
     }
   }
+  // the stream must hold the data words plus one read-ahead word (Lerc2.cpp:2583-2587)
+  if (ok && 4 * (((pos & 31) ? 1 : 0) + (pos >> 5) + 1) > a.streamLen) ok = 0;
   if (!ok) atomicOr(a.status, DECF_BAD_STREAM);
 }
 
@@ -409,6 +411,14 @@ int decodeHuffmanFast(Context* ctx, const HuffmanTable& t, const uint8_t* dStrea
       }
     }
   }
+  {  // the codes must be prefix free (the reference's tree build and the serial kernel's trie reject the table otherwise)
+    struct LC { uint32_t aligned; int len; };
+    LC all[256]; int nAll = 0;
+    for (int sIdx = 0; sIdx < 256; sIdx++) if (t.len[sIdx]) { all[nAll].len = t.len[sIdx]; all[nAll].aligned = t.len[sIdx] == 32 ? t.code[sIdx] : (t.code[sIdx] << (32 - t.len[sIdx])); nAll++; }
+    for (int i = 0; i < nAll; i++)
+      for (int j = 0; j < nAll; j++)
+        if (i != j && all[i].len <= all[j].len && (all[j].aligned >> (32 - all[i].len)) == (all[i].aligned >> (32 - all[i].len))) return 0;
+  }
   const unsigned long long nBits = (unsigned long long)(streamLen / 4) * 32;
   if (nBits < 64) return 0;
   const unsigned long long nSym = (unsigned long long)H * W * D;
@@ -417,15 +427,15 @@ int decodeHuffmanFast(Context* ctx, const HuffmanTable& t, const uint8_t* dStrea
   unsigned long long* dArr = (unsigned long long*)ctx->arena.alloc((size_t)nChunks * 8 * 3);
   uint32_t* dCount = (uint32_t*)ctx->arena.alloc((size_t)(nChunks + 1) * 4);
   uint32_t* dBase = (uint32_t*)ctx->arena.alloc((size_t)(nChunks + 1) * 4);
-  int* dFlags = (int*)ctx->arena.alloc(16);
-  int* hFlags = (int*)ctx->pinnedAlloc(16);
+  int* dFlags = (int*)ctx->arena.alloc(32);
+  int* hFlags = (int*)ctx->pinnedAlloc(32);
   if (!dT || !dArr || !dCount || !dBase || !dFlags || !hFlags) return 0;
   cudaMemcpyAsync(dT, hT, sizeof(HuffFastTables), cudaMemcpyHostToDevice, st);
-  cudaMemsetAsync(dFlags, 0, 16, st);
+  cudaMemsetAsync(dFlags, 0, 32, st);
   cudaMemsetAsync(dCount + nChunks, 0, 4, st);
   HuffFastArgs ha;
   ha.stream = dStream; ha.nBits = nBits; ha.tab = dT; ha.nSym = nSym; ha.nChunks = nChunks;
-  ha.startA = dArr; ha.endA = dArr + nChunks; ha.endB = dArr + 2 * (size_t)nChunks; ha.count = dCount; ha.changed = dFlags; ha.bad = dFlags + 1;
+  ha.startA = dArr; ha.endA = dArr + nChunks; ha.endB = dArr + 2 * (size_t)nChunks; ha.count = dCount; ha.changed = dFlags; ha.bad = dFlags + 1; ha.endBit = (unsigned long long*)(dFlags + 4);
   const int grid = (nChunks + 255) / 256;
   int iter = 0;
   for (;; iter++) {
@@ -462,8 +472,12 @@ int decodeHuffmanFast(Context* ctx, const HuffmanTable& t, const uint8_t* dStrea
     LERC_LAUNCH(ctx, k_huff_col0, D, 256, 0, dPlanes, H, W, D, off, dCol0);
     LERC_LAUNCH(ctx, k_huff_rows<T>, H, 256, 0, dPlanes, dCol0, H, W, D, off, (T*)dData);
   }
-  if (!cudaOk(cudaMemcpyAsync(hFlags, dFlags, 8, cudaMemcpyDeviceToHost, st), "D2H") || !cudaOk(cudaStreamSynchronize(st), "sync")) return -1;
+  if (!cudaOk(cudaMemcpyAsync(hFlags, dFlags, 32, cudaMemcpyDeviceToHost, st), "D2H") || !cudaOk(cudaStreamSynchronize(st), "sync")) return -1;
   if (hFlags[1]) return 0;
+  {  // the stream must hold the data words plus the read-ahead word (Lerc2.cpp:2583-2587)
+    unsigned long long endBit; std::memcpy(&endBit, hFlags + 4, 8);
+    if (endBit == 0 || 4 * (((endBit & 31) ? 1 : 0) + (size_t)(endBit >> 5) + 1) > streamLen) return 0;
+  }
   globalStats().fastPathDecodes++;
   return 1;
 }

@@ -638,6 +638,7 @@ __global__ void __launch_bounds__(FD_DWARPS * 32) k_dec_blocks(FastDecArgs a) {
         T out[8];
         int len = 0;
         if (rc == 0 || fdPattern((uint32_t)win.lo & 0xff, version) != (tx & (version >= 5 ? 14 : 15))) { fallback = true; why |= 512; }
+        else if (rc > 0 && q.len > MAXU) { fallback = true; why |= 32768; }   // longer than the staged look-ahead: general decoder
         else if (rc > 0) {
           len = q.len;
           if (q.mode == 2) {

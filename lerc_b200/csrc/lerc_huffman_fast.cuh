@@ -42,6 +42,7 @@ struct HuffFastArgs {
   unsigned long long* startA; unsigned long long* endA; unsigned long long* endB;   // [nChunks]
   uint32_t* count;                                      // [nChunks + 1]
   int* changed; int* bad;
+  unsigned long long* endBit;                           // bit position after the band's last symbol
 };
 
 // 32 bits starting at bit position p (MSB first inside little-endian words), stream pointer of any alignment
@@ -113,6 +114,7 @@ __global__ void __launch_bounds__(256) k_huff_emit(HuffFastArgs a, const unsigne
     if (!len) { atomicOr(a.bad, 1); break; }                               // no code on the true chain: the serial decoder decides
     out[n++] = (uint8_t)sym;
     p += len;
+    if (n == a.nSym) *a.endBit = p;
   }
 }
 
