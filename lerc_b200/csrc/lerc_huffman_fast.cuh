@@ -57,6 +57,33 @@ __device__ __forceinline__ uint32_t hfPeek(const uint8_t* __restrict__ s, unsign
   return __funnelshift_l(w1, w0, o);                                                // (w0 << o) | (w1 >> (32 - o))
 }
 
+// Sequential MSB-first bit reader over little-endian 32-bit stream words (stream pointer of any alignment):
+// 64-bit window, one aligned 32-bit load per 32 consumed bits.
+struct HfReader {
+  const uint32_t* al; uint32_t sh;      // aligned word pointer of stream word `next`, byte misalignment * 8
+  uint32_t carry;                       // aligned word already loaded (low part of the next stream word)
+  unsigned long long buf; int avail;    // bits of the stream starting at the current position, left aligned
+  __device__ __forceinline__ uint32_t word() {                     // next stream word
+    const uint32_t hi = __ldg(al + 1);
+    const uint32_t w = __funnelshift_r(carry, hi, sh);
+    carry = hi; al++;
+    return w;
+  }
+  __device__ __forceinline__ void init(const uint8_t* __restrict__ s, unsigned long long p) {
+    const uintptr_t ad = (uintptr_t)(s + (p >> 5) * 4);
+    al = (const uint32_t*)(ad & ~(uintptr_t)3); sh = (uint32_t)(ad & 3) * 8;
+    carry = __ldg(al);
+    const uint32_t w0 = word(), w1 = word();
+    const uint32_t o = (uint32_t)(p & 31);
+    buf = (((unsigned long long)w0 << 32) | w1) << o; avail = 64 - (int)o;
+  }
+  __device__ __forceinline__ uint32_t peek32() const { return (uint32_t)(buf >> 32); }
+  __device__ __forceinline__ void consume(int len) {
+    buf <<= len; avail -= len;
+    if (avail <= 32) { buf |= (unsigned long long)word() << (32 - avail); avail += 32; }
+  }
+};
+
 // one symbol at bit position p: returns its length (0 = the 32 bits are no code) and the symbol
 __device__ __forceinline__ int hfDecodeOne(const HuffFastTables* __restrict__ t, const uint16_t* __restrict__ sLut, uint32_t bits32, int& sym) {
   const uint32_t e = sLut[bits32 >> 20];
@@ -87,10 +114,20 @@ __global__ void __launch_bounds__(256) k_huff_chunks(HuffFastArgs a, int iter) {
   }
   a.startA[t] = start;
   unsigned long long p = start; uint32_t cnt = 0;
-  while (p < chunkEnd) {
+  if (p < chunkEnd && p + 192 <= a.nBits) {
+    HfReader rd; rd.init(a.stream, p);
+    const unsigned long long safeEnd = a.nBits - 192;                      // the reader runs up to two words ahead
+    while (p < chunkEnd && p <= safeEnd) {
+      int sym; int len = hfDecodeOne(a.tab, sLut, rd.peek32(), sym);
+      cnt += len ? 1 : 0;
+      len = len ? len : 1;                                                 // a speculative start may see a non-code: skip a bit
+      rd.consume(len); p += len;
+    }
+  }
+  while (p < chunkEnd) {                                                   // last words of the stream: position-addressed reads
     if (p + 32 > a.nBits) { p = chunkEnd; break; }                         // inside the read-ahead padding
     int sym; const int len = hfDecodeOne(a.tab, sLut, hfPeek(a.stream, p), sym);
-    p += len ? len : 1;                                                    // a speculative start may see a non-code: skip a bit
+    p += len ? len : 1;
     cnt += len ? 1 : 0;
   }
   endCur[t] = p; a.count[t] = cnt;
@@ -108,10 +145,22 @@ __global__ void __launch_bounds__(256) k_huff_emit(HuffFastArgs a, const unsigne
   const unsigned long long chunkEnd = min((unsigned long long)(t + 1) * HF_CHUNK, a.nBits);
   unsigned long long p = t == 0 ? 0ull : endFinal[t - 1];
   unsigned long long n = symBase[t];
-  while (p < chunkEnd && n < a.nSym) {
+  bool stop = false;
+  if (p < chunkEnd && p + 192 <= a.nBits) {
+    HfReader rd; rd.init(a.stream, p);
+    const unsigned long long safeEnd = a.nBits - 192;
+    while (p < chunkEnd && n < a.nSym && p <= safeEnd) {
+      int sym; const int len = hfDecodeOne(a.tab, sLut, rd.peek32(), sym);
+      if (!len) { atomicOr(a.bad, 1); stop = true; break; }                // no code on the true chain: the serial decoder decides
+      out[n++] = (uint8_t)sym;
+      rd.consume(len); p += len;
+      if (n == a.nSym) *a.endBit = p;
+    }
+  }
+  while (!stop && p < chunkEnd && n < a.nSym) {
     if (p + 32 > a.nBits) { atomicOr(a.bad, 1); break; }
     int sym; const int len = hfDecodeOne(a.tab, sLut, hfPeek(a.stream, p), sym);
-    if (!len) { atomicOr(a.bad, 1); break; }                               // no code on the true chain: the serial decoder decides
+    if (!len) { atomicOr(a.bad, 1); break; }
     out[n++] = (uint8_t)sym;
     p += len;
     if (n == a.nSym) *a.endBit = p;

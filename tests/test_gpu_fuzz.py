@@ -53,7 +53,10 @@ def _cases():
     out = [("f32", c2_raster(264, 520), 0.01, {}),
            ("i16", np.clip(c2_raster(200, 333) * 3 - 2000, -32768, 32767).astype(np.int16), 0, {}),
            ("f32_masked", c2_raster(128, 256), 0.01, {"mask": (rng.random((128, 256)) > 0.1).astype(np.uint8)}),
-           ("u8x3", c4_raster(96, 128), 0, {"n_depth": 3})]
+           ("u8x3", c4_raster(96, 128), 0, {"n_depth": 3}),
+           ("u8x3_masked", c4_raster(64, 96), 0, {"n_depth": 3, "mask": (rng.random((64, 96)) > 0.2).astype(np.uint8)}),
+           ("f64", c2_raster(72, 200).astype(np.float64), 0.001, {}),
+           ("f32_2bands", np.stack([c2_raster(64, 128, seed=1), c2_raster(64, 128, seed=2)]), 0.01, {"n_bands": 2})]
     return out
 
 
