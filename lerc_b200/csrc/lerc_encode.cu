@@ -520,29 +520,43 @@ __device__ inline unsigned long long symbolIndex(const HuffArgs& a, unsigned lon
 // code lengths of every segment, a scan turns them into bit offsets, pass 2 ORs the codes into a zeroed,
 // word-aligned scratch stream (MSB first inside little-endian 32-bit words, Huffman.h:218-255).
 template <class T, bool WRITE>
-__global__ void k_huffman_segments(HuffArgs a, unsigned long long* __restrict__ segBits, const unsigned long long* __restrict__ segOff,
+__global__ void __launch_bounds__(256) k_huffman_segments(HuffArgs a, unsigned long long* __restrict__ segBits, const unsigned long long* __restrict__ segOff,
                                    uint32_t* __restrict__ words) {
+  // WRITE: a segment's bits are assembled in a per-warp shared-memory window (shared-memory atomics), then stored; only the
+  // first and last word of the segment are shared with the neighbouring segments and go through global atomics.
+  constexpr int NW = 640;                                  // window words per warp (a 1024-pixel segment at 20 bits/pixel)
+  __shared__ uint32_t sWin[WRITE ? 8 * NW : 1];
   const T* data = (const T*)a.data;
-  const int lane = threadIdx.x & 31, warpsPerCta = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31, warpsPerCta = blockDim.x >> 5, warp = threadIdx.x >> 5;
   const long long nPix = (long long)a.H * a.W;
   const int nChunks = (int)((nPix + 1023) >> 10);
   const long long nSeg = a.delta ? (long long)nChunks * a.D : nChunks;
   const int off = PixelTraits<T>::code == DT_Char ? 128 : 0;
-  for (long long seg = (long long)blockIdx.x * warpsPerCta + (threadIdx.x >> 5); seg < nSeg; seg += (long long)gridDim.x * warpsPerCta) {
+  for (long long seg = (long long)blockIdx.x * warpsPerCta + warp; seg < nSeg; seg += (long long)gridDim.x * warpsPerCta) {
     const int chunk = a.delta ? (int)(seg % nChunks) : (int)seg;
     const int dFirst = a.delta ? (int)(seg / nChunks) : 0, dLast = a.delta ? dFirst + 1 : a.D;
     unsigned long long bitPos = WRITE ? segOff[seg] : 0, total = 0;
+    unsigned long long w0 = 0, w1 = 0; bool staged = false;
+    uint32_t* win = sWin + (WRITE ? warp * NW : 0);
+    if (WRITE) {
+      const unsigned long long endBit = segOff[seg + 1];
+      w0 = bitPos >> 5; w1 = endBit > bitPos ? ((endBit - 1) >> 5) : w0;
+      staged = (w1 - w0 + 1) <= (unsigned long long)NW;
+      if (staged) { for (int i = lane; i <= (int)(w1 - w0); i += 32) win[i] = 0; __syncwarp(); }
+    }
     for (int step = 0; step < 32; step++) {
       const long long k = (long long)chunk * 1024 + step * 32 + lane;
       const bool valid = k < nPix && (!a.bits || maskBit(a.bits, k));
       unsigned long long myBits = 0;
-      uint32_t codes[1]; (void)codes;
       const int i = valid ? (int)(k / a.W) : 0, j = valid ? (int)(k - (long long)i * a.W) : 0;
+      int syms[4]; int nd = 0;
       if (valid)
         for (int d = dFirst; d < dLast; d++) {
           const T val = data[k * a.D + d];
           const int sym = off + (int)(a.delta ? (T)(val - deltaPredictor(data, a.bits, k, i, j, a.W, a.D, d)) : val);
           myBits += a.len[sym];
+          if (nd < 4) syms[nd] = sym;
+          nd++;
         }
       // exclusive prefix of myBits over the lanes (stream order inside the step is lane order)
       unsigned long long incl = myBits;
@@ -550,17 +564,34 @@ __global__ void k_huffman_segments(HuffArgs a, unsigned long long* __restrict__ 
       const unsigned long long stepTotal = __shfl_sync(FULL, incl, 31);
       if (WRITE && valid) {
         unsigned long long bp = bitPos + incl - myBits;
-        for (int d = dFirst; d < dLast; d++) {
-          const T val = data[k * a.D + d];
-          const int sym = off + (int)(a.delta ? (T)(val - deltaPredictor(data, a.bits, k, i, j, a.W, a.D, d)) : val);
+        int q = 0;
+        for (int d = dFirst; d < dLast; d++, q++) {
+          int sym;
+          if (q < 4) sym = syms[q];
+          else { const T val = data[k * a.D + d]; sym = off + (int)(a.delta ? (T)(val - deltaPredictor(data, a.bits, k, i, j, a.W, a.D, d)) : val); }
           const int len = a.len[sym]; const uint32_t code = a.code[sym];
           const unsigned long long wi = bp >> 5; const int used = (int)(bp & 31);
-          if (32 - used >= len) atomicOr(&words[wi], code << (32 - used - len));
-          else { const int spill = len - (32 - used); atomicOr(&words[wi], code >> spill); atomicOr(&words[wi + 1], code << (32 - spill)); }
+          if (staged) {
+            if (32 - used >= len) atomicOr(&win[wi - w0], code << (32 - used - len));
+            else { const int spill = len - (32 - used); atomicOr(&win[wi - w0], code >> spill); atomicOr(&win[wi - w0 + 1], code << (32 - spill)); }
+          } else {
+            if (32 - used >= len) atomicOr(&words[wi], code << (32 - used - len));
+            else { const int spill = len - (32 - used); atomicOr(&words[wi], code >> spill); atomicOr(&words[wi + 1], code << (32 - spill)); }
+          }
           bp += len;
         }
       }
       bitPos += stepTotal; total += stepTotal;
+    }
+    if (WRITE && staged) {
+      __syncwarp();
+      const int nw = (int)(w1 - w0) + 1;
+      for (int i = lane; i < nw; i += 32) {
+        const uint32_t v = win[i];
+        if (i == 0 || i == nw - 1) { if (v) atomicOr(&words[w0 + i], v); }      // shared with the neighbouring segment
+        else words[w0 + i] = v;
+      }
+      __syncwarp();
     }
     if (!WRITE && lane == 0) segBits[seg] = total;
   }
