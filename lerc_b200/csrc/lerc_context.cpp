@@ -91,13 +91,16 @@ void profileReport(char* buf, int bufLen, bool reset) {
 }
 
 Context* acquireContext() {
+  int dev = 0;
+  const cudaError_t devErr = cudaGetDevice(&dev);
   {
     std::lock_guard<std::mutex> lock(gMutex);
     if (gNoDevice) return nullptr;
-    if (!gFree.empty()) { Context* c = gFree.back(); gFree.pop_back(); cudaSetDevice(c->device); return c; }
+    if (devErr == cudaSuccess)                      // contexts are bound to the device that was current when they were created
+      for (size_t i = gFree.size(); i-- > 0;)
+        if (gFree[i]->device == dev) { Context* c = gFree[i]; gFree.erase(gFree.begin() + (long)i); return c; }
   }
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) {
+  if (devErr != cudaSuccess) {
     // No usable CUDA device: the product has no CPU fallback by design; every call fails loudly.
     std::lock_guard<std::mutex> lock(gMutex);
     gNoDevice = true;
