@@ -29,8 +29,10 @@ namespace lerc {
 enum { DECF_FALLBACK = 8 };
 constexpr int FD_SUB = 4096;          // sub-chunk bytes
 constexpr int FD_CAND = 16;           // surviving entry candidates kept per sub-chunk / region
-constexpr int FD_MAXHOP = 504;        // recorded unit lengths per candidate (multiple of 8)
-constexpr int FD_LENS = 512;          // bytes reserved per candidate for them
+constexpr int FD_MAXHOP = 4096;       // blocks per sub-chunk a chain may hold (1-byte blocks fill a sub-chunk with 4096)
+constexpr int FD_LENS = 512;          // bytes reserved per candidate for its unit lengths, run-length coded:
+constexpr int FD_PAIRS = 252;         //   up to FD_PAIRS (length code, repeat) byte pairs, pair count as uint16 at byte FD_LENS - 2
+constexpr int FD_BATCH = 512;         // block positions expanded at a time in k_dec_blocks / k_dec_offsets
 constexpr uint32_t FD_DEAD = 0xffffffffu;
 constexpr int FD_REG = 16;            // sub-chunks per region (one CTA of k_dec_walk / k_dec_blocks)
 
@@ -313,19 +315,31 @@ __global__ void __launch_bounds__(256) k_dec_walk(FastDecArgs a) {
       bool ok = true;
       unsigned long long acc = 0;
       uint8_t* lens = a.lens + ((size_t)s * FD_CAND + j) * FD_LENS;
+      int nPairs = 0, curCode = -1, curRun = 0;
+      // unit lengths are recorded as (code, repeat) pairs: code 255 stands for the raw 8x8 block (the only unit that can be
+      // longer than 254 bytes); flat regions (1..5-byte blocks, thousands per sub-chunk) collapse into a few pairs
+      auto flushPair = [&]() {
+        acc |= (unsigned long long)((unsigned)curCode | ((unsigned)curRun << 8)) << (16 * (nPairs & 3));
+        if ((nPairs & 3) == 3) { *(unsigned long long*)(lens + (nPairs & ~3) * 2) = acc; acc = 0; }
+        nPairs++;
+      };
       while (pos < subEnd) {
         const FdWin x = fdWindow(words, (uint32_t)(base + pos));
         int np;
         const int len = fdHopLen<T>(x, (left - pos >= 24) ? sReg + base + pos : nullptr, version, left - pos, tailRaw, np);   // byte-wise parser (LUT blocks) reads the staged bytes
-        // lengths are recorded as bytes; 255 stands for the raw 8x8 block (the only unit that can be longer)
         const int code = len == 1 + 64 * (int)sizeof(T) ? 255 : len;
         if (len <= 0 || (code != 255 && len >= 255) || cnt >= FD_MAXHOP || (cnt > 0 && !fdFollows(pat, np, version))) { ok = false; break; }
-        acc |= (unsigned long long)code << (8 * (cnt & 7));
-        if ((cnt & 7) == 7) { *(unsigned long long*)(lens + (cnt & ~7)) = acc; acc = 0; }
+        if (code == curCode && curRun < 255) curRun++;
+        else {
+          if (curCode >= 0) { if (nPairs >= FD_PAIRS) { ok = false; break; } flushPair(); }
+          curCode = code; curRun = 1;
+        }
         pos += len; cnt++; pat = np;
       }
+      if (ok && curCode >= 0) { if (nPairs >= FD_PAIRS) ok = false; else flushPair(); }
       if (ok) {
-        if (cnt & 7) *(unsigned long long*)(lens + (cnt & ~7)) = acc;
+        if (nPairs & 3) *(unsigned long long*)(lens + (nPairs & ~3) * 2) = acc;
+        *(uint16_t*)(lens + FD_LENS - 2) = (uint16_t)nPairs;
         e.entry = (uint32_t)c.entry + (uint32_t)s * FD_SUB; e.exit = (uint32_t)pos + (uint32_t)s * FD_SUB; e.count = (uint32_t)cnt;
       }
     }
@@ -350,6 +364,54 @@ __global__ void __launch_bounds__(256) k_dec_walk(FastDecArgs a) {
     }
     if (lane < FD_CAND) a.regTab[(size_t)reg * FD_CAND + lane] = cur;
   }
+}
+
+// ---- block positions from a candidate's run-length coded unit lengths -----------------------------------
+// fdLoadPairs gives every (length, repeat) pair its first block index and first byte position (per-warp table in
+// shared memory: [0..255] length, [256..511] first index, [512..767] first position, [768..1023] repeat).
+constexpr int FD_PTAB = 1024;
+template <int MAXU>
+__device__ __forceinline__ void fdLoadPairs(const uint8_t* __restrict__ lens, uint32_t firstPos, int lane, uint16_t* __restrict__ tab) {
+  const int nPairs = (int)*(const uint16_t*)(lens + FD_LENS - 2);
+  unsigned long long raw[2] = {0ull, 0ull};
+  if (lane * 8 < nPairs) { raw[0] = *(const unsigned long long*)(lens + lane * 16); raw[1] = *(const unsigned long long*)(lens + lane * 16 + 8); }
+  uint32_t nb = 0, by = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const uint32_t pr = (uint32_t)(raw[k >> 2] >> (16 * (k & 3))) & 0xffffu;
+    const uint32_t code = pr & 0xff, run = (lane * 8 + k < nPairs) ? (pr >> 8) : 0u;
+    nb += run; by += run * (code == 255 ? (uint32_t)MAXU : code);
+  }
+  uint32_t inb = nb, iby = by;
+#pragma unroll
+  for (int m = 1; m < 32; m <<= 1) {
+    const uint32_t o1 = __shfl_up_sync(FULL, inb, m), o2 = __shfl_up_sync(FULL, iby, m);
+    if (lane >= m) { inb += o1; iby += o2; }
+  }
+  uint32_t bi = inb - nb, pi = firstPos + iby - by;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const uint32_t pr = (uint32_t)(raw[k >> 2] >> (16 * (k & 3))) & 0xffffu;
+    const uint32_t code = pr & 0xff, run = (lane * 8 + k < nPairs) ? (pr >> 8) : 0u;
+    const uint32_t len = code == 255 ? (uint32_t)MAXU : code;
+    const int j = lane * 8 + k;
+    tab[j] = (uint16_t)len; tab[256 + j] = (uint16_t)bi; tab[512 + j] = (uint16_t)pi; tab[768 + j] = (uint16_t)run;
+    bi += run; pi += run * len;
+  }
+  __syncwarp();
+}
+// sPos[i - batchBase] = start of block i for batchBase <= i <= min(cnt, batchBase + FD_BATCH) (index cnt = the chain's exit)
+__device__ __forceinline__ void fdFillBatch(const uint16_t* __restrict__ tab, int batchBase, int cnt, uint32_t exitRel, int lane, uint16_t* __restrict__ sPos) {
+  const int hiIdx = min(cnt, batchBase + FD_BATCH);                  // last index wanted (inclusive)
+  for (int j = lane; j < 256; j += 32) {
+    const int run = tab[768 + j];
+    if (!run) continue;
+    const int idx0 = tab[256 + j], len = tab[j], pos0 = tab[512 + j];
+    const int i0 = max(idx0, batchBase), i1 = min(idx0 + run, hiIdx + 1);
+    for (int i = i0; i < i1; i++) sPos[i - batchBase] = (uint16_t)(pos0 + (i - idx0) * len);
+  }
+  if (lane == 0 && cnt >= batchBase && cnt <= hiIdx) sPos[cnt - batchBase] = (uint16_t)exitRel;
+  __syncwarp();
 }
 
 // ================= kernel 3: true entry of every region ==============================================
@@ -441,7 +503,8 @@ constexpr int FD_DWARPS = 8;
 template <class T>
 __global__ void __launch_bounds__(FD_DWARPS * 32) k_dec_offsets(FastDecArgs a, const uint8_t* __restrict__ bits, uint32_t* __restrict__ blockOff) {
   constexpr int MAXU = 1 + 64 * (int)sizeof(T);
-  __shared__ uint16_t sPosAll[FD_DWARPS * FD_LENS];
+  __shared__ uint16_t sPosAll[FD_DWARPS * (FD_BATCH + 8)];
+  __shared__ uint16_t sPairsAll[FD_DWARPS * FD_PTAB];
   __shared__ FdEntry sTab[FD_REG * FD_CAND];
   __shared__ uint32_t sTrue[(FD_REG + 1) * 3];
   __shared__ int sWhy;
@@ -474,7 +537,8 @@ __global__ void __launch_bounds__(FD_DWARPS * 32) k_dec_offsets(FastDecArgs a, c
 
   const int tailRaw = 1 + (a.nRows - (a.nTy - 1) * 8) * (a.nCols - (a.nTx - 1) * 8) * (int)sizeof(T);
   (void)tailRaw; (void)version;
-  uint16_t* sPos = sPosAll + warp * FD_LENS;
+  uint16_t* sPos = sPosAll + warp * (FD_BATCH + 8);
+  uint16_t* sPairs = sPairsAll + warp * FD_PTAB;
   for (int ls = warp; ls < nLocal; ls += FD_DWARPS) {
     const uint32_t pos0 = sTrue[3 * ls], blk0 = sTrue[3 * ls + 1], slot = sTrue[3 * ls + 2];
     if (pos0 >= FD_DEAD - 1) continue;
@@ -483,45 +547,29 @@ __global__ void __launch_bounds__(FD_DWARPS * 32) k_dec_offsets(FastDecArgs a, c
     const FdEntry me = sTab[ls * FD_CAND + slot];
     const int cnt = (int)me.count;
     bool fallback = false; unsigned why = 0;
-    {
-      const uint8_t* lens = a.lens + ((size_t)s * FD_CAND + slot) * FD_LENS;
-      uint32_t run = pos0 - (uint32_t)s * FD_SUB;
-      for (int base = 0; base <= cnt; base += 256) {
-        const int i8 = base + lane * 8;
-        const unsigned long long l8 = i8 < cnt ? *(const unsigned long long*)(lens + i8) : 0ull;
-        uint32_t pre[8]; uint32_t sum = 0;
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-          const uint32_t c8 = (uint32_t)((l8 >> (8 * k)) & 0xff);
-          pre[k] = sum; sum += (i8 + k < cnt) ? (c8 == 255 ? (uint32_t)MAXU : c8) : 0u;
+    fdLoadPairs<MAXU>(a.lens + ((size_t)s * FD_CAND + slot) * FD_LENS, pos0 - (uint32_t)s * FD_SUB, lane, sPairs);
+    for (int batchBase = 0; batchBase < cnt; batchBase += FD_BATCH) {
+      fdFillBatch(sPairs, batchBase, cnt, me.exit - (uint32_t)s * FD_SUB, lane, sPos);
+      const int nB = min(FD_BATCH, cnt - batchBase);
+      for (int i = lane; i < nB; i += 32) {
+        const uint32_t b = blk0 + (uint32_t)(batchBase + i);
+        if (b >= (uint32_t)nBlocks) break;
+        const uint32_t p = sPos[i], len = (uint32_t)sPos[i + 1] - p;
+        const unsigned long long gp = (unsigned long long)s * FD_SUB + p;
+        const unsigned flag = a.stream[gp];
+        if ((flag & 3) == 0) {                                           // raw: 1 + (valid pixels of the block) * sizeof(T) bytes
+          const int ty = (int)b / a.nTx, tx = (int)b - ty * a.nTx;
+          const int h = min(8, a.nRows - ty * 8), w = min(8, a.nCols - tx * 8);
+          int nv = 0;
+          for (int rr = 0; rr < h; rr++) {
+            const long long k0 = (long long)(ty * 8 + rr) * a.nCols + tx * 8;
+            for (int c = 0; c < w; c++) nv += maskBit(bits, k0 + c) ? 1 : 0;
+          }
+          if (len != 1u + (uint32_t)nv * (uint32_t)sizeof(T)) { fallback = true; why |= 1024; }
         }
-        uint32_t inc = sum;
-#pragma unroll
-        for (int m = 1; m < 32; m <<= 1) { const uint32_t o = __shfl_up_sync(FULL, inc, m); if (lane >= m) inc += o; }
-        const uint32_t mine = run + inc - sum;
-#pragma unroll
-        for (int k = 0; k < 8; k++) if (i8 + k <= cnt) sPos[i8 + k] = (uint16_t)(mine + pre[k]);
-        run += __shfl_sync(FULL, inc, 31);
+        blockOff[b] = (uint32_t)gp;
       }
-    }
-    __syncwarp();
-    for (int i = lane; i < cnt; i += 32) {
-      const uint32_t b = blk0 + (uint32_t)i;
-      if (b >= (uint32_t)nBlocks) break;
-      const uint32_t p = sPos[i], len = (uint32_t)sPos[i + 1] - p;
-      const unsigned long long gp = (unsigned long long)s * FD_SUB + p;
-      const unsigned flag = a.stream[gp];
-      if ((flag & 3) == 0) {                                           // raw: 1 + (valid pixels of the block) * sizeof(T) bytes
-        const int ty = (int)b / a.nTx, tx = (int)b - ty * a.nTx;
-        const int h = min(8, a.nRows - ty * 8), w = min(8, a.nCols - tx * 8);
-        int nv = 0;
-        for (int rr = 0; rr < h; rr++) {
-          const long long k0 = (long long)(ty * 8 + rr) * a.nCols + tx * 8;
-          for (int c = 0; c < w; c++) nv += maskBit(bits, k0 + c) ? 1 : 0;
-        }
-        if (len != 1u + (uint32_t)nv * (uint32_t)sizeof(T)) { fallback = true; why |= 1024; }
-      }
-      blockOff[b] = (uint32_t)gp;
+      __syncwarp();
     }
     const uint32_t blkEnd = blk0 + (uint32_t)cnt;
     const bool haveNext = expectExit < FD_DEAD - 1;
@@ -540,7 +588,8 @@ __global__ void __launch_bounds__(FD_DWARPS * 32) k_dec_blocks(FastDecArgs a) {
   constexpr int MAXU = 1 + 64 * (int)sizeof(T);
   constexpr int BUFB = ((FD_SUB + MAXU + 64 + 15) / 16) * 16;       // per-warp staging of one sub-chunk (+ look-ahead)
   extern __shared__ __align__(16) uint8_t smemD[];                   // [FD_DWARPS][BUFB] stream staging
-  __shared__ uint16_t sPosAll[FD_DWARPS * FD_LENS];
+  __shared__ uint16_t sPosAll[FD_DWARPS * (FD_BATCH + 8)];
+  __shared__ uint16_t sPairsAll[FD_DWARPS * FD_PTAB];
   __shared__ FdEntry sTab[FD_REG * FD_CAND];
   __shared__ uint32_t sTrue[(FD_REG + 1) * 3];
   __shared__ int sWhy;
@@ -577,7 +626,8 @@ __global__ void __launch_bounds__(FD_DWARPS * 32) k_dec_blocks(FastDecArgs a) {
   const bool vecOk = ((a.nCols * (int)sizeof(T)) % 16 == 0) && (((uintptr_t)data & 15) == 0);
   const int g = lane >> 3, r = lane & 7;
   uint8_t* buf = bufAll + (size_t)warp * BUFB;
-  uint16_t* sPos = sPosAll + warp * FD_LENS;
+  uint16_t* sPos = sPosAll + warp * (FD_BATCH + 8);
+  uint16_t* sPairs = sPairsAll + warp * FD_PTAB;
   for (int ls = warp; ls < nLocal; ls += FD_DWARPS) {
     const uint32_t pos0 = sTrue[3 * ls], blk0 = sTrue[3 * ls + 1], slot = sTrue[3 * ls + 2];
     if (pos0 >= FD_DEAD - 1) continue;                               // dead chain (reported through sWhy) or past the end
@@ -598,36 +648,19 @@ __global__ void __launch_bounds__(FD_DWARPS * 32) k_dec_blocks(FastDecArgs a) {
         ((uint4*)buf)[i] = x;
       }
     }
-    // block positions from the recorded unit lengths: sPos[i] = start of block i, sPos[cnt] = exit
-    {
-      const uint8_t* lens = a.lens + ((size_t)s * FD_CAND + slot) * FD_LENS;
-      uint32_t run = pos0 - (uint32_t)s * FD_SUB;
-      for (int base = 0; base <= cnt; base += 256) {                 // 8 lengths per lane and round
-        const int i8 = base + lane * 8;
-        const unsigned long long l8 = i8 < cnt ? *(const unsigned long long*)(lens + i8) : 0ull;
-        uint32_t pre[8]; uint32_t sum = 0;
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-          const uint32_t c8 = (uint32_t)((l8 >> (8 * k)) & 0xff);
-          pre[k] = sum; sum += (i8 + k < cnt) ? (c8 == 255 ? (uint32_t)MAXU : c8) : 0u;
-        }
-        uint32_t inc = sum;
-#pragma unroll
-        for (int m = 1; m < 32; m <<= 1) { const uint32_t o = __shfl_up_sync(FULL, inc, m); if (lane >= m) inc += o; }
-        const uint32_t mine = run + inc - sum;
-#pragma unroll
-        for (int k = 0; k < 8; k++) if (i8 + k <= cnt) sPos[i8 + k] = (uint16_t)(mine + pre[k]);
-        run += __shfl_sync(FULL, inc, 31);
-      }
-    }
+    // block positions from the recorded unit lengths, FD_BATCH blocks at a time: sPos[i] = start of block batchBase + i
+    fdLoadPairs<MAXU>(a.lens + ((size_t)s * FD_CAND + slot) * FD_LENS, pos0 - (uint32_t)s * FD_SUB, lane, sPairs);
     __syncwarp();
     const uint8_t* sb = buf + d;
     const uint32_t* words = (const uint32_t*)buf;
     bool fallback = false; unsigned why = 0;
-    for (int i0 = 0; i0 < cnt; i0 += 4) {
+    for (int batchBase = 0; batchBase < cnt; batchBase += FD_BATCH) {
+    fdFillBatch(sPairs, batchBase, cnt, me.exit - (uint32_t)s * FD_SUB, lane, sPos);
+    const int nB = min(FD_BATCH, cnt - batchBase);
+    for (int i0 = 0; i0 < nB; i0 += 4) {
       const int i = i0 + g;
-      const uint32_t b = blk0 + (uint32_t)i;
-      if (i < cnt && b < (uint32_t)nBlocks) {
+      const uint32_t b = blk0 + (uint32_t)(batchBase + i);
+      if (i < nB && b < (uint32_t)nBlocks) {
         const int p = sPos[i], pNext = sPos[i + 1];
         const int ty = (int)b / a.nTx, tx = (int)b - ty * a.nTx;
         const int bi0 = ty * 8, bj0 = tx * 8;
@@ -709,6 +742,8 @@ __global__ void __launch_bounds__(FD_DWARPS * 32) k_dec_blocks(FastDecArgs a) {
           }
         }
       }
+    }
+    __syncwarp();
     }
     // the serial parse continues in the next sub-chunk where the resolution assumed, with the block index it assumed;
     // or the stream's blocks end in here

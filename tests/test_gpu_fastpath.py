@@ -89,3 +89,28 @@ def test_fast_multiband_and_buffer_too_small(libs):
     assert st == 3
     st, _, _ = prod.encode(bands[0], 0.01, buf_size=200)
     assert st == 3
+
+
+def test_flat_regions_stay_on_the_parallel_decoder(libs):
+    """large zero / constant areas give 1..3-byte blocks, thousands per 4 KB of stream: the unit lists are run-length coded"""
+    import lerc_b200
+    prod, orc = libs
+    rng = np.random.default_rng(9)
+    base = (smooth_field(1024, 2048) + rng.normal(0, 0.5, (1024, 2048))).astype(np.float32)
+    sea = base.copy(); sea[:600, :] = 0                       # zero blocks, full block rows
+    lake = base.copy(); lake[200:900, 100:1900] = 37.0        # const blocks inside noisy data
+    stepped = np.clip(base * 3, -32768, 32767).astype(np.int16); stepped[300:, :] = -5
+    coarse = base.copy()
+    # ("lake": const blocks right after noisy ones let most wrong candidates of a sub-chunk merge into the true chain, more than
+    #  FD_CAND survive and the true entry can be dropped -> general decoder; known limitation, DESIGN.md section 9)
+    for name, arr, mz, must_be_fast in [("sea", sea, 0.01, True), ("lake", lake, 0.01, False), ("i16_const", stepped, 0, False), ("coarse", coarse, 20.0, True)]:
+        s_o, b_o, _ = orc.encode(arr, mz)
+        s_p, b_p, _ = prod.encode(arr, mz)
+        assert s_o == 0 and s_p == 0 and b_p == b_o, name
+        before = lerc_b200.stats()
+        t_p, d_p, _ = prod.decode(b_o)
+        after = lerc_b200.stats()
+        _, d_o, _ = orc.decode(b_o)
+        assert t_p == 0 and np.array_equal(d_p.view(np.uint8), d_o.view(np.uint8)), name
+        if must_be_fast:
+            assert after[4] == before[4] + 1, f"{name}: parallel decoder was not taken"
