@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(256) k_dec_candidates(FastDecArgs a) {
   }
   __syncwarp();
   // ---- hop with in-place stable compaction until at most FD_CAND walkers are left (wrong candidates die fast)
-  for (int pass = 0; nW > FD_CAND && pass < 8; pass++) {
+  for (int pass = 0; nW > FD_CAND - 1 && pass < 8; pass++) {
     int nNew = 0; bool moved = false;
     for (int base = 0; base < nW; base += 32) {
       const int i = base + lane;
@@ -268,13 +268,54 @@ __global__ void __launch_bounds__(256) k_dec_candidates(FastDecArgs a) {
     if (!__any_sync(FULL, moved)) break;
   }
   // more than FD_CAND left: keep the lowest entries (the true entry is the lowest position on the true chain)
-  const int nKeep = min(nW, FD_CAND);
+  const int nKeep = min(nW, FD_CAND - 1);                           // one slot stays free for the closure pass of k_dec_walk
   if (lane < nKeep) { FdCand c; c.entry = wEnt[lane]; c.pos = wPos[lane]; c.cnt = wCnt[lane]; c.pat = wPat[lane]; a.cand[(size_t)s * FD_CAND + lane] = c; }
   if (lane == 0) a.nCand[s] = (uint8_t)nKeep;
 }
 
 // ================= kernel 2: one lane per candidate walks to the end of its sub-chunk ================
 // CTA = region (subPerReg consecutive sub-chunks); afterwards warp 0 composes the region's sub-chunk maps.
+// Walks the chain that starts at byte `entry` of sub-chunk s to the end of the sub-chunk (bytes of the region staged in
+// shared memory: stagedBytes[base + p] = stream[s * FD_SUB + p]), recording the unit lengths as (code, repeat) pairs: code
+// 255 stands for the raw 8x8 block (the only unit that can be longer than 254 bytes); flat regions (1..5-byte blocks,
+// thousands per sub-chunk) collapse into a few pairs.  Returns false when the chain dies.
+template <class T>
+__device__ __forceinline__ bool fdWalkChain(const FastDecArgs& a, const uint8_t* __restrict__ stagedBytes, int base, int s, int entry,
+                                            int version, int tailRaw, uint8_t* __restrict__ lens, FdEntry& e) {
+  const uint32_t* words = (const uint32_t*)stagedBytes;
+  const unsigned long long start = (unsigned long long)s * FD_SUB;
+  const long long left = (long long)(a.streamLen - start);
+  const int subEnd = (int)min((long long)FD_SUB, left);
+  int pos = entry, cnt = 0, pat = 0;
+  bool ok = true;
+  unsigned long long acc = 0;
+  int nPairs = 0, curCode = -1, curRun = 0;
+  auto flushPair = [&]() {
+    acc |= (unsigned long long)((unsigned)curCode | ((unsigned)curRun << 8)) << (16 * (nPairs & 3));
+    if ((nPairs & 3) == 3) { *(unsigned long long*)(lens + (nPairs & ~3) * 2) = acc; acc = 0; }
+    nPairs++;
+  };
+  while (pos < subEnd) {
+    const FdWin x = fdWindow(words, (uint32_t)(base + pos));
+    int np;
+    const int len = fdHopLen<T>(x, (left - pos >= 24) ? stagedBytes + base + pos : nullptr, version, left - pos, tailRaw, np);   // byte-wise parser (LUT blocks) reads the staged bytes
+    const int code = len == 1 + 64 * (int)sizeof(T) ? 255 : len;
+    if (len <= 0 || (code != 255 && len >= 255) || cnt >= FD_MAXHOP || (cnt > 0 && !fdFollows(pat, np, version))) { ok = false; break; }
+    if (code == curCode && curRun < 255) curRun++;
+    else {
+      if (curCode >= 0) { if (nPairs >= FD_PAIRS) { ok = false; break; } flushPair(); }
+      curCode = code; curRun = 1;
+    }
+    pos += len; cnt++; pat = np;
+  }
+  if (ok && curCode >= 0) { if (nPairs >= FD_PAIRS) ok = false; else flushPair(); }
+  if (!ok) return false;
+  if (nPairs & 3) *(unsigned long long*)(lens + (nPairs & ~3) * 2) = acc;
+  *(uint16_t*)(lens + FD_LENS - 2) = (uint16_t)nPairs;
+  e.entry = (uint32_t)entry + (uint32_t)s * FD_SUB; e.exit = (uint32_t)pos + (uint32_t)s * FD_SUB; e.count = (uint32_t)cnt;
+  return true;
+}
+
 template <class T>
 __global__ void __launch_bounds__(256) k_dec_walk(FastDecArgs a) {
   __shared__ FdEntry sTab[FD_REG * FD_CAND];                        // [subPerReg <= FD_REG][FD_CAND]
@@ -306,47 +347,47 @@ __global__ void __launch_bounds__(256) k_dec_walk(FastDecArgs a) {
     FdEntry e; e.entry = FD_DEAD; e.exit = 0; e.count = 0;
     if (j < (int)a.nCand[s]) {
       const FdCand c = a.cand[(size_t)s * FD_CAND + j];
-      const unsigned long long start = (unsigned long long)s * FD_SUB;
-      const long long left = (long long)(a.streamLen - start);
-      const int subEnd = (int)min((long long)FD_SUB, left);
-      const int base = d + ls * FD_SUB;                               // sReg[base + p] = stream[start + p]
       // restart from the entry so that every unit length of the chain is recorded
-      int pos = c.entry, cnt = 0, pat = 0;
-      bool ok = true;
-      unsigned long long acc = 0;
-      uint8_t* lens = a.lens + ((size_t)s * FD_CAND + j) * FD_LENS;
-      int nPairs = 0, curCode = -1, curRun = 0;
-      // unit lengths are recorded as (code, repeat) pairs: code 255 stands for the raw 8x8 block (the only unit that can be
-      // longer than 254 bytes); flat regions (1..5-byte blocks, thousands per sub-chunk) collapse into a few pairs
-      auto flushPair = [&]() {
-        acc |= (unsigned long long)((unsigned)curCode | ((unsigned)curRun << 8)) << (16 * (nPairs & 3));
-        if ((nPairs & 3) == 3) { *(unsigned long long*)(lens + (nPairs & ~3) * 2) = acc; acc = 0; }
-        nPairs++;
-      };
-      while (pos < subEnd) {
-        const FdWin x = fdWindow(words, (uint32_t)(base + pos));
-        int np;
-        const int len = fdHopLen<T>(x, (left - pos >= 24) ? sReg + base + pos : nullptr, version, left - pos, tailRaw, np);   // byte-wise parser (LUT blocks) reads the staged bytes
-        const int code = len == 1 + 64 * (int)sizeof(T) ? 255 : len;
-        if (len <= 0 || (code != 255 && len >= 255) || cnt >= FD_MAXHOP || (cnt > 0 && !fdFollows(pat, np, version))) { ok = false; break; }
-        if (code == curCode && curRun < 255) curRun++;
-        else {
-          if (curCode >= 0) { if (nPairs >= FD_PAIRS) { ok = false; break; } flushPair(); }
-          curCode = code; curRun = 1;
-        }
-        pos += len; cnt++; pat = np;
-      }
-      if (ok && curCode >= 0) { if (nPairs >= FD_PAIRS) ok = false; else flushPair(); }
-      if (ok) {
-        if (nPairs & 3) *(unsigned long long*)(lens + (nPairs & ~3) * 2) = acc;
-        *(uint16_t*)(lens + FD_LENS - 2) = (uint16_t)nPairs;
-        e.entry = (uint32_t)c.entry + (uint32_t)s * FD_SUB; e.exit = (uint32_t)pos + (uint32_t)s * FD_SUB; e.count = (uint32_t)cnt;
-      }
+      FdEntry w;
+      if (fdWalkChain<T>(a, sReg, d + ls * FD_SUB, s, (int)c.entry, version, tailRaw, a.lens + ((size_t)s * FD_CAND + j) * FD_LENS, w)) e = w;
     }
     sTab[it] = e;
     a.subTab[(size_t)sub0 * FD_CAND + it] = e;
   }
   __syncthreads();
+  // ---- closure inside the region: every chain exit of sub-chunk ls - 1 must be an entry of sub-chunk ls.  The head-window
+  // speculation usually provides it; where it does not (e.g. when more wrong candidates than FD_CAND merged into the true chain
+  // and the true entry was not among the kept ones) the missing chain is walked now.  Sequential over the sub-chunks, lanes =
+  // the 16 exits of the previous one.
+  if (tid < 32) {
+    const int lane = tid;
+    for (int ls = 1; ls < nLocal; ls++) {
+      const int s = sub0 + ls;
+      uint32_t x = FD_DEAD;
+      if (lane < FD_CAND) { const FdEntry t = sTab[(ls - 1) * FD_CAND + lane]; if (t.entry != FD_DEAD) x = t.exit; }
+      const bool inSub = x != FD_DEAD && (unsigned long long)x < a.streamLen && x >= (uint32_t)s * FD_SUB && x < (uint32_t)(s + 1) * FD_SUB;
+      bool present = !inSub;
+      if (inSub) for (int e2 = 0; e2 < FD_CAND; e2++) present |= sTab[ls * FD_CAND + e2].entry == x;
+      unsigned miss = __ballot_sync(FULL, !present);
+      while (miss) {
+        const int src = __ffs(miss) - 1;
+        miss &= miss - 1;
+        const uint32_t xs = __shfl_sync(FULL, x, src);
+        if (lane == 0) {
+          bool have = false; int slot = -1;
+          for (int e2 = 0; e2 < FD_CAND; e2++) { const uint32_t en = sTab[ls * FD_CAND + e2].entry; have |= en == xs; if (en == FD_DEAD && slot < 0) slot = e2; }
+          if (!have && slot >= 0) {
+            FdEntry w;
+            if (fdWalkChain<T>(a, sReg, d + ls * FD_SUB, s, (int)(xs - (uint32_t)s * FD_SUB), version, tailRaw, a.lens + ((size_t)s * FD_CAND + slot) * FD_LENS, w)) {
+              sTab[ls * FD_CAND + slot] = w; a.subTab[(size_t)s * FD_CAND + slot] = w;
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+  __syncwarp();
   // ---- compose the sub-chunk maps of this region: lane j follows the chain that starts at entry j of the first sub-chunk
   if (tid < 32) {
     const int lane = tid;

@@ -103,7 +103,7 @@ def test_flat_regions_stay_on_the_parallel_decoder(libs):
     coarse = base.copy()
     # ("lake": const blocks right after noisy ones let most wrong candidates of a sub-chunk merge into the true chain, more than
     #  FD_CAND survive and the true entry can be dropped -> general decoder; known limitation)
-    for name, arr, mz, must_be_fast in [("sea", sea, 0.01, True), ("lake", lake, 0.01, False), ("i16_const", stepped, 0, False), ("coarse", coarse, 20.0, True)]:
+    for name, arr, mz, must_be_fast in [("sea", sea, 0.01, True), ("lake", lake, 0.01, True), ("i16_const", stepped, 0, False), ("coarse", coarse, 20.0, True)]:
         s_o, b_o, _ = orc.encode(arr, mz)
         s_p, b_p, _ = prod.encode(arr, mz)
         assert s_o == 0 and s_p == 0 and b_p == b_o, name
