@@ -359,7 +359,21 @@ __global__ void __launch_bounds__(256) k_dec_walk(FastDecArgs a) {
   // speculation usually provides it; where it does not (e.g. when more wrong candidates than FD_CAND merged into the true chain
   // and the true entry was not among the kept ones) the missing chain is walked now.  Sequential over the sub-chunks, lanes =
   // the 16 exits of the previous one.
-  if (tid < 32) {
+  // quick parallel check first (one warp per pair of neighbouring sub-chunks); the sequential pass runs only if something is missing
+  __shared__ int sMissing;
+  if (tid == 0) sMissing = 0;
+  __syncthreads();
+  for (int ls = 1 + (tid >> 5); ls < nLocal; ls += blockDim.x >> 5) {
+    const int lane = tid & 31, s = sub0 + ls;
+    uint32_t x = FD_DEAD;
+    if (lane < FD_CAND) { const FdEntry t = sTab[(ls - 1) * FD_CAND + lane]; if (t.entry != FD_DEAD) x = t.exit; }
+    const bool inSub = x != FD_DEAD && (unsigned long long)x < a.streamLen && x >= (uint32_t)s * FD_SUB && x < (uint32_t)(s + 1) * FD_SUB;
+    bool present = !inSub;
+    if (inSub) for (int e2 = 0; e2 < FD_CAND; e2++) present |= sTab[ls * FD_CAND + e2].entry == x;
+    if (__any_sync(FULL, !present) && lane == 0) sMissing = 1;
+  }
+  __syncthreads();
+  if (tid < 32 && sMissing) {
     const int lane = tid;
     for (int ls = 1; ls < nLocal; ls++) {
       const int s = sub0 + ls;
