@@ -153,3 +153,37 @@ def test_rle_against_reference_tokens(oracle):
     # a 5-run at the very end stays literal, a 6-run becomes a repeat token (RLE.cpp:74-79)
     five = np.zeros(5, np.uint8); six = np.zeros(6, np.uint8)
     assert lib.lo_rle_size(five.ctypes.data, 5) == 2 + 5 + 2 and lib.lo_rle_size(six.ctypes.data, 6) == 3 + 2
+
+
+def test_oracle_rejects_and_accepts_corrupted_blobs_like_the_reference(oracle):
+    """robustness pinning: 1-3 flipped bytes (checksum repaired so that the parsers are reached) -- the oracle's verdict and
+    pixels equal the unmodified reference's.  The GPU fuzz test (tests/test_gpu_fuzz.py) then holds the product to the oracle."""
+    from test_gpu_fuzz import repair
+    from cases import c2_raster, c4_raster
+    ref = ref_lib()
+    if ref is None:
+        pytest.skip("oracle/_ref/libLerc_ref.so absent")
+    rng = np.random.default_rng(5)
+    for arr, mz, kw in [(c2_raster(40, 41), 0.01, {}), (c4_raster(48, 64), 0, {"n_depth": 3}),
+                        (c2_raster(64, 64), 0.01, {"mask": (rng.random((64, 64)) > 0.2).astype(np.uint8)})]:
+        st, blob, _ = oracle.encode(arr, mz, **kw)
+        assert st == 0
+        st, info = oracle.blob_info(blob)
+        stricter = 0
+        for _ in range(60):
+            b = bytearray(blob)
+            for _ in range(int(rng.integers(1, 4))):
+                b[int(rng.integers(95, len(b)))] ^= int(rng.integers(1, 256))
+            bad = repair(bytes(b))
+            s_o, d_o, m_o = oracle.decode(bad, info=info)
+            s_r, d_r, m_r = ref.decode(bad, info=info)
+            if "mask" in kw and s_o != 0 and s_r == 0:
+                # A corrupted MASK can give a block more valid pixels than its bit-stuffed value count.  The reference then reads
+                # past the end of its value vector (Lerc2.cpp:2176-2199 has no bound check for version > 2: undefined behaviour,
+                # stale values of earlier blocks); the oracle and the product reject the blob.  Documented deviation (DESIGN.md).
+                stricter += 1
+                continue
+            assert (s_o == 0) == (s_r == 0)
+            if s_r == 0:
+                assert np.array_equal(d_o.view(np.uint8), d_r.view(np.uint8))
+        assert stricter <= 6
