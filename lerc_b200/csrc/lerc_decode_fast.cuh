@@ -426,7 +426,7 @@ __global__ void __launch_bounds__(256) k_dec_walk(FastDecArgs a) {
 // shared memory: [0..255] length, [256..511] first index, [512..767] first position, [768..1023] repeat).
 constexpr int FD_PTAB = 1024;
 template <int MAXU>
-__device__ __forceinline__ void fdLoadPairs(const uint8_t* __restrict__ lens, uint32_t firstPos, int lane, uint16_t* __restrict__ tab) {
+__device__ __forceinline__ int fdLoadPairs(const uint8_t* __restrict__ lens, uint32_t firstPos, int lane, uint16_t* __restrict__ tab) {
   const int nPairs = (int)*(const uint16_t*)(lens + FD_LENS - 2);
   unsigned long long raw[2] = {0ull, 0ull};
   if (lane * 8 < nPairs) { raw[0] = *(const unsigned long long*)(lens + lane * 16); raw[1] = *(const unsigned long long*)(lens + lane * 16 + 8); }
@@ -450,15 +450,16 @@ __device__ __forceinline__ void fdLoadPairs(const uint8_t* __restrict__ lens, ui
     const uint32_t code = pr & 0xff, run = (lane * 8 + k < nPairs) ? (pr >> 8) : 0u;
     const uint32_t len = code == 255 ? (uint32_t)MAXU : code;
     const int j = lane * 8 + k;
-    tab[j] = (uint16_t)len; tab[256 + j] = (uint16_t)bi; tab[512 + j] = (uint16_t)pi; tab[768 + j] = (uint16_t)run;
+    if (j < nPairs) { tab[j] = (uint16_t)len; tab[256 + j] = (uint16_t)bi; tab[512 + j] = (uint16_t)pi; tab[768 + j] = (uint16_t)run; }
     bi += run; pi += run * len;
   }
   __syncwarp();
+  return nPairs;
 }
 // sPos[i - batchBase] = start of block i for batchBase <= i <= min(cnt, batchBase + FD_BATCH) (index cnt = the chain's exit)
-__device__ __forceinline__ void fdFillBatch(const uint16_t* __restrict__ tab, int batchBase, int cnt, uint32_t exitRel, int lane, uint16_t* __restrict__ sPos) {
+__device__ __forceinline__ void fdFillBatch(const uint16_t* __restrict__ tab, int nPairs, int batchBase, int cnt, uint32_t exitRel, int lane, uint16_t* __restrict__ sPos) {
   const int hiIdx = min(cnt, batchBase + FD_BATCH);                  // last index wanted (inclusive)
-  for (int j = lane; j < 256; j += 32) {
+  for (int j = lane; j < nPairs; j += 32) {
     const int run = tab[768 + j];
     if (!run) continue;
     const int idx0 = tab[256 + j], len = tab[j], pos0 = tab[512 + j];
@@ -602,9 +603,9 @@ __global__ void __launch_bounds__(FD_DWARPS * 32) k_dec_offsets(FastDecArgs a, c
     const FdEntry me = sTab[ls * FD_CAND + slot];
     const int cnt = (int)me.count;
     bool fallback = false; unsigned why = 0;
-    fdLoadPairs<MAXU>(a.lens + ((size_t)s * FD_CAND + slot) * FD_LENS, pos0 - (uint32_t)s * FD_SUB, lane, sPairs);
+    const int nPairs = fdLoadPairs<MAXU>(a.lens + ((size_t)s * FD_CAND + slot) * FD_LENS, pos0 - (uint32_t)s * FD_SUB, lane, sPairs);
     for (int batchBase = 0; batchBase < cnt; batchBase += FD_BATCH) {
-      fdFillBatch(sPairs, batchBase, cnt, me.exit - (uint32_t)s * FD_SUB, lane, sPos);
+      fdFillBatch(sPairs, nPairs, batchBase, cnt, me.exit - (uint32_t)s * FD_SUB, lane, sPos);
       const int nB = min(FD_BATCH, cnt - batchBase);
       for (int i = lane; i < nB; i += 32) {
         const uint32_t b = blk0 + (uint32_t)(batchBase + i);
@@ -704,13 +705,13 @@ __global__ void __launch_bounds__(FD_DWARPS * 32) k_dec_blocks(FastDecArgs a) {
       }
     }
     // block positions from the recorded unit lengths, FD_BATCH blocks at a time: sPos[i] = start of block batchBase + i
-    fdLoadPairs<MAXU>(a.lens + ((size_t)s * FD_CAND + slot) * FD_LENS, pos0 - (uint32_t)s * FD_SUB, lane, sPairs);
+    const int nPairs = fdLoadPairs<MAXU>(a.lens + ((size_t)s * FD_CAND + slot) * FD_LENS, pos0 - (uint32_t)s * FD_SUB, lane, sPairs);
     __syncwarp();
     const uint8_t* sb = buf + d;
     const uint32_t* words = (const uint32_t*)buf;
     bool fallback = false; unsigned why = 0;
     for (int batchBase = 0; batchBase < cnt; batchBase += FD_BATCH) {
-    fdFillBatch(sPairs, batchBase, cnt, me.exit - (uint32_t)s * FD_SUB, lane, sPos);
+    fdFillBatch(sPairs, nPairs, batchBase, cnt, me.exit - (uint32_t)s * FD_SUB, lane, sPos);
     const int nB = min(FD_BATCH, cnt - batchBase);
     for (int i0 = 0; i0 < nB; i0 += 4) {
       const int i = i0 + g;
