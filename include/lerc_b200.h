@@ -39,6 +39,23 @@ LERC_B200_API void lerc_b200_get_stats(unsigned long long* out, int n);
 LERC_B200_API void lerc_b200_profile(int enable);
 LERC_B200_API void lerc_b200_get_profile(char* buf, int bufLen, int reset);
 
+/* ---- Tile batch (SURVEY.md 8(b) "batched tile entry point", BASELINE config 5) ------------------------------------------
+ * The reference codes one image per lerc_encode / lerc_decode call (Lerc_c_api.h:141-154, :238-252); callers that store
+ * rasters as tiles (MRF, GeoTIFF/LERC) loop over the tiles.  These entry points do that loop on the GPU in one pass:
+ * the raster pData[nRows][nCols] (one band, nDepth 1, every pixel valid, row-major, no padding) is cut into windows of
+ * tileRows x tileCols pixels (edge windows are smaller), tile t = ty * ceil(nCols / tileCols) + tx.  Every tile becomes
+ * (encode) / is read from (decode) its own standard Lerc2 blob -- byte for byte the blob lerc_encode writes for that
+ * window alone -- stored back to back: blob t occupies bytes [pTileOffsets[t], pTileOffsets[t + 1]) of the buffer
+ * (nTiles + 1 offsets; pTileOffsets[0] == 0).  All pointers may be host or CUDA device pointers.
+ * Status codes are those of Lerc_types.h.  BufferTooSmall when outBufferSize cannot hold the blobs;
+ * lerc_b200_tilesMaxBytes() is a size that always suffices. */
+LERC_B200_API unsigned long long lerc_b200_tilesMaxBytes(unsigned int dataType, int nCols, int nRows, int tileCols, int tileRows);
+LERC_B200_API unsigned int lerc_b200_encodeTiles(const void* pData, unsigned int dataType, int nCols, int nRows, int tileCols, int tileRows,
+                                                 double maxZErr, unsigned char* pOutBuffer, unsigned long long outBufferSize,
+                                                 unsigned long long* pTileOffsets, unsigned long long* nBytesWritten);
+LERC_B200_API unsigned int lerc_b200_decodeTiles(const unsigned char* pBlobs, unsigned long long blobBytes, const unsigned long long* pTileOffsets,
+                                                 unsigned int dataType, int nCols, int nRows, int tileCols, int tileRows, void* pData);
+
 LERC_B200_API const char* lerc_b200_version(void);
 
 #ifdef __cplusplus

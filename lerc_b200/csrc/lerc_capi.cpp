@@ -8,6 +8,7 @@
 #include <cstring>
 #include <climits>
 #include <algorithm>
+#include <vector>
 
 using namespace lerc;
 
@@ -321,6 +322,92 @@ void lerc_b200_get_stats(unsigned long long* out, int n) {
 
 void lerc_b200_profile(int enable) { gProfileEnabled = enable != 0; }
 void lerc_b200_get_profile(char* buf, int bufLen, int reset) { profileReport(buf, bufLen, reset != 0); }
+
+// ---- tile batch (lerc_tiles_encode.cuh / lerc_tiles_decode.cuh) -----------------------------------
+unsigned long long lerc_b200_tilesMaxBytes(unsigned int dataType, int nCols, int nRows, int tileCols, int tileRows) {
+  if (dataType >= (unsigned)DT_Undefined || nCols <= 0 || nRows <= 0 || tileCols <= 0 || tileRows <= 0) return 0;
+  const unsigned long long ts = (unsigned long long)typeSize((int)dataType);
+  const unsigned long long nx = ((unsigned long long)nCols + tileCols - 1) / tileCols, ny = ((unsigned long long)nRows + tileRows - 1) / tileRows;
+  const unsigned long long bx = ((unsigned long long)std::min(tileCols, nCols) + 7) / 8, by = ((unsigned long long)std::min(tileRows, nRows) + 7) / 8;
+  // per tile: header, mask byte count, ranges, two flag bytes, every block raw with its flag byte (the longest stream
+  // the single-pass encoder can emit before a smaller coding is chosen), slack for aligned stores
+  const unsigned long long perTile = 90 + 4 + 2 * ts + 2 + (unsigned long long)std::min(tileCols, nCols) * std::min(tileRows, nRows) * ts + bx * by + 32;
+  return nx * ny * perTile;
+}
+
+lerc_status lerc_b200_encodeTiles(const void* pData, unsigned int dataType, int nCols, int nRows, int tileCols, int tileRows, double maxZErr,
+                                  unsigned char* pOutBuffer, unsigned long long outBufferSize, unsigned long long* pTileOffsets,
+                                  unsigned long long* nBytesWritten) {
+  if (nBytesWritten) *nBytesWritten = 0;
+  if (!pData || !pOutBuffer || !pTileOffsets || !nBytesWritten || dataType >= (unsigned)DT_Undefined || !(maxZErr >= 0)) return WrongParam;
+  if (nCols <= 0 || nRows <= 0 || tileCols <= 0 || tileRows <= 0 || outBufferSize == 0) return WrongParam;
+  const size_t ts = (size_t)typeSize((int)dataType);
+  if (!dimsOk(1, std::min(tileCols, nCols), std::min(tileRows, nRows), ts)) return DimensionsTooLarge;
+  const unsigned long long nImg = (((unsigned long long)nCols + tileCols - 1) / tileCols) * (((unsigned long long)nRows + tileRows - 1) / tileRows);
+  if (nImg > 0x7fffffffull) return DimensionsTooLarge;
+  ContextGuard g;
+  Context* ctx = g.ctx;
+  if (!ctx) return Failed;
+  globalStats().encodeCalls++;
+  const size_t rasterBytes = (size_t)nCols * (size_t)nRows * ts;
+  const PtrKind kData = classifyPointer(pData), kOut = classifyPointer(pOutBuffer), kOff = classifyPointer(pTileOffsets);
+  const void* dData = pData;
+  if (kData != PTR_DEVICE) {
+    void* d = ctx->arena.alloc(rasterBytes);
+    if (!d || !cudaOk(cudaMemcpyAsync(d, pData, rasterBytes, cudaMemcpyHostToDevice, ctx->stream), "H2D raster")) return Failed;
+    dData = d;
+  }
+  uint8_t* dOut = pOutBuffer; size_t dOutCap = (size_t)outBufferSize;
+  if (kOut != PTR_DEVICE) {
+    dOutCap = (size_t)std::min<unsigned long long>(outBufferSize, lerc_b200_tilesMaxBytes(dataType, nCols, nRows, tileCols, tileRows));
+    dOut = (uint8_t*)ctx->arena.alloc(dOutCap + 16);
+    if (!dOut) return Failed;
+  }
+  std::vector<unsigned long long> hOff((size_t)nImg + 1, 0);
+  const ErrCode e = encodeTiles(ctx, (int)dataType, nCols, nRows, tileCols, tileRows, dData, maxZErr, dOut, dOutCap, hOff.data());
+  if (e == BufferTooSmall && kOut != PTR_DEVICE && dOutCap < (size_t)outBufferSize) return Failed;   // the bound was wrong: never expected
+  if (e != Ok) return e;
+  const unsigned long long total = hOff[(size_t)nImg];
+  if (kOut != PTR_DEVICE && !cudaOk(cudaMemcpyAsync(pOutBuffer, dOut, (size_t)total, cudaMemcpyDeviceToHost, ctx->stream), "D2H blobs")) return Failed;
+  if (kOff == PTR_DEVICE) { if (!cudaOk(cudaMemcpyAsync(pTileOffsets, hOff.data(), hOff.size() * 8, cudaMemcpyHostToDevice, ctx->stream), "H2D offsets")) return Failed; }
+  else std::memcpy(pTileOffsets, hOff.data(), hOff.size() * 8);
+  if (!cudaOk(cudaStreamSynchronize(ctx->stream), "sync")) return Failed;
+  *nBytesWritten = total;
+  return Ok;
+}
+
+lerc_status lerc_b200_decodeTiles(const unsigned char* pBlobs, unsigned long long blobBytes, const unsigned long long* pTileOffsets,
+                                  unsigned int dataType, int nCols, int nRows, int tileCols, int tileRows, void* pData) {
+  if (!pBlobs || !blobBytes || !pTileOffsets || !pData || dataType >= (unsigned)DT_Undefined) return WrongParam;
+  if (nCols <= 0 || nRows <= 0 || tileCols <= 0 || tileRows <= 0) return WrongParam;
+  const size_t ts = (size_t)typeSize((int)dataType);
+  if (!dimsOk(1, std::min(tileCols, nCols), std::min(tileRows, nRows), ts)) return DimensionsTooLarge;
+  const unsigned long long nImg = (((unsigned long long)nCols + tileCols - 1) / tileCols) * (((unsigned long long)nRows + tileRows - 1) / tileRows);
+  if (nImg > 0x7fffffffull) return DimensionsTooLarge;
+  ContextGuard g;
+  Context* ctx = g.ctx;
+  if (!ctx) return Failed;
+  globalStats().decodeCalls++;
+  const size_t rasterBytes = (size_t)nCols * (size_t)nRows * ts;
+  const PtrKind kBlob = classifyPointer(pBlobs), kData = classifyPointer(pData), kOff = classifyPointer(pTileOffsets);
+  std::vector<unsigned long long> hOff((size_t)nImg + 1);
+  if (kOff == PTR_DEVICE) {
+    if (!cudaOk(cudaMemcpyAsync(hOff.data(), pTileOffsets, hOff.size() * 8, cudaMemcpyDeviceToHost, ctx->stream), "D2H offsets") ||
+        !cudaOk(cudaStreamSynchronize(ctx->stream), "sync")) return Failed;
+  } else std::memcpy(hOff.data(), pTileOffsets, hOff.size() * 8);
+  const uint8_t* dBlobs = pBlobs;
+  if (kBlob != PTR_DEVICE) {
+    uint8_t* d = (uint8_t*)ctx->arena.alloc((size_t)blobBytes + 64);
+    if (!d || !cudaOk(cudaMemcpyAsync(d, pBlobs, (size_t)blobBytes, cudaMemcpyHostToDevice, ctx->stream), "H2D blobs")) return Failed;
+    dBlobs = d;
+  }
+  void* dData = pData;
+  if (kData != PTR_DEVICE) { dData = ctx->arena.alloc(rasterBytes); if (!dData) return Failed; }
+  const ErrCode e = decodeTiles(ctx, (int)dataType, nCols, nRows, tileCols, tileRows, dBlobs, (size_t)blobBytes, hOff.data(), dData);
+  if (e != Ok) return e;
+  if (kData != PTR_DEVICE && !cudaOk(cudaMemcpyAsync(pData, dData, rasterBytes, cudaMemcpyDeviceToHost, ctx->stream), "D2H raster")) return Failed;
+  return cudaOk(cudaStreamSynchronize(ctx->stream), "sync") ? Ok : Failed;
+}
 
 const char* lerc_b200_version(void) { return "lerc_b200 0.1 (Lerc2 v6 writer, v3-v6 reader; CUDA sm_100a)"; }
 

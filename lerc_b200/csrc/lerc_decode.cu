@@ -697,3 +697,5 @@ ErrCode decodeBand(Context* ctx, DecodeBandArgs& a, BandMaskState& ms) {
 }
 
 }  // namespace lerc
+
+#include "lerc_tiles_decode.cuh"

@@ -551,6 +551,91 @@ __global__ void __launch_bounds__(1024) k_dec_resolve(FastDecArgs a, int nBlocks
   }
 }
 
+// One row (lane r of the block's 8 lanes) of the block whose unit starts at byte p of the staged stream (`words` = the staging
+// buffer as aligned words, sb = words + d bytes = stream byte 0 of the stage).  The unit is parsed with the block's true size.
+// Returns the unit length; on a malformed / unsupported unit returns 0 and sets `why` (the caller falls back to the general decoder).
+template <class T>
+__device__ __forceinline__ int fdDecodeBlockRow(const uint32_t* __restrict__ words, const uint8_t* __restrict__ sb, int d, int p, int version, int patExpect,
+                                                int cells, int h, int w, int r, double invScale, double zMax, T (&out)[8], unsigned& why) {
+  constexpr int MAXU = 1 + 64 * (int)sizeof(T);
+  const FdWin win = fdWindow(words, (uint32_t)(d + p));
+  FdQuick q;
+  const int rc = fdQuick<T>(win, version, cells, true, q);
+  int len = 0;
+  if (rc == 0 || fdPattern((uint32_t)win.lo & 0xff, version) != patExpect) { why |= 512; }
+  else if (rc > 0 && q.len > MAXU) { why |= 32768; }                  // longer than the staged look-ahead: general decoder
+  else if (rc > 0) {
+    len = q.len;
+    if (q.mode == 2) {
+#pragma unroll
+      for (int kk = 0; kk < 8; kk++) out[kk] = (T)0;
+    } else if (q.mode == 0) {
+      const uint8_t* src = sb + p + 1 + (size_t)(r * w) * sizeof(T);
+#pragma unroll
+      for (int kk = 0; kk < 8; kk++) {
+        T val = (T)0;
+        if (kk < w && r < h) { uint8_t* vb = (uint8_t*)&val;
+#pragma unroll
+          for (int bb = 0; bb < (int)sizeof(T); bb++) vb[bb] = src[kk * sizeof(T) + bb]; }
+        out[kk] = val;
+      }
+    } else {
+      const int dtUsed = offsetTypeFromCode(PixelTraits<T>::code, q.tc);
+      unsigned long long ob = win.lo >> 8;
+      if (q.osz == 8) ob |= win.hi << 56;
+      const double offset = offsetFromBits(q.osz == 8 ? ob : (ob & ((1ull << (8 * q.osz)) - 1)), dtUsed);
+      if (q.mode == 3) {
+#pragma unroll
+        for (int kk = 0; kk < 8; kk++) out[kk] = (T)offset;
+      } else {
+        uint32_t qv[8];
+        const int nb = q.nb;
+        if (nb == 0) {
+#pragma unroll
+          for (int kk = 0; kk < 8; kk++) qv[kk] = 0;
+        } else if (w == 8 && nb <= 16) {
+          // the row is nb bytes at a byte boundary: 128-bit window, then split in halves / quarters / values
+          const FdWin rw = fdWindow(words, (uint32_t)(d + p + q.pay + r * nb));
+          const int s4 = 4 * nb, s2 = 2 * nb;
+          const unsigned long long m4 = s4 == 64 ? ~0ull : ((1ull << s4) - 1), m2 = (1ull << s2) - 1;
+          const uint32_t m1 = (1u << nb) - 1;
+          const unsigned long long h0 = rw.lo & m4;
+          const unsigned long long h1 = (s4 == 64 ? rw.hi : ((rw.lo >> s4) | (rw.hi << (64 - s4)))) & m4;
+          const unsigned long long q0 = h0 & m2, q1 = h0 >> s2, q2 = h1 & m2, q3 = h1 >> s2;
+          qv[0] = (uint32_t)q0 & m1; qv[1] = (uint32_t)(q0 >> nb); qv[2] = (uint32_t)q1 & m1; qv[3] = (uint32_t)(q1 >> nb);
+          qv[4] = (uint32_t)q2 & m1; qv[5] = (uint32_t)(q2 >> nb); qv[6] = (uint32_t)q3 & m1; qv[7] = (uint32_t)(q3 >> nb);
+        } else {
+          const uint32_t bit0 = (uint32_t)(r * w) * (uint32_t)nb;
+#pragma unroll
+          for (int kk = 0; kk < 8; kk++) qv[kk] = (kk < w && r < h) ? fdExtract(sb + p + q.pay, bit0 + (uint32_t)(kk * nb), nb) : 0u;
+        }
+#pragma unroll
+        for (int kk = 0; kk < 8; kk++) out[kk] = fdCast<T>(__dadd_rn(offset, __dmul_rn((double)qv[kk], invScale)), zMax);
+      }
+    }
+  } else {                                                     // LUT block or wide count field: byte-wise parser, out of line
+    len = fdDecodeSlowRow<T>(sb + p, version, cells, r, h, w, invScale, zMax, out);
+    if (len <= 0 || len > MAXU) { why |= len == -2 ? 16384 : 8192; len = 0; }
+  }
+  return len;
+}
+
+// 8 decoded pixels of one block row -> the raster (128-bit stores when the row is whole and aligned)
+template <class T>
+__device__ __forceinline__ void fdStoreRow(T* __restrict__ dst, const T (&out)[8], int w, bool vecOk) {
+  if (w == 8 && vecOk) {
+    if (sizeof(T) == 4) { uint32_t o[8]; memcpy(o, out, 32); ((uint4*)dst)[0] = make_uint4(o[0], o[1], o[2], o[3]); ((uint4*)dst)[1] = make_uint4(o[4], o[5], o[6], o[7]); }
+    else if (sizeof(T) == 8) { uint32_t o[16]; memcpy(o, out, 64);
+#pragma unroll
+      for (int kk = 0; kk < 4; kk++) ((uint4*)dst)[kk] = make_uint4(o[4 * kk], o[4 * kk + 1], o[4 * kk + 2], o[4 * kk + 3]); }
+    else if (sizeof(T) == 2) { uint32_t o[4]; memcpy(o, out, 16); ((uint4*)dst)[0] = make_uint4(o[0], o[1], o[2], o[3]); }
+    else { uint32_t o[2]; memcpy(o, out, 8); ((uint2*)dst)[0] = make_uint2(o[0], o[1]); }
+  } else {
+#pragma unroll
+    for (int kk = 0; kk < 8; kk++) if (kk < w) dst[kk] = out[kk];
+  }
+}
+
 constexpr int FD_DWARPS = 8;
 // ================= kernel 4b: block offsets only (masked rasters: the general block decoder does the pixels) =========
 // Same resolution as k_dec_blocks; instead of decoding, every block's stream offset is written to blockOff[] for
@@ -721,82 +806,13 @@ __global__ void __launch_bounds__(FD_DWARPS * 32) k_dec_blocks(FastDecArgs a) {
         const int ty = (int)b / a.nTx, tx = (int)b - ty * a.nTx;
         const int bi0 = ty * 8, bj0 = tx * 8;
         const int h = min(8, a.nRows - bi0), w = min(8, a.nCols - bj0), cells = h * w;
-        const FdWin win = fdWindow(words, (uint32_t)(d + p));
-        FdQuick q;
-        const int rc = fdQuick<T>(win, version, cells, true, q);
         T out[8];
-        int len = 0;
-        if (rc == 0 || fdPattern((uint32_t)win.lo & 0xff, version) != (tx & (version >= 5 ? 14 : 15))) { fallback = true; why |= 512; }
-        else if (rc > 0 && q.len > MAXU) { fallback = true; why |= 32768; }   // longer than the staged look-ahead: general decoder
-        else if (rc > 0) {
-          len = q.len;
-          if (q.mode == 2) {
-#pragma unroll
-            for (int kk = 0; kk < 8; kk++) out[kk] = (T)0;
-          } else if (q.mode == 0) {
-            const uint8_t* src = sb + p + 1 + (size_t)(r * w) * sizeof(T);
-#pragma unroll
-            for (int kk = 0; kk < 8; kk++) {
-              T val = (T)0;
-              if (kk < w && r < h) { uint8_t* vb = (uint8_t*)&val;
-#pragma unroll
-                for (int bb = 0; bb < (int)sizeof(T); bb++) vb[bb] = src[kk * sizeof(T) + bb]; }
-              out[kk] = val;
-            }
-          } else {
-            const int dtUsed = offsetTypeFromCode(PixelTraits<T>::code, q.tc);
-            unsigned long long ob = win.lo >> 8;
-            if (q.osz == 8) ob |= win.hi << 56;
-            const double offset = offsetFromBits(q.osz == 8 ? ob : (ob & ((1ull << (8 * q.osz)) - 1)), dtUsed);
-            if (q.mode == 3) {
-#pragma unroll
-              for (int kk = 0; kk < 8; kk++) out[kk] = (T)offset;
-            } else {
-              uint32_t qv[8];
-              const int nb = q.nb;
-              if (nb == 0) {
-#pragma unroll
-                for (int kk = 0; kk < 8; kk++) qv[kk] = 0;
-              } else if (w == 8 && nb <= 16) {
-                // the row is nb bytes at a byte boundary: 128-bit window, then split in halves / quarters / values
-                const FdWin rw = fdWindow(words, (uint32_t)(d + p + q.pay + r * nb));
-                const int s4 = 4 * nb, s2 = 2 * nb;
-                const unsigned long long m4 = s4 == 64 ? ~0ull : ((1ull << s4) - 1), m2 = (1ull << s2) - 1;
-                const uint32_t m1 = (1u << nb) - 1;
-                const unsigned long long h0 = rw.lo & m4;
-                const unsigned long long h1 = (s4 == 64 ? rw.hi : ((rw.lo >> s4) | (rw.hi << (64 - s4)))) & m4;
-                const unsigned long long q0 = h0 & m2, q1 = h0 >> s2, q2 = h1 & m2, q3 = h1 >> s2;
-                qv[0] = (uint32_t)q0 & m1; qv[1] = (uint32_t)(q0 >> nb); qv[2] = (uint32_t)q1 & m1; qv[3] = (uint32_t)(q1 >> nb);
-                qv[4] = (uint32_t)q2 & m1; qv[5] = (uint32_t)(q2 >> nb); qv[6] = (uint32_t)q3 & m1; qv[7] = (uint32_t)(q3 >> nb);
-              } else {
-                const uint32_t bit0 = (uint32_t)(r * w) * (uint32_t)nb;
-#pragma unroll
-                for (int kk = 0; kk < 8; kk++) qv[kk] = (kk < w && r < h) ? fdExtract(sb + p + q.pay, bit0 + (uint32_t)(kk * nb), nb) : 0u;
-              }
-#pragma unroll
-              for (int kk = 0; kk < 8; kk++) out[kk] = fdCast<T>(__dadd_rn(offset, __dmul_rn((double)qv[kk], a.invScale)), a.zMax);
-            }
-          }
-        } else {                                                     // LUT block or wide count field: byte-wise parser, out of line
-          len = fdDecodeSlowRow<T>(sb + p, version, cells, r, h, w, a.invScale, a.zMax, out);
-          if (len <= 0 || len > MAXU) { fallback = true; why |= len == -2 ? 16384 : 8192; len = 0; }
-        }
+        unsigned whyB = 0;
+        const int len = fdDecodeBlockRow<T>(words, sb, d, p, version, tx & (version >= 5 ? 14 : 15), cells, h, w, r, a.invScale, a.zMax, out, whyB);
+        if (whyB) { fallback = true; why |= whyB; }
         // the block, parsed with its true size, must end where the recorded chain continues
         if (!fallback && p + len != pNext) { fallback = true; why |= 1024; }
-        if (!fallback && r < h) {
-          T* dst = data + (size_t)(bi0 + r) * a.nCols + bj0;
-          if (w == 8 && vecOk) {
-            if (sizeof(T) == 4) { uint32_t o[8]; memcpy(o, out, 32); ((uint4*)dst)[0] = make_uint4(o[0], o[1], o[2], o[3]); ((uint4*)dst)[1] = make_uint4(o[4], o[5], o[6], o[7]); }
-            else if (sizeof(T) == 8) { uint32_t o[16]; memcpy(o, out, 64);
-#pragma unroll
-              for (int kk = 0; kk < 4; kk++) ((uint4*)dst)[kk] = make_uint4(o[4 * kk], o[4 * kk + 1], o[4 * kk + 2], o[4 * kk + 3]); }
-            else if (sizeof(T) == 2) { uint32_t o[4]; memcpy(o, out, 16); ((uint4*)dst)[0] = make_uint4(o[0], o[1], o[2], o[3]); }
-            else { uint32_t o[2]; memcpy(o, out, 8); ((uint2*)dst)[0] = make_uint2(o[0], o[1]); }
-          } else {
-#pragma unroll
-            for (int kk = 0; kk < 8; kk++) if (kk < w) dst[kk] = out[kk];
-          }
-        }
+        if (!fallback && r < h) fdStoreRow<T>(data + (size_t)(bi0 + r) * a.nCols + bj0, out, w, vecOk);
       }
     }
     __syncwarp();

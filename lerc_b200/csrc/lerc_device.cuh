@@ -184,4 +184,23 @@ __device__ __forceinline__ int warpSum(int v) {
   return v;
 }
 
+// Fletcher-32 from the partial sums A = SUM c, D = SUM (wordIndex mod 65535) * c over the checksum region of
+// length len (see k_fletcher_partial in lerc_mask.cu for the derivation).
+__host__ __device__ inline uint32_t fletcherFinish(unsigned long long A, unsigned long long D, long long len) {
+  const unsigned long long M = 65535ull, m = (unsigned long long)((len + 1) >> 1);
+  A %= M; D %= M;
+  unsigned long long s1 = (0xffffull + A) % M;
+  unsigned long long s2 = ((0xffffull % M) * ((m + 1) % M) + (m % M) * A + (M - D)) % M;
+  if (s1 == 0) s1 = M;
+  if (s2 == 0) s2 = M;
+  return (uint32_t)((s2 << 16) | s1);
+}
+__host__ __device__ inline void fletcherHostPartial(const uint8_t* bytes, long long r0, long long n, unsigned long long& A, unsigned long long& D) {
+  for (long long i = 0; i < n; i++) {
+    const long long r = r0 + i;
+    const unsigned long long c = (unsigned long long)bytes[i] << ((r & 1) ? 0 : 8);
+    A += c; D = (D + ((unsigned long long)((r >> 1) % 65535) * c) % 65535ull) % 65535ull;
+  }
+}
+
 }  // namespace lerc

@@ -701,7 +701,7 @@ bool encodeBandFast(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
       }
       const long long grid = std::min<long long>(nTiles, (long long)ctasPerSm * std::max(sms, 1));   // all CTAs co-resident (look-back)
       LaunchScope scope_(ctx, "k_encode_fused<T>");
-      kernel<<<(unsigned)grid, 256, smem, ctx->stream>>>(fa); ctx->kernelLaunches++;
+      kernel<<<(unsigned)grid, 256, smem, ctx->stream>>>(fa, FastNoBatch()); ctx->kernelLaunches++;
     };
     if (occ == 6) launch(k_encode_fused<T, 6>); else if (occ == 5) launch(k_encode_fused<T, 5>); else launch(k_encode_fused<T, 4>);
   } else {
@@ -1127,3 +1127,5 @@ ErrCode encodeBand(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t&
 }
 
 }  // namespace lerc
+
+#include "lerc_tiles_encode.cuh"

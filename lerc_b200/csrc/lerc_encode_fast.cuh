@@ -18,6 +18,7 @@
 // the facts afterwards and re-runs the general multi-pass encoder (encodeBandT) when any assumption failed, so
 // the bytes are always those of the reference.
 #pragma once
+#include <type_traits>
 
 namespace lerc {
 
@@ -41,6 +42,30 @@ struct FastEncArgs {
   long long regionOff;                 // checksum-region offset of stream[0] (= dataStart - 14)
   unsigned long long* tileState;       // [nTiles], zero-initialised
   FastEncResult* res;
+};
+
+// ---- tile batch (k_encode_fused<T, MINB, true>, lerc_tiles_encode.cuh): the raster is cut into imgRows x imgCols images, every
+// image becomes its own blob.  nTx / nTy / nRows / nCols of FastEncArgs then describe a FULL image; every image owns segPerImg
+// consecutive entries of tileState (edge images leave some of them empty).
+struct TileEncResult;
+struct FastBatchArgs {
+  int imgCols, imgRows, nImgX, nImgY, rasterCols, rasterRows, segPerImg, dataStart;
+  long long pitch;                     // elements per raster row
+  unsigned long long* imgState;        // [nImg], zero-initialised: look-back over whole blobs
+  TileEncResult* imgRes;               // [nImg], zero-initialised
+  uint8_t* out; unsigned long long outCap;
+};
+struct FastNoBatch {                   // what the one-image kernel gets instead: nothing (the names fold to constants)
+  static constexpr int imgCols = 0, imgRows = 0, nImgX = 0, nImgY = 0, rasterCols = 0, rasterRows = 0, segPerImg = 1, dataStart = 0;
+  static constexpr long long pitch = 0;
+  static constexpr unsigned long long* imgState = nullptr;
+  static constexpr TileEncResult* imgRes = nullptr;
+  static constexpr uint8_t* out = nullptr; static constexpr unsigned long long outCap = 0;
+};
+
+struct TileEncResult {                 // per image of a tile batch
+  unsigned long long negMinKey, maxKey, fletA, fletD, streamBytes;
+  unsigned int flags, pad;
 };
 
 // ---- helpers -----------------------------------------------------------------------------------
@@ -266,8 +291,8 @@ __device__ __noinline__ void fastGenericEmit(const FastEncArgs& a, uint32_t* sta
   orBits<8>(stage, (byte0 + (uint32_t)(osz + 3)) * 8 + (uint32_t)(r * w * nb), R, w * nb);
 }
 
-template <class T, int MINB>
-__global__ void __launch_bounds__(256, MINB) k_encode_fused(FastEncArgs a) {
+template <class T, int MINB, bool BATCH = false>
+__global__ void __launch_bounds__(256, MINB) k_encode_fused(FastEncArgs a, typename std::conditional<BATCH, FastBatchArgs, FastNoBatch>::type t) {
   using K = typename PixelTraits<T>::Key;
   constexpr bool isFlt = PixelTraits<T>::isFloat;
   constexpr int DT = PixelTraits<T>::code;
@@ -277,19 +302,21 @@ __global__ void __launch_bounds__(256, MINB) k_encode_fused(FastEncArgs a) {
   extern __shared__ __align__(16) uint32_t stageRaw[];          // two staging images (tiles alternate) | T sRow[256][8] (general path)
   T* sRow = (T*)(stageRaw + 2 * NQ * 4);
   __shared__ uint32_t sLen[2][TB];
-  __shared__ unsigned long long sTileOff;
+  __shared__ unsigned long long sTileOff, sLocalOff;
   __shared__ unsigned long long sKMin[8], sKMax[8], sFA[8], sFD[8];
   __shared__ unsigned int sFlg[8];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, sb = lane >> 3, r = lane & 7;
-  const unsigned int flagsSeen = *(volatile unsigned int*)&a.res->flags;
-  const unsigned long long negMinSeen = *(volatile unsigned long long*)&a.res->negMinKey, maxSeen = *(volatile unsigned long long*)&a.res->maxKey;
+  const unsigned int flagsSeen = BATCH ? 0u : *(volatile unsigned int*)&a.res->flags;
+  const unsigned long long negMinSeen = BATCH ? 0ull : *(volatile unsigned long long*)&a.res->negMinKey, maxSeen = BATCH ? 0ull : *(volatile unsigned long long*)&a.res->maxKey;
   for (int i = tid; i < 2 * NQ; i += 256) ((uint4*)stageRaw)[i] = make_uint4(0, 0, 0, 0);
 
   const T* data = (const T*)a.data;
-  const bool vecOk = ((a.nCols * (int)sizeof(T)) % 16 == 0) && (((uintptr_t)data & 15) == 0);
-  const int tpr = (a.nTx + TB - 1) / TB;                         // tiles per block row
-  const int nTiles = tpr * a.nTy;
+  const long long rowPitch = BATCH ? t.pitch : (long long)a.nCols;
+  const bool vecOk = BATCH ? (((t.pitch * (long long)sizeof(T)) % 16 == 0) && ((t.imgCols * (int)sizeof(T)) % 16 == 0) && (((uintptr_t)data & 15) == 0))
+                           : (((a.nCols * (int)sizeof(T)) % 16 == 0) && (((uintptr_t)data & 15) == 0));
+  const int tpr = (a.nTx + TB - 1) / TB;                         // tiles per block row (of a full image)
+  const int nTiles = BATCH ? t.segPerImg * t.nImgX * t.nImgY : tpr * a.nTy;
   const int b = warp * 4 + sb;
   constexpr unsigned long long ST_A = 1ull << 62, ST_P = 2ull << 62, VAL = (1ull << 62) - 1;
   volatile unsigned long long* st = a.tileState;
@@ -307,26 +334,42 @@ __global__ void __launch_bounds__(256, MINB) k_encode_fused(FastEncArgs a) {
     act = tile < nTiles && tx < a.nTx;
     h = act ? min(8, a.nRows - ty * 8) : 0; w = act ? min(8, a.nCols - tx * 8) : 0;
   };
+  // tile batch: tile -> (image, block row, segment); `org` = element offset of the image's first pixel in the raster
+  auto batchGeom = [&](int tile, int& img, int& local, size_t& org, int& ty, int& tx, int& h, int& w, bool& act) {
+    img = tile / t.segPerImg; local = tile - img * t.segPerImg;
+    const int tyT = local / tpr, segT = local - tyT * tpr;
+    const int iy = img / t.nImgX, ix = img - iy * t.nImgX;
+    const int rows = min(t.imgRows, t.rasterRows - iy * t.imgRows), cols = min(t.imgCols, t.rasterCols - ix * t.imgCols);
+    ty = tyT; tx = segT * TB + b;
+    act = tile < nTiles && ty * 8 < rows && tx * 8 < cols;
+    h = act ? min(8, rows - ty * 8) : 0; w = act ? min(8, cols - tx * 8) : 0;
+    org = (size_t)iy * t.imgRows * (size_t)t.pitch + (size_t)ix * t.imgCols;
+  };
   const int stepTy = (int)gridDim.x / tpr, stepSeg = (int)gridDim.x - stepTy * tpr;   // tile += gridDim.x in (block row, segment) form
   FastRow<T> cur, nxt;
   int ty, tx, h, w; bool act;
   int tile = blockIdx.x;
   int tyT = tile / tpr, segT = tile - tyT * tpr;
-  tileGeom(tile, tyT, segT, ty, tx, h, w, act);
+  int img = 0, local = 0, nimg = 0, nlocal = 0; size_t org = 0, norg = 0;          // tile batch only
+  if (BATCH) batchGeom(tile, img, local, org, ty, tx, h, w, act);
+  else tileGeom(tile, tyT, segT, ty, tx, h, w, act);
 #pragma unroll
   for (int k = 0; k < 8; k++) cur.v[k] = (T)0;
-  if (act && r < h) loadRow8<T>(data + (size_t)(ty * 8 + r) * a.nCols + tx * 8, w, vecOk && w == 8, cur.v);
+  if (act && r < h) loadRow8<T>(data + org + (size_t)(ty * 8 + r) * rowPitch + tx * 8, w, vecOk && w == 8, cur.v);
   __syncthreads();                                               // staging zeroed
 
   for (int it = 0; tile < nTiles; it++, tile += gridDim.x) {
     uint32_t* stage = stageRaw + (size_t)(it & 1) * NQ * 4 + 4;  // tile-local byte 0 of this tile's output image
     // ---- prefetch the next tile's pixels
     int nty, ntx, nh, nw; bool nact;
-    tyT += stepTy; segT += stepSeg; if (segT >= tpr) { segT -= tpr; tyT++; }
-    tileGeom(tile + gridDim.x, tyT, segT, nty, ntx, nh, nw, nact);
+    if (BATCH) batchGeom(tile + gridDim.x, nimg, nlocal, norg, nty, ntx, nh, nw, nact);
+    else {
+      tyT += stepTy; segT += stepSeg; if (segT >= tpr) { segT -= tpr; tyT++; }
+      tileGeom(tile + gridDim.x, tyT, segT, nty, ntx, nh, nw, nact);
+    }
 #pragma unroll
     for (int k = 0; k < 8; k++) nxt.v[k] = (T)0;
-    if (nact && r < nh) loadRow8<T>(data + (size_t)(nty * 8 + r) * a.nCols + ntx * 8, nw, vecOk && nw == 8, nxt.v);
+    if (nact && r < nh) loadRow8<T>(data + norg + (size_t)(nty * 8 + r) * rowPitch + ntx * 8, nw, vecOk && nw == 8, nxt.v);
 
     // ---- block statistics and coding choice
     const int j0 = tx * 8, n = h * w;
@@ -411,7 +454,7 @@ __global__ void __launch_bounds__(256, MINB) k_encode_fused(FastEncArgs a) {
     for (int s = 1; s < 32; s <<= 1) { const uint32_t o = __shfl_up_sync(FULL, inc, s); if (lane >= s) inc += o; }
     const uint32_t tileBytes = __shfl_sync(FULL, inc, 31);
     const uint32_t byte0 = __shfl_sync(FULL, inc - myLen, b);
-    if (tid == 0) st[tile] = (tile == 0 ? ST_P : ST_A) | (unsigned long long)tileBytes;   // publish before packing
+    if (tid == 0) st[tile] = ((BATCH ? local : tile) == 0 ? ST_P : ST_A) | (unsigned long long)tileBytes;   // publish before packing
 
     // ---- quantise (Lerc2.h:357-376), pack, OR into the staging image (WriteTile, Lerc2.cpp:1949-2021)
     if (hot) {
@@ -447,15 +490,16 @@ __global__ void __launch_bounds__(256, MINB) k_encode_fused(FastEncArgs a) {
     // ---- decoupled look-back (warp 0) for the tile's global byte offset
     if (warp == 0) {
       unsigned long long excl = 0;
-      if (tile > 0) {
+      const long long first = BATCH ? (long long)(tile - local) : 0;    // the chain restarts at every image of a tile batch
+      if (tile > first) {
         long long base = (long long)tile - 1;
         for (;;) {
           const long long idx = base - lane;
-          unsigned long long s = ST_P;                                  // virtual tiles before 0: prefix 0
-          if (idx >= 0) { do { s = st[idx]; } while ((s >> 62) == 0); }
+          unsigned long long s = ST_P;                                  // virtual tiles before the first: prefix 0
+          if (idx >= first) { do { s = st[idx]; } while ((s >> 62) == 0); }
           const unsigned isP = __ballot_sync(FULL, (s >> 62) == 2);
           const int firstP = isP ? __ffs(isP) - 1 : 32;
-          unsigned long long contrib = (lane <= firstP && idx >= 0) ? (s & VAL) : 0;
+          unsigned long long contrib = (lane <= firstP && idx >= first) ? (s & VAL) : 0;
 #pragma unroll
           for (int m = 16; m; m >>= 1) contrib += __shfl_xor_sync(FULL, contrib, m);
           excl += contrib;
@@ -464,9 +508,36 @@ __global__ void __launch_bounds__(256, MINB) k_encode_fused(FastEncArgs a) {
         }
         if (lane == 0) st[tile] = ST_P | (excl + tileBytes);
       }
-      if (lane == 0) {
-        sTileOff = excl;
-        if (tile == nTiles - 1) a.res->totalBytes = excl + tileBytes;
+      if (!BATCH) {
+        if (lane == 0) {
+          sTileOff = excl;
+          if (tile == nTiles - 1) a.res->totalBytes = excl + tileBytes;
+        }
+      } else {
+        // second look-back, over whole blobs: where does this image's blob start in the output?
+        volatile unsigned long long* ist = t.imgState;
+        const bool lastSeg = local == t.segPerImg - 1;
+        const unsigned long long blobBytes = (unsigned long long)t.dataStart + excl + tileBytes;      // meaningful for the last segment only
+        if (lastSeg && lane == 0) { t.imgRes[img].streamBytes = excl + tileBytes; __threadfence(); ist[img] = (img == 0 ? ST_P : ST_A) | blobBytes; }
+        unsigned long long imgBase = 0;
+        if (img > 0) {
+          long long base = (long long)img - 1;
+          for (;;) {
+            const long long idx = base - lane;
+            unsigned long long s = ST_P;
+            if (idx >= 0) { do { s = ist[idx]; } while ((s >> 62) == 0); }
+            const unsigned isP = __ballot_sync(FULL, (s >> 62) == 2);
+            const int firstP = isP ? __ffs(isP) - 1 : 32;
+            unsigned long long contrib = (lane <= firstP && idx >= 0) ? (s & VAL) : 0;
+#pragma unroll
+            for (int m = 16; m; m >>= 1) contrib += __shfl_xor_sync(FULL, contrib, m);
+            imgBase += contrib;
+            if (isP) break;
+            base -= 32;
+          }
+          if (lastSeg && lane == 0) ist[img] = ST_P | (imgBase + blobBytes);
+        }
+        if (lane == 0) { sTileOff = imgBase + (unsigned long long)t.dataStart + excl; sLocalOff = excl; }
       }
     }
     __syncthreads();                                             // staging image complete, tile offset known
@@ -475,9 +546,10 @@ __global__ void __launch_bounds__(256, MINB) k_encode_fused(FastEncArgs a) {
     // funnel shifts), Fletcher-32 partial sums of the same words (bytes outside the tile are zero in the image);
     // every chunk read is zeroed again for the tile after next
     const unsigned long long tileOff = sTileOff;
+    const unsigned long long localOff = BATCH ? sLocalOff : tileOff;     // offset inside this blob's micro-block stream
     {
-      uint8_t* gTile = a.stream + tileOff;
-      const bool fits = tileOff + tileBytes <= a.streamCap;
+      uint8_t* gTile = (BATCH ? t.out : a.stream) + tileOff;
+      const bool fits = tileOff + tileBytes <= (BATCH ? t.outCap : a.streamCap);
       if (!fits) overflow = true;
       const int pad = (int)((uintptr_t)gTile & 15);
       const int nChunks = (pad + (int)tileBytes + 15) >> 4;
@@ -499,7 +571,7 @@ __global__ void __launch_bounds__(256, MINB) k_encode_fused(FastEncArgs a) {
           }
         }
         // big-endian 16-bit words at even region offsets (Lerc2.cpp:1037-1064)
-        const long long r0 = a.regionOff + (long long)tileOff + s0;
+        const long long r0 = a.regionOff + (long long)localOff + s0;
         const unsigned par = (unsigned)(r0 & 1);
         const uint32_t w0 = (uint32_t)((unsigned long long)(r0 + 16) >> 1) % 65535u + 65535u - 8u;   // word index of byte r0 - par (mod 65535)
         uint32_t S = 0, S1 = 0, prev = 0;
@@ -516,9 +588,36 @@ __global__ void __launch_bounds__(256, MINB) k_encode_fused(FastEncArgs a) {
       }
     }
     prevBytes = tileBytes;
+    if (BATCH && (nimg != img || tile + (int)gridDim.x >= nTiles)) {
+      // ---- the next tile belongs to another image: hand this image's facts and checksum partials over
+#pragma unroll
+      for (int m = 1; m < 32; m <<= 1) {
+        const K omin = shflXorK<K>(gMin, m), omax = shflXorK<K>(gMax, m);
+        gMin = omin < gMin ? omin : gMin; gMax = omax > gMax ? omax : gMax;
+      }
+      if (overflow) myFlags |= FASTF_OVERFLOW;
+      myFlags = __reduce_or_sync(FULL, myFlags);
+      fa %= 65535ull; fd %= 65535ull;
+#pragma unroll
+      for (int m = 16; m; m >>= 1) { fa += __shfl_xor_sync(FULL, fa, m); fd += __shfl_xor_sync(FULL, fd, m); }
+      if (lane == 0) { sKMin[warp] = (unsigned long long)gMin; sKMax[warp] = (unsigned long long)gMax; sFlg[warp] = myFlags; sFA[warp] = fa; sFD[warp] = fd; }
+      __syncthreads();
+      if (tid == 0) {
+        unsigned long long A = 0, D = 0, kMin = ~0ull, kMax = 0; unsigned int fl = 0;
+        for (int i = 0; i < 8; i++) { A += sFA[i]; D += sFD[i]; kMin = sKMin[i] < kMin ? sKMin[i] : kMin; kMax = sKMax[i] > kMax ? sKMax[i] : kMax; fl |= sFlg[i]; }
+        TileEncResult* ir = t.imgRes + img;
+        if (A | D) { atomicAdd(&ir->fletA, A); atomicAdd(&ir->fletD, D % 65535ull); }
+        if (kMax >= kMin) { atomicMax(&ir->negMinKey, ~kMin); atomicMax(&ir->maxKey, kMax); }
+        if (fl) atomicOr(&ir->flags, fl);
+      }
+      gMin = keyMaxValue<K>(); gMax = 0; myFlags = 0; fa = 0; fd = 0; overflow = false;
+      // (the barrier after the next tile's block lengths separates these shared arrays from their next use)
+    }
     // ---- next tile
     cur = nxt; ty = nty; tx = ntx; h = nh; w = nw; act = nact;
+    if (BATCH) { img = nimg; local = nlocal; org = norg; }
   }
+  if (BATCH) return;
 
   // ---- image-global facts and checksum partials of this CTA
 #pragma unroll
@@ -814,24 +913,5 @@ __global__ void __launch_bounds__(256, 4) k_encode_warp(FastEncArgs a) {
 // small blob prefix (header, mask length, ranges, flag bytes) written from kernel parameters
 struct PrefixBytes { uint8_t b[128]; int n; };
 __global__ void k_write_prefix(uint8_t* dst, PrefixBytes p) { if ((int)threadIdx.x < p.n) dst[threadIdx.x] = p.b[threadIdx.x]; }
-
-// Fletcher-32 from the partial sums A = SUM c, D = SUM (wordIndex mod 65535) * c over the checksum region of
-// length len (see k_fletcher_partial in lerc_mask.cu for the derivation).
-inline uint32_t fletcherFinish(unsigned long long A, unsigned long long D, long long len) {
-  const unsigned long long M = 65535ull, m = (unsigned long long)((len + 1) >> 1);
-  A %= M; D %= M;
-  unsigned long long s1 = (0xffffull + A) % M;
-  unsigned long long s2 = ((0xffffull % M) * ((m + 1) % M) + (m % M) * A + (M - D)) % M;
-  if (s1 == 0) s1 = M;
-  if (s2 == 0) s2 = M;
-  return (uint32_t)((s2 << 16) | s1);
-}
-inline void fletcherHostPartial(const uint8_t* bytes, long long r0, long long n, unsigned long long& A, unsigned long long& D) {
-  for (long long i = 0; i < n; i++) {
-    const long long r = r0 + i;
-    const unsigned long long c = (unsigned long long)bytes[i] << ((r & 1) ? 0 : 8);
-    A += c; D = (D + ((unsigned long long)((r >> 1) % 65535) * c) % 65535ull) % 65535ull;
-  }
-}
 
 }  // namespace lerc

@@ -163,6 +163,19 @@ struct DecodeBandArgs {
 };
 ErrCode decodeBand(Context* ctx, DecodeBandArgs& a, BandMaskState& ms);
 
+// Tile batch (include/lerc_b200.h, lerc_tiles_encode.cuh / lerc_tiles_decode.cuh): every tileRows x tileCols window of a
+// one-band raster is its own Lerc2 blob.  hOffsets: host array of nTiles + 1 byte offsets into dOut / dBlobs.
+struct TilesGeom {
+  int dt, nCols, nRows, tileCols, tileRows, nImgX, nImgY;
+  long long nImg() const { return (long long)nImgX * nImgY; }
+  int rowsOf(long long img) const { const int iy = (int)(img / nImgX); const int r = nRows - iy * tileRows; return r < tileRows ? r : tileRows; }
+  int colsOf(long long img) const { const int ix = (int)(img % nImgX); const int c = nCols - ix * tileCols; return c < tileCols ? c : tileCols; }
+};
+ErrCode encodeTiles(Context* ctx, int dt, int nCols, int nRows, int tileCols, int tileRows, const void* dData, double maxZErr,
+                    uint8_t* dOut, size_t outCap, unsigned long long* hOffsets);
+ErrCode decodeTiles(Context* ctx, int dt, int nCols, int nRows, int tileCols, int tileRows, const uint8_t* dBlobs, size_t blobBytes,
+                    const unsigned long long* hOffsets, void* dData);
+
 // misc device utilities (lerc_mask.cu)
 void launchConvertToDouble(Context* ctx, const void* dSrc, int dt, size_t n, double* dDst);   // in-place safe back-to-front
 

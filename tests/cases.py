@@ -93,3 +93,33 @@ def all_cases(h=257, w=300, seed=1):
     add("f32_8x8", f32[:8, :8].copy(), 0.01)
     add("i16_smooth_low_bitrate", (smooth / 300).astype(np.int16), 0)   # < 1.5 bpp -> 16x16 blocks
     return cases
+
+
+def tile_cases(seed=5):
+    """(name, raster, tileRows, tileCols, maxZErr) for the tile batch entry points: ordinary tiles plus tiles that flip an
+    image-global decision of the encoder (constant, all-integer, pre-rounded, NaN, LUT-friendly, flat -> 16x16 / one sweep)."""
+    rng = np.random.default_rng(seed)
+    cases = []
+    f = c2_raster(200, 330)
+    cases.append(("f32_64x64_0.01", f, 64, 64, 0.01))
+    cases.append(("f32_40x56_edge_0.01", f, 40, 56, 0.01))
+    cases.append(("f32_256x256_single", c2_raster(256, 256), 256, 256, 0.01))
+    cases.append(("f32_one_tile_bigger", f, 512, 512, 0.01))
+    cases.append(("f32_8x8_tiles", f[:40, :48].copy(), 8, 8, 0.01))
+    cases.append(("f64_48x48_0.001", f.astype(np.float64) + 1e-7, 48, 48, 0.001))
+    cases.append(("i16_64x64_lossless", np.clip(smooth_field(200, 330) / 8 + rng.normal(0, 2, (200, 330)), -3e4, 3e4).astype(np.int16), 64, 64, 0))
+    cases.append(("u16_64x80_lossy2", (smooth_field(130, 250) + rng.normal(0, 3, (130, 250))).astype(np.uint16), 64, 80, 2))
+    cases.append(("i32_32x32_lossless", (smooth_field(100, 100) * 1000 + rng.normal(0, 50, (100, 100))).astype(np.int32), 32, 32, 0))
+    cases.append(("u8_64x64_lossless", np.clip(smooth_field(128, 192) / 8 + rng.normal(0, 2, (128, 192)), 0, 255).astype(np.uint8), 64, 64, 0))
+    mixed = c2_raster(192, 256)
+    mixed[0:64, 0:64] = 3.25                                   # constant tile
+    mixed[0:64, 64:128] = np.round(mixed[0:64, 64:128])        # all-integer tile
+    mixed[0:64, 128:192] = np.round(mixed[0:64, 128:192], 1)   # on a 0.1 grid: maxZError raised
+    mixed[64:128, 0:64] = (np.floor(mixed[64:128, 0:64] / 40) * 40)     # LUT friendly
+    mixed[64:128, 64:128] = 0.0                                # all zero
+    mixed[70:80, 130:150] = np.nan                             # NaN -> mask
+    mixed[128:192, 0:64] = np.floor(smooth_field(64, 64) / 300)         # flat: 16x16 blocks
+    mixed[128:192, 64:128] = rng.random((64, 64)).astype(np.float32) * 1e30   # raw / one sweep
+    cases.append(("f32_mixed_decisions", mixed, 64, 64, 0.01))
+    cases.append(("f32_lossless", f[:100, :100].copy(), 50, 50, 0))
+    return cases

@@ -159,3 +159,52 @@ def oracle_lib():
 def product_lib():
     p = _first(os.path.join(ROOT, "lerc_b200", "libLerc.so.4"))
     return LercLib(p) if p else None
+
+
+# ---- tile batch extension (include/lerc_b200.h) ---------------------------------------------------------
+def tiles_api(lib):
+    """ctypes signatures of lerc_b200_encodeTiles / decodeTiles / tilesMaxBytes on a loaded product library."""
+    u, i, d, p, ull = C.c_uint, C.c_int, C.c_double, C.c_void_p, C.c_ulonglong
+    lib.lib.lerc_b200_tilesMaxBytes.argtypes = [u, i, i, i, i]
+    lib.lib.lerc_b200_tilesMaxBytes.restype = ull
+    lib.lib.lerc_b200_encodeTiles.argtypes = [p, u, i, i, i, i, d, p, ull, p, p]
+    lib.lib.lerc_b200_encodeTiles.restype = u
+    lib.lib.lerc_b200_decodeTiles.argtypes = [p, ull, p, u, i, i, i, i, p]
+    lib.lib.lerc_b200_decodeTiles.restype = u
+    return lib.lib
+
+
+def encode_tiles(lib, raster, tile_rows, tile_cols, max_z_err, buf_size=None):
+    """host buffers through lerc_b200_encodeTiles: returns (status, list of blobs, offsets)"""
+    api = tiles_api(lib)
+    a = np.ascontiguousarray(raster)
+    n_rows, n_cols = a.shape
+    n_tiles = ((n_rows + tile_rows - 1) // tile_rows) * ((n_cols + tile_cols - 1) // tile_cols)
+    if buf_size is None:
+        buf_size = int(api.lerc_b200_tilesMaxBytes(DT_CODE[a.dtype], n_cols, n_rows, tile_cols, tile_rows))
+    out = np.full(buf_size, 0xAB, dtype=np.uint8)
+    off = np.zeros(n_tiles + 1, dtype=np.uint64)
+    n = C.c_ulonglong(0)
+    st = api.lerc_b200_encodeTiles(a.ctypes.data, DT_CODE[a.dtype], n_cols, n_rows, tile_cols, tile_rows, max_z_err,
+                                   out.ctypes.data, buf_size, off.ctypes.data, C.addressof(n))
+    if st:
+        return st, None, None
+    assert int(off[-1]) == n.value
+    return st, [out[int(off[t]):int(off[t + 1])].tobytes() for t in range(n_tiles)], off
+
+
+def decode_tiles(lib, blobs, dtype, n_rows, n_cols, tile_rows, tile_cols):
+    api = tiles_api(lib)
+    buf = np.frombuffer(b"".join(blobs) + b"\0" * 16, dtype=np.uint8)
+    off = np.zeros(len(blobs) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([len(b) for b in blobs])
+    out = np.full((n_rows, n_cols), 0x5A, dtype=dtype)
+    st = api.lerc_b200_decodeTiles(buf.ctypes.data, int(off[-1]), off.ctypes.data, DT_CODE[np.dtype(dtype)], n_cols, n_rows,
+                                   tile_cols, tile_rows, out.ctypes.data)
+    return st, out
+
+
+def tile_windows(n_rows, n_cols, tile_rows, tile_cols):
+    for y in range(0, n_rows, tile_rows):
+        for x in range(0, n_cols, tile_cols):
+            yield slice(y, min(y + tile_rows, n_rows)), slice(x, min(x + tile_cols, n_cols))

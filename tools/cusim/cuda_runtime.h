@@ -100,6 +100,7 @@ cudaError_t cudaFree(void* p);
 cudaError_t cudaFreeHost(void* p);
 cudaError_t cudaMemcpy(void* dst, const void* src, size_t n, cudaMemcpyKind kind);
 cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t n, cudaMemcpyKind kind, cudaStream_t s = nullptr);
+cudaError_t cudaMemcpy2DAsync(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, cudaMemcpyKind kind, cudaStream_t s = nullptr);
 cudaError_t cudaMemset(void* dst, int v, size_t n);
 cudaError_t cudaMemsetAsync(void* dst, int v, size_t n, cudaStream_t s = nullptr);
 cudaError_t cudaStreamCreate(cudaStream_t* s);

@@ -297,6 +297,10 @@ cudaError_t cudaFree(void* p) {
 cudaError_t cudaFreeHost(void* p) { return cudaFree(p); }
 cudaError_t cudaMemcpy(void* dst, const void* src, size_t n, cudaMemcpyKind) { std::memmove(dst, src, n); return cudaSuccess; }
 cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t n, cudaMemcpyKind, cudaStream_t) { std::memmove(dst, src, n); return cudaSuccess; }
+cudaError_t cudaMemcpy2DAsync(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, cudaMemcpyKind, cudaStream_t) {
+  for (size_t r = 0; r < height; r++) std::memmove((uint8_t*)dst + r * dpitch, (const uint8_t*)src + r * spitch, width);
+  return cudaSuccess;
+}
 cudaError_t cudaMemset(void* dst, int v, size_t n) { std::memset(dst, v, n); return cudaSuccess; }
 cudaError_t cudaMemsetAsync(void* dst, int v, size_t n, cudaStream_t) { std::memset(dst, v, n); return cudaSuccess; }
 struct CusimStream { int id; };
