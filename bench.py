@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- LERC encode+decode throughput of lerc_b200 on B200 (driver contract, task section 4).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c4]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c4|c5] [--gather]
 
 One "step" = lerc_encode + lerc_decode of one synthetic raster of BASELINE.json configs[1]
 (4096x4096 float32, 1 band, maxZError = 0.01; generator tests/cases.py:c2_raster).
@@ -14,6 +14,9 @@ One "step" = lerc_encode + lerc_decode of one synthetic raster of BASELINE.json 
 With N > 1 (torchrun) every rank codes its own raster (independent objects, weak scaling, no data-path
 collective); rank 0 reports units of all ranks / max-over-ranks time.
 --impl reference times the reference's CPU implementation on the host cores and prints the same JSON line.
+--workload c5 (BASELINE configs[4]): every rank holds an 8192 x 65536 strip of the 65536^2 float32 raster (8192 tiles of
+256 x 256; 8 ranks = the whole raster) and codes it with ONE lerc_b200_encodeTiles + ONE lerc_b200_decodeTiles call per
+step; --gather adds the all-gather of the per-tile streams (lerc_b200/tiles.py) as a separately reported time.
 """
 import argparse
 import ctypes as C
@@ -34,10 +37,14 @@ WORKLOADS = {
     # name: (rows, cols, nDepth, dtype code, maxZErr, description)
     "c2": (4096, 4096, 1, 6, 0.01, "4096x4096 float32 1-band encode+decode maxZError=0.01"),
     "c4": (8192, 8192, 3, 1, 0.0, "8192x8192 nDepth=3 uint8 lossless (Huffman path)"),
+    # per-rank strip of the 65536^2 raster; rows can be lowered with --strip-rows for a quick run
+    "c5": (8192, 65536, 1, 6, 0.01, "65536x65536 float32 as 256x256 tiles, 8192-row strip (8192 tiles) per GPU, encodeTiles+decodeTiles maxZError=0.01"),
 }
+TILE = 256
 
 
-METRIC = {"c2": "Gpixels/s encode+decode float32 @ maxZError=0.01; achieved HBM GB/s vs peak", "c4": "Gpixels/s encode+decode uint8 nDepth=3 lossless"}
+METRIC = {"c2": "Gpixels/s encode+decode float32 @ maxZError=0.01; achieved HBM GB/s vs peak", "c4": "Gpixels/s encode+decode uint8 nDepth=3 lossless",
+          "c5": "Gpixels/s encode+decode float32 @ maxZError=0.01, 256x256 tiles (one blob per tile); achieved HBM GB/s vs peak"}
 
 
 def make_raster(workload, seed):
@@ -99,7 +106,12 @@ def cpu_reference_run(workload, seconds_budget=20.0, threads=None):
     # re-entrant: one independent call per core)
     threads = threads or os.cpu_count() or 1
     strip_rows = min(rows, 1024 if workload == "c2" else 512)
-    img = make_raster(workload, 1234)[:strip_rows]
+    if workload == "c5":                               # one 256 x 256 tile per call, as the reference's tile callers do
+        from cases import c2_raster
+        strip_rows, cols = TILE, TILE
+        img = c2_raster(TILE, TILE, seed=1234)
+    else:
+        img = make_raster(workload, 1234)[:strip_rows]
     n_px = strip_rows * cols
 
     def one(out):
@@ -114,7 +126,7 @@ def cpu_reference_run(workload, seconds_budget=20.0, threads=None):
     single = []
     one(single)
     reps = max(1, int(seconds_budget / max(single[0], 1e-3) / 2))
-    reps = min(reps, 8)
+    reps = min(reps, 8 if workload != "c5" else 2000)
     t0 = time.perf_counter()
     res = []
     th = [threading.Thread(target=lambda: [one(res) for _ in range(reps)]) for _ in range(threads)]
@@ -127,6 +139,180 @@ def cpu_reference_run(workload, seconds_budget=20.0, threads=None):
             "sample": f"{strip_rows}x{cols} strip of the workload raster, {reps} encode+decode calls on each of {threads} threads ({wall:.1f} s wall)"}, wall / (threads * reps) * 1e3
 
 
+
+# ---------------------------------------------------------------------------------------------------
+def device_c2_strip(torch, rows, cols, row0, seed):
+    """tests/cases.py:c2_raster evaluated on the device for rows [row0, row0 + rows) of a cols-wide raster (fp64 math, cast to
+    float32; the noise comes from torch's generator, so only the distribution -- not the values -- matches the numpy one)."""
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    out = torch.empty((rows, cols), dtype=torch.float32, device="cuda")
+    xx = torch.arange(cols, dtype=torch.float64, device="cuda")[None, :]
+    for r0 in range(0, rows, 512):
+        r1 = min(rows, r0 + 512)
+        yy = torch.arange(row0 + r0, row0 + r1, dtype=torch.float64, device="cuda")[:, None]
+        z = 1000 + 300 * torch.sin(xx / 97) * torch.cos(yy / 131) + 50 * torch.sin(xx / 13 + yy / 17)
+        z += torch.randn((r1 - r0, cols), dtype=torch.float64, device="cuda", generator=g) * 0.5
+        out[r0:r1] = z.to(torch.float32)
+    return out
+
+
+def main_tiles(args, lib, rank, world, local_rank, warm, peak_gbs, peak_src):
+    import torch
+    import torch.distributed as dist
+    import lerc_b200
+    from lercapi import tiles_api
+    from lerc_b200.tiles import gather_container
+
+    rows, cols, depth, dt, mz, desc = WORKLOADS["c5"]
+    if args.strip_rows:
+        rows = args.strip_rows
+    assert rows % TILE == 0 and cols % TILE == 0
+    api = tiles_api(lib)
+    n_px = rows * cols
+    n_tiles = (rows // TILE) * (cols // TILE)
+    raw_bytes = n_px * 4
+    d_img = device_c2_strip(torch, rows, cols, rank * rows, 1234 + rank)
+    cap = int(api.lerc_b200_tilesMaxBytes(dt, cols, rows, TILE, TILE))
+    d_out = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    d_off = torch.zeros(n_tiles + 1, dtype=torch.int64, device="cuda")
+    d_dec = torch.empty_like(d_img)
+    n_written = C.c_ulonglong(0)
+    stream = torch.cuda.current_stream()
+    lerc_b200.set_stream(stream.cuda_stream, True)
+
+    def step_device():
+        st = api.lerc_b200_encodeTiles(d_img.data_ptr(), dt, cols, rows, TILE, TILE, mz, d_out.data_ptr(), cap, d_off.data_ptr(), C.addressof(n_written))
+        assert st == 0, f"lerc_b200_encodeTiles status {st}"
+        st = api.lerc_b200_decodeTiles(d_out.data_ptr(), n_written.value, d_off.data_ptr(), dt, cols, rows, TILE, TILE, d_dec.data_ptr())
+        assert st == 0, f"lerc_b200_decodeTiles status {st}"
+        return n_written.value
+
+    s0 = lerc_b200.stats()
+    for _ in range(warm):
+        blob_bytes = step_device()
+    s1 = lerc_b200.stats()
+    fast_enc, fast_dec = (s1[3] - s0[3]) // warm, (s1[4] - s0[4]) // warm
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    t_s = time.perf_counter()
+    while len(sampler.rows) < 2 and time.perf_counter() - t_s < 3.0:
+        step_device()
+    torch.cuda.synchronize()
+    launches0 = lerc_b200.stats()[0]
+    ev_all = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    ev_all[0].record(stream)
+    for _ in range(args.steps):
+        step_device()
+    ev_all[1].record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches = lerc_b200.stats()[0] - launches0
+    dev_ms = ev_all[0].elapsed_time(ev_all[1])
+    clocks = sampler.stop()
+    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    value = world * n_px / (ms_per_step * 1e-3) / 1e9
+    err = float((d_dec.double() - d_img.double()).abs().max().item())
+    assert err <= mz * 1.1, f"round trip error {err} exceeds maxZError {mz}"
+
+    # ---- per-kernel roofline (instrumented pass)
+    lerc_b200.kernel_times(reset=True)
+    lerc_b200.profile(True)
+    PROF = 3
+    for _ in range(PROF):
+        step_device()
+    torch.cuda.synchronize()
+    lerc_b200.profile(False)
+    kt = lerc_b200.kernel_times(reset=True)
+    top_name, (top_cnt, top_ms) = max(kt.items(), key=lambda kv: kv[1][1])
+    per_launch_ms = top_ms / top_cnt
+    algo_bytes = raw_bytes + blob_bytes          # both dominant kernels (fused tile encoder, tile block decoder) move the raster and the blobs once
+    achieved = algo_bytes / (per_launch_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": top_name, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs, "traffic": None,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": algo_bytes, "algorithmic_bytes_are": "strip read/written once + its blobs written/read once",
+                "kernel_ms_per_launch": per_launch_ms, "kernel_share_of_step": top_ms / PROF / ms_per_step,
+                "step_frac": (2 * algo_bytes) / (ms_per_step * 1e-3) / 1e9 / peak_gbs,
+                "kernels": {n: {"launches_per_step": c / PROF, "ms_per_step": m / PROF} for n, (c, m) in sorted(kt.items(), key=lambda kv: -kv[1][1])[:10]}}
+
+    # ---- the all-gather of the per-tile streams (only exchange step of the path; reported beside the codec time)
+    gather = None
+    if args.gather:
+        torch.cuda.synchronize()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        container, offsets = gather_container(d_out[:blob_bytes], d_off, n_tiles * world)      # warm-up
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        g0.record(stream)
+        container, offsets = gather_container(d_out[:blob_bytes], d_off, n_tiles * world)
+        g1.record(stream)
+        torch.cuda.synchronize()
+        tg = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        gather = {"ms": float(tg.item()), "container_bytes": int(container.numel()), "tiles": int(offsets.numel() - 1)}
+        del container
+
+    # ---- end to end: pinned host buffers through the same calls
+    lerc_b200.set_stream(0, False)
+    e2e_rows = min(rows, 2048)                                      # bounded: a 2048-row strip (2048 tiles, 537 MB) per call
+    e2e_px = e2e_rows * cols
+    e2e_tiles = (e2e_rows // TILE) * (cols // TILE)
+    h_in = d_img[:e2e_rows].cpu().pin_memory()
+    e2e_cap = int(api.lerc_b200_tilesMaxBytes(dt, cols, e2e_rows, TILE, TILE))
+    h_blob = torch.empty(e2e_cap, dtype=torch.uint8).pin_memory()
+    h_off = torch.zeros(e2e_tiles + 1, dtype=torch.int64)
+    h_out = torch.empty_like(h_in).pin_memory()
+
+    def step_host():
+        st = api.lerc_b200_encodeTiles(h_in.data_ptr(), dt, cols, e2e_rows, TILE, TILE, mz, h_blob.data_ptr(), e2e_cap, h_off.data_ptr(), C.addressof(n_written))
+        assert st == 0
+        st = api.lerc_b200_decodeTiles(h_blob.data_ptr(), n_written.value, h_off.data_ptr(), dt, cols, e2e_rows, TILE, TILE, h_out.data_ptr())
+        assert st == 0
+        return n_written.value
+
+    step_host()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    E2E = 3
+    t0 = time.perf_counter()
+    for _ in range(E2E):
+        nb = step_host()
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / E2E
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e = {"value": world * e2e_px / float(t.item()) / 1e9, "unit": "Gpixels/s", "ms_per_step": float(t.item()) * 1e3,
+           "h2d_bytes_per_step": e2e_px * 4 + nb, "d2h_bytes_per_step": nb + e2e_px * 4, "sample": f"{e2e_rows}x{cols} strip ({e2e_tiles} tiles) per call",
+           "timer": "host wall clock around the synchronous C-API calls"}
+    assert float((h_out.double() - h_in.double()).abs().max().item()) <= mz * 1.1
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline and args.gpus == 1:
+            cpu, _ = cpu_reference_run("c5", seconds_budget=15.0)
+        line = {"metric": METRIC["c5"], "value": value, "unit": "Gpixels/s", "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms_per_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": desc if not args.strip_rows else desc.replace("8192-row strip (8192 tiles)", f"{rows}-row strip ({n_tiles} tiles)"),
+                           "generator": "bench.py:device_c2_strip (tests/cases.py:c2_raster formula on the device)", "tiles_per_gpu": n_tiles,
+                           "blob_bytes": blob_bytes, "compression_ratio": raw_bytes / blob_bytes, "fused_encodes_per_step": fast_enc, "batch_decodes_per_step": fast_dec,
+                           "l2": f"strip {raw_bytes // 2**20} MiB + blobs {blob_bytes // 2**20} MiB per direction >> 126 MB L2",
+                           "sharding": "contiguous tile rows per rank, no data-path collective in the codec" + ("; stream all-gather timed separately" if args.gather else "")},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "gather": gather}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 # ---------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -136,6 +322,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", action="store_true", help="c5: also time the all-gather of the per-tile streams")
+    ap.add_argument("--strip-rows", type=int, default=0, help="c5: rows of the per-rank strip (multiple of 256; default 8192)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -168,6 +356,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = product_lib()
     assert lib is not None, "lerc_b200/libLerc.so.4 missing: run python __graft_entry__.py"
+    if args.workload == "c5":
+        return main_tiles(args, lib, rank, world, local_rank, warm, peak_gbs, peak_src)
     enc, dec = lib.f["encode"], lib.f["decode"]
     ts = np.dtype(DT_NP[dt]).itemsize
     raw_bytes = n_px * depth * ts

@@ -17,6 +17,7 @@ REQUIRED_SYMBOLS = [
     "lerc_getBlobInfo", "lerc_getDataRanges", "lerc_decode", "lerc_decodeToDouble",
     "lerc_computeCompressedSize_4D", "lerc_encode_4D", "lerc_decode_4D", "lerc_decodeToDouble_4D",
     "lerc_b200_set_stream", "lerc_b200_get_stats", "lerc_b200_version", "lerc_b200_profile", "lerc_b200_get_profile",
+    "lerc_b200_tilesMaxBytes", "lerc_b200_encodeTiles", "lerc_b200_decodeTiles",
 ]
 
 

@@ -25,35 +25,34 @@ def offsets_from_sizes(sizes):
     return out
 
 
-def gather_streams(local_blobs, n_tiles, group=None, device=None):
-    """local_blobs: the tile streams (bytes / uint8 tensors) of this rank's shard, in tile order.
-    Returns (container uint8 tensor with all n_tiles streams back to back in tile order, int64 offsets[n_tiles + 1])."""
+def gather_container(local, local_offsets, n_tiles, group=None):
+    """local: uint8 tensor with this rank's tile streams back to back in tile order (what lerc_b200_encodeTiles writes for the
+    rank's tile range); local_offsets: its n_local + 1 byte offsets.  Returns (container with all n_tiles streams back to back
+    in global tile order, int64 offsets[n_tiles + 1]) on every rank: one all-gather of the byte counts, an exclusive prefix
+    sum, one padded all-gather of the payloads."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     lo, hi = shard_tiles(n_tiles, rank, world)
-    assert len(local_blobs) == hi - lo, (len(local_blobs), lo, hi)
-    if device is None:
-        device = local_blobs[0].device if (local_blobs and torch.is_tensor(local_blobs[0])) else torch.device("cpu")
-    blobs = [b if torch.is_tensor(b) else torch.frombuffer(bytearray(b), dtype=torch.uint8) for b in local_blobs]
-    blobs = [b.to(device) for b in blobs]
+    device = local.device
+    off = torch.as_tensor(local_offsets).to(device=device, dtype=torch.int64)
+    assert off.numel() == hi - lo + 1, (off.numel(), lo, hi)
     max_tiles = -(-n_tiles // world)
     my_sizes = torch.zeros(max_tiles, dtype=torch.int64, device=device)
-    if blobs:
-        my_sizes[: len(blobs)] = torch.tensor([b.numel() for b in blobs], dtype=torch.int64, device=device)
+    my_sizes[: hi - lo] = off[1:] - off[:-1]
     if world == 1:
         all_sizes = [my_sizes]
     else:
         all_sizes = [torch.empty_like(my_sizes) for _ in range(world)]
         dist.all_gather(all_sizes, my_sizes, group=group)
     # per-tile sizes in global tile order
-    sizes = torch.cat([all_sizes[r][: shard_tiles(n_tiles, r, world)[1] - shard_tiles(n_tiles, r, world)[0]] for r in range(world)])
+    counts = [shard_tiles(n_tiles, r, world)[1] - shard_tiles(n_tiles, r, world)[0] for r in range(world)]
+    sizes = torch.cat([all_sizes[r][: counts[r]] for r in range(world)])
     offsets = offsets_from_sizes(sizes)
-    rank_bytes = [int(all_sizes[r].sum().item()) for r in range(world)]
+    rank_bytes = torch.stack([a.sum() for a in all_sizes]).tolist()
+    assert rank_bytes[rank] <= local.numel()
     pad = max(rank_bytes) if rank_bytes else 0
     mine = torch.zeros(max(pad, 1), dtype=torch.uint8, device=device)
-    if blobs:
-        cat = torch.cat(blobs)
-        mine[: cat.numel()] = cat
+    mine[: rank_bytes[rank]] = local[: rank_bytes[rank]]
     if world == 1:
         parts = [mine]
     else:
@@ -62,3 +61,15 @@ def gather_streams(local_blobs, n_tiles, group=None, device=None):
     container = torch.cat([parts[r][: rank_bytes[r]] for r in range(world)])
     assert container.numel() == int(offsets[-1].item())
     return container, offsets
+
+
+def gather_streams(local_blobs, n_tiles, group=None, device=None):
+    """local_blobs: the tile streams (bytes / uint8 tensors) of this rank's shard, in tile order.
+    Returns (container uint8 tensor with all n_tiles streams back to back in tile order, int64 offsets[n_tiles + 1])."""
+    if device is None:
+        device = local_blobs[0].device if (local_blobs and torch.is_tensor(local_blobs[0])) else torch.device("cpu")
+    blobs = [b if torch.is_tensor(b) else torch.frombuffer(bytearray(b), dtype=torch.uint8) for b in local_blobs]
+    blobs = [b.to(device) for b in blobs]
+    local = torch.cat(blobs) if blobs else torch.zeros(0, dtype=torch.uint8, device=device)
+    off = offsets_from_sizes(torch.tensor([b.numel() for b in blobs], dtype=torch.int64, device=device))
+    return gather_container(local, off, n_tiles, group=group)
