@@ -81,6 +81,12 @@ __global__ void k_tiles_parse(TilesDecArgs a) {
   a.recs[img] = rec;
 }
 
+// bytes of a block offset stored with type code tc for pixel type T (Lerc2.h:528-542), 0 when the code is not valid for T
+template <class T> __device__ __forceinline__ int offsetSizeFromCode(int tc) {
+  const int dtUsed = offsetTypeFromCode(PixelTraits<T>::code, tc);
+  return dtUsed == DT_Undefined ? 0 : dtSize(dtUsed);
+}
+
 constexpr int TD_WIN = 4096;          // stream bytes walked per window
 constexpr int TD_MAXW = 1024;         // blocks per window at most (flat areas: 1-3 bytes per block)
 
@@ -175,11 +181,22 @@ __global__ void __launch_bounds__(NT) k_tiles_blocks(TilesDecArgs a) {
           if (pos >= streamLen) { bad = 1; break; }
           const int h = min(8, rows - ty * 8), w = min(8, cols - tx * 8);
           const uint8_t* p = sBuf + d + (pos - cur);
-          FdUnit u;
-          if (!fdParse<T>(p, version, h * w, true, u) || fdPattern(p[0], version) != (tx & (version >= 5 ? 14 : 15)) || u.len > MAXU ||
-              (unsigned long long)pos + (unsigned)u.len > streamLen) { bad = 1; break; }
+          const uint32_t flag = p[0];
+          int len;
+          // the common unit first: bit-stuffed, one-byte count, no LUT (flag | offset | numBits byte | count | packed values)
+          const int oszQ = offsetSizeFromCode<T>((int)(flag >> 6));
+          const uint32_t nbByte = p[1 + oszQ];
+          if ((flag & 3) == 1 && !(version >= 5 && (flag & 4)) && oszQ > 0 && (nbByte & 0xe0) == 0x80) {
+            if (p[2 + oszQ] != (uint32_t)(h * w)) { bad = 1; break; }
+            len = 3 + oszQ + (int)(((uint32_t)(h * w) * (nbByte & 31) + 7) >> 3);
+          } else {
+            FdUnit u;
+            if (!fdParse<T>(p, version, h * w, true, u) || u.len > MAXU) { bad = 1; break; }
+            len = u.len;
+          }
+          if (fdPattern(flag, version) != (tx & (version >= 5 ? 14 : 15)) || (unsigned long long)pos + (unsigned)len > streamLen) { bad = 1; break; }
           sPos[n++] = (uint16_t)(pos - cur);
-          pos += (uint32_t)u.len;
+          pos += (uint32_t)len;
           blk++;
           if (++tx == nTx) { tx = 0; ty++; }
         }
@@ -264,9 +281,16 @@ ErrCode decodeTilesT(Context* ctx, const TilesGeom& g, const uint8_t* dBlobs, si
     a.blobs = dBlobs; a.offsets = dOff; a.nImg = (int)nImg; a.nImgX = g.nImgX; a.imgCols = g.tileCols; a.imgRows = g.tileRows;
     a.rasterCols = g.nCols; a.rasterRows = g.nRows; a.recs = dRecs; a.data = dData;
     LERC_LAUNCH(ctx, k_tiles_parse<T>, (unsigned)((nImg + 127) / 128), 128, 0, a);
-    constexpr int NT = 128;
-    const long long grid = std::min<long long>(nImg, (long long)smCount() * 16);
-    LERC_LAUNCH(ctx, (k_tiles_blocks<T, NT>), (unsigned)grid, NT, 0, a);
+    // CTA size: fewer threads per CTA = more CTAs (and header walkers) per SM; LERC_B200_TILES_NT = 64 | 128 | 256 for experiments
+    static const int nt = [] { const char* e = std::getenv("LERC_B200_TILES_NT"); const int v = e ? std::atoi(e) : 128; return (v == 64 || v == 256) ? v : 128; }();
+    auto launch = [&](auto kernel, int NT) {
+      static int ctasPerSm = 0;                     // all CTAs resident, each strides over the blobs: no tail wave
+      if (!ctasPerSm && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSm, kernel, NT, 0) != cudaSuccess || ctasPerSm < 1)) ctasPerSm = 1;
+      const long long grid = std::min<long long>(nImg, (long long)smCount() * ctasPerSm);
+      LaunchScope scope_(ctx, "k_tiles_blocks<T>");
+      kernel<<<(unsigned)grid, NT, 0, ctx->stream>>>(a); ctx->kernelLaunches++;
+    };
+    if (nt == 64) launch(k_tiles_blocks<T, 64>, 64); else if (nt == 256) launch(k_tiles_blocks<T, 256>, 256); else launch(k_tiles_blocks<T, 128>, 128);
     if (!cudaOk(cudaMemcpyAsync(recs.data(), dRecs, (size_t)nImg * sizeof(TileDecRec), cudaMemcpyDeviceToHost, st), "D2H tile records")) return Failed;
     if (!cudaOk(cudaStreamSynchronize(st), "sync")) return Failed;
     if (!cudaOk(cudaGetLastError(), "decodeTiles")) return Failed;

@@ -212,7 +212,7 @@ ErrCode encodeTilesFast(Context* ctx, const TilesGeom& g, const void* dData, dou
       if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSm, kernel, 256, smem) != cudaSuccess || ctasPerSm < 1) ctasPerSm = 1;
     }
     const long long grid = std::min<long long>(nSeg, (long long)ctasPerSm * std::max(sms, 1));       // all CTAs co-resident (look-back)
-    LERC_LAUNCH(ctx, (k_encode_fused<T, 4, true>), (unsigned)grid, 256, smem, fa, fb);
+    { LaunchScope scope_(ctx, "k_encode_fused<T, tiles>"); kernel<<<(unsigned)grid, 256, smem, ctx->stream>>>(fa, fb); ctx->kernelLaunches++; }
   }
   ctx->joinSide();
   TileFinishArgs ta;
