@@ -657,7 +657,8 @@ bool encodeBandFast(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
   const size_t dataStart = (size_t)headerBytes(6) + 4 + 2 * sizeof(T) + 1;
   if (a.outCapacity < dataStart + 1) return false;                     // let the general path report BufferTooSmall exactly
 
-  const size_t stateBytes = sizeof(FastEncResult) + 9 * 8 + (size_t)nTiles * 8;
+  const size_t nGroups = (size_t)((nTiles + 31) / 32);
+  const size_t stateBytes = sizeof(FastEncResult) + 9 * 8 + (size_t)nTiles * 8 + nGroups * 8;
   uint8_t* dState = (uint8_t*)ctx->arena.alloc(stateBytes);
   struct HostRes { FastEncResult r; unsigned long long raise[9]; };
   HostRes* hRes = (HostRes*)ctx->pinnedAlloc(sizeof(HostRes));
@@ -688,6 +689,9 @@ bool encodeBandFast(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
   uint8_t* blob = a.dOut + a.outOffset;
   fa.stream = blob + dataStart; fa.streamCap = a.outCapacity - dataStart; fa.regionOff = (long long)dataStart - 14;
   fa.tileState = (unsigned long long*)(dState + sizeof(FastEncResult) + 9 * 8); fa.res = dRes;
+  // look-back: aggregates per group of 32 tiles (two dependent rounds per tile) unless LERC_B200_ENC_LB=chain (plain chain, ~grid / 32 rounds)
+  static const bool groupLb = [] { const char* e = std::getenv("LERC_B200_ENC_LB"); return !(e && std::strcmp(e, "chain") == 0); }();
+  fa.groupState = (groupLb && ctaTiles) ? fa.tileState + nTiles : nullptr;
   constexpr int MAXB = 1 + 64 * (int)sizeof(T);
   int dev = 0, sms = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (ctaTiles) {

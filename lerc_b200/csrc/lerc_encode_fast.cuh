@@ -42,6 +42,7 @@ struct FastEncArgs {
   long long regionOff;                 // checksum-region offset of stream[0] (= dataStart - 14)
   unsigned long long* tileState;       // [nTiles], zero-initialised
   FastEncResult* res;
+  unsigned long long* groupState;      // [ceil(nTiles / 32)], zero-initialised: aggregates of 32 consecutive tiles (two-round look-back); nullptr = plain chain
 };
 
 // ---- tile batch (k_encode_fused<T, MINB, true>, lerc_tiles_encode.cuh): the raster is cut into imgRows x imgCols images, every
@@ -491,6 +492,49 @@ __global__ void __launch_bounds__(256, MINB) k_encode_fused(FastEncArgs a, typen
     if (warp == 0) {
       unsigned long long excl = 0;
       const long long first = BATCH ? (long long)(tile - local) : 0;    // the chain restarts at every image of a tile batch
+      if (!BATCH && a.groupState) {
+        // Two-round look-back.  With G resident CTAs the plain chain below needs ~G / 32 dependent rounds per tile (the tiles of the
+        // current sweep only have aggregates yet); here round 1 covers the predecessors inside the tile's group of 32 and round 2
+        // the aggregates of whole groups, published by the CTA that sizes a group's last tile.
+        volatile unsigned long long* gs = a.groupState;
+        const int l = tile & 31;
+        const long long g = tile >> 5;
+        bool needGroups = g > 0;
+        {
+          const long long idx = (long long)tile - 1 - lane;
+          const bool in = lane < l;
+          unsigned long long s = 0;
+          if (in) { do { s = st[idx]; } while ((s >> 62) == 0); }
+          const unsigned isP = __ballot_sync(FULL, in && (s >> 62) == 2);
+          const int firstP = isP ? __ffs(isP) - 1 : 32;
+          unsigned long long contrib = (in && lane <= firstP) ? (s & VAL) : 0;
+#pragma unroll
+          for (int m = 16; m; m >>= 1) contrib += __shfl_xor_sync(FULL, contrib, m);
+          excl = contrib;
+          if (isP) needGroups = false;                                  // an inclusive prefix inside the group: excl is already global
+        }
+        if (l == 31 && needGroups && lane == 0) gs[g] = ST_A | (excl + tileBytes);    // this group's bytes (its 32 tiles are all sized)
+        if (needGroups) {
+          long long base = g - 1;
+          for (;;) {
+            const long long idx = base - lane;
+            unsigned long long s = ST_P;                                // virtual groups before 0: prefix 0
+            if (idx >= 0) { do { s = gs[idx]; } while ((s >> 62) == 0); }
+            const unsigned isP = __ballot_sync(FULL, (s >> 62) == 2);
+            const int firstP = isP ? __ffs(isP) - 1 : 32;
+            unsigned long long contrib = (lane <= firstP && idx >= 0) ? (s & VAL) : 0;
+#pragma unroll
+            for (int m = 16; m; m >>= 1) contrib += __shfl_xor_sync(FULL, contrib, m);
+            excl += contrib;
+            if (isP) break;
+            base -= 32;
+          }
+        }
+        if (lane == 0) {
+          if (tile > 0) st[tile] = ST_P | (excl + tileBytes);
+          if (l == 31) gs[g] = ST_P | (excl + tileBytes);               // inclusive prefix of the whole group
+        }
+      } else
       if (tile > first) {
         long long base = (long long)tile - 1;
         for (;;) {

@@ -196,7 +196,7 @@ ErrCode encodeTilesFast(Context* ctx, const TilesGeom& g, const void* dData, dou
   fa.maxZErr = maxZErr; fa.scale = 1.0 / (2.0 * maxZErr); fa.maxZErr3 = 3.0 * maxZErr; fa.maxQ = fa.dt <= DT_UShort ? (1u << 15) - 1 : (1u << 30) - 1;   // Lerc2.h:685-703
   fa.intLossless = (!isFlt && maxZErr == 0.5) ? 1 : 0;
   fa.regionOff = (long long)dataStart - 14;
-  fa.tileState = dSegState;
+  fa.tileState = dSegState; fa.groupState = nullptr;
   FastBatchArgs fb;
   fb.imgCols = g.tileCols; fb.imgRows = g.tileRows; fb.nImgX = g.nImgX; fb.nImgY = g.nImgY; fb.rasterCols = g.nCols; fb.rasterRows = g.nRows;
   fb.segPerImg = segPerImg; fb.dataStart = dataStart; fb.pitch = g.nCols;
