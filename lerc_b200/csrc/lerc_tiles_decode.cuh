@@ -281,8 +281,8 @@ ErrCode decodeTilesT(Context* ctx, const TilesGeom& g, const uint8_t* dBlobs, si
     a.blobs = dBlobs; a.offsets = dOff; a.nImg = (int)nImg; a.nImgX = g.nImgX; a.imgCols = g.tileCols; a.imgRows = g.tileRows;
     a.rasterCols = g.nCols; a.rasterRows = g.nRows; a.recs = dRecs; a.data = dData;
     LERC_LAUNCH(ctx, k_tiles_parse<T>, (unsigned)((nImg + 127) / 128), 128, 0, a);
-    // CTA size: fewer threads per CTA = more CTAs (and header walkers) per SM; LERC_B200_TILES_NT = 64 (default; measured 1.28 ms vs 1.33 / 1.77 ms for 128 / 256 on 4096 tiles) | 128 | 256 | 32 (one warp per blob: no CTA-wide waiting on the header walk)
-    static const int nt = [] { const char* e = std::getenv("LERC_B200_TILES_NT"); const int v = e ? std::atoi(e) : 64; return (v == 32 || v == 128 || v == 256) ? v : 64; }();
+    // CTA size: fewer threads per CTA = more CTAs (and header walkers) per SM; LERC_B200_TILES_NT = 32 (default: one warp per blob, no CTA-wide waiting on the header walk; measured 0.94 ms on 4096 tiles) | 64 (1.28 ms) | 128 (1.33 ms) | 256 (1.77 ms)
+    static const int nt = [] { const char* e = std::getenv("LERC_B200_TILES_NT"); const int v = e ? std::atoi(e) : 32; return (v == 64 || v == 128 || v == 256) ? v : 32; }();
     auto launch = [&](auto kernel, int NT) {
       static int ctasPerSm = 0;                     // all CTAs resident, each strides over the blobs: no tail wave
       if (!ctasPerSm && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSm, kernel, NT, 0) != cudaSuccess || ctasPerSm < 1)) ctasPerSm = 1;
@@ -290,7 +290,7 @@ ErrCode decodeTilesT(Context* ctx, const TilesGeom& g, const uint8_t* dBlobs, si
       LaunchScope scope_(ctx, "k_tiles_blocks<T>");
       kernel<<<(unsigned)grid, NT, 0, ctx->stream>>>(a); ctx->kernelLaunches++;
     };
-    if (nt == 32) launch(k_tiles_blocks<T, 32>, 32); else if (nt == 128) launch(k_tiles_blocks<T, 128>, 128); else if (nt == 256) launch(k_tiles_blocks<T, 256>, 256); else launch(k_tiles_blocks<T, 64>, 64);
+    if (nt == 64) launch(k_tiles_blocks<T, 64>, 64); else if (nt == 128) launch(k_tiles_blocks<T, 128>, 128); else if (nt == 256) launch(k_tiles_blocks<T, 256>, 256); else launch(k_tiles_blocks<T, 32>, 32);
     if (!cudaOk(cudaMemcpyAsync(recs.data(), dRecs, (size_t)nImg * sizeof(TileDecRec), cudaMemcpyDeviceToHost, st), "D2H tile records")) return Failed;
     if (!cudaOk(cudaStreamSynchronize(st), "sync")) return Failed;
     if (!cudaOk(cudaGetLastError(), "decodeTiles")) return Failed;

@@ -211,6 +211,56 @@ static void unpack_lsb(const u8* src, u32* v, u32 n, int nb) {
   }
 }
 
+/* Lerc2 v2 bit stuffing (BitStuffer2.cpp:292-425): values MSB-first inside little-endian uint32 words; the unused low
+ * bytes of the last word are dropped by shifting that word down (so its used bytes come first). */
+static u32 tail_bytes_not_needed(u32 n, int nb) {             /* BitStuffer2.h:127-132 */
+  int bitsTail = (int)(((u64)n * (u64)nb) & 31), bytesTail = (bitsTail + 7) >> 3;
+  return bytesTail > 0 ? (u32)(4 - bytesTail) : 0;
+}
+static void pack_msb_v2(u8* dst, const u32* v, u32 n, int nb) {
+  size_t nWords = (size_t)(((u64)n * (u64)nb + 31) / 32);
+  u32* w = (u32*)calloc(nWords + 1, sizeof(u32));
+  size_t k = 0; int bitPos = 0;
+  for (u32 i = 0; i < n; i++) {
+    if (32 - bitPos >= nb) {
+      w[k] |= v[i] << (32 - bitPos - nb);
+      bitPos += nb;
+      if (bitPos == 32) { bitPos = 0; k++; }
+    } else {
+      int r = nb - (32 - bitPos);
+      w[k] |= v[i] >> r; k++;
+      w[k] |= v[i] << (32 - r);
+      bitPos = r;
+    }
+  }
+  u32 drop = tail_bytes_not_needed(n, nb);
+  if (nWords) w[nWords - 1] >>= 8 * drop;
+  memcpy(dst, w, nWords * 4 - drop);            /* == packed_bytes(n, nb) */
+  free(w);
+}
+static void unpack_msb_v2(const u8* src, u32* v, u32 n, int nb) {
+  size_t nWords = (size_t)(((u64)n * (u64)nb + 31) / 32), len = packed_bytes(n, nb);
+  u32* w = (u32*)calloc(nWords + 1, sizeof(u32));
+  memcpy(w, src, len);
+  u32 drop = tail_bytes_not_needed(n, nb);
+  if (nWords) w[nWords - 1] <<= 8 * drop;
+  size_t k = 0; int bitPos = 0;
+  for (u32 i = 0; i < n; i++) {
+    if (32 - bitPos >= nb) {
+      v[i] = (w[k] << bitPos) >> (32 - nb);
+      bitPos += nb;
+      if (bitPos == 32) { bitPos = 0; k++; }
+    } else {
+      u32 hi = (w[k] << bitPos) >> (32 - nb); k++;
+      bitPos -= 32 - nb;
+      v[i] = hi | (w[k] >> (32 - bitPos));
+    }
+  }
+  free(w);
+}
+static void pack_bits(u8* dst, const u32* v, u32 n, int nb, int version) { if (version >= 3) pack_lsb(dst, v, n, nb); else pack_msb_v2(dst, v, n, nb); }
+static void unpack_bits(const u8* src, u32* v, u32 n, int nb, int version) { if (version >= 3) unpack_lsb(src, v, n, nb); else unpack_msb_v2(src, v, n, nb); }
+
 static u8* put_count(u8* p, u32 n, int nBytes) {
   if (nBytes == 1) *p = (u8)n;
   else if (nBytes == 2) { uint16_t s = (uint16_t)n; memcpy(p, &s, 2); }
@@ -223,13 +273,13 @@ static u32 simple_size(u32 n, u32 maxElem) {   /* BitStuffer2.h:68-74 */
 }
 
 /* BitStuffer2.cpp:35-75 */
-static u8* encode_simple(u8* p, const u32* v, u32 n) {
+static u8* encode_simple(u8* p, const u32* v, u32 n, int version) {
   u32 mx = 0;
   for (u32 i = 0; i < n; i++) if (v[i] > mx) mx = v[i];
   int nb = bit_length(mx), cb = count_field_bytes(n);
   *p++ = (u8)(nb | ((cb == 4 ? 0 : 3 - cb) << 6));
   p = put_count(p, n, cb);
-  if (nb > 0) { pack_lsb(p, v, n, nb); p += packed_bytes(n, nb); }
+  if (nb > 0) { pack_bits(p, v, n, nb, version); p += packed_bytes(n, nb); }
   return p;
 }
 
@@ -259,7 +309,7 @@ static u32 lut_or_simple_size(const u32* v, u32 n, u32* scratch, int* useLut) {
 }
 
 /* BitStuffer2.cpp:79-153.  v[] must contain a 0 (the block minimum).  NULL on failure. */
-static u8* encode_lut(u8* p, const u32* v, u32 n, u32* scratch, u32* idxScratch) {
+static u8* encode_lut(u8* p, const u32* v, u32 n, u32* scratch, u32* idxScratch, int version) {
   u32 m = distinct_sorted(v, n, scratch);
   if (m < 2 || m > 255 || scratch[0] != 0) return NULL;
   u32 nLut = m - 1;
@@ -273,14 +323,14 @@ static u8* encode_lut(u8* p, const u32* v, u32 n, u32* scratch, u32* idxScratch)
   *p++ = (u8)(nb | (1 << 5) | ((cb == 4 ? 0 : 3 - cb) << 6));
   p = put_count(p, n, cb);
   *p++ = (u8)(nLut + 1);
-  pack_lsb(p, scratch + 1, nLut, nb); p += packed_bytes(nLut, nb);
-  pack_lsb(p, idxScratch, n, nbIdx);  p += packed_bytes(n, nbIdx);
+  pack_bits(p, scratch + 1, nLut, nb, version); p += packed_bytes(nLut, nb);
+  pack_bits(p, idxScratch, n, nbIdx, version);  p += packed_bytes(n, nbIdx);
   return p;
 }
 
-/* BitStuffer2.cpp:159-258 (v3+ branch).  Returns bytes consumed, 0 on malformed input.
+/* BitStuffer2.cpp:159-258 (both bit orders).  Returns bytes consumed, 0 on malformed input.
  * v[] must hold maxCount entries. */
-static size_t decode_bitstuffed(const u8* p, size_t avail, u32* v, u32 maxCount, u32* nOut) {
+static size_t decode_bitstuffed(const u8* p, size_t avail, u32* v, u32 maxCount, u32* nOut, int version) {
   const u8* p0 = p;
   if (avail < 1) return 0;
   u8 b = *p++; avail--;
@@ -295,7 +345,7 @@ static size_t decode_bitstuffed(const u8* p, size_t avail, u32* v, u32 maxCount,
       if (n == 0) return 0;
       size_t len = packed_bytes(n, nb);
       if (avail < len) return 0;
-      unpack_lsb(p, v, n, nb); p += len;
+      unpack_bits(p, v, n, nb, version); p += len;
     } else memset(v, 0, n * sizeof(u32));
   } else {
     if (nb == 0 || avail < 1) return 0;
@@ -305,11 +355,11 @@ static size_t decode_bitstuffed(const u8* p, size_t avail, u32* v, u32 maxCount,
     size_t len = packed_bytes((u32)nLut, nb);
     if (avail < len) return 0;
     table[0] = 0;
-    unpack_lsb(p, table + 1, (u32)nLut, nb); p += len; avail -= len;
+    unpack_bits(p, table + 1, (u32)nLut, nb, version); p += len; avail -= len;
     int nbIdx = bit_length((u32)nLut);
     len = packed_bytes(n, nbIdx);
     if (avail < len) return 0;
-    unpack_lsb(p, v, n, nbIdx); p += len;
+    unpack_bits(p, v, n, nbIdx, version); p += len;
     for (u32 i = 0; i < n; i++) { if (v[i] > (u32)nLut) return 0; v[i] = table[v[i]]; }
   }
   *nOut = n;
@@ -465,14 +515,14 @@ static int msb_get(const u8* base, u64 bitPos) {
 }
 
 /* Huffman.cpp:126-166 + :442-467.  Destination must be zero-filled.  Returns bytes written. */
-static size_t huff_write_table(u8* p, const uint16_t* len, const u32* code, int size) {
+static size_t huff_write_table(u8* p, const uint16_t* len, const u32* code, int size, int version) {
   u8* p0 = p;
   int i0, i1, maxLen;
   if (!huff_range(len, size, &i0, &i1, &maxLen)) return 0;
   put_i32(&p, 4); put_i32(&p, size); put_i32(&p, i0); put_i32(&p, i1);
   u32 lens[512];
   for (int i = i0; i < i1; i++) lens[i - i0] = len[wrap(i, size)];
-  p = encode_simple(p, lens, (u32)(i1 - i0));
+  p = encode_simple(p, lens, (u32)(i1 - i0), version);
   msb_writer w = {p, 0};
   for (int i = i0; i < i1; i++) { int k = wrap(i, size); if (len[k] > 0) msb_put(&w, code[k], len[k]); }
   p += 4 * ((w.bitPos + 31) >> 5);
@@ -480,7 +530,7 @@ static size_t huff_write_table(u8* p, const uint16_t* len, const u32* code, int 
 }
 
 /* Huffman.cpp:170-234 + :471-537.  Returns bytes consumed or 0. */
-static size_t huff_read_table(const u8* p, size_t avail, uint16_t* len, u32* code, int* sizeOut) {
+static size_t huff_read_table(const u8* p, size_t avail, uint16_t* len, u32* code, int* sizeOut, int version) {
   const u8* p0 = p;
   if (avail < 16) return 0;
   int ver = get_i32(&p), size = get_i32(&p), i0 = get_i32(&p), i1 = get_i32(&p);
@@ -488,7 +538,7 @@ static size_t huff_read_table(const u8* p, size_t avail, uint16_t* len, u32* cod
   if (ver < 2 || i0 >= i1 || i0 < 0 || size < 0 || size > 256) return 0;
   if (wrap(i0, size) >= size || wrap(i1 - 1, size) >= size || i1 - i0 > 512) return 0;
   u32 lens[512], n = 0;
-  size_t used = decode_bitstuffed(p, avail, lens, (u32)(i1 - i0), &n);
+  size_t used = decode_bitstuffed(p, avail, lens, (u32)(i1 - i0), &n, version);
   if (!used || n != (u32)(i1 - i0)) return 0;
   p += used; avail -= used;
   for (int i = 0; i < size; i++) { len[i] = 0; code[i] = 0; }
@@ -726,7 +776,7 @@ static int read_band_header(const u8* p, size_t avail, lo_hdr* h, int* hasMask);
 /* ------------------------------------------------------------------------------------------- */
 /* API                                                                  Lerc_c_api_impl.cpp:33-305 */
 
-typedef unsigned (*enc_fn)(const void*, int, int, int, int, int, const u8*, double, u8*, unsigned, unsigned*, unsigned*);
+typedef unsigned (*enc_fn)(const void*, int, int, int, int, int, int, const u8*, double, u8*, unsigned, unsigned*, unsigned*);
 typedef unsigned (*dec_fn)(const u8*, unsigned, int, u8*, int, int, int, int, void*);
 static const enc_fn kEnc[8] = {encode_bands_i8, encode_bands_u8, encode_bands_i16, encode_bands_u16,
                                encode_bands_i32, encode_bands_u32, encode_bands_f32, encode_bands_f64};
@@ -745,10 +795,10 @@ static unsigned encode_common(const void* data, int version, unsigned dt, int nD
   if (!data || dt >= LO_UNDEFINED || nDepth <= 0 || nCols <= 0 || nRows <= 0 || nBands <= 0 || maxZErr < 0) return LO_WRONG_PARAM;
   if (!sizeOnly && (!out || !outSize)) return LO_WRONG_PARAM;
   if (!(nMasks == 0 || nMasks == 1 || nMasks == nBands) || (nMasks > 0 && !validBytes)) return LO_WRONG_PARAM;
-  if (!(version == -1 || version == 6)) return LO_WRONG_PARAM;     /* older writers: out of scope, see header */
+  if (version > 6 || (version >= 0 && version < 2)) return LO_WRONG_PARAM;   /* Lerc2::SetEncoderToOldVersion, Lerc2.cpp:52-63 */
   if (!dims_ok(nDepth, nCols, nRows, kTypeSize[dt])) return LO_DIMS_TOO_LARGE;
   if (!sizeOnly) memset(out, 0, outSize);                          /* Lerc.cpp:374 */
-  return kEnc[dt](data, nDepth, nCols, nRows, nBands, nMasks, validBytes, maxZErr, sizeOnly ? NULL : out, outSize, nWritten, nNeeded);
+  return kEnc[dt](data, version < 0 ? 6 : version, nDepth, nCols, nRows, nBands, nMasks, validBytes, maxZErr, sizeOnly ? NULL : out, outSize, nWritten, nNeeded);
 }
 
 unsigned lo_computeCompressedSizeForVersion(const void* data, int version, unsigned dt, int nDepth, int nCols, int nRows,

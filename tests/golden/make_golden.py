@@ -62,6 +62,27 @@ def main():
         dec.append(h.hexdigest())
     np.savez_compressed(os.path.join(HERE, "synthetic_ref.npz"), names=np.array(names), sizes=np.array(sizes), enc=np.array(enc), dec=np.array(dec))
     print("synthetic cases:", len(names))
+    # the same rasters through lerc_encodeForVersion(2..5) (Lerc::EncodeInternal_v5, Lerc.cpp:526-624): status, blob and pixel hashes
+    keys, status, enc, dec, sizes = [], [], [], [], []
+    for v in (2, 3, 4, 5):
+        for name, arr, mz, kw in all_cases():
+            st, blob, _ = ref.encode(arr, mz, version=v, **kw)
+            keys.append(f"{name}|{v}")
+            status.append(st)
+            if st != 0:
+                sizes.append(0); enc.append(""); dec.append("")
+                continue
+            st2, data, mask = ref.decode(blob)
+            assert st2 == 0
+            sizes.append(len(blob))
+            enc.append(hashlib.sha256(blob).hexdigest())
+            h = hashlib.sha256(data.tobytes())
+            if mask is not None:
+                h.update(mask.tobytes())
+            dec.append(h.hexdigest())
+    np.savez_compressed(os.path.join(HERE, "synthetic_ref_versions.npz"), keys=np.array(keys), status=np.array(status), sizes=np.array(sizes),
+                        enc=np.array(enc), dec=np.array(dec))
+    print("old-version cases:", len(keys))
 
 
 if __name__ == "__main__":

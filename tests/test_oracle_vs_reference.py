@@ -96,6 +96,52 @@ def test_synthetic_hashes(oracle):
     assert checked >= 50
 
 
+def test_old_codec_versions_hashes(oracle):
+    """lerc_encodeForVersion(2..5) (Lerc::EncodeInternal_v5, Lerc.cpp:526-624; v2 = MSB-first bit stuffing without checksum):
+    status, blob and decoded pixels of the oracle hash to the reference's (synthetic_ref_versions.npz)"""
+    g = np.load(os.path.join(GOLD, "synthetic_ref_versions.npz"))
+    want = {str(k): (int(st), int(s), str(e), str(d)) for k, st, s, e, d in zip(g["keys"], g["status"], g["sizes"], g["enc"], g["dec"])}
+    checked = 0
+    for v in (2, 3, 4, 5):
+        for name, arr, mz, kw in all_cases():
+            st_w, size_w, enc_w, dec_w = want[f"{name}|{v}"]
+            st, blob, _ = oracle.encode(arr, mz, version=v, **kw)
+            assert st == st_w, (name, v)
+            if st != 0:
+                continue
+            assert len(blob) == size_w and hashlib.sha256(blob).hexdigest() == enc_w, f"{name} v{v}: blob differs from the reference's"
+            st, data, mask = oracle.decode(blob)
+            assert st == 0
+            h = hashlib.sha256(data.tobytes())
+            if mask is not None:
+                h.update(mask.tobytes())
+            assert h.hexdigest() == dec_w, f"{name} v{v}: decoded pixels differ from the reference's"
+            st2, n = oracle.compute_size(arr, mz, version=v, **kw)
+            assert st2 == 0 and n == len(blob)
+            checked += 1
+    assert checked >= 200
+
+
+def test_bluemarble_reencode_v3_reproduces_the_shipped_blob(oracle):
+    """lerc_encodeForVersion(3) of the pixels decoded from testData/bluemarble_256_256_3_byte.lerc2 reproduces the
+    file except, per band, the checksum (4 bytes at offset 10) and the Huffman read-ahead pad (last 4 bytes)."""
+    blob = open(os.path.join(GOLD, "bluemarble_256_256_3_byte.lerc2"), "rb").read()
+    g = np.load(os.path.join(GOLD, "bluemarble_256_256_3_byte.npz"))
+    data, mask = g["data"], g["mask"]
+    n_bands = data.shape[0]
+    st, mine, _ = oracle.encode(np.ascontiguousarray(data[:, :, :, 0]), 0, n_bands=n_bands, mask=mask if mask.size else None, version=3)
+    assert st == 0 and len(mine) == len(blob)
+    a, b = np.frombuffer(mine, np.uint8).copy(), np.frombuffer(blob, np.uint8).copy()
+    pos = 0
+    for _ in range(n_bands):
+        size = int(np.frombuffer(blob[pos + 30:pos + 34], np.int32)[0])          # v3 header: blobSize at byte 30
+        for buf in (a, b):
+            buf[pos + 10:pos + 14] = 0
+            buf[pos + size - 4:pos + size] = 0
+        pos += size
+    assert pos == len(blob) and np.array_equal(a, b)
+
+
 def test_against_reference_library(oracle):
     ref = ref_lib()
     if ref is None:
