@@ -53,10 +53,12 @@ lerc_status encodeImpl(const void* pData, int version, unsigned dataType, int nD
   if (!pData || dataType >= (unsigned)DT_Undefined || nDepth <= 0 || nCols <= 0 || nRows <= 0 || nBands <= 0 || maxZErr < 0) return WrongParam;
   if (!sizeOnly && (!pOut || !outSize)) return WrongParam;
   if (!(nMasks == 0 || nMasks == 1 || nMasks == nBands) || (nMasks > 0 && !pValidBytes)) return WrongParam;
-  if (!(version == -1 || version == 6)) return WrongParam;             // older writers: documented deviation
+  if (version > 6 || (version >= 0 && version < 2)) return WrongParam;   // Lerc2::SetEncoderToOldVersion (Lerc2.cpp:52-63); any negative value = current
+  if (version < 0) version = 6;
   if (anyNoData(pUsesNoData, nBands)) return WrongParam;               // noData remapping: SURVEY.md 8f-4, not implemented
   const size_t ts = (size_t)typeSize((int)dataType);
   if (!dimsOk(nDepth, nCols, nRows, ts)) return DimensionsTooLarge;
+  if (version < 4 && nDepth > 1) return Failed;                          // Lerc2::Set refuses nDepth > 1 before codec version 4 (Lerc2.cpp:85-86)
 
   ContextGuard g;
   Context* ctx = g.ctx;
@@ -96,7 +98,7 @@ lerc_status encodeImpl(const void* pData, int version, unsigned dataType, int nD
     a.dValidBytes = nullptr;
     if (nMasks > 0) a.dValidBytes = (const uint8_t*)toDevice(ctx, pValidBytes + (nMasks > 1 ? nPix * (size_t)b : 0), nPix, kMask, dMaskScratch);
     if (!a.dData || (nMasks > 0 && !a.dValidBytes)) return Failed;
-    a.maxZErr = maxZErr; a.iBand = b; a.nBands = nBands; a.nMasks = nMasks; a.anyMaskModified = anyModified;
+    a.maxZErr = maxZErr; a.iBand = b; a.nBands = nBands; a.nMasks = nMasks; a.anyMaskModified = anyModified; a.version = version;
     a.dOut = sizeOnly ? nullptr : dOut; a.outOffset = offset; a.outCapacity = sizeOnly ? 0 : (dOutCap > offset ? dOutCap - offset : 0);
     uint32_t bandBytes = 0;
     const size_t arenaMark = ctx->arena.used, pinnedMark = ctx->pinnedUsed;
@@ -409,6 +411,6 @@ lerc_status lerc_b200_decodeTiles(const unsigned char* pBlobs, unsigned long lon
   return cudaOk(cudaStreamSynchronize(ctx->stream), "sync") ? Ok : Failed;
 }
 
-const char* lerc_b200_version(void) { return "lerc_b200 0.1 (Lerc2 v6 writer, v3-v6 reader; CUDA sm_100a)"; }
+const char* lerc_b200_version(void) { return "lerc_b200 0.2 (Lerc2 v2-v6 writer and reader, tile batch; CUDA sm_100a)"; }
 
 }  // extern "C"

@@ -112,6 +112,18 @@ template <class T> __device__ __forceinline__ T castClamped(double z, double zMa
   return (T)v;
 }
 
+// codec version 2 (MSB-first words, BitStuffer2.cpp:352-425): element e of n
+__device__ inline uint32_t extractBitsV2(const uint8_t* __restrict__ payload, uint32_t payloadLen, uint32_t e, int nb, uint32_t n) {
+  uint32_t x = 0;
+  for (int t = 0; t < nb; t++) {
+    const uint32_t sb = e * (uint32_t)nb + (uint32_t)t;
+    const int k = v2ByteOfStreamBit(sb, n, nb);
+    const uint32_t bit = (k >= 0 && (uint32_t)k < payloadLen) ? ((payload[k] >> (7 - (sb & 7))) & 1u) : 0u;
+    x = (x << 1) | bit;
+  }
+  return x;
+}
+
 __device__ inline uint32_t extractBits(const uint8_t* __restrict__ payload, uint32_t payloadLen, uint32_t e, int nb) {
   const unsigned long long bit = (unsigned long long)e * nb;
   const uint32_t k0 = (uint32_t)(bit >> 3); const int sh = (int)(bit & 7);
@@ -158,7 +170,7 @@ __global__ void k_tiles_decode(DecTileArgs a) {
             nLut = (int)p[unitLen] - 1; unitLen += 1;
             const uint8_t* lp = p + unitLen; const uint32_t lutLen = packedBytes(nLut, nb);
             if (lane == 0) sLut[warp][0] = 0;
-            for (int i = lane; i < nLut; i += 32) sLut[warp][1 + i] = extractBits(lp, lutLen, i, nb);
+            for (int i = lane; i < nLut; i += 32) sLut[warp][1 + i] = a.version >= 3 ? extractBits(lp, lutLen, i, nb) : extractBitsV2(lp, lutLen, i, nb, (uint32_t)nLut);
             __syncwarp();
             unitLen += lutLen;
             nbIdx = bitLength((uint32_t)nLut);
@@ -195,8 +207,8 @@ __global__ void k_tiles_decode(DecTileArgs a) {
         } else {
           if ((unsigned)e >= n) { bad = true; continue; }
           uint32_t q = 0;
-          if (lut) { const uint32_t idx = extractBits(payload, payloadLen, e, nbIdx); if (idx > (uint32_t)nLut) { bad = true; continue; } q = sLut[warp][idx]; }
-          else if (nb) q = extractBits(payload, payloadLen, e, nb);
+          if (lut) { const uint32_t idx = a.version >= 3 ? extractBits(payload, payloadLen, e, nbIdx) : extractBitsV2(payload, payloadLen, e, nbIdx, n); if (idx > (uint32_t)nLut) { bad = true; continue; } q = sLut[warp][idx]; }
+          else if (nb) q = a.version >= 3 ? extractBits(payload, payloadLen, e, nb) : extractBitsV2(payload, payloadLen, e, nb, n);
           double z = __dadd_rn(offset, __dmul_rn((double)q, invScale));
           if (diff) z = __dadd_rn(z, (double)data[m - 1]);
           data[m] = castClamped<T>(z, zMax);
@@ -612,7 +624,7 @@ ErrCode decodeBandT(Context* ctx, DecodeBandArgs& a, BandMaskState& ms) {
         std::vector<uint8_t> tb(std::min<size_t>(2048, (size_t)hd.blobSize - pos));
         if (!src.fetch(pos, tb.size(), tb.data())) return Failed;
         HuffmanTable t;
-        const size_t used = t.read(tb.data(), tb.size());
+        const size_t used = t.read(tb.data(), tb.size(), hd.version);
         if (!used) return Failed;
         pos += used;
         HuffDecArgs ha;

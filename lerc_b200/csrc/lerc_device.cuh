@@ -82,6 +82,16 @@ __device__ __forceinline__ int bitLength(uint32_t v) { return 32 - __clz(v); }  
 __device__ __forceinline__ int countFieldBytes(uint32_t n) { return n < 256 ? 1 : (n < 65536 ? 2 : 4); }
 __device__ __forceinline__ uint32_t packedBytes(uint32_t n, int nb) { return (uint32_t)(((unsigned long long)n * nb + 7) >> 3); }
 
+// ---- Lerc2 v2 bit stuffing (BitStuffer2.cpp:292-425): values MSB-first inside little-endian uint32 words, the unused low bytes
+// of the last word dropped by shifting that word down.  Stored byte holding stream bit s (it is bit 7 - s % 8 of that byte), or -1.
+__device__ __forceinline__ int v2ByteOfStreamBit(uint32_t s, uint32_t n, int nb) {
+  const uint32_t total = n * (uint32_t)nb, nWords = (total + 31) >> 5, w = s >> 5;
+  const int bitsTail = (int)(total & 31), bytesTail = (bitsTail + 7) >> 3, drop = bytesTail > 0 ? 4 - bytesTail : 0;
+  const int jj = 3 - (int)((s & 31) >> 3);
+  const int k = (int)(4 * w) + jj - (w == nWords - 1 ? drop : 0);
+  return k >= (int)(4 * w) ? k : -1;
+}
+
 // ---- fp64 arithmetic exactly as the reference's x86-64 build evaluates it: no contraction --------
 // (the translation units are additionally compiled with -fmad=false)
 __device__ __forceinline__ double blockMaxVal(double zMin, double zMax, double maxZErr) {     // Lerc2.h:337-341

@@ -134,6 +134,14 @@ __global__ void k_stats_finish(const T* __restrict__ data, int nDepth, StatsBuff
 // value on a coarser grid is also on every finer one (each factor divides the next), where its rounding
 // distance is 0.  So the per-candidate maximum over ALL valid values equals the reference's bookkeeping, and
 // row-wise pruning only removes candidates whose final maximum would fail anyway.
+// codec versions 2..5: NaN -> -FLT_MAX / -DBL_MAX (Lerc::ReplaceNaNValues, Lerc.cpp:906-930); pixels whose depths are all NaN
+// were already made invalid by k_mask_build, their values no longer matter
+template <class T>
+__global__ void k_replace_nan(T* __restrict__ data, long long nElem) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nElem; e += (long long)gridDim.x * blockDim.x)
+    if (isNaNVal(data[e])) data[e] = (T)(sizeof(T) == 4 ? -FLT_MAX : -DBL_MAX);
+}
+
 struct RaiseArgs { double fac[9]; int n; };
 
 template <class T>
@@ -207,8 +215,24 @@ template <class T> __device__ inline TileSmem<T> carveTileSmem(uint8_t* base, in
 }
 
 // n values of `vals`, nb bits each, LSB first, written byte by byte (BitStuffer2.cpp:432-472)
-__device__ inline void emitPacked(uint8_t* __restrict__ p, const uint32_t* __restrict__ vals, uint32_t n, int nb, int lane) {
+__device__ inline void emitPacked(uint8_t* __restrict__ p, const uint32_t* __restrict__ vals, uint32_t n, int nb, int lane, int version = 6) {
   const uint32_t nBytes = packedBytes(n, nb);
+  if (version < 3) {                                   // codec version 2: MSB-first words (compatibility writer, bit by bit)
+    const uint32_t total = n * (uint32_t)nb, nWords = (total + 31) >> 5;
+    const int bitsTail = (int)(total & 31), bytesTail = (bitsTail + 7) >> 3, drop = bytesTail > 0 ? 4 - bytesTail : 0;
+    for (uint32_t k = lane; k < nBytes; k += 32) {
+      const uint32_t w = k >> 2;
+      const int jj = (int)(k & 3) + (w == nWords - 1 ? drop : 0);          // byte of the little-endian word this stored byte came from
+      const uint32_t s0 = 32 * w + (uint32_t)(3 - jj) * 8;                   // stream bit held by bit 7 of the byte
+      uint32_t acc = 0;
+      for (int u = 0; u < 8; u++) {
+        const uint32_t sb = s0 + (uint32_t)u, i = sb / (uint32_t)nb, t = sb - i * (uint32_t)nb;
+        if (i < n && ((vals[i] >> (nb - 1 - (int)t)) & 1)) acc |= 0x80u >> u;
+      }
+      p[k] = (uint8_t)acc;
+    }
+    return;
+  }
   for (uint32_t k = lane; k < nBytes; k += 32) {
     const uint32_t bit0 = k * 8;
     uint32_t i = bit0 / (uint32_t)nb, acc = 0;
@@ -317,11 +341,11 @@ __device__ inline int emitBlock(const TileArgs& a, uint8_t* p, const V* vals, in
     for (int k = 0; k < cb; k++) p[pos + 1 + k] = (uint8_t)((uint32_t)n >> (8 * k));
   }
   pos += 1 + cb;
-  if (c.mode == BEM_SIMPLE) { emitPacked(p + pos, q, n, c.nb, lane); return pos + (int)packedBytes(n, c.nb); }
+  if (c.mode == BEM_SIMPLE) { emitPacked(p + pos, q, n, c.nb, lane, a.version); return pos + (int)packedBytes(n, c.nb); }
   if (lane == 0) p[pos] = (uint8_t)(c.nLut + 1);
   pos += 1;
-  emitPacked(p + pos, lut + 1, c.nLut, c.nb, lane); pos += (int)packedBytes(c.nLut, c.nb);   // LUT without the leading 0
-  emitPacked(p + pos, rank, n, c.nbIdx, lane);      pos += (int)packedBytes(n, c.nbIdx);
+  emitPacked(p + pos, lut + 1, c.nLut, c.nb, lane, a.version); pos += (int)packedBytes(c.nLut, c.nb);   // LUT without the leading 0
+  emitPacked(p + pos, rank, n, c.nbIdx, lane, a.version);      pos += (int)packedBytes(n, c.nbIdx);
   return pos;
 }
 
@@ -637,7 +661,7 @@ template <class T>
 bool encodeBandFast(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t& bandBytes, ErrCode& err) {
   constexpr bool isFlt = PixelTraits<T>::isFloat;
   using K = typename PixelTraits<T>::Key;
-  if (sizeof(T) == 1 || a.nDepth != 1 || a.dValidBytes || a.anyMaskModified || !a.dOut) return false;
+  if (sizeof(T) == 1 || a.nDepth != 1 || a.dValidBytes || a.anyMaskModified || !a.dOut || a.version != 6) return false;
   if (std::getenv("LERC_B200_NO_FAST")) return false;
   double maxZErr = a.maxZErr;
   if (isFlt) { if (!(maxZErr > 0)) return false; }                    // float lossless: FPL / raw decisions stay in the general path
@@ -799,8 +823,8 @@ ErrCode encodeBandT(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
   }
 
   HeaderInfo hd;
-  hd.version = 6; hd.nRows = a.nRows; hd.nCols = a.nCols; hd.nDepth = nDepth; hd.dt = PixelTraits<T>::code;
-  hd.nBlobsMore = a.nBands - 1 - a.iBand;
+  hd.version = a.version; hd.nRows = a.nRows; hd.nCols = a.nCols; hd.nDepth = nDepth; hd.dt = PixelTraits<T>::code;
+  hd.nBlobsMore = a.version >= 6 ? a.nBands - 1 - a.iBand : 0;
 
   // small device scratch for counters, pulled back through pinned memory
   int* dCounters = (int*)ctx->arena.alloc(64);
@@ -852,7 +876,18 @@ ErrCode encodeBandT(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
     if (statFlags & STATF_NAN) { if (!buildMask(nullptr)) return Failed; }
     else statsDone = true;
   }
-  if (maskFlags & MASKF_MIXED_NAN) return NaNFound;                          // Lerc.cpp:1481-1484
+  if (maskFlags & MASKF_MIXED_NAN) {
+    if (a.version >= 6) return NaNFound;                                     // Lerc.cpp:1481-1484
+    // codec versions 2..5 (Lerc::ReplaceNaNValues, Lerc.cpp:901-939): a NaN beside real values of the same pixel becomes -FLT_MAX / -DBL_MAX
+    if constexpr (isFlt) {
+      T* copy = (T*)ctx->arena.alloc((size_t)nPix * nDepth * sizeof(T));
+      if (!copy) return Failed;
+      cudaMemcpyAsync(copy, a.dData, (size_t)nPix * nDepth * sizeof(T), cudaMemcpyDeviceToDevice, st);
+      const long long nElem = nPix * nDepth;
+      LERC_LAUNCH(ctx, k_replace_nan<T>, (int)std::min<long long>((nElem + 255) / 256, 148 * 16), 256, 0, copy, nElem);
+      a.dData = copy;
+    }
+  }
   if (maskFlags & MASKF_MODIFIED) a.anyMaskModified = true;
   if (!haveBits) cudaMemsetAsync(bits, 0xff, nBits, st);
 
@@ -882,7 +917,7 @@ ErrCode encodeBandT(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
     launchRleEncode(ctx, bits, (long long)nBits, dRle, dSize);
     if (!d2h(ctx, &rleBytes, dSize, 1)) return Failed;
   }
-  const uint32_t headMask = (uint32_t)headerBytes(6) + 4 + rleBytes;
+  const uint32_t headMask = (uint32_t)headerBytes(a.version) + 4 + rleBytes;
 
   // ---- 2. global decisions -----------------------------------------------------------------------
   double maxZErr = a.maxZErr;
@@ -894,7 +929,8 @@ ErrCode encodeBandT(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
   bool constImage = false, allDepthsConst = false;
 
   if (numValid == 0) {
-    if (isFlt) maxZErr = 0; else maxZErr = std::max(0.5, std::floor(maxZErr));
+    if (!isFlt) maxZErr = std::max(0.5, std::floor(maxZErr));
+    else if (a.version >= 6) maxZErr = 0;                 // codec version 6 only: the noData / NaN filter resets it for an empty band (Lerc.cpp:1378-1552)
     hd.maxZError = maxZErr; hd.blobSize = (int)headMask;
   } else {
     if (!statsDone && !runStats(dBitsOrNull, statFlags)) return Failed;
@@ -904,6 +940,7 @@ ErrCode encodeBandT(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
       bool allInt = !(statFlags & STATF_NOT_INT);
       const double lim = sizeof(T) == 4 ? 8388608.0 : 9007199254740992.0;
       allInt = allInt && zMin >= -lim && zMin <= lim && zMax >= -lim && zMax <= lim;       // Lerc.cpp:1490-1500
+      if (a.version < 6) allInt = false;                                                     // the all-integer rule came with codec version 6 (Lerc.cpp:1490-1502)
       if (allInt) maxZErr = std::max(0.5, std::floor(maxZErr));
       hd.bIsInt = allInt ? 1 : 0;
       if (maxZErr > 0) {                                                                      // Lerc2.cpp:226-231
@@ -936,10 +973,12 @@ ErrCode encodeBandT(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
     hd.blobSize = (int)headMask;
     constImage = zMin == zMax;
     if (!constImage) {
-      rangesBytes = 2 * (size_t)nDepth * sizeof(T);
-      if ((size_t)headMask + rangesBytes > (size_t)INT_MAX) return Failed;
-      hd.blobSize = (int)(headMask + rangesBytes);
-      allDepthsConst = 0 == std::memcmp(ranges.data(), ranges.data() + nDepth, sizeof(double) * nDepth);
+      if (a.version >= 4) {                                                                   // Lerc2.cpp:260-281
+        rangesBytes = 2 * (size_t)nDepth * sizeof(T);
+        if ((size_t)headMask + rangesBytes > (size_t)INT_MAX) return Failed;
+        hd.blobSize = (int)(headMask + rangesBytes);
+        allDepthsConst = 0 == std::memcmp(ranges.data(), ranges.data() + nDepth, sizeof(double) * nDepth);
+      }
     }
   }
 
@@ -962,9 +1001,9 @@ ErrCode encodeBandT(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
 
   if (numValid > 0 && !constImage && !allDepthsConst) {
     ta.data = a.dData; ta.bits = dBitsOrNull; ta.nRows = a.nRows; ta.nCols = a.nCols; ta.nDepth = nDepth;
-    ta.dt = hd.dt; ta.version = 6; ta.maxZErr = maxZErr;
+    ta.dt = hd.dt; ta.version = a.version; ta.maxZErr = maxZErr;
     ta.maxQ = hd.dt <= DT_UShort ? (1u << 15) - 1 : (1u << 30) - 1;                          // Lerc2.h:685-703
-    ta.tryDiff = (!isFlt && nDepth > 1 && maxZErr == 0.5) ? 1 : 0;                           // Lerc2.cpp:1493-1495
+    ta.tryDiff = (a.version >= 5 && !isFlt && nDepth > 1 && maxZErr == 0.5) ? 1 : 0;                           // Lerc2.cpp:1493-1495
     ta.checkOverflow = ((hd.dt == DT_Int || hd.dt == DT_UInt) && (hd.zMax - hd.zMin >= 2147483647.0)) ? 1 : 0;
     ta.allValidImage = numValid == nPix ? 1 : 0;
     auto countPass = [&](int mb, uint32_t*& dLen, uint32_t*& dOff, size_t& nBlocks, long long& total) -> bool {
@@ -997,7 +1036,7 @@ ErrCode encodeBandT(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
       int histo[512];
       if (!d2h(ctx, histo, dHisto, 512)) return Failed;
       HuffmanTable t0, t1; int n0 = 0, n1 = 0;
-      if (!(t0.buildFromHistogram(histo) && t0.totalBytes(histo, n0))) n0 = 0;
+      if (a.version < 4 || !(t0.buildFromHistogram(histo) && t0.totalBytes(histo, n0))) n0 = 0;    // plain Huffman: codec version >= 4 (Lerc2.cpp:2280)
       if (!(t1.buildFromHistogram(histo + 256) && t1.totalBytes(histo + 256, n1))) n1 = 0;
       if (n0 > 0 || n1 > 0) {
         const bool plain = (n0 > 0 && n1 > 0) ? (n0 <= n1) : (n0 > n1);
@@ -1030,7 +1069,7 @@ ErrCode encodeBandT(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
 
   // ---- 3. write ---------------------------------------------------------------------------------
   uint8_t* blob = a.dOut + a.outOffset;
-  const size_t hb = (size_t)headerBytes(6);
+  const size_t hb = (size_t)headerBytes(a.version);
   // (a) header + mask length field
   uint8_t* hHead = (uint8_t*)ctx->pinnedAlloc(hb + 4);
   if (!hHead) return Failed;
@@ -1044,13 +1083,15 @@ ErrCode encodeBandT(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
   if (numValid > 0 && !constImage) {
     std::vector<uint8_t> tail(rangesBytes + 2 + 4096, 0);
     size_t tp = 0;
-    for (int m = 0; m < nDepth; m++) { T v = (T)ranges[m]; std::memcpy(tail.data() + tp, &v, sizeof(T)); tp += sizeof(T); }
-    for (int m = 0; m < nDepth; m++) { T v = (T)ranges[nDepth + m]; std::memcpy(tail.data() + tp, &v, sizeof(T)); tp += sizeof(T); }
+    if (a.version >= 4) {
+      for (int m = 0; m < nDepth; m++) { T v = (T)ranges[m]; std::memcpy(tail.data() + tp, &v, sizeof(T)); tp += sizeof(T); }
+      for (int m = 0; m < nDepth; m++) { T v = (T)ranges[nDepth + m]; std::memcpy(tail.data() + tp, &v, sizeof(T)); tp += sizeof(T); }
+    }
     size_t huffTableBytes = 0;
     if (!allDepthsConst) {
       tail[tp++] = oneSweep ? 1 : 0;
       if (!oneSweep && (hd.tryHuffmanInt() || hd.tryHuffmanFlt())) tail[tp++] = (uint8_t)imageMode;
-      if (writeHuffman) { huffTableBytes = huff.write(tail.data() + tp); if (!huffTableBytes) return Failed; tp += huffTableBytes; }
+      if (writeHuffman) { huffTableBytes = huff.write(tail.data() + tp, a.version); if (!huffTableBytes) return Failed; tp += huffTableBytes; }
     }
     uint8_t* hTail = (uint8_t*)ctx->pinnedAlloc(tp);
     if (!hTail) return Failed;
@@ -1107,10 +1148,12 @@ ErrCode encodeBandT(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
     return Failed;
   }
   // (c) checksum over [14, blobSize) stored at byte 10                        Lerc2.cpp:1012-1030
-  unsigned long long* dAcc = (unsigned long long*)ctx->arena.alloc(16);
-  if (!dAcc) return Failed;
-  cudaMemsetAsync(dAcc, 0, 16, st);
-  launchFletcher(ctx, blob + 14, (long long)hd.blobSize - 14, dAcc, blob + 10, 0, nullptr);
+  if (a.version >= 3) {
+    unsigned long long* dAcc = (unsigned long long*)ctx->arena.alloc(16);
+    if (!dAcc) return Failed;
+    cudaMemsetAsync(dAcc, 0, 16, st);
+    launchFletcher(ctx, blob + 14, (long long)hd.blobSize - 14, dAcc, blob + 10, 0, nullptr);
+  }
   return cudaOk(cudaGetLastError(), "encodeBand") ? Ok : Failed;
 }
 

@@ -207,7 +207,17 @@ bool assignDepths(const std::vector<TreeNode>& pool, int root, int depth, uint16
 }
 
 // fixed-width LSB-first packing of the code-length array (BitStuffer2::EncodeSimple, BitStuffer2.cpp:35-75)
-size_t stuffSimple(uint8_t* dst, const uint32_t* v, uint32_t n) {
+// Lerc2 v2 bit stuffing (BitStuffer2.cpp:292-425): values MSB-first inside little-endian uint32 words, the unused low bytes of
+// the last word dropped by shifting that word down.  Stored byte that holds stream bit s (bit 7 - s % 8 of that byte), or -1.
+static long v2ByteOfStreamBit(uint64_t s, uint32_t n, int nb) {
+  const uint64_t total = (uint64_t)n * nb, nWords = (total + 31) / 32, w = s >> 5;
+  const int bitsTail = (int)(total & 31), bytesTail = (bitsTail + 7) >> 3, drop = bytesTail > 0 ? 4 - bytesTail : 0;
+  const int jj = 3 - (int)((s & 31) >> 3);                       // byte of the little-endian word
+  const long k = (long)(4 * w) + jj - (w == nWords - 1 ? drop : 0);
+  return k >= (long)(4 * w) ? k : -1;
+}
+
+size_t stuffSimple(uint8_t* dst, const uint32_t* v, uint32_t n, int version) {
   uint32_t mx = 0;
   for (uint32_t i = 0; i < n; i++) mx = std::max(mx, v[i]);
   const int nb = bitLength(mx), cb = n < 256 ? 1 : (n < 65536 ? 2 : 4);
@@ -218,17 +228,23 @@ size_t stuffSimple(uint8_t* dst, const uint32_t* v, uint32_t n) {
   if (nb > 0) {
     const size_t len = ((size_t)n * nb + 7) >> 3;
     std::memset(p, 0, len);
-    uint64_t bit = 0;
-    for (uint32_t i = 0; i < n; i++, bit += nb) {
-      uint64_t x = (uint64_t)v[i] << (bit & 7);
-      for (size_t k = bit >> 3; x; k++, x >>= 8) p[k] |= (uint8_t)x;
+    if (version >= 3) {
+      uint64_t bit = 0;
+      for (uint32_t i = 0; i < n; i++, bit += nb) {
+        uint64_t x = (uint64_t)v[i] << (bit & 7);
+        for (size_t k = bit >> 3; x; k++, x >>= 8) p[k] |= (uint8_t)x;
+      }
+    } else {
+      for (uint32_t i = 0; i < n; i++)
+        for (int t = 0; t < nb; t++)
+          if ((v[i] >> (nb - 1 - t)) & 1) { const long k = v2ByteOfStreamBit((uint64_t)i * nb + t, n, nb); if (k >= 0 && (size_t)k < len) p[k] |= (uint8_t)(0x80u >> (((uint64_t)i * nb + t) & 7)); }
     }
     p += len;
   }
   return (size_t)(p - dst);
 }
 
-size_t unstuffSimple(const uint8_t* src, size_t avail, uint32_t* v, uint32_t expect) {   // BitStuffer2.cpp:159-196
+size_t unstuffSimple(const uint8_t* src, size_t avail, uint32_t* v, uint32_t expect, int version) {   // BitStuffer2.cpp:159-196
   if (avail < 1) return 0;
   const uint8_t b = src[0];
   const int code = b >> 6, cb = code == 0 ? 4 : 3 - code, nb = b & 31;
@@ -242,11 +258,25 @@ size_t unstuffSimple(const uint8_t* src, size_t avail, uint32_t* v, uint32_t exp
   const uint8_t* p = src + 1 + cb;
   uint64_t bit = 0;
   const uint32_t mask = nb ? ((nb == 32) ? 0xffffffffu : ((1u << nb) - 1)) : 0;
-  for (uint32_t i = 0; i < n; i++, bit += nb) {
-    uint64_t x = 0;
-    const size_t k0 = bit >> 3;
-    for (int k = 0; k < 5 && k0 + k < len; k++) x |= (uint64_t)p[k0 + k] << (8 * k);
-    v[i] = (uint32_t)(x >> (bit & 7)) & mask;
+  if (version >= 3) {
+    for (uint32_t i = 0; i < n; i++, bit += nb) {
+      uint64_t x = 0;
+      const size_t k0 = bit >> 3;
+      for (int k = 0; k < 5 && k0 + k < len; k++) x |= (uint64_t)p[k0 + k] << (8 * k);
+      v[i] = (uint32_t)(x >> (bit & 7)) & mask;
+    }
+  } else {
+    if (nb > 0 && n == 0) return 0;                    // BitUnStuff_Before_Lerc2v3 rejects an empty array (BitStuffer2.cpp:355)
+    for (uint32_t i = 0; i < n; i++) {
+      uint32_t x = 0;
+      for (int t = 0; t < nb; t++) {
+        const uint64_t sb = (uint64_t)i * nb + t;
+        const long k = v2ByteOfStreamBit(sb, n, nb);
+        const uint32_t b1 = (k >= 0 && (size_t)k < len) ? ((p[k] >> (7 - (sb & 7))) & 1u) : 0u;
+        x = (x << 1) | b1;
+      }
+      v[i] = x;
+    }
   }
   return 1 + (size_t)cb + len;
 }
@@ -346,28 +376,28 @@ bool HuffmanTable::totalBytes(const int* histo, int& nBytes) const {
   return true;
 }
 
-size_t HuffmanTable::write(uint8_t* dst) const {
+size_t HuffmanTable::write(uint8_t* dst, int version) const {
   int i0, i1, maxLen;
   if (!range(i0, i1, maxLen)) return 0;
   Writer w{dst};
   w.put<int32_t>(4); w.put<int32_t>(256); w.put<int32_t>(i0); w.put<int32_t>(i1);
   uint32_t lens[512];
   for (int i = i0; i < i1; i++) lens[i - i0] = len[wrapIdx(i, 256)];
-  w.p += stuffSimple(w.p, lens, (uint32_t)(i1 - i0));
+  w.p += stuffSimple(w.p, lens, (uint32_t)(i1 - i0), version);
   uint64_t bitPos = 0;
   for (int i = i0; i < i1; i++) { const int k = wrapIdx(i, 256); if (len[k]) putBitsMsb(w.p, bitPos, code[k], len[k]); }
   w.p += 4 * ((bitPos + 31) >> 5);
   return (size_t)(w.p - dst);
 }
 
-size_t HuffmanTable::read(const uint8_t* src, size_t avail) {
+size_t HuffmanTable::read(const uint8_t* src, size_t avail, int version) {
   if (avail < 16) return 0;
   Reader r{src};
   const int ver = r.get<int32_t>(), size = r.get<int32_t>(), i0 = r.get<int32_t>(), i1 = r.get<int32_t>();
   if (ver < 2 || i0 >= i1 || i0 < 0 || size < 0 || size > 256 || i1 - i0 > 512) return 0;
   if (wrapIdx(i0, size) >= size || wrapIdx(i1 - 1, size) >= size) return 0;
   uint32_t lens[512];
-  const size_t used = unstuffSimple(r.p, avail - 16, lens, (uint32_t)(i1 - i0));
+  const size_t used = unstuffSimple(r.p, avail - 16, lens, (uint32_t)(i1 - i0), version);
   if (!used) return 0;
   r.p += used;
   std::fill(len, len + 256, (uint16_t)0);

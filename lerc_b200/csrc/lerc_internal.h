@@ -70,8 +70,8 @@ struct HuffmanTable {
   bool range(int& i0, int& i1, int& maxLen) const;        // Huffman.cpp:383-438
   bool tableBytes(int& nBytes) const;                     // Huffman.cpp:357-379
   bool totalBytes(const int* histo, int& nBytes) const;   // Huffman.cpp:85-111
-  size_t write(uint8_t* dst) const;                       // Huffman.cpp:126-166; dst zero-filled; returns bytes
-  size_t read(const uint8_t* src, size_t avail);          // Huffman.cpp:170-234; returns bytes consumed or 0
+  size_t write(uint8_t* dst, int version = 6) const;      // Huffman.cpp:126-166; dst zero-filled; returns bytes (version 2: MSB-first code lengths)
+  size_t read(const uint8_t* src, size_t avail, int version = 6);   // Huffman.cpp:170-234; returns bytes consumed or 0
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -142,6 +142,7 @@ struct EncodeBandArgs {
   const uint8_t* dValidBytes;     // this band's byte mask on the device, or nullptr
   double maxZErr;
   int iBand, nBands, nMasks;
+  int version = 6;                // codec version to write: 6, or 2..5 (Lerc::EncodeInternal_v5, Lerc.cpp:526-624)
   bool anyMaskModified;           // in/out across bands (Lerc.cpp:714-720)
   uint8_t* dOut;                  // device output buffer (whole multi-band blob), may be nullptr for size-only
   size_t outCapacity;             // bytes available in dOut from outOffset

@@ -5,7 +5,7 @@ Drives tools/cusim/_build/libLerc_sim.so (the product sources compiled against t
 through the same C-ABI calls as tests/test_gpu_parity.py and compares with the oracle.  A pass here means the kernel
 LOGIC is right for these inputs; the GPU parity tests (-m gpu, on the B200) remain the only parity evidence.
 
-  python tools/cusim/check.py [-k substring] [--size H W]
+  python tools/cusim/check.py [-k substring] [--size H W] [--versions]
 """
 import argparse
 import os
@@ -24,8 +24,9 @@ def sim_lib():
     return LercLib(os.path.join(ROOT, "tools", "cusim", "_build", "libLerc_sim.so"))
 
 
-def check_case(sim, orc, name, arr, mz, kw):
+def check_case(sim, orc, name, arr, mz, kw, version=None):
     t0 = time.time()
+    kw = dict(kw, version=version)
     st_o, blob_o, _ = orc.encode(arr, mz, **kw)
     st_s, blob_s, buf = sim.encode(arr, mz, **kw)
     msg = []
@@ -58,12 +59,14 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("-k", default="")
     ap.add_argument("--size", nargs=2, type=int, default=[70, 90])
+    ap.add_argument("--versions", action="store_true", help="also lerc_encodeForVersion with codec versions 2..5")
     a = ap.parse_args()
     sim, orc = sim_lib(), oracle_lib()
     bad = 0
-    for name, arr, mz, kw in all_cases(a.size[0], a.size[1]):
-        if a.k in name:
-            bad += not check_case(sim, orc, name, arr, mz, kw)
+    for version in ([None, 2, 3, 4, 5] if a.versions else [None]):
+        for name, arr, mz, kw in all_cases(a.size[0], a.size[1]):
+            if a.k in name:
+                bad += not check_case(sim, orc, name + ("" if version is None else f" v{version}"), arr, mz, kw, version)
     print("failures:", bad)
     return 1 if bad else 0
 
