@@ -49,13 +49,14 @@ const void* toDevice(Context* ctx, const void* p, size_t bytes, PtrKind kind, vo
 
 lerc_status encodeImpl(const void* pData, int version, unsigned dataType, int nDepth, int nCols, int nRows, int nBands, int nMasks,
                        const unsigned char* pValidBytes, double maxZErr, unsigned char* pOut, unsigned outSize,
-                       unsigned* nWritten, unsigned* nNeeded, bool sizeOnly, const unsigned char* pUsesNoData) {
+                       unsigned* nWritten, unsigned* nNeeded, bool sizeOnly, const unsigned char* pUsesNoData, const double* noDataValues = nullptr) {
   if (!pData || dataType >= (unsigned)DT_Undefined || nDepth <= 0 || nCols <= 0 || nRows <= 0 || nBands <= 0 || maxZErr < 0) return WrongParam;
   if (!sizeOnly && (!pOut || !outSize)) return WrongParam;
   if (!(nMasks == 0 || nMasks == 1 || nMasks == nBands) || (nMasks > 0 && !pValidBytes)) return WrongParam;
   if (version > 6 || (version >= 0 && version < 2)) return WrongParam;   // Lerc2::SetEncoderToOldVersion (Lerc2.cpp:52-63); any negative value = current
   if (version < 0) version = 6;
-  if (anyNoData(pUsesNoData, nBands)) return WrongParam;               // noData remapping: SURVEY.md 8f-4, not implemented
+  const bool haveNoData = anyNoData(pUsesNoData, nBands);
+  if (haveNoData && (!noDataValues || version <= 5)) return WrongParam;   // Lerc.cpp:649-652, :378-383 (no noData before codec version 6)
   const size_t ts = (size_t)typeSize((int)dataType);
   if (!dimsOk(nDepth, nCols, nRows, ts)) return DimensionsTooLarge;
   if (version < 4 && nDepth > 1) return Failed;                          // Lerc2::Set refuses nDepth > 1 before codec version 4 (Lerc2.cpp:85-86)
@@ -93,15 +94,30 @@ lerc_status encodeImpl(const void* pData, int version, unsigned dataType, int nD
   bool anyModified = false;
   for (int b = 0; b < nBands; b++) {
     EncodeBandArgs a;
+    const size_t arenaMark = ctx->arena.used, pinnedMark = ctx->pinnedUsed;
     a.dt = (int)dataType; a.nDepth = nDepth; a.nCols = nCols; a.nRows = nRows;
     a.dData = toDevice(ctx, (const uint8_t*)pData + nElemBytes * (size_t)b, nElemBytes, kData, dBandScratch);
     a.dValidBytes = nullptr;
     if (nMasks > 0) a.dValidBytes = (const uint8_t*)toDevice(ctx, pValidBytes + (nMasks > 1 ? nPix * (size_t)b : 0), nPix, kMask, dMaskScratch);
     if (!a.dData || (nMasks > 0 && !a.dValidBytes)) return Failed;
     a.maxZErr = maxZErr; a.iBand = b; a.nBands = nBands; a.nMasks = nMasks; a.anyMaskModified = anyModified; a.version = version;
+    if (haveNoData && pUsesNoData[b]) {
+      // a caller-supplied noData value for this band (Lerc.cpp:687-711): the filter works on private copies of band and mask
+      void* dCopy = ctx->arena.alloc(nElemBytes);
+      uint8_t* dMaskCopy = (uint8_t*)ctx->arena.alloc(nPix);
+      if (!dCopy || !dMaskCopy) return Failed;
+      if (!cudaOk(cudaMemcpyAsync(dCopy, a.dData, nElemBytes, cudaMemcpyDeviceToDevice, ctx->stream), "band copy")) return Failed;
+      if (a.dValidBytes) { if (!cudaOk(cudaMemcpyAsync(dMaskCopy, a.dValidBytes, nPix, cudaMemcpyDeviceToDevice, ctx->stream), "mask copy")) return Failed; }
+      else cudaMemsetAsync(dMaskCopy, 1, nPix, ctx->stream);
+      NoDataVerdict nd;
+      const ErrCode pe = prefilterNoData(ctx, (int)dataType, dCopy, dMaskCopy, (long long)nPix, nDepth, maxZErr, noDataValues[b], nd);
+      if (pe != Ok) return pe;
+      a.dData = dCopy; a.dValidBytes = dMaskCopy; a.maxZErr = nd.maxZErr;
+      a.prefiltered = true; a.isAllInt = nd.isAllInt; a.passNoData = nd.needNoData; a.noDataVal = nd.noDataVal; a.noDataOrig = noDataValues[b];
+      if (nd.maskModified) a.anyMaskModified = true;
+    }
     a.dOut = sizeOnly ? nullptr : dOut; a.outOffset = offset; a.outCapacity = sizeOnly ? 0 : (dOutCap > offset ? dOutCap - offset : 0);
     uint32_t bandBytes = 0;
-    const size_t arenaMark = ctx->arena.used, pinnedMark = ctx->pinnedUsed;
     const ErrCode e = encodeBand(ctx, a, ms, bandBytes);
     if (e == BufferTooSmall && !sizeOnly && kOut != PTR_DEVICE && dOutCap < (size_t)outSize) return Failed;   // our bound was wrong: never expected
     if (e != Ok) return e;
@@ -148,9 +164,11 @@ lerc_status decodeImpl(const unsigned char* pBlob, unsigned blobSize, int nMasks
   const size_t ts = (size_t)typeSize((int)dataType);
   if (!dimsOk(nDepth, nCols, nRows, ts)) return DimensionsTooLarge;
   if (nMasks < li.nMasks || nBands > li.nBands) return WrongParam;     // Lerc.cpp:423-428
-  if (li.nUsesNoDataValue && nDepth > 1) {                             // Lerc.cpp:431-445
+  const bool wantNoData = li.nUsesNoDataValue && nDepth > 1;
+  if (wantNoData) {                                                    // Lerc.cpp:431-445
     if (!pUsesNoData || !noDataValues) return HasNoData;
-    return Failed;                                                     // noData remapping not implemented
+    std::memset(pUsesNoData, 0, (size_t)nBands);
+    std::memset(noDataValues, 0, (size_t)nBands * sizeof(double));
   }
 
   ContextGuard g;
@@ -195,6 +213,12 @@ lerc_status decodeImpl(const unsigned char* pBlob, unsigned blobSize, int nMasks
     const size_t arenaMark = ctx->arena.used, pinnedMark = ctx->pinnedUsed;
     e = decodeBand(ctx, a, ms);
     if (e != Ok) return e;
+    if (wantNoData) {                                                  // Lerc.cpp:472-479
+      pUsesNoData[b] = hd.bPassNoDataValues ? 1 : 0;
+      noDataValues[b] = hd.noDataValOrig;
+      if (hd.bPassNoDataValues && hd.noDataVal != hd.noDataValOrig)
+        launchRemapNoData(ctx, (int)dataType, a.dData, ms.dBits, (long long)nPix, nDepth, hd.noDataVal, hd.noDataValOrig);
+    }
 
     if (!direct) {
       if (toDouble && dataType != (unsigned)DT_Double) {
@@ -249,21 +273,21 @@ lerc_status lerc_encode(const void* pData, unsigned int dataType, int nDepth, in
 
 lerc_status lerc_computeCompressedSize_4D(const void* pData, unsigned int dataType, int nDepth, int nCols, int nRows, int nBands, int nMasks,
                                           const unsigned char* pValidBytes, double maxZErr, unsigned int* numBytes,
-                                          const unsigned char* pUsesNoData, const double* /*noDataValues*/) {
+                                          const unsigned char* pUsesNoData, const double* noDataValues) {
   if (!numBytes) return WrongParam;
   *numBytes = 0;
   unsigned w = 0;
-  return encodeImpl(pData, -1, dataType, nDepth, nCols, nRows, nBands, nMasks, pValidBytes, maxZErr, nullptr, 0, &w, numBytes, true, pUsesNoData);
+  return encodeImpl(pData, -1, dataType, nDepth, nCols, nRows, nBands, nMasks, pValidBytes, maxZErr, nullptr, 0, &w, numBytes, true, pUsesNoData, noDataValues);
 }
 
 lerc_status lerc_encode_4D(const void* pData, unsigned int dataType, int nDepth, int nCols, int nRows, int nBands, int nMasks,
                            const unsigned char* pValidBytes, double maxZErr, unsigned char* pOutBuffer, unsigned int outBufferSize,
-                           unsigned int* nBytesWritten, const unsigned char* pUsesNoData, const double* /*noDataValues*/) {
+                           unsigned int* nBytesWritten, const unsigned char* pUsesNoData, const double* noDataValues) {
   if (!nBytesWritten) return WrongParam;
   *nBytesWritten = 0;
   unsigned need = 0;
   return encodeImpl(pData, -1, dataType, nDepth, nCols, nRows, nBands, nMasks, pValidBytes, maxZErr, pOutBuffer, outBufferSize,
-                    nBytesWritten, &need, false, pUsesNoData);
+                    nBytesWritten, &need, false, pUsesNoData, noDataValues);
 }
 
 lerc_status lerc_getBlobInfo(const unsigned char* pLercBlob, unsigned int blobSize, unsigned int* infoArray, double* dataRangeArray,

@@ -12,6 +12,8 @@
 #include "lerc_kernels.h"
 #include <cub/device/device_scan.cuh>
 #include <cmath>
+#include <vector>
+#include <algorithm>
 #include <cstring>
 #include <cstdio>
 
@@ -825,6 +827,7 @@ ErrCode encodeBandT(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
   HeaderInfo hd;
   hd.version = a.version; hd.nRows = a.nRows; hd.nCols = a.nCols; hd.nDepth = nDepth; hd.dt = PixelTraits<T>::code;
   hd.nBlobsMore = a.version >= 6 ? a.nBands - 1 - a.iBand : 0;
+  if (a.passNoData) { hd.bPassNoDataValues = 1; hd.noDataVal = a.noDataVal; hd.noDataValOrig = a.noDataOrig; }   // Lerc2.cpp:116-126
 
   // small device scratch for counters, pulled back through pinned memory
   int* dCounters = (int*)ctx->arena.alloc(64);
@@ -940,6 +943,7 @@ ErrCode encodeBandT(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
       bool allInt = !(statFlags & STATF_NOT_INT);
       const double lim = sizeof(T) == 4 ? 8388608.0 : 9007199254740992.0;
       allInt = allInt && zMin >= -lim && zMin <= lim && zMax >= -lim && zMax <= lim;       // Lerc.cpp:1490-1500
+      if (a.prefiltered) allInt = a.isAllInt;                                                // decided by prefilterNoData without the noData values
       if (a.version < 6) allInt = false;                                                     // the all-integer rule came with codec version 6 (Lerc.cpp:1490-1502)
       if (allInt) maxZErr = std::max(0.5, std::floor(maxZErr));
       hd.bIsInt = allInt ? 1 : 0;
@@ -1169,6 +1173,171 @@ ErrCode encodeBand(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t&
     case DT_UInt:   return encodeBandT<uint32_t>(ctx, a, ms, bandBytes);
     case DT_Float:  return encodeBandT<float>(ctx, a, ms, bandBytes);
     case DT_Double: return encodeBandT<double>(ctx, a, ms, bandBytes);
+    default: return WrongParam;
+  }
+}
+
+}  // namespace lerc
+
+// =================================================================================================
+// bands with a caller-supplied noData value (the _4D calls): Lerc::FilterNoDataAndNaN (Lerc.cpp:1378-1552, float types) and
+// Lerc::FilterNoData (Lerc.cpp:1241-1374, integer types), on private device copies of the band and its byte mask
+namespace lerc {
+namespace {
+
+enum { NDF_MODIFIED = 1, NDF_LEFT = 2, NDF_NOT_INT = 4, NDF_ANY_VALID = 8 };
+struct NoDataScan { unsigned long long minKey, negMaxKey; unsigned int flags, pad; };   // minKey starts at ~0, negMaxKey (= ~maxKey) at ~0
+
+template <class T>
+__global__ void k_nodata_scan(T* __restrict__ data, uint8_t* __restrict__ maskBytes, long long nPix, int nDepth, double noDataD, NoDataScan* __restrict__ out) {
+  constexpr bool isFlt = PixelTraits<T>::isFloat;
+  using K = typename PixelTraits<T>::Key;
+  const T origNoData = (T)noDataD;
+  K kmin = keyMaxValue<K>(), kmax = 0;
+  unsigned int flags = 0;
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < nPix; k += (long long)gridDim.x * blockDim.x) {
+    if (!maskBytes[k]) continue;
+    T* px = data + k * nDepth;
+    int bad = 0;
+    for (int m = 0; m < nDepth; m++) {
+      const T z = px[m];
+      if (isFlt && isNaNVal(z)) { bad++; px[m] = nDepth > 1 ? origNoData : (T)0; }        // Lerc.cpp:1436-1444
+      else if (z == origNoData) bad++;
+      else {
+        const K key = toKey(z);
+        kmin = key < kmin ? key : kmin; kmax = key > kmax ? key : kmax;
+        flags |= NDF_ANY_VALID;
+        if (isFlt && !(z == (T)floor((double)z + 0.5))) flags |= NDF_NOT_INT;             // Lerc.h:248
+      }
+    }
+    if (bad == nDepth) { maskBytes[k] = 0; flags |= NDF_MODIFIED; }
+    else if (bad > 0) flags |= NDF_LEFT;
+  }
+  kmin = warpMin(kmin); kmax = warpMax(kmax);
+  flags = __reduce_or_sync(FULL, flags);
+  if ((threadIdx.x & 31) == 0 && flags) {
+    if (flags & NDF_ANY_VALID) { atomicMin(&out->minKey, (unsigned long long)kmin); atomicMin(&out->negMaxKey, ~(unsigned long long)kmax); }
+    atomicOr(&out->flags, flags);
+  }
+}
+
+template <class T>
+__global__ void k_nodata_remap(T* __restrict__ data, const uint8_t* __restrict__ maskBytes, long long nPix, int nDepth, double fromD, double toD) {
+  const T from = (T)fromD, to = (T)toD;
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < nPix; k += (long long)gridDim.x * blockDim.x) {
+    if (!maskBytes[k]) continue;
+    T* px = data + k * nDepth;
+    for (int m = 0; m < nDepth; m++) if (px[m] == from) px[m] = to;
+  }
+}
+
+template <class T> bool isIntegralHost(T z) { return z == (T)std::floor((double)z + 0.5); }
+
+// Lerc::FindNewNoDataBelowValidMin (Lerc.cpp:1556-1618)
+template <class T>
+bool findNewNoData(double minVal, double maxZErr, bool allInt, double lowIntLimit, T& out) {
+  std::vector<T> cand;
+  if (allInt) {
+    for (double dist : {4 * maxZErr, 1.0, 10.0, 100.0, 1000.0, 10000.0}) cand.push_back((T)(minVal - dist));
+    cand.push_back((T)(minVal > 0 ? std::floor(minVal / 2) : minVal * 2));
+  } else {
+    for (double dist : {4 * maxZErr, 0.0001, 0.001, 0.01, 0.1, 1.0, 10.0, 100.0, 1000.0, 10000.0}) cand.push_back((T)(minVal - dist));
+    cand.push_back((T)(minVal > 0 ? minVal / 2 : minVal * 2));
+  }
+  std::sort(cand.begin(), cand.end(), [](T x, T y) { return x > y; });
+  const T lowest = (T)(sizeof(T) == 4 ? -FLT_MAX : -DBL_MAX);
+  for (T v : cand)
+    if (allInt ? (v > (T)lowIntLimit && v < (T)(minVal - 2 * maxZErr) && isIntegralHost(v)) : (v > lowest && v < (T)(minVal - 2 * maxZErr))) { out = v; return true; }
+  return false;
+}
+
+template <class T>
+ErrCode prefilterNoDataT(Context* ctx, void* dData, uint8_t* dMaskBytes, long long nPix, int nDepth, double maxZErr, double noDataOrigD, NoDataVerdict& out) {
+  constexpr bool isFlt = PixelTraits<T>::isFloat;
+  using K = typename PixelTraits<T>::Key;
+  out.maxZErr = maxZErr; out.noDataVal = noDataOrigD; out.maskModified = out.needNoData = out.isAllInt = false;
+  double tLo = 0, tHi = 0;
+  if (isFlt) { if (sizeof(T) == 4 && (noDataOrigD < -FLT_MAX || noDataOrigD > FLT_MAX)) return WrongParam; }
+  else {
+    static const double kLo[6] = {-128, 0, -32768, 0, -2147483648.0, 0}, kHi[6] = {127, 255, 32767, 65535, 2147483647.0, 4294967295.0};   // GetTypeRange
+    tLo = kLo[PixelTraits<T>::code]; tHi = kHi[PixelTraits<T>::code];
+    if (noDataOrigD < tLo || noDataOrigD > tHi) return WrongParam;
+  }
+  const T origNoData = (T)noDataOrigD;
+  cudaStream_t st = ctx->stream;
+  NoDataScan* dScan = (NoDataScan*)ctx->arena.alloc(sizeof(NoDataScan));
+  NoDataScan* hScan = (NoDataScan*)ctx->pinnedAlloc(sizeof(NoDataScan));
+  if (!dScan || !hScan) return Failed;
+  hScan->minKey = ~0ull; hScan->negMaxKey = ~0ull; hScan->flags = 0; hScan->pad = 0;
+  cudaMemcpyAsync(dScan, hScan, sizeof(NoDataScan), cudaMemcpyHostToDevice, st);
+  const int grid = (int)std::max<long long>(1, std::min<long long>((nPix + 255) / 256, 148 * 16));
+  LERC_LAUNCH(ctx, k_nodata_scan<T>, grid, 256, 0, (T*)dData, dMaskBytes, nPix, nDepth, noDataOrigD, dScan);
+  if (!cudaOk(cudaMemcpyAsync(hScan, dScan, sizeof(NoDataScan), cudaMemcpyDeviceToHost, st), "D2H noData scan") || !cudaOk(cudaStreamSynchronize(st), "sync")) return Failed;
+  const unsigned fl = hScan->flags;
+  out.maskModified = (fl & NDF_MODIFIED) != 0;
+  const bool left = (fl & NDF_LEFT) != 0;
+  if (!(fl & NDF_ANY_VALID)) { out.maxZErr = isFlt ? 0 : 0.5; return Ok; }                         // no valid data in this band
+  const double minVal = (double)fromKeyHost<T>((K)hScan->minKey), maxVal = (double)fromKeyHost<T>((K)~hScan->negMaxKey);
+  auto remap = [&](T to) {
+    LERC_LAUNCH(ctx, k_nodata_remap<T>, grid, 256, 0, (T*)dData, (const uint8_t*)dMaskBytes, nPix, nDepth, noDataOrigD, (double)to);
+    out.noDataVal = (double)to;
+  };
+  if constexpr (isFlt) {
+    out.needNoData = left;
+    const double lowIntLimit = sizeof(T) == 4 ? -8388608.0 : -9007199254740992.0, highIntLimit = -lowIntLimit;
+    bool allInt = !(fl & NDF_NOT_INT);
+    double mzL = maxZErr;
+    if (allInt) {
+      allInt = minVal >= lowIntLimit && minVal <= highIntLimit && maxVal >= lowIntLimit && maxVal <= highIntLimit;
+      if (left) allInt = allInt && isIntegralHost(origNoData) && origNoData >= lowIntLimit && origNoData <= highIntLimit;
+      if (allInt) mzL = std::max(0.5, std::floor(maxZErr));
+    }
+    out.isAllInt = allInt;
+    if (mzL == 0) return Ok;
+    const double dist = allInt ? std::floor(mzL) : 2 * mzL;
+    if (origNoData >= minVal - dist && origNoData <= maxVal + dist) { out.maxZErr = allInt ? 0.5 : 0; return Ok; }   // fall back to lossless
+    if (left) {
+      T to = origNoData;
+      if (findNewNoData<T>(minVal, mzL, allInt, lowIntLimit, to)) { if (to != origNoData) remap(to); }
+      else if ((double)origNoData >= minVal) mzL = allInt ? 0.5 : 0;
+    }
+    out.maxZErr = mzL;
+  } else {
+    out.needNoData = left;
+    double mzL = std::max(0.5, std::floor(maxZErr));
+    const double dist = std::floor(mzL);
+    if (origNoData >= minVal - dist && origNoData <= maxVal + dist) { out.maxZErr = 0.5; return Ok; }
+    if (left) {
+      const double minDist = std::floor(mzL) + 1;
+      double remapVal = minVal - minDist;
+      T to = origNoData;
+      if (remapVal >= tLo) to = (T)remapVal;
+      else {
+        mzL = 0.5;
+        remapVal = minVal - 1;
+        if (remapVal >= tLo) to = (T)remapVal;
+        else { remapVal = maxVal + 1; if (remapVal <= tHi && remapVal < origNoData) to = (T)remapVal; }
+      }
+      if (to != origNoData) remap(to);
+    }
+    out.maxZErr = mzL;
+  }
+  return cudaOk(cudaGetLastError(), "prefilterNoData") ? Ok : Failed;
+}
+
+}  // namespace
+
+ErrCode prefilterNoData(Context* ctx, int dt, void* dData, uint8_t* dMaskBytes, long long nPix, int nDepth, double maxZErr, double noDataOrig,
+                        NoDataVerdict& out) {
+  switch (dt) {
+    case DT_Char:   return prefilterNoDataT<int8_t>(ctx, dData, dMaskBytes, nPix, nDepth, maxZErr, noDataOrig, out);
+    case DT_Byte:   return prefilterNoDataT<uint8_t>(ctx, dData, dMaskBytes, nPix, nDepth, maxZErr, noDataOrig, out);
+    case DT_Short:  return prefilterNoDataT<int16_t>(ctx, dData, dMaskBytes, nPix, nDepth, maxZErr, noDataOrig, out);
+    case DT_UShort: return prefilterNoDataT<uint16_t>(ctx, dData, dMaskBytes, nPix, nDepth, maxZErr, noDataOrig, out);
+    case DT_Int:    return prefilterNoDataT<int32_t>(ctx, dData, dMaskBytes, nPix, nDepth, maxZErr, noDataOrig, out);
+    case DT_UInt:   return prefilterNoDataT<uint32_t>(ctx, dData, dMaskBytes, nPix, nDepth, maxZErr, noDataOrig, out);
+    case DT_Float:  return prefilterNoDataT<float>(ctx, dData, dMaskBytes, nPix, nDepth, maxZErr, noDataOrig, out);
+    case DT_Double: return prefilterNoDataT<double>(ctx, dData, dMaskBytes, nPix, nDepth, maxZErr, noDataOrig, out);
     default: return WrongParam;
   }
 }

@@ -143,6 +143,10 @@ struct EncodeBandArgs {
   double maxZErr;
   int iBand, nBands, nMasks;
   int version = 6;                // codec version to write: 6, or 2..5 (Lerc::EncodeInternal_v5, Lerc.cpp:526-624)
+  // a band that went through prefilterNoData (caller-supplied noData value, Lerc.cpp:687-711): NaN / noData are already moved to the
+  // mask or remapped, maxZErr is final, and the all-integer verdict and the header's noData fields are given
+  bool prefiltered = false, isAllInt = false, passNoData = false;
+  double noDataVal = 0, noDataOrig = 0;
   bool anyMaskModified;           // in/out across bands (Lerc.cpp:714-720)
   uint8_t* dOut;                  // device output buffer (whole multi-band blob), may be nullptr for size-only
   size_t outCapacity;             // bytes available in dOut from outOffset
@@ -176,6 +180,14 @@ ErrCode encodeTiles(Context* ctx, int dt, int nCols, int nRows, int tileCols, in
                     uint8_t* dOut, size_t outCap, unsigned long long* hOffsets);
 ErrCode decodeTiles(Context* ctx, int dt, int nCols, int nRows, int tileCols, int tileRows, const uint8_t* dBlobs, size_t blobBytes,
                     const unsigned long long* hOffsets, void* dData);
+
+// Lerc::FilterNoDataAndNaN / Lerc::FilterNoData (Lerc.cpp:1378-1552, :1241-1374) for a band with a caller-supplied noData value.
+// dData / dMaskBytes are private device copies of the band and its byte mask and are modified in place.
+struct NoDataVerdict { double maxZErr, noDataVal; bool maskModified, needNoData, isAllInt; };
+ErrCode prefilterNoData(Context* ctx, int dt, void* dData, uint8_t* dMaskBytes, long long nPix, int nDepth, double maxZErr, double noDataOrig,
+                        NoDataVerdict& out);
+// decode side, Lerc::RemapNoData (Lerc.cpp:1046-1076): valid pixels' values equal to (T)from become (T)to
+void launchRemapNoData(Context* ctx, int dt, void* dData, const uint8_t* dBits, long long nPix, int nDepth, double from, double to);
 
 // misc device utilities (lerc_mask.cu)
 void launchConvertToDouble(Context* ctx, const void* dSrc, int dt, size_t n, double* dDst);   // in-place safe back-to-front

@@ -292,6 +292,33 @@ void launchFletcher(Context* ctx, const uint8_t* dRegion, long long len, unsigne
 }
 
 // ------------------------------------------------------------------------------------------------
+// Lerc::RemapNoData (Lerc.cpp:1046-1076)
+template <class T>
+__global__ void k_remap_nodata(T* __restrict__ data, const uint8_t* __restrict__ bits, long long nPix, int nDepth, double fromD, double toD) {
+  const T from = (T)fromD, to = (T)toD;
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < nPix; k += (long long)gridDim.x * blockDim.x) {
+    if (!maskBit(bits, k)) continue;
+    T* px = data + k * nDepth;
+    for (int m = 0; m < nDepth; m++) if (px[m] == from) px[m] = to;
+  }
+}
+void launchRemapNoData(Context* ctx, int dt, void* dData, const uint8_t* dBits, long long nPix, int nDepth, double from, double to) {
+  int grid = (int)std::min<long long>((nPix + 255) / 256, 148 * 16);
+  if (grid < 1) grid = 1;
+  switch (dt) {
+    case DT_Char:   LERC_LAUNCH(ctx, k_remap_nodata<int8_t>,   grid, 256, 0, (int8_t*)dData, dBits, nPix, nDepth, from, to); break;
+    case DT_Byte:   LERC_LAUNCH(ctx, k_remap_nodata<uint8_t>,  grid, 256, 0, (uint8_t*)dData, dBits, nPix, nDepth, from, to); break;
+    case DT_Short:  LERC_LAUNCH(ctx, k_remap_nodata<int16_t>,  grid, 256, 0, (int16_t*)dData, dBits, nPix, nDepth, from, to); break;
+    case DT_UShort: LERC_LAUNCH(ctx, k_remap_nodata<uint16_t>, grid, 256, 0, (uint16_t*)dData, dBits, nPix, nDepth, from, to); break;
+    case DT_Int:    LERC_LAUNCH(ctx, k_remap_nodata<int32_t>,  grid, 256, 0, (int32_t*)dData, dBits, nPix, nDepth, from, to); break;
+    case DT_UInt:   LERC_LAUNCH(ctx, k_remap_nodata<uint32_t>, grid, 256, 0, (uint32_t*)dData, dBits, nPix, nDepth, from, to); break;
+    case DT_Float:  LERC_LAUNCH(ctx, k_remap_nodata<float>,    grid, 256, 0, (float*)dData, dBits, nPix, nDepth, from, to); break;
+    case DT_Double: LERC_LAUNCH(ctx, k_remap_nodata<double>,   grid, 256, 0, (double*)dData, dBits, nPix, nDepth, from, to); break;
+    default: break;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 template <class T>
 __global__ void k_to_double(const T* __restrict__ src, size_t n, double* __restrict__ dst) {
   for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) dst[k] = (double)src[k];

@@ -776,8 +776,8 @@ static int read_band_header(const u8* p, size_t avail, lo_hdr* h, int* hasMask);
 /* ------------------------------------------------------------------------------------------- */
 /* API                                                                  Lerc_c_api_impl.cpp:33-305 */
 
-typedef unsigned (*enc_fn)(const void*, int, int, int, int, int, int, const u8*, double, u8*, unsigned, unsigned*, unsigned*);
-typedef unsigned (*dec_fn)(const u8*, unsigned, int, u8*, int, int, int, int, void*);
+typedef unsigned (*enc_fn)(const void*, int, int, int, int, int, int, const u8*, double, u8*, unsigned, unsigned*, unsigned*, const u8*, const double*);
+typedef unsigned (*dec_fn)(const u8*, unsigned, int, u8*, int, int, int, int, void*, u8*, double*);
 static const enc_fn kEnc[8] = {encode_bands_i8, encode_bands_u8, encode_bands_i16, encode_bands_u16,
                                encode_bands_i32, encode_bands_u32, encode_bands_f32, encode_bands_f64};
 static const dec_fn kDec[8] = {decode_bands_i8, decode_bands_u8, decode_bands_i16, decode_bands_u16,
@@ -789,16 +789,28 @@ static int dims_ok(int nDepth, int nCols, int nRows, int elemSize) {     /* Lerc
   return !(nPix > lim || b * (u64)nDepth > lim || b * (u64)nDepth * nPix > lim);
 }
 
+static unsigned encode_common4(const void* data, int version, unsigned dt, int nDepth, int nCols, int nRows, int nBands,
+                               int nMasks, const u8* validBytes, double maxZErr, u8* out, unsigned outSize,
+                               unsigned* nWritten, unsigned* nNeeded, int sizeOnly, const u8* usesNoData, const double* noDataValues);
 static unsigned encode_common(const void* data, int version, unsigned dt, int nDepth, int nCols, int nRows, int nBands,
                               int nMasks, const u8* validBytes, double maxZErr, u8* out, unsigned outSize,
                               unsigned* nWritten, unsigned* nNeeded, int sizeOnly) {
+  return encode_common4(data, version, dt, nDepth, nCols, nRows, nBands, nMasks, validBytes, maxZErr, out, outSize, nWritten, nNeeded, sizeOnly, NULL, NULL);
+}
+static unsigned encode_common4(const void* data, int version, unsigned dt, int nDepth, int nCols, int nRows, int nBands,
+                               int nMasks, const u8* validBytes, double maxZErr, u8* out, unsigned outSize,
+                               unsigned* nWritten, unsigned* nNeeded, int sizeOnly, const u8* usesNoData, const double* noDataValues) {
   if (!data || dt >= LO_UNDEFINED || nDepth <= 0 || nCols <= 0 || nRows <= 0 || nBands <= 0 || maxZErr < 0) return LO_WRONG_PARAM;
   if (!sizeOnly && (!out || !outSize)) return LO_WRONG_PARAM;
   if (!(nMasks == 0 || nMasks == 1 || nMasks == nBands) || (nMasks > 0 && !validBytes)) return LO_WRONG_PARAM;
   if (version > 6 || (version >= 0 && version < 2)) return LO_WRONG_PARAM;   /* Lerc2::SetEncoderToOldVersion, Lerc2.cpp:52-63 */
   if (!dims_ok(nDepth, nCols, nRows, kTypeSize[dt])) return LO_DIMS_TOO_LARGE;
   if (!sizeOnly) memset(out, 0, outSize);                          /* Lerc.cpp:374 */
-  return kEnc[dt](data, version < 0 ? 6 : version, nDepth, nCols, nRows, nBands, nMasks, validBytes, maxZErr, sizeOnly ? NULL : out, outSize, nWritten, nNeeded);
+  int anyNoData = 0;
+  if (usesNoData) for (int i = 0; i < nBands; i++) if (usesNoData[i]) anyNoData = 1;
+  if (anyNoData && (!noDataValues || (version >= 0 && version <= 5))) return LO_WRONG_PARAM;     /* Lerc.cpp:649-652, :378-383 */
+  return kEnc[dt](data, version < 0 ? 6 : version, nDepth, nCols, nRows, nBands, nMasks, validBytes, maxZErr, sizeOnly ? NULL : out, outSize, nWritten, nNeeded,
+                  anyNoData ? usesNoData : NULL, noDataValues);
 }
 
 unsigned lo_computeCompressedSizeForVersion(const void* data, int version, unsigned dt, int nDepth, int nCols, int nRows,
@@ -927,8 +939,14 @@ unsigned lo_getDataRanges(const unsigned char* blob, unsigned blobSize, int nDep
   return blob_info(blob, blobSize, &li, mins, maxs, (size_t)nDepth * (size_t)nBands);
 }
 
+unsigned lo_decode_4D(const unsigned char* blob, unsigned blobSize, int nMasks, unsigned char* validBytes, int nDepth,
+                      int nCols, int nRows, int nBands, unsigned dt, void* data, unsigned char* usesNoData, double* noDataValues);
 unsigned lo_decode(const unsigned char* blob, unsigned blobSize, int nMasks, unsigned char* validBytes, int nDepth,
                    int nCols, int nRows, int nBands, unsigned dt, void* data) {
+  return lo_decode_4D(blob, blobSize, nMasks, validBytes, nDepth, nCols, nRows, nBands, dt, data, NULL, NULL);
+}
+unsigned lo_decode_4D(const unsigned char* blob, unsigned blobSize, int nMasks, unsigned char* validBytes, int nDepth,
+                      int nCols, int nRows, int nBands, unsigned dt, void* data, unsigned char* usesNoData, double* noDataValues) {
   if (!blob || !blobSize || !data || dt >= LO_UNDEFINED || nDepth <= 0 || nCols <= 0 || nRows <= 0 || nBands <= 0) return LO_WRONG_PARAM;
   if (!(nMasks == 0 || nMasks == 1 || nMasks == nBands) || (nMasks > 0 && !validBytes)) return LO_WRONG_PARAM;
   if (!dims_ok(nDepth, nCols, nRows, kTypeSize[dt])) return LO_DIMS_TOO_LARGE;
@@ -936,13 +954,23 @@ unsigned lo_decode(const unsigned char* blob, unsigned blobSize, int nMasks, uns
   unsigned e = blob_info(blob, blobSize, &li, NULL, NULL, 0);
   if (e) return e;
   if (nMasks < li.nMasks || nBands > li.nBands) return LO_WRONG_PARAM;    /* Lerc.cpp:423-428 */
-  if (li.nUsesNoData && nDepth > 1) return LO_HAS_NODATA;                  /* Lerc.cpp:431-434; _4D out of scope */
+  int wantNoData = li.nUsesNoData && nDepth > 1;
+  if (wantNoData) {                                                        /* Lerc.cpp:431-445 */
+    if (!usesNoData || !noDataValues) return LO_HAS_NODATA;
+    memset(usesNoData, 0, (size_t)nBands); memset(noDataValues, 0, (size_t)nBands * sizeof(double));
+  }
   if ((unsigned)li.dt != dt) return LO_FAILED;   /* deviation: the reference reinterprets; see DESIGN.md */
-  return kDec[dt](blob, blobSize, nMasks, validBytes, nDepth, nCols, nRows, nBands, data);
+  return kDec[dt](blob, blobSize, nMasks, validBytes, nDepth, nCols, nRows, nBands, data, wantNoData ? usesNoData : NULL, noDataValues);
 }
 
+unsigned lo_decodeToDouble_4D(const unsigned char* blob, unsigned blobSize, int nMasks, unsigned char* validBytes, int nDepth,
+                              int nCols, int nRows, int nBands, double* data, unsigned char* usesNoData, double* noDataValues);
 unsigned lo_decodeToDouble(const unsigned char* blob, unsigned blobSize, int nMasks, unsigned char* validBytes, int nDepth,
-                           int nCols, int nRows, int nBands, double* data) {       /* Lerc_c_api_impl.cpp:256-304 */
+                           int nCols, int nRows, int nBands, double* data) {
+  return lo_decodeToDouble_4D(blob, blobSize, nMasks, validBytes, nDepth, nCols, nRows, nBands, data, NULL, NULL);
+}
+unsigned lo_decodeToDouble_4D(const unsigned char* blob, unsigned blobSize, int nMasks, unsigned char* validBytes, int nDepth,
+                              int nCols, int nRows, int nBands, double* data, unsigned char* usesNoData, double* noDataValues) {       /* Lerc_c_api_impl.cpp:256-304 */
   if (!blob || !blobSize || !data || nDepth <= 0 || nCols <= 0 || nRows <= 0 || nBands <= 0) return LO_WRONG_PARAM;
   if (!(nMasks == 0 || nMasks == 1 || nMasks == nBands) || (nMasks > 0 && !validBytes)) return LO_WRONG_PARAM;
   lo_info li;
@@ -950,10 +978,29 @@ unsigned lo_decodeToDouble(const unsigned char* blob, unsigned blobSize, int nMa
   if (e) return e;
   if (li.nDepth != nDepth || li.nCols != nCols || li.nRows != nRows || li.nBands != nBands) return LO_FAILED;
   size_t n = (size_t)nDepth * (size_t)nCols * (size_t)nRows * (size_t)nBands;
-  if (li.dt == LO_DOUBLE) return lo_decode(blob, blobSize, nMasks, validBytes, nDepth, nCols, nRows, nBands, LO_DOUBLE, data);
+  if (li.dt == LO_DOUBLE) return lo_decode_4D(blob, blobSize, nMasks, validBytes, nDepth, nCols, nRows, nBands, LO_DOUBLE, data, usesNoData, noDataValues);
   u8* tmp = (u8*)data + n * (8 - (size_t)kTypeSize[li.dt]);   /* decode into the tail, widen front to back */
-  e = lo_decode(blob, blobSize, nMasks, validBytes, nDepth, nCols, nRows, nBands, (unsigned)li.dt, tmp);
+  e = lo_decode_4D(blob, blobSize, nMasks, validBytes, nDepth, nCols, nRows, nBands, (unsigned)li.dt, tmp, usesNoData, noDataValues);
   if (e) return e;
   for (size_t k = 0; k < n; k++) data[k] = read_offset(tmp + k * (size_t)kTypeSize[li.dt], li.dt);
   return LO_OK;
+}
+
+/* ---- the _4D entry points (Lerc_c_api_impl.cpp:33-93, :178-252 with the noData arguments) ---- */
+unsigned lo_computeCompressedSize_4D(const void* data, unsigned dt, int nDepth, int nCols, int nRows, int nBands, int nMasks,
+                                     const unsigned char* validBytes, double maxZErr, unsigned* numBytes,
+                                     const unsigned char* usesNoData, const double* noDataValues) {
+  if (!numBytes) return LO_WRONG_PARAM;
+  *numBytes = 0;
+  unsigned w = 0;
+  return encode_common4(data, -1, dt, nDepth, nCols, nRows, nBands, nMasks, validBytes, maxZErr, NULL, 0, &w, numBytes, 1, usesNoData, noDataValues);
+}
+
+unsigned lo_encode_4D(const void* data, unsigned dt, int nDepth, int nCols, int nRows, int nBands, int nMasks,
+                      const unsigned char* validBytes, double maxZErr, unsigned char* out, unsigned outSize, unsigned* nWritten,
+                      const unsigned char* usesNoData, const double* noDataValues) {
+  if (!nWritten) return LO_WRONG_PARAM;
+  *nWritten = 0;
+  unsigned need = 0;
+  return encode_common4(data, -1, dt, nDepth, nCols, nRows, nBands, nMasks, validBytes, maxZErr, out, outSize, nWritten, &need, 0, usesNoData, noDataValues);
 }

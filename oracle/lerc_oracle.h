@@ -13,12 +13,12 @@
  *   (b) the unmodified reference itself compiled to oracle/_ref/libLerc_ref.so (oracle/Makefile),
  *       byte-for-byte on seeded synthetic rasters of all 8 pixel types.
  *
- * Scope: Lerc2 v6 writer; v3..v6 reader; tiling, one-sweep raw, const image,
- * RLE bit mask, per-depth ranges, depth-delta blocks, LUT blocks, 8-bit Huffman / delta-Huffman,
- * Fletcher-32, multi-band concatenation.  Not restated (SURVEY 8f "next"): the lossless-float FPL
- * codec (maxZError == 0 float/double blobs are written as raw/const micro-blocks, which every Lerc2
- * reader decodes; FPL blobs are rejected on decode), noData remapping of the _4D API, the integer
- * bit-plane mode, pre-v3 bit-stuffing, Lerc1.
+ * Scope: Lerc2 writer and reader for codec versions 2..6 (2..5 = Lerc::EncodeInternal_v5; version 2 with
+ * its MSB-first bit stuffing and no checksum); tiling, one-sweep raw, const image, RLE bit mask, per-depth ranges,
+ * depth-delta blocks, LUT blocks, 8-bit Huffman / delta-Huffman, Fletcher-32, multi-band concatenation, the _4D calls with
+ * per-band noData values (FilterNoDataAndNaN / FilterNoData / RemapNoData).  Not restated (SURVEY 8f "next"): the
+ * lossless-float FPL codec (maxZError == 0 float/double blobs are written as raw/const micro-blocks, which every Lerc2
+ * reader decodes; FPL blobs are rejected on decode), the integer bit-plane mode, Lerc1.
  *
  * The exported functions use the reference C API's argument lists (src/LercLib/include/Lerc_c_api.h:126-380)
  * with an `lo_` prefix so one ctypes binding drives all three libraries.
@@ -52,6 +52,18 @@ unsigned lo_decode(const unsigned char* blob, unsigned blobSize, int nMasks, uns
                    int nCols, int nRows, int nBands, unsigned dt, void* data);
 unsigned lo_decodeToDouble(const unsigned char* blob, unsigned blobSize, int nMasks, unsigned char* validBytes, int nDepth,
                            int nCols, int nRows, int nBands, double* data);
+
+/* the _4D entry points: per-band noData values (Lerc_c_api.h:295-380; Lerc.cpp:1241-1374, :1378-1618, :1046-1076) */
+unsigned lo_computeCompressedSize_4D(const void* data, unsigned dt, int nDepth, int nCols, int nRows, int nBands, int nMasks,
+                                     const unsigned char* validBytes, double maxZErr, unsigned* numBytes,
+                                     const unsigned char* usesNoData, const double* noDataValues);
+unsigned lo_encode_4D(const void* data, unsigned dt, int nDepth, int nCols, int nRows, int nBands, int nMasks,
+                      const unsigned char* validBytes, double maxZErr, unsigned char* out, unsigned outSize, unsigned* nWritten,
+                      const unsigned char* usesNoData, const double* noDataValues);
+unsigned lo_decode_4D(const unsigned char* blob, unsigned blobSize, int nMasks, unsigned char* validBytes, int nDepth,
+                      int nCols, int nRows, int nBands, unsigned dt, void* data, unsigned char* usesNoData, double* noDataValues);
+unsigned lo_decodeToDouble_4D(const unsigned char* blob, unsigned blobSize, int nMasks, unsigned char* validBytes, int nDepth,
+                              int nCols, int nRows, int nBands, double* data, unsigned char* usesNoData, double* noDataValues);
 
 /* building blocks exposed for unit tests */
 uint32_t lo_fletcher32(const uint8_t* bytes, int len);

@@ -123,3 +123,50 @@ def tile_cases(seed=5):
     cases.append(("f32_mixed_decisions", mixed, 64, 64, 0.01))
     cases.append(("f32_lossless", f[:100, :100].copy(), 50, 50, 0))
     return cases
+
+
+def nodata_cases(seed=11):
+    """(name, array [nBands?][rows][cols][nDepth?], maxZErr, kwargs incl. uses_no_data / no_data) for the _4D calls:
+    noData values beside valid values of the same pixel (nDepth > 1), pixels that are noData in every depth, NaN together
+    with noData, noData close to / far from the valid range, integer and float types, all-integer floats, several bands."""
+    rng = np.random.default_rng(seed)
+    h, w = 48, 60
+    cases = []
+
+    def add(name, arr, mz, **kw):
+        cases.append((name, arr, mz, kw))
+
+    base = (rng.random((h, w, 3)) * 100 + 50).astype(np.float32)
+    a = base.copy(); a[3:9, 5:20, 1] = -9999; a[20:24, 10:14, :] = -9999
+    add("f32_d3_nodata_far", a, 0.01, n_depth=3, uses_no_data=[1], no_data=[-9999.0])
+    add("f32_d3_nodata_far_lossless", a, 0, n_depth=3, uses_no_data=[1], no_data=[-9999.0])
+    b = base.copy(); b[3:9, 5:20, 1] = 49.9995; b[20:24, 10:14, :] = 49.9995
+    add("f32_d3_nodata_close", b, 0.01, n_depth=3, uses_no_data=[1], no_data=[49.9995])
+    c = base.copy(); c[3:9, 5:20, 1] = 1e30
+    add("f32_d3_nodata_above", c, 0.01, n_depth=3, uses_no_data=[1], no_data=[1e30])
+    d = base.copy(); d[3:9, 5:20, 1] = -9999; d[30:33, 2:9, 2] = np.nan; d[40:42, 40:44, :] = np.nan
+    add("f32_d3_nodata_and_nan", d, 0.01, n_depth=3, uses_no_data=[1], no_data=[-9999.0])
+    e = np.round(base); e[3:9, 5:20, 0] = -32768
+    add("f32_d3_allint_nodata", e.astype(np.float32), 0.01, n_depth=3, uses_no_data=[1], no_data=[-32768.0])
+    add("f32_d3_allint_nodata_3.2", e.astype(np.float32), 3.2, n_depth=3, uses_no_data=[1], no_data=[-32768.0])
+    f = base[:, :, 0].copy(); f[5:15, 5:25] = -1
+    add("f32_d1_nodata", f, 0.01, uses_no_data=[1], no_data=[-1.0])
+    g = (rng.random((h, w, 3)) * 100 + 50).astype(np.float64); g[1:4, 1:30, 2] = -1e300
+    add("f64_d3_nodata_huge", g, 0.001, n_depth=3, uses_no_data=[1], no_data=[-1e300])
+    i16 = (rng.integers(100, 2000, (h, w, 3))).astype(np.int16); i16[3:9, 5:20, 1] = -32768; i16[20:24, 10:14, :] = -32768
+    add("i16_d3_nodata", i16, 0, n_depth=3, uses_no_data=[1], no_data=[-32768.0])
+    add("i16_d3_nodata_lossy3", i16, 3, n_depth=3, uses_no_data=[1], no_data=[-32768.0])
+    u8 = (rng.integers(1, 255, (h, w, 3))).astype(np.uint8); u8[3:9, 5:20, 1] = 0
+    add("u8_d3_nodata_0_adjacent", u8, 0, n_depth=3, uses_no_data=[1], no_data=[0.0])
+    u8b = (rng.integers(0, 200, (h, w, 3))).astype(np.uint8); u8b[3:9, 5:20, 1] = 255
+    add("u8_d3_nodata_255_min0", u8b, 0, n_depth=3, uses_no_data=[1], no_data=[255.0])
+    i32 = (rng.integers(-1000, 1000, (h, w, 2))).astype(np.int32); i32[0:5, 0:9, 0] = 2147483647
+    add("i32_d2_nodata_max", i32, 2, n_depth=2, uses_no_data=[1], no_data=[2147483647.0])
+    bands = np.stack([a, base, d])
+    add("f32_d3_3bands_mixed", bands, 0.01, n_depth=3, n_bands=3, uses_no_data=[1, 0, 1], no_data=[-9999.0, 0.0, -9999.0])
+    m = np.ones((h, w), np.uint8); m[0:10, 0:10] = 0
+    add("f32_d3_nodata_masked", a, 0.01, n_depth=3, mask=m, uses_no_data=[1], no_data=[-9999.0])
+    add("f32_d3_flag_without_values", base, 0.01, n_depth=3, uses_no_data=[1], no_data=None)          # WrongParam
+    add("u8_d3_nodata_out_of_range", u8, 0, n_depth=3, uses_no_data=[1], no_data=[300.0])              # WrongParam
+    add("f32_d3_all_nodata", np.full((h, w, 3), -5.0, np.float32), 0.01, n_depth=3, uses_no_data=[1], no_data=[-5.0])
+    return cases

@@ -19,7 +19,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
 from lercapi import ref_lib  # noqa: E402
-from cases import all_cases  # noqa: E402
+from cases import all_cases, nodata_cases  # noqa: E402
 
 REF = "/root/reference"
 
@@ -83,6 +83,24 @@ def main():
     np.savez_compressed(os.path.join(HERE, "synthetic_ref_versions.npz"), keys=np.array(keys), status=np.array(status), sizes=np.array(sizes),
                         enc=np.array(enc), dec=np.array(dec))
     print("old-version cases:", len(keys))
+    # the _4D calls with per-band noData values (Lerc.cpp:1241-1374, :1378-1618, :1046-1076)
+    names, status, enc, dec, sizes, uses, vals = [], [], [], [], [], [], []
+    for name, arr, mz, kw in nodata_cases():
+        st, blob = ref.encode_4d(arr, mz, **kw)
+        names.append(name); status.append(st)
+        if st != 0:
+            sizes.append(0); enc.append(""); dec.append(""); uses.append(""); vals.append("")
+            continue
+        st2, data, mask, u, v = ref.decode_4d(blob)
+        assert st2 == 0
+        sizes.append(len(blob)); enc.append(hashlib.sha256(blob).hexdigest())
+        h = hashlib.sha256(data.tobytes())
+        if mask is not None:
+            h.update(mask.tobytes())
+        dec.append(h.hexdigest()); uses.append(u.tobytes().hex()); vals.append(v.tobytes().hex())
+    np.savez_compressed(os.path.join(HERE, "nodata_ref.npz"), names=np.array(names), status=np.array(status), sizes=np.array(sizes),
+                        enc=np.array(enc), dec=np.array(dec), uses=np.array(uses), vals=np.array(vals))
+    print("noData cases:", len(names))
 
 
 if __name__ == "__main__":

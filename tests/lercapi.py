@@ -100,6 +100,48 @@ class LercLib:
                                             n_masks, mp, max_z_err, out.ctypes.data, buf_size, C.addressof(n))
         return st, out[: n.value].tobytes(), out
 
+    # ---- the _4D calls: per-band noData values (Lerc_c_api.h:295-380) -------------------------------
+    def encode_4d(self, arr, max_z_err, n_depth=1, n_bands=1, mask=None, uses_no_data=None, no_data=None, buf_size=None, size_only=False):
+        """returns (status, blob bytes) or, with size_only, (status, byte count)"""
+        a, n_rows, n_cols = self._shape(arr, n_depth, n_bands)
+        n_masks, mp = self._mask(mask, n_bands, n_rows, n_cols)
+        u = None if uses_no_data is None else np.ascontiguousarray(uses_no_data, dtype=np.uint8)
+        v = None if no_data is None else np.ascontiguousarray(no_data, dtype=np.float64)
+        up, vp = (None if u is None else u.ctypes.data), (None if v is None else v.ctypes.data)
+        n = C.c_uint(0)
+        if size_only:
+            st = self.f["computeCompressedSize_4D"](a.ctypes.data, DT_CODE[a.dtype], n_depth, n_cols, n_rows, n_bands, n_masks, mp, max_z_err,
+                                                    C.addressof(n), up, vp)
+            return st, n.value
+        if buf_size is None:
+            buf_size = int(a.nbytes * 1.1) + 4096 + (n_rows * n_cols * n_bands) // 4
+        out = np.full(buf_size, 0xAB, dtype=np.uint8)
+        st = self.f["encode_4D"](a.ctypes.data, DT_CODE[a.dtype], n_depth, n_cols, n_rows, n_bands, n_masks, mp, max_z_err,
+                                 out.ctypes.data, buf_size, C.addressof(n), up, vp)
+        return st, out[: n.value].tobytes()
+
+    def decode_4d(self, blob, n_masks=None, to_double=False, want_no_data=True):
+        """returns (status, data [nBands][nRows][nCols][nDepth], mask or None, usesNoData[nBands], noDataValues[nBands])"""
+        b = np.frombuffer(blob, dtype=np.uint8)
+        st, info = self.blob_info(blob)
+        if st:
+            return st, None, None, None, None
+        nb, nr, nc, nd = info["nBands"], info["nRows"], info["nCols"], info["nDepth"]
+        if n_masks is None:
+            n_masks = info["nMasks"]
+        dt = info["dataType"]
+        data = np.full((nb, nr, nc, nd), 0x5A, dtype=np.float64 if to_double else DT_NP[dt])
+        mask = np.full((n_masks, nr, nc), 7, dtype=np.uint8) if n_masks > 0 else None
+        mp = mask.ctypes.data if mask is not None else None
+        uses = np.full(nb, 9, dtype=np.uint8)
+        vals = np.full(nb, -7.0, dtype=np.float64)
+        up, vp = (uses.ctypes.data, vals.ctypes.data) if want_no_data else (None, None)
+        if to_double:
+            st = self.f["decodeToDouble_4D"](b.ctypes.data, b.size, n_masks, mp, nd, nc, nr, nb, data.ctypes.data, up, vp)
+        else:
+            st = self.f["decode_4D"](b.ctypes.data, b.size, n_masks, mp, nd, nc, nr, nb, dt, data.ctypes.data, up, vp)
+        return st, data, mask, uses, vals
+
     def blob_info(self, blob):
         b = np.frombuffer(blob, dtype=np.uint8)
         info = np.zeros(11, dtype=np.uint32)

@@ -12,7 +12,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from cases import all_cases
+from cases import all_cases, nodata_cases
 from lercapi import ROOT, oracle_lib, ref_lib
 
 GOLD = os.path.join(ROOT, "tests", "golden")
@@ -120,6 +120,40 @@ def test_old_codec_versions_hashes(oracle):
             assert st2 == 0 and n == len(blob)
             checked += 1
     assert checked >= 200
+
+
+NODATA_FPL_CASES = {"f32_d3_nodata_far_lossless", "f32_d3_nodata_close"}      # the filter falls back to lossless float: FPL in the reference
+
+
+def test_nodata_4d_hashes(oracle):
+    """lerc_encode_4D / lerc_decode_4D with per-band noData values: status, blob, decoded pixels and the returned noData arrays of the
+    oracle equal the reference's (nodata_ref.npz); where the reference switches to its FPL codec the oracle must still round-trip"""
+    g = np.load(os.path.join(GOLD, "nodata_ref.npz"))
+    want = {str(n): (int(st), int(s), str(e), str(d), str(u), str(v)) for n, st, s, e, d, u, v in
+            zip(g["names"], g["status"], g["sizes"], g["enc"], g["dec"], g["uses"], g["vals"])}
+    for name, arr, mz, kw in nodata_cases():
+        st_w, size_w, enc_w, dec_w, uses_w, vals_w = want[name]
+        st, blob = oracle.encode_4d(arr, mz, **kw)
+        assert st == st_w, name
+        if st != 0:
+            continue
+        st, data, mask, uses, vals = oracle.decode_4d(blob)
+        assert st == 0, name
+        assert uses.tobytes().hex() == uses_w and vals.tobytes().hex() == vals_w, name
+        if name in NODATA_FPL_CASES:
+            a = np.ascontiguousarray(arr).reshape(data.shape)
+            valid = np.ones(a.shape[1:3], bool) if mask is None else mask[0].astype(bool)
+            assert np.array_equal(data[0][valid].view(np.uint8), a[0][valid].view(np.uint8)), name
+            continue
+        assert len(blob) == size_w and hashlib.sha256(blob).hexdigest() == enc_w, f"{name}: blob differs from the reference's"
+        h = hashlib.sha256(data.tobytes())
+        if mask is not None:
+            h.update(mask.tobytes())
+        assert h.hexdigest() == dec_w, f"{name}: decoded pixels differ from the reference's"
+        assert oracle.encode_4d(arr, mz, size_only=True, **kw) == (0, len(blob)), name
+        info = oracle.blob_info(blob)[1]
+        has = info["nUsesNoDataValue"] > 0 and info["nDepth"] > 1
+        assert oracle.decode_4d(blob, want_no_data=False)[0] == (5 if has else 0), name      # ErrCode::HasNoData (Lerc.cpp:431-434)
 
 
 def test_bluemarble_reencode_v3_reproduces_the_shipped_blob(oracle):
