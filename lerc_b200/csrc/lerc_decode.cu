@@ -350,7 +350,7 @@ int smCount() {
 // stream's shape is outside what it handles (nothing launched).
 template <class T>
 bool launchDecodeFast(Context* ctx, const HeaderInfo& hd, const uint8_t* dStream, size_t streamLen, void* dData, int* dStatus,
-                      const uint8_t* dBits = nullptr, uint32_t* dBlockOff = nullptr) {
+                      const uint8_t* dBits = nullptr, uint32_t* dBlockOff = nullptr, FastDecArgs* faOut = nullptr) {
   // dBlockOff == nullptr: every pixel valid, decode the pixels too; else (masked raster) only the block offsets are produced
   const bool allValid = (long long)hd.numValidPixel == (long long)hd.nCols * hd.nRows;
   if (hd.nDepth != 1 || hd.microBlockSize != 8 || hd.version < 3 || (dBlockOff == nullptr) != allValid) return false;
@@ -376,6 +376,8 @@ bool launchDecodeFast(Context* ctx, const HeaderInfo& hd, const uint8_t* dStream
   fa.regEntry = (uint32_t*)sp; sp += szEnt;
   fa.nCand = sp;
   fa.status = dStatus;
+  fa.repairReg = -1; fa.repairPos = 0;
+  if (faOut) *faOut = fa;
   static bool attrSet = false;
   if (!attrSet) {
     if (!cudaOk(cudaFuncSetAttribute(k_dec_blocks<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB), "smem attribute")) return false;
@@ -388,6 +390,41 @@ bool launchDecodeFast(Context* ctx, const HeaderInfo& hd, const uint8_t* dStream
   if (dBlockOff) LERC_LAUNCH(ctx, k_dec_offsets<T>, nReg, FD_DWARPS * 32, 0, fa, dBits, dBlockOff);
   else LERC_LAUNCH(ctx, k_dec_blocks<T>, nReg, FD_DWARPS * 32, smemB, fa);
   return cudaOk(cudaGetLastError(), "launch fast decode");
+}
+
+// The speculative decoder gave up because the true chain entered a region at a position that was not among the region's kept
+// candidates (a "candidate flood": long runs of 2-3-byte blocks make hundreds of byte positions parse as block headers that all
+// merge into the true chain).  The true entry of that region is known from the resolve pass, so the region is
+// repaired -- its first sub-chunk is walked from the true entry, closure and composition run again -- and the resolve pass is
+// repeated, region after region, instead of handing the whole stream to the serial walk.  Returns true when the stream was
+// decoded by the block-parallel kernels after all (status word cleared and checked by the caller as usual).
+template <class T>
+bool repairDecodeFast(Context* ctx, FastDecArgs fa, const uint8_t* dBits, uint32_t* dBlockOff, int* dStatus) {
+  cudaStream_t st = ctx->stream;
+  const size_t smemB = fastDecodeBlocksSmem<T>(), smemW = fastDecodeWalkSmem<T>();
+  std::vector<uint32_t> ent(2 * ((size_t)fa.nReg + 1));
+  int lastRepaired = -1;
+  for (int iter = 0; iter < 64; iter++) {
+    int hs = 0;
+    if (!cudaOk(cudaMemcpyAsync(ent.data(), fa.regEntry, ent.size() * 4, cudaMemcpyDeviceToHost, st), "D2H region entries") ||
+        !cudaOk(cudaMemcpyAsync(&hs, dStatus, 4, cudaMemcpyDeviceToHost, st), "D2H") || !cudaOk(cudaStreamSynchronize(st), "sync")) return false;
+    if (iter > 0 && !(hs & DECF_FALLBACK)) {                       // the chain now runs through: decode the blocks
+      if (dBlockOff) LERC_LAUNCH(ctx, k_dec_offsets<T>, fa.nReg, FD_DWARPS * 32, 0, fa, dBits, dBlockOff);
+      else LERC_LAUNCH(ctx, k_dec_blocks<T>, fa.nReg, FD_DWARPS * 32, smemB, fa);
+      return cudaOk(cudaGetLastError(), "launch fast decode (repaired)");
+    }
+    if (!(hs & 32)) return false;                                  // not the resolve pass that gave up
+    int f = -1;
+    for (int r = 1; r <= fa.nReg; r++) if (ent[2 * (size_t)r] == FD_DEAD) { f = r; break; }
+    if (f < 1 || ent[2 * (size_t)(f - 1)] >= FD_DEAD - 1 || f - 1 == lastRepaired) return false;
+    lastRepaired = f - 1;
+    FastDecArgs ra = fa;
+    ra.repairReg = f - 1; ra.repairPos = ent[2 * (size_t)(f - 1)];
+    cudaMemsetAsync(dStatus, 0, 4, st);
+    LERC_LAUNCH(ctx, k_dec_walk<T>, 1, 256, smemW, ra);
+    LERC_LAUNCH(ctx, k_dec_resolve, 1, 1024, 0, fa, fa.nTx * fa.nTy);
+  }
+  return false;
 }
 
 // Parallel Huffman decode (lerc_huffman_fast.cuh) of an all-valid 8-bit band.  Returns 1 when the band was decoded,
@@ -644,13 +681,20 @@ ErrCode decodeBandT(Context* ctx, DecodeBandArgs& a, BandMaskState& ms) {
     }
   }
   // micro-block stream: single-kernel speculative decoder first (lerc_decode_fast.cuh)
-  if (mayFast && launchDecodeFast<T>(ctx, hd, blob + pos, (size_t)hd.blobSize - pos, a.dData, dStatus)) {
+  FastDecArgs fdArgs;
+  if (mayFast && launchDecodeFast<T>(ctx, hd, blob + pos, (size_t)hd.blobSize - pos, a.dData, dStatus, nullptr, nullptr, &fdArgs)) {
     int hs = 0;
     ctx->joinSide();
     if (!cudaOk(cudaMemcpyAsync(&hs, dStatus, 4, cudaMemcpyDeviceToHost, st), "D2H") || !cudaOk(cudaStreamSynchronize(st), "sync")) return Failed;
     if (hs && std::getenv("LERC_B200_VERBOSE")) std::fprintf(stderr, "[lerc_b200] fused decoder status %d\n", hs);
     if (!(hs & DECF_FALLBACK)) { if (hs == 0) globalStats().fastPathDecodes++; return (hs & 7) == 0 ? Ok : Failed; }
     if (hs & 7) return Failed;                                  // e.g. checksum mismatch (bits above DECF_FALLBACK say why the fused decoder gave up)
+    if ((hs & 32) && repairDecodeFast<T>(ctx, fdArgs, nullptr, nullptr, dStatus)) {            // candidate flood: repair the regions the chain could not enter
+      if (!cudaOk(cudaMemcpyAsync(&hs, dStatus, 4, cudaMemcpyDeviceToHost, st), "D2H") || !cudaOk(cudaStreamSynchronize(st), "sync")) return Failed;
+      if (hs && std::getenv("LERC_B200_VERBOSE")) std::fprintf(stderr, "[lerc_b200] fused decoder status after repair %d\n", hs);
+      if (hs == 0) { globalStats().fastPathDecodes++; return Ok; }
+      if (hs & 7) return Failed;
+    }
     cudaMemsetAsync(dStatus, 0, 4, st);
   }
   zeroFill();
@@ -668,12 +712,16 @@ ErrCode decodeBandT(Context* ctx, DecodeBandArgs& a, BandMaskState& ms) {
   // any inconsistency the exact serial walk
   bool haveOffsets = false;
   if (hd.numValidPixel != nPix && !ta.allValidImage && nDepth == 1 &&
-      launchDecodeFast<T>(ctx, hd, ta.stream, (size_t)ta.streamLen, nullptr, dStatus, ms.dBits, ta.blockOff)) {
+      launchDecodeFast<T>(ctx, hd, ta.stream, (size_t)ta.streamLen, nullptr, dStatus, ms.dBits, ta.blockOff, &fdArgs)) {
     int hs = 0;
     ctx->joinSide();
     if (!cudaOk(cudaMemcpyAsync(&hs, dStatus, 4, cudaMemcpyDeviceToHost, st), "D2H") || !cudaOk(cudaStreamSynchronize(st), "sync")) return Failed;
     if (hs && std::getenv("LERC_B200_VERBOSE")) std::fprintf(stderr, "[lerc_b200] speculative block offsets status %d\n", hs);
     if (hs & 7) return Failed;
+    if ((hs & DECF_FALLBACK) && (hs & 32) && repairDecodeFast<T>(ctx, fdArgs, ms.dBits, ta.blockOff, dStatus)) {
+      if (!cudaOk(cudaMemcpyAsync(&hs, dStatus, 4, cudaMemcpyDeviceToHost, st), "D2H") || !cudaOk(cudaStreamSynchronize(st), "sync")) return Failed;
+      if (hs & 7) return Failed;
+    }
     if (!(hs & DECF_FALLBACK)) { haveOffsets = true; globalStats().fastPathDecodes++; }
     else cudaMemsetAsync(dStatus, 0, 4, st);
   }

@@ -51,6 +51,9 @@ struct FastDecArgs {
   FdEntry* regTab;                       // [nReg][FD_CAND]
   uint32_t* regEntry;                    // [nReg + 1][2] true (position, block index) at the start of every region
   int* status;
+  // repair launch of k_dec_walk (one CTA): the true chain enters region repairReg at stream position repairPos, which the
+  // head-window speculation did not keep among the region's candidates (candidate flood); -1 = normal launch
+  int repairReg; uint32_t repairPos;
 };
 
 // ---- unit header ---------------------------------------------------------------------------------
@@ -322,7 +325,7 @@ __global__ void __launch_bounds__(256) k_dec_walk(FastDecArgs a) {
   extern __shared__ __align__(16) uint8_t sReg[];                    // the region's bytes: FD_REG * FD_SUB + look-ahead
   constexpr int MAXU = 1 + 64 * (int)sizeof(T);
   constexpr int AHEAD = ((MAXU + 64 + 15) / 16) * 16;
-  const int reg = blockIdx.x, tid = threadIdx.x;
+  const int reg = a.repairReg >= 0 ? a.repairReg : (int)blockIdx.x, tid = threadIdx.x;
   const int sub0 = reg * a.subPerReg, nLocal = max(0, min(a.nSub, sub0 + a.subPerReg) - sub0);
   const int version = a.version;
   const int tailRaw = 1 + (a.nRows - (a.nTy - 1) * 8) * (a.nCols - (a.nTx - 1) * 8) * (int)sizeof(T);
@@ -342,6 +345,22 @@ __global__ void __launch_bounds__(256) k_dec_walk(FastDecArgs a) {
   }
   __syncthreads();
   const uint32_t* words = (const uint32_t*)sReg;
+  (void)words;
+  if (a.repairReg >= 0) {
+    // repair launch: the tables of this region exist; the true entry of the region is walked into a free slot of the first
+    // sub-chunk, then closure and composition below run again
+    for (int it = tid; it < nLocal * FD_CAND; it += blockDim.x) sTab[it] = a.subTab[(size_t)sub0 * FD_CAND + it];
+    __syncthreads();
+    if (tid == 0 && nLocal > 0 && a.repairPos >= (uint32_t)sub0 * FD_SUB && a.repairPos < (uint32_t)(sub0 + 1) * FD_SUB) {
+      bool have = false; int slot = -1;
+      for (int e2 = 0; e2 < FD_CAND; e2++) { const uint32_t en = sTab[e2].entry; have |= en == a.repairPos; if (en == FD_DEAD && slot < 0) slot = e2; }
+      FdEntry w;
+      if (!have && slot >= 0 &&
+          fdWalkChain<T>(a, sReg, d, sub0, (int)(a.repairPos - (uint32_t)sub0 * FD_SUB), version, tailRaw, a.lens + ((size_t)sub0 * FD_CAND + slot) * FD_LENS, w)) {
+        sTab[slot] = w; a.subTab[(size_t)sub0 * FD_CAND + slot] = w;
+      }
+    }
+  } else
   for (int it = tid; it < nLocal * FD_CAND; it += blockDim.x) {
     const int ls = it / FD_CAND, j = it - ls * FD_CAND, s = sub0 + ls;
     FdEntry e; e.entry = FD_DEAD; e.exit = 0; e.count = 0;
@@ -361,7 +380,7 @@ __global__ void __launch_bounds__(256) k_dec_walk(FastDecArgs a) {
   // the 16 exits of the previous one.
   // quick parallel check first (one warp per pair of neighbouring sub-chunks); the sequential pass runs only if something is missing
   __shared__ int sMissing;
-  if (tid == 0) sMissing = 0;
+  if (tid == 0) sMissing = a.repairReg >= 0 ? 1 : 0;
   __syncthreads();
   for (int ls = 1 + (tid >> 5); ls < nLocal; ls += blockDim.x >> 5) {
     const int lane = tid & 31, s = sub0 + ls;

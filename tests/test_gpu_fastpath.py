@@ -114,3 +114,35 @@ def test_flat_regions_stay_on_the_parallel_decoder(libs):
         assert t_p == 0 and np.array_equal(d_p.view(np.uint8), d_o.view(np.uint8)), name
         if must_be_fast:
             assert after[4] == before[4] + 1, f"{name}: parallel decoder was not taken"
+
+
+@pytest.mark.parametrize("kind", ["one_band", "six_bands", "masked_band"])
+def test_candidate_flood_is_repaired_not_serialised(libs, kind):
+    """Flat rows between noisy ones: thousands of 2-byte const blocks make hundreds of byte positions of a region's head window
+    parse as block headers, the true entry is not among the kept candidates, and the resolve pass cannot enter the region.
+    The decoder must repair those regions (k_dec_walk repair launch + another resolve pass) and stay on the block-parallel
+    kernels instead of handing the stream to the serial walk."""
+    import lerc_b200
+    prod, orc = libs
+    h, w = 1536, 2048
+    img = c2_raster(h, w)
+    mask = None
+    if kind == "one_band":
+        img[h // 3:2 * h // 3, :] = 77.0
+    elif kind == "six_bands":
+        for k in range(6):
+            img[k * 256 + 100:k * 256 + 180, :] = float(k) * 3 + 1
+    else:
+        img[500:1100, :] = 9.0
+        mask = np.ones((h, w), np.uint8)
+        mask[10:50, 10:200] = 0
+    s_o, blob, _ = orc.encode(img, 0.01, mask=mask)
+    assert s_o == 0
+    before = lerc_b200.stats()
+    t_p, d_p, m_p = prod.decode(blob)
+    after = lerc_b200.stats()
+    t_o, d_o, m_o = orc.decode(blob)
+    assert t_p == 0 and t_o == 0 and np.array_equal(d_p.view(np.uint8), d_o.view(np.uint8))
+    assert m_o is None or np.array_equal(m_o, m_p)
+    assert after[4] == before[4] + 1, "the speculative decoder fell back to the serial walk"
+    assert after[0] - before[0] <= 24, "more launches than a few region repairs need"
