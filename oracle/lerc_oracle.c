@@ -592,6 +592,106 @@ static int trie_build(trie* t, const uint16_t* len, const u32* code, int size) {
 }
 
 /* ------------------------------------------------------------------------------------------- */
+/* Lossless float / double codec "FPL" (IEM_DeltaDeltaHuffman), DECODE side.
+ * fpl_Lerc2Ext.cpp:725-866 (DecodeHuffmanFlt[Slice]), :133-169 (restoreSequence), :612-722 (restoreCrossBytes / restoreByteOrder);
+ * fpl_EsriHuffman.cpp:37-75 (decodePackBits), :453-558 (DecodeHuffman); fpl_UnitTypes.cpp:40-63, :98-111, :140-156, :626-735, :775-888.
+ * The whole array is coded (invalid pixels included), one byte plane of the (bit-transformed) values at a time. */
+static int fpl_plane_decode(const u8* p, size_t size, u8* out, size_t n) {
+  if (size < 1) return 0;
+  switch (p[0]) {
+    case 1: {                                             /* HUFFMAN_RLE: one value */
+      if (size < 6) return 0;
+      u32 cnt; memcpy(&cnt, p + 2, 4);
+      if ((size_t)cnt != n) return 0;
+      memset(out, p[1], n);
+      return 1;
+    }
+    case 2:                                               /* HUFFMAN_NO_ENCODING */
+      if (size < 1 + n) return 0;
+      memcpy(out, p + 1, n);
+      return 1;
+    case 3: {                                             /* HUFFMAN_PACKBITS */
+      size_t cur = 0, i = 1;
+      while (i < size) {
+        int b = p[i++];
+        if (b <= 127) { size_t c = (size_t)b + 1; if (cur + (size_t)b >= n || i + c > size) return 0; memcpy(out + cur, p + i, c); cur += c; i += c; }
+        else { size_t c = (size_t)b - 127 + 1; if (cur + (size_t)b - 127 >= n || i >= size) return 0; memset(out + cur, p[i], c); cur += c; i++; }
+      }
+      return cur == n;
+    }
+    case 0: {                                             /* HUFFMAN_NORMAL: code table (bit stuffed like codec version >= 3) + MSB-first bit stream */
+      uint16_t len[256]; u32 code[256]; int sz = 0;
+      size_t tb = huff_read_table(p + 1, size - 1, len, code, &sz, 5);
+      if (!tb) return 0;
+      const u8* q = p + 1 + tb; size_t avail = size - 1 - tb;
+      trie* t = (trie*)malloc(sizeof(trie));
+      if (!trie_build(t, len, code, sz)) { free(t); return 0; }
+      u64 pos = 0, nBits = (u64)(avail / 4) * 32;
+      int ok = 1;
+      for (size_t m = 0; m < n && ok; m++) {
+        int cur = 0;
+        while (t->n[cur].sym < 0) {
+          if (pos >= nBits) { ok = 0; break; }
+          int nx = t->n[cur].kid[msb_get(q, pos++)];
+          if (nx < 0) { ok = 0; break; }
+          cur = nx;
+        }
+        if (ok) out[m] = (u8)t->n[cur].sym;
+      }
+      free(t);
+      return ok;
+    }
+    default: return 0;
+  }
+}
+
+static u32 fpl_add32(u32 a, u32 b) { return ((a + b) & 0x007FFFFFu) | (((((a >> 23) & 0x1FF) + ((b >> 23) & 0x1FF)) & 0x1FF) << 23); }
+static u64 fpl_add64(u64 a, u64 b) { return ((a + b) & 0x000FFFFFFFFFFFFFull) | (((((a >> 52) & 0xFFF) + ((b >> 52) & 0xFFF)) & 0xFFF) << 52); }
+
+/* One slice of cols x rows units.  Returns the number of bytes consumed, 0 on failure. */
+static size_t fpl_decode_slice(const u8* p, size_t avail, void* data, int isDouble, size_t cols, size_t rows) {
+  const u8* p0 = p;
+  const size_t unit = isDouble ? 8 : 4, n = cols * rows;
+  if (avail < 1 || n == 0) return 0;
+  const int pred = *p++; avail--;
+  if (pred > 2) return 0;
+  u8* planes = (u8*)malloc(n * unit);
+  int ok = 1;
+  u8* asm_ = (u8*)data;
+  for (size_t b = 0; b < unit && ok; b++) {
+    if (avail < 6) { ok = 0; break; }
+    u8 idx = p[0], level = p[1]; u32 csize; memcpy(&csize, p + 2, 4);
+    p += 6; avail -= 6;
+    if (idx >= unit || level > 5 || avail < csize) { ok = 0; break; }
+    u8* pl = planes + b * n;
+    if (!fpl_plane_decode(p, csize, pl, n)) { ok = 0; break; }
+    p += csize; avail -= csize;
+    for (int l = level; l > 0; l--) for (size_t i = (size_t)l; i < n; i++) pl[i] = (u8)(pl[i] + pl[i - 1]);     /* restoreSequence */
+    for (size_t i = 0; i < n; i++) asm_[i * unit + idx] = pl[i];
+  }
+  free(planes);
+  if (!ok) return 0;
+  const int delta = pred == 1 ? 1 : (pred == 2 ? 2 : 0);
+  if (!isDouble) {
+    u32* d = (u32*)data;
+    if (pred == 2) for (size_t c = 0; c < cols; c++) for (size_t r = 1; r < rows; r++) d[r * cols + c] = fpl_add32(d[r * cols + c], d[(r - 1) * cols + c]);
+    if (delta > 0) for (size_t r = 0; r < rows; r++) for (size_t i = 1; i < cols; i++) d[r * cols + i] = fpl_add32(d[r * cols + i], d[r * cols + i - 1]);
+    for (size_t i = 0; i < n; i++) { u32 a = d[i]; d[i] = (a & 0x007FFFFFu) | (((a >> 24) & 0xFF) << 23) | (((a >> 23) & 1u) << 31); }   /* undo_moveBits2Front */
+  } else {
+    u64* d = (u64*)data;
+    if (pred == 2) for (size_t c = 0; c < cols; c++) for (size_t r = 1; r < rows; r++) d[r * cols + c] = fpl_add64(d[r * cols + c], d[(r - 1) * cols + c]);
+    if (delta > 0) for (size_t r = 0; r < rows; r++) for (size_t i = 1; i < cols; i++) d[r * cols + i] = fpl_add64(d[r * cols + i], d[r * cols + i - 1]);
+  }
+  return (size_t)(p - p0);
+}
+
+/* fpl_Lerc2Ext.cpp:725-736: nDepth > 1 is one slice of nDepth columns and nCols * nRows rows */
+static size_t fpl_decode(const u8* p, size_t avail, void* data, int isDouble, int nCols, int nRows, int nDepth) {
+  if (nDepth == 1) return fpl_decode_slice(p, avail, data, isDouble, (size_t)nCols, (size_t)nRows);
+  return fpl_decode_slice(p, avail, data, isDouble, (size_t)nDepth, (size_t)nCols * (size_t)nRows);
+}
+
+/* ------------------------------------------------------------------------------------------- */
 /* shared helpers of the typed code                                                               */
 
 static int mask_bit(const u8* bits, int64_t k) { return (bits[k >> 3] & (0x80 >> (k & 7))) != 0; }

@@ -170,3 +170,30 @@ def nodata_cases(seed=11):
     add("u8_d3_nodata_out_of_range", u8, 0, n_depth=3, uses_no_data=[1], no_data=[300.0])              # WrongParam
     add("f32_d3_all_nodata", np.full((h, w, 3), -5.0, np.float32), 0.01, n_depth=3, uses_no_data=[1], no_data=[-5.0])
     return cases
+
+
+def fpl_cases(seed=21):
+    """(name, array, kwargs) of float rasters for maxZError = 0: the reference codes these with its lossless FPL codec
+    (IEM_DeltaDeltaHuffman, fpl_*.cpp) when that is >= 10 % smaller than raw blocks.  Used for DECODE parity: the blobs the
+    reference makes from them are committed in tests/golden/fpl_ref.npz."""
+    rng = np.random.default_rng(seed)
+    f = c2_raster(97, 131)
+    cases = [("f32_noisy", f, {}), ("f64_noisy", f.astype(np.float64) * 1.0000001, {}),
+             ("f32_smooth", smooth_field(80, 133).astype(np.float32), {}),
+             ("f32_const_rows", np.repeat(rng.random((60, 1)).astype(np.float32), 90, 1), {}),
+             ("f32_const_cols", np.repeat(rng.random((1, 90)).astype(np.float32), 60, 0), {})]
+    m = np.ones((97, 131), np.uint8)
+    m[20:60, 30:100] = 0
+    cases.append(("f32_masked", f, {"mask": m}))
+    fn = f.copy()
+    fn[10:20, 10:50] = np.nan
+    cases.append(("f32_nan", fn, {}))
+    cases.append(("f32_depth3", (c4_raster(40, 50).astype(np.float32) * np.float32(1.37)), {"n_depth": 3}))
+    cases.append(("f64_depth2", rng.random((30, 40, 2)), {"n_depth": 2}))
+    cases.append(("f32_3bands", np.stack([f, f * 2, f + 5]), {"n_bands": 3}))
+    cases.append(("f32_eighths", (np.round(f * 8) / 8).astype(np.float32), {}))
+    cases.append(("f32_huge_noise", (rng.random((64, 70)) * 1e30).astype(np.float32), {}))
+    cases.append(("f32_one_row", f[:1, :].copy(), {}))
+    cases.append(("f32_one_col", f[:, :1].copy(), {}))
+    cases.append(("f32_big", c2_raster(300, 517), {}))
+    return cases

@@ -19,7 +19,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
 from lercapi import ref_lib  # noqa: E402
-from cases import all_cases, nodata_cases  # noqa: E402
+from cases import all_cases, fpl_cases, nodata_cases  # noqa: E402
 
 REF = "/root/reference"
 
@@ -101,6 +101,20 @@ def main():
     np.savez_compressed(os.path.join(HERE, "nodata_ref.npz"), names=np.array(names), status=np.array(status), sizes=np.array(sizes),
                         enc=np.array(enc), dec=np.array(dec), uses=np.array(uses), vals=np.array(vals))
     print("noData cases:", len(names))
+    # lossless float: the blobs the reference makes with its FPL codec (decode parity; the blobs themselves are the fixtures)
+    out = {}
+    for name, arr, kw in fpl_cases():
+        st, blob, _ = ref.encode(arr, 0, **kw)
+        assert st == 0
+        st, data, mask = ref.decode(blob)
+        assert st == 0
+        h = hashlib.sha256(data.tobytes())
+        if mask is not None:
+            h.update(mask.tobytes())
+        out["blob_" + name] = np.frombuffer(blob, np.uint8)
+        out["hash_" + name] = np.array(h.hexdigest())
+    np.savez_compressed(os.path.join(HERE, "fpl_ref.npz"), **out)
+    print("FPL cases:", len(out) // 2)
 
 
 if __name__ == "__main__":

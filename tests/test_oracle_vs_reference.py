@@ -12,7 +12,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from cases import all_cases, nodata_cases
+from cases import all_cases, fpl_cases, nodata_cases
 from lercapi import ROOT, oracle_lib, ref_lib
 
 GOLD = os.path.join(ROOT, "tests", "golden")
@@ -154,6 +154,23 @@ def test_nodata_4d_hashes(oracle):
         info = oracle.blob_info(blob)[1]
         has = info["nUsesNoDataValue"] > 0 and info["nDepth"] > 1
         assert oracle.decode_4d(blob, want_no_data=False)[0] == (5 if has else 0), name      # ErrCode::HasNoData (Lerc.cpp:431-434)
+
+
+def test_fpl_blobs_decode_like_the_reference(oracle):
+    """blobs made by the reference's lossless float codec (IEM_DeltaDeltaHuffman, fpl_*.cpp): the oracle's decode hashes to the
+    reference's (fpl_ref.npz), invalid pixels included, and equals the input on the valid pixels"""
+    g = np.load(os.path.join(GOLD, "fpl_ref.npz"))
+    n_fpl = 0
+    for name, arr, kw in fpl_cases():
+        blob = g["blob_" + name].tobytes()
+        st, data, mask = oracle.decode(blob)
+        assert st == 0, name
+        h = hashlib.sha256(data.tobytes())
+        if mask is not None:
+            h.update(mask.tobytes())
+        assert h.hexdigest() == str(g["hash_" + name]), f"{name}: decoded pixels differ from the reference's"
+        n_fpl += b"\x03" in blob[90:140]           # (the image-mode byte 3 sits right behind header, mask count and ranges)
+    assert n_fpl >= 10
 
 
 def test_bluemarble_reencode_v3_reproduces_the_shipped_blob(oracle):
