@@ -531,6 +531,12 @@ int decodeHuffmanFast(Context* ctx, const HuffmanTable& t, const uint8_t* dStrea
   return 1;
 }
 
+}  // namespace
+}  // namespace lerc
+#include "lerc_fpl_decode.cuh"
+namespace lerc {
+namespace {
+
 template <class T>
 ErrCode decodeBandT(Context* ctx, DecodeBandArgs& a, BandMaskState& ms) {
   const HeaderInfo& hd = a.hd;
@@ -677,7 +683,14 @@ ErrCode decodeBandT(Context* ctx, DecodeBandArgs& a, BandMaskState& ms) {
         }
         LERC_LAUNCH(ctx, k_huffman_decode_seq<T>, 1, 32, 0, ha);
         return finish();
-      } else return Failed;                      // FPL lossless-float blobs (mode 3): not implemented (DESIGN.md "Deviations")
+      } else if constexpr (PixelTraits<T>::isFloat) {
+        // the reference's lossless float codec (fpl_*.cpp; lerc_fpl_decode.cuh): codes the whole array, invalid pixels included
+        if (!(hd.tryHuffmanFlt() && mode == IEM_DeltaDeltaHuffman)) return Failed;                                   // Lerc2.cpp:674-680
+        const ErrCode fe = decodeFpl<T>(ctx, [&](size_t o, size_t len, void* dst) { return src.fetch(o, len, dst); }, blob, pos, (size_t)hd.blobSize,
+                                        hd.nCols, hd.nRows, nDepth, a.dData, dStatus);
+        if (fe != Ok) return fe;
+        return finish();
+      } else return Failed;
     }
   }
   // micro-block stream: single-kernel speculative decoder first (lerc_decode_fast.cuh)

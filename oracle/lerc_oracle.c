@@ -639,6 +639,9 @@ static int fpl_plane_decode(const u8* p, size_t size, u8* out, size_t n) {
         if (ok) out[m] = (u8)t->n[cur].sym;
       }
       free(t);
+      /* like the 8-bit Huffman path (Lerc2.cpp:2583-2587): the data words plus the read-ahead word must be there.  The reference's
+       * FPL reader does not check this (it would read past the plane on corrupted input); the oracle and the product do. */
+      if (ok && avail < 4 * (((pos & 31) ? 1 : 0) + (size_t)(pos >> 5) + 1)) ok = 0;
       return ok;
     }
     default: return 0;

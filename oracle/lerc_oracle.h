@@ -16,9 +16,9 @@
  * Scope: Lerc2 writer and reader for codec versions 2..6 (2..5 = Lerc::EncodeInternal_v5; version 2 with
  * its MSB-first bit stuffing and no checksum); tiling, one-sweep raw, const image, RLE bit mask, per-depth ranges,
  * depth-delta blocks, LUT blocks, 8-bit Huffman / delta-Huffman, Fletcher-32, multi-band concatenation, the _4D calls with
- * per-band noData values (FilterNoDataAndNaN / FilterNoData / RemapNoData).  Not restated (SURVEY 8f "next"): the
- * lossless-float FPL codec (maxZError == 0 float/double blobs are written as raw/const micro-blocks, which every Lerc2
- * reader decodes; FPL blobs are rejected on decode), the integer bit-plane mode, Lerc1.
+ * per-band noData values (FilterNoDataAndNaN / FilterNoData / RemapNoData), the DECODER of the lossless-float FPL codec.
+ * Not restated (SURVEY 8f "next"): the FPL encoder (maxZError == 0 float/double blobs are written as raw/const micro-blocks,
+ * which every Lerc2 reader decodes), the integer bit-plane mode, Lerc1.
  *
  * The exported functions use the reference C API's argument lists (src/LercLib/include/Lerc_c_api.h:126-380)
  * with an `lo_` prefix so one ctypes binding drives all three libraries.

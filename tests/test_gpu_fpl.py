@@ -1,0 +1,69 @@
+"""GPU tests (-m gpu): decoding blobs written by the reference's lossless float codec (FPL, image mode IEM_DeltaDeltaHuffman,
+fpl_*.cpp; product: lerc_b200/csrc/lerc_fpl_decode.cuh).  The blobs are the reference's own output for tests/cases.py:fpl_cases
+(committed in tests/golden/fpl_ref.npz with the hash of what the reference decodes); the oracle's decoder is pinned to those
+hashes by tests/test_oracle_vs_reference.py::test_fpl_blobs_decode_like_the_reference."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from cases import fpl_cases
+from lercapi import ROOT, oracle_lib, product_lib
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(ROOT, "tests", "golden")
+CASES = fpl_cases()
+
+
+@pytest.fixture(scope="module")
+def libs():
+    prod, orc = product_lib(), oracle_lib()
+    assert prod is not None and orc is not None
+    return prod, orc
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_fpl_blob_decodes_like_reference(libs, case):
+    prod, orc = libs
+    name, arr, kw = case
+    g = np.load(os.path.join(GOLD, "fpl_ref.npz"))
+    blob = g["blob_" + name].tobytes()
+    st, data, mask = prod.decode(blob)
+    assert st == 0
+    h = hashlib.sha256(data.tobytes())
+    if mask is not None:
+        h.update(mask.tobytes())
+    assert h.hexdigest() == str(g["hash_" + name]), "decoded pixels differ from the reference's"
+    t_o, d_o, m_o = orc.decode(blob)
+    assert t_o == 0 and np.array_equal(d_o.view(np.uint8), data.view(np.uint8))
+    # lossless: the valid pixels are the input, bit for bit (NaN pixels were moved to the mask by the encoder)
+    a = np.ascontiguousarray(arr).reshape(data.shape)
+    for b in range(data.shape[0]):
+        valid = np.ones(data.shape[1:3], bool) if mask is None else mask[b if mask.shape[0] > 1 else 0].astype(bool)
+        assert np.array_equal(data[b][valid].view(np.uint8), a[b][valid].view(np.uint8))
+
+
+def test_corrupted_fpl_blobs_fail_like_the_oracle(libs):
+    """(the reference's FPL reader has no bound checks on the plane streams -- it accepts all of these and may read past the
+    plane; the oracle and the product apply the 8-bit Huffman path's rules and agree with each other)"""
+    prod, orc = libs
+    g = np.load(os.path.join(GOLD, "fpl_ref.npz"))
+    blob = bytearray(g["blob_f32_noisy"].tobytes())
+    rng = np.random.default_rng(5)
+    import ctypes as C
+    fl = orc.lib.lo_fletcher32
+    fl.restype = C.c_uint32
+    fl.argtypes = [C.c_void_p, C.c_int]
+    for _ in range(40):
+        bad = bytearray(blob)
+        k = int(rng.integers(110, len(bad) - 8))
+        bad[k] ^= int(rng.integers(1, 256))
+        buf = np.frombuffer(bytes(bad), np.uint8).copy()
+        cs = fl(buf[14:].ctypes.data, len(bad) - 14)                       # repair the checksum so that the FPL parser is reached
+        buf[10:14] = np.frombuffer(np.uint32(cs).tobytes(), np.uint8)
+        s_o, d_o, _ = orc.decode(buf.tobytes())
+        s_p, d_p, _ = prod.decode(buf.tobytes())
+        assert (s_p == 0) == (s_o == 0), f"byte {k}: status {s_p} vs oracle {s_o}"
+        if s_o == 0:
+            assert np.array_equal(d_p.view(np.uint8), d_o.view(np.uint8))

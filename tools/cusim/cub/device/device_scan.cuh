@@ -11,5 +11,13 @@ struct DeviceScan {
     for (int i = 0; i < n; i++) { V v = (V)in[i]; out[i] = run; run = (V)(run + v); }
     return cudaSuccess;
   }
+  template <class In, class Out>
+  static cudaError_t InclusiveSum(void* tmp, size_t& tmpBytes, In in, Out out, int n, cudaStream_t = nullptr) {
+    if (!tmp) { tmpBytes = 16; return cudaSuccess; }
+    using V = std::remove_reference_t<decltype(out[0])>;
+    V run = 0;
+    for (int i = 0; i < n; i++) { run = (V)(run + (V)in[i]); out[i] = run; }
+    return cudaSuccess;
+  }
 };
 }  // namespace cub
