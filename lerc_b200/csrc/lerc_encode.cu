@@ -648,6 +648,7 @@ __global__ void k_one_sweep_gather(const T* __restrict__ data, const uint8_t* __
 
 }  // namespace lerc
 #include "lerc_encode_fast.cuh"
+#include "lerc_encode_pipe.cuh"
 namespace lerc {
 
 // =================================================================================================
@@ -720,7 +721,19 @@ bool encodeBandFast(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
   fa.groupState = (groupLb && ctaTiles) ? fa.tileState + nTiles : nullptr;
   constexpr int MAXB = 1 + 64 * (int)sizeof(T);
   int dev = 0, sms = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (ctaTiles) {
+  static const bool pipeEnc = [] { const char* e = std::getenv("LERC_B200_ENC"); return e && std::strcmp(e, "pipe") == 0; }();
+  if (pipeEnc) {
+    // experimental: look-back deferred by one tile and done by every warp, one barrier per tile (lerc_encode_pipe.cuh)
+    const size_t smem = (size_t)((FAST_TB * MAXB + 15) / 16 + 3) * 16 * 3 + 256 * 8 * sizeof(T);       // three staging images + the general path's pixel rows
+    fa.groupState = fa.tileState + nTiles;
+    static int ctasPerSm = 0;
+    if (!ctasPerSm) {
+      cudaFuncSetAttribute(k_encode_pipe<T, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSm, k_encode_pipe<T, 4>, 256, smem) != cudaSuccess || ctasPerSm < 1) ctasPerSm = 1;
+    }
+    const long long grid = std::min<long long>(nTiles, (long long)ctasPerSm * std::max(sms, 1));     // all CTAs co-resident (look-back)
+    LERC_LAUNCH(ctx, (k_encode_pipe<T, 4>), (unsigned)grid, 256, smem, fa);
+  } else if (ctaTiles) {
     const size_t smem = (size_t)((FAST_TB * MAXB + 15) / 16 + 3) * 16 * 2 + 256 * 8 * sizeof(T);       // two staging images + the general path's pixel rows
     static const int occ = [] { const char* e = std::getenv("LERC_B200_ENC_OCC"); const int v = e ? std::atoi(e) : 4; return (v == 5 || v == 6) ? v : 4; }();
     auto launch = [&](auto kernel) {
