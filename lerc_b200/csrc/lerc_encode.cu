@@ -136,6 +136,53 @@ __global__ void k_stats_finish(const T* __restrict__ data, int nDepth, StatsBuff
 // value on a coarser grid is also on every finer one (each factor divides the next), where its rounding
 // distance is 0.  So the per-candidate maximum over ALL valid values equals the reference's bookkeeping, and
 // row-wise pruning only removes candidates whose final maximum would fail anyway.
+// bit-plane mode (Lerc2::TryBitPlaneCompression, Lerc2.cpp:1071-1229): per bit plane, how often do horizontally / vertically
+// neighbouring valid pixels differ in that bit?  grid.y = depth; counts[depth * 32 + plane], pairs = number of neighbour pairs.
+// allValid1: the reference's special case (nDepth == 1, every pixel valid) leaves out the last row and the last column.
+template <class T>
+__global__ void k_bitplane_counts(const T* __restrict__ data, const uint8_t* __restrict__ bits, int nRows, int nCols, int nDepth, int allValid1,
+                                  unsigned long long* __restrict__ counts, unsigned long long* __restrict__ pairs) {
+  constexpr int NB = 8 * (int)sizeof(T);
+  const int m = blockIdx.y;
+  unsigned int c[NB];
+#pragma unroll
+  for (int s = 0; s < NB; s++) c[s] = 0;
+  unsigned long long np = 0;
+  const long long nPix = (long long)nRows * nCols;
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < nPix; k += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(k / nCols), j = (int)(k - (long long)i * nCols);
+    bool hori, vert;
+    if (allValid1) { hori = vert = (i < nRows - 1 && j < nCols - 1); }
+    else {
+      const bool v = !bits || maskBit(bits, k);                       // bits == nullptr: every pixel valid (nDepth > 1)
+      hori = v && j < nCols - 1 && (!bits || maskBit(bits, k + 1));
+      vert = v && i < nRows - 1 && (!bits || maskBit(bits, k + nCols));
+    }
+    const long long m0 = k * nDepth + m;
+    const uint32_t x = (uint32_t)(long long)data[m0];
+    if (hori) {
+      const uint32_t d = x ^ (uint32_t)(long long)data[m0 + nDepth];
+#pragma unroll
+      for (int s = 0; s < NB; s++) c[s] += (d >> s) & 1u;
+      np++;
+    }
+    if (vert) {
+      const uint32_t d = x ^ (uint32_t)(long long)data[m0 + (long long)nDepth * nCols];
+#pragma unroll
+      for (int s = 0; s < NB; s++) c[s] += (d >> s) & 1u;
+      np++;
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < NB; s++) {
+    unsigned int v = c[s];
+    for (int sh = 16; sh; sh >>= 1) v += __shfl_xor_sync(FULL, v, sh);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(&counts[(size_t)m * 32 + s], (unsigned long long)v);
+  }
+  for (int sh = 16; sh; sh >>= 1) np += __shfl_xor_sync(FULL, np, sh);
+  if (m == 0 && (threadIdx.x & 31) == 0 && np) atomicAdd(pairs, np);
+}
+
 // codec versions 2..5: NaN -> -FLT_MAX / -DBL_MAX (Lerc::ReplaceNaNValues, Lerc.cpp:906-930); pixels whose depths are all NaN
 // were already made invalid by k_mask_build, their values no longer matter
 template <class T>
@@ -658,6 +705,42 @@ namespace {
 
 template <class V> bool d2h(Context* ctx, V* hostDst, const void* dSrc, size_t count);
 
+// Lerc2::TryBitPlaneCompression (Lerc2.cpp:1071-1229): device counts, the reference's decision in double precision on the host
+template <class T>
+bool tryBitPlane(Context* ctx, const T* dData, const uint8_t* dBitsOrNull, int nRows, int nCols, int nDepth, int numValid, double eps, double& newMaxZErr) {
+  newMaxZErr = 0;
+  constexpr int maxShift = 8 * (int)sizeof(T), minCnt = 5000;
+  if (eps <= 0 || numValid < minCnt) return false;
+  const size_t nCounts = (size_t)nDepth * 32 + 1;
+  unsigned long long* dCounts = (unsigned long long*)ctx->arena.alloc(nCounts * 8);
+  if (!dCounts) return false;
+  cudaMemsetAsync(dCounts, 0, nCounts * 8, ctx->stream);
+  const long long nPix = (long long)nRows * nCols;
+  const int allValid1 = (nDepth == 1 && !dBitsOrNull) ? 1 : 0;
+  const dim3 grid((unsigned)std::max<long long>(1, std::min<long long>((nPix + 255) / 256, 148 * 8)), (unsigned)nDepth);
+  LERC_LAUNCH(ctx, k_bitplane_counts<T>, grid, 256, 0, dData, dBitsOrNull, nRows, nCols, nDepth, allValid1, dCounts, dCounts + (nCounts - 1));
+  std::vector<unsigned long long> h(nCounts);
+  if (!d2h(ctx, h.data(), dCounts, nCounts)) return false;
+  const unsigned long long cnt = h[nCounts - 1];
+  if (cnt < (unsigned long long)minCnt) return false;
+  int nCutFound = 0, lastPlaneKept = 0;
+  for (int s = maxShift - 1; s >= 0; s--) {
+    bool crit = true;
+    for (int d = 0; d < nDepth; d++) {
+      const double x = (double)h[(size_t)d * 32 + s], n = (double)cnt, m = x / n;
+      if (std::fabs(1 - 2 * m) >= eps) crit = false;
+    }
+    if (crit && nCutFound < 2) {
+      if (nCutFound == 0) lastPlaneKept = s;
+      if (nCutFound == 1 && s < lastPlaneKept - 1) { lastPlaneKept = s; nCutFound = 0; }
+      nCutFound++;
+    }
+  }
+  lastPlaneKept = std::max(0, lastPlaneKept);
+  newMaxZErr = (double)((1 << lastPlaneKept) >> 1);
+  return true;
+}
+
 // Single-pass encoder (lerc_encode_fast.cuh).  Returns true when the band was written (or a definite error is
 // in `err`); false when one of its assumptions did not hold and the general encoder must run instead.
 template <class T>
@@ -665,7 +748,7 @@ bool encodeBandFast(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
   constexpr bool isFlt = PixelTraits<T>::isFloat;
   using K = typename PixelTraits<T>::Key;
   if (sizeof(T) == 1 || a.nDepth != 1 || a.dValidBytes || a.anyMaskModified || !a.dOut || a.version != 6) return false;
-  if (std::getenv("LERC_B200_NO_FAST")) return false;
+  if (std::getenv("LERC_B200_NO_FAST") || a.maxZErr == 777) return false;     // 777: bit-plane mode (general path)
   double maxZErr = a.maxZErr;
   if (isFlt) { if (!(maxZErr > 0)) return false; }                    // float lossless: FPL / raw decisions stay in the general path
   else maxZErr = std::max(0.5, std::floor(maxZErr));                   // Lerc2.cpp:219
@@ -945,6 +1028,7 @@ ErrCode encodeBandT(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
   bool constImage = false, allDepthsConst = false;
 
   if (numValid == 0) {
+    if (maxZErr == 777 && (!isFlt || a.version < 6)) { if (isFlt) return Failed; maxZErr = 0; }   // cheat code without enough data: lossless (Lerc2.cpp:210-224)
     if (!isFlt) maxZErr = std::max(0.5, std::floor(maxZErr));
     else if (a.version >= 6) maxZErr = 0;                 // codec version 6 only: the noData / NaN filter resets it for an empty band (Lerc.cpp:1378-1552)
     hd.maxZError = maxZErr; hd.blobSize = (int)headMask;
@@ -960,6 +1044,7 @@ ErrCode encodeBandT(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
       if (a.version < 6) allInt = false;                                                     // the all-integer rule came with codec version 6 (Lerc.cpp:1490-1502)
       if (allInt) maxZErr = std::max(0.5, std::floor(maxZErr));
       hd.bIsInt = allInt ? 1 : 0;
+      if (maxZErr == 777) return Failed;                                                      // the bit-plane "cheat code" is refused for float types (Lerc2.cpp:210-224)
       if (maxZErr > 0) {                                                                      // Lerc2.cpp:226-231
         static const double kErr[9] = {1, 0.5, 0.1, 0.05, 0.01, 0.005, 0.001, 0.0005, 0.0001};
         static const double kFac[9] = {1, 2, 10, 20, 100, 200, 1000, 2000, 10000};
@@ -984,6 +1069,13 @@ ErrCode encodeBandT(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
         if (pass(0, 1) && (a.nRows == 1 || pass(1, a.nRows))) maxZErr = err[0];
       }
     } else {
+      if constexpr (!isFlt) {
+        if (maxZErr == 777) {                                                                 // bit-plane mode (Lerc2.cpp:210-217, :1071-1229)
+          double nz = 0;
+          if (!tryBitPlane<T>(ctx, (const T*)a.dData, dBitsOrNull, a.nRows, a.nCols, nDepth, numValid, 0.01, nz)) nz = 0;
+          maxZErr = nz;
+        }
+      }
       maxZErr = std::max(0.5, std::floor(maxZErr));                                          // Lerc2.cpp:219
     }
     hd.maxZError = maxZErr; hd.zMin = zMin; hd.zMax = zMax;

@@ -148,7 +148,7 @@ ErrCode encodeOneTile(Context* ctx, const TilesGeom& g, const void* dData, doubl
 
 template <class T>
 bool tilesFastEligible(const TilesGeom& g, double maxZErr) {
-  if (sizeof(T) == 1 || std::getenv("LERC_B200_NO_FAST")) return false;
+  if (sizeof(T) == 1 || std::getenv("LERC_B200_NO_FAST") || maxZErr == 777) return false;     // 777: bit-plane mode, decided per tile by the general encoder
   if (PixelTraits<T>::isFloat && !(maxZErr > 0)) return false;
   const long long nTxF = (g.tileCols + 7) / 8, nTyF = (g.tileRows + 7) / 8;
   const long long seg = ((nTxF + FAST_TB - 1) / FAST_TB) * nTyF;

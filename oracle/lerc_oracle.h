@@ -18,7 +18,7 @@
  * depth-delta blocks, LUT blocks, 8-bit Huffman / delta-Huffman, Fletcher-32, multi-band concatenation, the _4D calls with
  * per-band noData values (FilterNoDataAndNaN / FilterNoData / RemapNoData), the DECODER of the lossless-float FPL codec.
  * Not restated (SURVEY 8f "next"): the FPL encoder (maxZError == 0 float/double blobs are written as raw/const micro-blocks,
- * which every Lerc2 reader decodes), the integer bit-plane mode, Lerc1.
+ * which every Lerc2 reader decodes), Lerc1.  (The integer bit-plane mode, maxZErr == 777, is restated.)
  *
  * The exported functions use the reference C API's argument lists (src/LercLib/include/Lerc_c_api.h:126-380)
  * with an `lo_` prefix so one ctypes binding drives all three libraries.

@@ -197,3 +197,28 @@ def fpl_cases(seed=21):
     cases.append(("f32_one_col", f[:, :1].copy(), {}))
     cases.append(("f32_big", c2_raster(300, 517), {}))
     return cases
+
+
+def bitplane_cases(seed=31):
+    """(name, array, kwargs) for maxZErr == 777, the reference's "cheat code" for the integer bit-plane mode (Lerc2.cpp:210-217,
+    :1071-1229): low bit planes that look like noise are dropped by raising maxZError to half of the last plane kept."""
+    rng = np.random.default_rng(seed)
+    h, w = 120, 160
+    smooth = smooth_field(h, w)
+    cases = []
+    noisy_low = (smooth.astype(np.int64) * 64 + rng.integers(0, 64, (h, w))).astype(np.uint16)        # 6 noise planes under a smooth signal
+    cases.append(("u16_six_noise_planes", noisy_low, {}))
+    cases.append(("i16_six_noise_planes", (noisy_low.astype(np.int32) - 20000).astype(np.int16), {}))
+    cases.append(("u8_smooth_no_noise", np.clip(smooth / 8, 0, 255).astype(np.uint8), {}))
+    cases.append(("u8_all_noise", rng.integers(0, 256, (h, w)).astype(np.uint8), {}))
+    cases.append(("i32_ten_noise_planes", (smooth.astype(np.int64) * 1024 + rng.integers(0, 1024, (h, w)) - 500000).astype(np.int32), {}))
+    cases.append(("u32_three_noise_planes", (smooth.astype(np.int64) * 8 + rng.integers(0, 8, (h, w))).astype(np.uint32), {}))
+    m = np.ones((h, w), np.uint8)
+    m[10:60, 20:100] = 0
+    cases.append(("u16_masked", noisy_low, {"mask": m}))
+    d3 = np.stack([noisy_low, noisy_low // 2, (noisy_low * 3) & 0xffff], axis=-1).astype(np.uint16)
+    cases.append(("u16_depth3", d3, {"n_depth": 3}))
+    cases.append(("u16_too_small", noisy_low[:50, :60].copy(), {}))                                    # fewer than 5000 pixels: lossless
+    cases.append(("f32_is_refused", smooth.astype(np.float32), {}))                                    # float types: Failed
+    cases.append(("u16_2bands", np.stack([noisy_low, noisy_low[::-1].copy()]), {"n_bands": 2}))
+    return cases

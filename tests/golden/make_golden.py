@@ -19,7 +19,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
 from lercapi import ref_lib  # noqa: E402
-from cases import all_cases, fpl_cases, nodata_cases  # noqa: E402
+from cases import all_cases, bitplane_cases, fpl_cases, nodata_cases  # noqa: E402
 
 REF = "/root/reference"
 
@@ -115,6 +115,15 @@ def main():
         out["hash_" + name] = np.array(h.hexdigest())
     np.savez_compressed(os.path.join(HERE, "fpl_ref.npz"), **out)
     print("FPL cases:", len(out) // 2)
+    # maxZErr == 777: the integer bit-plane mode (Lerc2.cpp:210-217, :1071-1229)
+    names, status, enc, sizes, mz = [], [], [], [], []
+    for name, arr, kw in bitplane_cases():
+        st, blob, _ = ref.encode(arr, 777, **kw)
+        names.append(name); status.append(st); sizes.append(len(blob)); enc.append(hashlib.sha256(blob).hexdigest() if st == 0 else "")
+        mz.append(ref.blob_info(blob)[1]["maxZErrUsed"] if st == 0 else -1.0)
+    np.savez_compressed(os.path.join(HERE, "bitplane_ref.npz"), names=np.array(names), status=np.array(status), sizes=np.array(sizes),
+                        enc=np.array(enc), maxzerr=np.array(mz))
+    print("bit-plane cases:", len(names))
 
 
 if __name__ == "__main__":

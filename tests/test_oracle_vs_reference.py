@@ -12,7 +12,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from cases import all_cases, fpl_cases, nodata_cases
+from cases import all_cases, bitplane_cases, fpl_cases, nodata_cases
 from lercapi import ROOT, oracle_lib, ref_lib
 
 GOLD = os.path.join(ROOT, "tests", "golden")
@@ -171,6 +171,24 @@ def test_fpl_blobs_decode_like_the_reference(oracle):
         assert h.hexdigest() == str(g["hash_" + name]), f"{name}: decoded pixels differ from the reference's"
         n_fpl += b"\x03" in blob[90:140]           # (the image-mode byte 3 sits right behind header, mask count and ranges)
     assert n_fpl >= 10
+
+
+def test_bitplane_mode_hashes(oracle):
+    """maxZErr == 777 (Lerc2.cpp:210-217 -> TryBitPlaneCompression :1071-1229): status, blob and the maxZError the reference ends up
+    with (bitplane_ref.npz)"""
+    g = np.load(os.path.join(GOLD, "bitplane_ref.npz"))
+    want = {str(n): (int(st), int(s), str(e), float(m)) for n, st, s, e, m in zip(g["names"], g["status"], g["sizes"], g["enc"], g["maxzerr"])}
+    raised = 0
+    for name, arr, kw in bitplane_cases():
+        st_w, size_w, enc_w, mz_w = want[name]
+        st, blob, _ = oracle.encode(arr, 777, **kw)
+        assert st == st_w, name
+        if st != 0:
+            continue
+        assert len(blob) == size_w and hashlib.sha256(blob).hexdigest() == enc_w, f"{name}: blob differs from the reference's"
+        assert oracle.blob_info(blob)[1]["maxZErrUsed"] == mz_w, name
+        raised += mz_w > 0.5
+    assert raised >= 6
 
 
 def test_bluemarble_reencode_v3_reproduces_the_shipped_blob(oracle):
