@@ -159,8 +159,21 @@ void runCta(Cta& cta, dim3 grid, dim3 block, unsigned bx, unsigned by, unsigned 
   const int deadlockS = envInt("CUSIM_DEADLOCK_S", 30);
   unsigned long long lastProgress = ~0ull;
   auto lastChange = std::chrono::steady_clock::now();
+  // CUSIM_SHUFFLE=<seed>: the fibers of a CTA are resumed in a different pseudo-random order on every pass (warps and lanes alike), to
+  // shake out code that only works because lower-numbered threads happen to run first
+  const int shuffleSeed = envInt("CUSIM_SHUFFLE", 0);
+  std::vector<int> order((size_t)n);
+  for (int t = 0; t < n; t++) order[(size_t)t] = t;
+  unsigned long long rng = 0x9E3779B97F4A7C15ull * (unsigned long long)(shuffleSeed + 1) + bx * 7919ull + by * 104729ull;
   while (cta.nExited < n) {
-    for (int t = 0; t < n; t++) {
+    if (shuffleSeed) {
+      for (int t = n - 1; t > 0; t--) {
+        rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
+        std::swap(order[(size_t)t], order[(size_t)(rng % (unsigned long long)(t + 1))]);
+      }
+    }
+    for (int q = 0; q < n; q++) {
+      const int t = order[(size_t)q];
       Fiber& f = cta.fibers[(size_t)t];
       if (f.done) continue;
       cta.cur = &f;
