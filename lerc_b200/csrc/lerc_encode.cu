@@ -815,7 +815,7 @@ bool encodeBandFast(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
       if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSm, k_encode_pipe<T, 4>, 256, smem) != cudaSuccess || ctasPerSm < 1) ctasPerSm = 1;
     }
     const long long grid = std::min<long long>(nTiles, (long long)ctasPerSm * std::max(sms, 1));     // all CTAs co-resident (look-back)
-    LERC_LAUNCH(ctx, (k_encode_pipe<T, 4>), (unsigned)grid, 256, smem, fa);
+    LERC_LAUNCH(ctx, (k_encode_pipe<T, 4>), (unsigned)grid, 256, smem, fa, FastNoBatch());
   } else if (ctaTiles) {
     const size_t smem = (size_t)((FAST_TB * MAXB + 15) / 16 + 3) * 16 * 2 + 256 * 8 * sizeof(T);       // two staging images + the general path's pixel rows
     static const int occ = [] { const char* e = std::getenv("LERC_B200_ENC_OCC"); const int v = e ? std::atoi(e) : 4; return (v == 5 || v == 6) ? v : 4; }();

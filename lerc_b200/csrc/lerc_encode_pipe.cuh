@@ -9,16 +9,15 @@
 //     LERC_B200_ENC_LB=group protocol: 64 cached 8-byte loads per warp and tile), so no warp waits for another one;
 //   * three staging images rotate (tile i packs, tile i - 1 is flushed, tile i - 2's image is zeroed): ONE __syncthreads per tile
 //     instead of two.
-// Same bytes as k_encode_fused (checked on tools/cusim against the oracle); not yet timed on a B200.  One image only (no tile batch).
+// Same bytes as k_encode_fused (checked on tools/cusim against the oracle, also under shuffled thread schedules); not yet timed on a
+// B200.  BATCH = true is the tile batch form (lerc_tiles_encode.cuh): local and blob-level look-backs are both deferred and per warp,
+// the per-image facts and checksum partials are handed over per warp with atomics, so the tile loop keeps its single barrier.
 #pragma once
 
 namespace lerc {
 
-template <class T, int MINB>
-__global__ void __launch_bounds__(256, MINB) k_encode_pipe(FastEncArgs a) {
-  constexpr bool BATCH = false;
-  const FastNoBatch t;
-  (void)t;
+template <class T, int MINB, bool BATCH = false>
+__global__ void __launch_bounds__(256, MINB) k_encode_pipe(FastEncArgs a, typename std::conditional<BATCH, FastBatchArgs, FastNoBatch>::type t) {
   using K = typename PixelTraits<T>::Key;
   constexpr bool isFlt = PixelTraits<T>::isFloat;
   constexpr int DT = PixelTraits<T>::code;
@@ -52,7 +51,7 @@ __global__ void __launch_bounds__(256, MINB) k_encode_pipe(FastEncArgs a) {
   unsigned long long fa = 0, fd = 0;
   bool overflow = false;
   uint32_t prevBytes = 0, prevPrevBytes = 0;
-  int prevTile = -1;
+  int prevTile = -1, prevImg = 0, prevLocal = 0;
 
   // geometry + pixel row of a tile for this lane
   auto tileGeom = [&](int tile, int tyT, int segT, int& ty, int& tx, int& h, int& w, bool& act) {
@@ -86,8 +85,9 @@ __global__ void __launch_bounds__(256, MINB) k_encode_pipe(FastEncArgs a) {
 
   // ---- deferred: global byte offset of a tile (two-round look-back through the group aggregates, done by EVERY warp on its own one
   // tile later, when the predecessors' states are long published -- no warp waits for another one) and its flush to HBM
-  auto finishTile = [&](const int tile, const uint32_t tileBytes, uint32_t* const stage) {
-    unsigned long long excl = 0;
+  auto finishTile = [&](const int tile, const uint32_t tileBytes, uint32_t* const stage, const int img, const int local) {
+    unsigned long long excl = 0, imgBase = 0;
+    if (!BATCH)
     {
       volatile unsigned long long* gs = a.groupState;
       const int l = tile & 31;
@@ -129,13 +129,56 @@ __global__ void __launch_bounds__(256, MINB) k_encode_pipe(FastEncArgs a) {
         if (tile == nTiles - 1) a.res->totalBytes = excl + tileBytes;
       }
     }
-    const unsigned long long tileOff = excl;
+    else {
+      // tile batch: the chain restarts at every image (offsets inside the blob); a second look-back over whole blobs places the blob
+      const long long first = (long long)(tile - local);
+      if (tile > first) {
+        long long base = (long long)tile - 1;
+        for (;;) {
+          const long long idx = base - lane;
+          unsigned long long s = ST_P;                                  // virtual tiles before the image's first: prefix 0
+          if (idx >= first) { do { s = st[idx]; } while ((s >> 62) == 0); }
+          const unsigned isP = __ballot_sync(FULL, (s >> 62) == 2);
+          const int firstP = isP ? __ffs(isP) - 1 : 32;
+          unsigned long long contrib = (lane <= firstP && idx >= first) ? (s & VAL) : 0;
+#pragma unroll
+          for (int m = 16; m; m >>= 1) contrib += __shfl_xor_sync(FULL, contrib, m);
+          excl += contrib;
+          if (isP) break;
+          base -= 32;
+        }
+        if (warp == 0 && lane == 0) st[tile] = ST_P | (excl + tileBytes);
+      }
+      volatile unsigned long long* ist = t.imgState;
+      const bool lastSeg = local == t.segPerImg - 1;
+      const unsigned long long blobBytes = (unsigned long long)t.dataStart + excl + tileBytes;      // meaningful for the last segment only
+      if (lastSeg && warp == 0 && lane == 0) { t.imgRes[img].streamBytes = excl + tileBytes; __threadfence(); ist[img] = (img == 0 ? ST_P : ST_A) | blobBytes; }
+      if (img > 0) {
+        long long base = (long long)img - 1;
+        for (;;) {
+          const long long idx = base - lane;
+          unsigned long long s = ST_P;
+          if (idx >= 0) { do { s = ist[idx]; } while ((s >> 62) == 0); }
+          const unsigned isP = __ballot_sync(FULL, (s >> 62) == 2);
+          const int firstP = isP ? __ffs(isP) - 1 : 32;
+          unsigned long long contrib = (lane <= firstP && idx >= 0) ? (s & VAL) : 0;
+#pragma unroll
+          for (int m = 16; m; m >>= 1) contrib += __shfl_xor_sync(FULL, contrib, m);
+          imgBase += contrib;
+          if (isP) break;
+          base -= 32;
+        }
+        if (lastSeg && warp == 0 && lane == 0) ist[img] = ST_P | (imgBase + blobBytes);
+      }
+    }
+    const unsigned long long localOff = excl;                             // offset inside this blob's micro-block stream
+    const unsigned long long tileOff = BATCH ? imgBase + (unsigned long long)t.dataStart + excl : excl;
     // ---- staging -> HBM in 16-byte chunks aligned to the GLOBAL address (the staging image is re-aligned with
     // funnel shifts), Fletcher-32 partial sums of the same words (bytes outside the tile are zero in the image);
     // every chunk read is zeroed again for the tile after next
     {
-      uint8_t* gTile = a.stream + tileOff;
-      const bool fits = tileOff + tileBytes <= a.streamCap;
+      uint8_t* gTile = (BATCH ? t.out : a.stream) + tileOff;
+      const bool fits = tileOff + tileBytes <= (BATCH ? t.outCap : a.streamCap);
       if (!fits) overflow = true;
       const int pad = (int)((uintptr_t)gTile & 15);
       const int nChunks = (pad + (int)tileBytes + 15) >> 4;
@@ -157,7 +200,7 @@ __global__ void __launch_bounds__(256, MINB) k_encode_pipe(FastEncArgs a) {
           }
         }
         // big-endian 16-bit words at even region offsets (Lerc2.cpp:1037-1064)
-        const long long r0 = a.regionOff + (long long)tileOff + s0;
+        const long long r0 = a.regionOff + (long long)localOff + s0;
         const unsigned par = (unsigned)(r0 & 1);
         const uint32_t w0 = (uint32_t)((unsigned long long)(r0 + 16) >> 1) % 65535u + 65535u - 8u;   // word index of byte r0 - par (mod 65535)
         uint32_t S = 0, S1 = 0, prev = 0;
@@ -172,6 +215,19 @@ __global__ void __launch_bounds__(256, MINB) k_encode_pipe(FastEncArgs a) {
         }
         fa += S; fd += (unsigned long long)w0 * S + S1;
       }
+    }
+    if (BATCH) {
+      // the checksum partials of this tile belong to its image: every warp hands its share over (no CTA-wide reduction, no barrier)
+      unsigned long long A = fa % 65535ull, D = fd % 65535ull;
+#pragma unroll
+      for (int m = 16; m; m >>= 1) { A += __shfl_xor_sync(FULL, A, m); D += __shfl_xor_sync(FULL, D, m); }
+      unsigned int ov = __reduce_or_sync(FULL, overflow ? (unsigned int)FASTF_OVERFLOW : 0u);
+      if (lane == 0) {
+        TileEncResult* ir = t.imgRes + img;
+        if (A | D) { atomicAdd(&ir->fletA, A); atomicAdd(&ir->fletD, D % 65535ull); }
+        if (ov) atomicOr(&ir->flags, ov);
+      }
+      fa = 0; fd = 0; overflow = false;
     }
   };
 
@@ -257,6 +313,22 @@ __global__ void __launch_bounds__(256, MINB) k_encode_pipe(FastEncArgs a) {
       }
     }
     if (r == 0) sLen[it & 1][b] = (uint32_t)nBytes;
+    if (BATCH) {
+      // image-global facts of this tile (min / max keys, flags) go to its image right away, per warp
+      K wMin = gMin, wMax = gMax;
+#pragma unroll
+      for (int m = 1; m < 32; m <<= 1) {
+        const K omin = shflXorK<K>(wMin, m), omax = shflXorK<K>(wMax, m);
+        wMin = omin < wMin ? omin : wMin; wMax = omax > wMax ? omax : wMax;
+      }
+      const unsigned int wf = __reduce_or_sync(FULL, myFlags);
+      if (lane == 0) {
+        TileEncResult* ir = t.imgRes + img;
+        if (wMax >= wMin) { atomicMax(&ir->negMinKey, ~(unsigned long long)wMin); atomicMax(&ir->maxKey, (unsigned long long)wMax); }
+        if (wf) atomicOr(&ir->flags, wf);
+      }
+      gMin = keyMaxValue<K>(); gMax = 0; myFlags = 0;
+    }
     __syncthreads();                                             // the ONLY barrier per tile: block lengths visible; every warp has packed tile it - 1 and flushed tile it - 2
     if (it > 1) {  // zero what tile it - 2 used of its image (flushed by every warp before this barrier); tile it + 1 packs into it after the next barrier
       const int nz = (((int)prevPrevBytes + 15) >> 4) + 3;
@@ -305,14 +377,15 @@ __global__ void __launch_bounds__(256, MINB) k_encode_pipe(FastEncArgs a) {
     }
 
     // ---- the previous tile: offset + flush (its image was completed by every warp before this iteration's barrier)
-    if (it > 0) finishTile(prevTile, prevBytes, stageRaw + (size_t)((it - 1) % 3) * NQ * 4 + 4);
-    prevPrevBytes = prevBytes; prevBytes = tileBytes; prevTile = tile;
+    if (it > 0) finishTile(prevTile, prevBytes, stageRaw + (size_t)((it - 1) % 3) * NQ * 4 + 4, prevImg, prevLocal);
+    prevPrevBytes = prevBytes; prevBytes = tileBytes; prevTile = tile; prevImg = img; prevLocal = local;
     // ---- next tile
     cur = nxt; ty = nty; tx = ntx; h = nh; w = nw; act = nact;
     if (BATCH) { img = nimg; local = nlocal; org = norg; }
   }
   __syncthreads();                                               // the last tile is packed
-  if (prevTile >= 0) finishTile(prevTile, prevBytes, stageRaw + (size_t)(((prevTile - (int)blockIdx.x) / (int)gridDim.x) % 3) * NQ * 4 + 4);
+  if (prevTile >= 0) finishTile(prevTile, prevBytes, stageRaw + (size_t)(((prevTile - (int)blockIdx.x) / (int)gridDim.x) % 3) * NQ * 4 + 4, prevImg, prevLocal);
+  if (BATCH) return;
 
   // ---- image-global facts and checksum partials of this CTA
 #pragma unroll
