@@ -655,6 +655,30 @@ __device__ __forceinline__ void fdStoreRow(T* __restrict__ dst, const T (&out)[8
   }
 }
 
+// True (position, block index, candidate slot) at the start of every sub-chunk of region `reg`, by one warp: the chain is followed
+// sub-chunk by sub-chunk (a dependent walk of <= FD_REG steps), the FD_CAND candidates of a step are compared by 16 lanes at once.
+__device__ __forceinline__ void fdTrueEntries(const FastDecArgs& a, int reg, int nLocal, int nBlocks, const FdEntry* __restrict__ sTab,
+                                              uint32_t* __restrict__ sTrue, int* __restrict__ sWhy, int lane) {
+  uint32_t pos = a.regEntry[2 * reg], blk = a.regEntry[2 * reg + 1];
+  for (int ls = 0; ls <= nLocal; ls++) {
+    if (lane == 0) { sTrue[3 * ls] = pos; sTrue[3 * ls + 1] = blk; sTrue[3 * ls + 2] = 0; }
+    if (ls == nLocal) break;
+    if (pos == FD_DEAD) { if (lane == 0) for (int k = ls; k <= nLocal; k++) { sTrue[3 * k] = FD_DEAD; sTrue[3 * k + 1] = blk; } break; }
+    if (pos == FD_DEAD - 1 || blk >= (uint32_t)nBlocks) {                        // past the last block
+      if (lane == 0) for (int k = ls; k <= nLocal; k++) { sTrue[3 * k] = FD_DEAD - 1; sTrue[3 * k + 1] = blk; }
+      break;
+    }
+    FdEntry t; t.entry = FD_DEAD; t.exit = 0; t.count = 0;
+    if (lane < FD_CAND) t = sTab[ls * FD_CAND + lane];
+    const unsigned m = __ballot_sync(FULL, t.entry != FD_DEAD && t.entry == pos);
+    if (!m) { if (lane == 0) *sWhy |= 64; pos = FD_DEAD; continue; }
+    const int src = __ffs(m) - 1;                                                 // the lowest matching slot, like the serial search
+    if (lane == 0) sTrue[3 * ls + 2] = (uint32_t)src;
+    pos = __shfl_sync(FULL, t.exit, src); blk += __shfl_sync(FULL, t.count, src);
+  }
+  __syncwarp();
+}
+
 constexpr int FD_DWARPS = 8;
 // ================= kernel 4b: block offsets only (masked rasters: the general block decoder does the pixels) =========
 // Same resolution as k_dec_blocks; instead of decoding, every block's stream offset is written to blockOff[] for
@@ -678,21 +702,7 @@ __global__ void __launch_bounds__(FD_DWARPS * 32) k_dec_offsets(FastDecArgs a, c
   for (int i = tid; i < nLocal * FD_CAND; i += blockDim.x) sTab[i] = a.subTab[(size_t)sub0 * FD_CAND + i];
   __syncthreads();
   // ---- true entry (position, block index, candidate slot) of every sub-chunk of the region
-  if (tid == 0) {
-    uint32_t pos = a.regEntry[2 * reg], blk = a.regEntry[2 * reg + 1];
-    for (int ls = 0; ls <= nLocal; ls++) {
-      sTrue[3 * ls] = pos; sTrue[3 * ls + 1] = blk; sTrue[3 * ls + 2] = 0;
-      if (ls == nLocal) break;
-      if (pos == FD_DEAD) { for (int k = ls; k <= nLocal; k++) { sTrue[3 * k] = FD_DEAD; sTrue[3 * k + 1] = blk; } break; }
-      if (pos == FD_DEAD - 1 || blk >= (uint32_t)nBlocks) { for (int k = ls; k <= nLocal; k++) { sTrue[3 * k] = FD_DEAD - 1; sTrue[3 * k + 1] = blk; } break; }   // past the last block
-      bool found = false;
-      for (int e = 0; e < FD_CAND; e++) {
-        const FdEntry t = sTab[ls * FD_CAND + e];
-        if (t.entry != FD_DEAD && t.entry == pos) { sTrue[3 * ls + 2] = (uint32_t)e; pos = t.exit; blk += t.count; found = true; break; }
-      }
-      if (!found) { sWhy |= 64; pos = FD_DEAD; }
-    }
-  }
+  if (tid < 32) fdTrueEntries(a, reg, nLocal, nBlocks, sTab, sTrue, &sWhy, lane);
   __syncthreads();
 
   const int tailRaw = 1 + (a.nRows - (a.nTy - 1) * 8) * (a.nCols - (a.nTx - 1) * 8) * (int)sizeof(T);
@@ -764,21 +774,7 @@ __global__ void __launch_bounds__(FD_DWARPS * 32) k_dec_blocks(FastDecArgs a) {
   for (int i = tid; i < nLocal * FD_CAND; i += blockDim.x) sTab[i] = a.subTab[(size_t)sub0 * FD_CAND + i];
   __syncthreads();
   // ---- true entry (position, block index, candidate slot) of every sub-chunk of the region
-  if (tid == 0) {
-    uint32_t pos = a.regEntry[2 * reg], blk = a.regEntry[2 * reg + 1];
-    for (int ls = 0; ls <= nLocal; ls++) {
-      sTrue[3 * ls] = pos; sTrue[3 * ls + 1] = blk; sTrue[3 * ls + 2] = 0;
-      if (ls == nLocal) break;
-      if (pos == FD_DEAD) { for (int k = ls; k <= nLocal; k++) { sTrue[3 * k] = FD_DEAD; sTrue[3 * k + 1] = blk; } break; }
-      if (pos == FD_DEAD - 1 || blk >= (uint32_t)nBlocks) { for (int k = ls; k <= nLocal; k++) { sTrue[3 * k] = FD_DEAD - 1; sTrue[3 * k + 1] = blk; } break; }   // past the last block
-      bool found = false;
-      for (int e = 0; e < FD_CAND; e++) {
-        const FdEntry t = sTab[ls * FD_CAND + e];
-        if (t.entry != FD_DEAD && t.entry == pos) { sTrue[3 * ls + 2] = (uint32_t)e; pos = t.exit; blk += t.count; found = true; break; }
-      }
-      if (!found) { sWhy |= 64; pos = FD_DEAD; }
-    }
-  }
+  if (tid < 32) fdTrueEntries(a, reg, nLocal, nBlocks, sTab, sTrue, &sWhy, lane);
   __syncthreads();
 
   // ---- decode: one warp per sub-chunk, 4 blocks at a time, 8 lanes per block (lane r = block row r)
