@@ -63,3 +63,51 @@ def kernel_times(reset=True):
         name, cnt, ms = line.split("\t")
         out[name] = (int(cnt), float(ms))
     return out
+
+
+# ---- tile batch (include/lerc_b200.h): thin wrappers over lerc_b200_encodeTiles / lerc_b200_decodeTiles ------------------------------
+_DT_CODES = {"int8": 0, "uint8": 1, "int16": 2, "uint16": 3, "int32": 4, "uint32": 5, "float32": 6, "float64": 7}
+_lib.lerc_b200_tilesMaxBytes.restype = ctypes.c_ulonglong
+_lib.lerc_b200_tilesMaxBytes.argtypes = [ctypes.c_uint] + [ctypes.c_int] * 4
+_lib.lerc_b200_encodeTiles.restype = ctypes.c_uint
+_lib.lerc_b200_encodeTiles.argtypes = [ctypes.c_void_p, ctypes.c_uint, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double,
+                                       ctypes.c_void_p, ctypes.c_ulonglong, ctypes.c_void_p, ctypes.c_void_p]
+_lib.lerc_b200_decodeTiles.restype = ctypes.c_uint
+_lib.lerc_b200_decodeTiles.argtypes = [ctypes.c_void_p, ctypes.c_ulonglong, ctypes.c_void_p, ctypes.c_uint, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                       ctypes.c_int, ctypes.c_void_p]
+
+
+def _ptr(buf):
+    """address of a numpy array (host) or a torch tensor (host or CUDA): the library accepts both kinds of pointers"""
+    if hasattr(buf, "data_ptr"):
+        return buf.data_ptr()
+    return buf.ctypes.data
+
+
+def _dtype_code(buf):
+    name = str(buf.dtype).replace("torch.", "")
+    return _DT_CODES[name]
+
+
+def tiles_max_bytes(dtype_code, n_rows, n_cols, tile_rows, tile_cols):
+    """an output size that always suffices for encode_tiles (lerc_b200_tilesMaxBytes)"""
+    return int(_lib.lerc_b200_tilesMaxBytes(dtype_code, n_cols, n_rows, tile_cols, tile_rows))
+
+
+def encode_tiles(raster, tile_rows, tile_cols, max_z_err, out, offsets):
+    """raster: contiguous [n_rows][n_cols] numpy array or torch tensor (host or CUDA); out: uint8 buffer of at least
+    tiles_max_bytes(...) bytes; offsets: 64-bit integer buffer with n_tiles + 1 entries.  Every tile_rows x tile_cols window becomes
+    its own standard Lerc2 blob, blob t = out[offsets[t]:offsets[t + 1]].  Returns (lerc_status, bytes written)."""
+    n_rows, n_cols = int(raster.shape[0]), int(raster.shape[1])
+    n = ctypes.c_ulonglong(0)
+    cap = int(out.numel() if hasattr(out, "numel") else out.size)
+    st = _lib.lerc_b200_encodeTiles(_ptr(raster), _dtype_code(raster), n_cols, n_rows, tile_cols, tile_rows, float(max_z_err),
+                                    _ptr(out), cap, _ptr(offsets), ctypes.addressof(n))
+    return int(st), int(n.value)
+
+
+def decode_tiles(blobs, n_bytes, offsets, out, tile_rows, tile_cols):
+    """inverse of encode_tiles: decodes the n_tiles blobs addressed by `offsets` into the [n_rows][n_cols] buffer `out`.
+    Returns the lerc_status."""
+    n_rows, n_cols = int(out.shape[0]), int(out.shape[1])
+    return int(_lib.lerc_b200_decodeTiles(_ptr(blobs), int(n_bytes), _ptr(offsets), _dtype_code(out), n_cols, n_rows, tile_cols, tile_rows, _ptr(out)))

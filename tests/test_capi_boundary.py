@@ -79,3 +79,27 @@ def test_no_cpu_fallback_without_gpu(lib):
         pass
     st, blob, _ = lib.encode(np.ones((16, 16), np.float32), 0.01)
     assert st == 1 and blob == b""
+
+
+def test_tile_batch_wrappers_fail_loudly_without_gpu(lib):
+    """lerc_b200.encode_tiles / decode_tiles (Python view of lerc_b200_encodeTiles / decodeTiles): argument plumbing works on the
+    CPU, and without a CUDA device the calls return Failed -- there is no CPU fallback"""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("GPU present")
+    except ImportError:
+        pass
+    import sys
+    sys.path.insert(0, ROOT)
+    import lerc_b200
+    img = np.ones((64, 96), np.float32)
+    cap = lerc_b200.tiles_max_bytes(6, 64, 96, 32, 32)
+    assert cap >= img.nbytes
+    out = np.zeros(cap, np.uint8)
+    off = np.zeros(7, np.uint64)
+    st, n = lerc_b200.encode_tiles(img, 32, 32, 0.01, out, off)
+    assert st == 1 and n == 0
+    dec = np.zeros_like(img)
+    assert lerc_b200.decode_tiles(out, 100, off, dec, 32, 32) == 1
+    assert lerc_b200.tiles_max_bytes(99, 64, 96, 32, 32) == 0          # unknown data type
