@@ -44,3 +44,18 @@ def test_bitplane_mode_through_the_tile_batch(libs):
     for t, (ys, xs) in enumerate(tile_windows(arr.shape[0], arr.shape[1], 80, 80)):
         s_o, b_o, _ = orc.encode(np.ascontiguousarray(arr[ys, xs]), 777)
         assert s_o == 0 and blobs[t] == b_o, f"tile {t}"
+
+
+def test_bitplane_mode_edge_cases(libs):
+    """empty bands, float types and old codec versions with the cheat code (Lerc2.cpp:205-224; v6 floats: the noData / NaN filter
+    resets maxZError for an empty band first, Lerc.cpp:1473-1478)"""
+    prod, orc = libs
+    rng = np.random.default_rng(0)
+    a16 = rng.integers(0, 1000, (90, 100)).astype(np.int16)
+    f32 = rng.random((90, 100)).astype(np.float32)
+    zero = np.zeros((90, 100), np.uint8)
+    for arr, kw in [(a16, dict(mask=zero)), (f32, dict(mask=zero)), (f32, dict(mask=zero, version=5)), (np.full((90, 100), np.nan, np.float32), {}),
+                    (a16, dict(version=4)), (f32, {}), (a16[:20, :30].copy(), dict(version=3))]:
+        s_o, b_o, _ = orc.encode(arr, 777, **kw)
+        s_p, b_p, _ = prod.encode(arr, 777, **kw)
+        assert s_p == s_o and b_p == b_o, kw
