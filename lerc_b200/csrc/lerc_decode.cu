@@ -377,6 +377,8 @@ bool launchDecodeFast(Context* ctx, const HeaderInfo& hd, const uint8_t* dStream
   fa.nCand = sp;
   fa.status = dStatus;
   fa.repairReg = -1; fa.repairPos = 0;
+  static const bool closureDec = [] { const char* e = std::getenv("LERC_B200_DEC"); return e && std::strcmp(e, "closure") == 0; }();
+  fa.firstOnly = closureDec ? 1 : 0;
   if (faOut) *faOut = fa;
   static bool attrSet = false;
   if (!attrSet) {

@@ -54,6 +54,9 @@ struct FastDecArgs {
   // repair launch of k_dec_walk (one CTA): the true chain enters region repairReg at stream position repairPos, which the
   // head-window speculation did not keep among the region's candidates (candidate flood); -1 = normal launch
   int repairReg; uint32_t repairPos;
+  // experimental (LERC_B200_DEC=closure): head-window candidates only for the FIRST sub-chunk of every region; the entries of the other
+  // sub-chunks are the real chain exits of their predecessors, walked by k_dec_walk's closure pass (one lane per distinct exit)
+  int firstOnly;
 };
 
 // ---- unit header ---------------------------------------------------------------------------------
@@ -216,6 +219,7 @@ __global__ void __launch_bounds__(256) k_dec_candidates(FastDecArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int s = blockIdx.x * 8 + warp;
   if (s >= a.nSub) return;
+  if (a.firstOnly && (s % a.subPerReg) != 0) { if (lane == 0) a.nCand[s] = 0; return; }
   const int version = a.version;
   const int tailRaw = 1 + (a.nRows - (a.nTy - 1) * 8) * (a.nCols - (a.nTx - 1) * 8) * (int)sizeof(T);
   const unsigned long long start = (unsigned long long)s * FD_SUB;
@@ -380,7 +384,7 @@ __global__ void __launch_bounds__(256) k_dec_walk(FastDecArgs a) {
   // the 16 exits of the previous one.
   // quick parallel check first (one warp per pair of neighbouring sub-chunks); the sequential pass runs only if something is missing
   __shared__ int sMissing;
-  if (tid == 0) sMissing = a.repairReg >= 0 ? 1 : 0;
+  if (tid == 0) sMissing = (a.repairReg >= 0 || a.firstOnly) ? 1 : 0;
   __syncthreads();
   for (int ls = 1 + (tid >> 5); ls < nLocal; ls += blockDim.x >> 5) {
     const int lane = tid & 31, s = sub0 + ls;
@@ -402,6 +406,27 @@ __global__ void __launch_bounds__(256) k_dec_walk(FastDecArgs a) {
       bool present = !inSub;
       if (inSub) for (int e2 = 0; e2 < FD_CAND; e2++) present |= sTab[ls * FD_CAND + e2].entry == x;
       unsigned miss = __ballot_sync(FULL, !present);
+      if (a.firstOnly) {
+        // every DISTINCT missing exit is walked by its own lane into its own free slot of this sub-chunk
+        bool leader = !present;
+        for (int o = 0; o < FD_CAND; o++) { const uint32_t xo = __shfl_sync(FULL, x, o); const bool mo = (miss >> o) & 1; if (mo && o < lane && xo == x) leader = false; }
+        const unsigned leaders = __ballot_sync(FULL, leader);
+        const unsigned freeSlots = __ballot_sync(FULL, lane < FD_CAND && sTab[ls * FD_CAND + lane].entry == FD_DEAD);
+        if (leader) {
+          int k = __popc(leaders & ((1u << lane) - 1));
+          unsigned f = freeSlots;
+          while (k > 0 && f) { f &= f - 1; k--; }
+          if (f) {
+            const int slot = __ffs(f) - 1;
+            FdEntry w;
+            if (fdWalkChain<T>(a, sReg, d + ls * FD_SUB, s, (int)(x - (uint32_t)s * FD_SUB), version, tailRaw, a.lens + ((size_t)s * FD_CAND + slot) * FD_LENS, w)) {
+              sTab[ls * FD_CAND + slot] = w; a.subTab[(size_t)s * FD_CAND + slot] = w;
+            }
+          }
+        }
+        __syncwarp();
+        miss = 0;
+      }
       while (miss) {
         const int src = __ffs(miss) - 1;
         miss &= miss - 1;
