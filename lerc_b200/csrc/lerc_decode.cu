@@ -346,6 +346,18 @@ int smCount() {
   return n;
 }
 
+// k_dec_resolve: the region tables stay in global memory (default) or are staged in shared memory when they fit (experimental,
+// LERC_B200_DEC_RESOLVE=smem)
+inline void launchResolve(Context* ctx, const FastDecArgs& fa) {
+  static const bool smemResolve = [] { const char* e = std::getenv("LERC_B200_DEC_RESOLVE"); return e && std::strcmp(e, "smem") == 0; }();
+  const size_t bytes = (size_t)fa.nReg * FD_CAND * sizeof(FdEntry);
+  if (smemResolve && bytes <= 160 * 1024) {
+    static bool attrSet = false;
+    if (!attrSet) { cudaFuncSetAttribute(k_dec_resolve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attrSet = true; }
+    LERC_LAUNCH(ctx, k_dec_resolve<true>, 1, 1024, bytes, fa, fa.nTx * fa.nTy);
+  } else LERC_LAUNCH(ctx, k_dec_resolve<false>, 1, 1024, 0, fa, fa.nTx * fa.nTy);
+}
+
 // Launches the speculative parallel decoder (lerc_decode_fast.cuh) on the micro-block stream.  Returns false when the
 // stream's shape is outside what it handles (nothing launched).
 template <class T>
@@ -388,7 +400,7 @@ bool launchDecodeFast(Context* ctx, const HeaderInfo& hd, const uint8_t* dStream
   }
   LERC_LAUNCH(ctx, k_dec_candidates<T>, (nSub + 7) / 8, 256, 0, fa);
   LERC_LAUNCH(ctx, k_dec_walk<T>, nReg, 256, smemW, fa);
-  LERC_LAUNCH(ctx, k_dec_resolve, 1, 1024, 0, fa, fa.nTx * fa.nTy);
+  launchResolve(ctx, fa);
   if (dBlockOff) LERC_LAUNCH(ctx, k_dec_offsets<T>, nReg, FD_DWARPS * 32, 0, fa, dBits, dBlockOff);
   else LERC_LAUNCH(ctx, k_dec_blocks<T>, nReg, FD_DWARPS * 32, smemB, fa);
   return cudaOk(cudaGetLastError(), "launch fast decode");
@@ -424,7 +436,7 @@ bool repairDecodeFast(Context* ctx, FastDecArgs fa, const uint8_t* dBits, uint32
     ra.repairReg = f - 1; ra.repairPos = ent[2 * (size_t)(f - 1)];
     cudaMemsetAsync(dStatus, 0, 4, st);
     LERC_LAUNCH(ctx, k_dec_walk<T>, 1, 256, smemW, ra);
-    LERC_LAUNCH(ctx, k_dec_resolve, 1, 1024, 0, fa, fa.nTx * fa.nTy);
+    launchResolve(ctx, fa);
   }
   return false;
 }

@@ -522,7 +522,18 @@ __device__ __forceinline__ void fdFillBatch(const uint16_t* __restrict__ tab, in
 //   B  one thread composes the 32 chunk maps serially                        -> true entry of every chunk
 //   C  every warp walks its regions again with the single true chain         -> regEntry[r] for every region
 static_assert(FD_CAND == 16, "k_dec_resolve pairs 16 entry lanes with 16 chain lanes");
+template <bool SMEM>
 __global__ void __launch_bounds__(1024) k_dec_resolve(FastDecArgs a, int nBlocks) {
+  // SMEM (experimental, LERC_B200_DEC_RESOLVE=smem): the region tables are copied to shared memory first, so that the ~56 dependent
+  // steps below wait for shared memory instead of L2 (the kernel is one CTA of pure latency)
+  extern __shared__ __align__(16) uint8_t sRegTabRaw[];
+  const FdEntry* tab = a.regTab;
+  if (SMEM) {
+    FdEntry* sTabAll = (FdEntry*)sRegTabRaw;
+    for (int i = threadIdx.x; i < a.nReg * FD_CAND; i += blockDim.x) sTabAll[i] = a.regTab[i];
+    __syncthreads();
+    tab = sTabAll;
+  }
   __shared__ uint32_t sEnt[32][FD_CAND], sExit[32][FD_CAND], sCnt[32][FD_CAND];
   __shared__ uint32_t sChunkPos[33], sChunkBlk[33];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -532,13 +543,13 @@ __global__ void __launch_bounds__(1024) k_dec_resolve(FastDecArgs a, int nBlocks
   {
     const int L = lane & 15;
     uint32_t ent = FD_DEAD, pos = FD_DEAD, cnt = 0;
-    if (r0 < r1) { const FdEntry t = a.regTab[(size_t)r0 * FD_CAND + L]; ent = t.entry; pos = t.exit; cnt = t.count; }
+    if (r0 < r1) { const FdEntry t = tab[(size_t)r0 * FD_CAND + L]; ent = t.entry; pos = t.exit; cnt = t.count; }
     bool alive = ent != FD_DEAD;
     FdEntry nx; nx.entry = FD_DEAD; nx.exit = 0; nx.count = 0;
-    if (r0 + 1 < r1) nx = a.regTab[(size_t)(r0 + 1) * FD_CAND + L];
+    if (r0 + 1 < r1) nx = tab[(size_t)(r0 + 1) * FD_CAND + L];
     for (int r = r0 + 1; r < r1; r++) {
       const FdEntry t = nx;                                          // lanes 0..15 and 16..31 hold the same 16 entries
-      if (r + 1 < r1) nx = a.regTab[(size_t)(r + 1) * FD_CAND + L];  // independent of the chains: overlaps the match
+      if (r + 1 < r1) nx = tab[(size_t)(r + 1) * FD_CAND + L];  // independent of the chains: overlaps the match
       const bool chain = lane >= 16;
       const bool active = chain && alive && (unsigned long long)pos < a.streamLen;   // a chain that reached the end of the stream is complete
       int hit = -1;
@@ -580,11 +591,11 @@ __global__ void __launch_bounds__(1024) k_dec_resolve(FastDecArgs a, int nBlocks
     uint32_t pos = sChunkPos[warp], blk = sChunkBlk[warp];
     bool dead = pos == FD_DEAD;
     FdEntry nx; nx.entry = FD_DEAD; nx.exit = 0; nx.count = 0;
-    if (lane < FD_CAND && r0 < r1) nx = a.regTab[(size_t)r0 * FD_CAND + lane];
+    if (lane < FD_CAND && r0 < r1) nx = tab[(size_t)r0 * FD_CAND + lane];
     for (int r = r0; r < r1; r++) {
       const FdEntry t = nx;
       nx.entry = FD_DEAD;
-      if (lane < FD_CAND && r + 1 < r1) nx = a.regTab[(size_t)(r + 1) * FD_CAND + lane];   // independent of the chain: overlaps the lookup
+      if (lane < FD_CAND && r + 1 < r1) nx = tab[(size_t)(r + 1) * FD_CAND + lane];   // independent of the chain: overlaps the lookup
       if (lane == 0) { a.regEntry[2 * r] = dead ? FD_DEAD : (blk >= (uint32_t)nBlocks ? FD_DEAD - 1 : pos); a.regEntry[2 * r + 1] = blk; }
       if (dead || blk >= (uint32_t)nBlocks) continue;
       const unsigned m = __ballot_sync(FULL, t.entry == pos && t.entry != FD_DEAD);
