@@ -128,3 +128,31 @@ def test_device_pointers_config5_shape(libs):
         ys, xs = wins[k]
         st_o, d_o, _ = orc.decode(out[off[k]:off[k + 1]].tobytes())
         assert st_o == 0 and np.array_equal(dec[ys, xs].view(np.uint8), d_o[0, :, :, 0].view(np.uint8)), f"tile {k}"
+
+
+def test_corrupted_tiles_fuzz(libs):
+    """1-3 flipped bytes in one tile's blob, checksum repaired so that the header parser, the walker and the block decoder of the batch
+    path are reached: status and pixels of lerc_b200_decodeTiles equal the oracle's lerc_decode of that blob"""
+    prod, orc = libs
+    fl = orc.lib.lo_fletcher32
+    fl.restype = C.c_uint32
+    fl.argtypes = [C.c_void_p, C.c_int]
+    img = c2_raster(128, 192)
+    img[70:100, :] = 5.0
+    wins = list(tile_windows(128, 192, 64, 64))
+    blobs = _oracle_blobs(orc, img, 64, 64, 0.01)
+    rng = np.random.default_rng(9)
+    for it in range(60):
+        t = int(rng.integers(0, len(blobs)))
+        b = bytearray(blobs[t])
+        for _ in range(int(rng.integers(1, 4))):
+            b[int(rng.integers(14, len(b)))] ^= int(rng.integers(1, 256))
+        buf = np.frombuffer(bytes(b), np.uint8).copy()
+        cs = fl(buf[14:].ctypes.data, len(b) - 14)
+        buf[10:14] = np.frombuffer(np.uint32(cs).tobytes(), np.uint8)
+        s_o, d_o, _ = orc.decode(buf.tobytes())
+        s_p, d_p = decode_tiles(prod, blobs[:t] + [buf.tobytes()] + blobs[t + 1:], np.float32, 128, 192, 64, 64)
+        assert (s_p == 0) == (s_o == 0), f"case {it}, tile {t}: status {s_p} vs oracle {s_o}"
+        if s_o == 0:
+            ys, xs = wins[t]
+            assert np.array_equal(d_p[ys, xs].view(np.uint8), d_o[0, :, :, 0].view(np.uint8)), f"case {it}, tile {t}"
