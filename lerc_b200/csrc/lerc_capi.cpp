@@ -125,10 +125,13 @@ lerc_status encodeImpl(const void* pData, int version, unsigned dataType, int nD
     if (need + bandBytes > (uint64_t)UINT_MAX) return DimensionsTooLarge;   // Lerc.cpp:757-758
     need += bandBytes;
     offset += bandBytes;
-    // per-band scratch is recycled; everything allocated before the band loop (and the mask of the previous band) stays
-    if (!cudaOk(cudaStreamSynchronize(ctx->stream), "band sync")) return Failed;
-    if (ctx->arena.retired.empty()) ctx->arena.used = arenaMark;
-    ctx->pinnedUsed = pinnedMark;
+    // per-band scratch is recycled; everything allocated before the band loop (and the mask of the previous band) stays.
+    // (After the last band of a writing call the synchronisation below, behind the tail fill / blob copy, covers it.)
+    if (b + 1 < nBands || sizeOnly) {
+      if (!cudaOk(cudaStreamSynchronize(ctx->stream), "band sync")) return Failed;
+      if (ctx->arena.retired.empty()) ctx->arena.used = arenaMark;
+      ctx->pinnedUsed = pinnedMark;
+    }
   }
   if (nNeeded) *nNeeded = (unsigned)need;
   if (sizeOnly) return Ok;
