@@ -200,7 +200,7 @@ def oracle_lib():
 
 def product_lib():
     if os.environ.get("LERC_B200_SIM") == "1":       # development only (tools/cusim/README.md): never set by the driver, the gpu tests or bench.py
-        return LercLib(os.path.join(ROOT, "tools", "cusim", "_build", "libLerc_sim.so"))
+        return LercLib(os.path.join(ROOT, "tools", "cusim", os.environ.get("CUSIM_BUILD_DIR", "_build"), "libLerc_sim.so"))
     p = _first(os.path.join(ROOT, "lerc_b200", "libLerc.so.4"))
     return LercLib(p) if p else None
 

@@ -21,7 +21,7 @@ from cases import all_cases  # noqa: E402
 
 
 def sim_lib():
-    return LercLib(os.path.join(ROOT, "tools", "cusim", "_build", "libLerc_sim.so"))
+    return LercLib(os.path.join(ROOT, "tools", "cusim", os.environ.get("CUSIM_BUILD_DIR", "_build"), "libLerc_sim.so"))
 
 
 def check_case(sim, orc, name, arr, mz, kw, version=None):

@@ -14,7 +14,7 @@ from cases import tile_cases  # noqa: E402
 
 
 def main():
-    sim = LercLib(os.path.join(ROOT, "tools", "cusim", "_build", "libLerc_sim.so"))
+    sim = LercLib(os.path.join(ROOT, "tools", "cusim", os.environ.get("CUSIM_BUILD_DIR", "_build"), "libLerc_sim.so"))
     orc = oracle_lib()
     only = sys.argv[1] if len(sys.argv) > 1 else ""
     bad = 0

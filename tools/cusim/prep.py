@@ -9,7 +9,7 @@ The product sources themselves are not modified."""
 import os, re, shutil, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-OUT = os.path.join(ROOT, "tools", "cusim", "_build", "tree")
+OUT = os.path.join(ROOT, "tools", "cusim", os.environ.get("CUSIM_BUILD_DIR", "_build"), "tree")
 
 LAUNCH = re.compile(r"([A-Za-z_][\w:<>, ]*?)<<<(.+?)>>>\((.*?)\);")
 DYN = re.compile(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?([\w:]+(?:\s+[\w:]+)*?)\s+(\w+)\[\];")
