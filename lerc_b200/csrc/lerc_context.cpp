@@ -21,6 +21,16 @@ bool cudaOk(cudaError_t e, const char* what) {
 
 // ---- arena ----------------------------------------------------------------------------------
 void* Arena::alloc(size_t bytes, size_t align) {
+#ifdef LERC_CUSIM
+  // simulator builds only (tools/cusim): with CUSIM_GUARD_ARENA every scratch allocation is its own heap block, so that an
+  // AddressSanitizer build puts redzones around each of them
+  if (std::getenv("CUSIM_GUARD_ARENA")) {
+    uint8_t* p = nullptr;
+    if (!cudaOk(cudaMalloc(&p, ((bytes ? bytes : 1) + 15) / 16 * 16), "cudaMalloc(guarded scratch)")) return nullptr;   // whole 16-byte chunks, like the real arena
+    retired.push_back(p);
+    return p;
+  }
+#endif
   size_t off = (used + align - 1) / align * align;
   if (off + bytes > cap) {
     // Grow by replacing the block.  Pointers handed out earlier in this call stay valid because the
