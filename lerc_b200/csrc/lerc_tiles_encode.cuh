@@ -49,7 +49,7 @@ __global__ void k_try_raise_tiles(const T* __restrict__ data, long long pitch, i
   }
 }
 
-enum { TILEST_OK = 0, TILEST_GENERAL = 1, TILEST_OVERFLOW = 2 };
+enum { TILEST_OK = 0, TILEST_GENERAL = 1, TILEST_OVERFLOW = 2, TILEST_ALLINT = 3 };   // ALLINT: the only obstacle is that all-integer floats want max(0.5, floor(maxZErr))
 
 struct TileFinishArgs {
   const TileEncResult* res; const unsigned long long* imgState; const unsigned long long* raise;
@@ -80,12 +80,14 @@ __global__ void k_tiles_finish(TileFinishArgs a) {
   const double zMin = (double)lo, zMax = (double)hi;
   if (zMin == zMax) st = TILEST_GENERAL;                                   // constant image: no stream at all
   uint8_t bIsInt = 0;
-  if (isFlt && st == TILEST_OK) {
+  bool allIntMismatch = false;
+  const bool hard = (r.flags & FASTF_NAN) || zMin == zMax;                // obstacles that do not depend on maxZError
+  if (isFlt && (st == TILEST_OK || !hard)) {
     if ((zMin == 0 && __double_as_longlong(zMin) < 0) || (zMax == 0 && __double_as_longlong(zMax) >= 0)) st = TILEST_GENERAL;   // sign of a zero extreme
     bool allInt = !(r.flags & FASTF_NOT_INT);
     const double lim = sizeof(T) == 4 ? 8388608.0 : 9007199254740992.0;
     allInt = allInt && zMin >= -lim && zMin <= lim && zMax >= -lim && zMax <= lim;             // Lerc.cpp:1490-1500
-    if (allInt) { const double f = floor(a.maxZErr); if ((f > 0.5 ? f : 0.5) != a.maxZErr) st = TILEST_GENERAL; bIsInt = 1; }
+    if (allInt) { const double f = floor(a.maxZErr); if ((f > 0.5 ? f : 0.5) != a.maxZErr) allIntMismatch = true; bIsInt = 1; }
     for (int c = 0; c < a.ra.n; c++) {                                     // PruneCandidates on row 0 (Lerc2.cpp:1322-1339)
       const double m = __longlong_as_double((long long)a.raise[(size_t)img * 9 + c]);
       if (!(__ddiv_rn(m, a.ra.fac[c]) > __dmul_rn(a.maxZErr, 0.5))) st = TILEST_GENERAL;     // a candidate survived: full scan needed
@@ -96,6 +98,9 @@ __global__ void k_tiles_finish(TileFinishArgs a) {
   if ((double)nData * 8 < (double)nPix * 1.5 && nData < 4 * oneSweepBytes && (rows > 8 || cols > 8)) st = TILEST_GENERAL;    // 16x16 retry (Lerc2.cpp:333-357)
   if (oneSweepBytes <= nData) st = TILEST_GENERAL;                         // one sweep raw wins (Lerc2.cpp:364-373)
   const unsigned long long total = (unsigned long long)a.dataStart + nData;
+  // all-integer floats at a bound that is not max(0.5, floor(.)): the LUT / candidate / size tests above were made with the wrong bound;
+  // unless something independent of the bound stands in the way, the image only needs the other bound
+  if (allIntMismatch) st = (!hard && !((zMin == 0 && __double_as_longlong(zMin) < 0) || (zMax == 0 && __double_as_longlong(zMax) >= 0))) ? TILEST_ALLINT : TILEST_GENERAL;
   if ((r.flags & FASTF_OVERFLOW) || start + total > a.outCap) st = TILEST_OVERFLOW;
   a.status[img] = st;
   if (st != TILEST_OK) return;
@@ -250,8 +255,23 @@ ErrCode encodeTilesT(Context* ctx, const TilesGeom& g, const void* dData, double
   bool fast = false;
   if constexpr (sizeof(T) > 1) fast = tilesFastEligible<T>(g, maxZErr);
   if constexpr (sizeof(T) > 1) if (fast) {
-    const ErrCode e = encodeTilesFast<T>(ctx, g, dData, maxZErr, dOut, outCap, status, end);
+    ErrCode e = encodeTilesFast<T>(ctx, g, dData, maxZErr, dOut, outCap, status, end);
     if (e != Ok) return e;
+    if (PixelTraits<T>::isFloat) {
+      // integer-valued float rasters (elevation models stored as float): every tile wants max(0.5, floor(maxZErr)) (Lerc.cpp:1490-1502).
+      // One more fused pass with that bound codes them all, instead of the general encoder tile by tile.
+      // Tiles the first pass had to hand to the general encoder for another reason (constant, NaN, ...) stay handed over; the second
+      // pass is only possible when the first one produced no blob worth keeping.
+      long long nAllInt = 0, nKeep = 0;
+      for (long long i = 0; i < nImg; i++) { nAllInt += status[(size_t)i] == TILEST_ALLINT; nKeep += status[(size_t)i] == TILEST_OK || status[(size_t)i] == TILEST_OVERFLOW; }
+      if (nAllInt > 0 && nKeep == 0) {
+        const std::vector<uint32_t> first = status;
+        e = encodeTilesFast<T>(ctx, g, dData, std::max(0.5, std::floor(maxZErr)), dOut, outCap, status, end);
+        if (e != Ok) return e;
+        for (long long i = 0; i < nImg; i++)
+          if (first[(size_t)i] != TILEST_ALLINT && status[(size_t)i] != TILEST_OVERFLOW) status[(size_t)i] = TILEST_GENERAL;
+      }
+    }
     bool allOk = true, overflow = false;
     for (long long i = 0; i < nImg; i++) { allOk = allOk && status[(size_t)i] == TILEST_OK; overflow = overflow || status[(size_t)i] == TILEST_OVERFLOW; }
     if (allOk) {

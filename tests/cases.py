@@ -122,6 +122,13 @@ def tile_cases(seed=5):
     mixed[128:192, 64:128] = rng.random((64, 64)).astype(np.float32) * 1e30   # raw / one sweep
     cases.append(("f32_mixed_decisions", mixed, 64, 64, 0.01))
     cases.append(("f32_lossless", f[:100, :100].copy(), 50, 50, 0))
+    whole = np.round(f)                                        # every tile all-integer: second fused pass at max(0.5, floor(maxZErr))
+    cases.append(("f32_all_integer_0.01", whole, 64, 64, 0.01))
+    cases.append(("f32_all_integer_3.7", whole, 64, 64, 3.7))
+    whole0 = whole.copy()
+    whole0[0:64, 0:64] = 7.0                                   # ... but one of them constant
+    cases.append(("f32_all_integer_one_const", whole0, 64, 64, 0.01))
+    cases.append(("f64_all_integer_0.3", np.round(f.astype(np.float64) * 3), 48, 48, 0.3))
     return cases
 
 
