@@ -695,6 +695,250 @@ static size_t fpl_decode(const u8* p, size_t avail, void* data, int isDouble, in
 }
 
 /* ------------------------------------------------------------------------------------------- */
+/* FPL, ENCODE side.  fpl_Lerc2Ext.cpp:62-101 (test blocks), :103-131 (byte derivatives), :170-232 (testBlocksSize), :238-330
+ * (getBestLevel2), :341-395 (selectInitialLinearOrCrossDelta), :397-436 (compressedLength / EncodeHuffmanFlt), :438-608
+ * (ComputeHuffmanCodesFlt[Slice]); fpl_Compression.cpp:53-112 (compress_buffer / getEntropySize); fpl_EsriHuffman.cpp:82-259
+ * (PackBits), :262-452 (EncodeHuffman); fpl_UnitTypes.cpp:39-51, :83-97, :119-136, :302-357, :436-517 (float transform, split
+ * subtraction, row / cross derivatives); fpl_Predictor.cpp:30-76.
+ *
+ * One deviation, on purpose: the reference leaves the read-ahead word behind every Huffman-coded byte plane uninitialised (it
+ * is malloc'ed and never written, fpl_EsriHuffman.cpp:403-448, and copied into the blob with the plane).  This restatement
+ * writes zeros there, like the 8-bit Huffman path does; tests compare reference-made blobs with those 4 bytes per plane (and the
+ * checksum they feed) set aside. */
+
+enum { FPL_PRIME = 7, FPL_MAX_DELTA = 5, FPL_SAMPLE = 8 * 1024 };
+
+/* Test switch: 0 makes the encoder skip the lossless float codec (raw tiling / one sweep is written instead, as a build without
+ * fpl_*.cpp would), for checking a product that does not write FPL yet.  Returns the previous setting.  Default: on = the reference. */
+static int g_fplEncoder = 1;
+int lo_fpl_encoder(int on) { int was = g_fplEncoder; g_fplEncoder = on != 0; return was; }
+
+typedef struct { u8 pred; int nPlanes; u8 level[8]; u32 size[8]; u8* buf[8]; } fpl_plan;
+
+static void fpl_plan_free(fpl_plan* pl) { for (int i = 0; i < 8; i++) { free(pl->buf[i]); pl->buf[i] = NULL; } pl->nPlanes = 0; }
+
+static u32 fpl_sub32(u32 a, u32 b) { return ((a - b) & 0x007FFFFFu) | (((((a >> 23) & 0x1FF) - ((b >> 23) & 0x1FF)) & 0x1FF) << 23); }
+static u64 fpl_sub64(u64 a, u64 b) {
+  return (((a & 0x000FFFFFFFFFFFFFull) - (b & 0x000FFFFFFFFFFFFFull)) & 0x000FFFFFFFFFFFFFull) | (((((a >> 52) & 0xFFF) - ((b >> 52) & 0xFFF)) & 0xFFF) << 52);
+}
+static u32 fpl_bits_to_front(u32 a) { return (a & 0x007FFFFFu) | (((a >> 23) & 0xFF) << 24) | ((a >> 31) << 23); }
+
+/* fpl_Compression.cpp:85-112: entropy of every 7th byte, in whole bytes */
+static long fpl_entropy_size(const u8* p, size_t size) {
+  unsigned long table[256]; memset(table, 0, sizeof table);
+  int total = 0;
+  for (size_t i = 0; i < size; i += FPL_PRIME) { table[p[i]]++; total++; }
+  double bitsSum = 0;
+  for (int i = 0; i < 256; i++) {
+    if (!table[i]) continue;
+    double pr = (double)total / table[i];
+    double bits = log2(pr);
+    bitsSum += bits * table[i];
+  }
+  return (long)((bitsSum + 7) / 8);
+}
+
+/* row derivative (level 1 inside every row) and column derivative; both run backwards, so every element sees its
+ * neighbour's old value */
+static void fpl_rows_derivative(void* data, int isDouble, size_t cols, size_t rows) {
+  for (size_t r = 0; r < rows; r++)
+    for (size_t i = cols - 1; i >= 1; i--) {
+      if (isDouble) { u64* d = (u64*)data + r * cols; d[i] = fpl_sub64(d[i], d[i - 1]); }
+      else { u32* d = (u32*)data + r * cols; d[i] = fpl_sub32(d[i], d[i - 1]); }
+    }
+}
+static void fpl_cols_derivative(void* data, int isDouble, size_t cols, size_t rows) {
+  for (size_t c = 0; c < cols; c++)
+    for (size_t r = rows - 1; r >= 1; r--) {
+      if (isDouble) { u64* d = (u64*)data; d[r * cols + c] = fpl_sub64(d[r * cols + c], d[(r - 1) * cols + c]); }
+      else { u32* d = (u32*)data; d[r * cols + c] = fpl_sub32(d[r * cols + c], d[(r - 1) * cols + c]); }
+    }
+}
+
+typedef struct { long top, height; } fpl_block;
+
+/* fpl_Lerc2Ext.cpp:62-101.  Returns the number of blocks (<= count). */
+static int fpl_test_blocks(int width, int height, fpl_block** out) {
+  size_t size = (size_t)width * (size_t)height;
+  double t = round((double)size / FPL_SAMPLE);
+  int count = (int)round(sqrt(t + 1));
+  int bh = FPL_SAMPLE / width;
+  if (bh < 4) bh = 4;
+  while (count * bh > height && count > 1) count--;
+  float topMargin = (float)((height - count * bh) / (2.0 * count));
+  float delta = 2.0f * topMargin + bh;
+  fpl_block* b = (fpl_block*)malloc((size_t)count * sizeof(fpl_block));
+  int n = 0;
+  for (int i = 0; i < count; i++) {
+    fpl_block tb; tb.top = (long)(topMargin + delta * i); tb.height = bh;
+    if (tb.top < 0) tb.top = 0;
+    if (tb.top + tb.height > height) tb.height = height - tb.top;
+    if (tb.height > 0) b[n++] = tb;
+  }
+  *out = b;
+  return n;
+}
+
+/* fpl_Lerc2Ext.cpp:170-232 with test_first_byte_delta = true */
+static size_t fpl_test_blocks_size(const fpl_block* blk, int nBlk, int unit, const u8* data, long width) {
+  size_t ret = 0;
+  for (int b = 0; b < nBlk; b++) {
+    size_t start = (size_t)unit * (size_t)blk[b].top * (size_t)width, length = (size_t)blk[b].height * (size_t)width;
+    u8* plane = (u8*)malloc(length);
+    for (int byte = 0; byte < unit; byte++) {
+      for (size_t i = 0; i < length; i++) plane[i] = data[start + (size_t)byte + i * (size_t)unit];
+      size_t e1 = (size_t)fpl_entropy_size(plane, length);
+      int off = FPL_PRIME * (((int)length - 1) / FPL_PRIME);                    /* setDerivativePrime :103-116 */
+      for (; off >= 1; off -= FPL_PRIME) plane[off] = (u8)(plane[off] - plane[off - 1]);
+      size_t e2 = (size_t)fpl_entropy_size(plane, length);
+      ret += e1 < e2 ? e1 : e2;
+    }
+    free(plane);
+  }
+  return ret;
+}
+
+/* fpl_Lerc2Ext.cpp:238-330 */
+static int fpl_best_level(const u8* p, size_t size, int maxDelta) {
+  if (maxDelta == 0) return 0;
+  const unsigned target = FPL_SAMPLE;
+  double t = round((double)size / target);
+  int count = (int)round(sqrt(t + 1));
+  while ((size_t)((unsigned)count * target) > size && count > 0) count--;
+  if (count == 0) return 0;                       /* no snippet: every level estimates 0 bytes, level 0 stays */
+  float topMargin = (float)(((unsigned)(int)size - (unsigned)count * target) / (2.0 * count));
+  float delta = 2.0f * topMargin + target;
+  long* start = (long*)malloc((size_t)count * sizeof(long)); int* len = (int*)malloc((size_t)count * sizeof(int));
+  int n = 0;
+  for (int i = 0; i < count; i++) {
+    long st = (long)(topMargin + delta * i); int ln = (int)target;
+    if (st < 0) st = 0;
+    if (st + ln > (int)size) ln = (int)size - (int)st;
+    if (ln > 0) { start[n] = st; len[n] = ln; n++; }
+  }
+  u8* copy = (u8*)malloc(size); memcpy(copy, p, size);
+  size_t best = 0; int ret = 0;
+  for (int l = 0; l <= maxDelta; l++) {
+    if (l > 0)
+      for (int s = 0; s < n; s++)
+        for (int i = (int)start[s] + len[s] - 1; i >= (int)start[s] + l; i--) copy[i] = (u8)(copy[i] - copy[i - 1]);
+    size_t comp = 0;
+    for (int s = 0; s < n; s++) comp += (size_t)fpl_entropy_size(copy + start[s], (size_t)len[s]);
+    if (comp < best || l == 0) { best = comp; ret = l; } else break;
+  }
+  free(copy); free(start); free(len);
+  return ret;
+}
+
+/* fpl_EsriHuffman.cpp:82-166 / :169-259.  out == NULL: size only. */
+static long fpl_packbits_encode(const u8* ptr, size_t size, u8* out) {
+  long curr = 0, litPos = -1; int lit = 0;
+  for (size_t i = 0; i <= size;) {
+    int b = (i == size) ? -1 : ptr[i];
+    int rep = 0;
+    while (i < size - 1 && b == ptr[i + 1] && rep < 128) { i++; rep++; }
+    i++;
+    if (rep == 0 && b >= 0) {
+      if (litPos < 0) { litPos = curr; curr++; }
+      if (out) out[curr] = (u8)b;
+      curr++; lit++;
+      if (lit == 128) { if (out) out[litPos] = (u8)(lit - 1); lit = 0; litPos = -1; }
+    } else {
+      if (lit > 0) { if (out) out[litPos] = (u8)(lit - 1); litPos = -1; lit = 0; }
+      if (rep > 0) { if (out) { out[curr] = (u8)(127 + rep); out[curr + 1] = (u8)b; } curr += 2; }
+    }
+  }
+  return curr;
+}
+
+/* fpl_EsriHuffman.cpp:316-452 with use_rle.  Returns a malloc'ed buffer and its size; 0 = failure (:340-343). */
+static size_t fpl_plane_encode(const u8* in, size_t n, u8** outBuf) {
+  int histo[256]; memset(histo, 0, sizeof histo);
+  for (size_t i = 0; i < n; i++) histo[in[i]]++;
+  int distinct = 0;
+  for (int i = 0; i < 256; i++) distinct += histo[i] > 0;
+  if (distinct < 2) {                                                           /* one value: flag, value, count */
+    u8* o = (u8*)calloc(6, 1); u32 len = (u32)n;
+    o[0] = 1; o[1] = in[0]; memcpy(o + 2, &len, 4);
+    *outBuf = o; return 6;
+  }
+  uint16_t hl[256]; u32 hc[256]; int numBytes = 0;
+  if (!lo_huffman_lengths(histo, 256, hl, hc) || !huff_total_bytes(histo, hl, 256, &numBytes) || numBytes <= 0) return 0;
+  long pb = fpl_packbits_encode(in, n, NULL);
+  if (pb > 0 && pb < numBytes && pb < (long)n) {
+    u8* o = (u8*)malloc((size_t)pb + 1);
+    o[0] = 3; fpl_packbits_encode(in, n, o + 1);
+    *outBuf = o; return (size_t)pb + 1;
+  }
+  if (numBytes >= (int)n) {
+    u8* o = (u8*)malloc(n + 1);
+    o[0] = 2; memcpy(o + 1, in, n);
+    *outBuf = o; return n + 1;
+  }
+  u8* o = (u8*)calloc((size_t)numBytes + 1, 1);
+  o[0] = 0;
+  size_t tb = huff_write_table(o + 1, hl, hc, 256, 5);
+  if (!tb) { free(o); return 0; }
+  msb_writer w = {o + 1 + tb, 0};
+  for (size_t i = 0; i < n; i++) msb_put(&w, hc[in[i]], hl[in[i]]);
+  size_t total = 1 + tb + 4 * ((size_t)(w.bitPos >> 5) + ((w.bitPos & 31) ? 1 : 0) + 1);
+  *outBuf = o; return total;
+}
+
+/* fpl_Lerc2Ext.cpp:455-608 */
+static int fpl_plan_slice(const void* input, int isDouble, size_t cols, size_t rows, fpl_plan* plan) {
+  const int unit = isDouble ? 8 : 4;
+  const size_t n = cols * rows;
+  fpl_plan_free(plan);
+  u8* values = (u8*)malloc(n * (size_t)unit); memcpy(values, input, n * (size_t)unit);
+  if (!isDouble) { u32* v = (u32*)values; for (size_t i = 0; i < n; i++) v[i] = fpl_bits_to_front(v[i]); }
+  u8* copy = (u8*)malloc(n * (size_t)unit); memcpy(copy, values, n * (size_t)unit);
+  fpl_block* blk = NULL; int nBlk = fpl_test_blocks((int)cols, (int)rows, &blk);
+  size_t stats[3];
+  stats[0] = fpl_test_blocks_size(blk, nBlk, unit, copy, (long)cols);
+  fpl_rows_derivative(copy, isDouble, cols, rows);
+  stats[1] = fpl_test_blocks_size(blk, nBlk, unit, copy, (long)cols);
+  fpl_cols_derivative(copy, isDouble, cols, rows);
+  stats[2] = fpl_test_blocks_size(blk, nBlk, unit, copy, (long)cols);
+  free(copy); free(blk);
+  int pred = 0;
+  if (stats[1] < stats[pred]) pred = 1;
+  if (stats[2] < stats[pred]) pred = 2;
+  if (pred >= 1) fpl_rows_derivative(values, isDouble, cols, rows);
+  if (pred == 2) fpl_cols_derivative(values, isDouble, cols, rows);
+  const int maxDelta = FPL_MAX_DELTA - pred;
+  u8* plane = (u8*)malloc(n);
+  int ok = 1;
+  plan->pred = (u8)pred;
+  for (int byte = 0; byte < unit && ok; byte++) {
+    for (size_t i = 0; i < n; i++) plane[i] = values[i * (size_t)unit + (size_t)byte];
+    int level = fpl_best_level(plane, n, maxDelta);
+    for (int l = 1; l <= level; l++) for (int i = (int)n - 1; i >= l; i--) plane[i] = (u8)(plane[i] - plane[i - 1]);   /* :118-131 */
+    size_t sz = fpl_plane_encode(plane, n, &plan->buf[byte]);
+    if (!sz) { ok = 0; break; }
+    plan->level[byte] = (u8)level; plan->size[byte] = (u32)sz; plan->nPlanes = byte + 1;
+  }
+  free(plane); free(values);
+  if (!ok) fpl_plan_free(plan);
+  return ok;
+}
+
+static int fpl_plan_make(const void* input, int isDouble, int nCols, int nRows, int nDepth, fpl_plan* plan) {   /* :438-453 */
+  if (nDepth == 1) return fpl_plan_slice(input, isDouble, (size_t)nCols, (size_t)nRows, plan);
+  return fpl_plan_slice(input, isDouble, (size_t)nDepth, (size_t)nCols * (size_t)nRows, plan);
+}
+static int fpl_plan_bytes(const fpl_plan* pl) { int64_t r = 1; for (int i = 0; i < pl->nPlanes; i++) r += (int64_t)pl->size[i] + 6; return r > INT_MAX ? -1 : (int)r; }   /* :397-408 */
+static u8* fpl_plan_write(const fpl_plan* pl, u8* p) {                                                              /* :410-436 */
+  *p++ = pl->pred;
+  for (int i = 0; i < pl->nPlanes; i++) {
+    *p++ = (u8)i; *p++ = pl->level[i];
+    memcpy(p, &pl->size[i], 4); p += 4;
+    memcpy(p, pl->buf[i], pl->size[i]); p += pl->size[i];
+  }
+  return p;
+}
+
+/* ------------------------------------------------------------------------------------------- */
 /* shared helpers of the typed code                                                               */
 
 static int mask_bit(const u8* bits, int64_t k) { return (bits[k >> 3] & (0x80 >> (k & 7))) != 0; }
@@ -774,6 +1018,7 @@ typedef struct {
   int encodeMask, oneSweep, imageMode;
   u32 maxQ;
   uint16_t hLen[256]; u32 hCode[256]; int haveHuff;
+  fpl_plan fpl;          /* lossless float codec: the coded byte planes wait here between sizing and writing */
 } band_state;
 
 enum { IEM_TILING = 0, IEM_DELTA_HUFFMAN = 1, IEM_HUFFMAN = 2, IEM_DELTA_DELTA_HUFFMAN = 3 };

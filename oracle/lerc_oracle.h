@@ -70,6 +70,7 @@ uint32_t lo_fletcher32(const uint8_t* bytes, int len);
 size_t   lo_rle_size(const uint8_t* src, size_t n);
 size_t   lo_rle_encode(const uint8_t* src, size_t n, uint8_t* dst);           /* returns bytes written */
 int      lo_rle_decode(const uint8_t* src, size_t srcLen, uint8_t* dst, size_t dstLen);
+int      lo_fpl_encoder(int on);   /* test switch: 0 = float maxZError 0 is written without the FPL codec; returns the previous setting */
 int      lo_huffman_lengths(const int* histo, int n, uint16_t* lenOut, uint32_t* codeOut); /* 1 on success */
 
 #ifdef __cplusplus

@@ -193,9 +193,17 @@ def ref_lib():
     return LercLib(p) if p else None
 
 
-def oracle_lib():
+PRODUCT_WRITES_FPL = False     # the product's encoder still writes float maxZError 0 as raw tiling
+
+
+def oracle_lib(fpl_encoder=None):
+    """fpl_encoder: True = the reference's behaviour (lossless float codec on encode), None = what the product writes today"""
     p = _first(os.path.join(ROOT, "oracle", "_build", "liblerc_oracle.so"))
-    return LercLib(p, prefix="lo_") if p else None
+    if not p:
+        return None
+    lib = LercLib(p, prefix="lo_")
+    lib.lib.lo_fpl_encoder(1 if (PRODUCT_WRITES_FPL if fpl_encoder is None else fpl_encoder) else 0)
+    return lib
 
 
 def product_lib():
@@ -252,3 +260,52 @@ def tile_windows(n_rows, n_cols, tile_rows, tile_cols):
     for y in range(0, n_rows, tile_rows):
         for x in range(0, n_cols, tile_cols):
             yield slice(y, min(y + tile_rows, n_rows)), slice(x, min(x + tile_cols, n_cols))
+
+
+def fletcher32(data):
+    """Lerc2.cpp:1012-1064 over a bytes-like object (numpy; big-endian 16-bit words, sums start at 0xffff, odd tail byte << 8)"""
+    b = np.frombuffer(bytes(data), dtype=np.uint8).astype(np.uint64)
+    n = len(b) // 2
+    w = (b[0:2 * n:2] << np.uint64(8)) + b[1:2 * n:2]
+    if len(b) & 1:
+        w = np.append(w, b[-1] << np.uint64(8))
+    # sum1 = 0xffff + sum(w), sum2 = sum of the running sum1 values; both mod 65535 with 0 written as 0xffff (end-around carry)
+    k = np.arange(len(w), 0, -1, dtype=np.uint64)
+    s1 = (0xffff + int(w.sum())) % 65535
+    s2 = (0xffff + 0xffff * len(w) + int((w * k % np.uint64(65535)).sum())) % 65535
+    s1 = s1 or 0xffff
+    s2 = s2 or 0xffff
+    return (s2 << 16) | s1
+
+
+def fpl_normalize(blob):
+    """The reference leaves the read-ahead word behind every Huffman-coded byte plane of its lossless float codec uninitialised
+    (fpl_EsriHuffman.cpp:403-448: malloc'ed, never written, copied into the blob).  Returns the blob with those 4 bytes per plane
+    zeroed and the band checksums redone, so that reference-made blobs can be compared byte for byte; any other blob is returned
+    unchanged (v6 float bands only)."""
+    import struct
+    b = bytearray(blob)
+    pos = 0
+    while pos + 90 <= len(b) and b[pos:pos + 6] == b"Lerc2 ":
+        version = struct.unpack_from("<i", b, pos + 6)[0]
+        if version != 6:
+            break
+        n_rows, n_cols, n_depth, n_valid, _mb, blob_size, dt, _more = struct.unpack_from("<8i", b, pos + 14)
+        z_min, z_max = struct.unpack_from("<2d", b, pos + 58)
+        p = pos + 90
+        p += 4 + struct.unpack_from("<i", b, p)[0]
+        if dt in (6, 7) and n_valid > 0 and z_min != z_max:
+            sz = 4 if dt == 6 else 8
+            ranges = bytes(b[p:p + 2 * sz * n_depth])
+            p += 2 * sz * n_depth
+            if ranges[:sz * n_depth] != ranges[sz * n_depth:] and b[p] == 0 and b[p + 1] == 3 and struct.unpack_from("<d", b, pos + 50)[0] == 0:
+                p += 3
+                for _ in range(sz):
+                    size = struct.unpack_from("<I", b, p + 2)[0]
+                    if b[p + 6] == 0:
+                        b[p + 6 + size - 4:p + 6 + size] = b"\0\0\0\0"
+                    p += 6 + size
+                assert p == pos + blob_size
+                struct.pack_into("<I", b, pos + 10, fletcher32(b[pos + 14:pos + blob_size]))
+        pos += blob_size
+    return bytes(b)

@@ -23,7 +23,7 @@ FPL_CASES = {"f32_lossless_raw", "f64_lossless_raw"}   # reference uses the FPL 
 def oracle():
     if oracle_lib() is None:
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")])
-    lib = oracle_lib()
+    lib = oracle_lib(fpl_encoder=True)
     assert lib is not None
     return lib
 
@@ -170,6 +170,24 @@ def test_fpl_blobs_decode_like_the_reference(oracle):
             h.update(mask.tobytes())
         assert h.hexdigest() == str(g["hash_" + name]), f"{name}: decoded pixels differ from the reference's"
         n_fpl += b"\x03" in blob[90:140]           # (the image-mode byte 3 sits right behind header, mask count and ranges)
+    assert n_fpl >= 10
+
+
+def test_fpl_encoder_makes_the_references_blobs(oracle):
+    """float rasters at maxZError 0: the oracle's lossless float ENCODER (predictor choice from entropy estimates of test blocks,
+    per-plane byte-delta level, Huffman / PackBits / raw / one-value planes, the 10 % rule against raw tiling) writes the blobs
+    the reference wrote (fpl_ref.npz) - up to the 4 uninitialised bytes the reference leaves behind each Huffman-coded plane"""
+    from lercapi import fpl_normalize
+    g = np.load(os.path.join(GOLD, "fpl_ref.npz"))
+    n_fpl = 0
+    for name, arr, kw in fpl_cases():
+        want = g["blob_" + name].tobytes()
+        st, blob, _ = oracle.encode(arr, 0.0, **kw)
+        assert st == 0, name
+        assert fpl_normalize(blob) == blob, name
+        assert blob == fpl_normalize(want), f"{name}: blob differs from the reference's"
+        assert oracle.compute_size(arr, 0.0, **kw) == (0, len(want)), name
+        n_fpl += b"\x03" in blob[90:140]
     assert n_fpl >= 10
 
 
