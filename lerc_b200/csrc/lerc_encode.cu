@@ -705,6 +705,12 @@ namespace {
 
 template <class V> bool d2h(Context* ctx, V* hostDst, const void* dSrc, size_t count);
 
+}  // namespace
+}  // namespace lerc
+#include "lerc_fpl_encode.cuh"
+namespace lerc {
+namespace {
+
 // Lerc2::TryBitPlaneCompression (Lerc2.cpp:1071-1229): device counts, the reference's decision in double precision on the host
 template <class T>
 bool tryBitPlane(Context* ctx, const T* dData, const uint8_t* dBitsOrNull, int nRows, int nCols, int nDepth, int numValid, double eps, double& newMaxZErr) {
@@ -1022,6 +1028,7 @@ ErrCode encodeBandT(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
   double maxZErr = a.maxZErr;
   std::vector<uint8_t> prefix;                      // header .. flags, assembled on the host
   bool oneSweep = false; int imageMode = IEM_Tiling; bool writeTiles = false, writeHuffman = false;
+  FplPlan fpl;
   HuffmanTable huff;
   int mbFinal = 8;
   size_t rangesBytes = 0;
@@ -1153,6 +1160,13 @@ ErrCode encodeBandT(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
         if (nHuff < nTiling) { imageMode = plain ? IEM_Huffman : IEM_DeltaHuffman; huff = plain ? t0 : t1; nData = nHuff; }
       }
     }
+    if constexpr (isFlt) {
+      if (hd.tryHuffmanFlt()) {                                                               // Lerc2.cpp:305-328: lossless float codec
+        if (!planFpl<T>(ctx, (const T*)a.dData, a.dValidBytes, a.nCols, a.nRows, nDepth, fpl)) return Failed;
+        nHuff = std::min<long long>(fpl.bytes(), INT_MAX);
+        if ((double)nHuff < (double)nTiling * 0.9) { nData = nHuff; imageMode = IEM_DeltaDeltaHuffman; }   // at least 10 % better than tiling
+      }
+    }
     // 16x16 retry when the bit rate is tiny (Lerc2.cpp:333-357)
     const size_t oneSweepBytes = sizeof(T) * (size_t)nDepth * (size_t)numValid;
     if (((size_t)nTiling * 8 < (size_t)nPix * nDepth * 1.5) && ((size_t)nTiling < 4 * oneSweepBytes) &&
@@ -1200,7 +1214,7 @@ ErrCode encodeBandT(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
     if (!allDepthsConst) {
       tail[tp++] = oneSweep ? 1 : 0;
       if (!oneSweep && (hd.tryHuffmanInt() || hd.tryHuffmanFlt())) tail[tp++] = (uint8_t)imageMode;
-      if (writeHuffman) { huffTableBytes = huff.write(tail.data() + tp, a.version); if (!huffTableBytes) return Failed; tp += huffTableBytes; }
+      if (writeHuffman && !isFlt) { huffTableBytes = huff.write(tail.data() + tp, a.version); if (!huffTableBytes) return Failed; tp += huffTableBytes; }
     }
     uint8_t* hTail = (uint8_t*)ctx->pinnedAlloc(tp);
     if (!hTail) return Failed;
@@ -1219,7 +1233,11 @@ ErrCode encodeBandT(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
         }
         pos += len * (size_t)numValid;
       } else if (writeHuffman) {
-        if constexpr (!isFlt && sizeof(T) == 1) {
+        if constexpr (isFlt) {                                                                // Lerc2.cpp:437-449
+          size_t w = 0;
+          if (imageMode != IEM_DeltaDeltaHuffman || !writeFpl(ctx, fpl, blob + pos, w)) return Failed;
+          pos += w;
+        } else if constexpr (sizeof(T) == 1) {
           if (!ensureChunkBase()) return Failed;
           HuffArgs ha;
           ha.data = a.dData; ha.bits = dBitsOrNull; ha.chunkBase = dChunkBase; ha.H = a.nRows; ha.W = a.nCols; ha.D = nDepth;

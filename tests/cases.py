@@ -206,6 +206,33 @@ def fpl_cases(seed=21):
     return cases
 
 
+def fpl_encode_cases(seed=23):
+    """more float rasters for maxZError = 0, ENCODE parity with the oracle (itself pinned to the reference's blobs on fpl_cases):
+    every predictor (none / row / row + column), byte-delta levels > 0, one-value, PackBits, stored and Huffman planes, inputs
+    shorter than one 8 KB sample, nDepth > 1, long runs that cross PackBits' 129-byte chunks"""
+    rng = np.random.default_rng(seed)
+    cases = [
+        ("f32_sparse", np.where(rng.random((300, 400)) < 0.01, 1.5, 0).astype(np.float32), {}),
+        ("f32_ramp", np.arange(500 * 600, dtype=np.float32).reshape(500, 600) * np.float32(0.37), {}),
+        ("f64_ramp", np.arange(300 * 200, dtype=np.float64).reshape(300, 200) * 0.001, {}),
+        ("f32_sin", np.sin(np.arange(512 * 512, dtype=np.float32).reshape(512, 512) / 97).astype(np.float32), {}),
+        ("f32_depth4", rng.random((100, 120, 4)).astype(np.float32) * np.float32(3), {"n_depth": 4}),
+        ("f32_tiny", rng.random((5, 7)).astype(np.float32), {}),
+        ("f32_8191", rng.random((1, 8191)).astype(np.float32), {}),
+        ("f32_8192", rng.random((1, 8192)).astype(np.float32), {}),
+        ("f32_thin", rng.random((9000, 3)).astype(np.float32), {}),
+        ("f32_quarters", (np.round(smooth_field(400, 400)) / 4).astype(np.float32), {}),
+        ("f32_long_runs", np.repeat(np.repeat(rng.integers(0, 3, (4, 5)).astype(np.float32), 100, 0), 200, 1), {}),
+        ("f64_smooth", smooth_field(300, 500) * 1.000001, {}),
+    ]
+    m = np.ones((300, 400), np.uint8)
+    m[50:200, 100:300] = 0
+    nan = c2_raster(300, 400)
+    nan[100:120, 50:350] = np.nan                              # NaN at valid and at masked pixels
+    cases.append(("f32_nan_and_mask", nan, {"mask": m}))
+    return cases
+
+
 def bitplane_cases(seed=31):
     """(name, array, kwargs) for maxZErr == 777, the reference's "cheat code" for the integer bit-plane mode (Lerc2.cpp:210-217,
     :1071-1229): low bit planes that look like noise are dropped by raising maxZError to half of the last plane kept."""

@@ -193,7 +193,7 @@ def ref_lib():
     return LercLib(p) if p else None
 
 
-PRODUCT_WRITES_FPL = False     # the product's encoder still writes float maxZError 0 as raw tiling
+PRODUCT_WRITES_FPL = True      # float maxZError 0 goes through the lossless float codec like in the reference
 
 
 def oracle_lib(fpl_encoder=None):

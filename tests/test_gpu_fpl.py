@@ -1,4 +1,6 @@
-"""GPU tests (-m gpu): decoding blobs written by the reference's lossless float codec (FPL, image mode IEM_DeltaDeltaHuffman,
+"""GPU tests (-m gpu): the lossless float codec.  ENCODE (lerc_b200/csrc/lerc_fpl_encode.cuh): float rasters at maxZError 0 must
+come out as the reference's blobs (fpl_ref.npz, up to the 4 uninitialised bytes the reference leaves per Huffman plane, see
+lercapi.fpl_normalize) and as the oracle's.  DECODE: blobs written by the reference's lossless float codec (FPL, image mode IEM_DeltaDeltaHuffman,
 fpl_*.cpp; product: lerc_b200/csrc/lerc_fpl_decode.cuh).  The blobs are the reference's own output for tests/cases.py:fpl_cases
 (committed in tests/golden/fpl_ref.npz with the hash of what the reference decodes); the oracle's decoder is pinned to those
 hashes by tests/test_oracle_vs_reference.py::test_fpl_blobs_decode_like_the_reference."""
@@ -8,17 +10,18 @@ import os
 import numpy as np
 import pytest
 
-from cases import fpl_cases
-from lercapi import ROOT, oracle_lib, product_lib
+from cases import fpl_cases, fpl_encode_cases
+from lercapi import ROOT, fpl_normalize, oracle_lib, product_lib
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(ROOT, "tests", "golden")
 CASES = fpl_cases()
+ENC_CASES = fpl_encode_cases()
 
 
 @pytest.fixture(scope="module")
 def libs():
-    prod, orc = product_lib(), oracle_lib()
+    prod, orc = product_lib(), oracle_lib(fpl_encoder=True)
     assert prod is not None and orc is not None
     return prod, orc
 
@@ -67,3 +70,33 @@ def test_corrupted_fpl_blobs_fail_like_the_oracle(libs):
         assert (s_p == 0) == (s_o == 0), f"byte {k}: status {s_p} vs oracle {s_o}"
         if s_o == 0:
             assert np.array_equal(d_p.view(np.uint8), d_o.view(np.uint8))
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_fpl_encoder_writes_the_references_blob(libs, case):
+    prod, orc = libs
+    name, arr, kw = case
+    g = np.load(os.path.join(GOLD, "fpl_ref.npz"))
+    want = fpl_normalize(g["blob_" + name].tobytes())
+    st, blob, whole = prod.encode(arr, 0.0, **kw)
+    assert st == 0
+    assert blob == want, f"len {len(blob)} vs the reference's {len(want)}"
+    assert not whole[len(blob):].any()                                       # Lerc.cpp:374: the rest of the buffer stays zero
+    assert prod.compute_size(arr, 0.0, **kw) == (0, len(want))
+    assert prod.encode(arr, 0.0, buf_size=len(want) - 1, **kw)[0] == 3      # BufferTooSmall
+
+
+@pytest.mark.parametrize("case", ENC_CASES, ids=[c[0] for c in ENC_CASES])
+def test_fpl_encoder_matches_oracle(libs, case):
+    prod, orc = libs
+    name, arr, kw = case
+    s_o, b_o, _ = orc.encode(arr, 0.0, **kw)
+    s_p, b_p, _ = prod.encode(arr, 0.0, **kw)
+    assert s_o == 0 and s_p == 0
+    assert b_p == b_o, f"len {len(b_p)} vs {len(b_o)}"
+    st, data, mask = prod.decode(b_p)
+    t_o, d_o, m_o = orc.decode(b_p)
+    assert st == 0 and t_o == 0 and np.array_equal(d_o.view(np.uint8), data.view(np.uint8))
+    a = np.ascontiguousarray(arr).reshape(data.shape)
+    valid = np.ones(data.shape[1:3], bool) if mask is None else mask[0].astype(bool)
+    assert np.array_equal(data[0][valid].view(np.uint8), a[0][valid].view(np.uint8))
