@@ -224,6 +224,7 @@ def fpl_encode_cases(seed=23):
         ("f32_quarters", (np.round(smooth_field(400, 400)) / 4).astype(np.float32), {}),
         ("f32_long_runs", np.repeat(np.repeat(rng.integers(0, 3, (4, 5)).astype(np.float32), 100, 0), 200, 1), {}),
         ("f64_smooth", smooth_field(300, 500) * 1.000001, {}),
+        ("f32_1024x2048", c2_raster(1024, 2048), {}),         # 16 test blocks / snippets, 2 M values per plane
     ]
     m = np.ones((300, 400), np.uint8)
     m[50:200, 100:300] = 0
