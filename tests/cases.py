@@ -234,6 +234,45 @@ def fpl_encode_cases(seed=23):
     return cases
 
 
+def fpl_fuzz_cases(seed=29, n=40):
+    """seeded random float rasters for maxZError = 0: degenerate shapes (one row / column, fewer than 7 values, wider than one
+    8 KB test block, exactly 8192 + 1 values), nDepth 1..5, masks, NaNs, value patterns that hit every plane coding"""
+    rng = np.random.default_rng(seed)
+    shapes = [(1, 2), (2, 1), (3, 3), (1, 9000), (9000, 1), (2, 5000), (4, 20000), (7, 7), (64, 129), (130, 64), (8, 1024), (1024, 8),
+              (1, 8193), (3, 2731), (2731, 3), (5, 1639), (90, 91), (17, 4000)]
+    cases = []
+    for it in range(n):
+        h, w = shapes[rng.integers(len(shapes))]
+        dt = np.float32 if rng.random() < 0.7 else np.float64
+        nd = 1 if rng.random() < 0.7 else int(rng.integers(2, 6))
+        if nd > 1 and h * w > 20000:
+            h, w = min(h, 50), min(w, 60)
+        kind = int(rng.integers(6))
+        shp = (h, w) if nd == 1 else (h, w, nd)
+        if kind == 0:
+            a = rng.random(shp)
+        elif kind == 1:
+            a = np.cumsum(rng.normal(0, 1, shp), axis=1)
+        elif kind == 2:
+            a = np.where(rng.random(shp) < 0.02, rng.random(shp), 0)
+        elif kind == 3:
+            a = np.round(rng.random(shp) * 4) / 4 + 1
+        elif kind == 4:
+            a = (np.arange(int(np.prod(shp))).reshape(shp) % int(rng.integers(2, 300))) * 0.5
+        else:
+            a = rng.integers(0, 2, shp) * 1e20 + rng.random(shp)
+        a = a.astype(dt)
+        kw = {}
+        if nd > 1:
+            kw["n_depth"] = nd
+        if rng.random() < 0.25:
+            kw["mask"] = (rng.random((h, w)) < 0.8).astype(np.uint8)
+        if rng.random() < 0.2 and nd == 1:
+            a[rng.random((h, w)) < 0.05] = np.nan
+        cases.append((f"{it:02d}_{dt.__name__}_{h}x{w}x{nd}_k{kind}", a, kw))
+    return cases
+
+
 def bitplane_cases(seed=31):
     """(name, array, kwargs) for maxZErr == 777, the reference's "cheat code" for the integer bit-plane mode (Lerc2.cpp:210-217,
     :1071-1229): low bit planes that look like noise are dropped by raising maxZError to half of the last plane kept."""

@@ -10,7 +10,7 @@ import os
 import numpy as np
 import pytest
 
-from cases import fpl_cases, fpl_encode_cases
+from cases import fpl_cases, fpl_encode_cases, fpl_fuzz_cases
 from lercapi import ROOT, fpl_normalize, oracle_lib, product_lib
 
 pytestmark = pytest.mark.gpu
@@ -100,3 +100,13 @@ def test_fpl_encoder_matches_oracle(libs, case):
     a = np.ascontiguousarray(arr).reshape(data.shape)
     valid = np.ones(data.shape[1:3], bool) if mask is None else mask[0].astype(bool)
     assert np.array_equal(data[0][valid].view(np.uint8), a[0][valid].view(np.uint8))
+
+
+def test_fpl_encoder_fuzz(libs):
+    """40 seeded random rasters (degenerate shapes, nDepth, masks, NaNs): status and blob equal the oracle's"""
+    prod, orc = libs
+    for name, arr, kw in fpl_fuzz_cases():
+        s_o, b_o, _ = orc.encode(arr, 0.0, **kw)
+        s_p, b_p, _ = prod.encode(arr, 0.0, **kw)
+        assert s_p == s_o, name
+        assert b_p == b_o, f"{name}: len {len(b_p or b'')} vs {len(b_o or b'')}"

@@ -12,7 +12,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from cases import all_cases, bitplane_cases, fpl_cases, nodata_cases
+from cases import all_cases, bitplane_cases, fpl_cases, fpl_encode_cases, fpl_fuzz_cases, nodata_cases
 from lercapi import ROOT, oracle_lib, ref_lib
 
 GOLD = os.path.join(ROOT, "tests", "golden")
@@ -189,6 +189,21 @@ def test_fpl_encoder_makes_the_references_blobs(oracle):
         assert oracle.compute_size(arr, 0.0, **kw) == (0, len(want)), name
         n_fpl += b"\x03" in blob[90:140]
     assert n_fpl >= 10
+
+
+def test_fpl_encoder_vs_live_reference(oracle):
+    """the extra encode cases and the fuzz set of the GPU tests, oracle against oracle/_ref (the unmodified reference compiled in
+    place) where that library exists -- it does not travel in git, so this one skips without it"""
+    from lercapi import fpl_normalize, ref_lib
+    ref = ref_lib()
+    if ref is None:
+        pytest.skip("oracle/_ref/libLerc_ref.so not built")
+    for name, arr, kw in fpl_encode_cases() + fpl_fuzz_cases():
+        s_r, b_r, _ = ref.encode(arr, 0.0, **kw)
+        s_o, b_o, _ = oracle.encode(arr, 0.0, **kw)
+        assert s_r == s_o, name
+        if s_r == 0:
+            assert fpl_normalize(b_r) == b_o, name
 
 
 def test_bitplane_mode_hashes(oracle):
