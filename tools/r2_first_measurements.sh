@@ -13,8 +13,11 @@ run_bench() {   # name, env assignments..., then bench arguments after --
   shift
   env "${envs[@]}" timeout 120 python bench.py "$@" --no-cpu-baseline > "$OUT/bench_$name.json" 2> "$OUT/bench_$name.err"
 }
-# 1. parity of the whole GPU suite with the defaults (includes the bit-plane tests that have only seen the simulator so far)
-timeout 200 python -m pytest tests -x -q -m gpu -p no:cacheprovider > "$OUT/tests_default.log" 2>&1
+# 1. parity of the whole GPU suite with the defaults.  Written after round 1's last GPU minute, simulator-validated only: the bit-plane
+#    tests, the lossless float (FPL) encoder tests, the all-integer tile cases.  No -x here: one surprise must not hide the rest.
+timeout 400 python -m pytest tests -q -m gpu -p no:cacheprovider > "$OUT/tests_default.log" 2>&1
+#    compute-sanitizer over the FPL encoder (new kernels: PackBits scans, plane Huffman writer)
+timeout 300 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_fpl.py -q -m gpu -p no:cacheprovider -k "encoder and (noisy or sparse or long_runs or depth4 or tiny)" > "$OUT/sanitizer_fpl.log" 2>&1
 # 2. parity of the variants (encoder / decoder paths are exercised by the parity, fast-path, fuzz and tile suites)
 LERC_B200_ENC=pipe timeout 200 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fastpath.py tests/test_gpu_tiles.py tests/test_gpu_large.py -x -q -m gpu -p no:cacheprovider > "$OUT/tests_enc_pipe.log" 2>&1
 LERC_B200_DEC=closure LERC_B200_DEC_RESOLVE=smem timeout 200 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fastpath.py tests/test_gpu_fuzz.py tests/test_gpu_large.py -x -q -m gpu -p no:cacheprovider > "$OUT/tests_dec_variants.log" 2>&1
