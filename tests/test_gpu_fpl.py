@@ -10,8 +10,8 @@ import os
 import numpy as np
 import pytest
 
-from cases import fpl_cases, fpl_encode_cases, fpl_fuzz_cases
-from lercapi import ROOT, fpl_normalize, oracle_lib, product_lib
+from cases import c2_raster, fpl_cases, fpl_encode_cases, fpl_fuzz_cases
+from lercapi import ROOT, fpl_normalize, oracle_lib, product_lib, ref_lib
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(ROOT, "tests", "golden")
@@ -110,3 +110,18 @@ def test_fpl_encoder_fuzz(libs):
         s_p, b_p, _ = prod.encode(arr, 0.0, **kw)
         assert s_p == s_o, name
         assert b_p == b_o, f"{name}: len {len(b_p or b'')} vs {len(b_o or b'')}"
+
+
+def test_fpl_full_size_lossless_round_trip(libs):
+    """BASELINE configs[1]'s raster (4096 x 4096 float32) at maxZError 0: the blob is the reference's (the oracle's where the
+    reference library is not on the box), and decode(encode(x)) == x bit for bit"""
+    prod, orc = libs
+    img = c2_raster(4096, 4096)
+    chk = ref_lib() or orc
+    s_r, b_r, _ = chk.encode(img, 0.0)
+    s_p, b_p, _ = prod.encode(img, 0.0)
+    assert s_r == 0 and s_p == 0
+    assert b_p == fpl_normalize(b_r), f"len {len(b_p)} vs {len(b_r)}"
+    assert len(b_p) < 0.9 * img.nbytes                                       # the codec was taken (raw tiling would be > 64 MiB)
+    st, data, _ = prod.decode(b_p)
+    assert st == 0 and np.array_equal(data.reshape(img.shape).view(np.uint32), img.view(np.uint32))
