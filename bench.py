@@ -37,20 +37,22 @@ WORKLOADS = {
     # name: (rows, cols, nDepth, dtype code, maxZErr, description)
     "c2": (4096, 4096, 1, 6, 0.01, "4096x4096 float32 1-band encode+decode maxZError=0.01"),
     "c4": (8192, 8192, 3, 1, 0.0, "8192x8192 nDepth=3 uint8 lossless (Huffman path)"),
+    # not a BASELINE config: configs[1]'s raster at maxZError 0 = the lossless float (FPL) codec, for profiling that path
+    "c2l": (4096, 4096, 1, 6, 0.0, "4096x4096 float32 1-band encode+decode maxZError=0 (lossless float codec)"),
     # per-rank strip of the 65536^2 raster; rows can be lowered with --strip-rows for a quick run
     "c5": (8192, 65536, 1, 6, 0.01, "65536x65536 float32 as 256x256 tiles, 8192-row strip (8192 tiles) per GPU, encodeTiles+decodeTiles maxZError=0.01"),
 }
 TILE = 256
 
 
-METRIC = {"c2": "Gpixels/s encode+decode float32 @ maxZError=0.01; achieved HBM GB/s vs peak", "c4": "Gpixels/s encode+decode uint8 nDepth=3 lossless",
+METRIC = {"c2": "Gpixels/s encode+decode float32 @ maxZError=0.01; achieved HBM GB/s vs peak", "c2l": "Gpixels/s encode+decode float32 lossless", "c4": "Gpixels/s encode+decode uint8 nDepth=3 lossless",
           "c5": "Gpixels/s encode+decode float32 @ maxZError=0.01, 256x256 tiles (one blob per tile); achieved HBM GB/s vs peak"}
 
 
 def make_raster(workload, seed):
     from cases import c2_raster, c4_raster
     rows, cols, depth, dt, mz, _ = WORKLOADS[workload]
-    if workload == "c2":
+    if workload in ("c2", "c2l"):
         return c2_raster(rows, cols, seed=seed, phase=0.1 * (seed % 7))
     return c4_raster(rows, cols, seed=seed)
 
@@ -105,7 +107,7 @@ def cpu_reference_run(workload, seconds_budget=20.0, threads=None):
     # bounded sample: a horizontal strip of the workload raster per thread (the library is single-threaded and
     # re-entrant: one independent call per core)
     threads = threads or os.cpu_count() or 1
-    strip_rows = min(rows, 1024 if workload == "c2" else 512)
+    strip_rows = min(rows, 1024 if workload in ("c2", "c2l") else 512)
     if workload == "c5":                               # one 256 x 256 tile per call, as the reference's tile callers do
         from cases import c2_raster
         strip_rows, cols = TILE, TILE

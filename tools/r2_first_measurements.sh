@@ -28,6 +28,7 @@ run_bench c2_dec_closure LERC_B200_DEC=closure -- --steps 20
 run_bench c2_dec_resolve_smem LERC_B200_DEC_RESOLVE=smem -- --steps 20
 run_bench c2_all LERC_B200_ENC=pipe LERC_B200_DEC=closure LERC_B200_DEC_RESOLVE=smem -- --steps 20
 run_bench c5_default -- --workload c5 --strip-rows 4096 --steps 5
+run_bench c2l_lossless_float -- --workload c2l --steps 5
 run_bench c5_enc_pipe LERC_B200_ENC=pipe -- --workload c5 --strip-rows 4096 --steps 5
 for f in "$OUT"/tests_*.log; do echo "== $f"; tail -2 "$f"; done
 python - <<'PY'
