@@ -193,16 +193,14 @@ def ref_lib():
     return LercLib(p) if p else None
 
 
-PRODUCT_WRITES_FPL = True      # float maxZError 0 goes through the lossless float codec like in the reference
-
-
-def oracle_lib(fpl_encoder=None):
-    """fpl_encoder: True = the reference's behaviour (lossless float codec on encode), None = what the product writes today"""
+def oracle_lib(fpl_encoder=True):
+    """fpl_encoder=False: float rasters at maxZError 0 are written without the lossless float codec (raw tiling / one sweep), as a
+    build of the reference without fpl_*.cpp would -- a test switch of the oracle, not used by the suite"""
     p = _first(os.path.join(ROOT, "oracle", "_build", "liblerc_oracle.so"))
     if not p:
         return None
     lib = LercLib(p, prefix="lo_")
-    lib.lib.lo_fpl_encoder(1 if (PRODUCT_WRITES_FPL if fpl_encoder is None else fpl_encoder) else 0)
+    lib.lib.lo_fpl_encoder(1 if fpl_encoder else 0)
     return lib
 
 
