@@ -49,11 +49,15 @@ __global__ void k_try_raise_tiles(const T* __restrict__ data, long long pitch, i
   }
 }
 
-enum { TILEST_OK = 0, TILEST_GENERAL = 1, TILEST_OVERFLOW = 2, TILEST_ALLINT = 3 };   // ALLINT: the only obstacle is that all-integer floats want max(0.5, floor(maxZErr))
+// ALLINT: the only obstacle is that all-integer floats want max(0.5, floor(maxZErr)).  CONST: every pixel holds the same value; the blob is
+// header + empty mask (TILE_CONST_BYTES), written at the start of the image's slot
+// CONST_INT: a constant all-integer float image: its blob is the same for maxZErr and for max(0.5, floor(maxZErr))
+enum { TILEST_OK = 0, TILEST_GENERAL = 1, TILEST_OVERFLOW = 2, TILEST_ALLINT = 3, TILEST_CONST = 4, TILEST_CONST_INT = 5 };
+constexpr int TILE_CONST_BYTES = 90 + 4;
 
 struct TileFinishArgs {
   const TileEncResult* res; const unsigned long long* imgState; const unsigned long long* raise;
-  RaiseArgs ra;
+  RaiseArgs ra; double raiseErr[9];                 // raiseErr[c]: the maxZError candidate c stands for (Lerc2.cpp:1242-1251)
   int nImg, nImgX, imgCols, imgRows, rasterCols, rasterRows, dataStart;
   double maxZErr;
   uint8_t* out; unsigned long long outCap;
@@ -81,9 +85,10 @@ __global__ void k_tiles_finish(TileFinishArgs a) {
   if (zMin == zMax) st = TILEST_GENERAL;                                   // constant image: no stream at all
   uint8_t bIsInt = 0;
   bool allIntMismatch = false;
-  const bool hard = (r.flags & FASTF_NAN) || zMin == zMax;                // obstacles that do not depend on maxZError
+  const bool constImg = minKey == maxKey && !(r.flags & FASTF_NAN);       // one bit pattern everywhere (a mix of +0 and -0 is not)
+  const bool hard = (r.flags & FASTF_NAN) || (zMin == zMax && !constImg);  // obstacles that do not depend on maxZError
   if (isFlt && (st == TILEST_OK || !hard)) {
-    if ((zMin == 0 && __double_as_longlong(zMin) < 0) || (zMax == 0 && __double_as_longlong(zMax) >= 0)) st = TILEST_GENERAL;   // sign of a zero extreme
+    if (!constImg && ((zMin == 0 && __double_as_longlong(zMin) < 0) || (zMax == 0 && __double_as_longlong(zMax) >= 0))) st = TILEST_GENERAL;   // sign of a zero extreme
     bool allInt = !(r.flags & FASTF_NOT_INT);
     const double lim = sizeof(T) == 4 ? 8388608.0 : 9007199254740992.0;
     allInt = allInt && zMin >= -lim && zMin <= lim && zMax >= -lim && zMax <= lim;             // Lerc.cpp:1490-1500
@@ -100,10 +105,23 @@ __global__ void k_tiles_finish(TileFinishArgs a) {
   const unsigned long long total = (unsigned long long)a.dataStart + nData;
   // all-integer floats at a bound that is not max(0.5, floor(.)): the LUT / candidate / size tests above were made with the wrong bound;
   // unless something independent of the bound stands in the way, the image only needs the other bound
-  if (allIntMismatch) st = (!hard && !((zMin == 0 && __double_as_longlong(zMin) < 0) || (zMax == 0 && __double_as_longlong(zMax) >= 0))) ? TILEST_ALLINT : TILEST_GENERAL;
+  if (allIntMismatch) st = (!hard && (constImg || !((zMin == 0 && __double_as_longlong(zMin) < 0) || (zMax == 0 && __double_as_longlong(zMax) >= 0)))) ? TILEST_ALLINT : TILEST_GENERAL;
   if ((r.flags & FASTF_OVERFLOW) || start + total > a.outCap) st = TILEST_OVERFLOW;
+  // constant image (Lerc2.cpp:255-258): no ranges, no stream.  maxZError in the header: what TryRaiseMaxZError finds for the one
+  // value there is (row 0 speaks for the whole image), unless the all-integer rule already fixed it
+  double hdrMaxZErr = a.maxZErr;
+  bool writeConst = false;
+  if (constImg && st != TILEST_OVERFLOW) {
+    if (isFlt && bIsInt) { const double f = floor(a.maxZErr); hdrMaxZErr = f > 0.5 ? f : 0.5; }          // Lerc.cpp:1490-1502
+    if (isFlt && !bIsInt)
+      for (int c = 0; c < a.ra.n; c++) {
+        const double m = __longlong_as_double((long long)a.raise[(size_t)img * 9 + c]);
+        if (!(__ddiv_rn(m, a.ra.fac[c]) > __dmul_rn(a.maxZErr, 0.5))) { hdrMaxZErr = a.raiseErr[c]; break; }
+      }
+    st = (isFlt && bIsInt) ? TILEST_CONST_INT : TILEST_CONST; writeConst = true;
+  }
   a.status[img] = st;
-  if (st != TILEST_OK) return;
+  if (st != TILEST_OK && !writeConst) return;
 
   // ---- header (Lerc2.cpp:710-760, version 6), mask byte count 0, ranges, "not one sweep"; checksum over [14, total)
   uint8_t b[128];
@@ -112,17 +130,24 @@ __global__ void k_tiles_finish(TileFinishArgs a) {
   auto put64 = [&](int at, double d) { const unsigned long long v = (unsigned long long)__double_as_longlong(d); for (int i = 0; i < 8; i++) b[at + i] = (uint8_t)(v >> (8 * i)); };
   b[0] = 'L'; b[1] = 'e'; b[2] = 'r'; b[3] = 'c'; b[4] = '2'; b[5] = ' ';
   put32(6, 6u); put32(14, (uint32_t)rows); put32(18, (uint32_t)cols); put32(22, 1u); put32(26, (uint32_t)nPix); put32(30, 8u);
-  put32(34, (uint32_t)total); put32(38, (uint32_t)PixelTraits<T>::code); put32(42, 0u);
+  put32(34, writeConst ? (uint32_t)TILE_CONST_BYTES : (uint32_t)total); put32(38, (uint32_t)PixelTraits<T>::code); put32(42, 0u);
   b[46] = 0; b[47] = bIsInt;
-  put64(50, a.maxZErr); put64(58, zMin); put64(66, zMax);                  // noDataVal, noDataValOrig stay 0
+  put64(50, hdrMaxZErr); put64(58, zMin); put64(66, zMax);                  // noDataVal, noDataValOrig stay 0
   int p = 90 + 4;
+  uint8_t* dst = a.out + start;
+  if (writeConst) {
+    unsigned long long A0 = 0, D0 = 0;
+    fletcherHostPartial(b + 14, 0, (long long)p - 14, A0, D0);
+    put32(10, fletcherFinish(A0, D0, (long long)p - 14));
+    for (int i = 0; i < p; i++) dst[i] = b[i];
+    return;
+  }
   { uint8_t tmp[8]; memcpy(tmp, &lo, sizeof(T)); for (int i = 0; i < (int)sizeof(T); i++) b[p + i] = tmp[i]; p += (int)sizeof(T);
     memcpy(tmp, &hi, sizeof(T)); for (int i = 0; i < (int)sizeof(T); i++) b[p + i] = tmp[i]; p += (int)sizeof(T); }
   b[p++] = 0;
   unsigned long long A = r.fletA, D = r.fletD % 65535ull;
   fletcherHostPartial(b + 14, 0, (long long)p - 14, A, D);
   put32(10, fletcherFinish(A, D, (long long)total - 14));
-  uint8_t* dst = a.out + start;
   for (int i = 0; i < p; i++) dst[i] = b[i];
 }
 
@@ -185,10 +210,11 @@ ErrCode encodeTilesFast(Context* ctx, const TilesGeom& g, const void* dData, dou
   uint32_t* dStatus = (uint32_t*)(dState + offStatus);
 
   RaiseArgs ra; ra.n = 0;
+  double raiseErr[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   if (isFlt) {
     static const double kErr[9] = {1, 0.5, 0.1, 0.05, 0.01, 0.005, 0.001, 0.0005, 0.0001};
     static const double kFac[9] = {1, 2, 10, 20, 100, 200, 1000, 2000, 10000};
-    for (int i = 0; i < 9; i++) if (kErr[i] / 2 > maxZErr) { ra.fac[ra.n] = kFac[i]; ra.n++; }
+    for (int i = 0; i < 9; i++) if (kErr[i] / 2 > maxZErr) { ra.fac[ra.n] = kFac[i]; raiseErr[ra.n] = kErr[i] / 2; ra.n++; }
     if (ra.n > 0) {
       ctx->forkSide();
       LERC_LAUNCH(ctx, k_try_raise_tiles<T>, (unsigned)((nImg + 7) / 8), 256, 0, (const T*)dData, (long long)g.nCols, (int)nImg, g.nImgX, g.tileCols, g.tileRows, g.nCols, ra, dRaise);
@@ -236,6 +262,7 @@ ErrCode encodeTilesFast(Context* ctx, const TilesGeom& g, const void* dData, dou
   ctx->joinSide();
   TileFinishArgs ta;
   ta.res = dRes; ta.imgState = dImgState; ta.raise = dRaise; ta.ra = ra;
+  for (int i = 0; i < 9; i++) ta.raiseErr[i] = raiseErr[i];
   ta.nImg = (int)nImg; ta.nImgX = g.nImgX; ta.imgCols = g.tileCols; ta.imgRows = g.tileRows; ta.rasterCols = g.nCols; ta.rasterRows = g.nRows;
   ta.dataStart = dataStart; ta.maxZErr = maxZErr; ta.out = dOut; ta.outCap = outCap; ta.status = dStatus;
   LERC_LAUNCH(ctx, k_tiles_finish<T>, (unsigned)((nImg + 127) / 128), 128, 0, ta);
@@ -263,13 +290,13 @@ ErrCode encodeTilesT(Context* ctx, const TilesGeom& g, const void* dData, double
       // Tiles the first pass had to hand to the general encoder for another reason (constant, NaN, ...) stay handed over; the second
       // pass is only possible when the first one produced no blob worth keeping.
       long long nAllInt = 0, nKeep = 0;
-      for (long long i = 0; i < nImg; i++) { nAllInt += status[(size_t)i] == TILEST_ALLINT; nKeep += status[(size_t)i] == TILEST_OK || status[(size_t)i] == TILEST_OVERFLOW; }
+      for (long long i = 0; i < nImg; i++) { nAllInt += status[(size_t)i] == TILEST_ALLINT; nKeep += status[(size_t)i] == TILEST_OK || status[(size_t)i] == TILEST_OVERFLOW || status[(size_t)i] == TILEST_CONST; }
       if (nAllInt > 0 && nKeep == 0) {
         const std::vector<uint32_t> first = status;
         e = encodeTilesFast<T>(ctx, g, dData, std::max(0.5, std::floor(maxZErr)), dOut, outCap, status, end);
         if (e != Ok) return e;
         for (long long i = 0; i < nImg; i++)
-          if (first[(size_t)i] != TILEST_ALLINT && status[(size_t)i] != TILEST_OVERFLOW) status[(size_t)i] = TILEST_GENERAL;
+          if (first[(size_t)i] != TILEST_ALLINT && first[(size_t)i] != TILEST_CONST_INT && status[(size_t)i] != TILEST_OVERFLOW) status[(size_t)i] = TILEST_GENERAL;
       }
     }
     bool allOk = true, overflow = false;
@@ -297,7 +324,15 @@ ErrCode encodeTilesT(Context* ctx, const TilesGeom& g, const void* dData, double
   hOffsets[0] = 0;
   long long i = 0;
   while (i < nImg) {
-    if (fast && status[(size_t)i] == TILEST_OK) {
+    if (fast && (status[(size_t)i] == TILEST_CONST || status[(size_t)i] == TILEST_CONST_INT)) {                       // constant image: its short blob sits at the start of its slot
+      const unsigned long long from = i == 0 ? 0 : end[(size_t)i - 1];
+      if (cursor + TILE_CONST_BYTES > outCap) return BufferTooSmall;
+      if (!cudaOk(cudaMemcpyAsync(dOut + cursor, dKeep + from, TILE_CONST_BYTES, cudaMemcpyDeviceToDevice, ctx->stream), "blob move")) return Failed;
+      cursor += TILE_CONST_BYTES;
+      hOffsets[i + 1] = cursor;
+      globalStats().fastPathEncodes += 1;
+      i++;
+    } else if (fast && status[(size_t)i] == TILEST_OK) {
       long long j = i;                                                    // run of good images: one copy
       while (j + 1 < nImg && status[(size_t)j + 1] == TILEST_OK) j++;
       const unsigned long long from = i == 0 ? 0 : end[(size_t)i - 1], to = end[(size_t)j];

@@ -129,6 +129,25 @@ def tile_cases(seed=5):
     whole0[0:64, 0:64] = 7.0                                   # ... but one of them constant
     cases.append(("f32_all_integer_one_const", whole0, 64, 64, 0.01))
     cases.append(("f64_all_integer_0.3", np.round(f.astype(np.float64) * 3), 48, 48, 0.3))
+    # constant tiles (header-only blobs, decided on the device): values on and off the decimal grids maxZError may be raised to,
+    # integers, zeros of both signs, a tile mixing +0 and -0, constant tiles at the ragged edge
+    cst = c2_raster(192, 330)
+    for k, v in enumerate([3.25, 0.1, 7.0, 0.0, -0.0, 1e-3, 123.456, -2.5]):
+        y, x = divmod(k, 4)
+        cst[y * 64:(y + 1) * 64, x * 64:(x + 1) * 64] = v
+    cst[128:192, 0:64] = 0.0
+    cst[128:192:2, 0:64] = -0.0
+    cst[128:192, 320:330] = 42.5
+    for mz in (0.01, 0.3, 0.0004):
+        cases.append((f"f32_const_tiles_{mz}", cst, 64, 64, mz))
+    cases.append(("f64_const_tiles_0.01", cst.astype(np.float64), 64, 64, 0.01))
+    ci = np.clip(smooth_field(128, 200) / 8 + rng.normal(0, 2, (128, 200)), -3e4, 3e4).astype(np.int16)
+    ci[0:64, 0:64] = -17
+    ci[64:128, 128:192] = 0
+    ci[64:128, 192:200] = 5
+    cases.append(("i16_const_tiles_lossless", ci, 64, 64, 0))
+    cases.append(("i32_const_tiles_lossy3", ci.astype(np.int32) * 5, 64, 64, 3))
+    cases.append(("f32_every_tile_const", np.repeat(np.repeat(rng.integers(0, 4, (3, 5)).astype(np.float32) * np.float32(1.5), 32, 0), 32, 1), 32, 32, 0.01))
     return cases
 
 
