@@ -16,7 +16,7 @@
 
 namespace lerc {
 
-enum { TILED_DONE = 0, TILED_FAST = 1, TILED_GENERAL = 2 };
+enum { TILED_DONE = 0, TILED_FAST = 1, TILED_GENERAL = 2, TILED_CONST = 3 };   // CONST: header-only blob of a constant image, value in rec.zMax
 
 struct TileDecRec { uint32_t status, streamOff, streamLen, version, checksum, blobSize; double invScale, zMax; };
 
@@ -58,7 +58,11 @@ __global__ void k_tiles_parse(TilesDecArgs a) {
     const double maxZErr = tdRdF64(p + q), zMin = tdRdF64(p + q + 8), zMax = tdRdF64(p + q + 16);
     if (nRows != rows || nCols != cols || nDepth != 1 || numValid != rows * cols || mb != 8 || dt != DT || passNoData) break;
     if (blobSize < hb + 4 || (unsigned long long)blobSize > avail) break;
-    if (!(maxZErr >= 0) || zMin == zMax) break;
+    if (zMin == zMax) {                                                                  // constant image: header + empty mask, nothing else (Lerc2.cpp:410-413)
+      if (blobSize == hb + 4 && tdRd32(p + hb) == 0) { rec.status = TILED_CONST; rec.blobSize = (uint32_t)blobSize; rec.zMax = zMin; }
+      break;
+    }
+    if (!(maxZErr >= 0)) break;
     if ((dt == DT_Byte || dt == DT_Char) && maxZErr == 0.5) break;                       // an image-mode byte follows (Huffman)
     if (version >= 6 && dt >= DT_Float && maxZErr == 0) break;                           // likewise (lossless float)
     int pos = hb;
@@ -105,9 +109,30 @@ __global__ void __launch_bounds__(NT) k_tiles_blocks(TilesDecArgs a) {
 
   for (int img = blockIdx.x; img < a.nImg; img += gridDim.x) {
     const TileDecRec rec = a.recs[img];
-    if (rec.status != TILED_FAST) continue;                                   // uniform for the CTA
+    if (rec.status != TILED_FAST && rec.status != TILED_CONST) continue;      // uniform for the CTA
     const int iy = img / a.nImgX, ix = img - iy * a.nImgX;
     const int rows = min(a.imgRows, a.rasterRows - iy * a.imgRows), cols = min(a.imgCols, a.rasterCols - ix * a.imgCols);
+    if (rec.status == TILED_CONST) {                                          // Lerc2::FillConstImage (Lerc2.cpp:2681-2721): every pixel = (T)zMin
+      if (tid == 0) {
+        const uint8_t* cb = a.blobs + a.offsets[img] + 14;
+        const int len = (int)rec.blobSize - 14;                               // <= 80 header bytes behind the checksum field
+        unsigned long long A = 0, D = 0;
+        fletcherHostPartial(cb, 0, len, A, D);
+        sBad = fletcherFinish(A, D, len) == rec.checksum ? 0 : 1;
+      }
+      __syncthreads();
+      const bool ok = sBad == 0;
+      if (ok) {
+        const T v = (T)rec.zMax;
+        for (int k = tid; k < rows * cols; k += NT) {
+          const int rr = k / cols, cc = k - rr * cols;
+          data[((long long)iy * a.imgRows + rr) * (long long)a.rasterCols + (long long)ix * a.imgCols + cc] = v;
+        }
+      }
+      __syncthreads();                                                        // sBad is reused by the next blob
+      if (tid == 0) a.recs[img].status = ok ? TILED_DONE : TILED_GENERAL;
+      continue;
+    }
     const int nTx = (cols + 7) / 8, nTy = (rows + 7) / 8, nBlocks = nTx * nTy;
     const uint8_t* blob = a.blobs + a.offsets[img];
     const int version = (int)rec.version;
