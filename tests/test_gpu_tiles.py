@@ -88,6 +88,26 @@ def test_corrupted_tile_fails_like_lerc_decode(libs):
     assert st == st_o
 
 
+def test_corrupted_constant_tile_fails_like_lerc_decode(libs):
+    """a header-only blob (constant tile) with one byte changed: the batch decoder and the oracle agree on the verdict for every byte
+    position tried, and on the pixels where the change is harmless"""
+    prod, orc = libs
+    img = c2_raster(128, 192)
+    img[0:64, 64:128] = 3.25
+    blobs = _oracle_blobs(orc, img, 64, 64, 0.01)
+    assert len(blobs[1]) == 94
+    rng = np.random.default_rng(3)
+    for _ in range(24):
+        bad = bytearray(blobs[1])
+        k = int(rng.integers(0, 94))
+        bad[k] ^= int(rng.integers(1, 256))
+        st_o, d_o, _ = orc.decode(bytes(bad))
+        st, dec = decode_tiles(prod, [blobs[0], bytes(bad)] + blobs[2:], np.float32, 128, 192, 64, 64)
+        assert (st == 0) == (st_o == 0), f"byte {k}: status {st} vs oracle {st_o}"
+        if st == 0:
+            assert np.array_equal(dec[0:64, 64:128].view(np.uint8), d_o[0, :, :, 0].view(np.uint8))
+
+
 def test_device_pointers_config5_shape(libs):
     """BASELINE config 5's tile shape on device-resident buffers: 2048 x 4096 float32 as 128 tiles of 256 x 256."""
     import torch
