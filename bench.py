@@ -453,6 +453,7 @@ def main():
     per_launch_ms = top_ms / top_cnt
     # algorithmic bytes of one launch of the dominant kernel: what the kernel must move once
     algo_table = {
+        "k_encode_tile": (raw_bytes + blob_bytes, "raster read once + block stream written once"),
         "k_encode_fused": (raw_bytes + blob_bytes, "raster read once + block stream written once"),
         "k_dec_blocks": (raw_bytes + blob_bytes, "block stream read once + raster written once"),
         "k_dec_walk": (blob_bytes, "block stream headers (bounded by the stream size)"),

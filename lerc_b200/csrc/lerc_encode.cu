@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <cstring>
 #include <cstdio>
+#include <atomic>
 
 namespace lerc {
 
@@ -695,7 +696,7 @@ __global__ void k_one_sweep_gather(const T* __restrict__ data, const uint8_t* __
 
 }  // namespace lerc
 #include "lerc_encode_fast.cuh"
-#include "lerc_encode_pipe.cuh"
+#include "lerc_encode_tile.cuh"
 namespace lerc {
 
 // =================================================================================================
@@ -763,11 +764,8 @@ bool encodeBandFast(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
   cudaStream_t st = ctx->stream;
   const int nTx = (a.nCols + 7) / 8, nTy = (a.nRows + 7) / 8;
   const long long nBlocks = (long long)nTx * nTy;
-  // two tile shapes: one CTA per 32 blocks (default) or one warp per 4 blocks (LERC_B200_ENC=warp; no CTA barriers, but 8x
-  // the look-back traffic: measured 206 us vs 108 us on the 4096^2 float workload, kept for comparison)
-  static const bool ctaTiles = [] { const char* e = std::getenv("LERC_B200_ENC"); return !(e && std::strcmp(e, "warp") == 0); }();
-  const int TB = ctaTiles ? FAST_TB : 4;
-  const long long nTiles = (long long)((nTx + TB - 1) / TB) * nTy;      // tiles never wrap a block row
+  constexpr int TW = EncTile<T>::TW;
+  const long long nTiles = (long long)((nTx + TW - 1) / TW) * nTy;      // tiles never wrap a block row
   if (nTiles > 0x7fffffffLL) return false;
   (void)nBlocks;
   const size_t dataStart = (size_t)headerBytes(6) + 4 + 2 * sizeof(T) + 1;
@@ -805,46 +803,18 @@ bool encodeBandFast(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
   uint8_t* blob = a.dOut + a.outOffset;
   fa.stream = blob + dataStart; fa.streamCap = a.outCapacity - dataStart; fa.regionOff = (long long)dataStart - 14;
   fa.tileState = (unsigned long long*)(dState + sizeof(FastEncResult) + 9 * 8); fa.res = dRes;
-  // look-back: aggregates per group of 32 tiles (two dependent rounds per tile) unless LERC_B200_ENC_LB=chain (plain chain, ~grid / 32 rounds)
-  static const bool groupLb = [] { const char* e = std::getenv("LERC_B200_ENC_LB"); return !(e && std::strcmp(e, "chain") == 0); }();
-  fa.groupState = (groupLb && ctaTiles) ? fa.tileState + nTiles : nullptr;
-  constexpr int MAXB = 1 + 64 * (int)sizeof(T);
-  int dev = 0, sms = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  static const bool pipeEnc = [] { const char* e = std::getenv("LERC_B200_ENC"); return e && std::strcmp(e, "pipe") == 0; }();
-  if (pipeEnc) {
-    // experimental: look-back deferred by one tile and done by every warp, one barrier per tile (lerc_encode_pipe.cuh)
-    const size_t smem = (size_t)((FAST_TB * MAXB + 15) / 16 + 3) * 16 * 3 + 256 * 8 * sizeof(T);       // three staging images + the general path's pixel rows
-    fa.groupState = fa.tileState + nTiles;
-    static int ctasPerSm = 0;
-    if (!ctasPerSm) {
-      cudaFuncSetAttribute(k_encode_pipe<T, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSm, k_encode_pipe<T, 4>, 256, smem) != cudaSuccess || ctasPerSm < 1) ctasPerSm = 1;
+  fa.groupState = fa.tileState + nTiles;                               // look-back level 2: aggregates per group of 32 tiles
+  {
+    // one CTA per tile, tiles taken by ticket (no co-residency assumption); dynamic shared memory opt-in once per device
+    constexpr size_t smem = (size_t)EncTile<T>::SMEM;
+    static std::atomic<unsigned long long> attrDone{0};
+    const unsigned long long devBit = 1ull << (ctx->device & 63);
+    if (!(attrDone.load(std::memory_order_relaxed) & devBit)) {
+      if (!cudaOk(cudaFuncSetAttribute(k_encode_tile<T, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "encode tile smem")) return false;
+      attrDone.fetch_or(devBit, std::memory_order_relaxed);
     }
-    const long long grid = std::min<long long>(nTiles, (long long)ctasPerSm * std::max(sms, 1));     // all CTAs co-resident (look-back)
-    LERC_LAUNCH(ctx, (k_encode_pipe<T, 4>), (unsigned)grid, 256, smem, fa, FastNoBatch());
-  } else if (ctaTiles) {
-    const size_t smem = (size_t)((FAST_TB * MAXB + 15) / 16 + 3) * 16 * 2 + 256 * 8 * sizeof(T);       // two staging images + the general path's pixel rows
-    static const int occ = [] { const char* e = std::getenv("LERC_B200_ENC_OCC"); const int v = e ? std::atoi(e) : 4; return (v == 5 || v == 6) ? v : 4; }();
-    auto launch = [&](auto kernel) {
-      static int ctasPerSm = 0;
-      if (!ctasPerSm) {
-        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSm, kernel, 256, smem) != cudaSuccess || ctasPerSm < 1) ctasPerSm = 1;
-      }
-      const long long grid = std::min<long long>(nTiles, (long long)ctasPerSm * std::max(sms, 1));   // all CTAs co-resident (look-back)
-      LaunchScope scope_(ctx, "k_encode_fused<T>");
-      kernel<<<(unsigned)grid, 256, smem, ctx->stream>>>(fa, FastNoBatch()); ctx->kernelLaunches++;
-    };
-    if (occ == 6) launch(k_encode_fused<T, 6>); else if (occ == 5) launch(k_encode_fused<T, 5>); else launch(k_encode_fused<T, 4>);
-  } else {
-    const size_t smem = (size_t)((4 * MAXB + 15) / 16 + 3) * 16 * 8 + 256 * 8 * sizeof(T);               // one staging image per warp + the general path's pixel rows
-    static int ctasPerSm = 0;
-    if (!ctasPerSm) {
-      cudaFuncSetAttribute(k_encode_warp<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSm, k_encode_warp<T>, 256, smem) != cudaSuccess || ctasPerSm < 1) ctasPerSm = 1;
-    }
-    const long long grid = std::min<long long>((nTiles + 7) / 8, (long long)ctasPerSm * std::max(sms, 1));   // all warps co-resident (look-back)
-    LERC_LAUNCH(ctx, k_encode_warp<T>, (unsigned)grid, 256, smem, fa);
+    LaunchScope scope_(ctx, "k_encode_tile<T>");
+    k_encode_tile<T, 4><<<(unsigned)nTiles, 256, smem, ctx->stream>>>(fa); ctx->kernelLaunches++;
   }
   ctx->joinSide();
   if (!cudaOk(cudaMemcpyAsync(hRes, dState, sizeof(HostRes), cudaMemcpyDeviceToHost, st), "D2H fast result")) { err = Failed; return true; }

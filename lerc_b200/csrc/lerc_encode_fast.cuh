@@ -688,272 +688,6 @@ __global__ void __launch_bounds__(256, MINB) k_encode_fused(FastEncArgs a, typen
   }
 }
 
-template <class T>
-__global__ void __launch_bounds__(256, 4) k_encode_warp(FastEncArgs a) {
-  using K = typename PixelTraits<T>::Key;
-  constexpr bool isFlt = PixelTraits<T>::isFloat;
-  constexpr int DT = PixelTraits<T>::code;
-  constexpr int TB = 4;                                         // blocks per tile: one warp, no CTA-wide barrier anywhere
-  constexpr int MAXB = 1 + 64 * (int)sizeof(T);                 // longest block: raw (Lerc2.h:427)
-  constexpr int NQ = (TB * MAXB + 15) / 16 + 3;                 // staging uint4s per warp: 16 zero bytes | tile output | zero tail
-  extern __shared__ __align__(16) uint32_t stageRaw[];          // [8 warps] staging images | T sRow[256][8] (general path)
-  T* sRow = (T*)(stageRaw + 8 * NQ * 4);
-  __shared__ unsigned long long sKMin[8], sKMax[8], sFA[8], sFD[8];
-  __shared__ unsigned int sFlg[8];
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, sb = lane >> 3, r = lane & 7;
-  const unsigned int flagsSeen = *(volatile unsigned int*)&a.res->flags;
-  const unsigned long long negMinSeen = *(volatile unsigned long long*)&a.res->negMinKey, maxSeen = *(volatile unsigned long long*)&a.res->maxKey;
-  for (int i = tid; i < 8 * NQ; i += 256) ((uint4*)stageRaw)[i] = make_uint4(0, 0, 0, 0);
-
-  const T* data = (const T*)a.data;
-  const bool vecOk = ((a.nCols * (int)sizeof(T)) % 16 == 0) && (((uintptr_t)data & 15) == 0);
-  const int tpr = (a.nTx + TB - 1) / TB;                         // tiles per block row
-  const int nTiles = tpr * a.nTy;
-  const int b = sb;
-  const int nWarps = (int)gridDim.x * 8, gw = (int)blockIdx.x * 8 + warp;   // persistent warps: warp gw codes tiles gw, gw + nWarps, ...
-  constexpr unsigned long long ST_A = 1ull << 62, ST_P = 2ull << 62, VAL = (1ull << 62) - 1;
-  volatile unsigned long long* st = a.tileState;
-
-  // running image-global facts and checksum partials of this thread
-  K gMin = keyMaxValue<K>(), gMax = 0;
-  unsigned int myFlags = 0;
-  unsigned long long fa = 0, fd = 0;
-  bool overflow = false;
-
-  // geometry + pixel row of a tile for this lane
-  auto tileGeom = [&](int tile, int tyT, int segT, int& ty, int& tx, int& h, int& w, bool& act) {
-    ty = tyT; tx = segT * TB + b;
-    act = tile < nTiles && tx < a.nTx;
-    h = act ? min(8, a.nRows - ty * 8) : 0; w = act ? min(8, a.nCols - tx * 8) : 0;
-  };
-  const int stepTy = nWarps / tpr, stepSeg = nWarps - stepTy * tpr;   // tile += nWarps in (block row, segment) form
-  FastRow<T> cur, nxt;
-  int ty, tx, h, w; bool act;
-  int tile = gw;
-  int tyT = tile / tpr, segT = tile - tyT * tpr;
-  tileGeom(tile, tyT, segT, ty, tx, h, w, act);
-#pragma unroll
-  for (int k = 0; k < 8; k++) cur.v[k] = (T)0;
-  if (act && r < h) loadRow8<T>(data + (size_t)(ty * 8 + r) * a.nCols + tx * 8, w, vecOk && w == 8, cur.v);
-  __syncthreads();                                               // staging zeroed (the only CTA-wide barrier before the final reduction)
-
-  uint32_t* stage = stageRaw + (size_t)warp * NQ * 4 + 4;          // tile-local byte 0 of this warp's output image
-  for (; tile < nTiles; tile += nWarps) {
-    // ---- prefetch the next tile's pixels
-    int nty, ntx, nh, nw; bool nact;
-    tyT += stepTy; segT += stepSeg; if (segT >= tpr) { segT -= tpr; tyT++; }
-    tileGeom(tile + nWarps, tyT, segT, nty, ntx, nh, nw, nact);
-#pragma unroll
-    for (int k = 0; k < 8; k++) nxt.v[k] = (T)0;
-    if (nact && r < nh) loadRow8<T>(data + (size_t)(nty * 8 + r) * a.nCols + ntx * 8, nw, vecOk && nw == 8, nxt.v);
-
-    // ---- block statistics and coding choice
-    const int j0 = tx * 8, n = h * w;
-    int mode = BEM_SIMPLE, nb = 0, tc = 0, dtUsed = DT, nBytes = 0; uint32_t maxElem = 0; double zMin = 0; T lo = (T)0;
-    bool hot = false;
-    if (isFlt && sizeof(T) == 4) {
-      // hot path test for full 8x8 float blocks coded "bit-stuffed, offset as float/short/byte"
-      float fv[8];
-#pragma unroll
-      for (int k = 0; k < 8; k++) memcpy(&fv[k], &cur.v[k], 4);
-      float mn = fminf(fminf(fminf(fv[0], fv[1]), fminf(fv[2], fv[3])), fminf(fminf(fv[4], fv[5]), fminf(fv[6], fv[7])));
-      float mx = fmaxf(fmaxf(fmaxf(fv[0], fv[1]), fmaxf(fv[2], fv[3])), fmaxf(fmaxf(fv[4], fv[5]), fmaxf(fv[6], fv[7])));
-      float t0 = 0.f;                                              // NaN iff some value is NaN or +-Inf
-#pragma unroll
-      for (int k = 0; k < 8; k++) t0 = __fmaf_rn(fv[k], 0.f, t0);
-      int same = 0;
-#pragma unroll
-      for (int k = 1; k < 8; k++) same += (fv[k] == fv[k - 1]) ? 1 : 0;
-      const float up = __shfl_up_sync(FULL, fv[7], 1, 8);
-      same += (fv[0] == (r == 0 ? 0.f : up)) ? 1 : 0;
-      const bool full = act && h == 8 && w == 8;
-      uint32_t kmn = toKey(mn), kmx = toKey(mx);
-      int nonFinite = (t0 != t0) ? 1 : 0;
-#pragma unroll
-      for (int m = 1; m < 8; m <<= 1) {                              // 8-lane groups: xor shuffles stay inside the group
-        const uint32_t omn = __shfl_xor_sync(FULL, kmn, m), omx = __shfl_xor_sync(FULL, kmx, m);
-        kmn = omn < kmn ? omn : kmn; kmx = omx > kmx ? omx : kmx;
-        const int pk = __shfl_xor_sync(FULL, same | (nonFinite << 16), m);
-        same += pk & 0xffff; nonFinite |= pk >> 16;
-      }
-      const bool finite = nonFinite == 0;
-      const float lof = fromKey<float>(kmn), hif = fromKey<float>(kmx);
-      const double zMn = (double)lof, zMx = (double)hif;
-      const double mv = __dmul_rn(__dsub_rn(zMx, zMn), a.scale);
-      const uint32_t me = roundToUInt(mv);
-      const int nbh = bitLength(me);
-      const bool lutCand = (zMx > __dadd_rn(zMn, a.maxZErr3)) && (2 * same > 64);
-      hot = full && finite && !(mv > (double)a.maxQ) && me > 0 && nbh <= 16 && !lutCand && !(lof == 0.f && hif == 0.f);
-      hot = __all_sync(FULL, hot || !act) && __any_sync(FULL, act);
-      if (hot && act) {
-        memcpy(&lo, &lof, 4); zMin = zMn; maxElem = me; nb = nbh;
-        // offset in the smallest type that holds it (Lerc2.h:457-542, float row)
-        const bool isInt = lof == truncf(lof);
-        tc = (isInt && lof >= 0.f && lof <= 255.f) ? 2 : ((isInt && lof >= -32768.f && lof <= 32767.f) ? 1 : 0);
-        dtUsed = tc == 0 ? DT_Float : (tc == 1 ? DT_Short : DT_Byte);
-        nBytes = 1 + (4 >> tc) + 2 + 8 * nb;
-        gMin = kmn < gMin ? (K)kmn : gMin; gMax = kmx > gMax ? (K)kmx : gMax;
-        if (!(flagsSeen & FASTF_NOT_INT) && !(myFlags & FASTF_NOT_INT)) {          // all-integer test (Lerc.h:248)
-          bool ni = false;
-#pragma unroll
-          for (int k = 0; k < 8; k++) ni |= fv[k] != truncf(fv[k]);
-          if (ni) myFlags |= FASTF_NOT_INT;
-        }
-      }
-    }
-    if (!hot) {
-      unsigned int fl = 0; K kmin, kmax;
-#pragma unroll
-      for (int k = 0; k < 8; k++) sRow[tid * 8 + k] = cur.v[k];
-      fastGenericChoice<T>(a, sRow + tid * 8, h, w, r, act, nBytes, mode, nb, tc, dtUsed, maxElem, zMin, lo, fl, kmin, kmax);
-      myFlags |= fl;
-      if (act) { gMin = kmin < gMin ? kmin : gMin; gMax = kmax > gMax ? kmax : gMax; }
-      if (isFlt && act && r < h && !(flagsSeen & FASTF_NOT_INT) && !(myFlags & FASTF_NOT_INT)) {
-        bool ni = false;
-#pragma unroll
-        for (int k = 0; k < 8; k++) ni |= k < w && (sizeof(T) == 4 ? ((float)cur.v[k] != truncf((float)cur.v[k])) : ((double)cur.v[k] != trunc((double)cur.v[k])));
-        if (ni) myFlags |= FASTF_NOT_INT;
-      }
-    }
-    // ---- tile-local byte offsets of the 4 blocks
-    const uint32_t l0 = __shfl_sync(FULL, (uint32_t)nBytes, 0), l1 = __shfl_sync(FULL, (uint32_t)nBytes, 8), l2 = __shfl_sync(FULL, (uint32_t)nBytes, 16), l3 = __shfl_sync(FULL, (uint32_t)nBytes, 24);
-    const uint32_t tileBytes = l0 + l1 + l2 + l3;
-    const uint32_t byte0 = (sb > 0 ? l0 : 0u) + (sb > 1 ? l1 : 0u) + (sb > 2 ? l2 : 0u);
-    if (lane == 0) st[tile] = (tile == 0 ? ST_P : ST_A) | (unsigned long long)tileBytes;   // publish before packing
-
-    // ---- quantise (Lerc2.h:357-376), pack, OR into the staging image (WriteTile, Lerc2.cpp:1949-2021)
-    if (hot) {
-      if (act) {
-        const int osz = 4 >> tc;
-        if (r == 0) {                                              // flag | offset | numBits byte | count
-          const uint32_t flag = (uint32_t)((((j0 >> 3) & 15) << 2) & 0x38);
-          const unsigned long long ob = offsetBits(zMin, dtUsed);
-          unsigned long long hd = (unsigned long long)(flag | 1 | (tc << 6)) | (ob << 8);
-          hd |= ((unsigned long long)(nb | (2 << 6)) | (64ull << 8)) << (8 * (1 + osz));
-          const uint32_t H[2] = {(uint32_t)hd, (uint32_t)(hd >> 32)};
-          orBits<2>(stage, byte0 * 8, H, (3 + osz) * 8);
-        }
-        float fv[8];
-#pragma unroll
-        for (int k = 0; k < 8; k++) memcpy(&fv[k], &cur.v[k], 4);
-        uint32_t q[8];
-#pragma unroll
-        for (int k = 0; k < 8; k++) q[k] = quantizeOne((double)fv[k], zMin, a.scale);
-        // 8 values of nb <= 16 bits -> 128 bits
-        const unsigned long long p0 = q[0] | ((unsigned long long)q[1] << nb), p1 = q[2] | ((unsigned long long)q[3] << nb);
-        const unsigned long long p2 = q[4] | ((unsigned long long)q[5] << nb), p3 = q[6] | ((unsigned long long)q[7] << nb);
-        const int s2 = 2 * nb, s4 = 4 * nb;
-        const unsigned long long h0 = p0 | (p1 << s2), h1 = p2 | (p3 << s2);      // 4 nb <= 64 bits each
-        const unsigned long long r0 = s4 == 64 ? h0 : (h0 | (h1 << s4)), r1 = s4 == 64 ? h1 : (h1 >> (64 - s4));
-        const uint32_t R[4] = {(uint32_t)r0, (uint32_t)(r0 >> 32), (uint32_t)r1, (uint32_t)(r1 >> 32)};
-        orBits<4>(stage, (byte0 + (uint32_t)(osz + 3) + (uint32_t)(r * nb)) * 8, R, 8 * nb);
-      }
-    } else if (act) {
-      fastGenericEmit<T>(a, stage, sRow + tid * 8, h, w, r, j0, byte0, mode, nb, tc, dtUsed, maxElem, zMin, lo);
-    }
-
-    __syncwarp();                                                // staging image complete
-    // ---- decoupled look-back for the tile's global byte offset
-    unsigned long long tileOff = 0;
-    if (tile > 0) {
-      long long base = (long long)tile - 1;
-      for (;;) {
-        const long long idx = base - lane;
-        unsigned long long s = ST_P;                                  // virtual tiles before 0: prefix 0
-        if (idx >= 0) { do { s = st[idx]; } while ((s >> 62) == 0); }
-        const unsigned isP = __ballot_sync(FULL, (s >> 62) == 2);
-        const int firstP = isP ? __ffs(isP) - 1 : 32;
-        unsigned long long contrib = (lane <= firstP && idx >= 0) ? (s & VAL) : 0;
-#pragma unroll
-        for (int m = 16; m; m >>= 1) contrib += __shfl_xor_sync(FULL, contrib, m);
-        tileOff += contrib;
-        if (isP) break;
-        base -= 32;
-      }
-      if (lane == 0) st[tile] = ST_P | (tileOff + tileBytes);
-    }
-    if (lane == 0 && tile == nTiles - 1) a.res->totalBytes = tileOff + tileBytes;
-
-    // ---- staging -> HBM in 16-byte chunks aligned to the GLOBAL address (the staging image is re-aligned with
-    // funnel shifts), Fletcher-32 partial sums of the same words (bytes outside the tile are zero in the image);
-    // every chunk read is zeroed again for the tile after next
-    {
-      uint8_t* gTile = a.stream + tileOff;
-      const bool fits = tileOff + tileBytes <= a.streamCap;
-      if (!fits) overflow = true;
-      const int pad = (int)((uintptr_t)gTile & 15);
-      const int nChunks = (pad + (int)tileBytes + 15) >> 4;
-      const int bs8 = ((-pad) & 3) * 8;
-      for (int cI = lane; cI < nChunks; cI += 32) {
-        const int s0 = cI * 16 - pad;                                     // tile-local byte of the chunk's first byte (>= -15)
-        const int wi = s0 >> 2;                                           // floor
-        uint32_t x[5];
-#pragma unroll
-        for (int k = 0; k < 5; k++) x[k] = stage[wi + k];
-        uint32_t o[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) o[k] = __funnelshift_r(x[k], x[k + 1], bs8);
-        if (fits) {
-          if (s0 >= 0 && s0 + 16 <= (int)tileBytes) *(uint4*)(gTile + s0) = make_uint4(o[0], o[1], o[2], o[3]);
-          else {
-#pragma unroll
-            for (int j = 0; j < 16; j++) if (s0 + j >= 0 && s0 + j < (int)tileBytes) gTile[s0 + j] = (uint8_t)(o[j >> 2] >> (8 * (j & 3)));
-          }
-        }
-        // big-endian 16-bit words at even region offsets (Lerc2.cpp:1037-1064)
-        const long long r0 = a.regionOff + (long long)tileOff + s0;
-        const unsigned par = (unsigned)(r0 & 1);
-        const uint32_t w0 = (uint32_t)((unsigned long long)(r0 + 16) >> 1) % 65535u + 65535u - 8u;   // word index of byte r0 - par (mod 65535)
-        uint32_t S = 0, S1 = 0, prev = 0;
-#pragma unroll
-        for (int k = 0; k < 5; k++) {
-          const uint32_t cw = k < 4 ? o[k] : 0u;
-          const uint32_t y = __funnelshift_l(prev, cw, par * 8);        // bytes shifted up by one when the chunk starts at an odd offset
-          const uint32_t pw = __byte_perm(y, 0, 0x2301);                // low half = first BE word, high half = second
-          const uint32_t wlo = pw & 0xffffu, whi = pw >> 16;
-          S += wlo + whi; S1 += (uint32_t)(2 * k) * (wlo + whi) + whi;
-          prev = cw;
-        }
-        fa += S; fd += (unsigned long long)w0 * S + S1;
-      }
-    }
-    __syncwarp();
-    {  // zero what this tile used of the image
-      const int nz = (((int)tileBytes + 15) >> 4) + 3;
-      uint4* img = (uint4*)(stage - 4);
-      for (int i = lane; i < nz && i < NQ; i += 32) img[i] = make_uint4(0, 0, 0, 0);
-    }
-    __syncwarp();
-    // ---- next tile
-    cur = nxt; ty = nty; tx = ntx; h = nh; w = nw; act = nact;
-  }
-
-  // ---- image-global facts and checksum partials of this CTA
-#pragma unroll
-  for (int m = 1; m < 32; m <<= 1) {
-    const K omin = shflXorK<K>(gMin, m), omax = shflXorK<K>(gMax, m);
-    gMin = omin < gMin ? omin : gMin; gMax = omax > gMax ? omax : gMax;
-  }
-  if (overflow) myFlags |= FASTF_OVERFLOW;
-  myFlags = __reduce_or_sync(FULL, myFlags);
-  fa %= 65535ull; fd %= 65535ull;
-#pragma unroll
-  for (int m = 16; m; m >>= 1) { fa += __shfl_xor_sync(FULL, fa, m); fd += __shfl_xor_sync(FULL, fd, m); }
-  if (lane == 0) { sKMin[warp] = (unsigned long long)gMin; sKMax[warp] = (unsigned long long)gMax; sFlg[warp] = myFlags; sFA[warp] = fa; sFD[warp] = fd; }
-  __syncthreads();
-  if (tid == 0) {
-    unsigned long long A = 0, D = 0, kMin = ~0ull, kMax = 0; unsigned int fl = 0;
-    for (int i = 0; i < 8; i++) { A += sFA[i]; D += sFD[i]; kMin = sKMin[i] < kMin ? sKMin[i] : kMin; kMax = sKMax[i] > kMax ? sKMax[i] : kMax; fl |= sFlg[i]; }
-    if (A | D) { atomicAdd(&a.res->fletA[blockIdx.x % FAST_SLOTS], A); atomicAdd(&a.res->fletD[blockIdx.x % FAST_SLOTS], D % 65535ull); }
-    if (kMax >= kMin) {
-      if (~kMin > negMinSeen) atomicMax(&a.res->negMinKey, ~kMin);
-      if (kMax > maxSeen) atomicMax(&a.res->maxKey, kMax);
-    }
-    if (fl & ~flagsSeen) atomicOr(&a.res->flags, fl);
-  }
-}
-
 // small blob prefix (header, mask length, ranges, flag bytes) written from kernel parameters
 struct PrefixBytes { uint8_t b[128]; int n; };
 __global__ void k_write_prefix(uint8_t* dst, PrefixBytes p) { if ((int)threadIdx.x < p.n) dst[threadIdx.x] = p.b[threadIdx.x]; }

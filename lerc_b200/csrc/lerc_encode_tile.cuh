@@ -1,0 +1,438 @@
+// lerc_encode_tile.cuh -- the single-pass Lerc2 band encoder of the headline path (included by lerc_encode.cu).
+// Raster shape: every pixel valid, nDepth == 1, 8x8 micro-blocks, 16/32/64-bit pixel types.
+//
+// One CTA codes one tile = 8 pixel rows x TW micro-blocks of one block row, taken by an atomic ticket in stream
+// order (Lerc2.cpp:1507-1521), so forward progress never depends on which CTAs are co-resident:
+//
+//   stage     the tile's rows are copied into shared memory by the copy engine: one cp.async.bulk (TMA, SASS
+//             UBLKCP) per pixel row, completion on an mbarrier (lerc_tma.cuh).  The row pitch is the row
+//             size + 16 bytes, which makes both access patterns below bank-conflict free.
+//   size      two threads per micro-block: min / max / non-finite / equal-neighbour filter over its 64 pixels
+//             (GetValidDataAndStats, Lerc2.cpp:1717-1799), coding choice + byte length (NumBytesTile, Lerc2.h:416-453)
+//   scan      warp 0: exclusive scan of the block lengths; the tile's byte count is published for the look-back
+//   pack      one thread per block row: fp64 quantisation without contraction (Quantize, Lerc2.h:357-376),
+//             8 x numBits bits packed in registers, OR-ed into the staging image of the tile's output bytes
+//             (WriteTile Lerc2.cpp:1949-2021, BitStuffer2::EncodeSimple BitStuffer2.cpp:35-75, :432-472)
+//   look-back warp 0, AFTER its share of the packing: decoupled look-back over the tiles' byte counts (two
+//             levels: predecessors inside the group of 32 tiles, then aggregates of whole groups) gives the
+//             tile's byte offset in the stream; by then the predecessors have long published
+//   flush     staging -> HBM in 16-byte chunks aligned to the GLOBAL address (the image is re-aligned with funnel
+//             shifts), Fletcher-32 partial sums of exactly those bytes with dp4a (Lerc2.cpp:1037-1064)
+//
+// Several CTAs are resident per SM, so one CTA's barrier / look-back waits are filled by its neighbours' work.
+// Like its predecessor the kernel is speculative about the image-global decisions (Lerc2.cpp:179-381); the
+// facts it collects (min / max, NaN, all-integer, LUT candidates, overflow) let the caller verify them.
+#pragma once
+#include "lerc_tma.cuh"
+
+namespace lerc {
+
+template <class T> struct EncTile {
+  static constexpr int ROWB = 8 * (int)sizeof(T);                 // bytes of one block row
+  static constexpr int TW = (4096 / ROWB) < 128 ? (4096 / ROWB) : 128;   // micro-blocks per tile: 128 (16/32-bit), 64 (64-bit)
+  static constexpr int ROW_BYTES = TW * ROWB;                     // 4096 or 2048
+  static constexpr int PITCH = ROW_BYTES + 16;                    // == 16 mod 128: rows r = 0..7 of a block fall into 8 different 16-byte bank groups
+  static constexpr int IN_BYTES = 8 * PITCH;
+  static constexpr int STAGE_CAP = 17920;                         // output bytes coded per pass (128 blocks of 16-bit values: 17280)
+  static constexpr int STAGE_BYTES = 16 + STAGE_CAP + 48;         // 16 zero bytes | image | zero tail
+  static constexpr int INFO_OFF = IN_BYTES + STAGE_BYTES;         // uint4 sInfo[TW]
+  static constexpr int OFFS_OFF = INFO_OFF + TW * 16;             // uint32 sOff[TW + 1]
+  static constexpr int SMEM = OFFS_OFF + (TW + 1) * 4 + 12;
+};
+
+// sInfo[b]: x = low 32 bits of the block minimum, w = high 32 bits (64-bit types), z = unused,
+// y = numBits | offset type code << 5 | mode << 7 | (maxElem == 0) << 9 | hot << 10
+enum { TINFO_HOT = 1 << 10, TINFO_CONST = 1 << 9 };
+
+// ---- coding choice of one block by ONE thread, any block shape / pixel type (the path of everything the hot path excludes:
+// edge blocks, raw / all-zero / constant blocks, LUT candidates, values wider than 16 bits, non-float types)
+template <class T>
+__device__ __noinline__ void tileGenericChoice(const FastEncArgs& a, const uint8_t* __restrict__ blk, int pitch, int h, int w,
+                                               uint4& info, uint32_t& len, unsigned int& flags,
+                                               typename PixelTraits<T>::Key& kminOut, typename PixelTraits<T>::Key& kmaxOut) {
+  using K = typename PixelTraits<T>::Key;
+  constexpr bool isFlt = PixelTraits<T>::isFloat;
+  constexpr int DT = PixelTraits<T>::code;
+  K kmin = keyMaxValue<K>(), kmax = 0;
+  int same = 0;
+  bool notInt = false;
+  T prev = (T)0;                                                        // Lerc2.cpp:1729
+  for (int y = 0; y < h; y++) {
+    const T* row = (const T*)(blk + (size_t)y * pitch);
+    for (int x = 0; x < w; x++) {
+      const T v = row[x];
+      const K key = toKey(v);
+      kmin = key < kmin ? key : kmin; kmax = key > kmax ? key : kmax;
+      same += (v == prev) ? 1 : 0; prev = v;
+      if (isFlt) notInt |= (sizeof(T) == 4 ? ((float)v != truncf((float)v)) : ((double)v != trunc((double)v)));
+    }
+  }
+  kminOut = kmin; kmaxOut = kmax;
+  const int n = h * w;
+  const T lo = fromKey<T>(kmin), hi = fromKey<T>(kmax);
+  const double zMin = (double)lo, zMax = (double)hi;
+  unsigned int fl = notInt ? FASTF_NOT_INT : 0;
+  if (isFlt && (isNaNVal(lo) || isNaNVal(hi))) fl |= FASTF_NAN;
+  if (n > 4 && (zMax > __dadd_rn(zMin, a.maxZErr3)) && (2 * same > n)) fl |= FASTF_LUT;            // Lerc2.cpp:1794-1795
+  flags = fl;
+  int mode = BEM_RAW, nb = 0, tc = 0, dtUsed = DT, nBytes = 0;
+  uint32_t maxElem = 0;
+  const int raw = 1 + n * (int)sizeof(T);                                                          // NumBytesTile, Lerc2.h:416-453; tryLut == false
+  if (zMin == 0 && zMax == 0) { nBytes = 1; mode = BEM_ZERO; }
+  else {
+    const double mv = __dmul_rn(__dsub_rn(zMax, zMin), a.scale);
+    if (mv > (double)a.maxQ) nBytes = raw;
+    else {
+      tc = reduceOffsetType(zMin, DT, dtUsed);
+      int nbt = 1 + dtSize(dtUsed);
+      maxElem = roundToUInt(mv);
+      if (maxElem > 0) { nb = bitLength(maxElem); nbt += 2 + (int)packedBytes(n, nb); }
+      if (nbt < raw) { mode = BEM_SIMPLE; nBytes = nbt; } else nBytes = raw;
+    }
+  }
+  unsigned long long lb = 0; memcpy(&lb, &lo, sizeof(T));
+  info.x = (uint32_t)lb; info.w = (uint32_t)(lb >> 32); info.z = 0;
+  info.y = (uint32_t)(nb | (tc << 5) | (mode << 7) | (maxElem == 0 ? TINFO_CONST : 0));
+  len = (uint32_t)nBytes;
+}
+
+// Fletcher-32 partial sums of one 16-byte output chunk whose first byte has checksum-region offset r0 (parity PAR):
+// S = sum of the chunk's bytes weighted 256 (even region offsets) / 1 (odd), S1 = the same weighted with the byte's
+// word index relative to the chunk's first word.
+template <int PAR>
+__device__ __forceinline__ void fletcherChunk(const uint32_t (&o)[4], uint32_t& S, uint32_t& S1) {
+  uint32_t H = 0, L = 0, HW = 0, LW = 0;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    if (PAR == 0) {   // bytes 0, 2 of a word are high bytes; word index of byte 4j + m: (4j + m) >> 1
+      H = __dp4a(o[j], 0x00010001u, H);  L = __dp4a(o[j], 0x01000100u, L);
+      HW = __dp4a(o[j], (uint32_t)(2 * j) | ((uint32_t)(2 * j + 1) << 16), HW);
+      LW = __dp4a(o[j], ((uint32_t)(2 * j) << 8) | ((uint32_t)(2 * j + 1) << 24), LW);
+    } else {          // bytes 1, 3 are high bytes; word index of byte 4j + m: (4j + m + 1) >> 1
+      H = __dp4a(o[j], 0x01000100u, H);  L = __dp4a(o[j], 0x00010001u, L);
+      HW = __dp4a(o[j], ((uint32_t)(2 * j + 1) << 8) | ((uint32_t)(2 * j + 2) << 24), HW);
+      LW = __dp4a(o[j], (uint32_t)(2 * j) | ((uint32_t)(2 * j + 1) << 16), LW);
+    }
+  }
+  S = 256u * H + L; S1 = 256u * HW + LW;
+}
+
+template <class T, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_encode_tile(FastEncArgs a) {
+  using K = typename PixelTraits<T>::Key;
+  using C = EncTile<T>;
+  constexpr bool isFlt = PixelTraits<T>::isFloat;
+  constexpr bool hotType = isFlt && sizeof(T) == 4;
+  constexpr int TW = C::TW, PITCH = C::PITCH, ROWB = C::ROWB;
+  extern __shared__ __align__(16) uint8_t tileSmem[];
+  uint8_t* sIn = tileSmem;
+  uint32_t* stageRaw = (uint32_t*)(tileSmem + C::IN_BYTES);
+  uint32_t* stage = stageRaw + 4;                                 // pass-local byte 0 of the output image
+  uint4* sInfo = (uint4*)(tileSmem + C::INFO_OFF);
+  uint32_t* sOff = (uint32_t*)(tileSmem + C::OFFS_OFF);
+  __shared__ __align__(8) uint64_t sBar;
+  __shared__ int sTile;
+  __shared__ unsigned long long sTileOff;
+  __shared__ unsigned long long sKMin[8], sKMax[8], sFA[8], sFD[8];
+  __shared__ unsigned int sFlg[8];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const T* data = (const T*)a.data;
+  const bool vecOk = (((long long)a.nCols * (int)sizeof(T)) % 16 == 0) && (((uintptr_t)data & 15) == 0);
+  const int tpr = (a.nTx + TW - 1) / TW;                          // tiles per block row
+  const int nTiles = tpr * a.nTy;
+  constexpr unsigned long long ST_A = 1ull << 62, ST_P = 2ull << 62, VAL = (1ull << 62) - 1;
+  volatile unsigned long long* st = a.tileState;
+
+  // ---- ticket, copy engine
+  if (tid == 0) {
+    const int t = (int)atomicAdd(&a.res->ticket, 1u);
+    sTile = t;
+    if (vecOk) {
+      const int tyT = t / tpr, seg = t - tyT * tpr;
+      const int h = min(8, a.nRows - tyT * 8), cols = min(TW * 8, a.nCols - seg * TW * 8);
+      const uint32_t rowBytes = (uint32_t)cols * (uint32_t)sizeof(T);
+      mbarInit(&sBar, 1);
+      mbarExpectTx(&sBar, rowBytes * (uint32_t)h);
+      const T* src = data + (size_t)(tyT * 8) * a.nCols + (size_t)seg * TW * 8;
+      for (int y = 0; y < h; y++) bulkLoad(sIn + y * PITCH, src + (size_t)y * a.nCols, rowBytes, &sBar);
+    }
+  }
+  for (int i = tid; i < C::STAGE_BYTES / 16; i += 256) ((uint4*)stageRaw)[i] = make_uint4(0, 0, 0, 0);
+  const unsigned int flagsSeen = *(volatile unsigned int*)&a.res->flags;
+  const unsigned long long negMinSeen = *(volatile unsigned long long*)&a.res->negMinKey, maxSeen = *(volatile unsigned long long*)&a.res->maxKey;
+  __syncthreads();
+  const int tile = sTile;
+  const int tyT = tile / tpr, seg = tile - tyT * tpr;
+  const int bx0 = seg * TW;                                        // first block column of the tile
+  const int nbk = min(TW, a.nTx - bx0);                            // blocks in the tile
+  const int h = min(8, a.nRows - tyT * 8);
+  if (vecOk) mbarWait(&sBar, 0);
+  else {
+    const int cols = min(TW * 8, a.nCols - bx0 * 8);
+    const T* src = data + (size_t)(tyT * 8) * a.nCols + (size_t)bx0 * 8;
+    for (int y = 0; y < h; y++)
+      for (int x = tid; x < cols; x += 256) ((T*)(sIn + y * PITCH))[x] = src[(size_t)y * a.nCols + x];
+    __syncthreads();
+  }
+
+  // running image-global facts and checksum partials of this thread
+  K gMin = keyMaxValue<K>(), gMax = 0;
+  unsigned int myFlags = 0;
+  unsigned long long fa = 0, fd = 0;
+
+  // ---- size: two threads per block (rows 0-3 / 4-7)
+  for (int bb = tid >> 1; bb < TW; bb += 128) {
+    const int hf = tid & 1;
+    const bool act = bb < nbk;
+    const int w = act ? min(8, a.nCols - (bx0 + bb) * 8) : 0;
+    const bool full = act && h == 8 && w == 8;
+    bool hot = false;
+    uint4 info = make_uint4(0, 0, 0, 0);
+    uint32_t len = 0;
+    if (hotType) {
+      // hot path test for full 8x8 float blocks coded "bit-stuffed, <= 16 bits, offset as float/short/byte".  The thread with hf == 1
+      // reads the two halves of a row in swapped order (bank-conflict free); min / max / the filters do not care about the order.
+      const uint8_t* base = sIn + (hf * 4) * PITCH + bb * ROWB;
+      float mn = __int_as_float(0x7f800000), mx = __int_as_float(0xff800000), t0 = 0.f;   // t0: NaN iff some value is NaN or +-Inf
+      bool eq = false, ni = (flagsSeen & FASTF_NOT_INT) != 0;
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const uint4 A = *(const uint4*)(base + i * PITCH + hf * 16), B = *(const uint4*)(base + i * PITCH + 16 - hf * 16);
+        const float a0 = __uint_as_float(A.x), a1 = __uint_as_float(A.y), a2 = __uint_as_float(A.z), a3 = __uint_as_float(A.w);
+        const float b0 = __uint_as_float(B.x), b1 = __uint_as_float(B.y), b2 = __uint_as_float(B.z), b3 = __uint_as_float(B.w);
+        mn = fminf(fminf(fminf(mn, a0), fminf(a1, a2)), fminf(fminf(a3, b0), fminf(fminf(b1, b2), b3)));
+        mx = fmaxf(fmaxf(fmaxf(mx, a0), fmaxf(a1, a2)), fmaxf(fmaxf(a3, b0), fmaxf(fmaxf(b1, b2), b3)));
+        t0 = __fmaf_rn(a0, 0.f, t0); t0 = __fmaf_rn(a1, 0.f, t0); t0 = __fmaf_rn(a2, 0.f, t0); t0 = __fmaf_rn(a3, 0.f, t0);
+        t0 = __fmaf_rn(b0, 0.f, t0); t0 = __fmaf_rn(b1, 0.f, t0); t0 = __fmaf_rn(b2, 0.f, t0); t0 = __fmaf_rn(b3, 0.f, t0);
+        // equal neighbours inside a 16-byte group: 48 of the block's 64 (value, predecessor) pairs.  No such pair => at most 16 equal
+        // pairs => never a LUT candidate (needs more than 32, Lerc2.cpp:1794); otherwise the exact count is taken below.
+        eq |= (a0 == a1) | (a1 == a2) | (a2 == a3) | (b0 == b1) | (b1 == b2) | (b2 == b3);
+        if (!ni) {                                                  // all-integer test (Lerc.h:248): exact per thread, cheap once a fraction was seen
+          ni = a0 != truncf(a0);
+          if (!ni) ni = (a1 != truncf(a1)) | (a2 != truncf(a2)) | (a3 != truncf(a3)) | (b0 != truncf(b0)) | (b1 != truncf(b1)) | (b2 != truncf(b2)) | (b3 != truncf(b3));
+        }
+      }
+      mn = fminf(mn, __shfl_xor_sync(FULL, mn, 1)); mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, 1));
+      unsigned pk = (t0 != t0 ? 1u : 0u) | (eq ? 2u : 0u);
+      pk |= __shfl_xor_sync(FULL, pk, 1);
+      const double zMn = (double)mn, zMx = (double)mx;
+      const double mv = __dmul_rn(__dsub_rn(zMx, zMn), a.scale);
+      const uint32_t me = roundToUInt(mv);
+      const int nbh = bitLength(me);
+      const bool lutMaybe = (pk & 2) && (zMx > __dadd_rn(zMn, a.maxZErr3));
+      hot = full && !(pk & 1) && !(mv > (double)a.maxQ) && me > 0 && nbh <= 16 && !lutMaybe && !(mn == 0.f && mx == 0.f);
+      if (hot) {
+        // offset in the smallest type that holds it (Lerc2.h:457-542, float row)
+        const bool isInt = mn == truncf(mn);
+        const int tc = (isInt && mn >= 0.f && mn <= 255.f) ? 2 : ((isInt && mn >= -32768.f && mn <= 32767.f) ? 1 : 0);
+        len = (uint32_t)(3 + (4 >> tc) + 8 * nbh);
+        info.x = __float_as_uint(mn); info.y = (uint32_t)(nbh | (tc << 5) | (BEM_SIMPLE << 7) | TINFO_HOT);
+        const uint32_t kmn = toKey(mn), kmx = toKey(mx);
+        gMin = kmn < gMin ? (K)kmn : gMin; gMax = kmx > gMax ? (K)kmx : gMax;
+        if (ni) myFlags |= FASTF_NOT_INT;
+      }
+    }
+    if (!hot && act && hf == 0) {
+      unsigned int fl = 0; K kmin, kmax;
+      tileGenericChoice<T>(a, sIn + bb * ROWB, PITCH, h, w, info, len, fl, kmin, kmax);
+      myFlags |= fl;
+      gMin = kmin < gMin ? kmin : gMin; gMax = kmax > gMax ? kmax : gMax;
+    }
+    if (hf == 0) { sInfo[bb] = info; sOff[bb] = len; }
+  }
+  __syncthreads();
+
+  // ---- scan (warp 0): block lengths -> exclusive byte offsets inside the tile, sOff[TW] = the tile's bytes
+  if (warp == 0) {
+    constexpr int PER = TW / 32;
+    uint32_t v[PER], sum = 0;
+#pragma unroll
+    for (int k = 0; k < PER; k++) { v[k] = sOff[lane * PER + k]; sum += v[k]; }
+    uint32_t inc = sum;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) { const uint32_t o = __shfl_up_sync(FULL, inc, s); if (lane >= s) inc += o; }
+    uint32_t run = inc - sum;
+#pragma unroll
+    for (int k = 0; k < PER; k++) { sOff[lane * PER + k] = run; run += v[k]; }
+    if (lane == 31) { sOff[TW] = inc; st[tile] = (tile == 0 ? ST_P : ST_A) | (unsigned long long)inc; }   // publish before packing
+  }
+  __syncthreads();
+  const uint32_t tileBytes = sOff[TW];
+
+  // ---- pack + flush, in passes of at most STAGE_CAP output bytes (one pass unless the blocks are wider than 16 bits per value)
+  const unsigned par = (unsigned)((a.regionOff + (long long)(uintptr_t)a.stream) & 1);    // parity of the region offset of every 16-byte aligned output byte
+  bool overflow = false, haveOff = false;
+  unsigned long long tileOff = 0;
+  int bLo = 0;
+  uint32_t passBase = 0;
+  while (bLo < nbk) {
+    int bHi = nbk;
+    if (tileBytes - passBase > (uint32_t)C::STAGE_CAP) {           // largest bHi with sOff[bHi] - passBase <= STAGE_CAP (a block is at most 513 bytes)
+      int lo = bLo + 1, hi = nbk;
+      while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (sOff[mid] - passBase <= (uint32_t)C::STAGE_CAP) lo = mid; else hi = mid - 1; }
+      bHi = lo;
+    }
+    const uint32_t passBytes = (bHi == nbk ? tileBytes : sOff[bHi]) - passBase;
+
+    // headers of the hot blocks: flag | offset | numBits byte | count (WriteTile, Lerc2.cpp:1949-2021; BitStuffer2.cpp:35-75)
+    for (int b = bLo + tid; b < bHi; b += 256) {
+      const uint4 info = sInfo[b];
+      if (info.y & TINFO_HOT) {
+        const int nb = info.y & 31, tc = (info.y >> 5) & 3, osz = 4 >> tc;
+        const int j0 = (bx0 + b) * 8;
+        const uint32_t flag = (uint32_t)((((j0 >> 3) & 15) << 2) & 0x38);
+        const float lof = __uint_as_float(info.x);
+        const unsigned long long ob = tc == 0 ? (unsigned long long)info.x : (tc == 1 ? (unsigned long long)(uint16_t)(int16_t)lof : (unsigned long long)(uint8_t)lof);
+        unsigned long long hd = (unsigned long long)(flag | 1 | (tc << 6)) | (ob << 8);
+        hd |= ((unsigned long long)(nb | (2 << 6)) | (64ull << 8)) << (8 * (1 + osz));
+        const uint32_t H[2] = {(uint32_t)hd, (uint32_t)(hd >> 32)};
+        orBits<2>(stage, (sOff[b] - passBase) * 8, H, (3 + osz) * 8);
+      }
+    }
+    // block rows: 8 lanes per block
+    for (int g = bLo * 8 + tid; g < bHi * 8; g += 256) {
+      const int bb = g >> 3, r = g & 7;
+      const uint4 info = sInfo[bb];
+      const uint32_t byte0 = sOff[bb] - passBase;
+      const uint8_t* row = sIn + r * PITCH + bb * ROWB;
+      if (hotType && (info.y & TINFO_HOT)) {
+        const int nb = info.y & 31, osz = 4 >> ((info.y >> 5) & 3);
+        const uint4 A = *(const uint4*)row, B = *(const uint4*)(row + 16);
+        const double zMin = (double)__uint_as_float(info.x);
+        uint32_t q[8];
+        q[0] = quantizeOne((double)__uint_as_float(A.x), zMin, a.scale); q[1] = quantizeOne((double)__uint_as_float(A.y), zMin, a.scale);
+        q[2] = quantizeOne((double)__uint_as_float(A.z), zMin, a.scale); q[3] = quantizeOne((double)__uint_as_float(A.w), zMin, a.scale);
+        q[4] = quantizeOne((double)__uint_as_float(B.x), zMin, a.scale); q[5] = quantizeOne((double)__uint_as_float(B.y), zMin, a.scale);
+        q[6] = quantizeOne((double)__uint_as_float(B.z), zMin, a.scale); q[7] = quantizeOne((double)__uint_as_float(B.w), zMin, a.scale);
+        // 8 values of nb <= 16 bits -> 128 bits
+        const unsigned long long p0 = q[0] | ((unsigned long long)q[1] << nb), p1 = q[2] | ((unsigned long long)q[3] << nb);
+        const unsigned long long p2 = q[4] | ((unsigned long long)q[5] << nb), p3 = q[6] | ((unsigned long long)q[7] << nb);
+        const int s2 = 2 * nb, s4 = 4 * nb;
+        const unsigned long long h0 = p0 | (p1 << s2), h1 = p2 | (p3 << s2);      // 4 nb <= 64 bits each
+        const unsigned long long r0 = s4 == 64 ? h0 : (h0 | (h1 << s4)), r1 = s4 == 64 ? h1 : (h1 >> (64 - s4));
+        const uint32_t R[4] = {(uint32_t)r0, (uint32_t)(r0 >> 32), (uint32_t)r1, (uint32_t)(r1 >> 32)};
+        orBits<4>(stage, (byte0 + (uint32_t)(osz + 3) + (uint32_t)(r * nb)) * 8, R, 8 * nb);
+      } else {
+        const int w = min(8, a.nCols - (bx0 + bb) * 8);
+        const int mode = (info.y >> 7) & 3, nb = info.y & 31, tc = (info.y >> 5) & 3;
+        const int dtUsed = offsetTypeFromCode(PixelTraits<T>::code, tc);
+        const unsigned long long lb = (unsigned long long)info.x | ((unsigned long long)info.w << 32);
+        T lo; memcpy(&lo, &lb, sizeof(T));
+        fastGenericEmit<T>(a, stage, (const T*)row, h, w, r, (bx0 + bb) * 8, byte0, mode, nb, tc, dtUsed, (info.y & TINFO_CONST) ? 0u : 1u, (double)lo, lo);
+      }
+    }
+
+    // ---- decoupled look-back (warp 0, once per tile) for the tile's byte offset in the stream
+    if (!haveOff && warp == 0) {
+      unsigned long long excl = 0;
+      volatile unsigned long long* gs = a.groupState;
+      const int l = tile & 31;
+      const long long g = tile >> 5;
+      bool needGroups = g > 0;
+      {  // round 1: the predecessors inside the tile's group of 32
+        const long long idx = (long long)tile - 1 - lane;
+        const bool in = lane < l;
+        unsigned long long s = 0;
+        if (in) { do { s = st[idx]; } while ((s >> 62) == 0); }
+        const unsigned isP = __ballot_sync(FULL, in && (s >> 62) == 2);
+        const int firstP = isP ? __ffs(isP) - 1 : 32;
+        unsigned long long contrib = (in && lane <= firstP) ? (s & VAL) : 0;
+#pragma unroll
+        for (int m = 16; m; m >>= 1) contrib += __shfl_xor_sync(FULL, contrib, m);
+        excl = contrib;
+        if (isP) needGroups = false;                                    // an inclusive prefix inside the group: excl is already global
+      }
+      if (l == 31 && needGroups && lane == 0) gs[g] = ST_A | (excl + tileBytes);      // this group's bytes (its 32 tiles are all sized)
+      if (needGroups) {  // round 2: aggregates of whole groups, published by the CTA that sized a group's last tile
+        long long base = g - 1;
+        for (;;) {
+          const long long idx = base - lane;
+          unsigned long long s = ST_P;                                  // virtual groups before 0: prefix 0
+          if (idx >= 0) { do { s = gs[idx]; } while ((s >> 62) == 0); }
+          const unsigned isP = __ballot_sync(FULL, (s >> 62) == 2);
+          const int firstP = isP ? __ffs(isP) - 1 : 32;
+          unsigned long long contrib = (lane <= firstP && idx >= 0) ? (s & VAL) : 0;
+#pragma unroll
+          for (int m = 16; m; m >>= 1) contrib += __shfl_xor_sync(FULL, contrib, m);
+          excl += contrib;
+          if (isP) break;
+          base -= 32;
+        }
+      }
+      if (lane == 0) {
+        if (tile > 0) st[tile] = ST_P | (excl + tileBytes);
+        if (l == 31) gs[g] = ST_P | (excl + tileBytes);                 // inclusive prefix of the whole group
+        sTileOff = excl;
+        if (tile == nTiles - 1) a.res->totalBytes = excl + tileBytes;
+      }
+    }
+    __syncthreads();                                               // staging image complete, tile offset known
+    if (!haveOff) { tileOff = sTileOff; haveOff = true; }
+
+    // ---- staging -> HBM, Fletcher-32 partial sums of the same 16-byte chunks (bytes outside the pass are zero in the image)
+    {
+      const unsigned long long passOff = tileOff + passBase;         // offset of the pass's first byte in the block stream
+      uint8_t* gPass = a.stream + passOff;
+      const bool fits = passOff + passBytes <= a.streamCap;
+      if (!fits) overflow = true;
+      const int pad = (int)((uintptr_t)gPass & 15);
+      const int nChunks = (pad + (int)passBytes + 15) >> 4;
+      const int bs8 = ((-pad) & 3) * 8;
+      for (int cI = tid; cI < nChunks; cI += 256) {
+        const int s0 = cI * 16 - pad;                                     // pass-local byte of the chunk's first byte (>= -15)
+        const int wi = s0 >> 2;                                           // floor
+        uint32_t x[5];
+#pragma unroll
+        for (int k = 0; k < 5; k++) x[k] = stage[wi + k];
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) o[k] = __funnelshift_r(x[k], x[k + 1], bs8);
+        if (fits) {
+          if (s0 >= 0 && s0 + 16 <= (int)passBytes) *(uint4*)(gPass + s0) = make_uint4(o[0], o[1], o[2], o[3]);
+          else {
+#pragma unroll
+            for (int j = 0; j < 16; j++) if (s0 + j >= 0 && s0 + j < (int)passBytes) gPass[s0 + j] = (uint8_t)(o[j >> 2] >> (8 * (j & 3)));
+          }
+        }
+        const long long r0 = a.regionOff + (long long)passOff + s0;       // region offset of the chunk's first byte; r0 & 1 == par
+        const uint32_t w0 = (uint32_t)((unsigned long long)(r0 - par) >> 1) % 65535u;   // word index of the chunk's first word (mod 65535)
+        uint32_t S, S1;
+        if (par) fletcherChunk<1>(o, S, S1); else fletcherChunk<0>(o, S, S1);
+        fa += S; fd += (unsigned long long)w0 * S + S1;
+      }
+    }
+    bLo = bHi; passBase += passBytes;
+    if (bLo < nbk) {                                                 // another pass: clear the image
+      __syncthreads();
+      for (int i = tid; i < C::STAGE_BYTES / 16; i += 256) ((uint4*)stageRaw)[i] = make_uint4(0, 0, 0, 0);
+      __syncthreads();
+    }
+  }
+
+  // ---- image-global facts and checksum partials of this CTA
+#pragma unroll
+  for (int m = 1; m < 32; m <<= 1) {
+    const K omin = shflXorK<K>(gMin, m), omax = shflXorK<K>(gMax, m);
+    gMin = omin < gMin ? omin : gMin; gMax = omax > gMax ? omax : gMax;
+  }
+  if (overflow) myFlags |= FASTF_OVERFLOW;
+  myFlags = __reduce_or_sync(FULL, myFlags);
+  fa %= 65535ull; fd %= 65535ull;
+#pragma unroll
+  for (int m = 16; m; m >>= 1) { fa += __shfl_xor_sync(FULL, fa, m); fd += __shfl_xor_sync(FULL, fd, m); }
+  if (lane == 0) { sKMin[warp] = (unsigned long long)gMin; sKMax[warp] = (unsigned long long)gMax; sFlg[warp] = myFlags; sFA[warp] = fa; sFD[warp] = fd; }
+  __syncthreads();
+  if (tid == 0) {
+    unsigned long long A = 0, D = 0, kMin = ~0ull, kMax = 0; unsigned int fl = 0;
+    for (int i = 0; i < 8; i++) { A += sFA[i]; D += sFD[i]; kMin = sKMin[i] < kMin ? sKMin[i] : kMin; kMax = sKMax[i] > kMax ? sKMax[i] : kMax; fl |= sFlg[i]; }
+    if (A | D) { atomicAdd(&a.res->fletA[tile % FAST_SLOTS], A); atomicAdd(&a.res->fletD[tile % FAST_SLOTS], D % 65535ull); }
+    if (kMax >= kMin) {
+      if (~kMin > negMinSeen) atomicMax(&a.res->negMinKey, ~kMin);
+      if (kMax > maxSeen) atomicMax(&a.res->maxKey, kMax);
+    }
+    if (fl & ~flagsSeen) atomicOr(&a.res->flags, fl);
+  }
+}
+
+}  // namespace lerc

@@ -236,19 +236,6 @@ ErrCode encodeTilesFast(Context* ctx, const TilesGeom& g, const void* dData, dou
     constexpr int MAXB = 1 + 64 * (int)sizeof(T);
     const size_t smem = (size_t)((FAST_TB * MAXB + 15) / 16 + 3) * 16 * 2 + 256 * 8 * sizeof(T);
     int dev = 0, sms = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    static const bool pipeEnc = [] { const char* e = std::getenv("LERC_B200_ENC"); return e && std::strcmp(e, "pipe") == 0; }();
-    if (pipeEnc) {
-      // experimental (lerc_encode_pipe.cuh): look-backs deferred by one tile and done per warp, one barrier per tile
-      const size_t smemP = (size_t)((FAST_TB * MAXB + 15) / 16 + 3) * 16 * 3 + 256 * 8 * sizeof(T);
-      static int ctasPipe = 0;
-      auto kp = k_encode_pipe<T, 4, true>;
-      if (!ctasPipe) {
-        cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemP);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPipe, kp, 256, smemP) != cudaSuccess || ctasPipe < 1) ctasPipe = 1;
-      }
-      const long long gridP = std::min<long long>(nSeg, (long long)ctasPipe * std::max(sms, 1));
-      { LaunchScope scope_(ctx, "k_encode_pipe<T, tiles>"); kp<<<(unsigned)gridP, 256, smemP, ctx->stream>>>(fa, fb); ctx->kernelLaunches++; }
-    } else {
     static int ctasPerSm = 0;
     auto kernel = k_encode_fused<T, 4, true>;
     if (!ctasPerSm) {
@@ -257,7 +244,6 @@ ErrCode encodeTilesFast(Context* ctx, const TilesGeom& g, const void* dData, dou
     }
     const long long grid = std::min<long long>(nSeg, (long long)ctasPerSm * std::max(sms, 1));       // all CTAs co-resident (look-back)
     { LaunchScope scope_(ctx, "k_encode_fused<T, tiles>"); kernel<<<(unsigned)grid, 256, smem, ctx->stream>>>(fa, fb); ctx->kernelLaunches++; }
-    }
   }
   ctx->joinSide();
   TileFinishArgs ta;

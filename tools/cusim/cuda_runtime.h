@@ -211,6 +211,10 @@ static inline unsigned __brev(unsigned v) { unsigned r = 0; for (int i = 0; i < 
 static inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned s) { s &= 31; return (unsigned)(((((unsigned long long)hi << 32) | lo) << s) >> 32); }
 static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned s) { s &= 31; return (unsigned)((((unsigned long long)hi << 32) | lo) >> s); }
 static inline unsigned __funnelshift_lc(unsigned lo, unsigned hi, unsigned s) { if (s >= 32) return lo; return __funnelshift_l(lo, hi, s); }
+static inline unsigned __dp4a(unsigned a, unsigned b, unsigned c) {   // unsigned 4 x 8-bit dot product + c
+  for (int i = 0; i < 4; i++) c += ((a >> (8 * i)) & 0xffu) * ((b >> (8 * i)) & 0xffu);
+  return c;
+}
 static inline unsigned __funnelshift_rc(unsigned lo, unsigned hi, unsigned s) { if (s >= 32) return hi; return __funnelshift_r(lo, hi, s); }
 static inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {
   const unsigned long long src = ((unsigned long long)y << 32) | x;
