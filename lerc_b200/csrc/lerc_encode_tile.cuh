@@ -13,9 +13,9 @@
 //   pack      one thread per block row: fp64 quantisation without contraction (Quantize, Lerc2.h:357-376),
 //             8 x numBits bits packed in registers, OR-ed into the staging image of the tile's output bytes
 //             (WriteTile Lerc2.cpp:1949-2021, BitStuffer2::EncodeSimple BitStuffer2.cpp:35-75, :432-472)
-//   look-back warp 0, AFTER its share of the packing: decoupled look-back over the tiles' byte counts (two
-//             levels: predecessors inside the group of 32 tiles, then aggregates of whole groups) gives the
-//             tile's byte offset in the stream; by then the predecessors have long published
+//   look-back warp 7, while the other warps pack: decoupled look-back over the tiles' byte counts (two levels:
+//             predecessors inside the group of 32 tiles, then aggregates of whole groups) gives the tile's byte
+//             offset in the stream; everything it waits for is published before the predecessors' packing
 //   flush     staging -> HBM in 16-byte chunks aligned to the GLOBAL address (the image is re-aligned with funnel
 //             shifts), Fletcher-32 partial sums of exactly those bytes with dp4a (Lerc2.cpp:1037-1064)
 //
@@ -117,6 +117,26 @@ __device__ __forceinline__ void fletcherChunk(const uint32_t (&o)[4], uint32_t& 
   S = 256u * H + L; S1 = 256u * HW + LW;
 }
 
+// OR a word into shared memory: one ATOMS.OR without a result.  (ptxas turns a predicated red into a branch around the ATOMS,
+// four instructions; OR-ing a zero word costs one.)
+__device__ __forceinline__ void smemOr(uint32_t* p, uint32_t v) {
+#ifndef LERC_CUSIM
+  asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(smemAddr(p)), "r"(v) : "memory");
+#else
+  atomicOr(p, v);
+#endif
+}
+// one thread takes the next value of a shared-memory counter (kept away from the compiler's warp-aggregated atomics)
+__device__ __forceinline__ int smemTake(int* p) {
+#ifndef LERC_CUSIM
+  int v;
+  asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(v) : "r"(smemAddr(p)) : "memory");
+  return v;
+#else
+  return atomicAdd(p, 1);
+#endif
+}
+
 template <class T, int MINB>
 __global__ void __launch_bounds__(256, MINB) k_encode_tile(FastEncArgs a) {
   using K = typename PixelTraits<T>::Key;
@@ -131,7 +151,7 @@ __global__ void __launch_bounds__(256, MINB) k_encode_tile(FastEncArgs a) {
   uint4* sInfo = (uint4*)(tileSmem + C::INFO_OFF);
   uint32_t* sOff = (uint32_t*)(tileSmem + C::OFFS_OFF);
   __shared__ __align__(8) uint64_t sBar;
-  __shared__ int sTile;
+  __shared__ int sTile, sNextChunk;
   __shared__ unsigned long long sTileOff;
   __shared__ unsigned long long sKMin[8], sKMax[8], sFA[8], sFD[8];
   __shared__ unsigned int sFlg[8];
@@ -147,7 +167,7 @@ __global__ void __launch_bounds__(256, MINB) k_encode_tile(FastEncArgs a) {
   // ---- ticket, copy engine
   if (tid == 0) {
     const int t = (int)atomicAdd(&a.res->ticket, 1u);
-    sTile = t;
+    sTile = t; sNextChunk = 0;
     if (vecOk) {
       const int tyT = t / tpr, seg = t - tyT * tpr;
       const int h = min(8, a.nRows - tyT * 8), cols = min(TW * 8, a.nCols - seg * TW * 8);
@@ -290,41 +310,11 @@ __global__ void __launch_bounds__(256, MINB) k_encode_tile(FastEncArgs a) {
         orBits<2>(stage, (sOff[b] - passBase) * 8, H, (3 + osz) * 8);
       }
     }
-    // block rows: 8 lanes per block
-    for (int g = bLo * 8 + tid; g < bHi * 8; g += 256) {
-      const int bb = g >> 3, r = g & 7;
-      const uint4 info = sInfo[bb];
-      const uint32_t byte0 = sOff[bb] - passBase;
-      const uint8_t* row = sIn + r * PITCH + bb * ROWB;
-      if (hotType && (info.y & TINFO_HOT)) {
-        const int nb = info.y & 31, osz = 4 >> ((info.y >> 5) & 3);
-        const uint4 A = *(const uint4*)row, B = *(const uint4*)(row + 16);
-        const double zMin = (double)__uint_as_float(info.x);
-        uint32_t q[8];
-        q[0] = quantizeOne((double)__uint_as_float(A.x), zMin, a.scale); q[1] = quantizeOne((double)__uint_as_float(A.y), zMin, a.scale);
-        q[2] = quantizeOne((double)__uint_as_float(A.z), zMin, a.scale); q[3] = quantizeOne((double)__uint_as_float(A.w), zMin, a.scale);
-        q[4] = quantizeOne((double)__uint_as_float(B.x), zMin, a.scale); q[5] = quantizeOne((double)__uint_as_float(B.y), zMin, a.scale);
-        q[6] = quantizeOne((double)__uint_as_float(B.z), zMin, a.scale); q[7] = quantizeOne((double)__uint_as_float(B.w), zMin, a.scale);
-        // 8 values of nb <= 16 bits -> 128 bits
-        const unsigned long long p0 = q[0] | ((unsigned long long)q[1] << nb), p1 = q[2] | ((unsigned long long)q[3] << nb);
-        const unsigned long long p2 = q[4] | ((unsigned long long)q[5] << nb), p3 = q[6] | ((unsigned long long)q[7] << nb);
-        const int s2 = 2 * nb, s4 = 4 * nb;
-        const unsigned long long h0 = p0 | (p1 << s2), h1 = p2 | (p3 << s2);      // 4 nb <= 64 bits each
-        const unsigned long long r0 = s4 == 64 ? h0 : (h0 | (h1 << s4)), r1 = s4 == 64 ? h1 : (h1 >> (64 - s4));
-        const uint32_t R[4] = {(uint32_t)r0, (uint32_t)(r0 >> 32), (uint32_t)r1, (uint32_t)(r1 >> 32)};
-        orBits<4>(stage, (byte0 + (uint32_t)(osz + 3) + (uint32_t)(r * nb)) * 8, R, 8 * nb);
-      } else {
-        const int w = min(8, a.nCols - (bx0 + bb) * 8);
-        const int mode = (info.y >> 7) & 3, nb = info.y & 31, tc = (info.y >> 5) & 3;
-        const int dtUsed = offsetTypeFromCode(PixelTraits<T>::code, tc);
-        const unsigned long long lb = (unsigned long long)info.x | ((unsigned long long)info.w << 32);
-        T lo; memcpy(&lo, &lb, sizeof(T));
-        fastGenericEmit<T>(a, stage, (const T*)row, h, w, r, (bx0 + bb) * 8, byte0, mode, nb, tc, dtUsed, (info.y & TINFO_CONST) ? 0u : 1u, (double)lo, lo);
-      }
-    }
-
-    // ---- decoupled look-back (warp 0, once per tile) for the tile's byte offset in the stream
-    if (!haveOff && warp == 0) {
+    // ---- decoupled look-back (warp 7, once per tile, right after the tile's byte count was published) for the tile's byte offset
+    // in the stream.  Everything it waits for is published by the predecessors BEFORE their packing: a tile's own byte count
+    // after its scan, a group's aggregate by the warp 7 of the group's last tile in its round 1.  The other warps pack meanwhile;
+    // warp 7 joins them when it is done (block rows are handed out in chunks of 32).
+    if (!haveOff && warp == 7) {
       unsigned long long excl = 0;
       volatile unsigned long long* gs = a.groupState;
       const int l = tile & 31;
@@ -344,7 +334,7 @@ __global__ void __launch_bounds__(256, MINB) k_encode_tile(FastEncArgs a) {
         if (isP) needGroups = false;                                    // an inclusive prefix inside the group: excl is already global
       }
       if (l == 31 && needGroups && lane == 0) gs[g] = ST_A | (excl + tileBytes);      // this group's bytes (its 32 tiles are all sized)
-      if (needGroups) {  // round 2: aggregates of whole groups, published by the CTA that sized a group's last tile
+      if (needGroups) {  // round 2: aggregates of whole groups
         long long base = g - 1;
         for (;;) {
           const long long idx = base - lane;
@@ -365,6 +355,62 @@ __global__ void __launch_bounds__(256, MINB) k_encode_tile(FastEncArgs a) {
         if (l == 31) gs[g] = ST_P | (excl + tileBytes);                 // inclusive prefix of the whole group
         sTileOff = excl;
         if (tile == nTiles - 1) a.res->totalBytes = excl + tileBytes;
+      }
+    }
+
+    // block rows: 8 lanes per block, in chunks of 32 rows (4 blocks).  Warps 0..6 take the first chunks round-robin; the last
+    // (up to four) chunks are taken from a CTA-wide counter by whoever is free first, warp 7 included once its look-back is done.
+    const int rowEnd = bHi * 8;
+    const int nChunks = ((bHi - bLo) * 8 + 31) >> 5, nStatic = nChunks - min(4, nChunks);
+    for (int k = 0;; k++) {
+      int chunk = warp + 7 * k;
+      if (warp == 7 || chunk >= nStatic) {
+        chunk = 0;
+        if (lane == 0) chunk = smemTake(&sNextChunk);
+        chunk = nStatic + __shfl_sync(FULL, chunk, 0);
+        if (chunk >= nChunks) break;
+      }
+      const int g = bLo * 8 + chunk * 32 + lane;
+      if (g >= rowEnd) continue;
+      const int bb = g >> 3, r = g & 7;
+      const uint4 info = sInfo[bb];
+      const uint32_t byte0 = sOff[bb] - passBase;
+      const uint8_t* row = sIn + r * PITCH + bb * ROWB;
+      if (hotType && (info.y & TINFO_HOT)) {
+        const int nb = info.y & 31, osz = 4 >> ((info.y >> 5) & 3);
+        const uint4 A = *(const uint4*)row, B = *(const uint4*)(row + 16);
+        const double zMin = (double)__uint_as_float(info.x);
+        uint32_t q[8];
+        q[0] = quantizeOne((double)__uint_as_float(A.x), zMin, a.scale); q[1] = quantizeOne((double)__uint_as_float(A.y), zMin, a.scale);
+        q[2] = quantizeOne((double)__uint_as_float(A.z), zMin, a.scale); q[3] = quantizeOne((double)__uint_as_float(A.w), zMin, a.scale);
+        q[4] = quantizeOne((double)__uint_as_float(B.x), zMin, a.scale); q[5] = quantizeOne((double)__uint_as_float(B.y), zMin, a.scale);
+        q[6] = quantizeOne((double)__uint_as_float(B.z), zMin, a.scale); q[7] = quantizeOne((double)__uint_as_float(B.w), zMin, a.scale);
+        // 8 values of nb <= 16 bits -> 128 bits, value k at bit k * nb (BitStuffer2.cpp:432-472): pairs by multiply-add, then clamped funnel shifts
+        const uint32_t m = 1u << nb;
+        const uint32_t p0 = q[1] * m + q[0], p1 = q[3] * m + q[2], p2 = q[5] * m + q[4], p3 = q[7] * m + q[6];   // 2 nb <= 32 bits each
+        const int s2 = 2 * nb;
+        const uint32_t a0 = p0 | __funnelshift_lc(0u, p1, s2), a1 = __funnelshift_lc(p1, 0u, s2);        // values 0..3: 4 nb <= 64 bits
+        const uint32_t b0 = p2 | __funnelshift_lc(0u, p3, s2), b1 = __funnelshift_lc(p3, 0u, s2);        // values 4..7
+        uint32_t R0, R1, R2, R3;
+        if (nb > 8) { const int t = 4 * nb - 32; R0 = a0; R1 = a1 | __funnelshift_lc(0u, b0, t); R2 = __funnelshift_lc(b0, b1, t); R3 = __funnelshift_lc(b1, 0u, t); }
+        else { const int t = 4 * nb; R0 = a0 | __funnelshift_lc(0u, b0, t); R1 = __funnelshift_lc(b0, 0u, t); R2 = 0; R3 = 0; }
+        // the row's nb bytes start at a byte position: shift into place, OR the non-zero words into the image
+        const uint32_t dByte = byte0 + (uint32_t)(osz + 3) + (uint32_t)(r * nb);
+        const uint32_t sh = (dByte & 3) * 8;
+        uint32_t* wp = stage + (dByte >> 2);
+        smemOr(wp, R0 << sh);
+        smemOr(wp + 1, __funnelshift_l(R0, R1, sh));
+        smemOr(wp + 2, __funnelshift_l(R1, R2, sh));
+        smemOr(wp + 3, __funnelshift_l(R2, R3, sh));                // (zero words included: the image has a zero tail behind the pass's bytes)
+        const uint32_t x4 = __funnelshift_l(R3, 0u, sh);            // non-zero only for 15- and 16-bit values
+        if (x4) smemOr(wp + 4, x4);
+      } else {
+        const int w = min(8, a.nCols - (bx0 + bb) * 8);
+        const int mode = (info.y >> 7) & 3, nb = info.y & 31, tc = (info.y >> 5) & 3;
+        const int dtUsed = offsetTypeFromCode(PixelTraits<T>::code, tc);
+        const unsigned long long lb = (unsigned long long)info.x | ((unsigned long long)info.w << 32);
+        T lo; memcpy(&lo, &lb, sizeof(T));
+        fastGenericEmit<T>(a, stage, (const T*)row, h, w, r, (bx0 + bb) * 8, byte0, mode, nb, tc, dtUsed, (info.y & TINFO_CONST) ? 0u : 1u, (double)lo, lo);
       }
     }
     __syncthreads();                                               // staging image complete, tile offset known
@@ -406,6 +452,7 @@ __global__ void __launch_bounds__(256, MINB) k_encode_tile(FastEncArgs a) {
     if (bLo < nbk) {                                                 // another pass: clear the image
       __syncthreads();
       for (int i = tid; i < C::STAGE_BYTES / 16; i += 256) ((uint4*)stageRaw)[i] = make_uint4(0, 0, 0, 0);
+      if (tid == 0) sNextChunk = 0;
       __syncthreads();
     }
   }
