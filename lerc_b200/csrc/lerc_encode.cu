@@ -805,16 +805,20 @@ bool encodeBandFast(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
   fa.tileState = (unsigned long long*)(dState + sizeof(FastEncResult) + 9 * 8); fa.res = dRes;
   fa.groupState = fa.tileState + nTiles;                               // look-back level 2: aggregates per group of 32 tiles
   {
-    // one CTA per tile, tiles taken by ticket (no co-residency assumption); dynamic shared memory opt-in once per device
+    // persistent CTAs, tiles taken by ticket (no co-residency assumption); shared memory opt-in and occupancy once per device
     constexpr size_t smem = (size_t)EncTile<T>::SMEM;
-    static std::atomic<unsigned long long> attrDone{0};
-    const unsigned long long devBit = 1ull << (ctx->device & 63);
-    if (!(attrDone.load(std::memory_order_relaxed) & devBit)) {
-      if (!cudaOk(cudaFuncSetAttribute(k_encode_tile<T, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "encode tile smem")) return false;
-      attrDone.fetch_or(devBit, std::memory_order_relaxed);
+    static std::atomic<int> ctasPerSmOf[64];
+    const int dv = ctx->device & 63;
+    int ctasPerSm = ctasPerSmOf[dv].load(std::memory_order_relaxed);
+    if (!ctasPerSm) {
+      if (!cudaOk(cudaFuncSetAttribute(k_encode_tile<T, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "encode tile smem")) return false;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSm, k_encode_tile<T, 3>, ENC_THREADS, smem) != cudaSuccess || ctasPerSm < 1) ctasPerSm = 1;
+      ctasPerSmOf[dv].store(ctasPerSm, std::memory_order_relaxed);
     }
+    int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    const long long grid = std::min<long long>(nTiles, (long long)ctasPerSm * std::max(sms, 1));
     LaunchScope scope_(ctx, "k_encode_tile<T>");
-    k_encode_tile<T, 4><<<(unsigned)nTiles, 256, smem, ctx->stream>>>(fa); ctx->kernelLaunches++;
+    k_encode_tile<T, 3><<<(unsigned)grid, ENC_THREADS, smem, ctx->stream>>>(fa); ctx->kernelLaunches++;
   }
   ctx->joinSide();
   if (!cudaOk(cudaMemcpyAsync(hRes, dState, sizeof(HostRes), cudaMemcpyDeviceToHost, st), "D2H fast result")) { err = Failed; return true; }

@@ -1,27 +1,29 @@
 // lerc_encode_tile.cuh -- the single-pass Lerc2 band encoder of the headline path (included by lerc_encode.cu).
 // Raster shape: every pixel valid, nDepth == 1, 8x8 micro-blocks, 16/32/64-bit pixel types.
 //
-// One CTA codes one tile = 8 pixel rows x TW micro-blocks of one block row, taken by an atomic ticket in stream
-// order (Lerc2.cpp:1507-1521), so forward progress never depends on which CTAs are co-resident:
+// Persistent, warp-specialised CTAs (8 compute warps + 1 control warp, several CTAs per SM).  A CTA codes one tile after the
+// other; a tile = 8 pixel rows x TW micro-blocks of one block row, taken by an atomic ticket in stream order
+// (Lerc2.cpp:1507-1521), so forward progress never depends on which CTAs are co-resident.  Per tile k:
 //
-//   stage     the tile's rows are copied into shared memory by the copy engine: one cp.async.bulk (TMA, SASS
-//             UBLKCP) per pixel row, completion on an mbarrier (lerc_tma.cuh).  The row pitch is the row
-//             size + 16 bytes, which makes both access patterns below bank-conflict free.
+//   stage     the tile's rows are copied into shared memory by the copy engine: one cp.async.bulk (TMA, SASS UBLKCP) per
+//             pixel row, completion on an mbarrier (lerc_tma.cuh).  The copy of tile k+1 (whose ticket was requested at the
+//             top of tile k) is issued as soon as tile k is packed and runs under the flush.  The row pitch is the row size
+//             + 16 bytes, which makes both access patterns below bank-conflict free.
 //   size      two threads per micro-block: min / max / non-finite / equal-neighbour filter over its 64 pixels
 //             (GetValidDataAndStats, Lerc2.cpp:1717-1799), coding choice + byte length (NumBytesTile, Lerc2.h:416-453)
-//   scan      warp 0: exclusive scan of the block lengths; the tile's byte count is published for the look-back
-//   pack      one thread per block row: fp64 quantisation without contraction (Quantize, Lerc2.h:357-376),
-//             8 x numBits bits packed in registers, OR-ed into the staging image of the tile's output bytes
+//   scan      warp 0: exclusive scan of the block lengths; the tile's byte count is published for the other CTAs and
+//             posted to the control warp
+//   look-back control warp: decoupled look-back over the tiles' byte counts (two levels: predecessors inside the group of
+//             32 tiles, then aggregates of whole groups) gives the tile's byte offset in the stream.  Nobody waits for
+//             it: the offset of tile k is needed when tile k+1 has been packed.
+//   pack      one thread per block row: fp64 quantisation without contraction (Quantize, Lerc2.h:357-376), 8 x numBits
+//             bits packed in registers, OR-ed into one of two staging images of the tile's output bytes
 //             (WriteTile Lerc2.cpp:1949-2021, BitStuffer2::EncodeSimple BitStuffer2.cpp:35-75, :432-472)
-//   look-back warp 7, while the other warps pack: decoupled look-back over the tiles' byte counts (two levels:
-//             predecessors inside the group of 32 tiles, then aggregates of whole groups) gives the tile's byte
-//             offset in the stream; everything it waits for is published before the predecessors' packing
-//   flush     staging -> HBM in 16-byte chunks aligned to the GLOBAL address (the image is re-aligned with funnel
-//             shifts), Fletcher-32 partial sums of exactly those bytes with dp4a (Lerc2.cpp:1037-1064)
+//   flush     of tile k-1: staging -> HBM in 16-byte chunks aligned to the GLOBAL address (the image is re-aligned with
+//             funnel shifts), Fletcher-32 partial sums of exactly those bytes with dp4a (Lerc2.cpp:1037-1064)
 //
-// Several CTAs are resident per SM, so one CTA's barrier / look-back waits are filled by its neighbours' work.
-// Like its predecessor the kernel is speculative about the image-global decisions (Lerc2.cpp:179-381); the
-// facts it collects (min / max, NaN, all-integer, LUT candidates, overflow) let the caller verify them.
+// Like its predecessor the kernel is speculative about the image-global decisions (Lerc2.cpp:179-381); the facts it
+// collects (min / max, NaN, all-integer, LUT candidates, overflow) let the caller verify them.
 #pragma once
 #include "lerc_tma.cuh"
 
@@ -35,7 +37,7 @@ template <class T> struct EncTile {
   static constexpr int IN_BYTES = 8 * PITCH;
   static constexpr int STAGE_CAP = 17920;                         // output bytes coded per pass (128 blocks of 16-bit values: 17280)
   static constexpr int STAGE_BYTES = 16 + STAGE_CAP + 48;         // 16 zero bytes | image | zero tail
-  static constexpr int INFO_OFF = IN_BYTES + STAGE_BYTES;         // uint4 sInfo[TW]
+  static constexpr int INFO_OFF = IN_BYTES + 2 * STAGE_BYTES;     // two staging images (tiles alternate), then uint4 sInfo[TW]
   static constexpr int OFFS_OFF = INFO_OFF + TW * 16;             // uint32 sOff[TW + 1]
   static constexpr int SMEM = OFFS_OFF + (TW + 1) * 4 + 12;
 };
@@ -126,19 +128,11 @@ __device__ __forceinline__ void smemOr(uint32_t* p, uint32_t v) {
   atomicOr(p, v);
 #endif
 }
-// one thread takes the next value of a shared-memory counter (kept away from the compiler's warp-aggregated atomics)
-__device__ __forceinline__ int smemTake(int* p) {
-#ifndef LERC_CUSIM
-  int v;
-  asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(v) : "r"(smemAddr(p)) : "memory");
-  return v;
-#else
-  return atomicAdd(p, 1);
-#endif
-}
+
+constexpr int ENC_COMPUTE = 256, ENC_THREADS = ENC_COMPUTE + 32;    // 8 compute warps + the control warp
 
 template <class T, int MINB>
-__global__ void __launch_bounds__(256, MINB) k_encode_tile(FastEncArgs a) {
+__global__ void __launch_bounds__(ENC_THREADS, MINB) k_encode_tile(FastEncArgs a) {
   using K = typename PixelTraits<T>::Key;
   using C = EncTile<T>;
   constexpr bool isFlt = PixelTraits<T>::isFloat;
@@ -146,13 +140,11 @@ __global__ void __launch_bounds__(256, MINB) k_encode_tile(FastEncArgs a) {
   constexpr int TW = C::TW, PITCH = C::PITCH, ROWB = C::ROWB;
   extern __shared__ __align__(16) uint8_t tileSmem[];
   uint8_t* sIn = tileSmem;
-  uint32_t* stageRaw = (uint32_t*)(tileSmem + C::IN_BYTES);
-  uint32_t* stage = stageRaw + 4;                                 // pass-local byte 0 of the output image
   uint4* sInfo = (uint4*)(tileSmem + C::INFO_OFF);
   uint32_t* sOff = (uint32_t*)(tileSmem + C::OFFS_OFF);
-  __shared__ __align__(8) uint64_t sBar;
-  __shared__ int sTile, sNextChunk;
-  __shared__ unsigned long long sTileOff;
+  __shared__ __align__(8) uint64_t sBarFull, sBarScan[2], sBarOff[2];
+  __shared__ int sTileNext, sMailTile[2];
+  __shared__ unsigned long long sMailBytes[2], sOffS[2];
   __shared__ unsigned long long sKMin[8], sKMax[8], sFA[8], sFD[8];
   __shared__ unsigned int sFlg[8];
 
@@ -164,159 +156,35 @@ __global__ void __launch_bounds__(256, MINB) k_encode_tile(FastEncArgs a) {
   constexpr unsigned long long ST_A = 1ull << 62, ST_P = 2ull << 62, VAL = (1ull << 62) - 1;
   volatile unsigned long long* st = a.tileState;
 
-  // ---- ticket, copy engine
+  // the copy engine brings tile t into sIn (thread 0 of the compute warps)
+  auto issueLoad = [&](int t) {
+    const int tyT = t / tpr, seg = t - tyT * tpr;
+    const int h = min(8, a.nRows - tyT * 8), cols = min(TW * 8, a.nCols - seg * TW * 8);
+    const uint32_t rowBytes = (uint32_t)cols * (uint32_t)sizeof(T);
+    mbarExpectTx(&sBarFull, rowBytes * (uint32_t)h);
+    const T* src = data + (size_t)(tyT * 8) * a.nCols + (size_t)seg * TW * 8;
+    for (int y = 0; y < h; y++) bulkLoad(sIn + y * PITCH, src + (size_t)y * a.nCols, rowBytes, &sBarFull);
+    mbarSimCopiesDone(&sBarFull);
+  };
+
   if (tid == 0) {
+    mbarInit(&sBarFull, 1); mbarInit(&sBarScan[0], 1); mbarInit(&sBarScan[1], 1); mbarInit(&sBarOff[0], 1); mbarInit(&sBarOff[1], 1);
     const int t = (int)atomicAdd(&a.res->ticket, 1u);
-    sTile = t; sNextChunk = 0;
-    if (vecOk) {
-      const int tyT = t / tpr, seg = t - tyT * tpr;
-      const int h = min(8, a.nRows - tyT * 8), cols = min(TW * 8, a.nCols - seg * TW * 8);
-      const uint32_t rowBytes = (uint32_t)cols * (uint32_t)sizeof(T);
-      mbarInit(&sBar, 1);
-      mbarExpectTx(&sBar, rowBytes * (uint32_t)h);
-      const T* src = data + (size_t)(tyT * 8) * a.nCols + (size_t)seg * TW * 8;
-      for (int y = 0; y < h; y++) bulkLoad(sIn + y * PITCH, src + (size_t)y * a.nCols, rowBytes, &sBar);
-    }
+    sTileNext = t;
+    if (vecOk && t < nTiles) issueLoad(t);
   }
-  for (int i = tid; i < C::STAGE_BYTES / 16; i += 256) ((uint4*)stageRaw)[i] = make_uint4(0, 0, 0, 0);
-  const unsigned int flagsSeen = *(volatile unsigned int*)&a.res->flags;
-  const unsigned long long negMinSeen = *(volatile unsigned long long*)&a.res->negMinKey, maxSeen = *(volatile unsigned long long*)&a.res->maxKey;
-  __syncthreads();
-  const int tile = sTile;
-  const int tyT = tile / tpr, seg = tile - tyT * tpr;
-  const int bx0 = seg * TW;                                        // first block column of the tile
-  const int nbk = min(TW, a.nTx - bx0);                            // blocks in the tile
-  const int h = min(8, a.nRows - tyT * 8);
-  if (vecOk) mbarWait(&sBar, 0);
-  else {
-    const int cols = min(TW * 8, a.nCols - bx0 * 8);
-    const T* src = data + (size_t)(tyT * 8) * a.nCols + (size_t)bx0 * 8;
-    for (int y = 0; y < h; y++)
-      for (int x = tid; x < cols; x += 256) ((T*)(sIn + y * PITCH))[x] = src[(size_t)y * a.nCols + x];
-    __syncthreads();
-  }
-
-  // running image-global facts and checksum partials of this thread
-  K gMin = keyMaxValue<K>(), gMax = 0;
-  unsigned int myFlags = 0;
-  unsigned long long fa = 0, fd = 0;
-
-  // ---- size: two threads per block (rows 0-3 / 4-7)
-  for (int bb = tid >> 1; bb < TW; bb += 128) {
-    const int hf = tid & 1;
-    const bool act = bb < nbk;
-    const int w = act ? min(8, a.nCols - (bx0 + bb) * 8) : 0;
-    const bool full = act && h == 8 && w == 8;
-    bool hot = false;
-    uint4 info = make_uint4(0, 0, 0, 0);
-    uint32_t len = 0;
-    if (hotType) {
-      // hot path test for full 8x8 float blocks coded "bit-stuffed, <= 16 bits, offset as float/short/byte".  The thread with hf == 1
-      // reads the two halves of a row in swapped order (bank-conflict free); min / max / the filters do not care about the order.
-      const uint8_t* base = sIn + (hf * 4) * PITCH + bb * ROWB;
-      float mn = __int_as_float(0x7f800000), mx = __int_as_float(0xff800000), t0 = 0.f;   // t0: NaN iff some value is NaN or +-Inf
-      bool eq = false, ni = (flagsSeen & FASTF_NOT_INT) != 0;
-#pragma unroll
-      for (int i = 0; i < 4; i++) {
-        const uint4 A = *(const uint4*)(base + i * PITCH + hf * 16), B = *(const uint4*)(base + i * PITCH + 16 - hf * 16);
-        const float a0 = __uint_as_float(A.x), a1 = __uint_as_float(A.y), a2 = __uint_as_float(A.z), a3 = __uint_as_float(A.w);
-        const float b0 = __uint_as_float(B.x), b1 = __uint_as_float(B.y), b2 = __uint_as_float(B.z), b3 = __uint_as_float(B.w);
-        mn = fminf(fminf(fminf(mn, a0), fminf(a1, a2)), fminf(fminf(a3, b0), fminf(fminf(b1, b2), b3)));
-        mx = fmaxf(fmaxf(fmaxf(mx, a0), fmaxf(a1, a2)), fmaxf(fmaxf(a3, b0), fmaxf(fmaxf(b1, b2), b3)));
-        t0 = __fmaf_rn(a0, 0.f, t0); t0 = __fmaf_rn(a1, 0.f, t0); t0 = __fmaf_rn(a2, 0.f, t0); t0 = __fmaf_rn(a3, 0.f, t0);
-        t0 = __fmaf_rn(b0, 0.f, t0); t0 = __fmaf_rn(b1, 0.f, t0); t0 = __fmaf_rn(b2, 0.f, t0); t0 = __fmaf_rn(b3, 0.f, t0);
-        // equal neighbours inside a 16-byte group: 48 of the block's 64 (value, predecessor) pairs.  No such pair => at most 16 equal
-        // pairs => never a LUT candidate (needs more than 32, Lerc2.cpp:1794); otherwise the exact count is taken below.
-        eq |= (a0 == a1) | (a1 == a2) | (a2 == a3) | (b0 == b1) | (b1 == b2) | (b2 == b3);
-        if (!ni) {                                                  // all-integer test (Lerc.h:248): exact per thread, cheap once a fraction was seen
-          ni = a0 != truncf(a0);
-          if (!ni) ni = (a1 != truncf(a1)) | (a2 != truncf(a2)) | (a3 != truncf(a3)) | (b0 != truncf(b0)) | (b1 != truncf(b1)) | (b2 != truncf(b2)) | (b3 != truncf(b3));
-        }
-      }
-      mn = fminf(mn, __shfl_xor_sync(FULL, mn, 1)); mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, 1));
-      unsigned pk = (t0 != t0 ? 1u : 0u) | (eq ? 2u : 0u);
-      pk |= __shfl_xor_sync(FULL, pk, 1);
-      const double zMn = (double)mn, zMx = (double)mx;
-      const double mv = __dmul_rn(__dsub_rn(zMx, zMn), a.scale);
-      const uint32_t me = roundToUInt(mv);
-      const int nbh = bitLength(me);
-      const bool lutMaybe = (pk & 2) && (zMx > __dadd_rn(zMn, a.maxZErr3));
-      hot = full && !(pk & 1) && !(mv > (double)a.maxQ) && me > 0 && nbh <= 16 && !lutMaybe && !(mn == 0.f && mx == 0.f);
-      if (hot) {
-        // offset in the smallest type that holds it (Lerc2.h:457-542, float row)
-        const bool isInt = mn == truncf(mn);
-        const int tc = (isInt && mn >= 0.f && mn <= 255.f) ? 2 : ((isInt && mn >= -32768.f && mn <= 32767.f) ? 1 : 0);
-        len = (uint32_t)(3 + (4 >> tc) + 8 * nbh);
-        info.x = __float_as_uint(mn); info.y = (uint32_t)(nbh | (tc << 5) | (BEM_SIMPLE << 7) | TINFO_HOT);
-        const uint32_t kmn = toKey(mn), kmx = toKey(mx);
-        gMin = kmn < gMin ? (K)kmn : gMin; gMax = kmx > gMax ? (K)kmx : gMax;
-        if (ni) myFlags |= FASTF_NOT_INT;
-      }
-    }
-    if (!hot && act && hf == 0) {
-      unsigned int fl = 0; K kmin, kmax;
-      tileGenericChoice<T>(a, sIn + bb * ROWB, PITCH, h, w, info, len, fl, kmin, kmax);
-      myFlags |= fl;
-      gMin = kmin < gMin ? kmin : gMin; gMax = kmax > gMax ? kmax : gMax;
-    }
-    if (hf == 0) { sInfo[bb] = info; sOff[bb] = len; }
-  }
+  for (int i = tid; i < 2 * C::STAGE_BYTES / 16; i += ENC_THREADS) ((uint4*)(tileSmem + C::IN_BYTES))[i] = make_uint4(0, 0, 0, 0);
   __syncthreads();
 
-  // ---- scan (warp 0): block lengths -> exclusive byte offsets inside the tile, sOff[TW] = the tile's bytes
-  if (warp == 0) {
-    constexpr int PER = TW / 32;
-    uint32_t v[PER], sum = 0;
-#pragma unroll
-    for (int k = 0; k < PER; k++) { v[k] = sOff[lane * PER + k]; sum += v[k]; }
-    uint32_t inc = sum;
-#pragma unroll
-    for (int s = 1; s < 32; s <<= 1) { const uint32_t o = __shfl_up_sync(FULL, inc, s); if (lane >= s) inc += o; }
-    uint32_t run = inc - sum;
-#pragma unroll
-    for (int k = 0; k < PER; k++) { sOff[lane * PER + k] = run; run += v[k]; }
-    if (lane == 31) { sOff[TW] = inc; st[tile] = (tile == 0 ? ST_P : ST_A) | (unsigned long long)inc; }   // publish before packing
-  }
-  __syncthreads();
-  const uint32_t tileBytes = sOff[TW];
-
-  // ---- pack + flush, in passes of at most STAGE_CAP output bytes (one pass unless the blocks are wider than 16 bits per value)
-  const unsigned par = (unsigned)((a.regionOff + (long long)(uintptr_t)a.stream) & 1);    // parity of the region offset of every 16-byte aligned output byte
-  bool overflow = false, haveOff = false;
-  unsigned long long tileOff = 0;
-  int bLo = 0;
-  uint32_t passBase = 0;
-  while (bLo < nbk) {
-    int bHi = nbk;
-    if (tileBytes - passBase > (uint32_t)C::STAGE_CAP) {           // largest bHi with sOff[bHi] - passBase <= STAGE_CAP (a block is at most 513 bytes)
-      int lo = bLo + 1, hi = nbk;
-      while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (sOff[mid] - passBase <= (uint32_t)C::STAGE_CAP) lo = mid; else hi = mid - 1; }
-      bHi = lo;
-    }
-    const uint32_t passBytes = (bHi == nbk ? tileBytes : sOff[bHi]) - passBase;
-
-    // headers of the hot blocks: flag | offset | numBits byte | count (WriteTile, Lerc2.cpp:1949-2021; BitStuffer2.cpp:35-75)
-    for (int b = bLo + tid; b < bHi; b += 256) {
-      const uint4 info = sInfo[b];
-      if (info.y & TINFO_HOT) {
-        const int nb = info.y & 31, tc = (info.y >> 5) & 3, osz = 4 >> tc;
-        const int j0 = (bx0 + b) * 8;
-        const uint32_t flag = (uint32_t)((((j0 >> 3) & 15) << 2) & 0x38);
-        const float lof = __uint_as_float(info.x);
-        const unsigned long long ob = tc == 0 ? (unsigned long long)info.x : (tc == 1 ? (unsigned long long)(uint16_t)(int16_t)lof : (unsigned long long)(uint8_t)lof);
-        unsigned long long hd = (unsigned long long)(flag | 1 | (tc << 6)) | (ob << 8);
-        hd |= ((unsigned long long)(nb | (2 << 6)) | (64ull << 8)) << (8 * (1 + osz));
-        const uint32_t H[2] = {(uint32_t)hd, (uint32_t)(hd >> 32)};
-        orBits<2>(stage, (sOff[b] - passBase) * 8, H, (3 + osz) * 8);
-      }
-    }
-    // ---- decoupled look-back (warp 7, once per tile, right after the tile's byte count was published) for the tile's byte offset
-    // in the stream.  Everything it waits for is published by the predecessors BEFORE their packing: a tile's own byte count
-    // after its scan, a group's aggregate by the warp 7 of the group's last tile in its round 1.  The other warps pack meanwhile;
-    // warp 7 joins them when it is done (block rows are handed out in chunks of 32).
-    if (!haveOff && warp == 7) {
+  // ================= control warp: look-back of every tile the compute warps post =================
+  if (warp == ENC_COMPUTE / 32) {
+    volatile unsigned long long* gs = a.groupState;
+    for (int k = 0;; k++) {
+      mbarWait(&sBarScan[k & 1], (uint32_t)(k >> 1) & 1u);
+      const int tile = sMailTile[k & 1];
+      if (tile < 0) break;
+      const unsigned long long tileBytes = sMailBytes[k & 1];
       unsigned long long excl = 0;
-      volatile unsigned long long* gs = a.groupState;
       const int l = tile & 31;
       const long long g = tile >> 5;
       bool needGroups = g > 0;
@@ -324,7 +192,7 @@ __global__ void __launch_bounds__(256, MINB) k_encode_tile(FastEncArgs a) {
         const long long idx = (long long)tile - 1 - lane;
         const bool in = lane < l;
         unsigned long long s = 0;
-        if (in) { do { s = st[idx]; } while ((s >> 62) == 0); }
+        if (in) { while (((s = st[idx]) >> 62) == 0) __nanosleep(40); }
         const unsigned isP = __ballot_sync(FULL, in && (s >> 62) == 2);
         const int firstP = isP ? __ffs(isP) - 1 : 32;
         unsigned long long contrib = (in && lane <= firstP) ? (s & VAL) : 0;
@@ -339,7 +207,7 @@ __global__ void __launch_bounds__(256, MINB) k_encode_tile(FastEncArgs a) {
         for (;;) {
           const long long idx = base - lane;
           unsigned long long s = ST_P;                                  // virtual groups before 0: prefix 0
-          if (idx >= 0) { do { s = gs[idx]; } while ((s >> 62) == 0); }
+          if (idx >= 0) { while (((s = gs[idx]) >> 62) == 0) __nanosleep(40); }
           const unsigned isP = __ballot_sync(FULL, (s >> 62) == 2);
           const int firstP = isP ? __ffs(isP) - 1 : 32;
           unsigned long long contrib = (lane <= firstP && idx >= 0) ? (s & VAL) : 0;
@@ -353,25 +221,75 @@ __global__ void __launch_bounds__(256, MINB) k_encode_tile(FastEncArgs a) {
       if (lane == 0) {
         if (tile > 0) st[tile] = ST_P | (excl + tileBytes);
         if (l == 31) gs[g] = ST_P | (excl + tileBytes);                 // inclusive prefix of the whole group
-        sTileOff = excl;
         if (tile == nTiles - 1) a.res->totalBytes = excl + tileBytes;
+        sOffS[k & 1] = excl;
+        mbarArrive(&sBarOff[k & 1]);
+      }
+      __syncwarp();
+    }
+    return;
+  }
+
+  // ================= compute warps =================
+  const unsigned int flagsSeen = *(volatile unsigned int*)&a.res->flags;
+  const unsigned long long negMinSeen = *(volatile unsigned long long*)&a.res->negMinKey, maxSeen = *(volatile unsigned long long*)&a.res->maxKey;
+  const unsigned par = (unsigned)((a.regionOff + (long long)(uintptr_t)a.stream) & 1);    // parity of the region offset of every 16-byte aligned output byte
+  // running image-global facts and checksum partials of this thread
+  K gMin = keyMaxValue<K>(), gMax = 0;
+  unsigned int myFlags = 0;
+  unsigned long long fa = 0, fd = 0;
+  bool overflow = false;
+
+  // staging image -> HBM: passBytes bytes that start at stream offset passOff
+  auto flushPass = [&](const uint32_t* stage, unsigned long long passOff, uint32_t passBytes) {
+    uint8_t* gPass = a.stream + passOff;
+    const bool fits = passOff + passBytes <= a.streamCap;
+    if (!fits) overflow = true;
+    const int pad = (int)((uintptr_t)gPass & 15);
+    const int nChunks = (pad + (int)passBytes + 15) >> 4;
+    const int bs8 = ((-pad) & 3) * 8;
+    for (int cI = tid; cI < nChunks; cI += ENC_COMPUTE) {
+      const int s0 = cI * 16 - pad;                                     // pass-local byte of the chunk's first byte (>= -15)
+      const int wi = s0 >> 2;                                           // floor
+      uint32_t x[5];
+#pragma unroll
+      for (int k = 0; k < 5; k++) x[k] = stage[wi + k];
+      uint32_t o[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) o[k] = __funnelshift_r(x[k], x[k + 1], bs8);
+      if (fits) {
+        if (s0 >= 0 && s0 + 16 <= (int)passBytes) *(uint4*)(gPass + s0) = make_uint4(o[0], o[1], o[2], o[3]);
+        else {
+#pragma unroll
+          for (int j = 0; j < 16; j++) if (s0 + j >= 0 && s0 + j < (int)passBytes) gPass[s0 + j] = (uint8_t)(o[j >> 2] >> (8 * (j & 3)));
+        }
+      }
+      const long long r0 = a.regionOff + (long long)passOff + s0;       // region offset of the chunk's first byte; r0 & 1 == par
+      const uint32_t w0 = (uint32_t)((unsigned long long)(r0 - par) >> 1) % 65535u;   // word index of the chunk's first word (mod 65535)
+      uint32_t S, S1;
+      if (par) fletcherChunk<1>(o, S, S1); else fletcherChunk<0>(o, S, S1);
+      fa += S; fd += (unsigned long long)w0 * S + S1;
+    }
+  };
+  // headers + rows of blocks [bLo, bHi) into `stage` (pass-local byte 0 = tile byte passBase)
+  auto packBlocks = [&](uint32_t* stage, int bx0, int h, int bLo, int bHi, uint32_t passBase) {
+    // headers of the hot blocks: flag | offset | numBits byte | count (WriteTile, Lerc2.cpp:1949-2021; BitStuffer2.cpp:35-75)
+    for (int b = bLo + tid; b < bHi; b += ENC_COMPUTE) {
+      const uint4 info = sInfo[b];
+      if (info.y & TINFO_HOT) {
+        const int nb = info.y & 31, tc = (info.y >> 5) & 3, osz = 4 >> tc;
+        const int j0 = (bx0 + b) * 8;
+        const uint32_t flag = (uint32_t)((((j0 >> 3) & 15) << 2) & 0x38);
+        const float lof = __uint_as_float(info.x);
+        const unsigned long long ob = tc == 0 ? (unsigned long long)info.x : (tc == 1 ? (unsigned long long)(uint16_t)(int16_t)lof : (unsigned long long)(uint8_t)lof);
+        unsigned long long hd = (unsigned long long)(flag | 1 | (tc << 6)) | (ob << 8);
+        hd |= ((unsigned long long)(nb | (2 << 6)) | (64ull << 8)) << (8 * (1 + osz));
+        const uint32_t H[2] = {(uint32_t)hd, (uint32_t)(hd >> 32)};
+        orBits<2>(stage, (sOff[b] - passBase) * 8, H, (3 + osz) * 8);
       }
     }
-
-    // block rows: 8 lanes per block, in chunks of 32 rows (4 blocks).  Warps 0..6 take the first chunks round-robin; the last
-    // (up to four) chunks are taken from a CTA-wide counter by whoever is free first, warp 7 included once its look-back is done.
-    const int rowEnd = bHi * 8;
-    const int nChunks = ((bHi - bLo) * 8 + 31) >> 5, nStatic = nChunks - min(4, nChunks);
-    for (int k = 0;; k++) {
-      int chunk = warp + 7 * k;
-      if (warp == 7 || chunk >= nStatic) {
-        chunk = 0;
-        if (lane == 0) chunk = smemTake(&sNextChunk);
-        chunk = nStatic + __shfl_sync(FULL, chunk, 0);
-        if (chunk >= nChunks) break;
-      }
-      const int g = bLo * 8 + chunk * 32 + lane;
-      if (g >= rowEnd) continue;
+    // block rows: 8 lanes per block
+    for (int g = bLo * 8 + tid; g < bHi * 8; g += ENC_COMPUTE) {
       const int bb = g >> 3, r = g & 7;
       const uint4 info = sInfo[bb];
       const uint32_t byte0 = sOff[bb] - passBase;
@@ -394,7 +312,7 @@ __global__ void __launch_bounds__(256, MINB) k_encode_tile(FastEncArgs a) {
         uint32_t R0, R1, R2, R3;
         if (nb > 8) { const int t = 4 * nb - 32; R0 = a0; R1 = a1 | __funnelshift_lc(0u, b0, t); R2 = __funnelshift_lc(b0, b1, t); R3 = __funnelshift_lc(b1, 0u, t); }
         else { const int t = 4 * nb; R0 = a0 | __funnelshift_lc(0u, b0, t); R1 = __funnelshift_lc(b0, 0u, t); R2 = 0; R3 = 0; }
-        // the row's nb bytes start at a byte position: shift into place, OR the non-zero words into the image
+        // the row's nb bytes start at a byte position: shift into place, OR the words into the image
         const uint32_t dByte = byte0 + (uint32_t)(osz + 3) + (uint32_t)(r * nb);
         const uint32_t sh = (dByte & 3) * 8;
         uint32_t* wp = stage + (dByte >> 2);
@@ -413,49 +331,172 @@ __global__ void __launch_bounds__(256, MINB) k_encode_tile(FastEncArgs a) {
         fastGenericEmit<T>(a, stage, (const T*)row, h, w, r, (bx0 + bb) * 8, byte0, mode, nb, tc, dtUsed, (info.y & TINFO_CONST) ? 0u : 1u, (double)lo, lo);
       }
     }
-    __syncthreads();                                               // staging image complete, tile offset known
-    if (!haveOff) { tileOff = sTileOff; haveOff = true; }
+  };
 
-    // ---- staging -> HBM, Fletcher-32 partial sums of the same 16-byte chunks (bytes outside the pass are zero in the image)
-    {
-      const unsigned long long passOff = tileOff + passBase;         // offset of the pass's first byte in the block stream
-      uint8_t* gPass = a.stream + passOff;
-      const bool fits = passOff + passBytes <= a.streamCap;
-      if (!fits) overflow = true;
-      const int pad = (int)((uintptr_t)gPass & 15);
-      const int nChunks = (pad + (int)passBytes + 15) >> 4;
-      const int bs8 = ((-pad) & 3) * 8;
-      for (int cI = tid; cI < nChunks; cI += 256) {
-        const int s0 = cI * 16 - pad;                                     // pass-local byte of the chunk's first byte (>= -15)
-        const int wi = s0 >> 2;                                           // floor
-        uint32_t x[5];
+  int pendK = -1; uint32_t pendBytes = 0;                          // the tile whose staging image still waits for its offset
+  int tile = sTileNext;
+  int k = 0;                                                        // tiles this CTA has posted to its control warp
+  for (; tile < nTiles; k++) {
+    int nextT = 0;
+    if (tid == 0) nextT = (int)atomicAdd(&a.res->ticket, 1u);      // ticket of tile k + 1: in flight until the tile is packed
+    const int tyT = tile / tpr, seg = tile - tyT * tpr;
+    const int bx0 = seg * TW;                                      // first block column of the tile
+    const int nbk = min(TW, a.nTx - bx0);                          // blocks in the tile
+    const int h = min(8, a.nRows - tyT * 8);
+    uint32_t* stage = (uint32_t*)(tileSmem + C::IN_BYTES + (k & 1) * C::STAGE_BYTES) + 4;   // pass-local byte 0 of this tile's output image
+    if (vecOk) mbarWait(&sBarFull, (uint32_t)k & 1u);
+    else {
+      const int cols = min(TW * 8, a.nCols - bx0 * 8);
+      const T* src = data + (size_t)(tyT * 8) * a.nCols + (size_t)bx0 * 8;
+      for (int y = 0; y < h; y++)
+        for (int x = tid; x < cols; x += ENC_COMPUTE) ((T*)(sIn + y * PITCH))[x] = src[(size_t)y * a.nCols + x];
+      namedBarSync(1, ENC_COMPUTE);
+    }
+
+    // ---- size: two threads per block (rows 0-3 / 4-7)
+    for (int bb = tid >> 1; bb < TW; bb += ENC_COMPUTE / 2) {
+      const int hf = tid & 1;
+      const bool act = bb < nbk;
+      const int w = act ? min(8, a.nCols - (bx0 + bb) * 8) : 0;
+      const bool full = act && h == 8 && w == 8;
+      bool hot = false;
+      uint4 info = make_uint4(0, 0, 0, 0);
+      uint32_t len = 0;
+      if (hotType) {
+        // hot path test for full 8x8 float blocks coded "bit-stuffed, <= 16 bits, offset as float/short/byte".  The thread with hf == 1
+        // reads the two halves of a row in swapped order (bank-conflict free); min / max / the filters do not care about the order.
+        const uint8_t* base = sIn + (hf * 4) * PITCH + bb * ROWB;
+        float mn = __int_as_float(0x7f800000), mx = __int_as_float(0xff800000), t0 = 0.f;   // t0: NaN iff some value is NaN or +-Inf
+        bool eq = false, ni = ((flagsSeen | myFlags) & FASTF_NOT_INT) != 0;
 #pragma unroll
-        for (int k = 0; k < 5; k++) x[k] = stage[wi + k];
-        uint32_t o[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) o[k] = __funnelshift_r(x[k], x[k + 1], bs8);
-        if (fits) {
-          if (s0 >= 0 && s0 + 16 <= (int)passBytes) *(uint4*)(gPass + s0) = make_uint4(o[0], o[1], o[2], o[3]);
-          else {
-#pragma unroll
-            for (int j = 0; j < 16; j++) if (s0 + j >= 0 && s0 + j < (int)passBytes) gPass[s0 + j] = (uint8_t)(o[j >> 2] >> (8 * (j & 3)));
+        for (int i = 0; i < 4; i++) {
+          const uint4 A = *(const uint4*)(base + i * PITCH + hf * 16), B = *(const uint4*)(base + i * PITCH + 16 - hf * 16);
+          const float a0 = __uint_as_float(A.x), a1 = __uint_as_float(A.y), a2 = __uint_as_float(A.z), a3 = __uint_as_float(A.w);
+          const float b0 = __uint_as_float(B.x), b1 = __uint_as_float(B.y), b2 = __uint_as_float(B.z), b3 = __uint_as_float(B.w);
+          mn = fminf(fminf(fminf(mn, a0), fminf(a1, a2)), fminf(fminf(a3, b0), fminf(fminf(b1, b2), b3)));
+          mx = fmaxf(fmaxf(fmaxf(mx, a0), fmaxf(a1, a2)), fmaxf(fmaxf(a3, b0), fmaxf(fmaxf(b1, b2), b3)));
+          t0 = __fmaf_rn(a0, 0.f, t0); t0 = __fmaf_rn(a1, 0.f, t0); t0 = __fmaf_rn(a2, 0.f, t0); t0 = __fmaf_rn(a3, 0.f, t0);
+          t0 = __fmaf_rn(b0, 0.f, t0); t0 = __fmaf_rn(b1, 0.f, t0); t0 = __fmaf_rn(b2, 0.f, t0); t0 = __fmaf_rn(b3, 0.f, t0);
+          // equal neighbours inside a 16-byte group: 48 of the block's 64 (value, predecessor) pairs.  No such pair => at most 16 equal
+          // pairs => never a LUT candidate (needs more than 32, Lerc2.cpp:1794); otherwise the exact count is taken below.
+          eq |= (a0 == a1) | (a1 == a2) | (a2 == a3) | (b0 == b1) | (b1 == b2) | (b2 == b3);
+          if (!ni) {                                                  // all-integer test (Lerc.h:248): exact per thread, cheap once a fraction was seen
+            ni = a0 != truncf(a0);
+            if (!ni) ni = (a1 != truncf(a1)) | (a2 != truncf(a2)) | (a3 != truncf(a3)) | (b0 != truncf(b0)) | (b1 != truncf(b1)) | (b2 != truncf(b2)) | (b3 != truncf(b3));
           }
         }
-        const long long r0 = a.regionOff + (long long)passOff + s0;       // region offset of the chunk's first byte; r0 & 1 == par
-        const uint32_t w0 = (uint32_t)((unsigned long long)(r0 - par) >> 1) % 65535u;   // word index of the chunk's first word (mod 65535)
-        uint32_t S, S1;
-        if (par) fletcherChunk<1>(o, S, S1); else fletcherChunk<0>(o, S, S1);
-        fa += S; fd += (unsigned long long)w0 * S + S1;
+        mn = fminf(mn, __shfl_xor_sync(FULL, mn, 1)); mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, 1));
+        unsigned pk = (t0 != t0 ? 1u : 0u) | (eq ? 2u : 0u);
+        pk |= __shfl_xor_sync(FULL, pk, 1);
+        const double zMn = (double)mn, zMx = (double)mx;
+        const double mv = __dmul_rn(__dsub_rn(zMx, zMn), a.scale);
+        const uint32_t me = roundToUInt(mv);
+        const int nbh = bitLength(me);
+        const bool lutMaybe = (pk & 2) && (zMx > __dadd_rn(zMn, a.maxZErr3));
+        hot = full && !(pk & 1) && !(mv > (double)a.maxQ) && me > 0 && nbh <= 16 && !lutMaybe && !(mn == 0.f && mx == 0.f);
+        if (hot) {
+          // offset in the smallest type that holds it (Lerc2.h:457-542, float row)
+          const bool isInt = mn == truncf(mn);
+          const int tc = (isInt && mn >= 0.f && mn <= 255.f) ? 2 : ((isInt && mn >= -32768.f && mn <= 32767.f) ? 1 : 0);
+          len = (uint32_t)(3 + (4 >> tc) + 8 * nbh);
+          info.x = __float_as_uint(mn); info.y = (uint32_t)(nbh | (tc << 5) | (BEM_SIMPLE << 7) | TINFO_HOT);
+          const uint32_t kmn = toKey(mn), kmx = toKey(mx);
+          gMin = kmn < gMin ? (K)kmn : gMin; gMax = kmx > gMax ? (K)kmx : gMax;
+          if (ni) myFlags |= FASTF_NOT_INT;
+        }
+      }
+      if (!hot && act && hf == 0) {
+        unsigned int fl = 0; K kmin, kmax;
+        tileGenericChoice<T>(a, sIn + bb * ROWB, PITCH, h, w, info, len, fl, kmin, kmax);
+        myFlags |= fl;
+        gMin = kmin < gMin ? kmin : gMin; gMax = kmax > gMax ? kmax : gMax;
+      }
+      if (hf == 0) { sInfo[bb] = info; sOff[bb] = len; }
+    }
+    namedBarSync(1, ENC_COMPUTE);
+
+    // ---- scan (warp 0): block lengths -> exclusive byte offsets inside the tile, sOff[TW] = the tile's bytes; publish; post
+    if (warp == 0) {
+      constexpr int PER = TW / 32;
+      uint32_t v[PER], sum = 0;
+#pragma unroll
+      for (int j = 0; j < PER; j++) { v[j] = sOff[lane * PER + j]; sum += v[j]; }
+      uint32_t inc = sum;
+#pragma unroll
+      for (int s = 1; s < 32; s <<= 1) { const uint32_t o = __shfl_up_sync(FULL, inc, s); if (lane >= s) inc += o; }
+      uint32_t run = inc - sum;
+#pragma unroll
+      for (int j = 0; j < PER; j++) { sOff[lane * PER + j] = run; run += v[j]; }
+      if (lane == 31) {
+        sOff[TW] = inc;
+        st[tile] = (tile == 0 ? ST_P : ST_A) | (unsigned long long)inc;        // for the other CTAs' look-backs
+        sMailTile[k & 1] = tile; sMailBytes[k & 1] = inc;
+        mbarArrive(&sBarScan[k & 1]);                                          // for this CTA's control warp
       }
     }
-    bLo = bHi; passBase += passBytes;
-    if (bLo < nbk) {                                                 // another pass: clear the image
-      __syncthreads();
-      for (int i = tid; i < C::STAGE_BYTES / 16; i += 256) ((uint4*)stageRaw)[i] = make_uint4(0, 0, 0, 0);
-      if (tid == 0) sNextChunk = 0;
-      __syncthreads();
+    namedBarSync(1, ENC_COMPUTE);
+    const uint32_t tileBytes = sOff[TW];
+
+    if (tileBytes <= (uint32_t)C::STAGE_CAP) {
+      // ---- the common case: one pass into this tile's staging image; it is flushed when the next tile has been packed
+      packBlocks(stage, bx0, h, 0, nbk, 0u);
+      if (tid == 0) sTileNext = nextT;
+      namedBarSync(1, ENC_COMPUTE);                                  // image complete, sIn free
+      const int tn = sTileNext;
+      if (tid == 0 && vecOk && tn < nTiles) issueLoad(tn);
+      if (pendK >= 0) {
+        mbarWait(&sBarOff[pendK & 1], (uint32_t)(pendK >> 1) & 1u);
+        uint32_t* pst = (uint32_t*)(tileSmem + C::IN_BYTES + (pendK & 1) * C::STAGE_BYTES);
+        flushPass(pst + 4, sOffS[pendK & 1], pendBytes);
+        namedBarSync(1, ENC_COMPUTE);
+        for (int i = tid; i < (int)((pendBytes + 16 + 48 + 15) >> 4) && i < C::STAGE_BYTES / 16; i += ENC_COMPUTE) ((uint4*)pst)[i] = make_uint4(0, 0, 0, 0);
+      }
+      pendK = k; pendBytes = tileBytes;
+      tile = tn;
+    } else {
+      // ---- more than STAGE_CAP bytes (values wider than 16 bits, raw blocks): passes of at most STAGE_CAP bytes, each flushed at
+      // once; the tile's offset is waited for here
+      if (pendK >= 0) {                                              // first the waiting tile: its image is the other one
+        mbarWait(&sBarOff[pendK & 1], (uint32_t)(pendK >> 1) & 1u);
+        uint32_t* pst = (uint32_t*)(tileSmem + C::IN_BYTES + (pendK & 1) * C::STAGE_BYTES);
+        flushPass(pst + 4, sOffS[pendK & 1], pendBytes);
+        namedBarSync(1, ENC_COMPUTE);
+        for (int i = tid; i < C::STAGE_BYTES / 16; i += ENC_COMPUTE) ((uint4*)pst)[i] = make_uint4(0, 0, 0, 0);
+        pendK = -1;
+      }
+      mbarWait(&sBarOff[k & 1], (uint32_t)(k >> 1) & 1u);
+      const unsigned long long tileOff = sOffS[k & 1];
+      int bLo = 0;
+      uint32_t passBase = 0;
+      while (bLo < nbk) {
+        int bHi = nbk;
+        if (tileBytes - passBase > (uint32_t)C::STAGE_CAP) {           // largest bHi with sOff[bHi] - passBase <= STAGE_CAP (a block is at most 513 bytes)
+          int lo = bLo + 1, hi = nbk;
+          while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (sOff[mid] - passBase <= (uint32_t)C::STAGE_CAP) lo = mid; else hi = mid - 1; }
+          bHi = lo;
+        }
+        const uint32_t passBytes = (bHi == nbk ? tileBytes : sOff[bHi]) - passBase;
+        packBlocks(stage, bx0, h, bLo, bHi, passBase);
+        namedBarSync(1, ENC_COMPUTE);
+        flushPass(stage, tileOff + passBase, passBytes);
+        namedBarSync(1, ENC_COMPUTE);
+        for (int i = tid; i < C::STAGE_BYTES / 16; i += ENC_COMPUTE) ((uint4*)(stage - 4))[i] = make_uint4(0, 0, 0, 0);
+        bLo = bHi; passBase += passBytes;
+        if (bLo < nbk) namedBarSync(1, ENC_COMPUTE);
+      }
+      if (tid == 0) sTileNext = nextT;
+      namedBarSync(1, ENC_COMPUTE);                                  // image cleared, sIn free
+      const int tn = sTileNext;
+      if (tid == 0 && vecOk && tn < nTiles) issueLoad(tn);
+      tile = tn;
     }
   }
+  // ---- the last tile's image; stop the control warp
+  if (pendK >= 0) {
+    mbarWait(&sBarOff[pendK & 1], (uint32_t)(pendK >> 1) & 1u);
+    flushPass((uint32_t*)(tileSmem + C::IN_BYTES + (pendK & 1) * C::STAGE_BYTES) + 4, sOffS[pendK & 1], pendBytes);
+  }
+  if (tid == 0) { sMailTile[k & 1] = -1; mbarArrive(&sBarScan[k & 1]); }
 
   // ---- image-global facts and checksum partials of this CTA
 #pragma unroll
@@ -469,11 +510,11 @@ __global__ void __launch_bounds__(256, MINB) k_encode_tile(FastEncArgs a) {
 #pragma unroll
   for (int m = 16; m; m >>= 1) { fa += __shfl_xor_sync(FULL, fa, m); fd += __shfl_xor_sync(FULL, fd, m); }
   if (lane == 0) { sKMin[warp] = (unsigned long long)gMin; sKMax[warp] = (unsigned long long)gMax; sFlg[warp] = myFlags; sFA[warp] = fa; sFD[warp] = fd; }
-  __syncthreads();
+  namedBarSync(1, ENC_COMPUTE);
   if (tid == 0) {
     unsigned long long A = 0, D = 0, kMin = ~0ull, kMax = 0; unsigned int fl = 0;
     for (int i = 0; i < 8; i++) { A += sFA[i]; D += sFD[i]; kMin = sKMin[i] < kMin ? sKMin[i] : kMin; kMax = sKMax[i] > kMax ? sKMax[i] : kMax; fl |= sFlg[i]; }
-    if (A | D) { atomicAdd(&a.res->fletA[tile % FAST_SLOTS], A); atomicAdd(&a.res->fletD[tile % FAST_SLOTS], D % 65535ull); }
+    if (A | D) { atomicAdd(&a.res->fletA[blockIdx.x % FAST_SLOTS], A); atomicAdd(&a.res->fletD[blockIdx.x % FAST_SLOTS], D % 65535ull); }
     if (kMax >= kMin) {
       if (~kMin > negMinSeen) atomicMax(&a.res->negMinKey, ~kMin);
       if (kMax > maxSeen) atomicMax(&a.res->maxKey, kMax);

@@ -69,6 +69,7 @@ struct ThreadCtx {          // what a CUDA thread sees
 ThreadCtx& self();
 void yield();                                                     // give the other fibers of the CTA a turn
 void syncthreads();
+void namedBarrier(int id, int nThreads);
 void warpExchange(unsigned mask, uint64_t mine, uint64_t out[32], unsigned* present);   // rendezvous of the lanes in mask
 void launch(dim3 grid, dim3 block, size_t smem, void* stream, const std::function<void()>& body);
 inline void* dynSmem() { return self().dynSmem; }

@@ -80,6 +80,7 @@ struct Cta {
   std::vector<WarpState> warps;
   int nThreads = 0, nExited = 0;
   int barCount = 0; unsigned barGen = 0;
+  int nbarCount[16] = {0}; unsigned nbarGen[16] = {0};     // named barriers (bar.sync id, nThreads)
   void* schedSp = nullptr;
   Fiber* cur = nullptr;
   const std::function<void()>* body = nullptr;
@@ -207,6 +208,21 @@ void syncthreads() {
   for (;;) {
     if (cta->barGen != myGen) break;
     if (cta->barCount + cta->nExited >= cta->nThreads) { cta->barCount = 0; cta->barGen++; cta->progress++; break; }
+    switchToScheduler();
+  }
+  f->waitingOn = "";
+}
+
+void namedBarrier(int id, int nThreads) {
+  Cta* cta = tlCta;
+  Fiber* f = cta->cur;
+  if (id < 1 || id > 15) { std::fprintf(stderr, "[cusim] named barrier id %d out of range\n", id); std::abort(); }
+  const unsigned myGen = cta->nbarGen[id];
+  cta->nbarCount[id]++;
+  f->waitingOn = "named barrier";
+  for (;;) {
+    if (cta->nbarGen[id] != myGen) break;
+    if (cta->nbarCount[id] >= nThreads) { cta->nbarCount[id] = 0; cta->nbarGen[id]++; cta->progress++; break; }
     switchToScheduler();
   }
   f->waitingOn = "";

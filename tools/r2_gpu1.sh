@@ -1,14 +1,14 @@
 #!/bin/bash
 # round 2, GPU call 1: parity of the new tile encoder + first timing + ncu capture
 set -u
-OUT=gpurun_out/r2a
+OUT=gpurun_out/${R2OUT:-r2b}
 mkdir -p "$OUT"
 timeout 300 python -m pytest tests/test_gpu_fastpath.py tests/test_gpu_parity.py tests/test_gpu_large.py tests/test_gpu_tiles.py -x -q -m gpu -p no:cacheprovider > "$OUT/tests.log" 2>&1
 tail -3 "$OUT/tests.log"
 timeout 200 python bench.py --steps 20 --no-cpu-baseline > "$OUT/bench_c2.json" 2> "$OUT/bench_c2.err"
 python - <<'PY'
 import json
-d = json.load(open("gpurun_out/r2a/bench_c2.json"))
+d = json.load(open("gpurun_out/"+__import__("os").environ.get("R2OUT","r2b")+"/bench_c2.json"))
 print(round(d["value"], 2), "Gpx/s", round(d["ms_per_step"], 4), "ms", {n: round(v["ms_per_step"], 4) for n, v in d["roofline"]["kernels"].items()})
 print("e2e", d["e2e"]["value"], d["clocks"])
 PY
