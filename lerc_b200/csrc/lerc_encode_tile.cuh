@@ -192,7 +192,11 @@ __global__ void __launch_bounds__(ENC_THREADS, MINB) k_encode_tile(FastEncArgs a
         const long long idx = (long long)tile - 1 - lane;
         const bool in = lane < l;
         unsigned long long s = 0;
-        if (in) { while (((s = st[idx]) >> 62) == 0) __nanosleep(40); }
+        for (;;) {                                                      // warp-uniform polling: one round of loads, then sleep
+          if (in && (s >> 62) == 0) s = st[idx];
+          if (__all_sync(FULL, !in || (s >> 62) != 0)) break;
+          __nanosleep(200);
+        }
         const unsigned isP = __ballot_sync(FULL, in && (s >> 62) == 2);
         const int firstP = isP ? __ffs(isP) - 1 : 32;
         unsigned long long contrib = (in && lane <= firstP) ? (s & VAL) : 0;
@@ -206,8 +210,12 @@ __global__ void __launch_bounds__(ENC_THREADS, MINB) k_encode_tile(FastEncArgs a
         long long base = g - 1;
         for (;;) {
           const long long idx = base - lane;
-          unsigned long long s = ST_P;                                  // virtual groups before 0: prefix 0
-          if (idx >= 0) { while (((s = gs[idx]) >> 62) == 0) __nanosleep(40); }
+          unsigned long long s = idx >= 0 ? 0ull : ST_P;                // virtual groups before 0: prefix 0
+          for (;;) {
+            if ((s >> 62) == 0) s = gs[idx];
+            if (__all_sync(FULL, (s >> 62) != 0)) break;
+            __nanosleep(200);
+          }
           const unsigned isP = __ballot_sync(FULL, (s >> 62) == 2);
           const int firstP = isP ? __ffs(isP) - 1 : 32;
           unsigned long long contrib = (lane <= firstP && idx >= 0) ? (s & VAL) : 0;
