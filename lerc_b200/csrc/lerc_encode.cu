@@ -772,7 +772,7 @@ bool encodeBandFast(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
   if (a.outCapacity < dataStart + 1) return false;                     // let the general path report BufferTooSmall exactly
 
   const size_t nGroups = (size_t)((nTiles + 31) / 32);
-  const size_t stateBytes = sizeof(FastEncResult) + 9 * 8 + (size_t)nTiles * 8 + nGroups * 8;
+  const size_t stateBytes = sizeof(FastEncResult) + 9 * 8 + (size_t)nTiles * 8 + 2 * nGroups * 8;
   uint8_t* dState = (uint8_t*)ctx->arena.alloc(stateBytes);
   struct HostRes { FastEncResult r; unsigned long long raise[9]; };
   HostRes* hRes = (HostRes*)ctx->pinnedAlloc(sizeof(HostRes));
@@ -803,7 +803,7 @@ bool encodeBandFast(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
   uint8_t* blob = a.dOut + a.outOffset;
   fa.stream = blob + dataStart; fa.streamCap = a.outCapacity - dataStart; fa.regionOff = (long long)dataStart - 14;
   fa.tileState = (unsigned long long*)(dState + sizeof(FastEncResult) + 9 * 8); fa.res = dRes;
-  fa.groupState = fa.tileState + nTiles;                               // look-back level 2: aggregates per group of 32 tiles
+  fa.groupState = fa.tileState + nTiles; fa.groupAcc = fa.groupState + nGroups;   // look-back level 2: groups of 32 tiles
   {
     // persistent CTAs, tiles taken by ticket (no co-residency assumption); shared memory opt-in and occupancy once per device
     constexpr size_t smem = (size_t)EncTile<T>::SMEM;

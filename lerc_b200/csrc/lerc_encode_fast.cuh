@@ -43,6 +43,7 @@ struct FastEncArgs {
   unsigned long long* tileState;       // [nTiles], zero-initialised
   FastEncResult* res;
   unsigned long long* groupState;      // [ceil(nTiles / 32)], zero-initialised: aggregates of 32 consecutive tiles (two-round look-back); nullptr = plain chain
+  unsigned long long* groupAcc;        // [ceil(nTiles / 32)], zero-initialised: atomic accumulators of the groups (lerc_lookback.cuh)
 };
 
 // ---- tile batch (k_encode_fused<T, MINB, true>, lerc_tiles_encode.cuh): the raster is cut into imgRows x imgCols images, every

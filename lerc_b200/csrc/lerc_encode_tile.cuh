@@ -26,6 +26,7 @@
 // collects (min / max, NaN, all-integer, LUT candidates, overflow) let the caller verify them.
 #pragma once
 #include "lerc_tma.cuh"
+#include "lerc_lookback.cuh"
 
 namespace lerc {
 
@@ -153,7 +154,6 @@ __global__ void __launch_bounds__(ENC_THREADS, MINB) k_encode_tile(FastEncArgs a
   const bool vecOk = (((long long)a.nCols * (int)sizeof(T)) % 16 == 0) && (((uintptr_t)data & 15) == 0);
   const int tpr = (a.nTx + TW - 1) / TW;                          // tiles per block row
   const int nTiles = tpr * a.nTy;
-  constexpr unsigned long long ST_A = 1ull << 62, ST_P = 2ull << 62, VAL = (1ull << 62) - 1;
   volatile unsigned long long* st = a.tileState;
 
   // the copy engine brings tile t into sIn (thread 0 of the compute warps)
@@ -184,51 +184,8 @@ __global__ void __launch_bounds__(ENC_THREADS, MINB) k_encode_tile(FastEncArgs a
       const int tile = sMailTile[k & 1];
       if (tile < 0) break;
       const unsigned long long tileBytes = sMailBytes[k & 1];
-      unsigned long long excl = 0;
-      const int l = tile & 31;
-      const long long g = tile >> 5;
-      bool needGroups = g > 0;
-      {  // round 1: the predecessors inside the tile's group of 32
-        const long long idx = (long long)tile - 1 - lane;
-        const bool in = lane < l;
-        unsigned long long s = 0;
-        for (;;) {                                                      // warp-uniform polling: one round of loads, then sleep
-          if (in && (s >> 62) == 0) s = st[idx];
-          if (__all_sync(FULL, !in || (s >> 62) != 0)) break;
-          __nanosleep(200);
-        }
-        const unsigned isP = __ballot_sync(FULL, in && (s >> 62) == 2);
-        const int firstP = isP ? __ffs(isP) - 1 : 32;
-        unsigned long long contrib = (in && lane <= firstP) ? (s & VAL) : 0;
-#pragma unroll
-        for (int m = 16; m; m >>= 1) contrib += __shfl_xor_sync(FULL, contrib, m);
-        excl = contrib;
-        if (isP) needGroups = false;                                    // an inclusive prefix inside the group: excl is already global
-      }
-      if (l == 31 && needGroups && lane == 0) gs[g] = ST_A | (excl + tileBytes);      // this group's bytes (its 32 tiles are all sized)
-      if (needGroups) {  // round 2: aggregates of whole groups
-        long long base = g - 1;
-        for (;;) {
-          const long long idx = base - lane;
-          unsigned long long s = idx >= 0 ? 0ull : ST_P;                // virtual groups before 0: prefix 0
-          for (;;) {
-            if ((s >> 62) == 0) s = gs[idx];
-            if (__all_sync(FULL, (s >> 62) != 0)) break;
-            __nanosleep(200);
-          }
-          const unsigned isP = __ballot_sync(FULL, (s >> 62) == 2);
-          const int firstP = isP ? __ffs(isP) - 1 : 32;
-          unsigned long long contrib = (lane <= firstP && idx >= 0) ? (s & VAL) : 0;
-#pragma unroll
-          for (int m = 16; m; m >>= 1) contrib += __shfl_xor_sync(FULL, contrib, m);
-          excl += contrib;
-          if (isP) break;
-          base -= 32;
-        }
-      }
+      const unsigned long long excl = lookbackExclusive(st, a.groupAcc, gs, tile, tileBytes, lane);
       if (lane == 0) {
-        if (tile > 0) st[tile] = ST_P | (excl + tileBytes);
-        if (l == 31) gs[g] = ST_P | (excl + tileBytes);                 // inclusive prefix of the whole group
         if (tile == nTiles - 1) a.res->totalBytes = excl + tileBytes;
         sOffS[k & 1] = excl;
         mbarArrive(&sBarOff[k & 1]);
@@ -346,7 +303,6 @@ __global__ void __launch_bounds__(ENC_THREADS, MINB) k_encode_tile(FastEncArgs a
   int k = 0;                                                        // tiles this CTA has posted to its control warp
   for (; tile < nTiles; k++) {
     int nextT = 0;
-    if (tid == 0) nextT = (int)atomicAdd(&a.res->ticket, 1u);      // ticket of tile k + 1: in flight until the tile is packed
     const int tyT = tile / tpr, seg = tile - tyT * tpr;
     const int bx0 = seg * TW;                                      // first block column of the tile
     const int nbk = min(TW, a.nTx - bx0);                          // blocks in the tile
@@ -437,13 +393,14 @@ __global__ void __launch_bounds__(ENC_THREADS, MINB) k_encode_tile(FastEncArgs a
       for (int j = 0; j < PER; j++) { sOff[lane * PER + j] = run; run += v[j]; }
       if (lane == 31) {
         sOff[TW] = inc;
-        st[tile] = (tile == 0 ? ST_P : ST_A) | (unsigned long long)inc;        // for the other CTAs' look-backs
+        lookbackPublish(st, a.groupAcc, tile, inc);                                     // for the other CTAs' look-backs
         sMailTile[k & 1] = tile; sMailBytes[k & 1] = inc;
         mbarArrive(&sBarScan[k & 1]);                                          // for this CTA's control warp
       }
     }
     namedBarSync(1, ENC_COMPUTE);
     const uint32_t tileBytes = sOff[TW];
+    if (tid == 0) nextT = (int)atomicAdd(&a.res->ticket, 1u);      // ticket of tile k + 1: in flight while this tile is packed
 
     if (tileBytes <= (uint32_t)C::STAGE_CAP) {
       // ---- the common case: one pass into this tile's staging image; it is flushed when the next tile has been packed
