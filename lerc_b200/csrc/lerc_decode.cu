@@ -332,8 +332,10 @@ __global__ void k_huffman_decode_seq(HuffDecArgs a) {
 
 }  // namespace lerc
 #include "lerc_decode_fast.cuh"
+#include "lerc_decode_stream.cuh"
 #include "lerc_huffman_fast.cuh"
 #include <cub/device/device_scan.cuh>
+#include <atomic>
 namespace lerc {
 
 // =================================================================================================
@@ -356,6 +358,47 @@ inline void launchResolve(Context* ctx, const FastDecArgs& fa) {
     if (!attrSet) { cudaFuncSetAttribute(k_dec_resolve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attrSet = true; }
     LERC_LAUNCH(ctx, k_dec_resolve<true>, 1, 1024, bytes, fa, fa.nTx * fa.nTy);
   } else LERC_LAUNCH(ctx, k_dec_resolve<false>, 1, 1024, 0, fa, fa.nTx * fa.nTy);
+}
+
+// Single-kernel stream decoder (lerc_decode_stream.cuh): all-valid, nDepth == 1, 8x8 blocks, codec version >= 3.
+// prefA / prefD: Fletcher partial sums of the band blob's bytes [14, streamPos) (host).  Returns 1 = decoded and the
+// checksum is right, 0 = the kernel gave up (nothing is known about the blob: run the other decoders), -1 = checksum
+// mismatch or CUDA error.
+template <class T>
+int decodeStreamFast(Context* ctx, const HeaderInfo& hd, const uint8_t* dBlob, size_t streamPos, unsigned long long prefA, unsigned long long prefD, void* dData) {
+  const size_t streamLen = (size_t)hd.blobSize - streamPos;
+  if (streamLen == 0 || streamLen >= 0xfff00000ull || std::getenv("LERC_B200_NO_FAST")) return 0;
+  cudaStream_t st = ctx->stream;
+  const int nChunks = (int)((streamLen + DS_CHUNK - 1) / DS_CHUNK);
+  const size_t nGroups = ((size_t)nChunks + 31) / 32;
+  const size_t stateBytes = 64 + ((size_t)nChunks * 2 + nGroups * 2) * 8;
+  uint8_t* dState = (uint8_t*)ctx->arena.alloc(stateBytes);
+  unsigned int* hStatus = (unsigned int*)ctx->pinnedAlloc(16);
+  if (!dState || !hStatus) return 0;
+  cudaMemsetAsync(dState, 0, stateBytes, st);
+  StreamDecArgs sa;
+  sa.stream = dBlob + streamPos; sa.streamLen = streamLen;
+  sa.nRows = hd.nRows; sa.nCols = hd.nCols; sa.nTx = (hd.nCols + 7) / 8; sa.nTy = (hd.nRows + 7) / 8; sa.version = hd.version;
+  sa.nTxMagic = sa.nTx >= 2 ? (uint32_t)((1ull << 32) / (unsigned)sa.nTx) + 1u : 0u;
+  sa.invScale = 2 * hd.maxZError; sa.zMax = hd.zMax; sa.data = dData; sa.nChunks = nChunks;
+  sa.res = (StreamDecResult*)dState;
+  sa.exitState = (unsigned long long*)(dState + 64); sa.cntState = sa.exitState + nChunks;
+  sa.groupState = sa.cntState + nChunks; sa.groupAcc = sa.groupState + nGroups;
+  sa.regionOff = (long long)streamPos - 14; sa.regionLen = (long long)hd.blobSize - 14;
+  sa.prefA = prefA % 65535ull; sa.prefD = prefD % 65535ull; sa.expectChecksum = hd.checksum; sa.haveChecksum = hd.version >= 3 ? 1 : 0;
+  constexpr size_t smem = (size_t)DecStream<T>::SMEM;
+  static std::atomic<unsigned long long> attrDone{0};
+  const unsigned long long devBit = 1ull << (ctx->device & 63);
+  if (!(attrDone.load(std::memory_order_relaxed) & devBit)) {
+    if (!cudaOk(cudaFuncSetAttribute(k_decode_stream<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "decode stream smem")) return 0;
+    attrDone.fetch_or(devBit, std::memory_order_relaxed);
+  }
+  { LaunchScope scope_(ctx, "k_decode_stream<T>"); k_decode_stream<T><<<(unsigned)nChunks, DS_THREADS, smem, st>>>(sa); ctx->kernelLaunches++; }
+  if (!cudaOk(cudaMemcpyAsync(hStatus, &sa.res->status, 4, cudaMemcpyDeviceToHost, st), "D2H stream status") || !cudaOk(cudaStreamSynchronize(st), "sync")) return -1;
+  if (!cudaOk(cudaGetLastError(), "k_decode_stream")) return -1;
+  if (*hStatus && std::getenv("LERC_B200_VERBOSE")) std::fprintf(stderr, "[lerc_b200] stream decoder status %u\n", *hStatus);
+  if (*hStatus & DSF_CHECKSUM) return -1;
+  return (*hStatus & DSF_FALLBACK) ? 0 : 1;
 }
 
 // Launches the speculative parallel decoder (lerc_decode_fast.cuh) on the micro-block stream.  Returns false when the
@@ -571,16 +614,21 @@ ErrCode decodeBandT(Context* ctx, DecodeBandArgs& a, BandMaskState& ms) {
   if (!dStatus) return Failed;
   cudaMemsetAsync(dStatus, 0, 16, st);
 
-  // checksum (Lerc2.cpp:592-601); the verdict is read together with the other status bits at the end
-  if (hd.version >= 3) {
-    if (hd.blobSize < 14) return Failed;
+  // checksum (Lerc2.cpp:592-601); the verdict is read together with the other status bits at the end.  The single-kernel stream
+  // decoder sums the blob itself, so the launch waits until it is known whether that decoder applies.
+  if (hd.version >= 3 && hd.blobSize < 14) return Failed;
+  bool checksumLaunched = false;
+  auto launchChecksum = [&]() -> bool {
+    if (hd.version < 3 || checksumLaunched) return true;
     unsigned long long* dAcc = (unsigned long long*)ctx->arena.alloc(16);
-    if (!dAcc) return Failed;
+    if (!dAcc) return false;
     ctx->forkSide();                                   // the checksum only reads the blob: it runs beside the decode kernels
     cudaMemsetAsync(dAcc, 0, 16, ctx->stream);
     launchFletcher(ctx, blob + 14, (long long)hd.blobSize - 14, dAcc, nullptr, hd.checksum, dStatus);
     ctx->backToMain();
-  }
+    checksumLaunched = true;
+    return true;
+  };
 
   // mask (Lerc2.cpp:961-1008)
   size_t pos = (size_t)headerBytes(hd.version);
@@ -605,10 +653,11 @@ ErrCode decodeBandT(Context* ctx, DecodeBandArgs& a, BandMaskState& ms) {
   const bool mayFast = nDepth == 1 && hd.numValidPixel == nPix && hd.microBlockSize == 8 && hd.version >= 3 && hd.zMin != hd.zMax;
   bool zeroFilled = false;
   auto zeroFill = [&]() { if (!zeroFilled) { cudaMemsetAsync(a.dData, 0, (size_t)nPix * nDepth * sizeof(T), st); zeroFilled = true; } };
-  if (!mayFast) zeroFill();
+  if (!mayFast) { zeroFill(); if (!launchChecksum()) return Failed; }
 
   auto finish = [&]() -> ErrCode {
     int hStatus[2] = {0, 1};
+    if (!launchChecksum()) return Failed;              // (paths that did not launch it earlier)
     ctx->joinSide();
     if (!cudaOk(cudaMemcpyAsync(hStatus, dStatus, 8, cudaMemcpyDeviceToHost, st), "D2H status")) return Failed;
     if (!cudaOk(cudaStreamSynchronize(st), "sync")) return Failed;
@@ -649,6 +698,7 @@ ErrCode decodeBandT(Context* ctx, DecodeBandArgs& a, BandMaskState& ms) {
   pos += 1;
   if (flags[0]) {                                                                       // one sweep
     zeroFill();
+    if (!launchChecksum()) return Failed;
     const size_t len = (size_t)nDepth * sizeof(T);
     // numValidPixel of the header is trusted here only after comparing with the mask popcount on the device path below
     if (hd.numValidPixel == nPix) {
@@ -676,6 +726,7 @@ ErrCode decodeBandT(Context* ctx, DecodeBandArgs& a, BandMaskState& ms) {
     if (mode > 3 || (mode > 2 && hd.version < 6) || (mode > 1 && hd.version < 4)) return Failed;
     if (mode != IEM_Tiling) {
       zeroFill();
+      if (!launchChecksum()) return Failed;
       if constexpr (sizeof(T) == 1) {
         if (!(hd.tryHuffmanInt() && (mode == IEM_DeltaHuffman || (hd.version >= 4 && mode == IEM_Huffman)))) return Failed;
         std::vector<uint8_t> tb(std::min<size_t>(2048, (size_t)hd.blobSize - pos));
@@ -707,7 +758,19 @@ ErrCode decodeBandT(Context* ctx, DecodeBandArgs& a, BandMaskState& ms) {
       } else return Failed;
     }
   }
-  // micro-block stream: single-kernel speculative decoder first (lerc_decode_fast.cuh)
+  // micro-block stream: the single-kernel stream decoder first (lerc_decode_stream.cuh) ...
+  if (mayFast) {
+    unsigned long long pA = 0, pD = 0;
+    uint8_t pre[256];
+    if (pos > 14 && pos - 14 <= sizeof pre && src.fetch(14, pos - 14, pre)) {
+      fletcherHostPartial(pre, 0, (long long)pos - 14, pA, pD);
+      const int rc = decodeStreamFast<T>(ctx, hd, blob, pos, pA, pD, a.dData);
+      if (rc < 0) return Failed;
+      if (rc > 0) { globalStats().fastPathDecodes++; return Ok; }
+    }
+    if (!launchChecksum()) return Failed;
+  }
+  // ... then the multi-kernel speculative decoder (lerc_decode_fast.cuh: keeps up to 16 entry candidates per sub-chunk, repairs floods)
   FastDecArgs fdArgs;
   if (mayFast && launchDecodeFast<T>(ctx, hd, blob + pos, (size_t)hd.blobSize - pos, a.dData, dStatus, nullptr, nullptr, &fdArgs)) {
     int hs = 0;

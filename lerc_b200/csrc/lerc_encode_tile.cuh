@@ -27,6 +27,7 @@
 #pragma once
 #include "lerc_tma.cuh"
 #include "lerc_lookback.cuh"
+#include "lerc_fletcher.cuh"
 
 namespace lerc {
 
@@ -97,27 +98,6 @@ __device__ __noinline__ void tileGenericChoice(const FastEncArgs& a, const uint8
   info.x = (uint32_t)lb; info.w = (uint32_t)(lb >> 32); info.z = 0;
   info.y = (uint32_t)(nb | (tc << 5) | (mode << 7) | (maxElem == 0 ? TINFO_CONST : 0));
   len = (uint32_t)nBytes;
-}
-
-// Fletcher-32 partial sums of one 16-byte output chunk whose first byte has checksum-region offset r0 (parity PAR):
-// S = sum of the chunk's bytes weighted 256 (even region offsets) / 1 (odd), S1 = the same weighted with the byte's
-// word index relative to the chunk's first word.
-template <int PAR>
-__device__ __forceinline__ void fletcherChunk(const uint32_t (&o)[4], uint32_t& S, uint32_t& S1) {
-  uint32_t H = 0, L = 0, HW = 0, LW = 0;
-#pragma unroll
-  for (int j = 0; j < 4; j++) {
-    if (PAR == 0) {   // bytes 0, 2 of a word are high bytes; word index of byte 4j + m: (4j + m) >> 1
-      H = __dp4a(o[j], 0x00010001u, H);  L = __dp4a(o[j], 0x01000100u, L);
-      HW = __dp4a(o[j], (uint32_t)(2 * j) | ((uint32_t)(2 * j + 1) << 16), HW);
-      LW = __dp4a(o[j], ((uint32_t)(2 * j) << 8) | ((uint32_t)(2 * j + 1) << 24), LW);
-    } else {          // bytes 1, 3 are high bytes; word index of byte 4j + m: (4j + m + 1) >> 1
-      H = __dp4a(o[j], 0x01000100u, H);  L = __dp4a(o[j], 0x00010001u, L);
-      HW = __dp4a(o[j], ((uint32_t)(2 * j + 1) << 8) | ((uint32_t)(2 * j + 2) << 24), HW);
-      LW = __dp4a(o[j], (uint32_t)(2 * j) | ((uint32_t)(2 * j + 1) << 16), LW);
-    }
-  }
-  S = 256u * H + L; S1 = 256u * HW + LW;
 }
 
 // OR a word into shared memory: one ATOMS.OR without a result.  (ptxas turns a predicated red into a branch around the ATOMS,

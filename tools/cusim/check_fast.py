@@ -60,6 +60,7 @@ def cases():
 
 
 def main():
+    os.environ.setdefault("LERC_B200_VERBOSE", "1")
     ap = argparse.ArgumentParser()
     ap.add_argument("-k", default="")
     args = ap.parse_args()
@@ -84,14 +85,27 @@ def main():
             msg.append("single-pass encoder not taken")
         if s_o == 0:
             t_o, d_o, _ = orc.decode(b_o)
-            t_s, d_s, _ = sim.decode(b_o)
+            # stderr of the library (LERC_B200_VERBOSE names a decoder that gave up) goes through a temporary file
+            import tempfile
+            sys.stderr.flush()
+            saved = os.dup(2)
+            with tempfile.TemporaryFile() as tf:
+                os.dup2(tf.fileno(), 2)
+                try:
+                    t_s, d_s, _ = sim.decode(b_o)
+                finally:
+                    os.dup2(saved, 2); os.close(saved)
+                tf.seek(0)
+                if os.environ.get("DS_DEBUG"):
+                    sys.stdout.write(tf.read().decode()); tf.seek(0)
+                note = " ".join(l.decode().strip().replace("[lerc_b200] ", "") for l in tf.readlines() if b"status" in l)
             after = stats(sim)
             if t_s != t_o or (t_o == 0 and not np.array_equal(d_s.view(np.uint8), d_o.view(np.uint8))):
                 msg.append("decode differs")
             fast_dec = after[4] == mid[4] + 1
         else:
             fast_dec = False
-        print(f"{'ok  ' if not msg else 'FAIL'} {name:36s} {time.time() - t0:6.1f}s enc_fast={mid[3] - before[3]} dec_fast={int(fast_dec)} {'; '.join(msg)}", flush=True)
+        print(f"{'ok  ' if not msg else 'FAIL'} {name:36s} {time.time() - t0:6.1f}s enc_fast={mid[3] - before[3]} dec_fast={int(fast_dec)} {note if s_o == 0 else ''} {'; '.join(msg)}", flush=True)
         fails += bool(msg)
     print("failures:", fails)
     return 1 if fails else 0
