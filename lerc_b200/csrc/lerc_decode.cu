@@ -367,7 +367,7 @@ inline void launchResolve(Context* ctx, const FastDecArgs& fa) {
 template <class T>
 int decodeStreamFast(Context* ctx, const HeaderInfo& hd, const uint8_t* dBlob, size_t streamPos, unsigned long long prefA, unsigned long long prefD, void* dData) {
   const size_t streamLen = (size_t)hd.blobSize - streamPos;
-  if (streamLen == 0 || streamLen >= 0xfff00000ull || std::getenv("LERC_B200_NO_FAST")) return 0;
+  if (streamLen == 0 || streamLen >= 0xfff00000ull || !std::isfinite(hd.zMax) || std::getenv("LERC_B200_NO_FAST")) return 0;
   cudaStream_t st = ctx->stream;
   const int nChunks = (int)((streamLen + DS_CHUNK - 1) / DS_CHUNK);
   const size_t nGroups = ((size_t)nChunks + 31) / 32;

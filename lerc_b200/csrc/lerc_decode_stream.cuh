@@ -9,11 +9,13 @@
 //   stage      the chunk (+ look-ahead for the unit that straddles its end) is copied into shared memory by the copy
 //              engine: one cp.async.bulk (TMA, SASS UBLKCP) from the 16-byte aligned address below the chunk, completion
 //              on an mbarrier; the last partial 16 bytes of the stream are read byte-wise (nothing is read past the blob)
-//   guess      one warp per 2 KB sub-chunk: the lowest byte position of the sub-chunk's head window (the true chain must
-//              enter inside the first MAXU bytes) from which DS_HOPS consecutive units parse with consistent integrity
-//              bits (Lerc2.cpp:2045).  A wrong guess is a position inside the previous unit whose chain has merged into
-//              the true chain - it differs from the true chain in its first few hops only.
-//   walk       lane 0 of every warp hops from header to header to the end of its sub-chunk, recording the positions
+//   guess      the chunk is cut into 32 sub-chunks of 512 bytes; every warp scans the head windows of four of them (the true
+//              chain must enter a sub-chunk inside its first MAXU bytes), 32 byte positions per step, for the first position
+//              that reads as the headers of two full bit-stuffed blocks in a row (mode 1, one-byte count of 64, consecutive
+//              integrity bits); windows without one (flat regions) take the first position from which DS_HOPS units parse with
+//              consistent integrity bits (Lerc2.cpp:2045).  A wrong guess is a position inside the previous unit whose chain
+//              merges into the true chain or dies - it differs from the true chain in its first few hops only.
+//   walk       warp 0, one LANE per sub-chunk: hop from header to header to the end of the sub-chunk, recording the positions
 //   publish    the chunk's speculative exit (where its last chain leaves the chunk) for the next chunk; the previous
 //              chunk's exit is this chunk's TRUE entry (chunk 0 starts at 0)
 //   patch      one thread walks from the true entry until it hits a recorded position (usually at once), sub-chunk by
@@ -37,12 +39,12 @@
 namespace lerc {
 
 constexpr int DS_CHUNK = 16384;                 // stream bytes per CTA
-constexpr int DS_SUBS = 8;                      // sub-chunks per chunk, one warp each
+constexpr int DS_SUBS = 32;                     // sub-chunks per chunk, one lane of warp 0 each
 constexpr int DS_SUB = DS_CHUNK / DS_SUBS;
 constexpr int DS_LIST = DS_SUB + 8;             // recorded positions per sub-chunk (1-byte units fill it with DS_SUB)
-constexpr int DS_PATCH = 64;                    // hops the patch walk may need before it joins the recorded chain
-constexpr int DS_HOPS = 4;                      // units a head-window position must parse to become the guess
-constexpr int DS_THREADS = DS_SUBS * 32;
+constexpr int DS_PATCH = 96;                    // hops the patch walk may need before it joins the recorded chain
+constexpr int DS_HOPS = 4;                      // units a head-window position must parse to become the guess (windows without a strict candidate)
+constexpr int DS_THREADS = 256;
 enum { DSF_FALLBACK = 8, DSF_CHECKSUM = 2 };
 
 struct StreamDecResult {                        // device, zero-initialised per call
@@ -81,6 +83,20 @@ __device__ __forceinline__ void dsDivMod(uint32_t b, int nTx, uint32_t magic, in
   q = (int)qq; r = (int)(b - qq * (uint32_t)nTx);
 }
 
+// Header of a FULL bit-stuffed block (mode 1, no LUT, one-byte count == 64) in the window's bytes?  Returns the unit length or 0.
+template <class T>
+__device__ __forceinline__ int dsStrictLen(const FdWin& x, int version) {
+  constexpr int DT = PixelTraits<T>::code;
+  const uint32_t flag = (uint32_t)x.lo & 0xff;
+  if ((flag & 3) != 1 || (version >= 5 && (flag & 4))) return 0;
+  const int dtUsed = offsetTypeFromCode(DT, (int)(flag >> 6));
+  if (dtUsed == DT_Undefined) return 0;
+  const int osz = dtSize(dtUsed);
+  const uint32_t b = fdByte(x, 1 + osz), n = fdByte(x, 2 + osz);
+  if ((b & 0xe0) != 0x80 || (b & 31) == 0 || n != 64) return 0;
+  return 3 + osz + 8 * (int)(b & 31);
+}
+
 template <class T>
 __global__ void __launch_bounds__(DS_THREADS, 4) k_decode_stream(StreamDecArgs a) {
   using C = DecStream<T>;
@@ -94,7 +110,7 @@ __global__ void __launch_bounds__(DS_THREADS, 4) k_decode_stream(StreamDecArgs a
   __shared__ __align__(8) uint64_t sBar;
   __shared__ int sChunk, sOk, sTotal;
   __shared__ unsigned long long sBlk0;
-  __shared__ unsigned long long sFA[DS_SUBS], sFD[DS_SUBS];
+  __shared__ unsigned long long sFA[DS_THREADS / 32], sFD[DS_THREADS / 32];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int version = a.version;
@@ -135,22 +151,38 @@ __global__ void __launch_bounds__(DS_THREADS, 4) k_decode_stream(StreamDecArgs a
     return fdHopLen<T>(fdWindow(words, (uint32_t)(d + p)), sb + p, version, left - p, tailRaw, pat);
   };
 
-  // ---- guess (whole warp) + walk (lane 0) of sub-chunk `warp`
-  if (warp < nSubs) {
-    const int s = warp, subStart = s * DS_SUB, subEnd = min(subStart + DS_SUB, chunkLen);
-    uint16_t* list = sListAll + s * DS_LIST;
-    // A guess whose chain dies before the end of the sub-chunk was a wrong one (the true chain of a well-formed stream never
-    // dies): the search resumes behind it, a few times.
-    int searchFrom = subStart;
-    for (int attempt = 0; attempt < 6; attempt++) {
-      int guess = -1;
-      if (c == 0 && s == 0) guess = 0;                                // the stream starts with block 0
-      else {
-        // Raw units carry no redundancy (any byte with zero mode bits "is" a raw block of MAXU bytes), so a position whose first
-        // unit is not raw is preferred wherever it lies in the head window; the lowest other survivor is the reserve.
-        const int headEnd = min(subStart + MAXU, testable);
+  // ---- guess: every warp scans the head windows of four sub-chunks
+  for (int s = warp; s < nSubs; s += DS_THREADS / 32) {
+    const int subStart = s * DS_SUB;
+    int guess = -1;
+    if (c == 0 && s == 0) guess = 0;                                  // the stream starts with block 0
+    else {
+      const int headEnd = min(subStart + MAXU, testable);
+      for (int base = subStart; base < headEnd && guess < 0; base += 32) {
+        const int p = base + lane;
+        // two full bit-stuffed blocks in a row with consecutive integrity bits (one alone can be faked by the bytes of a block's offset)
+        bool hit = false;
+        if (p < headEnd) {
+          const FdWin w1 = fdWindow(words, (uint32_t)(d + p));
+          const int len = dsStrictLen<T>(w1, version);
+          if (len > 0 && (long long)len <= left - p) {
+            if ((long long)len == left - p) hit = true;                  // the stream's last block
+            else if (p + len < testable) {
+              const FdWin w2 = fdWindow(words, (uint32_t)(d + p + len));
+              const int len2 = dsStrictLen<T>(w2, version);
+              hit = len2 > 0 && (long long)len2 <= left - p - len &&
+                    fdFollows(fdPattern((uint32_t)w1.lo & 0xff, version), fdPattern((uint32_t)w2.lo & 0xff, version), version);
+            }
+          }
+        }
+        const unsigned m = __ballot_sync(FULL, hit);
+        if (m) guess = base + __ffs(m) - 1;
+      }
+      if (guess < 0) {
+        // no full bit-stuffed block starts in the window (flat region, edge blocks, raw blocks): general units, DS_HOPS of them with
+        // consistent integrity bits; raw units carry no redundancy, so a position whose first unit is not raw is preferred
         int reserve = -1;
-        for (int base = searchFrom; base < headEnd && guess < 0; base += 32) {
+        for (int base = subStart; base < headEnd && guess < 0; base += 32) {
           const int p = base + lane;
           bool alive = p < headEnd, firstRaw = false;
           int q = p, pat = 0;
@@ -168,108 +200,118 @@ __global__ void __launch_bounds__(DS_THREADS, 4) k_decode_stream(StreamDecArgs a
         }
         if (guess < 0) guess = reserve;
       }
-      int dead = 0;
-      if (lane == 0) {
-        int n = 0, p = guess, pat = 0;
-        if (guess >= 0) {
-          while (p < subEnd) {
-            if (n >= DS_LIST) { dead = 1; break; }
-            int np;
-            const int len = hopLen(p, np);
-            if (len <= 0 || (n > 0 && !fdFollows(pat, np, version))) { dead = 1; break; }
-            list[n++] = (uint16_t)p;
-            p += len; pat = np;
-          }
-        }
-        sGuess[s] = guess; sCnt[s] = n; sExit[s] = p; sDead[s] = dead;
-      }
-      dead = __shfl_sync(FULL, dead, 0);
-      if (!dead || guess < 0 || (c == 0 && s == 0)) break;
-      searchFrom = guess + 1;
     }
+    if (lane == 0) sGuess[s] = guess;
   }
   __syncthreads();
 
-  // ---- publish the speculative exit, take the true entry, patch, count (thread 0)
-  if (tid == 0) {
-    volatile unsigned long long* ex = a.exitState;
-    const int sL = nSubs - 1;
-    const bool spec = nSubs > 0 && sGuess[sL] >= 0 && !sDead[sL];
-    const unsigned long long specExit = spec ? start + (unsigned long long)sExit[sL] : 0;
-    if (spec) ex[c] = specExit + 1;
-    bool ok = nSubs > 0;
-    long long p = 0;
-    if (c > 0) {
-      unsigned long long v;
-      while ((v = ex[c - 1]) == 0) __nanosleep(100);
-      if (v >> 63) ok = false; else p = (long long)(v - 1) - (long long)start;
-      if (p < 0) ok = false;
-    }
-    int total = 0;
-    for (int s = 0; s < nSubs && ok; s++) {
-      const int subEnd = min((s + 1) * DS_SUB, chunkLen);
-      const uint16_t* list = sListAll + s * DS_LIST;
-      const int cnt = sCnt[s];
-      int cursor = 0, np = 0;
-      bool joined = false;
-      while (p < subEnd) {
-        while (cursor < cnt && (long long)list[cursor] < p) cursor++;
-        if (cursor < cnt && (long long)list[cursor] == p) { joined = true; break; }
-        if (np == DS_PATCH || p >= testable) { ok = false; break; }
-        int pat;
-        const int len = hopLen((int)p, pat);
-        if (len <= 0) { ok = false; break; }
-        sPatch[s][np++] = (uint16_t)p;
-        p += len;
-      }
-      if (!ok) break;
-      int cs = np, first = cnt;
-      if (joined) {
-        if (sDead[s]) { ok = false; break; }                          // the true chain runs into the unit that did not parse
-        first = cursor; cs += cnt - cursor; p = sExit[s];
-      }
-      sFirst[s] = first; sNPatch[s] = np; sPre[s] = total; sTrueExit[s] = (int)p;
-      total += cs;
-    }
-    if (ok) {
-      for (int s = nSubs; s <= DS_SUBS; s++) sPre[s] = total;
-      const unsigned long long finalExit = start + (unsigned long long)p;
-      if (spec) { if (finalExit != specExit) ok = false; }            // the next chunk may have started from a wrong entry
-      else ex[c] = finalExit + 1;
-    }
-#ifdef LERC_CUSIM
-    if (std::getenv("DS_DEBUG")) {
-      std::fprintf(stderr, "[ds] chunk %d ok %d p %lld spec %d specExit %llu start %llu chunkLen %d left %lld\n", c, (int)ok, p, (int)spec, specExit, start, chunkLen, left);
-      for (int s = 0; s < nSubs; s++) std::fprintf(stderr, "   sub %d guess %d cnt %d exit %d dead %d | first %d npatch %d pre %d trueExit %d\n", s, sGuess[s], sCnt[s], sExit[s], sDead[s], sFirst[s], sNPatch[s], sPre[s], sTrueExit[s]);
-    }
-#endif
-    if (!ok) {
-      total = 0;
-      atomicOr(&a.res->status, DSF_FALLBACK);
-      if (!spec) ex[c] = 1ull << 63;
-    }
-    sOk = ok ? 1 : 0; sTotal = total;
-    lookbackPublish(a.cntState, a.groupAcc, c, (unsigned long long)total);
-  }
-  __syncthreads();
-  const int total = sTotal;
-  const bool ok = sOk != 0;
-
-  // ---- index of the chunk's first block
   if (warp == 0) {
-    const unsigned long long blk0 = lookbackExclusive(a.cntState, a.groupAcc, a.groupState, c, (unsigned long long)total, lane);
+    // ---- walk: lane s hops through sub-chunk s from its guess, recording the positions
+    {
+      const int s = lane, subEnd = min((s + 1) * DS_SUB, chunkLen);
+      uint16_t* list = sListAll + s * DS_LIST;
+      int n = 0, dead = 0;
+      int guess = s < nSubs ? sGuess[s] : -1, p = guess;
+      const int headEnd = min(s * DS_SUB + MAXU, testable);
+      for (int attempt = 0; attempt < 64 && guess >= 0; attempt++) {
+        n = 0; dead = 0; p = guess;
+        int pat = 0;
+        while (p < subEnd) {
+          if (n >= DS_LIST) { dead = 1; break; }
+          int np;
+          const int len = hopLen(p, np);
+          if (len <= 0 || (n > 0 && !fdFollows(pat, np, version))) { dead = 1; break; }
+          list[n++] = (uint16_t)p;
+          p += len; pat = np;
+        }
+        // a chain that dies was a wrong guess (the true chain of a well-formed stream does not die): the next position of the head
+        // window from which a unit parses is tried (rare; the other lanes wait)
+        if (!dead || (c == 0 && s == 0)) break;
+        int q = guess + 1;
+        for (; q < headEnd; q++) { int np; if (hopLen(q, np) > 0) break; }
+        if (q >= headEnd) break;
+        guess = q;
+      }
+      if (s < nSubs) { sCnt[s] = n; sExit[s] = p; sDead[s] = dead; }
+    }
+    __syncwarp();
+    // ---- publish the speculative exit, take the true entry, patch, count (lane 0)
+    if (lane == 0) {
+      volatile unsigned long long* ex = a.exitState;
+      const int sL = nSubs - 1;
+      const bool spec = nSubs > 0 && sGuess[sL] >= 0 && !sDead[sL];
+      const unsigned long long specExit = spec ? start + (unsigned long long)sExit[sL] : 0;
+      if (spec) ex[c] = specExit + 1;
+      bool ok = nSubs > 0;
+      long long p = 0;
+      if (c > 0) {
+        unsigned long long v;
+        while ((v = ex[c - 1]) == 0) __nanosleep(100);
+        if (v >> 63) ok = false; else p = (long long)(v - 1) - (long long)start;
+        if (p < 0) ok = false;
+      }
+      int total = 0;
+      for (int s = 0; s < nSubs && ok; s++) {
+        const int subEnd = min((s + 1) * DS_SUB, chunkLen);
+        const uint16_t* list = sListAll + s * DS_LIST;
+        const int cnt = sCnt[s];
+        int cursor = 0, np = 0;
+        bool joined = false;
+        while (p < subEnd) {
+          while (cursor < cnt && (long long)list[cursor] < p) cursor++;
+          if (cursor < cnt && (long long)list[cursor] == p) { joined = true; break; }
+          if (np == DS_PATCH || p >= testable) { ok = false; break; }
+          int pat;
+          const int len = hopLen((int)p, pat);
+          if (len <= 0) { ok = false; break; }
+          sPatch[s][np++] = (uint16_t)p;
+          p += len;
+        }
+        if (!ok) break;
+        int cs = np, first = cnt;
+        if (joined) {
+          if (sDead[s]) { ok = false; break; }                        // the true chain runs into the unit that did not parse
+          first = cursor; cs += cnt - cursor; p = sExit[s];
+        }
+        sFirst[s] = first; sNPatch[s] = np; sPre[s] = total; sTrueExit[s] = (int)p;
+        total += cs;
+      }
+      if (ok) {
+        for (int s = nSubs; s <= DS_SUBS; s++) sPre[s] = total;
+        const unsigned long long finalExit = start + (unsigned long long)p;
+        if (spec) { if (finalExit != specExit) ok = false; }          // the next chunk may have started from a wrong entry
+        else ex[c] = finalExit + 1;
+      }
+#ifdef LERC_CUSIM
+      if (std::getenv("DS_DEBUG")) {
+        std::fprintf(stderr, "[ds] chunk %d ok %d p %lld spec %d specExit %llu start %llu chunkLen %d left %lld\n", c, (int)ok, p, (int)spec, specExit, start, chunkLen, left);
+        for (int s = 0; s < nSubs; s++) std::fprintf(stderr, "   sub %d guess %d cnt %d exit %d dead %d | first %d npatch %d pre %d trueExit %d\n", s, sGuess[s], sCnt[s], sExit[s], sDead[s], sFirst[s], sNPatch[s], sPre[s], sTrueExit[s]);
+      }
+#endif
+      if (!ok) {
+        total = 0;
+        atomicOr(&a.res->status, DSF_FALLBACK);
+        if (!spec) ex[c] = 1ull << 63;
+      }
+      sOk = ok ? 1 : 0; sTotal = total;
+      lookbackPublish(a.cntState, a.groupAcc, c, (unsigned long long)total);
+    }
+    __syncwarp();
+    // ---- index of the chunk's first block
+    const int totalW = sTotal;
+    const unsigned long long blk0 = lookbackExclusive(a.cntState, a.groupAcc, a.groupState, c, (unsigned long long)totalW, lane);
     if (lane == 0) {
       sBlk0 = blk0;
-      if (c == a.nChunks - 1 && ok && blk0 + (unsigned long long)total != (unsigned long long)nBlocks) atomicOr(&a.res->status, DSF_FALLBACK | 2048);
+      if (c == a.nChunks - 1 && sOk && blk0 + (unsigned long long)totalW != (unsigned long long)nBlocks) atomicOr(&a.res->status, DSF_FALLBACK | 2048);
     }
   }
 
-  // ---- Fletcher-32 partial sums of the chunk's bytes (warps 1..7 start while warp 0 looks back)
+  // ---- Fletcher-32 partial sums of the chunk's bytes (warps 1..7 while warp 0 walks and looks back)
   unsigned long long fa = 0, fd = 0;
-  if (a.haveChecksum) {
+  if (a.haveChecksum && warp > 0) {
     const unsigned par = (unsigned)((a.regionOff + (long long)(uintptr_t)a.stream) & 1);
     const int nGroups = (d + chunkLen + 15) >> 4;
-    for (int j = tid; j < nGroups; j += DS_THREADS) {
+    for (int j = tid - 32; j < nGroups; j += DS_THREADS - 32) {
       const uint4 x = ((const uint4*)buf)[j];
       uint32_t o[4] = {x.x, x.y, x.z, x.w};
       const int r = j * 16 - d;                                         // chunk-relative byte of the group's first byte
@@ -285,35 +327,71 @@ __global__ void __launch_bounds__(DS_THREADS, 4) k_decode_stream(StreamDecArgs a
     }
   }
   __syncthreads();
+  const bool ok = sOk != 0;
 
-  // ---- decode: 8 lanes per block (lane r = block row r), 32 blocks per sweep
+  // ---- decode: 8 lanes per block (lane r = block row r); lane group j takes the blocks of sub-chunk j one after the other
   if (ok) {
     T* data = (T*)a.data;
     const bool vecOk = ((a.nCols * (int)sizeof(T)) % 16 == 0) && (((uintptr_t)data & 15) == 0);
     const unsigned long long blk0 = sBlk0;
-    const int r = tid & 7;
+    const int r = tid & 7, s = tid >> 3;
+    const int npS = sNPatch[s], firstS = sFirst[s], cs = sPre[s + 1] - sPre[s];
+    const uint16_t* list = sListAll + s * DS_LIST;
+    const float zMaxF = (float)a.zMax;
     bool fallback = false; unsigned why = 0;
-    for (int k = tid >> 3; k < total; k += DS_THREADS / 8) {
-      int s = 0;
-#pragma unroll
-      for (int j = 1; j < DS_SUBS; j++) s += (k >= sPre[j]) ? 1 : 0;
-      const int i = k - sPre[s], npS = sNPatch[s], firstS = sFirst[s], cs = sPre[s + 1] - sPre[s];
-      const uint16_t* list = sListAll + s * DS_LIST;
-      const int p = i < npS ? (int)sPatch[s][i] : (int)list[firstS + i - npS];
+    int p = cs > 0 ? (npS > 0 ? (int)sPatch[s][0] : (int)list[firstS]) : 0;
+    int ty = 0, tx = 0;
+    if (cs > 0) {
+      const unsigned long long b0 = blk0 + (unsigned long long)sPre[s];
+      if (b0 + (unsigned long long)cs > (unsigned long long)nBlocks) { fallback = true; why |= 4096; }
+      else dsDivMod((uint32_t)b0, a.nTx, a.nTxMagic, ty, tx);
+    }
+    for (int i = 0; i < cs && !fallback; i++) {
       const int i1 = i + 1;
       const int pNext = i1 < cs ? (i1 < npS ? (int)sPatch[s][i1] : (int)list[firstS + i1 - npS]) : sTrueExit[s];
-      const unsigned long long b = blk0 + (unsigned long long)k;
-      if (b >= (unsigned long long)nBlocks) { fallback = true; why |= 4096; continue; }
-      int ty, tx;
-      dsDivMod((uint32_t)b, a.nTx, a.nTxMagic, ty, tx);
       const int bi0 = ty * 8, bj0 = tx * 8;
-      const int h = min(8, a.nRows - bi0), w = min(8, a.nCols - bj0), cells = h * w;
-      T out[8];
-      unsigned whyB = 0;
-      const int len = fdDecodeBlockRow<T>(words, sb, d, p, version, tx & (version >= 5 ? 14 : 15), cells, h, w, r, a.invScale, a.zMax, out, whyB);
-      if (whyB) { fallback = true; why |= whyB; }
-      else if (p + len != pNext) { fallback = true; why |= 1024; }      // parsed with its true size the block must end where the chain continues
-      else if (r < h) fdStoreRow<T>(data + (size_t)(bi0 + r) * a.nCols + bj0, out, w, vecOk);
+      const int h = min(8, a.nRows - bi0), w = min(8, a.nCols - bj0);
+      const int patExpect = tx & (version >= 5 ? 14 : 15);
+      bool done = false;
+      if constexpr (std::is_same<T, float>::value) {
+        // hot path: full 8x8 float block, bit-stuffed with at most 16 bits, one-byte count
+        const FdWin win = fdWindow(words, (uint32_t)(d + p));
+        const uint32_t flag = (uint32_t)win.lo & 0xff;
+        const int tc = (int)(flag >> 6), osz = tc == 0 ? 4 : (tc == 1 ? 2 : 1);
+        const uint32_t bq = fdByte(win, 1 + osz), n = fdByte(win, 2 + osz);
+        const int nb = (int)(bq & 31);
+        if ((flag & 3) == 1 && !(version >= 5 && (flag & 4)) && fdPattern(flag, version) == patExpect && h == 8 && w == 8 &&
+            (bq & 0xe0) == 0x80 && n == 64 && nb >= 1 && nb <= 16 && p + 3 + osz + 8 * nb == pNext) {
+          const uint32_t ob = (uint32_t)(win.lo >> 8);
+          const double offset = tc == 0 ? (double)__uint_as_float(ob) : (tc == 1 ? (double)(int16_t)(uint16_t)ob : (double)(uint8_t)ob);
+          const FdWin rw = fdWindow(words, (uint32_t)(d + p + 3 + osz + r * nb));
+          const int s4 = 4 * nb, s2 = 2 * nb;
+          const unsigned long long m4 = s4 == 64 ? ~0ull : ((1ull << s4) - 1), m2 = (1ull << s2) - 1;
+          const uint32_t m1 = (1u << nb) - 1;
+          const unsigned long long h0 = rw.lo & m4;
+          const unsigned long long h1 = (s4 == 64 ? rw.hi : ((rw.lo >> s4) | (rw.hi << (64 - s4)))) & m4;
+          const unsigned long long q0 = h0 & m2, q1 = h0 >> s2, q2 = h1 & m2, q3 = h1 >> s2;
+          uint32_t qv[8];
+          qv[0] = (uint32_t)q0 & m1; qv[1] = (uint32_t)(q0 >> nb); qv[2] = (uint32_t)q1 & m1; qv[3] = (uint32_t)(q1 >> nb);
+          qv[4] = (uint32_t)q2 & m1; qv[5] = (uint32_t)(q2 >> nb); qv[6] = (uint32_t)q3 & m1; qv[7] = (uint32_t)(q3 >> nb);
+          float out[8];
+          // (T)min(z, zMax) == min((T)z, (T)zMax): the conversion is monotonic (Lerc2.cpp:2160; zMax is finite, checked by the host)
+#pragma unroll
+          for (int kk = 0; kk < 8; kk++) out[kk] = fminf((float)__dadd_rn(offset, __dmul_rn((double)qv[kk], a.invScale)), zMaxF);
+          fdStoreRow<float>((float*)data + (size_t)(bi0 + r) * a.nCols + bj0, out, 8, vecOk);
+          done = true;
+        }
+      }
+      if (!done) {
+        T out[8];
+        unsigned whyB = 0;
+        const int len = fdDecodeBlockRow<T>(words, sb, d, p, version, patExpect, h * w, h, w, r, a.invScale, a.zMax, out, whyB);
+        if (whyB) { fallback = true; why |= whyB; }
+        else if (p + len != pNext) { fallback = true; why |= 1024; }    // parsed with its true size the block must end where the chain continues
+        else if (r < h) fdStoreRow<T>(data + (size_t)(bi0 + r) * a.nCols + bj0, out, w, vecOk);
+      }
+      p = pNext;
+      if (++tx == a.nTx) { tx = 0; ty++; }
     }
     if (fallback) atomicOr(&a.res->status, DSF_FALLBACK | why);
   }
@@ -326,7 +404,7 @@ __global__ void __launch_bounds__(DS_THREADS, 4) k_decode_stream(StreamDecArgs a
   __syncthreads();
   if (tid == 0) {
     unsigned long long A = 0, D = 0;
-    for (int i = 0; i < DS_SUBS; i++) { A += sFA[i]; D += sFD[i]; }
+    for (int i = 0; i < DS_THREADS / 32; i++) { A += sFA[i]; D += sFD[i]; }
     if (A | D) { atomicAdd(&a.res->fletA, A); atomicAdd(&a.res->fletD, D % 65535ull); }
     __threadfence();
     const unsigned int prev = atomicAdd(&a.res->done, 1u);
