@@ -233,68 +233,84 @@ __global__ void __launch_bounds__(DS_THREADS, 4) k_decode_stream(StreamDecArgs a
         guess = q;
       }
       if (s < nSubs) { sCnt[s] = n; sExit[s] = p; sDead[s] = dead; }
-    }
-    __syncwarp();
-    // ---- publish the speculative exit, take the true entry, patch, count (lane 0)
-    if (lane == 0) {
+      __syncwarp();
+
+      // ---- publish the speculative exit, take the true entry (lane 0), then every lane joins its sub-chunk's true entry - the exit of
+      // the sub-chunk before it - with its recorded chain: usually its first position; else a few hops from the entry until a recorded
+      // position is hit.  A lane whose chain was a stranger (never joined) changes its exit; its successors are redone.
       volatile unsigned long long* ex = a.exitState;
       const int sL = nSubs - 1;
-      const bool spec = nSubs > 0 && sGuess[sL] >= 0 && !sDead[sL];
-      const unsigned long long specExit = spec ? start + (unsigned long long)sExit[sL] : 0;
-      if (spec) ex[c] = specExit + 1;
-      bool ok = nSubs > 0;
-      long long p = 0;
-      if (c > 0) {
-        unsigned long long v;
-        while ((v = ex[c - 1]) == 0) __nanosleep(100);
-        if (v >> 63) ok = false; else p = (long long)(v - 1) - (long long)start;
-        if (p < 0) ok = false;
-      }
-      int total = 0;
-      for (int s = 0; s < nSubs && ok; s++) {
-        const int subEnd = min((s + 1) * DS_SUB, chunkLen);
-        const uint16_t* list = sListAll + s * DS_LIST;
-        const int cnt = sCnt[s];
-        int cursor = 0, np = 0;
-        bool joined = false;
-        while (p < subEnd) {
-          while (cursor < cnt && (long long)list[cursor] < p) cursor++;
-          if (cursor < cnt && (long long)list[cursor] == p) { joined = true; break; }
-          if (np == DS_PATCH || p >= testable) { ok = false; break; }
-          int pat;
-          const int len = hopLen((int)p, pat);
-          if (len <= 0) { ok = false; break; }
-          sPatch[s][np++] = (uint16_t)p;
-          p += len;
+      const int guessL = __shfl_sync(FULL, guess, sL), deadL = __shfl_sync(FULL, dead, sL), exitL = __shfl_sync(FULL, p, sL);
+      const bool spec = guessL >= 0 && !deadL;
+      const unsigned long long specExit = spec ? start + (unsigned long long)exitL : 0;
+      long long entry0 = 0;
+      bool ok = true;
+      if (lane == 0) {
+        if (spec) ex[c] = specExit + 1;
+        if (c > 0) {
+          unsigned long long v;
+          while ((v = ex[c - 1]) == 0) __nanosleep(100);
+          if (v >> 63) ok = false; else entry0 = (long long)(v - 1) - (long long)start;
+          if (entry0 < 0) ok = false;
         }
-        if (!ok) break;
-        int cs = np, first = cnt;
-        if (joined) {
-          if (sDead[s]) { ok = false; break; }                        // the true chain runs into the unit that did not parse
-          first = cursor; cs += cnt - cursor; p = sExit[s];
+      }
+      ok = __shfl_sync(FULL, ok ? 1 : 0, 0) != 0;
+      const int exitSpec = p;
+      int curExit = exitSpec, first = n, npatch = 0, cs = 0, prevEntry = -1;
+      bool bad = false, pending = true;
+      for (int iter = 0; iter < 12 && pending; iter++) {
+        int e = __shfl_up_sync(FULL, curExit, 1);
+        if (lane == 0) e = (int)entry0;
+        const bool need = s < nSubs && e != prevEntry;
+#ifdef LERC_CUSIM
+        if (std::getenv("DS_DEBUG2") && need) std::fprintf(stderr, "      iter %d lane %d e %d prev %d n %d list0 %d\n", iter, lane, e, prevEntry, n, n ? (int)list[0] : -1);
+#endif
+        if (need) {
+          prevEntry = e;
+          int q = e, cursor = 0;
+          bool joined = false;
+          npatch = 0; bad = false;
+          while (q < subEnd) {
+            while (cursor < n && (int)list[cursor] < q) cursor++;
+            if (cursor < n && (int)list[cursor] == q) { joined = true; break; }
+            if (npatch == DS_PATCH || q >= testable) { bad = true; break; }
+            int pat;
+            const int len = hopLen(q, pat);
+            if (len <= 0) { bad = true; break; }
+            sPatch[s][npatch++] = (uint16_t)q;
+            q += len;
+          }
+          if (joined) { if (dead) bad = true; first = cursor; cs = npatch + n - cursor; curExit = exitSpec; }   // (dead: the true chain runs into the unit that did not parse)
+          else if (bad) curExit = exitSpec;                           // (an entry that does not parse came from a stranger before this lane: wait for its correction)
+          else { first = n; cs = npatch; curExit = q; }
         }
-        sFirst[s] = first; sNPatch[s] = np; sPre[s] = total; sTrueExit[s] = (int)p;
-        total += cs;
+        pending = __any_sync(FULL, need);
       }
-      if (ok) {
-        for (int s = nSubs; s <= DS_SUBS; s++) sPre[s] = total;
-        const unsigned long long finalExit = start + (unsigned long long)p;
-        if (spec) { if (finalExit != specExit) ok = false; }          // the next chunk may have started from a wrong entry
-        else ex[c] = finalExit + 1;
-      }
+      if (pending || __any_sync(FULL, bad && s < nSubs)) ok = false;
+      // block counts -> exclusive prefix over the sub-chunks
+      int inc = s < nSubs ? cs : 0;
+#pragma unroll
+      for (int m = 1; m < 32; m <<= 1) { const int o = __shfl_up_sync(FULL, inc, m); if (lane >= m) inc += o; }
+      int total = __shfl_sync(FULL, inc, 31);
+      const unsigned long long finalExit = start + (unsigned long long)__shfl_sync(FULL, curExit, sL);
+      if (ok && spec && finalExit != specExit) ok = false;            // the next chunk may have started from a wrong entry
+      sFirst[s] = first; sNPatch[s] = npatch; sPre[s] = inc - (s < nSubs ? cs : 0); sTrueExit[s] = curExit;
+      if (lane == 31) sPre[DS_SUBS] = total;
 #ifdef LERC_CUSIM
       if (std::getenv("DS_DEBUG")) {
-        std::fprintf(stderr, "[ds] chunk %d ok %d p %lld spec %d specExit %llu start %llu chunkLen %d left %lld\n", c, (int)ok, p, (int)spec, specExit, start, chunkLen, left);
-        for (int s = 0; s < nSubs; s++) std::fprintf(stderr, "   sub %d guess %d cnt %d exit %d dead %d | first %d npatch %d pre %d trueExit %d\n", s, sGuess[s], sCnt[s], sExit[s], sDead[s], sFirst[s], sNPatch[s], sPre[s], sTrueExit[s]);
+        if (lane == 0) std::fprintf(stderr, "[ds] chunk %d ok %d entry %lld spec %d specExit %llu final %llu start %llu chunkLen %d left %lld total %d\n", c, (int)ok, entry0, (int)spec, specExit, finalExit, start, chunkLen, left, total);
+        if (s < nSubs) std::fprintf(stderr, "   sub %d guess %d cnt %d exit %d dead %d | first %d npatch %d cs %d trueExit %d bad %d\n", s, guess, n, exitSpec, dead, first, npatch, cs, curExit, (int)bad);
       }
 #endif
-      if (!ok) {
-        total = 0;
-        atomicOr(&a.res->status, DSF_FALLBACK);
-        if (!spec) ex[c] = 1ull << 63;
+      if (lane == 0) {
+        if (ok && !spec) ex[c] = finalExit + 1;
+        if (!ok) {
+          atomicOr(&a.res->status, DSF_FALLBACK);
+          if (!spec) ex[c] = 1ull << 63;
+        }
       }
-      sOk = ok ? 1 : 0; sTotal = total;
-      lookbackPublish(a.cntState, a.groupAcc, c, (unsigned long long)total);
+      if (!ok) total = 0;
+      if (lane == 0) { sOk = ok ? 1 : 0; sTotal = total; lookbackPublish(a.cntState, a.groupAcc, c, (unsigned long long)total); }
     }
     __syncwarp();
     // ---- index of the chunk's first block
