@@ -41,10 +41,10 @@ namespace lerc {
 constexpr int DS_CHUNK = 16384;                 // stream bytes per CTA
 constexpr int DS_SUBS = 32;                     // sub-chunks per chunk, one lane of warp 0 each
 constexpr int DS_SUB = DS_CHUNK / DS_SUBS;
-constexpr int DS_LIST = DS_SUB + 8;             // recorded positions per sub-chunk (1-byte units fill it with DS_SUB)
-constexpr int DS_PATCH = 96;                    // hops the patch walk may need before it joins the recorded chain
+constexpr int DS_LIST = 136;                    // recorded positions per sub-chunk; more units than that in 512 bytes (flat regions: 1..3-byte blocks) -> DSF_FALLBACK
+constexpr int DS_PATCH = 48;                    // hops the patch walk may need before it joins the recorded chain
 constexpr int DS_HOPS = 4;                      // units a head-window position must parse to become the guess (windows without a strict candidate)
-constexpr int DS_THREADS = 256;
+constexpr int DS_THREADS = 128;
 enum { DSF_FALLBACK = 8, DSF_CHECKSUM = 2 };
 
 struct StreamDecResult {                        // device, zero-initialised per call
@@ -83,22 +83,24 @@ __device__ __forceinline__ void dsDivMod(uint32_t b, int nTx, uint32_t magic, in
   q = (int)qq; r = (int)(b - qq * (uint32_t)nTx);
 }
 
-// Header of a FULL bit-stuffed block (mode 1, no LUT, one-byte count == 64) in the window's bytes?  Returns the unit length or 0.
+// Header of a FULL bit-stuffed block (mode 1, no LUT, one-byte count == 64) at byte pointer q (shared memory)?  Returns the unit
+// length or 0; pat = its integrity bits.  Three byte loads: cheap enough to test every byte position of a head window.
 template <class T>
-__device__ __forceinline__ int dsStrictLen(const FdWin& x, int version) {
+__device__ __forceinline__ int dsStrictLen(const uint8_t* __restrict__ q, int version, int& pat) {
   constexpr int DT = PixelTraits<T>::code;
-  const uint32_t flag = (uint32_t)x.lo & 0xff;
+  const uint32_t flag = q[0];
+  pat = fdPattern(flag, version);
   if ((flag & 3) != 1 || (version >= 5 && (flag & 4))) return 0;
   const int dtUsed = offsetTypeFromCode(DT, (int)(flag >> 6));
   if (dtUsed == DT_Undefined) return 0;
   const int osz = dtSize(dtUsed);
-  const uint32_t b = fdByte(x, 1 + osz), n = fdByte(x, 2 + osz);
+  const uint32_t b = q[1 + osz], n = q[2 + osz];
   if ((b & 0xe0) != 0x80 || (b & 31) == 0 || n != 64) return 0;
   return 3 + osz + 8 * (int)(b & 31);
 }
 
 template <class T>
-__global__ void __launch_bounds__(DS_THREADS, 4) k_decode_stream(StreamDecArgs a) {
+__global__ void __launch_bounds__(DS_THREADS, 7) k_decode_stream(StreamDecArgs a) {
   using C = DecStream<T>;
   constexpr int MAXU = C::MAXU;
   extern __shared__ __align__(16) uint8_t dsSmem[];
@@ -163,15 +165,13 @@ __global__ void __launch_bounds__(DS_THREADS, 4) k_decode_stream(StreamDecArgs a
         // two full bit-stuffed blocks in a row with consecutive integrity bits (one alone can be faked by the bytes of a block's offset)
         bool hit = false;
         if (p < headEnd) {
-          const FdWin w1 = fdWindow(words, (uint32_t)(d + p));
-          const int len = dsStrictLen<T>(w1, version);
+          int pat1, pat2;
+          const int len = dsStrictLen<T>(sb + p, version, pat1);
           if (len > 0 && (long long)len <= left - p) {
             if ((long long)len == left - p) hit = true;                  // the stream's last block
             else if (p + len < testable) {
-              const FdWin w2 = fdWindow(words, (uint32_t)(d + p + len));
-              const int len2 = dsStrictLen<T>(w2, version);
-              hit = len2 > 0 && (long long)len2 <= left - p - len &&
-                    fdFollows(fdPattern((uint32_t)w1.lo & 0xff, version), fdPattern((uint32_t)w2.lo & 0xff, version), version);
+              const int len2 = dsStrictLen<T>(sb + p + len, version, pat2);
+              hit = len2 > 0 && (long long)len2 <= left - p - len && fdFollows(pat1, pat2, version);
             }
           }
         }
@@ -350,11 +350,12 @@ __global__ void __launch_bounds__(DS_THREADS, 4) k_decode_stream(StreamDecArgs a
     T* data = (T*)a.data;
     const bool vecOk = ((a.nCols * (int)sizeof(T)) % 16 == 0) && (((uintptr_t)data & 15) == 0);
     const unsigned long long blk0 = sBlk0;
-    const int r = tid & 7, s = tid >> 3;
-    const int npS = sNPatch[s], firstS = sFirst[s], cs = sPre[s + 1] - sPre[s];
-    const uint16_t* list = sListAll + s * DS_LIST;
+    const int r = tid & 7;
     const float zMaxF = (float)a.zMax;
     bool fallback = false; unsigned why = 0;
+    for (int s = tid >> 3; s < nSubs && !fallback; s += DS_THREADS / 8) {
+    const int npS = sNPatch[s], firstS = sFirst[s], cs = sPre[s + 1] - sPre[s];
+    const uint16_t* list = sListAll + s * DS_LIST;
     int p = cs > 0 ? (npS > 0 ? (int)sPatch[s][0] : (int)list[firstS]) : 0;
     int ty = 0, tx = 0;
     if (cs > 0) {
@@ -408,6 +409,7 @@ __global__ void __launch_bounds__(DS_THREADS, 4) k_decode_stream(StreamDecArgs a
       }
       p = pNext;
       if (++tx == a.nTx) { tx = 0; ty++; }
+    }
     }
     if (fallback) atomicOr(&a.res->status, DSF_FALLBACK | why);
   }
