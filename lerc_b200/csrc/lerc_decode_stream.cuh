@@ -83,20 +83,22 @@ __device__ __forceinline__ void dsDivMod(uint32_t b, int nTx, uint32_t magic, in
   q = (int)qq; r = (int)(b - qq * (uint32_t)nTx);
 }
 
-// Header of a FULL bit-stuffed block (mode 1, no LUT, one-byte count == 64) at byte pointer q (shared memory)?  Returns the unit
-// length or 0; pat = its integrity bits.  Three byte loads: cheap enough to test every byte position of a head window.
+// Bytes of a block offset per offset-type code (Lerc2.h:528-542, offsetTypeFromCode + dtSize as a nibble table; 0 = no such type)
+template <class T> struct DsOszTable {
+  static constexpr int DT = PixelTraits<T>::code;
+  static constexpr uint32_t v = DT <= DT_Byte ? 0x1111u : DT == DT_Short ? 0x0112u : DT == DT_UShort ? 0x0012u : DT == DT_Int ? 0x1224u
+                              : DT == DT_UInt ? 0x0124u : DT == DT_Float ? 0x1124u : 0x2448u;
+};
+// Header of a FULL bit-stuffed block (mode 1, no LUT, one-byte count == 64) at byte pointer q (shared memory)?  Straight-line code, three
+// byte loads: cheap enough to test every byte position of a head window.  len = the unit's length, pat = its integrity bits.
 template <class T>
-__device__ __forceinline__ int dsStrictLen(const uint8_t* __restrict__ q, int version, int& pat) {
-  constexpr int DT = PixelTraits<T>::code;
+__device__ __forceinline__ bool dsStrict(const uint8_t* __restrict__ q, int version, int& len, int& pat) {
   const uint32_t flag = q[0];
-  pat = fdPattern(flag, version);
-  if ((flag & 3) != 1 || (version >= 5 && (flag & 4))) return 0;
-  const int dtUsed = offsetTypeFromCode(DT, (int)(flag >> 6));
-  if (dtUsed == DT_Undefined) return 0;
-  const int osz = dtSize(dtUsed);
+  const int osz = (int)((DsOszTable<T>::v >> (4 * (flag >> 6))) & 15u);
   const uint32_t b = q[1 + osz], n = q[2 + osz];
-  if ((b & 0xe0) != 0x80 || (b & 31) == 0 || n != 64) return 0;
-  return 3 + osz + 8 * (int)(b & 31);
+  pat = fdPattern(flag, version);
+  len = 3 + osz + 8 * (int)(b & 31);
+  return (flag & 3) == 1 && !(version >= 5 && (flag & 4)) && osz != 0 && (b & 0xe0) == 0x80 && (b & 31) != 0 && n == 64;
 }
 
 template <class T>
@@ -150,6 +152,8 @@ __global__ void __launch_bounds__(DS_THREADS, 7) k_decode_stream(StreamDecArgs a
 
   // one unit at chunk-relative position p (speculative: an 8x8 block is assumed); 0 = does not parse
   auto hopLen = [&](int p, int& pat) -> int {
+    int len;
+    if (dsStrict<T>(sb + p, version, len, pat) && (long long)len <= left - p) return len;      // the common unit, three byte loads
     return fdHopLen<T>(fdWindow(words, (uint32_t)(d + p)), sb + p, version, left - p, tailRaw, pat);
   };
 
@@ -163,16 +167,12 @@ __global__ void __launch_bounds__(DS_THREADS, 7) k_decode_stream(StreamDecArgs a
       for (int base = subStart; base < headEnd && guess < 0; base += 32) {
         const int p = base + lane;
         // two full bit-stuffed blocks in a row with consecutive integrity bits (one alone can be faked by the bytes of a block's offset)
-        bool hit = false;
-        if (p < headEnd) {
-          int pat1, pat2;
-          const int len = dsStrictLen<T>(sb + p, version, pat1);
-          if (len > 0 && (long long)len <= left - p) {
-            if ((long long)len == left - p) hit = true;                  // the stream's last block
-            else if (p + len < testable) {
-              const int len2 = dsStrictLen<T>(sb + p + len, version, pat2);
-              hit = len2 > 0 && (long long)len2 <= left - p - len && fdFollows(pat1, pat2, version);
-            }
+        int len = 0, pat1 = 0;
+        bool hit = p < headEnd && dsStrict<T>(sb + p, version, len, pat1) && (long long)len <= left - p;
+        if (__any_sync(FULL, hit)) {
+          if (hit && (long long)len != left - p) {                       // (a block that ends the stream needs no successor)
+            int len2 = 0, pat2 = 0;
+            hit = p + len < testable && dsStrict<T>(sb + p + len, version, len2, pat2) && (long long)len2 <= left - p - len && fdFollows(pat1, pat2, version);
           }
         }
         const unsigned m = __ballot_sync(FULL, hit);
@@ -382,15 +382,13 @@ __global__ void __launch_bounds__(DS_THREADS, 7) k_decode_stream(StreamDecArgs a
           const uint32_t ob = (uint32_t)(win.lo >> 8);
           const double offset = tc == 0 ? (double)__uint_as_float(ob) : (tc == 1 ? (double)(int16_t)(uint16_t)ob : (double)(uint8_t)ob);
           const FdWin rw = fdWindow(words, (uint32_t)(d + p + 3 + osz + r * nb));
-          const int s4 = 4 * nb, s2 = 2 * nb;
-          const unsigned long long m4 = s4 == 64 ? ~0ull : ((1ull << s4) - 1), m2 = (1ull << s2) - 1;
+          // value k sits at bit k * nb of the row's 128 bits: values 0..3 in the low 64 bits (4 nb <= 64), values 4..7 in the 64 bits from bit 4 nb
           const uint32_t m1 = (1u << nb) - 1;
-          const unsigned long long h0 = rw.lo & m4;
-          const unsigned long long h1 = (s4 == 64 ? rw.hi : ((rw.lo >> s4) | (rw.hi << (64 - s4)))) & m4;
-          const unsigned long long q0 = h0 & m2, q1 = h0 >> s2, q2 = h1 & m2, q3 = h1 >> s2;
+          const int s4 = 4 * nb;
+          const unsigned long long g1 = s4 == 64 ? rw.hi : ((rw.lo >> s4) | (rw.hi << (64 - s4)));
           uint32_t qv[8];
-          qv[0] = (uint32_t)q0 & m1; qv[1] = (uint32_t)(q0 >> nb); qv[2] = (uint32_t)q1 & m1; qv[3] = (uint32_t)(q1 >> nb);
-          qv[4] = (uint32_t)q2 & m1; qv[5] = (uint32_t)(q2 >> nb); qv[6] = (uint32_t)q3 & m1; qv[7] = (uint32_t)(q3 >> nb);
+          qv[0] = (uint32_t)rw.lo & m1; qv[1] = (uint32_t)(rw.lo >> nb) & m1; qv[2] = (uint32_t)(rw.lo >> (2 * nb)) & m1; qv[3] = (uint32_t)(rw.lo >> (3 * nb)) & m1;
+          qv[4] = (uint32_t)g1 & m1; qv[5] = (uint32_t)(g1 >> nb) & m1; qv[6] = (uint32_t)(g1 >> (2 * nb)) & m1; qv[7] = (uint32_t)(g1 >> (3 * nb)) & m1;
           float out[8];
           // (T)min(z, zMax) == min((T)z, (T)zMax): the conversion is monotonic (Lerc2.cpp:2160; zMax is finite, checked by the host)
 #pragma unroll
