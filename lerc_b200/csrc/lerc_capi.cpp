@@ -24,7 +24,7 @@ struct ContextGuard {
     if (ctx && tlsUseUserStream) { saved = ctx->stream; ctx->stream = tlsUserStream; }
   }
   ~ContextGuard() {
-    if (ctx) { if (saved) ctx->stream = saved; releaseContext(ctx); }
+    if (ctx) { if (saved) { cudaStreamSynchronize(ctx->stream); ctx->stream = saved; } releaseContext(ctx); }   // (the caller's stream is drained like the context's own)
   }
 };
 
@@ -91,7 +91,7 @@ lerc_status encodeImpl(const void* pData, int version, unsigned dataType, int nD
 
   size_t offset = 0;
   uint64_t need = 0;
-  bool anyModified = false;
+  bool anyModified = false, tailFilled = false;
   for (int b = 0; b < nBands; b++) {
     EncodeBandArgs a;
     const size_t arenaMark = ctx->arena.used, pinnedMark = ctx->pinnedUsed;
@@ -117,11 +117,13 @@ lerc_status encodeImpl(const void* pData, int version, unsigned dataType, int nD
       if (nd.maskModified) a.anyMaskModified = true;
     }
     a.dOut = sizeOnly ? nullptr : dOut; a.outOffset = offset; a.outCapacity = sizeOnly ? 0 : (dOutCap > offset ? dOutCap - offset : 0);
+    a.fillEnd = (!sizeOnly && kOut == PTR_DEVICE && nBands == 1) ? pOut + outSize : nullptr;   // the single-pass encoder zero-fills behind the blob itself
     uint32_t bandBytes = 0;
     const ErrCode e = encodeBand(ctx, a, ms, bandBytes);
     if (e == BufferTooSmall && !sizeOnly && kOut != PTR_DEVICE && dOutCap < (size_t)outSize) return Failed;   // our bound was wrong: never expected
     if (e != Ok) return e;
     anyModified = a.anyMaskModified;
+    tailFilled = a.tailFilled;
     if (need + bandBytes > (uint64_t)UINT_MAX) return DimensionsTooLarge;   // Lerc.cpp:757-758
     need += bandBytes;
     offset += bandBytes;
@@ -138,7 +140,7 @@ lerc_status encodeImpl(const void* pData, int version, unsigned dataType, int nD
 
   // the API zero-fills the whole output buffer before writing (Lerc.cpp:374): blob, then zeros
   if (kOut == PTR_DEVICE) {
-    if (outSize > offset && !cudaOk(cudaMemsetAsync(pOut + offset, 0, outSize - offset, ctx->stream), "memset tail")) return Failed;
+    if (!tailFilled && outSize > offset && !cudaOk(cudaMemsetAsync(pOut + offset, 0, outSize - offset, ctx->stream), "memset tail")) return Failed;
     if (!cudaOk(cudaStreamSynchronize(ctx->stream), "sync")) return Failed;
   } else {
     if (!cudaOk(cudaMemcpyAsync(pOut, dOut, offset, cudaMemcpyDeviceToHost, ctx->stream), "D2H blob")) return Failed;
@@ -156,7 +158,10 @@ lerc_status decodeImpl(const unsigned char* pBlob, unsigned blobSize, int nMasks
   if (!(nMasks == 0 || nMasks == 1 || nMasks == nBands) || (nMasks > 0 && !pValidBytes)) return WrongParam;
 
   const PtrKind kBlob = classifyPointer(pBlob);
+  ContextGuard g;                                                       // (before the header parse: device blobs are read on the call's stream)
+  Context* ctx = g.ctx;
   ByteSource src; src.base = pBlob; src.size = blobSize; src.onDevice = kBlob == PTR_DEVICE;
+  if (src.onDevice) { if (!ctx) return Failed; src.stream = ctx->stream; }
   BlobInfo li;
   ErrCode e = getBlobInfo(src, li, nullptr, nullptr, 0);                // fast; does most checks (Lerc.cpp:418)
   if (e != Ok) return e;
@@ -174,8 +179,6 @@ lerc_status decodeImpl(const unsigned char* pBlob, unsigned blobSize, int nMasks
     std::memset(noDataValues, 0, (size_t)nBands * sizeof(double));
   }
 
-  ContextGuard g;
-  Context* ctx = g.ctx;
   if (!ctx) return Failed;
   globalStats().decodeCalls++;
 

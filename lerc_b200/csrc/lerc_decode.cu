@@ -610,9 +610,17 @@ ErrCode decodeBandT(Context* ctx, DecodeBandArgs& a, BandMaskState& ms) {
   if (!a.src) { own.base = a.hBlob ? a.hBlob : a.dBlob; own.size = (size_t)hd.blobSize; own.onDevice = a.hBlob == nullptr; }
   const BandView src{a.src ? a.src : &own, a.src ? a.srcOff : 0, (size_t)hd.blobSize};
 
-  int* dStatus = (int*)ctx->arena.alloc(16);
-  if (!dStatus) return Failed;
-  cudaMemsetAsync(dStatus, 0, 16, st);
+  // status words of the kernels other than the stream decoder (allocated and cleared on first use: the stream decoder has its own)
+  int* dStatus = nullptr;
+  auto needStatus = [&]() -> bool {
+    if (dStatus) return true;
+    dStatus = (int*)ctx->arena.alloc(16);
+    if (!dStatus) return false;
+    cudaMemsetAsync(dStatus, 0, 16, st);
+    return true;
+  };
+  // the bit mask of an all-valid / all-invalid band is only written when something reads it
+  auto bitsNow = [&]() { if (ms.pendingFill >= 0) { cudaMemsetAsync(ms.dBits, ms.pendingFill, nBits, st); ms.pendingFill = -1; } };
 
   // checksum (Lerc2.cpp:592-601); the verdict is read together with the other status bits at the end.  The single-kernel stream
   // decoder sums the blob itself, so the launch waits until it is known whether that decoder applies.
@@ -622,6 +630,7 @@ ErrCode decodeBandT(Context* ctx, DecodeBandArgs& a, BandMaskState& ms) {
     if (hd.version < 3 || checksumLaunched) return true;
     unsigned long long* dAcc = (unsigned long long*)ctx->arena.alloc(16);
     if (!dAcc) return false;
+    if (!needStatus()) return false;
     ctx->forkSide();                                   // the checksum only reads the blob: it runs beside the decode kernels
     cudaMemsetAsync(dAcc, 0, 16, ctx->stream);
     launchFletcher(ctx, blob + 14, (long long)hd.blobSize - 14, dAcc, nullptr, hd.checksum, dStatus);
@@ -636,28 +645,30 @@ ErrCode decodeBandT(Context* ctx, DecodeBandArgs& a, BandMaskState& ms) {
   if (!src.fetch(pos, 4, &nm)) return Failed;
   pos += 4;
   if (nm < 0 || ((hd.numValidPixel == 0 || hd.numValidPixel == nPix) && nm != 0)) return Failed;
-  if (hd.numValidPixel == 0) { cudaMemsetAsync(ms.dBits, 0, nBits, st); ms.havePrev = true; }
-  else if (hd.numValidPixel == nPix) { cudaMemsetAsync(ms.dBits, 0xff, nBits, st); ms.havePrev = true; }
+  if (hd.numValidPixel == 0) { ms.pendingFill = 0; ms.havePrev = true; }
+  else if (hd.numValidPixel == nPix) { ms.pendingFill = 0xff; ms.havePrev = true; }
   else if (nm > 0) {
-    if (pos + (size_t)nm > (size_t)hd.blobSize) return Failed;
+    if (pos + (size_t)nm > (size_t)hd.blobSize || !needStatus()) return Failed;
+    ms.pendingFill = -1;
     int* dRleOk = dStatus + 1;
     launchRleDecode(ctx, blob + pos, (long long)(hd.blobSize - pos), ms.dBits, (long long)nBits, dRleOk);
     pos += (size_t)nm; ms.havePrev = true;
     ms.numValid = -1;    // (the RLE status is checked below)
   } else if (!ms.havePrev) return Failed;          // "same as previous band" without a previous band (Lerc2.cpp:1002)
+  else bitsNow();                                  // the previous band's mask is this band's
   const bool rleUsed = nm > 0;
-  if (a.dValidBytes) launchBitsToBytes(ctx, ms.dBits, nPix, a.dValidBytes);           // Lerc.cpp:481, :979-995
+  if (a.dValidBytes) { bitsNow(); launchBitsToBytes(ctx, ms.dBits, nPix, a.dValidBytes); }           // Lerc.cpp:481, :979-995
 
   // Lerc2.cpp:609 zero-fills the output; when every pixel is valid and coded by the micro-block stream each one is
   // overwritten, so the fill is deferred until the fused decoder is known not to apply.
   const bool mayFast = nDepth == 1 && hd.numValidPixel == nPix && hd.microBlockSize == 8 && hd.version >= 3 && hd.zMin != hd.zMax;
   bool zeroFilled = false;
   auto zeroFill = [&]() { if (!zeroFilled) { cudaMemsetAsync(a.dData, 0, (size_t)nPix * nDepth * sizeof(T), st); zeroFilled = true; } };
-  if (!mayFast) { zeroFill(); if (!launchChecksum()) return Failed; }
+  if (!mayFast) { bitsNow(); zeroFill(); if (!needStatus() || !launchChecksum()) return Failed; }
 
   auto finish = [&]() -> ErrCode {
     int hStatus[2] = {0, 1};
-    if (!launchChecksum()) return Failed;              // (paths that did not launch it earlier)
+    if (!needStatus() || !launchChecksum()) return Failed;              // (paths that did not launch it earlier)
     ctx->joinSide();
     if (!cudaOk(cudaMemcpyAsync(hStatus, dStatus, 8, cudaMemcpyDeviceToHost, st), "D2H status")) return Failed;
     if (!cudaOk(cudaStreamSynchronize(st), "sync")) return Failed;
@@ -669,6 +680,7 @@ ErrCode decodeBandT(Context* ctx, DecodeBandArgs& a, BandMaskState& ms) {
 
   if (hd.numValidPixel == 0) return finish();
   if (hd.zMin == hd.zMax) {
+    bitsNow();
     LERC_LAUNCH(ctx, k_fill_const<T>, fillGrid, 256, 0, (T*)a.dData, ms.dBits, nPix, nDepth, (double)(T)hd.zMin, (const double*)nullptr);
     return finish();
   }
@@ -681,12 +693,17 @@ ErrCode decodeBandT(Context* ctx, DecodeBandArgs& a, BandMaskState& ms) {
     pos += 2 * len;
     std::vector<double> zr(2 * (size_t)nDepth);
     for (int i = 0; i < 2 * nDepth; i++) zr[i] = (double)r[i];
-    double* dRanges = (double*)ctx->arena.alloc(16 * (size_t)nDepth);
-    double* hRanges = (double*)ctx->pinnedAlloc(16 * (size_t)nDepth);
-    if (!dRanges || !hRanges) return Failed;
-    std::memcpy(hRanges, zr.data(), 16 * (size_t)nDepth);
-    cudaMemcpyAsync(dRanges, hRanges, 16 * (size_t)nDepth, cudaMemcpyHostToDevice, st);
-    if (0 == std::memcmp(zr.data(), zr.data() + nDepth, sizeof(double) * nDepth)) {   // every depth constant
+    const bool allConst = 0 == std::memcmp(zr.data(), zr.data() + nDepth, sizeof(double) * nDepth);
+    double* dRanges = nullptr;
+    if (allConst || nDepth > 1) {                        // the kernels read the ranges only then
+      dRanges = (double*)ctx->arena.alloc(16 * (size_t)nDepth);
+      double* hRanges = (double*)ctx->pinnedAlloc(16 * (size_t)nDepth);
+      if (!dRanges || !hRanges) return Failed;
+      std::memcpy(hRanges, zr.data(), 16 * (size_t)nDepth);
+      cudaMemcpyAsync(dRanges, hRanges, 16 * (size_t)nDepth, cudaMemcpyHostToDevice, st);
+    }
+    if (allConst) {   // every depth constant
+      bitsNow();
       LERC_LAUNCH(ctx, k_fill_const<T>, fillGrid, 256, 0, (T*)a.dData, ms.dBits, nPix, nDepth, 0.0, (const double*)dRanges);
       return finish();
     }
@@ -697,8 +714,8 @@ ErrCode decodeBandT(Context* ctx, DecodeBandArgs& a, BandMaskState& ms) {
   if (!src.fetch(pos, std::min<size_t>(2, (size_t)hd.blobSize - pos), flags)) return Failed;
   pos += 1;
   if (flags[0]) {                                                                       // one sweep
-    zeroFill();
-    if (!launchChecksum()) return Failed;
+    bitsNow(); zeroFill();
+    if (!needStatus() || !launchChecksum()) return Failed;
     const size_t len = (size_t)nDepth * sizeof(T);
     // numValidPixel of the header is trusted here only after comparing with the mask popcount on the device path below
     if (hd.numValidPixel == nPix) {
@@ -725,8 +742,8 @@ ErrCode decodeBandT(Context* ctx, DecodeBandArgs& a, BandMaskState& ms) {
     pos += 1;
     if (mode > 3 || (mode > 2 && hd.version < 6) || (mode > 1 && hd.version < 4)) return Failed;
     if (mode != IEM_Tiling) {
-      zeroFill();
-      if (!launchChecksum()) return Failed;
+      bitsNow(); zeroFill();
+      if (!needStatus() || !launchChecksum()) return Failed;
       if constexpr (sizeof(T) == 1) {
         if (!(hd.tryHuffmanInt() && (mode == IEM_DeltaHuffman || (hd.version >= 4 && mode == IEM_Huffman)))) return Failed;
         std::vector<uint8_t> tb(std::min<size_t>(2048, (size_t)hd.blobSize - pos));
@@ -768,7 +785,8 @@ ErrCode decodeBandT(Context* ctx, DecodeBandArgs& a, BandMaskState& ms) {
       if (rc < 0) return Failed;
       if (rc > 0) { globalStats().fastPathDecodes++; return Ok; }
     }
-    if (!launchChecksum()) return Failed;
+    bitsNow();
+    if (!needStatus() || !launchChecksum()) return Failed;
   }
   // ... then the multi-kernel speculative decoder (lerc_decode_fast.cuh: keeps up to 16 entry candidates per sub-chunk, repairs floods)
   FastDecArgs fdArgs;

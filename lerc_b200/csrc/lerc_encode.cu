@@ -772,38 +772,31 @@ bool encodeBandFast(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
   if (a.outCapacity < dataStart + 1) return false;                     // let the general path report BufferTooSmall exactly
 
   const size_t nGroups = (size_t)((nTiles + 31) / 32);
-  const size_t stateBytes = sizeof(FastEncResult) + 9 * 8 + (size_t)nTiles * 8 + 2 * nGroups * 8;
+  const size_t stateBytes = sizeof(FastEncResult) + (size_t)nTiles * 8 + 2 * nGroups * 8;
   uint8_t* dState = (uint8_t*)ctx->arena.alloc(stateBytes);
-  struct HostRes { FastEncResult r; unsigned long long raise[9]; };
-  HostRes* hRes = (HostRes*)ctx->pinnedAlloc(sizeof(HostRes));
+  FastEncResult* hRes = (FastEncResult*)ctx->pinnedAlloc(sizeof(FastEncResult));
   if (!dState || !hRes) return false;
   FastEncResult* dRes = (FastEncResult*)dState;
-  unsigned long long* dRaise = (unsigned long long*)(dState + sizeof(FastEncResult));
   cudaMemsetAsync(dState, 0, stateBytes, st);
-
-  // float data already on a coarser decimal grid (Lerc2.cpp:226-231, :1233-1339): test the first row only; if a
-  // candidate survives it the general path does the full scan
-  RaiseArgs ra; ra.n = 0;
-  if (isFlt) {
-    static const double kErr[9] = {1, 0.5, 0.1, 0.05, 0.01, 0.005, 0.001, 0.0005, 0.0001};
-    static const double kFac[9] = {1, 2, 10, 20, 100, 200, 1000, 2000, 10000};
-    for (int i = 0; i < 9; i++) if (kErr[i] / 2 > maxZErr) { ra.fac[ra.n] = kFac[i]; ra.n++; }
-    if (ra.n > 0) {
-      int grid = (int)std::min<long long>((a.nCols + 255) / 256, 148);
-      ctx->forkSide();                                  // independent of the fused kernel: runs beside it
-      LERC_LAUNCH(ctx, k_try_raise<T>, grid, 256, 0, (const T*)a.dData, (const uint8_t*)nullptr, 0LL, (long long)a.nCols, 1, ra, dRaise);
-      ctx->backToMain();
-    }
-  }
 
   FastEncArgs fa;
   fa.data = a.dData; fa.nRows = a.nRows; fa.nCols = a.nCols; fa.nTx = nTx; fa.nTy = nTy; fa.dt = PixelTraits<T>::code;
   fa.maxZErr = maxZErr; fa.scale = 1.0 / (2.0 * maxZErr); fa.maxZErr3 = 3.0 * maxZErr; fa.maxQ = fa.dt <= DT_UShort ? (1u << 15) - 1 : (1u << 30) - 1;         // Lerc2.h:685-703
   fa.intLossless = (!isFlt && maxZErr == 0.5) ? 1 : 0;
+  // float data already on a coarser decimal grid (Lerc2.cpp:226-231, :1233-1339): the kernel tests the first row only; if a
+  // candidate survives it the general path does the full scan
+  fa.nRaise = 0;
+  if (isFlt) {
+    static const double kErr[9] = {1, 0.5, 0.1, 0.05, 0.01, 0.005, 0.001, 0.0005, 0.0001};
+    static const double kFac[9] = {1, 2, 10, 20, 100, 200, 1000, 2000, 10000};
+    for (int i = 0; i < 9; i++) if (kErr[i] / 2 > maxZErr) { fa.raiseFac[fa.nRaise] = kFac[i]; fa.nRaise++; }
+  }
   uint8_t* blob = a.dOut + a.outOffset;
   fa.stream = blob + dataStart; fa.streamCap = a.outCapacity - dataStart; fa.regionOff = (long long)dataStart - 14;
-  fa.tileState = (unsigned long long*)(dState + sizeof(FastEncResult) + 9 * 8); fa.res = dRes;
+  fa.tileState = (unsigned long long*)(dState + sizeof(FastEncResult)); fa.res = dRes;
   fa.groupState = fa.tileState + nTiles; fa.groupAcc = fa.groupState + nGroups;   // look-back level 2: groups of 32 tiles
+  fa.blob = blob; fa.dataStart = (int)dataStart; fa.nBlobsMore = a.nBands - 1 - a.iBand; fa.blobCap = a.outCapacity;
+  fa.fillEnd = (a.nBands == 1 && a.fillEnd && a.fillEnd > blob) ? a.fillEnd : nullptr;
   {
     // persistent CTAs, tiles taken by ticket (no co-residency assumption); shared memory opt-in and occupancy once per device
     constexpr size_t smem = (size_t)EncTile<T>::SMEM;
@@ -816,59 +809,21 @@ bool encodeBandFast(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
       ctasPerSmOf[dv].store(ctasPerSm, std::memory_order_relaxed);
     }
     int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-    const long long grid = std::min<long long>(nTiles, (long long)ctasPerSm * std::max(sms, 1));
+    const long long grid = std::min<long long>(nTiles, (long long)ctasPerSm * std::max(sms, 1));   // all CTAs resident (the zero fill at the end waits for the last tile)
     LaunchScope scope_(ctx, "k_encode_tile<T>");
     k_encode_tile<T, 3><<<(unsigned)grid, ENC_THREADS, smem, ctx->stream>>>(fa); ctx->kernelLaunches++;
   }
-  ctx->joinSide();
-  if (!cudaOk(cudaMemcpyAsync(hRes, dState, sizeof(HostRes), cudaMemcpyDeviceToHost, st), "D2H fast result")) { err = Failed; return true; }
+  if (!cudaOk(cudaMemcpyAsync(hRes, dRes, sizeof(FastEncResult), cudaMemcpyDeviceToHost, st), "D2H fast result")) { err = Failed; return true; }
   if (!cudaOk(cudaStreamSynchronize(st), "sync")) { err = Failed; return true; }
+  if (!cudaOk(cudaGetLastError(), "k_encode_tile")) { err = Failed; return true; }
 
-  // ---- were the assumptions right?
-  const FastEncResult& r = hRes->r;
-  if (r.flags & (FASTF_NAN | FASTF_LUT)) return false;
-  const K minKey = (K)~r.negMinKey, maxKey = (K)r.maxKey;
-  const T lo = fromKeyHost<T>(minKey), hi = fromKeyHost<T>(maxKey);
-  const double zMin = (double)lo, zMax = (double)hi;
-  if (zMin == zMax) return false;                                        // constant image: no stream at all
-  HeaderInfo hd;
-  if (isFlt) {
-    if ((lo == (T)0 && std::signbit(lo)) || (hi == (T)0 && !std::signbit(hi))) return false;   // sign of a zero extreme depends on scan order (general path)
-    bool allInt = !(r.flags & FASTF_NOT_INT);
-    const double lim = sizeof(T) == 4 ? 8388608.0 : 9007199254740992.0;
-    allInt = allInt && zMin >= -lim && zMin <= lim && zMax >= -lim && zMax <= lim;             // Lerc.cpp:1490-1500
-    if (allInt) { if (std::max(0.5, std::floor(maxZErr)) != maxZErr) return false; hd.bIsInt = 1; }
-    for (int c = 0; c < ra.n; c++) {                                      // PruneCandidates on row 0 (Lerc2.cpp:1322-1339)
-      double m; std::memcpy(&m, &hRes->raise[c], 8);
-      if (!(m / ra.fac[c] > maxZErr / 2)) return false;                   // a candidate survived: full scan needed
-    }
-  }
-  const unsigned long long nData = r.totalBytes;
-  const size_t oneSweepBytes = sizeof(T) * (size_t)nPix;
-  if ((double)nData * 8 < (double)nPix * 1.5 && nData < 4 * oneSweepBytes && (a.nRows > 8 || a.nCols > 8)) return false;   // 16x16 retry (Lerc2.cpp:333-357)
-  if (oneSweepBytes <= nData) return false;                              // one sweep raw wins (Lerc2.cpp:364-373)
-  const unsigned long long total = dataStart + nData;
-  if (total > (unsigned long long)INT_MAX) { err = Failed; return true; }
-  bandBytes = (uint32_t)total;
-  if (total > a.outCapacity || (r.flags & FASTF_OVERFLOW)) { err = BufferTooSmall; return true; }   // Lerc.cpp:764-765
-
-  // ---- header, mask length, ranges, flag byte; checksum from the kernel's partial sums (Lerc2.cpp:1012-1064)
-  hd.version = 6; hd.nRows = a.nRows; hd.nCols = a.nCols; hd.nDepth = 1; hd.dt = PixelTraits<T>::code;
-  hd.nBlobsMore = a.nBands - 1 - a.iBand; hd.numValidPixel = (int)nPix; hd.microBlockSize = 8;
-  hd.blobSize = (int)total; hd.maxZError = maxZErr; hd.zMin = zMin; hd.zMax = zMax;
-  PrefixBytes pb; std::memset(&pb, 0, sizeof pb);
-  writeHeader(pb.b, hd);
-  size_t p = (size_t)headerBytes(6) + 4;                                  // mask byte count 0
-  std::memcpy(pb.b + p, &lo, sizeof(T)); p += sizeof(T);
-  std::memcpy(pb.b + p, &hi, sizeof(T)); p += sizeof(T);
-  pb.b[p++] = 0;                                                          // not one sweep
-  pb.n = (int)p;
-  unsigned long long A = 0, D = 0;
-  for (int i = 0; i < FAST_SLOTS; i++) { A += r.fletA[i]; D = (D + r.fletD[i]) % 65535ull; }
-  fletcherHostPartial(pb.b + 14, 0, (long long)p - 14, A, D);
-  hd.checksum = fletcherFinish(A, D, (long long)total - 14);
-  std::memcpy(pb.b + 10, &hd.checksum, 4);
-  LERC_LAUNCH(ctx, k_write_prefix, 1, 128, 0, blob, pb);
+  // ---- the verdict of the device-side finish (encFinishBand)
+  const FastEncResult& r = *hRes;
+  if (r.status == FASTST_GENERAL || r.status == FASTST_PENDING) return false;   // an assumption of the single pass failed: general encoder
+  if (r.status == FASTST_TOO_LARGE) { err = Failed; return true; }
+  bandBytes = (uint32_t)r.bandBytes;
+  if (r.status == FASTST_TOO_SMALL) { err = BufferTooSmall; return true; }       // Lerc.cpp:764-765
+  a.tailFilled = fa.fillEnd != nullptr;
 
   // validity bookkeeping the band loop expects (Lerc.cpp:659-741): this band is all valid
   ms.numValid = (int)nPix;

@@ -110,6 +110,91 @@ __device__ __forceinline__ void smemOr(uint32_t* p, uint32_t v) {
 #endif
 }
 
+// Row 0 of the image against the coarser decimal grids of Lerc2::TryRaiseMaxZError (Lerc2.cpp:1233-1339): per candidate factor the
+// largest |round(x * fac) - x * fac| of the tile's part of row 0 (the tiles of block row 0 call this; the finish compares).
+template <class T>
+__device__ __noinline__ void encRaiseRow0(const FastEncArgs& a, const T* __restrict__ row, int cols, int tid, int nThreads) {
+  double m[9];
+#pragma unroll
+  for (int c = 0; c < 9; c++) m[c] = 0;
+  for (int e = tid; e < cols; e += nThreads) {
+    const double x = (double)row[e];
+#pragma unroll
+    for (int c = 0; c < 9; c++) {
+      if (c < a.nRaise) {
+        const double z = __dmul_rn(x, a.raiseFac[c]);
+        const double dlt = fabs(__dsub_rn(floor(__dadd_rn(z, 0.5)), z));
+        if (dlt > m[c]) m[c] = dlt;           // NaN / Inf never win, as with std::max(a, NaN)
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 9; c++) {
+    if (c < a.nRaise) {
+      unsigned long long b = (unsigned long long)__double_as_longlong(m[c]);     // non-negative doubles order like integers
+      for (int s = 16; s; s >>= 1) { const unsigned long long o = __shfl_xor_sync(FULL, b, s); b = o > b ? o : b; }
+      if ((tid & 31) == 0 && b) atomicMax(&a.res->raiseMax[c], b);
+    }
+  }
+}
+
+// The finish of the band by the last CTA's thread 0: were the assumptions of the single pass right (the tests the reference makes
+// before it codes a band, Lerc2.cpp:179-381, Lerc.cpp:1490-1502)?  If so header, mask byte count, ranges, flag byte and checksum are
+// written (Lerc2.cpp:710-760, :1012-1064).  Returns FASTST_*.
+template <class T>
+__device__ __noinline__ unsigned int encFinishBand(const FastEncArgs& a) {
+  constexpr bool isFlt = PixelTraits<T>::isFloat;
+  using K = typename PixelTraits<T>::Key;
+  volatile FastEncResult* r = a.res;
+  const unsigned int flags = r->flags;
+  if (flags & (FASTF_NAN | FASTF_LUT)) return FASTST_GENERAL;
+  const K minKey = (K)~r->negMinKey, maxKey = (K)r->maxKey;
+  const T lo = fromKey<T>(minKey), hi = fromKey<T>(maxKey);
+  const double zMin = (double)lo, zMax = (double)hi;
+  if (zMin == zMax) return FASTST_GENERAL;                                 // constant image: no stream at all
+  uint8_t bIsInt = 0;
+  if (isFlt) {
+    if ((zMin == 0 && __double_as_longlong(zMin) < 0) || (zMax == 0 && __double_as_longlong(zMax) >= 0)) return FASTST_GENERAL;   // sign of a zero extreme depends on scan order
+    bool allInt = !(flags & FASTF_NOT_INT);
+    const double lim = sizeof(T) == 4 ? 8388608.0 : 9007199254740992.0;
+    allInt = allInt && zMin >= -lim && zMin <= lim && zMax >= -lim && zMax <= lim;             // Lerc.cpp:1490-1500
+    if (allInt) { const double f = floor(a.maxZErr); if ((f > 0.5 ? f : 0.5) != a.maxZErr) return FASTST_GENERAL; bIsInt = 1; }
+    for (int c = 0; c < a.nRaise; c++) {                                   // PruneCandidates on row 0 (Lerc2.cpp:1322-1339)
+      const double m = __longlong_as_double((long long)r->raiseMax[c]);
+      if (!(__ddiv_rn(m, a.raiseFac[c]) > __dmul_rn(a.maxZErr, 0.5))) return FASTST_GENERAL;   // a candidate survived: full scan needed
+    }
+  }
+  const long long nPix = (long long)a.nRows * a.nCols;
+  const unsigned long long nData = r->totalBytes;
+  const unsigned long long oneSweepBytes = sizeof(T) * (unsigned long long)nPix;
+  if ((double)nData * 8 < (double)nPix * 1.5 && nData < 4 * oneSweepBytes && (a.nRows > 8 || a.nCols > 8)) return FASTST_GENERAL;   // 16x16 retry (Lerc2.cpp:333-357)
+  if (oneSweepBytes <= nData) return FASTST_GENERAL;                       // one sweep raw wins (Lerc2.cpp:364-373)
+  const unsigned long long total = (unsigned long long)a.dataStart + nData;
+  if (total > 0x7fffffffull) return FASTST_TOO_LARGE;
+  a.res->bandBytes = total;
+  if (total > a.blobCap || (flags & FASTF_OVERFLOW)) return FASTST_TOO_SMALL;                // Lerc.cpp:764-765
+
+  uint8_t b[128];
+  for (int i = 0; i < 128; i++) b[i] = 0;
+  auto put32 = [&](int at, uint32_t v) { for (int i = 0; i < 4; i++) b[at + i] = (uint8_t)(v >> (8 * i)); };
+  auto put64 = [&](int at, double d) { const unsigned long long v = (unsigned long long)__double_as_longlong(d); for (int i = 0; i < 8; i++) b[at + i] = (uint8_t)(v >> (8 * i)); };
+  b[0] = 'L'; b[1] = 'e'; b[2] = 'r'; b[3] = 'c'; b[4] = '2'; b[5] = ' ';
+  put32(6, 6u); put32(14, (uint32_t)a.nRows); put32(18, (uint32_t)a.nCols); put32(22, 1u); put32(26, (uint32_t)nPix); put32(30, 8u);
+  put32(34, (uint32_t)total); put32(38, (uint32_t)PixelTraits<T>::code); put32(42, (uint32_t)a.nBlobsMore);
+  b[46] = 0; b[47] = bIsInt;
+  put64(50, a.maxZErr); put64(58, zMin); put64(66, zMax);                   // noDataVal, noDataValOrig stay 0
+  int p = 90 + 4;                                                           // mask byte count 0
+  { uint8_t tmp[8]; memcpy(tmp, &lo, sizeof(T)); for (int i = 0; i < (int)sizeof(T); i++) b[p + i] = tmp[i]; p += (int)sizeof(T);
+    memcpy(tmp, &hi, sizeof(T)); for (int i = 0; i < (int)sizeof(T); i++) b[p + i] = tmp[i]; p += (int)sizeof(T); }
+  b[p++] = 0;                                                               // not one sweep
+  unsigned long long A = 0, D = 0;
+  for (int i = 0; i < FAST_SLOTS; i++) { A += r->fletA[i]; D = (D + r->fletD[i]) % 65535ull; }
+  fletcherHostPartial(b + 14, 0, (long long)p - 14, A, D);
+  put32(10, fletcherFinish(A, D, (long long)total - 14));
+  for (int i = 0; i < p; i++) a.blob[i] = b[i];
+  return FASTST_OK;
+}
+
 constexpr int ENC_COMPUTE = 256, ENC_THREADS = ENC_COMPUTE + 32;    // 8 compute warps + the control warp
 
 template <class T, int MINB>
@@ -166,7 +251,7 @@ __global__ void __launch_bounds__(ENC_THREADS, MINB) k_encode_tile(FastEncArgs a
       const unsigned long long tileBytes = sMailBytes[k & 1];
       const unsigned long long excl = lookbackExclusive(st, a.groupAcc, gs, tile, tileBytes, lane);
       if (lane == 0) {
-        if (tile == nTiles - 1) a.res->totalBytes = excl + tileBytes;
+        if (tile == nTiles - 1) { a.res->totalBytes = excl + tileBytes; __threadfence(); *(volatile unsigned int*)&a.res->totalReady = 1u; }
         sOffS[k & 1] = excl;
         mbarArrive(&sBarOff[k & 1]);
       }
@@ -296,6 +381,8 @@ __global__ void __launch_bounds__(ENC_THREADS, MINB) k_encode_tile(FastEncArgs a
         for (int x = tid; x < cols; x += ENC_COMPUTE) ((T*)(sIn + y * PITCH))[x] = src[(size_t)y * a.nCols + x];
       namedBarSync(1, ENC_COMPUTE);
     }
+
+    if (isFlt && a.nRaise > 0 && tyT == 0) encRaiseRow0<T>(a, (const T*)sIn, min(TW * 8, a.nCols - bx0 * 8), tid, ENC_COMPUTE);
 
     // ---- size: two threads per block (rows 0-3 / 4-7)
     for (int bb = tid >> 1; bb < TW; bb += ENC_COMPUTE / 2) {
@@ -465,6 +552,35 @@ __global__ void __launch_bounds__(ENC_THREADS, MINB) k_encode_tile(FastEncArgs a
       if (kMax > maxSeen) atomicMax(&a.res->maxKey, kMax);
     }
     if (fl & ~flagsSeen) atomicOr(&a.res->flags, fl);
+    // ---- the last CTA finishes the band: verdict, and if the single pass was right the blob's prefix and checksum
+    __threadfence();
+    if (atomicAdd(&a.res->done, 1u) == gridDim.x - 1) {
+      __threadfence();
+      const unsigned int verdict = encFinishBand<T>(a);
+      __threadfence();
+      *(volatile unsigned int*)&a.res->status = verdict;
+    }
+  }
+  // ---- zero fill behind the blob (the API zero-fills the whole output buffer, Lerc.cpp:374): every CTA a slice, as soon as the stream's
+  // length is known (all CTAs are resident: the grid is sized by occupancy)
+  if (a.fillEnd) {
+    if (tid == 0) { while (*(volatile unsigned int*)&a.res->totalReady == 0) __nanosleep(100); }
+    namedBarSync(1, ENC_COMPUTE);
+    const unsigned long long total = (unsigned long long)a.dataStart + *(volatile unsigned long long*)&a.res->totalBytes;
+    uint8_t* from = a.blob + total;
+    if (total <= a.blobCap && from < a.fillEnd) {
+      const unsigned long long n = (unsigned long long)(a.fillEnd - from);
+      const unsigned long long per = ((n + gridDim.x - 1) / gridDim.x + 15) & ~15ull;
+      const unsigned long long lo = (unsigned long long)blockIdx.x * per, hi = lo + per < n ? lo + per : n;
+      if (lo < n) {
+        uint8_t* p0 = from + lo; uint8_t* p1 = from + hi;
+        uint8_t* q0 = (uint8_t*)(((uintptr_t)p0 + 15) & ~(uintptr_t)15); if (q0 > p1) q0 = p1;
+        uint8_t* q1 = (uint8_t*)((uintptr_t)p1 & ~(uintptr_t)15); if (q1 < q0) q1 = q0;
+        for (uint8_t* q = p0 + tid; q < q0; q += ENC_COMPUTE) *q = 0;
+        for (uint4* q = (uint4*)q0 + tid; q < (uint4*)q1; q += ENC_COMPUTE) *q = make_uint4(0, 0, 0, 0);
+        for (uint8_t* q = q1 + tid; q < p1; q += ENC_COMPUTE) *q = 0;
+      }
+    }
   }
 }
 

@@ -85,10 +85,15 @@ bool readHeader(const uint8_t* src, size_t avail, HeaderInfo& h) {
 bool ByteSource::fetch(size_t off, size_t len, void* dst) const {
   if (off > size || len > size - off) return false;
   if (!onDevice) { std::memcpy(dst, base + off, len); return true; }
-  if (len > sizeof cache) return cudaMemcpy(dst, base + off, len, cudaMemcpyDeviceToHost) == cudaSuccess;
+  // on the call's stream (lerc_b200_set_stream: "ordered on the given stream like any other work"), else the legacy default stream
+  auto d2h = [&](void* to, const uint8_t* from, size_t n) {
+    if (!stream) return cudaMemcpy(to, from, n, cudaMemcpyDeviceToHost) == cudaSuccess;
+    return cudaMemcpyAsync(to, from, n, cudaMemcpyDeviceToHost, stream) == cudaSuccess && cudaStreamSynchronize(stream) == cudaSuccess;
+  };
+  if (len > sizeof cache) return d2h(dst, base + off, len);
   if (!(off >= cacheOff && off + len <= cacheOff + cacheLen)) {
     const size_t take = size - off < sizeof cache ? size - off : sizeof cache;
-    if (cudaMemcpy(cache, base + off, take, cudaMemcpyDeviceToHost) != cudaSuccess) { cacheLen = 0; return false; }
+    if (!d2h(cache, base + off, take)) { cacheLen = 0; return false; }
     cacheOff = off; cacheLen = take;
   }
   std::memcpy(dst, cache + (off - cacheOff), len);

@@ -46,6 +46,7 @@ struct ByteSource {
   const uint8_t* base = nullptr;
   size_t size = 0;
   bool onDevice = false;
+  cudaStream_t stream = nullptr;   // device blobs: the stream the call runs on (fetches are ordered behind the work that produced the blob); nullptr = legacy default stream
   bool fetch(size_t off, size_t len, void* dst) const;
   // device blobs: a small host copy of the bytes around the last fetch, so that the handful of header / mask length /
   // range / flag reads of one band cost one device-to-host copy (valid for the duration of one API call only)
@@ -134,6 +135,7 @@ struct BandMaskState {      // validity of the band being coded and of the previ
   uint8_t* dPrevBits = nullptr;
   int numValid = 0;
   bool havePrev = false;
+  int pendingFill = -1;           // decode: dBits is to be filled with this byte (all valid / all invalid) before its next use, -1 = dBits is current
 };
 
 struct EncodeBandArgs {
@@ -149,6 +151,8 @@ struct EncodeBandArgs {
   double noDataVal = 0, noDataOrig = 0;
   bool anyMaskModified;           // in/out across bands (Lerc.cpp:714-720)
   uint8_t* dOut;                  // device output buffer (whole multi-band blob), may be nullptr for size-only
+  uint8_t* fillEnd = nullptr;     // in: end of the caller's device buffer when the encoder may zero-fill behind the blob itself (one band)
+  bool tailFilled = false;        // out: it did
   size_t outCapacity;             // bytes available in dOut from outOffset
   size_t outOffset;               // where this band's blob starts
 };
