@@ -188,8 +188,11 @@ __device__ __noinline__ unsigned int encFinishBand(const FastEncArgs& a) {
     memcpy(tmp, &hi, sizeof(T)); for (int i = 0; i < (int)sizeof(T); i++) b[p + i] = tmp[i]; p += (int)sizeof(T); }
   b[p++] = 0;                                                               // not one sweep
   unsigned long long A = 0, D = 0;
-  for (int i = 0; i < FAST_SLOTS; i++) { A += r->fletA[i]; D = (D + r->fletD[i]) % 65535ull; }
-  fletcherHostPartial(b + 14, 0, (long long)p - 14, A, D);
+  for (int i = 0; i < FAST_SLOTS; i++) { A += r->fletA[i]; D += r->fletD[i]; }     // (every slot is a sum of a few hundred values below 65535)
+  for (int i = 14; i < p; i++) {                                           // the prefix's own bytes: region offsets 0 .. p - 15, no reduction needed
+    const unsigned long long c = (unsigned long long)b[i] << (((i - 14) & 1) ? 0 : 8);
+    A += c; D += (unsigned long long)((i - 14) >> 1) * c;
+  }
   put32(10, fletcherFinish(A, D, (long long)total - 14));
   for (int i = 0; i < p; i++) a.blob[i] = b[i];
   return FASTST_OK;
