@@ -13,6 +13,13 @@ One "step" = lerc_encode + lerc_decode of one synthetic raster of BASELINE.json 
   cpu_baseline  the unmodified reference (oracle/_ref/libLerc_ref.so) on the host cores, bounded sample
 With N > 1 (torchrun) every rank codes its own raster (independent objects, weak scaling, no data-path
 collective); rank 0 reports units of all ranks / max-over-ranks time.
+The default line also carries the other BASELINE configs as sub-records, measured the same way under a time budget:
+  "c5"  configs[4]: every rank codes its strip of the tiled 65536^2 raster (lerc_b200_encodeTiles / decodeTiles), then the
+        per-tile streams of all ranks are gathered over NCCL into one container (lerc_b200/tiles.py): kernel-only and
+        kernel+gather aggregate Gpixels/s, gather ms, bytes gathered, fraction of the NVLink peer bandwidth
+  "c4"  configs[3]: 8192^2 x 3 uint8 lossless (Huffman path), one raster per rank
+  "c3"  configs[2]: 16384^2 float32 x 4 bands at maxZError 0.001 (N = 1 only: 13 GB of buffers)
+(--no-sub skips them; --workload c3|c4|c5 runs one of them as the main line.)
 --impl reference times the reference's CPU implementation on the host cores and prints the same JSON line.
 --workload c5 (BASELINE configs[4]): every rank holds an 8192 x 65536 strip of the 65536^2 float32 raster (8192 tiles of
 256 x 256; 8 ranks = the whole raster) and codes it with ONE lerc_b200_encodeTiles + ONE lerc_b200_decodeTiles call per
@@ -36,6 +43,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 WORKLOADS = {
     # name: (rows, cols, nDepth, dtype code, maxZErr, description)
     "c2": (4096, 4096, 1, 6, 0.01, "4096x4096 float32 1-band encode+decode maxZError=0.01"),
+    "c3": (16384, 16384, 1, 6, 0.001, "16384x16384 float32 4-band (nBands=4) encode+decode maxZError=0.001"),
     "c4": (8192, 8192, 3, 1, 0.0, "8192x8192 nDepth=3 uint8 lossless (Huffman path)"),
     # not a BASELINE config: configs[1]'s raster at maxZError 0 = the lossless float (FPL) codec, for profiling that path
     "c2l": (4096, 4096, 1, 6, 0.0, "4096x4096 float32 1-band encode+decode maxZError=0 (lossless float codec)"),
@@ -43,9 +51,11 @@ WORKLOADS = {
     "c5": (8192, 65536, 1, 6, 0.01, "65536x65536 float32 as 256x256 tiles, 8192-row strip (8192 tiles) per GPU, encodeTiles+decodeTiles maxZError=0.01"),
 }
 TILE = 256
+BANDS = {"c3": 4}                      # bands per call (default 1)
+NVLINK_PEER_GBS = 770.0                # measured peer copy per direction (B200_PROFILING.md)
 
 
-METRIC = {"c2": "Gpixels/s encode+decode float32 @ maxZError=0.01; achieved HBM GB/s vs peak", "c2l": "Gpixels/s encode+decode float32 lossless", "c4": "Gpixels/s encode+decode uint8 nDepth=3 lossless",
+METRIC = {"c2": "Gpixels/s encode+decode float32 @ maxZError=0.01; achieved HBM GB/s vs peak", "c3": "Gpixels/s (pixels x bands) encode+decode float32 4 bands @ maxZError=0.001", "c2l": "Gpixels/s encode+decode float32 lossless", "c4": "Gpixels/s encode+decode uint8 nDepth=3 lossless",
           "c5": "Gpixels/s encode+decode float32 @ maxZError=0.01, 256x256 tiles (one blob per tile); achieved HBM GB/s vs peak"}
 
 

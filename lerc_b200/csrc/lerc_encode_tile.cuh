@@ -138,11 +138,11 @@ __device__ __noinline__ void encRaiseRow0(const FastEncArgs& a, const T* __restr
   }
 }
 
-// The finish of the band by the last CTA's thread 0: were the assumptions of the single pass right (the tests the reference makes
+// The finish of the band by warp 0 of the last CTA (all 32 lanes, converged): were the assumptions of the single pass right (the tests the reference makes
 // before it codes a band, Lerc2.cpp:179-381, Lerc.cpp:1490-1502)?  If so header, mask byte count, ranges, flag byte and checksum are
 // written (Lerc2.cpp:710-760, :1012-1064).  Returns FASTST_*.
 template <class T>
-__device__ __noinline__ unsigned int encFinishBand(const FastEncArgs& a) {
+__device__ __noinline__ unsigned int encFinishBand(const FastEncArgs& a, int lane) {
   constexpr bool isFlt = PixelTraits<T>::isFloat;
   using K = typename PixelTraits<T>::Key;
   volatile FastEncResult* r = a.res;
@@ -171,33 +171,61 @@ __device__ __noinline__ unsigned int encFinishBand(const FastEncArgs& a) {
   if (oneSweepBytes <= nData) return FASTST_GENERAL;                       // one sweep raw wins (Lerc2.cpp:364-373)
   const unsigned long long total = (unsigned long long)a.dataStart + nData;
   if (total > 0x7fffffffull) return FASTST_TOO_LARGE;
-  a.res->bandBytes = total;
+  if (lane == 0) a.res->bandBytes = total;
   if (total > a.blobCap || (flags & FASTF_OVERFLOW)) return FASTST_TOO_SMALL;                // Lerc.cpp:764-765
 
-  uint8_t b[128];
-  for (int i = 0; i < 128; i++) b[i] = 0;
-  auto put32 = [&](int at, uint32_t v) { for (int i = 0; i < 4; i++) b[at + i] = (uint8_t)(v >> (8 * i)); };
-  auto put64 = [&](int at, double d) { const unsigned long long v = (unsigned long long)__double_as_longlong(d); for (int i = 0; i < 8; i++) b[at + i] = (uint8_t)(v >> (8 * i)); };
-  b[0] = 'L'; b[1] = 'e'; b[2] = 'r'; b[3] = 'c'; b[4] = '2'; b[5] = ' ';
-  put32(6, 6u); put32(14, (uint32_t)a.nRows); put32(18, (uint32_t)a.nCols); put32(22, 1u); put32(26, (uint32_t)nPix); put32(30, 8u);
-  put32(34, (uint32_t)total); put32(38, (uint32_t)PixelTraits<T>::code); put32(42, (uint32_t)a.nBlobsMore);
-  b[46] = 0; b[47] = bIsInt;
-  put64(50, a.maxZErr); put64(58, zMin); put64(66, zMax);                   // noDataVal, noDataValOrig stay 0
-  int p = 90 + 4;                                                           // mask byte count 0
-  { uint8_t tmp[8]; memcpy(tmp, &lo, sizeof(T)); for (int i = 0; i < (int)sizeof(T); i++) b[p + i] = tmp[i]; p += (int)sizeof(T);
-    memcpy(tmp, &hi, sizeof(T)); for (int i = 0; i < (int)sizeof(T); i++) b[p + i] = tmp[i]; p += (int)sizeof(T); }
-  b[p++] = 0;                                                               // not one sweep
-  unsigned long long A = 0, D = 0;
-  for (int i = 0; i < FAST_SLOTS; i++) { A += r->fletA[i]; D += r->fletD[i]; }     // (every slot is a sum of a few hundred values below 65535)
-  for (int i = 14; i < p; i++) {                                           // the prefix's own bytes: region offsets 0 .. p - 15, no reduction needed
-    const unsigned long long c = (unsigned long long)b[i] << (((i - 14) & 1) ? 0 : 8);
-    A += c; D += (unsigned long long)((i - 14) >> 1) * c;
+  // ---- the prefix, by the whole warp: lane L owns bytes 4 L .. 4 L + 3 (everything in registers: a single thread building it in
+  // local memory takes microseconds at the very end of the kernel)
+  unsigned long long loB = 0, hiB = 0; memcpy(&loB, &lo, sizeof(T)); memcpy(&hiB, &hi, sizeof(T));
+  const unsigned long long mzB = (unsigned long long)__double_as_longlong(a.maxZErr), zMinB = (unsigned long long)__double_as_longlong(zMin), zMaxB = (unsigned long long)__double_as_longlong(zMax);
+  const int p = 90 + 4 + 2 * (int)sizeof(T) + 1;                            // header | mask byte count 0 | ranges | "not one sweep"
+  auto byteAt = [&](int i) -> uint32_t {
+    auto f32 = [&](uint32_t v, int at) { return (v >> (8 * (i - at))) & 0xffu; };
+    auto f64 = [&](unsigned long long v, int at) { return (uint32_t)(v >> (8 * (i - at))) & 0xffu; };
+    if (i < 6) return (uint32_t)"Lerc2 "[i];
+    if (i < 10) return f32(6u, 6);
+    if (i < 14) return 0u;                                                  // checksum: below
+    if (i < 18) return f32((uint32_t)a.nRows, 14);
+    if (i < 22) return f32((uint32_t)a.nCols, 18);
+    if (i < 26) return f32(1u, 22);
+    if (i < 30) return f32((uint32_t)nPix, 26);
+    if (i < 34) return f32(8u, 30);
+    if (i < 38) return f32((uint32_t)total, 34);
+    if (i < 42) return f32((uint32_t)PixelTraits<T>::code, 38);
+    if (i < 46) return f32((uint32_t)a.nBlobsMore, 42);
+    if (i < 50) return i == 47 ? (uint32_t)bIsInt : 0u;
+    if (i < 58) return f64(mzB, 50);
+    if (i < 66) return f64(zMinB, 58);
+    if (i < 74) return f64(zMaxB, 66);
+    if (i < 94) return 0u;                                                  // noDataVal, noDataValOrig, mask byte count
+    if (i < 94 + (int)sizeof(T)) return f64(loB, 94);
+    if (i < 94 + 2 * (int)sizeof(T)) return f64(hiB, 94 + (int)sizeof(T));
+    return 0u;
+  };
+  uint32_t myB[4];
+  unsigned long long A = r->fletA[lane], D = r->fletD[lane];                // FAST_SLOTS == 32: one slot per lane
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int i = 4 * lane + k;
+    myB[k] = i < p ? byteAt(i) : 0u;
+    if (i >= 14 && i < p) {                                                 // the prefix's own bytes: region offsets 0 .. p - 15
+      const unsigned long long c = (unsigned long long)myB[k] << (((i - 14) & 1) ? 0 : 8);
+      A += c; D += (unsigned long long)((i - 14) >> 1) * c;
+    }
   }
-  put32(10, fletcherFinish(A, D, (long long)total - 14));
-  for (int i = 0; i < p; i++) a.blob[i] = b[i];
+#pragma unroll
+  for (int m = 16; m; m >>= 1) { A += __shfl_xor_sync(FULL, A, m); D += __shfl_xor_sync(FULL, D, m); }
+  const uint32_t cs = fletcherFinish(A, D, (long long)total - 14);
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int i = 4 * lane + k;
+    if (i >= 10 && i < 14) myB[k] = (cs >> (8 * (i - 10))) & 0xffu;
+    if (i < p) a.blob[i] = (uint8_t)myB[k];
+  }
   return FASTST_OK;
 }
 
+static_assert(FAST_SLOTS == 32, "encFinishBand reads one checksum slot per lane");
 constexpr int ENC_COMPUTE = 256, ENC_THREADS = ENC_COMPUTE + 32;    // 8 compute warps + the control warp
 
 template <class T, int MINB>
@@ -555,13 +583,18 @@ __global__ void __launch_bounds__(ENC_THREADS, MINB) k_encode_tile(FastEncArgs a
       if (kMax > maxSeen) atomicMax(&a.res->maxKey, kMax);
     }
     if (fl & ~flagsSeen) atomicOr(&a.res->flags, fl);
-    // ---- the last CTA finishes the band: verdict, and if the single pass was right the blob's prefix and checksum
     __threadfence();
-    if (atomicAdd(&a.res->done, 1u) == gridDim.x - 1) {
+  }
+  // ---- the last CTA finishes the band (its warp 0): verdict, and if the single pass was right the blob's prefix and checksum
+  if (warp == 0) {
+    unsigned int last = 0;
+    if (lane == 0) last = atomicAdd(&a.res->done, 1u) == gridDim.x - 1 ? 1u : 0u;
+    last = __shfl_sync(FULL, last, 0);
+    if (last) {
       __threadfence();
-      const unsigned int verdict = encFinishBand<T>(a);
+      const unsigned int verdict = encFinishBand<T>(a, lane);
       __threadfence();
-      *(volatile unsigned int*)&a.res->status = verdict;
+      if (lane == 0) *(volatile unsigned int*)&a.res->status = verdict;
     }
   }
   // ---- zero fill behind the blob (the API zero-fills the whole output buffer, Lerc.cpp:374): every CTA a slice, as soon as the stream's

@@ -3,8 +3,9 @@ raster as 256 x 256 tiles, every tile its own standard Lerc2 blob; SURVEY.md sec
 
 Tiles are independent objects, so the codec needs no data-path collective: rank r codes the contiguous tile range
 shard_tiles(n_tiles, r, world).  Only the finished streams are exchanged: one fixed-size all-gather of the per-tile byte
-counts, an exclusive prefix sum for the global offsets, and one padded all-gather of the payloads (NCCL has no
-all-gather-v).  Works with any torch.distributed backend (nccl on GPUs, gloo in tests/test_tiles_gather.py).
+counts, an exclusive prefix sum for the global offsets, and the payloads straight into their final place in the container
+(one broadcast per source rank: NCCL has no all-gather-v).  Works with any torch.distributed backend (nccl on GPUs, gloo
+in tests/test_tiles_gather.py).
 """
 import torch
 import torch.distributed as dist
@@ -25,11 +26,16 @@ def offsets_from_sizes(sizes):
     return out
 
 
-def gather_container(local, local_offsets, n_tiles, group=None):
+def gather_container(local, local_offsets, n_tiles, group=None, out=None):
     """local: uint8 tensor with this rank's tile streams back to back in tile order (what lerc_b200_encodeTiles writes for the
     rank's tile range); local_offsets: its n_local + 1 byte offsets.  Returns (container with all n_tiles streams back to back
-    in global tile order, int64 offsets[n_tiles + 1]) on every rank: one all-gather of the byte counts, an exclusive prefix
-    sum, one padded all-gather of the payloads."""
+    in global tile order, int64 offsets[n_tiles + 1]) on every rank.
+
+    One fixed-size all-gather of the per-tile byte counts and an exclusive prefix sum give every rank the global offsets and
+    the byte range of every rank's streams; then every rank's streams go STRAIGHT to their final place in the container: one
+    broadcast per source rank into container[lo_r:hi_r] (NCCL has no all-gather-v; the broadcasts of one call are queued on
+    the same communicator and move exactly the bytes an all-gather-v would).  Nothing is padded, nothing is copied a second
+    time.  `out`: optional preallocated uint8 tensor for the container (at least the total size)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     lo, hi = shard_tiles(n_tiles, rank, world)
@@ -40,26 +46,30 @@ def gather_container(local, local_offsets, n_tiles, group=None):
     my_sizes = torch.zeros(max_tiles, dtype=torch.int64, device=device)
     my_sizes[: hi - lo] = off[1:] - off[:-1]
     if world == 1:
-        all_sizes = [my_sizes]
+        all_sizes = my_sizes[None, :]
     else:
-        all_sizes = [torch.empty_like(my_sizes) for _ in range(world)]
-        dist.all_gather(all_sizes, my_sizes, group=group)
+        parts = [torch.empty_like(my_sizes) for _ in range(world)]           # (a few KB: the list form works with every backend)
+        dist.all_gather(parts, my_sizes, group=group)
+        all_sizes = torch.stack(parts)
     # per-tile sizes in global tile order
     counts = [shard_tiles(n_tiles, r, world)[1] - shard_tiles(n_tiles, r, world)[0] for r in range(world)]
-    sizes = torch.cat([all_sizes[r][: counts[r]] for r in range(world)])
+    sizes = torch.cat([all_sizes[r, : counts[r]] for r in range(world)])
     offsets = offsets_from_sizes(sizes)
-    rank_bytes = torch.stack([a.sum() for a in all_sizes]).tolist()
+    rank_bytes = all_sizes.sum(dim=1).tolist()                    # (one small device-to-host read: the byte range of every rank)
     assert rank_bytes[rank] <= local.numel()
-    pad = max(rank_bytes) if rank_bytes else 0
-    mine = torch.zeros(max(pad, 1), dtype=torch.uint8, device=device)
-    mine[: rank_bytes[rank]] = local[: rank_bytes[rank]]
-    if world == 1:
-        parts = [mine]
-    else:
-        parts = [torch.empty_like(mine) for _ in range(world)]
-        dist.all_gather(parts, mine, group=group)
-    container = torch.cat([parts[r][: rank_bytes[r]] for r in range(world)])
-    assert container.numel() == int(offsets[-1].item())
+    total = int(sum(rank_bytes))
+    container = out[:total] if out is not None else torch.empty(total, dtype=torch.uint8, device=device)
+    start = 0
+    works = []
+    for r in range(world):
+        piece = container[start:start + rank_bytes[r]]
+        if r == rank:
+            piece.copy_(local[: rank_bytes[r]])
+        if world > 1 and rank_bytes[r] > 0:
+            works.append(dist.broadcast(piece, src=dist.get_global_rank(group, r) if group is not None else r, group=group, async_op=True))
+        start += rank_bytes[r]
+    for w in works:
+        w.wait()
     return container, offsets
 
 
