@@ -169,7 +169,94 @@ def device_c2_strip(torch, rows, cols, row0, seed):
     return out
 
 
-def main_tiles(args, lib, rank, world, local_rank, warm, peak_gbs, peak_src):
+def device_c4_raster(torch, rows, cols, seed):
+    """tests/cases.py:c4_raster's formula on the device: three smooth sinusoid fields + N(0, 2), clipped to uint8, depth-interleaved"""
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    out = torch.empty((rows, cols, 3), dtype=torch.uint8, device="cuda")
+    xx = torch.arange(cols, dtype=torch.float32, device="cuda")[None, :]
+    for r0 in range(0, rows, 1024):
+        r1 = min(rows, r0 + 1024)
+        yy = torch.arange(r0, r1, dtype=torch.float32, device="cuda")[:, None]
+        ch = [128 + 100 * torch.sin(xx / 53) * torch.cos(yy / 71), 128 + 90 * torch.sin(xx / 31 + 1) * torch.cos(yy / 47), 100 + 80 * torch.cos(xx / 91) * torch.sin(yy / 23)]
+        for c in range(3):
+            z = ch[c] + torch.randn((r1 - r0, cols), dtype=torch.float32, device="cuda", generator=g) * 2.0
+            out[r0:r1, :, c] = z.round().clamp(0, 255).to(torch.uint8)
+    return out
+
+
+def bench_raster_sub(lib, workload, steps, rank, world, peak_gbs):
+    """One of the whole-raster BASELINE configs as a sub-record of the default line: device-generated raster, device pointers through
+    the C ABI, CUDA events around `steps` encode+decode steps (max over ranks), dominant kernel from an instrumented pass."""
+    import torch
+    import torch.distributed as dist
+    import lerc_b200
+    rows, cols, depth, dt, mz, desc = WORKLOADS[workload]
+    bands = BANDS.get(workload, 1)
+    enc, dec = lib.f["encode"], lib.f["decode"]
+    if workload == "c4":
+        d_img = device_c4_raster(torch, rows, cols, 7 + rank)
+    else:
+        d_img = torch.stack([device_c2_strip(torch, rows, cols, 0, 1234 + b + 16 * rank) for b in range(bands)])
+    raw_bytes = d_img.numel() * d_img.element_size()
+    cap = min(raw_bytes + raw_bytes // 8 + 4096, 0xF0000000)                  # (outBufferSize is a 32-bit count)
+    d_blob = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    d_dec = torch.empty_like(d_img)
+    n_written = C.c_uint(0)
+    stream = torch.cuda.current_stream()
+    lerc_b200.set_stream(stream.cuda_stream, True)
+    tight = [cap]
+
+    def step():
+        st = enc(d_img.data_ptr(), dt, depth, cols, rows, bands, 0, None, mz, d_blob.data_ptr(), tight[0], C.addressof(n_written))
+        assert st == 0, f"{workload}: lerc_encode status {st}"
+        st = dec(d_blob.data_ptr(), n_written.value, 0, None, depth, cols, rows, bands, dt, d_dec.data_ptr())
+        assert st == 0, f"{workload}: lerc_decode status {st}"
+        return n_written.value
+
+    blob_bytes = step()
+    tight[0] = min(cap, int(blob_bytes * 1.02) + 65536)
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches0 = lerc_b200.stats()[0]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches = lerc_b200.stats()[0] - launches0
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / steps
+    err = float((d_dec.double() - d_img.double()).abs().max().item())
+    assert err <= max(mz, 0.5 if dt < 6 else 0) * 1.1 + 1e-12, f"{workload}: round trip error {err} exceeds maxZError {mz}"
+    lerc_b200.kernel_times(reset=True)
+    lerc_b200.profile(True)
+    step()
+    torch.cuda.synchronize()
+    lerc_b200.profile(False)
+    kt = lerc_b200.kernel_times(reset=True)
+    top_name, (top_cnt, top_ms) = max(kt.items(), key=lambda kv: kv[1][1])
+    n_px = rows * cols * bands
+    algo = 2 * (raw_bytes + blob_bytes)                                        # both directions: raster + blob moved once each
+    rec = {"workload": desc, "value": world * n_px / (ms * 1e-3) / 1e9, "unit": "Gpixels/s", "ms_per_step": ms, "steps": steps, "n_gpus": world,
+           "blob_bytes": blob_bytes, "compression_ratio": raw_bytes / blob_bytes, "gpu_launches_per_step": launches / steps,
+           "step_frac": algo / (ms * 1e-3) / 1e9 / peak_gbs, "dominant_kernel": top_name, "dominant_kernel_ms_per_step": top_ms,
+           "kernels": {n: round(m, 4) for n, (c, m) in sorted(kt.items(), key=lambda kv: -kv[1][1])[:6]},
+           "data": "synthetic, generated on the device (bench.py)", "sharding": "one raster per rank" if world > 1 else "single GPU"}
+    del d_img, d_blob, d_dec
+    torch.cuda.empty_cache()
+    return rec
+
+
+def main_tiles(args, lib, rank, world, local_rank, warm, peak_gbs, peak_src, sub=False):
     import torch
     import torch.distributed as dist
     import lerc_b200
@@ -253,24 +340,47 @@ def main_tiles(args, lib, rank, world, local_rank, warm, peak_gbs, peak_src):
                 "step_frac": (2 * algo_bytes) / (ms_per_step * 1e-3) / 1e9 / peak_gbs,
                 "kernels": {n: {"launches_per_step": c / PROF, "ms_per_step": m / PROF} for n, (c, m) in sorted(kt.items(), key=lambda kv: -kv[1][1])[:10]}}
 
-    # ---- the all-gather of the per-tile streams (only exchange step of the path; reported beside the codec time)
+    # ---- the gather of the per-tile streams of all ranks into one container (the only exchange step of the path; reported beside
+    # the codec time): sizes all-gather + prefix sum + every rank's streams straight into their place (lerc_b200/tiles.py)
     gather = None
-    if args.gather:
+    if args.gather or sub:
         torch.cuda.synchronize()
+        total_guess = int(blob_bytes * world * 1.1) + (1 << 20)
+        d_cont = torch.empty(total_guess, dtype=torch.uint8, device="cuda")
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        container, offsets = gather_container(d_out[:blob_bytes], d_off, n_tiles * world)      # warm-up
+        container, offsets = gather_container(d_out[:blob_bytes], d_off, n_tiles * world, out=d_cont)      # warm-up
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         g0.record(stream)
-        container, offsets = gather_container(d_out[:blob_bytes], d_off, n_tiles * world)
+        for _ in range(3):
+            container, offsets = gather_container(d_out[:blob_bytes], d_off, n_tiles * world, out=d_cont)
         g1.record(stream)
         torch.cuda.synchronize()
-        tg = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device="cuda")
+        tg = torch.tensor([g0.elapsed_time(g1) / 3], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(tg, op=dist.ReduceOp.MAX)
-        gather = {"ms": float(tg.item()), "container_bytes": int(container.numel()), "tiles": int(offsets.numel() - 1)}
-        del container
+        g_ms = float(tg.item())
+        cont_bytes = int(container.numel())
+        ingress = cont_bytes - blob_bytes                                       # bytes that enter this GPU over NVLink
+        gather = {"ms": g_ms, "container_bytes": cont_bytes, "tiles": int(offsets.numel() - 1), "comm_nranks": world,
+                  "ingress_bytes_per_gpu": ingress, "ingress_gbs_per_gpu": ingress / (g_ms * 1e-3) / 1e9 if g_ms > 0 else None,
+                  "frac_of_nvlink_peer": (ingress / (g_ms * 1e-3) / 1e9 / NVLINK_PEER_GBS) if (g_ms > 0 and world > 1) else None,
+                  "nvlink_peer_gbs": NVLINK_PEER_GBS,
+                  "kernel_plus_gather_gpixels": world * n_px / ((ms_per_step + g_ms) * 1e-3) / 1e9,
+                  "limiter": "gather (NVLink ingress)" if (world > 1 and g_ms > ms_per_step) else "codec kernels"}
+        del container, d_cont
+    if sub:
+        rec = {"workload": desc if rows == 8192 else desc.replace("8192-row strip (8192 tiles)", f"{rows}-row strip ({n_tiles} tiles)"),
+               "value": value, "unit": "Gpixels/s", "per_gpu_gpixels": value / world, "ms_per_step": ms_per_step, "steps": args.steps, "n_gpus": world, "tiles_per_gpu": n_tiles,
+               "blob_bytes_per_gpu": blob_bytes, "fused_encodes_per_step": fast_enc, "batch_decodes_per_step": fast_dec, "gpu_launches_per_step": launches / args.steps,
+               "step_frac": roofline["step_frac"], "dominant_kernel": roofline["kernel"], "dominant_kernel_frac": roofline["frac"],
+               "kernels": {n: round(v["ms_per_step"], 4) for n, v in roofline["kernels"].items()}, "gather": gather,
+               "sharding": "contiguous tile rows per rank; codec without collective; streams gathered over NCCL", "data": "synthetic, generated on the device"}
+        lerc_b200.set_stream(0, False)
+        del d_img, d_out, d_dec
+        torch.cuda.empty_cache()
+        return rec
 
     # ---- end to end: pinned host buffers through the same calls
     lerc_b200.set_stream(0, False)
@@ -336,6 +446,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gather", action="store_true", help="c5: also time the all-gather of the per-tile streams")
     ap.add_argument("--strip-rows", type=int, default=0, help="c5: rows of the per-rank strip (multiple of 256; default 8192)")
+    ap.add_argument("--no-sub", action="store_true", help="default workload: skip the c3 / c4 / c5 sub-records")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -370,6 +481,15 @@ def main():
     assert lib is not None, "lerc_b200/libLerc.so.4 missing: run python __graft_entry__.py"
     if args.workload == "c5":
         return main_tiles(args, lib, rank, world, local_rank, warm, peak_gbs, peak_src)
+    if args.workload in ("c3", "c4"):                                   # the big rasters: device-generated, one buffer set (far larger than L2)
+        rec = bench_raster_sub(lib, args.workload, max(3, min(args.steps, 10)), rank, world, peak_gbs)
+        if rank == 0:
+            print(json.dumps({"metric": METRIC[args.workload], "value": rec["value"], "unit": "Gpixels/s", "n_gpus": world, "steps": rec["steps"], "warmup": 3,
+                              "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64" if dt >= 6 else "u8",
+                              "data": "synthetic", "config": {"workload": desc}, "e2e": None, "gpu_launches": int(rec["gpu_launches_per_step"] * rec["steps"]), "record": rec}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
     enc, dec = lib.f["encode"], lib.f["decode"]
     ts = np.dtype(DT_NP[dt]).itemsize
     raw_bytes = n_px * depth * ts
@@ -465,6 +585,7 @@ def main():
     algo_table = {
         "k_encode_tile": (raw_bytes + blob_bytes, "raster read once + block stream written once"),
         "k_encode_fused": (raw_bytes + blob_bytes, "raster read once + block stream written once"),
+        "k_decode_stream": (raw_bytes + blob_bytes, "block stream read once + raster written once"),
         "k_dec_blocks": (raw_bytes + blob_bytes, "block stream read once + raster written once"),
         "k_dec_walk": (blob_bytes, "block stream headers (bounded by the stream size)"),
         "k_dec_candidates": (blob_bytes, "block stream (bounded by the stream size)"),
@@ -532,6 +653,22 @@ def main():
            "h2d_bytes_per_step": raw_bytes + nb, "d2h_bytes_per_step": nb + raw_bytes, "timer": "host wall clock around the synchronous C-API calls"}
     assert np.abs(h_out.numpy().astype(np.float64) - h_in[(E2E - 1) % 2].numpy().astype(np.float64)).max() <= max(mz, 0.5 if dt < 6 else 0) * 1.1 + 1e-12
 
+    # ---- the other BASELINE configs as sub-records (every rank takes part: c5 gathers over NCCL, c4 is one raster per rank)
+    subs = {}
+    if args.workload == "c2" and not args.no_sub:
+        import copy
+        sub_args = copy.copy(args)
+        sub_args.steps, sub_args.gather = 5, True
+        for name in ("c5", "c4", "c3"):
+            try:
+                if name == "c5":
+                    subs[name] = main_tiles(sub_args, lib, rank, world, local_rank, warm, peak_gbs, peak_src, sub=True)
+                elif name == "c4" or world == 1:
+                    subs[name] = bench_raster_sub(lib, name, 5 if name == "c4" else 3, rank, world, peak_gbs)
+            except Exception as ex:                                      # a sub-record must not take the headline down with it
+                subs[name] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
+                torch.cuda.empty_cache()
+
     if rank == 0:
         cpu = None
         if world >= 1 and not args.no_cpu_baseline and args.gpus == 1:
@@ -543,6 +680,7 @@ def main():
                            "l2": f"{NBUF} rotating raster/blob/output sets ({NBUF * (2 * raw_bytes + blob_bytes) // 2**20} MiB touched between reuses) > 126 MB L2",
                            "sharding": "one independent raster per rank, no data-path collective" if world > 1 else "single GPU"},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
+        line.update(subs)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
