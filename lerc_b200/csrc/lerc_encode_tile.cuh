@@ -145,10 +145,19 @@ template <class T>
 __device__ __noinline__ unsigned int encFinishBand(const FastEncArgs& a, int lane) {
   constexpr bool isFlt = PixelTraits<T>::isFloat;
   using K = typename PixelTraits<T>::Key;
-  volatile FastEncResult* r = a.res;
-  const unsigned int flags = r->flags;
+  // the result block in one round of loads (80 words, three per lane), fields by shuffle: a chain of dependent reads from L2 would cost
+  // microseconds at the very end of the kernel
+  static_assert(sizeof(FastEncResult) == 640 && offsetof(FastEncResult, raiseMax) == 68 * 8 && offsetof(FastEncResult, fletA) == 32 && offsetof(FastEncResult, fletD) == 288, "field map below");
+  const volatile unsigned long long* rw = (const volatile unsigned long long*)a.res;
+  const unsigned long long w0 = rw[lane], w1 = rw[32 + lane], w2 = lane < 16 ? rw[64 + lane] : 0ull;
+  auto word = [&](int i) -> unsigned long long {                          // (all three shuffles by every lane: the index may differ between lanes)
+    const unsigned long long x0 = __shfl_sync(FULL, w0, i & 31), x1 = __shfl_sync(FULL, w1, i & 31), x2 = __shfl_sync(FULL, w2, i & 31);
+    return i < 32 ? x0 : (i < 64 ? x1 : x2);
+  };
+  const unsigned long long rTotalBytes = word(0), rNegMinKey = word(1), rMaxKey = word(2);
+  const unsigned int flags = (unsigned int)word(3);
   if (flags & (FASTF_NAN | FASTF_LUT)) return FASTST_GENERAL;
-  const K minKey = (K)~r->negMinKey, maxKey = (K)r->maxKey;
+  const K minKey = (K)~rNegMinKey, maxKey = (K)rMaxKey;
   const T lo = fromKey<T>(minKey), hi = fromKey<T>(maxKey);
   const double zMin = (double)lo, zMax = (double)hi;
   if (zMin == zMax) return FASTST_GENERAL;                                 // constant image: no stream at all
@@ -160,12 +169,12 @@ __device__ __noinline__ unsigned int encFinishBand(const FastEncArgs& a, int lan
     allInt = allInt && zMin >= -lim && zMin <= lim && zMax >= -lim && zMax <= lim;             // Lerc.cpp:1490-1500
     if (allInt) { const double f = floor(a.maxZErr); if ((f > 0.5 ? f : 0.5) != a.maxZErr) return FASTST_GENERAL; bIsInt = 1; }
     for (int c = 0; c < a.nRaise; c++) {                                   // PruneCandidates on row 0 (Lerc2.cpp:1322-1339)
-      const double m = __longlong_as_double((long long)r->raiseMax[c]);
+      const double m = __longlong_as_double((long long)word(68 + c));
       if (!(__ddiv_rn(m, a.raiseFac[c]) > __dmul_rn(a.maxZErr, 0.5))) return FASTST_GENERAL;   // a candidate survived: full scan needed
     }
   }
   const long long nPix = (long long)a.nRows * a.nCols;
-  const unsigned long long nData = r->totalBytes;
+  const unsigned long long nData = rTotalBytes;
   const unsigned long long oneSweepBytes = sizeof(T) * (unsigned long long)nPix;
   if ((double)nData * 8 < (double)nPix * 1.5 && nData < 4 * oneSweepBytes && (a.nRows > 8 || a.nCols > 8)) return FASTST_GENERAL;   // 16x16 retry (Lerc2.cpp:333-357)
   if (oneSweepBytes <= nData) return FASTST_GENERAL;                       // one sweep raw wins (Lerc2.cpp:364-373)
@@ -203,7 +212,7 @@ __device__ __noinline__ unsigned int encFinishBand(const FastEncArgs& a, int lan
     return 0u;
   };
   uint32_t myB[4];
-  unsigned long long A = r->fletA[lane], D = r->fletD[lane];                // FAST_SLOTS == 32: one slot per lane
+  unsigned long long A = word(4 + lane), D = word(36 + lane);                // FAST_SLOTS == 32: one slot per lane (words 4..35, 36..67)
 #pragma unroll
   for (int k = 0; k < 4; k++) {
     const int i = 4 * lane + k;
@@ -591,10 +600,9 @@ __global__ void __launch_bounds__(ENC_THREADS, MINB) k_encode_tile(FastEncArgs a
     if (lane == 0) last = atomicAdd(&a.res->done, 1u) == gridDim.x - 1 ? 1u : 0u;
     last = __shfl_sync(FULL, last, 0);
     if (last) {
-      __threadfence();
+      __threadfence();                                               // (acquire: the other CTAs' results)
       const unsigned int verdict = encFinishBand<T>(a, lane);
-      __threadfence();
-      if (lane == 0) *(volatile unsigned int*)&a.res->status = verdict;
+      if (lane == 0) a.res->status = verdict;                          // read by the host after the kernel
     }
   }
   // ---- zero fill behind the blob (the API zero-fills the whole output buffer, Lerc.cpp:374): every CTA a slice, as soon as the stream's
