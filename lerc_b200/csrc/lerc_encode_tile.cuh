@@ -183,42 +183,45 @@ __device__ __noinline__ unsigned int encFinishBand(const FastEncArgs& a, int lan
   if (lane == 0) a.res->bandBytes = total;
   if (total > a.blobCap || (flags & FASTF_OVERFLOW)) return FASTST_TOO_SMALL;                // Lerc.cpp:764-765
 
-  // ---- the prefix, by the whole warp: lane L owns bytes 4 L .. 4 L + 3 (everything in registers: a single thread building it in
-  // local memory takes microseconds at the very end of the kernel)
+  // ---- the prefix: every lane stores one header field (16-bit pieces: all fields start at even offsets) into a shared-memory image,
+  // then lane L owns bytes 4 L .. 4 L + 3: checksum contribution, store.  (A single thread building the prefix byte by byte in local
+  // memory, or a byte-wise field search per lane, costs ~10 us at the very end of the kernel.)
+  __shared__ __align__(16) uint16_t sHdr[64];
+  sHdr[lane] = 0; sHdr[32 + lane] = 0;
+  __syncwarp();
   unsigned long long loB = 0, hiB = 0; memcpy(&loB, &lo, sizeof(T)); memcpy(&hiB, &hi, sizeof(T));
-  const unsigned long long mzB = (unsigned long long)__double_as_longlong(a.maxZErr), zMinB = (unsigned long long)__double_as_longlong(zMin), zMaxB = (unsigned long long)__double_as_longlong(zMax);
   const int p = 90 + 4 + 2 * (int)sizeof(T) + 1;                            // header | mask byte count 0 | ranges | "not one sweep"
-  auto byteAt = [&](int i) -> uint32_t {
-    auto f32 = [&](uint32_t v, int at) { return (v >> (8 * (i - at))) & 0xffu; };
-    auto f64 = [&](unsigned long long v, int at) { return (uint32_t)(v >> (8 * (i - at))) & 0xffu; };
-    if (i < 6) return (uint32_t)"Lerc2 "[i];
-    if (i < 10) return f32(6u, 6);
-    if (i < 14) return 0u;                                                  // checksum: below
-    if (i < 18) return f32((uint32_t)a.nRows, 14);
-    if (i < 22) return f32((uint32_t)a.nCols, 18);
-    if (i < 26) return f32(1u, 22);
-    if (i < 30) return f32((uint32_t)nPix, 26);
-    if (i < 34) return f32(8u, 30);
-    if (i < 38) return f32((uint32_t)total, 34);
-    if (i < 42) return f32((uint32_t)PixelTraits<T>::code, 38);
-    if (i < 46) return f32((uint32_t)a.nBlobsMore, 42);
-    if (i < 50) return i == 47 ? (uint32_t)bIsInt : 0u;
-    if (i < 58) return f64(mzB, 50);
-    if (i < 66) return f64(zMinB, 58);
-    if (i < 74) return f64(zMaxB, 66);
-    if (i < 94) return 0u;                                                  // noDataVal, noDataValOrig, mask byte count
-    if (i < 94 + (int)sizeof(T)) return f64(loB, 94);
-    if (i < 94 + 2 * (int)sizeof(T)) return f64(hiB, 94 + (int)sizeof(T));
-    return 0u;
-  };
-  uint32_t myB[4];
+  {
+    unsigned long long v = 0; int at = -1, nh = 0;                          // value, byte offset, 16-bit pieces
+    switch (lane) {
+      case 0: v = 0x203263'72654cull; at = 0; nh = 3; break;               // "Lerc2 "
+      case 1: v = 6; at = 6; nh = 2; break;                                 // version
+      case 2: v = (unsigned)a.nRows; at = 14; nh = 2; break;
+      case 3: v = (unsigned)a.nCols; at = 18; nh = 2; break;
+      case 4: v = 1; at = 22; nh = 2; break;                                // nDepth
+      case 5: v = (unsigned)nPix; at = 26; nh = 2; break;                   // numValidPixel
+      case 6: v = 8; at = 30; nh = 2; break;                                // microBlockSize
+      case 7: v = (unsigned)total; at = 34; nh = 2; break;                  // blobSize
+      case 8: v = (unsigned)PixelTraits<T>::code; at = 38; nh = 2; break;
+      case 9: v = (unsigned)a.nBlobsMore; at = 42; nh = 2; break;
+      case 10: v = (unsigned long long)bIsInt << 8; at = 46; nh = 1; break; // bPassNoDataValues = 0, bIsInt
+      case 11: v = (unsigned long long)__double_as_longlong(a.maxZErr); at = 50; nh = 4; break;
+      case 12: v = (unsigned long long)__double_as_longlong(zMin); at = 58; nh = 4; break;
+      case 13: v = (unsigned long long)__double_as_longlong(zMax); at = 66; nh = 4; break;
+      case 14: v = loB; at = 94; nh = (int)sizeof(T) / 2; break;            // ranges (noDataVal, noDataValOrig, mask byte count stay 0)
+      case 15: v = hiB; at = 94 + (int)sizeof(T); nh = (int)sizeof(T) / 2; break;
+      default: break;
+    }
+    for (int j = 0; j < nh; j++) sHdr[at / 2 + j] = (uint16_t)(v >> (16 * j));
+  }
+  __syncwarp();
+  const uint32_t myW = ((const uint32_t*)sHdr)[lane];
   unsigned long long A = word(4 + lane), D = word(36 + lane);                // FAST_SLOTS == 32: one slot per lane (words 4..35, 36..67)
 #pragma unroll
   for (int k = 0; k < 4; k++) {
     const int i = 4 * lane + k;
-    myB[k] = i < p ? byteAt(i) : 0u;
     if (i >= 14 && i < p) {                                                 // the prefix's own bytes: region offsets 0 .. p - 15
-      const unsigned long long c = (unsigned long long)myB[k] << (((i - 14) & 1) ? 0 : 8);
+      const unsigned long long c = (unsigned long long)((myW >> (8 * k)) & 0xffu) << (((i - 14) & 1) ? 0 : 8);
       A += c; D += (unsigned long long)((i - 14) >> 1) * c;
     }
   }
@@ -228,8 +231,9 @@ __device__ __noinline__ unsigned int encFinishBand(const FastEncArgs& a, int lan
 #pragma unroll
   for (int k = 0; k < 4; k++) {
     const int i = 4 * lane + k;
-    if (i >= 10 && i < 14) myB[k] = (cs >> (8 * (i - 10))) & 0xffu;
-    if (i < p) a.blob[i] = (uint8_t)myB[k];
+    uint32_t bk = (myW >> (8 * k)) & 0xffu;
+    if (i >= 10 && i < 14) bk = (cs >> (8 * (i - 10))) & 0xffu;
+    if (i < p) a.blob[i] = (uint8_t)bk;
   }
   return FASTST_OK;
 }
@@ -422,8 +426,6 @@ __global__ void __launch_bounds__(ENC_THREADS, MINB) k_encode_tile(FastEncArgs a
       namedBarSync(1, ENC_COMPUTE);
     }
 
-    if (isFlt && a.nRaise > 0 && tyT == 0) encRaiseRow0<T>(a, (const T*)sIn, min(TW * 8, a.nCols - bx0 * 8), tid, ENC_COMPUTE);
-
     // ---- size: two threads per block (rows 0-3 / 4-7)
     for (int bb = tid >> 1; bb < TW; bb += ENC_COMPUTE / 2) {
       const int hf = tid & 1;
@@ -508,6 +510,8 @@ __global__ void __launch_bounds__(ENC_THREADS, MINB) k_encode_tile(FastEncArgs a
     namedBarSync(1, ENC_COMPUTE);
     const uint32_t tileBytes = sOff[TW];
     if (tid == 0) nextT = (int)atomicAdd(&a.res->ticket, 1u);      // ticket of tile k + 1: in flight while this tile is packed
+    // row 0 of the image against the coarser decimal grids (block row 0 only; behind the publication, so that nobody's look-back waits for it)
+    if (isFlt && a.nRaise > 0 && tyT == 0) encRaiseRow0<T>(a, (const T*)sIn, min(TW * 8, a.nCols - bx0 * 8), tid, ENC_COMPUTE);
 
     if (tileBytes <= (uint32_t)C::STAGE_CAP) {
       // ---- the common case: one pass into this tile's staging image; it is flushed when the next tile has been packed
