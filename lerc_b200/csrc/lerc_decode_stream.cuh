@@ -428,7 +428,7 @@ __global__ void __launch_bounds__(DS_THREADS, 7) k_decode_stream(StreamDecArgs a
       __threadfence();
       const unsigned long long tA = (*(volatile unsigned long long*)&a.res->fletA + a.prefA) % 65535ull;
       const unsigned long long tD = (*(volatile unsigned long long*)&a.res->fletD % 65535ull + a.prefD) % 65535ull;
-      if (fletcherFinish(tA, tD, a.regionLen) != a.expectChecksum) atomicOr(&a.res->status, DSF_CHECKSUM);
+      if (fletcherFinishFast(tA, tD, a.regionLen) != a.expectChecksum) atomicOr(&a.res->status, DSF_CHECKSUM);
     }
   }
 }

@@ -168,9 +168,10 @@ __device__ __noinline__ unsigned int encFinishBand(const FastEncArgs& a, int lan
     const double lim = sizeof(T) == 4 ? 8388608.0 : 9007199254740992.0;
     allInt = allInt && zMin >= -lim && zMin <= lim && zMax >= -lim && zMax <= lim;             // Lerc.cpp:1490-1500
     if (allInt) { const double f = floor(a.maxZErr); if ((f > 0.5 ? f : 0.5) != a.maxZErr) return FASTST_GENERAL; bIsInt = 1; }
-    for (int c = 0; c < a.nRaise; c++) {                                   // PruneCandidates on row 0 (Lerc2.cpp:1322-1339)
-      const double m = __longlong_as_double((long long)word(68 + c));
-      if (!(__ddiv_rn(m, a.raiseFac[c]) > __dmul_rn(a.maxZErr, 0.5))) return FASTST_GENERAL;   // a candidate survived: full scan needed
+    {                                                                      // PruneCandidates on row 0 (Lerc2.cpp:1322-1339), candidate c by lane c
+      const double m = __longlong_as_double((long long)word(68 + (lane < 9 ? lane : 0)));
+      const bool survived = lane < a.nRaise && !(__ddiv_rn(m, a.raiseFac[lane < 9 ? lane : 0]) > __dmul_rn(a.maxZErr, 0.5));
+      if (__any_sync(FULL, survived)) return FASTST_GENERAL;               // a candidate survived: full scan needed
     }
   }
   const long long nPix = (long long)a.nRows * a.nCols;
@@ -227,7 +228,7 @@ __device__ __noinline__ unsigned int encFinishBand(const FastEncArgs& a, int lan
   }
 #pragma unroll
   for (int m = 16; m; m >>= 1) { A += __shfl_xor_sync(FULL, A, m); D += __shfl_xor_sync(FULL, D, m); }
-  const uint32_t cs = fletcherFinish(A, D, (long long)total - 14);
+  const uint32_t cs = fletcherFinishFast(A, D, (long long)total - 14);
 #pragma unroll
   for (int k = 0; k < 4; k++) {
     const int i = 4 * lane + k;

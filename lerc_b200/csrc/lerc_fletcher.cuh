@@ -27,4 +27,22 @@ __device__ __forceinline__ void fletcherChunk(const uint32_t (&o)[4], uint32_t& 
   S = 256u * H + L; S1 = 256u * HW + LW;
 }
 
+// x mod 65535 without a 64-bit division: 2^16 == 1 (mod 65535), so the 16-bit digits of x may simply be added
+__device__ __forceinline__ uint32_t mod65535(unsigned long long x) {
+  uint32_t s = (uint32_t)(x & 0xffff) + (uint32_t)((x >> 16) & 0xffff) + (uint32_t)((x >> 32) & 0xffff) + (uint32_t)(x >> 48);   // < 2^18
+  s = (s & 0xffff) + (s >> 16);                                            // < 2^16 + 4
+  s = (s & 0xffff) + (s >> 16);
+  return s == 65535u ? 0u : s;
+}
+// fletcherFinish (lerc_device.cuh) for device code that runs on a single warp at the end of a kernel: same value, 32-bit arithmetic
+__device__ __forceinline__ uint32_t fletcherFinishFast(unsigned long long A, unsigned long long D, long long len) {
+  const uint32_t M = 65535u;
+  const uint32_t a = mod65535(A), d = mod65535(D), m = mod65535((unsigned long long)((len + 1) >> 1));
+  uint32_t s1 = mod65535((unsigned long long)a);                            // (0xffff + a) mod M == a mod M
+  uint32_t s2 = mod65535((unsigned long long)m * a + (M - d));             // (0xffff mod M) * (m + 1) == 0
+  if (s1 == 0) s1 = M;
+  if (s2 == 0) s2 = M;
+  return (s2 << 16) | s1;
+}
+
 }  // namespace lerc
