@@ -24,7 +24,7 @@ struct ContextGuard {
     if (ctx && tlsUseUserStream) { saved = ctx->stream; ctx->stream = tlsUserStream; }
   }
   ~ContextGuard() {
-    if (ctx) { if (saved) { cudaStreamSynchronize(ctx->stream); ctx->stream = saved; } releaseContext(ctx); }   // (the caller's stream is drained like the context's own)
+    if (ctx) { if (saved) { if (ctx->drainOnRelease) cudaStreamSynchronize(ctx->stream); ctx->stream = saved; ctx->drainOnRelease = false; } releaseContext(ctx); }   // (the caller's stream is drained like the context's own)
   }
 };
 
@@ -141,11 +141,14 @@ lerc_status encodeImpl(const void* pData, int version, unsigned dataType, int nD
   // the API zero-fills the whole output buffer before writing (Lerc.cpp:374): blob, then zeros
   if (kOut == PTR_DEVICE) {
     if (!tailFilled && outSize > offset && !cudaOk(cudaMemsetAsync(pOut + offset, 0, outSize - offset, ctx->stream), "memset tail")) return Failed;
-    if (!cudaOk(cudaStreamSynchronize(ctx->stream), "sync")) return Failed;
+    // a device blob on the caller's stream (lerc_b200_set_stream) is complete in stream order (lerc_b200.h); otherwise on return
+    if (!tlsUseUserStream && !cudaOk(cudaStreamSynchronize(ctx->stream), "sync")) return Failed;
+    ctx->drainOnRelease = false;
   } else {
     if (!cudaOk(cudaMemcpyAsync(pOut, dOut, offset, cudaMemcpyDeviceToHost, ctx->stream), "D2H blob")) return Failed;
     if (outSize > offset) std::memset(pOut + offset, 0, outSize - offset);
     if (!cudaOk(cudaStreamSynchronize(ctx->stream), "sync")) return Failed;
+    ctx->drainOnRelease = false;
   }
   *nWritten = (unsigned)offset;
   return Ok;
@@ -240,6 +243,7 @@ lerc_status decodeImpl(const unsigned char* pBlob, unsigned blobSize, int nMasks
     ctx->pinnedUsed = pinnedMark;
     pos += (size_t)hd.blobSize;
   }
+  ctx->drainOnRelease = false;                                         // (every band ended with a synchronisation)
   return Ok;
 }
 

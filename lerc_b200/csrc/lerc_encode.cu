@@ -795,7 +795,7 @@ bool encodeBandFast(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
   fa.stream = blob + dataStart; fa.streamCap = a.outCapacity - dataStart; fa.regionOff = (long long)dataStart - 14;
   fa.tileState = (unsigned long long*)(dState + sizeof(FastEncResult)); fa.res = dRes;
   fa.groupState = fa.tileState + nTiles; fa.groupAcc = fa.groupState + nGroups;   // look-back level 2: groups of 32 tiles
-  fa.blob = blob; fa.dataStart = (int)dataStart; fa.nBlobsMore = a.nBands - 1 - a.iBand; fa.blobCap = a.outCapacity;
+  fa.blob = blob; fa.dataStart = (int)dataStart; fa.nBlobsMore = 0; fa.blobCap = a.outCapacity;
   fa.fillEnd = (a.nBands == 1 && a.fillEnd && a.fillEnd > blob) ? a.fillEnd : nullptr;
   {
     // persistent CTAs, tiles taken by ticket (no co-residency assumption); shared memory opt-in and occupancy once per device
@@ -817,12 +817,52 @@ bool encodeBandFast(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
   if (!cudaOk(cudaStreamSynchronize(st), "sync")) { err = Failed; return true; }
   if (!cudaOk(cudaGetLastError(), "k_encode_tile")) { err = Failed; return true; }
 
-  // ---- the verdict of the device-side finish (encFinishBand)
+  // ---- were the assumptions right?  (On the host: a single warp doing this at the end of the kernel runs cold code at the pace of its
+  // instruction fetches, ~8 us measured; here it costs nothing and the prefix follows in stream order.)
   const FastEncResult& r = *hRes;
-  if (r.status == FASTST_GENERAL || r.status == FASTST_PENDING) return false;   // an assumption of the single pass failed: general encoder
-  if (r.status == FASTST_TOO_LARGE) { err = Failed; return true; }
-  bandBytes = (uint32_t)r.bandBytes;
-  if (r.status == FASTST_TOO_SMALL) { err = BufferTooSmall; return true; }       // Lerc.cpp:764-765
+  if (r.flags & (FASTF_NAN | FASTF_LUT)) return false;
+  const K minKey = (K)~r.negMinKey, maxKey = (K)r.maxKey;
+  const T lo = fromKeyHost<T>(minKey), hi = fromKeyHost<T>(maxKey);
+  const double zMin = (double)lo, zMax = (double)hi;
+  if (zMin == zMax) return false;                                        // constant image: no stream at all
+  HeaderInfo hd;
+  if (isFlt) {
+    if ((lo == (T)0 && std::signbit(lo)) || (hi == (T)0 && !std::signbit(hi))) return false;   // sign of a zero extreme depends on scan order (general path)
+    bool allInt = !(r.flags & FASTF_NOT_INT);
+    const double lim = sizeof(T) == 4 ? 8388608.0 : 9007199254740992.0;
+    allInt = allInt && zMin >= -lim && zMin <= lim && zMax >= -lim && zMax <= lim;             // Lerc.cpp:1490-1500
+    if (allInt) { if (std::max(0.5, std::floor(maxZErr)) != maxZErr) return false; hd.bIsInt = 1; }
+    for (int c = 0; c < fa.nRaise; c++) {                                  // PruneCandidates on row 0 (Lerc2.cpp:1322-1339)
+      double m; std::memcpy(&m, &r.raiseMax[c], 8);
+      if (!(m / fa.raiseFac[c] > maxZErr / 2)) return false;               // a candidate survived: full scan needed
+    }
+  }
+  const unsigned long long nData = r.totalBytes;
+  const size_t oneSweepBytes = sizeof(T) * (size_t)nPix;
+  if ((double)nData * 8 < (double)nPix * 1.5 && nData < 4 * oneSweepBytes && (a.nRows > 8 || a.nCols > 8)) return false;   // 16x16 retry (Lerc2.cpp:333-357)
+  if (oneSweepBytes <= nData) return false;                              // one sweep raw wins (Lerc2.cpp:364-373)
+  const unsigned long long total = dataStart + nData;
+  if (total > (unsigned long long)INT_MAX) { err = Failed; return true; }
+  bandBytes = (uint32_t)total;
+  if (total > a.outCapacity || (r.flags & FASTF_OVERFLOW)) { err = BufferTooSmall; return true; }   // Lerc.cpp:764-765
+
+  // ---- header, mask length, ranges, flag byte; checksum from the kernel's partial sums (Lerc2.cpp:1012-1064)
+  hd.version = 6; hd.nRows = a.nRows; hd.nCols = a.nCols; hd.nDepth = 1; hd.dt = PixelTraits<T>::code;
+  hd.nBlobsMore = a.nBands - 1 - a.iBand; hd.numValidPixel = (int)nPix; hd.microBlockSize = 8;
+  hd.blobSize = (int)total; hd.maxZError = maxZErr; hd.zMin = zMin; hd.zMax = zMax;
+  PrefixBytes pb; std::memset(&pb, 0, sizeof pb);
+  writeHeader(pb.b, hd);
+  size_t p = (size_t)headerBytes(6) + 4;                                  // mask byte count 0
+  std::memcpy(pb.b + p, &lo, sizeof(T)); p += sizeof(T);
+  std::memcpy(pb.b + p, &hi, sizeof(T)); p += sizeof(T);
+  pb.b[p++] = 0;                                                          // not one sweep
+  pb.n = (int)p;
+  unsigned long long A = 0, D = 0;
+  for (int i = 0; i < FAST_SLOTS; i++) { A += r.fletA[i]; D = (D + r.fletD[i]) % 65535ull; }
+  fletcherHostPartial(pb.b + 14, 0, (long long)p - 14, A, D);
+  hd.checksum = fletcherFinish(A, D, (long long)total - 14);
+  std::memcpy(pb.b + 10, &hd.checksum, 4);
+  LERC_LAUNCH(ctx, k_write_prefix, 1, 128, 0, blob, pb);
   a.tailFilled = fa.fillEnd != nullptr;
 
   // validity bookkeeping the band loop expects (Lerc.cpp:659-741): this band is all valid

@@ -25,7 +25,6 @@ namespace lerc {
 enum { FASTF_NAN = 1, FASTF_NOT_INT = 2, FASTF_LUT = 4, FASTF_OVERFLOW = 8 };
 constexpr int FAST_SLOTS = 32;
 
-enum { FASTST_PENDING = 0, FASTST_OK = 1, FASTST_GENERAL = 2, FASTST_TOO_SMALL = 3, FASTST_TOO_LARGE = 4 };   // verdict of the device-side finish
 struct FastEncResult {                 // device, zero-initialised per call
   unsigned long long totalBytes;       // length of the micro-block stream
   unsigned long long negMinKey;        // ~min key (so that zero-init works with atomicMax)
@@ -33,9 +32,7 @@ struct FastEncResult {                 // device, zero-initialised per call
   unsigned int flags, ticket;
   unsigned long long fletA[FAST_SLOTS], fletD[FAST_SLOTS];
   unsigned long long raiseMax[9];      // row 0: max |round(x * fac) - x * fac| per TryRaiseMaxZError candidate, as double bits
-  unsigned int done, status;           // CTAs finished; FASTST_* once the last one has written (or refused) the blob's prefix
   unsigned int totalReady, pad;        // totalBytes is final
-  unsigned long long bandBytes;        // size of the band blob (FASTST_OK / FASTST_TOO_SMALL)
 };
 
 struct FastEncArgs {
@@ -49,7 +46,7 @@ struct FastEncArgs {
   FastEncResult* res;
   unsigned long long* groupState;      // [ceil(nTiles / 32)], zero-initialised: aggregates of 32 consecutive tiles (two-round look-back); nullptr = plain chain
   unsigned long long* groupAcc;        // [ceil(nTiles / 32)], zero-initialised: atomic accumulators of the groups (lerc_lookback.cuh)
-  // k_encode_tile only: row-0 test of TryRaiseMaxZError (Lerc2.cpp:1233-1339) and the finish of the band on the device
+  // k_encode_tile only: row-0 test of TryRaiseMaxZError (Lerc2.cpp:1233-1339), zero fill behind the blob
   double raiseFac[9]; int nRaise;
   uint8_t* blob; int dataStart, nBlobsMore;            // where the band blob starts; header field
   unsigned long long blobCap;                          // bytes available from `blob`

@@ -138,108 +138,6 @@ __device__ __noinline__ void encRaiseRow0(const FastEncArgs& a, const T* __restr
   }
 }
 
-// The finish of the band by warp 0 of the last CTA (all 32 lanes, converged): were the assumptions of the single pass right (the tests the reference makes
-// before it codes a band, Lerc2.cpp:179-381, Lerc.cpp:1490-1502)?  If so header, mask byte count, ranges, flag byte and checksum are
-// written (Lerc2.cpp:710-760, :1012-1064).  Returns FASTST_*.
-template <class T>
-__device__ __noinline__ unsigned int encFinishBand(const FastEncArgs& a, int lane) {
-  constexpr bool isFlt = PixelTraits<T>::isFloat;
-  using K = typename PixelTraits<T>::Key;
-  // the result block in one round of loads (80 words, three per lane), fields by shuffle: a chain of dependent reads from L2 would cost
-  // microseconds at the very end of the kernel
-  static_assert(sizeof(FastEncResult) == 640 && offsetof(FastEncResult, raiseMax) == 68 * 8 && offsetof(FastEncResult, fletA) == 32 && offsetof(FastEncResult, fletD) == 288, "field map below");
-  const volatile unsigned long long* rw = (const volatile unsigned long long*)a.res;
-  const unsigned long long w0 = rw[lane], w1 = rw[32 + lane], w2 = lane < 16 ? rw[64 + lane] : 0ull;
-  auto word = [&](int i) -> unsigned long long {                          // (all three shuffles by every lane: the index may differ between lanes)
-    const unsigned long long x0 = __shfl_sync(FULL, w0, i & 31), x1 = __shfl_sync(FULL, w1, i & 31), x2 = __shfl_sync(FULL, w2, i & 31);
-    return i < 32 ? x0 : (i < 64 ? x1 : x2);
-  };
-  const unsigned long long rTotalBytes = word(0), rNegMinKey = word(1), rMaxKey = word(2);
-  const unsigned int flags = (unsigned int)word(3);
-  if (flags & (FASTF_NAN | FASTF_LUT)) return FASTST_GENERAL;
-  const K minKey = (K)~rNegMinKey, maxKey = (K)rMaxKey;
-  const T lo = fromKey<T>(minKey), hi = fromKey<T>(maxKey);
-  const double zMin = (double)lo, zMax = (double)hi;
-  if (zMin == zMax) return FASTST_GENERAL;                                 // constant image: no stream at all
-  uint8_t bIsInt = 0;
-  if (isFlt) {
-    if ((zMin == 0 && __double_as_longlong(zMin) < 0) || (zMax == 0 && __double_as_longlong(zMax) >= 0)) return FASTST_GENERAL;   // sign of a zero extreme depends on scan order
-    bool allInt = !(flags & FASTF_NOT_INT);
-    const double lim = sizeof(T) == 4 ? 8388608.0 : 9007199254740992.0;
-    allInt = allInt && zMin >= -lim && zMin <= lim && zMax >= -lim && zMax <= lim;             // Lerc.cpp:1490-1500
-    if (allInt) { const double f = floor(a.maxZErr); if ((f > 0.5 ? f : 0.5) != a.maxZErr) return FASTST_GENERAL; bIsInt = 1; }
-    {                                                                      // PruneCandidates on row 0 (Lerc2.cpp:1322-1339), candidate c by lane c
-      const double m = __longlong_as_double((long long)word(68 + (lane < 9 ? lane : 0)));
-      const bool survived = lane < a.nRaise && !(__ddiv_rn(m, a.raiseFac[lane < 9 ? lane : 0]) > __dmul_rn(a.maxZErr, 0.5));
-      if (__any_sync(FULL, survived)) return FASTST_GENERAL;               // a candidate survived: full scan needed
-    }
-  }
-  const long long nPix = (long long)a.nRows * a.nCols;
-  const unsigned long long nData = rTotalBytes;
-  const unsigned long long oneSweepBytes = sizeof(T) * (unsigned long long)nPix;
-  if ((double)nData * 8 < (double)nPix * 1.5 && nData < 4 * oneSweepBytes && (a.nRows > 8 || a.nCols > 8)) return FASTST_GENERAL;   // 16x16 retry (Lerc2.cpp:333-357)
-  if (oneSweepBytes <= nData) return FASTST_GENERAL;                       // one sweep raw wins (Lerc2.cpp:364-373)
-  const unsigned long long total = (unsigned long long)a.dataStart + nData;
-  if (total > 0x7fffffffull) return FASTST_TOO_LARGE;
-  if (lane == 0) a.res->bandBytes = total;
-  if (total > a.blobCap || (flags & FASTF_OVERFLOW)) return FASTST_TOO_SMALL;                // Lerc.cpp:764-765
-
-  // ---- the prefix: every lane stores one header field (16-bit pieces: all fields start at even offsets) into a shared-memory image,
-  // then lane L owns bytes 4 L .. 4 L + 3: checksum contribution, store.  (A single thread building the prefix byte by byte in local
-  // memory, or a byte-wise field search per lane, costs ~10 us at the very end of the kernel.)
-  __shared__ __align__(16) uint16_t sHdr[64];
-  sHdr[lane] = 0; sHdr[32 + lane] = 0;
-  __syncwarp();
-  unsigned long long loB = 0, hiB = 0; memcpy(&loB, &lo, sizeof(T)); memcpy(&hiB, &hi, sizeof(T));
-  const int p = 90 + 4 + 2 * (int)sizeof(T) + 1;                            // header | mask byte count 0 | ranges | "not one sweep"
-  {
-    unsigned long long v = 0; int at = -1, nh = 0;                          // value, byte offset, 16-bit pieces
-    switch (lane) {
-      case 0: v = 0x203263'72654cull; at = 0; nh = 3; break;               // "Lerc2 "
-      case 1: v = 6; at = 6; nh = 2; break;                                 // version
-      case 2: v = (unsigned)a.nRows; at = 14; nh = 2; break;
-      case 3: v = (unsigned)a.nCols; at = 18; nh = 2; break;
-      case 4: v = 1; at = 22; nh = 2; break;                                // nDepth
-      case 5: v = (unsigned)nPix; at = 26; nh = 2; break;                   // numValidPixel
-      case 6: v = 8; at = 30; nh = 2; break;                                // microBlockSize
-      case 7: v = (unsigned)total; at = 34; nh = 2; break;                  // blobSize
-      case 8: v = (unsigned)PixelTraits<T>::code; at = 38; nh = 2; break;
-      case 9: v = (unsigned)a.nBlobsMore; at = 42; nh = 2; break;
-      case 10: v = (unsigned long long)bIsInt << 8; at = 46; nh = 1; break; // bPassNoDataValues = 0, bIsInt
-      case 11: v = (unsigned long long)__double_as_longlong(a.maxZErr); at = 50; nh = 4; break;
-      case 12: v = (unsigned long long)__double_as_longlong(zMin); at = 58; nh = 4; break;
-      case 13: v = (unsigned long long)__double_as_longlong(zMax); at = 66; nh = 4; break;
-      case 14: v = loB; at = 94; nh = (int)sizeof(T) / 2; break;            // ranges (noDataVal, noDataValOrig, mask byte count stay 0)
-      case 15: v = hiB; at = 94 + (int)sizeof(T); nh = (int)sizeof(T) / 2; break;
-      default: break;
-    }
-    for (int j = 0; j < nh; j++) sHdr[at / 2 + j] = (uint16_t)(v >> (16 * j));
-  }
-  __syncwarp();
-  const uint32_t myW = ((const uint32_t*)sHdr)[lane];
-  unsigned long long A = word(4 + lane), D = word(36 + lane);                // FAST_SLOTS == 32: one slot per lane (words 4..35, 36..67)
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    const int i = 4 * lane + k;
-    if (i >= 14 && i < p) {                                                 // the prefix's own bytes: region offsets 0 .. p - 15
-      const unsigned long long c = (unsigned long long)((myW >> (8 * k)) & 0xffu) << (((i - 14) & 1) ? 0 : 8);
-      A += c; D += (unsigned long long)((i - 14) >> 1) * c;
-    }
-  }
-#pragma unroll
-  for (int m = 16; m; m >>= 1) { A += __shfl_xor_sync(FULL, A, m); D += __shfl_xor_sync(FULL, D, m); }
-  const uint32_t cs = fletcherFinishFast(A, D, (long long)total - 14);
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    const int i = 4 * lane + k;
-    uint32_t bk = (myW >> (8 * k)) & 0xffu;
-    if (i >= 10 && i < 14) bk = (cs >> (8 * (i - 10))) & 0xffu;
-    if (i < p) a.blob[i] = (uint8_t)bk;
-  }
-  return FASTST_OK;
-}
-
-static_assert(FAST_SLOTS == 32, "encFinishBand reads one checksum slot per lane");
 constexpr int ENC_COMPUTE = 256, ENC_THREADS = ENC_COMPUTE + 32;    // 8 compute warps + the control warp
 
 template <class T, int MINB>
@@ -597,18 +495,6 @@ __global__ void __launch_bounds__(ENC_THREADS, MINB) k_encode_tile(FastEncArgs a
       if (kMax > maxSeen) atomicMax(&a.res->maxKey, kMax);
     }
     if (fl & ~flagsSeen) atomicOr(&a.res->flags, fl);
-    __threadfence();
-  }
-  // ---- the last CTA finishes the band (its warp 0): verdict, and if the single pass was right the blob's prefix and checksum
-  if (warp == 0) {
-    unsigned int last = 0;
-    if (lane == 0) last = atomicAdd(&a.res->done, 1u) == gridDim.x - 1 ? 1u : 0u;
-    last = __shfl_sync(FULL, last, 0);
-    if (last) {
-      __threadfence();                                               // (acquire: the other CTAs' results)
-      const unsigned int verdict = encFinishBand<T>(a, lane);
-      if (lane == 0) a.res->status = verdict;                          // read by the host after the kernel
-    }
   }
   // ---- zero fill behind the blob (the API zero-fills the whole output buffer, Lerc.cpp:374): every CTA a slice, as soon as the stream's
   // length is known (all CTAs are resident: the grid is sized by occupancy)

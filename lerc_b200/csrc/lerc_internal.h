@@ -94,6 +94,7 @@ struct Context {
   cudaStream_t side = nullptr, mainSaved = nullptr;
   cudaEvent_t evFork = nullptr, evJoin = nullptr;
   bool sidePending = false;
+  bool drainOnRelease = true;   // releaseContext synchronises the call's stream unless the call says its stream is idle / its results are stream-ordered
   void forkSide();
   void backToMain();
   void joinSide();

@@ -4,7 +4,7 @@ raster as 256 x 256 tiles, every tile its own standard Lerc2 blob; SURVEY.md sec
 Tiles are independent objects, so the codec needs no data-path collective: rank r codes the contiguous tile range
 shard_tiles(n_tiles, r, world).  Only the finished streams are exchanged: one fixed-size all-gather of the per-tile byte
 counts, an exclusive prefix sum for the global offsets, and the payloads straight into their final place in the container
-(one broadcast per source rank: NCCL has no all-gather-v).  Works with any torch.distributed backend (nccl on GPUs, gloo
+(one grouped launch of point-to-point transfers: NCCL has no all-gather-v).  Works with any torch.distributed backend (nccl on GPUs, gloo
 in tests/test_tiles_gather.py).
 """
 import torch
@@ -33,9 +33,8 @@ def gather_container(local, local_offsets, n_tiles, group=None, out=None):
 
     One fixed-size all-gather of the per-tile byte counts and an exclusive prefix sum give every rank the global offsets and
     the byte range of every rank's streams; then every rank's streams go STRAIGHT to their final place in the container: one
-    broadcast per source rank into container[lo_r:hi_r] (NCCL has no all-gather-v; the broadcasts of one call are queued on
-    the same communicator and move exactly the bytes an all-gather-v would).  Nothing is padded, nothing is copied a second
-    time.  `out`: optional preallocated uint8 tensor for the container (at least the total size)."""
+    grouped launch of point-to-point sends / receives (NCCL has no all-gather-v; the group moves exactly the bytes one would,
+    all peers at once).  Nothing is padded, nothing is copied a second time.  `out`: optional preallocated uint8 tensor for the container (at least the total size)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     lo, hi = shard_tiles(n_tiles, rank, world)
@@ -59,17 +58,26 @@ def gather_container(local, local_offsets, n_tiles, group=None, out=None):
     assert rank_bytes[rank] <= local.numel()
     total = int(sum(rank_bytes))
     container = out[:total] if out is not None else torch.empty(total, dtype=torch.uint8, device=device)
-    start = 0
-    works = []
+    starts = [0]
     for r in range(world):
-        piece = container[start:start + rank_bytes[r]]
-        if r == rank:
-            piece.copy_(local[: rank_bytes[r]])
-        if world > 1 and rank_bytes[r] > 0:
-            works.append(dist.broadcast(piece, src=dist.get_global_rank(group, r) if group is not None else r, group=group, async_op=True))
-        start += rank_bytes[r]
-    for w in works:
-        w.wait()
+        starts.append(starts[-1] + rank_bytes[r])
+    mine = container[starts[rank]:starts[rank + 1]]
+    mine.copy_(local[: rank_bytes[rank]])
+    if world > 1:
+        # one grouped launch of point-to-point transfers: this rank's streams to every peer, every peer's streams into their place here
+        # (with NCCL all of them run concurrently over NVLink / NVSwitch; exactly the bytes of an all-gather-v)
+        ops = []
+        for r in range(world):
+            if r == rank:
+                continue
+            peer = dist.get_global_rank(group, r) if group is not None else r
+            if rank_bytes[rank] > 0:
+                ops.append(dist.P2POp(dist.isend, mine, peer, group))
+            if rank_bytes[r] > 0:
+                ops.append(dist.P2POp(dist.irecv, container[starts[r]:starts[r + 1]], peer, group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
     return container, offsets
 
 
