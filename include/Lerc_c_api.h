@@ -21,9 +21,12 @@
  * pointer (pageable or pinned) OR a CUDA device pointer; device-resident buffers are used in place.
  * Further entry points (batched tiles, explicit streams, timing hooks) live in lerc_b200.h.
  *
- * Documented deviations from the reference (DESIGN.md "Deviations"): codecVersion 2..5 writers,
- * the maxZErr == 777 bit-plane switch and the noData arguments of the _4D functions are not
- * implemented (WrongParam / Failed); lossless float blobs are written without the FPL predictor.
+ * Implemented like the reference: codec versions 2..6 on the write side (lerc_*ForVersion), the
+ * maxZErr == 777 bit-plane switch, the noData arguments of the _4D functions, the lossless float
+ * (FPL) codec.  Documented deviations (DESIGN.md "Deviations"): Lerc1 blobs are not read (Failed);
+ * lerc_decode with a data type different from the blob's returns Failed (the reference
+ * reinterprets); the pUsesNoData / noDataValues arrays of the _4D functions are host arrays.
+ * tests/test_capi_boundary.py compares every prototype below with the reference's header.
  */
 #ifndef LERC_API_INCLUDE_GUARD
 #define LERC_API_INCLUDE_GUARD
@@ -62,7 +65,7 @@ extern "C" {
       int nMasks, const unsigned char* pValidBytes, double maxZErr,
       unsigned char* pOutBuffer, unsigned int outBufferSize, unsigned int* nBytesWritten);
 
-  /* Same with an explicit codec version; this library writes only -1 / 6 (reference :159-187). */
+  /* Same with an explicit codec version: -1 / 6 = current, 2..5 = the older writers (reference :159-187). */
   LERCDLL_API lerc_status lerc_computeCompressedSizeForVersion(
       const void* pData, int codecVersion, unsigned int dataType, int nDepth, int nCols, int nRows, int nBands,
       int nMasks, const unsigned char* pValidBytes, double maxZErr, unsigned int* numBytes);

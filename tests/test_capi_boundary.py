@@ -103,3 +103,33 @@ def test_tile_batch_wrappers_fail_loudly_without_gpu(lib):
     dec = np.zeros_like(img)
     assert lerc_b200.decode_tiles(out, 100, off, dec, 32, 32) == 1
     assert lerc_b200.tiles_max_bytes(99, 64, 96, 32, 32) == 0          # unknown data type
+
+
+def _prototypes(path):
+    """normalised C prototypes `name -> (return type, [argument types and names])` of a header"""
+    txt = open(path).read()
+    txt = re.sub(r"/\*.*?\*/", " ", txt, flags=re.S)
+    txt = re.sub(r"//[^\n]*", " ", txt)
+    txt = re.sub(r"^\s*#[^\n]*", " ", txt, flags=re.M).replace("EMSCRIPTEN_KEEPALIVE", " ")     # (the reference wraps three decoders for WebAssembly)
+    out = {}
+    for m in re.finditer(r"LERCDLL_API\s+([\w\s\*]+?)\s+(lerc_\w+)\s*\(([^)]*)\)\s*;", txt):
+        ret, name, args = m.group(1), m.group(2), m.group(3)
+        norm = lambda t: re.sub(r"\s*\*\s*", "* ", re.sub(r"\s+", " ", t.strip()))
+        out[name] = (norm(ret), [norm(a) for a in args.split(",")])
+    return out
+
+
+def test_prototypes_equal_the_references_header():
+    """the drop-in contract: every function of the reference's Lerc_c_api.h is declared here with the same return type, argument
+    types, argument names and order; Lerc_types.h carries the same enumerators"""
+    ref_h = "/root/reference/src/LercLib/include/Lerc_c_api.h"
+    if not os.path.exists(ref_h):
+        pytest.skip("reference tree not present (GPU box)")
+    ours, theirs = _prototypes(os.path.join(ROOT, "include", "Lerc_c_api.h")), _prototypes(ref_h)
+    assert len(theirs) == 12 and set(ours) == set(theirs)
+    for name in theirs:
+        assert ours[name] == theirs[name], (name, ours[name], theirs[name])
+    enum = lambda p: re.findall(r"\b([A-Za-z]\w*)\s*(?:=\s*\d+)?\s*[,}]", re.sub(r"/\*.*?\*/|//[^\n]*", " ", open(p).read(), flags=re.S))
+    ours_t = enum(os.path.join(ROOT, "include", "Lerc_types.h"))
+    theirs_t = enum("/root/reference/src/LercLib/include/Lerc_types.h")
+    assert [e for e in theirs_t if e in ours_t] == theirs_t, sorted(set(theirs_t) - set(ours_t))
