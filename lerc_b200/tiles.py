@@ -4,7 +4,8 @@ raster as 256 x 256 tiles, every tile its own standard Lerc2 blob; SURVEY.md sec
 Tiles are independent objects, so the codec needs no data-path collective: rank r codes the contiguous tile range
 shard_tiles(n_tiles, r, world).  Only the finished streams are exchanged: one fixed-size all-gather of the per-tile byte
 counts, an exclusive prefix sum for the global offsets, and the payloads straight into their final place in the container
-(one grouped launch of point-to-point transfers: NCCL has no all-gather-v).  Works with any torch.distributed backend (nccl on GPUs, gloo
+(equal chunks of the compact container through one all_gather_into_tensor, the misfit at the chunk ends point to point: NCCL
+has no all-gather-v).  Works with any torch.distributed backend (nccl on GPUs, gloo
 in tests/test_tiles_gather.py).
 """
 import torch
@@ -32,9 +33,10 @@ def gather_container(local, local_offsets, n_tiles, group=None, out=None):
     in global tile order, int64 offsets[n_tiles + 1]) on every rank.
 
     One fixed-size all-gather of the per-tile byte counts and an exclusive prefix sum give every rank the global offsets and
-    the byte range of every rank's streams; then every rank's streams go STRAIGHT to their final place in the container: one
-    grouped launch of point-to-point sends / receives (NCCL has no all-gather-v; the group moves exactly the bytes one would,
-    all peers at once).  Nothing is padded, nothing is copied a second time.  `out`: optional preallocated uint8 tensor for the container (at least the total size)."""
+    the byte range of every rank's streams; the compact container is then cut into `world` EQUAL chunks: the few bytes of a rank's
+    streams that fall outside its own chunk travel point to point, and one all_gather_into_tensor of the equal chunks writes
+    every rank's streams straight to their final place (NCCL has no all-gather-v).  Nothing is padded, nothing is copied a
+    second time.  `out`: optional preallocated uint8 tensor for the container (at least the total size)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     lo, hi = shard_tiles(n_tiles, rank, world)
@@ -57,27 +59,45 @@ def gather_container(local, local_offsets, n_tiles, group=None, out=None):
     rank_bytes = all_sizes.sum(dim=1).tolist()                    # (one small device-to-host read: the byte range of every rank)
     assert rank_bytes[rank] <= local.numel()
     total = int(sum(rank_bytes))
-    container = out[:total] if out is not None else torch.empty(total, dtype=torch.uint8, device=device)
     starts = [0]
     for r in range(world):
         starts.append(starts[-1] + rank_bytes[r])
-    mine = container[starts[rank]:starts[rank + 1]]
-    mine.copy_(local[: rank_bytes[rank]])
-    if world > 1:
-        # one grouped launch of point-to-point transfers: this rank's streams to every peer, every peer's streams into their place here
-        # (with NCCL all of them run concurrently over NVLink / NVSwitch; exactly the bytes of an all-gather-v)
-        ops = []
-        for r in range(world):
-            if r == rank:
-                continue
-            peer = dist.get_global_rank(group, r) if group is not None else r
-            if rank_bytes[rank] > 0:
-                ops.append(dist.P2POp(dist.isend, mine, peer, group))
-            if rank_bytes[r] > 0:
-                ops.append(dist.P2POp(dist.irecv, container[starts[r]:starts[r + 1]], peer, group))
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
+    if world == 1:
+        container = out[:total] if out is not None else torch.empty(total, dtype=torch.uint8, device=device)
+        container.copy_(local[:total])
+        return container, offsets
+    # The compact container is cut into `world` equal chunks of C bytes.  Rank r's own streams [starts[r], starts[r + 1]) are chunk r
+    # up to the small misfit at its two ends (the ranks' byte counts differ by a percent): those end pieces go point to point to the
+    # rank whose chunk they belong to, then ONE all_gather_into_tensor of the equal chunks lands every byte at its final place --
+    # the collective runs at all-gather bandwidth (all NVLink channels; a group of per-peer send/recv pairs measured 240 GB/s, a third of it).
+    C_ = -(-total // world)
+    C_ = (C_ + 15) // 16 * 16
+    full = out if (out is not None and out.numel() >= world * C_) else torch.empty(world * C_, dtype=torch.uint8, device=device)
+    chunk = full[rank * C_:(rank + 1) * C_]
+    ops = []
+    lo_b, hi_b = starts[rank], starts[rank + 1]
+    for q in range(world):
+        c0, c1 = q * C_, min((q + 1) * C_, total)
+        # my bytes that belong to chunk q
+        a0, a1 = max(lo_b, c0), min(hi_b, c1)
+        if a1 > a0:
+            piece = local[a0 - lo_b:a1 - lo_b]
+            if q == rank:
+                chunk[a0 - c0:a1 - c0].copy_(piece)
+            else:
+                ops.append(dist.P2POp(dist.isend, piece.contiguous(), dist.get_global_rank(group, q) if group is not None else q, group))
+        # rank q's bytes that belong to my chunk
+        if q != rank:
+            m0, m1 = rank * C_, min((rank + 1) * C_, total)
+            b0, b1 = max(starts[q], m0), min(starts[q + 1], m1)
+            if b1 > b0:
+                ops.append(dist.P2POp(dist.irecv, chunk[b0 - m0:b1 - m0], dist.get_global_rank(group, q) if group is not None else q, group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    in_place_ok = dist.get_backend(group) == "nccl"                    # (NCCL's in-place convention: the input is the rank's slot of the output)
+    dist.all_gather_into_tensor(full[:world * C_], chunk if in_place_ok else chunk.clone(), group=group)
+    container = full[:total]
     return container, offsets
 
 
