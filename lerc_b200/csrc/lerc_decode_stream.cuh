@@ -9,7 +9,7 @@
 //   stage      the chunk (+ look-ahead for the unit that straddles its end) is copied into shared memory by the copy
 //              engine: one cp.async.bulk (TMA, SASS UBLKCP) from the 16-byte aligned address below the chunk, completion
 //              on an mbarrier; the last partial 16 bytes of the stream are read byte-wise (nothing is read past the blob)
-//   guess      the chunk is cut into 32 sub-chunks of 512 bytes; every warp scans the head windows of four of them (the true
+//   guess      the chunk is cut into 16 sub-chunks of 1 KB; every warp scans the head windows of four of them (the true
 //              chain must enter a sub-chunk inside its first MAXU bytes), 32 byte positions per step, for the first position
 //              that reads as the headers of two full bit-stuffed blocks in a row (mode 1, one-byte count of 64, consecutive
 //              integrity bits); windows without one (flat regions) take the first position from which DS_HOPS units parse with
@@ -39,9 +39,9 @@
 namespace lerc {
 
 constexpr int DS_CHUNK = 16384;                 // stream bytes per CTA
-constexpr int DS_SUBS = 32;                     // sub-chunks per chunk, one lane of warp 0 each
+constexpr int DS_SUBS = 16;                     // sub-chunks per chunk, one lane of warp 0 each
 constexpr int DS_SUB = DS_CHUNK / DS_SUBS;
-constexpr int DS_LIST = 136;                    // recorded positions per sub-chunk; more units than that in 512 bytes (flat regions: 1..3-byte blocks) -> DSF_FALLBACK
+constexpr int DS_LIST = 264;                    // recorded positions per sub-chunk; more units than that in 1 KB (flat regions: 1..3-byte blocks) -> DSF_FALLBACK
 constexpr int DS_PATCH = 48;                    // hops the patch walk may need before it joins the recorded chain
 constexpr int DS_HOPS = 4;                      // units a head-window position must parse to become the guess (windows without a strict candidate)
 constexpr int DS_THREADS = 128;
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(DS_THREADS, 7) k_decode_stream(StreamDecArgs a
       int total = __shfl_sync(FULL, inc, 31);
       const unsigned long long finalExit = start + (unsigned long long)__shfl_sync(FULL, curExit, sL);
       if (ok && spec && finalExit != specExit) ok = false;            // the next chunk may have started from a wrong entry
-      sFirst[s] = first; sNPatch[s] = npatch; sPre[s] = inc - (s < nSubs ? cs : 0); sTrueExit[s] = curExit;
+      if (s < DS_SUBS) { sFirst[s] = first; sNPatch[s] = npatch; sPre[s] = inc - (s < nSubs ? cs : 0); sTrueExit[s] = curExit; }
       if (lane == 31) sPre[DS_SUBS] = total;
 #ifdef LERC_CUSIM
       if (std::getenv("DS_DEBUG")) {
