@@ -40,16 +40,6 @@ bool anyNoData(const unsigned char* pUsesNoData, int nBands) {
   return false;
 }
 
-// Device alias of a pinned host buffer (unified addressing), or nullptr.  Used for the zero-copy path: the single-pass kernels stream a
-// pinned host raster / blob straight over PCIe (TMA bulk loads read host memory like device memory) and store their output straight
-// into pinned host memory, so that the transfer in, the coding and the transfer out of ONE call overlap in full duplex instead of
-// running one after the other through a staging copy.
-void* pinnedAlias(const void* hostPtr) {
-  void* d = nullptr;
-  if (cudaHostGetDevicePointer(&d, const_cast<void*>(hostPtr), 0) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-  return d;
-}
-
 // Brings `bytes` at host/device pointer `p` onto the device (no copy if it already is there).
 const void* toDevice(Context* ctx, const void* p, size_t bytes, PtrKind kind, void* dScratch) {
   if (kind == PTR_DEVICE) return p;
@@ -77,18 +67,8 @@ lerc_status encodeImpl(const void* pData, int version, unsigned dataType, int nD
   globalStats().encodeCalls++;
 
   const size_t nPix = (size_t)nCols * (size_t)nRows, nElemBytes = nPix * (size_t)nDepth * ts, nBits = (nPix + 7) >> 3;
-  PtrKind kData = classifyPointer(pData);
-  const PtrKind kMask = pValidBytes ? classifyPointer(pValidBytes) : PTR_DEVICE;
-  PtrKind kOut = (!sizeOnly) ? classifyPointer(pOut) : PTR_DEVICE;
-  // zero-copy: pinned host raster in, pinned host blob out, and a raster the single-pass encoder takes (lerc_encode_tile.cuh)
-  bool zeroCopy = false;
-  const unsigned char* pOutHost = pOut;
-  if (!sizeOnly && kData == PTR_HOST_PINNED && kOut == PTR_HOST_PINNED && nMasks == 0 && !haveNoData && nDepth == 1 && version == 6 && ts >= 2 &&
-      maxZErr != 777 && !((dataType == (unsigned)DT_Float || dataType == (unsigned)DT_Double) && !(maxZErr > 0)) && !std::getenv("LERC_B200_NO_ZEROCOPY")) {
-    void* dIn = pinnedAlias(pData);
-    void* dO = pinnedAlias(pOut);
-    if (dIn && dO) { pData = dIn; pOut = (unsigned char*)dO; kData = PTR_DEVICE; kOut = PTR_DEVICE; zeroCopy = true; }
-  }
+  const PtrKind kData = classifyPointer(pData), kMask = pValidBytes ? classifyPointer(pValidBytes) : PTR_DEVICE;
+  const PtrKind kOut = (!sizeOnly) ? classifyPointer(pOut) : PTR_DEVICE;
 
   void* dBandScratch = kData != PTR_DEVICE ? ctx->arena.alloc(nElemBytes) : nullptr;
   void* dMaskScratch = (pValidBytes && kMask != PTR_DEVICE) ? ctx->arena.alloc(nPix) : nullptr;
@@ -137,7 +117,7 @@ lerc_status encodeImpl(const void* pData, int version, unsigned dataType, int nD
       if (nd.maskModified) a.anyMaskModified = true;
     }
     a.dOut = sizeOnly ? nullptr : dOut; a.outOffset = offset; a.outCapacity = sizeOnly ? 0 : (dOutCap > offset ? dOutCap - offset : 0);
-    a.fillEnd = (!sizeOnly && kOut == PTR_DEVICE && nBands == 1 && (!zeroCopy || outSize < (1u << 26))) ? pOut + outSize : nullptr;   // the single-pass encoder zero-fills behind the blob itself
+    a.fillEnd = (!sizeOnly && kOut == PTR_DEVICE && nBands == 1) ? pOut + outSize : nullptr;   // the single-pass encoder zero-fills behind the blob itself
     uint32_t bandBytes = 0;
     const ErrCode e = encodeBand(ctx, a, ms, bandBytes);
     if (e == BufferTooSmall && !sizeOnly && kOut != PTR_DEVICE && dOutCap < (size_t)outSize) return Failed;   // our bound was wrong: never expected
@@ -159,11 +139,7 @@ lerc_status encodeImpl(const void* pData, int version, unsigned dataType, int nD
   if (sizeOnly) return Ok;
 
   // the API zero-fills the whole output buffer before writing (Lerc.cpp:374): blob, then zeros
-  if (zeroCopy) {                                                      // the blob sits in the caller's pinned host buffer already
-    if (!cudaOk(cudaStreamSynchronize(ctx->stream), "sync")) return Failed;
-    if (!tailFilled && outSize > offset) std::memset(const_cast<unsigned char*>(pOutHost) + offset, 0, outSize - offset);
-    ctx->drainOnRelease = false;
-  } else if (kOut == PTR_DEVICE) {
+  if (kOut == PTR_DEVICE) {
     if (!tailFilled && outSize > offset && !cudaOk(cudaMemsetAsync(pOut + offset, 0, outSize - offset, ctx->stream), "memset tail")) return Failed;
     // a device blob on the caller's stream (lerc_b200_set_stream) is complete in stream order (lerc_b200.h); otherwise on return
     if (!tlsUseUserStream && !cudaOk(cudaStreamSynchronize(ctx->stream), "sync")) return Failed;
@@ -210,21 +186,10 @@ lerc_status decodeImpl(const unsigned char* pBlob, unsigned blobSize, int nMasks
   globalStats().decodeCalls++;
 
   const size_t nPix = (size_t)nCols * (size_t)nRows, nElem = nPix * (size_t)nDepth, nBits = (nPix + 7) >> 3;
-  PtrKind kData = classifyPointer(pData);
-  const PtrKind kMask = pValidBytes ? classifyPointer(pValidBytes) : PTR_DEVICE;
+  const PtrKind kData = classifyPointer(pData), kMask = pValidBytes ? classifyPointer(pValidBytes) : PTR_DEVICE;
 
-  // zero-copy: pinned host blob in, pinned host raster out, and a blob of the kind the single-kernel stream decoder takes
-  // (lerc_decode_stream.cuh: no masks, nDepth 1, 16/32/64-bit pixels, lossy or integer; anything else is staged as before)
-  bool zeroCopy = false;
   const uint8_t* dBlob = pBlob;
-  if (kBlob == PTR_HOST_PINNED && kData == PTR_HOST_PINNED && !pValidBytes && !toDouble && li.nMasks == 0 && li.nDepth == 1 && li.version >= 3 &&
-      li.nUsesNoDataValue == 0 && ts >= 2 && li.zMin != li.zMax && !((li.dt == DT_Float || li.dt == DT_Double) && li.maxZError == 0) &&
-      !std::getenv("LERC_B200_NO_ZEROCOPY")) {
-    void* dB = pinnedAlias(pBlob);
-    void* dD = pinnedAlias(pData);
-    if (dB && dD) { dBlob = (const uint8_t*)dB; pData = dD; kData = PTR_DEVICE; zeroCopy = true; }
-  }
-  if (!zeroCopy && kBlob != PTR_DEVICE) {
+  if (kBlob != PTR_DEVICE) {
     uint8_t* d = (uint8_t*)ctx->arena.alloc((size_t)blobSize + 64);
     if (!d || !cudaOk(cudaMemcpyAsync(d, pBlob, blobSize, cudaMemcpyHostToDevice, ctx->stream), "H2D blob")) return Failed;
     dBlob = d;

@@ -135,29 +135,6 @@ def test_device_pointers(libs):
     assert prod.f["getBlobInfo"](d_out.data_ptr(), n.value, info.ctypes.data, None, 11, 0) == 0 and info[3] == 517
 
 
-def test_pinned_host_buffers_zero_copy(libs):
-    """pinned host raster / blob / output: the single-pass kernels read and write them in place over PCIe (no staging copy);
-    same bytes, zero tail, same pixels -- also for an input the single pass refuses (NaN -> general encoder on the same pointers)"""
-    import ctypes as C
-    import torch
-    prod, orc = libs
-    for name, img, mz in (("noisy", c2_raster(520, 1040), 0.01), ("i16", np.clip(c2_raster(300, 517) * 3, -32768, 32767).astype(np.int16), 0),
-                          ("nan", np.where(c2_raster(200, 264) > 1290, np.float32(np.nan), c2_raster(200, 264)).astype(np.float32), 0.01)):
-        s_o, b_o, _ = orc.encode(img, mz)
-        dt = {np.dtype(np.float32): 6, np.dtype(np.int16): 2}[img.dtype]
-        h_img = torch.from_numpy(img.copy()).pin_memory()
-        h_out = torch.full((img.nbytes + 4096,), 0xAB, dtype=torch.uint8).pin_memory()
-        n = C.c_uint(0)
-        st = prod.f["encode"](h_img.data_ptr(), dt, 1, img.shape[1], img.shape[0], 1, 0, None, float(mz), h_out.data_ptr(), h_out.numel(), C.addressof(n))
-        assert st == s_o == 0 and n.value == len(b_o), (name, st, n.value, len(b_o))
-        host = h_out.numpy()
-        assert host[: n.value].tobytes() == b_o and not host[n.value:].any(), name
-        h_dec = torch.full(img.shape, -1, dtype=h_img.dtype).pin_memory()
-        st = prod.f["decode"](h_out.data_ptr(), n.value, 0, None, 1, img.shape[1], img.shape[0], 1, dt, h_dec.data_ptr())
-        _, d_ref, _ = orc.decode(b_o)
-        assert st == 0 and np.array_equal(h_dec.numpy().view(np.uint8), d_ref[0, :, :, 0].view(np.uint8)), name
-
-
 def test_kernels_actually_ran(libs):
     import sys
     sys.path.insert(0, ROOT)

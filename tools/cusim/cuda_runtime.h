@@ -96,7 +96,6 @@ enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 cudaError_t cusimMalloc(void** p, size_t n);
 template <class T> inline cudaError_t cudaMalloc(T** p, size_t n) { return cusimMalloc((void**)p, n); }
 cudaError_t cusimMallocHost(void** p, size_t n);
-static inline cudaError_t cudaHostGetDevicePointer(void** d, void* h, unsigned) { *d = h; return cudaSuccess; }   // unified addressing
 template <class T> inline cudaError_t cudaMallocHost(T** p, size_t n) { return cusimMallocHost((void**)p, n); }
 cudaError_t cudaFree(void* p);
 cudaError_t cudaFreeHost(void* p);
