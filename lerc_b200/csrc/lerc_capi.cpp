@@ -91,12 +91,15 @@ lerc_status encodeImpl(const void* pData, int version, unsigned dataType, int nD
 
   size_t offset = 0;
   uint64_t need = 0;
-  bool anyModified = false, tailFilled = false;
+  bool anyModified = false, tailFilled = false, hostCopied = false;
   for (int b = 0; b < nBands; b++) {
     EncodeBandArgs a;
     const size_t arenaMark = ctx->arena.used, pinnedMark = ctx->pinnedUsed;
     a.dt = (int)dataType; a.nDepth = nDepth; a.nCols = nCols; a.nRows = nRows;
-    a.dData = toDevice(ctx, (const uint8_t*)pData + nElemBytes * (size_t)b, nElemBytes, kData, dBandScratch);
+    // a host band is not copied here: encodeBand copies it itself (the single-pass encoder strip by strip, overlapped with the coding)
+    if (kData == PTR_DEVICE) a.dData = (const uint8_t*)pData + nElemBytes * (size_t)b;
+    else { a.dData = dBandScratch; a.hData = (const uint8_t*)pData + nElemBytes * (size_t)b; }
+    a.hOut = (!sizeOnly && kOut != PTR_DEVICE && nBands == 1) ? pOut : nullptr;
     a.dValidBytes = nullptr;
     if (nMasks > 0) a.dValidBytes = (const uint8_t*)toDevice(ctx, pValidBytes + (nMasks > 1 ? nPix * (size_t)b : 0), nPix, kMask, dMaskScratch);
     if (!a.dData || (nMasks > 0 && !a.dValidBytes)) return Failed;
@@ -106,7 +109,9 @@ lerc_status encodeImpl(const void* pData, int version, unsigned dataType, int nD
       void* dCopy = ctx->arena.alloc(nElemBytes);
       uint8_t* dMaskCopy = (uint8_t*)ctx->arena.alloc(nPix);
       if (!dCopy || !dMaskCopy) return Failed;
-      if (!cudaOk(cudaMemcpyAsync(dCopy, a.dData, nElemBytes, cudaMemcpyDeviceToDevice, ctx->stream), "band copy")) return Failed;
+      if (!cudaOk(a.hData ? cudaMemcpyAsync(dCopy, a.hData, nElemBytes, cudaMemcpyHostToDevice, ctx->stream)
+                          : cudaMemcpyAsync(dCopy, a.dData, nElemBytes, cudaMemcpyDeviceToDevice, ctx->stream), "band copy")) return Failed;
+      a.hData = nullptr;
       if (a.dValidBytes) { if (!cudaOk(cudaMemcpyAsync(dMaskCopy, a.dValidBytes, nPix, cudaMemcpyDeviceToDevice, ctx->stream), "mask copy")) return Failed; }
       else cudaMemsetAsync(dMaskCopy, 1, nPix, ctx->stream);
       NoDataVerdict nd;
@@ -124,6 +129,7 @@ lerc_status encodeImpl(const void* pData, int version, unsigned dataType, int nD
     if (e != Ok) return e;
     anyModified = a.anyMaskModified;
     tailFilled = a.tailFilled;
+    hostCopied = a.hostCopied;
     if (need + bandBytes > (uint64_t)UINT_MAX) return DimensionsTooLarge;   // Lerc.cpp:757-758
     need += bandBytes;
     offset += bandBytes;
@@ -145,7 +151,7 @@ lerc_status encodeImpl(const void* pData, int version, unsigned dataType, int nD
     if (!tlsUseUserStream && !cudaOk(cudaStreamSynchronize(ctx->stream), "sync")) return Failed;
     ctx->drainOnRelease = false;
   } else {
-    if (!cudaOk(cudaMemcpyAsync(pOut, dOut, offset, cudaMemcpyDeviceToHost, ctx->stream), "D2H blob")) return Failed;
+    if (!hostCopied && !cudaOk(cudaMemcpyAsync(pOut, dOut, offset, cudaMemcpyDeviceToHost, ctx->stream), "D2H blob")) return Failed;
     if (outSize > offset) std::memset(pOut + offset, 0, outSize - offset);
     if (!cudaOk(cudaStreamSynchronize(ctx->stream), "sync")) return Failed;
     ctx->drainOnRelease = false;
@@ -191,9 +197,11 @@ lerc_status decodeImpl(const unsigned char* pBlob, unsigned blobSize, int nMasks
   const uint8_t* dBlob = pBlob;
   if (kBlob != PTR_DEVICE) {
     uint8_t* d = (uint8_t*)ctx->arena.alloc((size_t)blobSize + 64);
-    if (!d || !cudaOk(cudaMemcpyAsync(d, pBlob, blobSize, cudaMemcpyHostToDevice, ctx->stream), "H2D blob")) return Failed;
+    // (a single-band blob is left to decodeBand: its stream decoder copies and decodes it strip by strip)
+    if (!d || (nBands > 1 && !cudaOk(cudaMemcpyAsync(d, pBlob, blobSize, cudaMemcpyHostToDevice, ctx->stream), "H2D blob"))) return Failed;
     dBlob = d;
   }
+  const bool blobPending = kBlob != PTR_DEVICE && nBands == 1;
   BandMaskState ms;
   ms.dBits = (uint8_t*)ctx->arena.alloc(nBits);
   if (!ms.dBits) return Failed;
@@ -216,6 +224,8 @@ lerc_status decodeImpl(const unsigned char* pBlob, unsigned blobSize, int nMasks
     a.dt = (int)dataType; a.nDepth = nDepth; a.nCols = nCols; a.nRows = nRows;
     a.dBlob = dBlob + pos; a.avail = blobSize - pos; a.hd = hd; a.hBlob = kBlob != PTR_DEVICE ? pBlob + pos : nullptr;
     a.src = &src; a.srcOff = pos;
+    if (blobPending) a.pendingBlob = (size_t)hd.blobSize;
+    if (!direct && !(toDouble && dataType != (unsigned)DT_Double)) a.hOut = (uint8_t*)pData + nElem * ts * (size_t)b;
     a.dData = direct ? (void*)((uint8_t*)pData + nElem * ts * (size_t)b) : dBandScratch;
     const bool wantMask = b < nMasks;
     a.dValidBytes = wantMask ? (kMask == PTR_DEVICE ? pValidBytes + nPix * (size_t)b : dMaskScratch) : nullptr;
@@ -234,7 +244,7 @@ lerc_status decodeImpl(const unsigned char* pBlob, unsigned blobSize, int nMasks
         double* dst = kData == PTR_DEVICE ? (double*)pData + nElem * (size_t)b : dDoubleScratch;
         launchConvertToDouble(ctx, dBandScratch, (int)dataType, nElem, dst);
         if (kData != PTR_DEVICE && !cudaOk(cudaMemcpyAsync((double*)pData + nElem * (size_t)b, dst, nElem * 8, cudaMemcpyDeviceToHost, ctx->stream), "D2H")) return Failed;
-      } else if (!cudaOk(cudaMemcpyAsync((uint8_t*)pData + nElem * ts * (size_t)b, dBandScratch, nElem * ts, cudaMemcpyDeviceToHost, ctx->stream), "D2H")) return Failed;
+      } else if (!a.hostCopied && !cudaOk(cudaMemcpyAsync((uint8_t*)pData + nElem * ts * (size_t)b, dBandScratch, nElem * ts, cudaMemcpyDeviceToHost, ctx->stream), "D2H")) return Failed;
     }
     if (wantMask && kMask != PTR_DEVICE &&
         !cudaOk(cudaMemcpyAsync(pValidBytes + nPix * (size_t)b, dMaskScratch, nPix, cudaMemcpyDeviceToHost, ctx->stream), "D2H mask")) return Failed;

@@ -67,6 +67,16 @@ void Context::joinSide() {
   if (sidePending) { cudaStreamWaitEvent(stream, evJoin, 0); sidePending = false; }
 }
 
+bool Context::pipeStreams() {
+  if (copyIn) return true;
+  if (!cudaOk(cudaStreamCreateWithFlags(&copyIn, cudaStreamNonBlocking), "cudaStreamCreate") ||
+      !cudaOk(cudaStreamCreateWithFlags(&copyOut, cudaStreamNonBlocking), "cudaStreamCreate")) { copyIn = copyOut = nullptr; return false; }
+  for (int d = 0; d < 2; d++)
+    for (int i = 0; i < 16; i++)
+      if (!cudaOk(cudaEventCreateWithFlags(&evStrip[d][i], cudaEventDisableTiming), "cudaEventCreate")) return false;
+  return true;
+}
+
 void* Context::pinnedAlloc(size_t bytes) {
   size_t off = (pinnedUsed + 63) / 64 * 64;
   if (off + bytes > pinnedCap) return nullptr;

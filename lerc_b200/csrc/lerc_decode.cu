@@ -365,16 +365,19 @@ inline void launchResolve(Context* ctx, const FastDecArgs& fa) {
 // checksum is right, 0 = the kernel gave up (nothing is known about the blob: run the other decoders), -1 = checksum
 // mismatch or CUDA error.
 template <class T>
-int decodeStreamFast(Context* ctx, const HeaderInfo& hd, const uint8_t* dBlob, size_t streamPos, unsigned long long prefA, unsigned long long prefD, void* dData) {
+int decodeStreamFast(Context* ctx, const HeaderInfo& hd, DecodeBandArgs& ba, size_t streamPos, unsigned long long prefA, unsigned long long prefD) {
+  const uint8_t* dBlob = ba.dBlob; void* dData = ba.dData;
   const size_t streamLen = (size_t)hd.blobSize - streamPos;
   if (streamLen == 0 || streamLen >= 0xfff00000ull || !std::isfinite(hd.zMax) || std::getenv("LERC_B200_NO_FAST")) return 0;
   cudaStream_t st = ctx->stream;
+  constexpr int MAXSTRIPS = 16;
   const int nChunks = (int)((streamLen + DS_CHUNK - 1) / DS_CHUNK);
   const size_t nGroups = ((size_t)nChunks + 31) / 32;
-  const size_t stateBytes = 64 + ((size_t)nChunks * 2 + nGroups * 2) * 8;
+  const size_t stateBytes = 128 + ((size_t)nChunks * 2 + nGroups * 2) * 8;         // result | ticket counters | chunk and group states
   uint8_t* dState = (uint8_t*)ctx->arena.alloc(stateBytes);
   unsigned int* hStatus = (unsigned int*)ctx->pinnedAlloc(16);
-  if (!dState || !hStatus) return 0;
+  unsigned long long* hEnd = (unsigned long long*)ctx->pinnedAlloc(8 * MAXSTRIPS);
+  if (!dState || !hStatus || !hEnd) return 0;
   cudaMemsetAsync(dState, 0, stateBytes, st);
   StreamDecArgs sa;
   sa.stream = dBlob + streamPos; sa.streamLen = streamLen;
@@ -382,7 +385,7 @@ int decodeStreamFast(Context* ctx, const HeaderInfo& hd, const uint8_t* dBlob, s
   sa.nTxMagic = sa.nTx >= 2 ? (uint32_t)((1ull << 32) / (unsigned)sa.nTx) + 1u : 0u;
   sa.invScale = 2 * hd.maxZError; sa.zMax = hd.zMax; sa.data = dData; sa.nChunks = nChunks;
   sa.res = (StreamDecResult*)dState;
-  sa.exitState = (unsigned long long*)(dState + 64); sa.cntState = sa.exitState + nChunks;
+  sa.exitState = (unsigned long long*)(dState + 128); sa.cntState = sa.exitState + nChunks;
   sa.groupState = sa.cntState + nChunks; sa.groupAcc = sa.groupState + nGroups;
   sa.regionOff = (long long)streamPos - 14; sa.regionLen = (long long)hd.blobSize - 14;
   sa.prefA = prefA % 65535ull; sa.prefD = prefD % 65535ull; sa.expectChecksum = hd.checksum; sa.haveChecksum = hd.version >= 3 ? 1 : 0;
@@ -393,12 +396,64 @@ int decodeStreamFast(Context* ctx, const HeaderInfo& hd, const uint8_t* dBlob, s
     if (!cudaOk(cudaFuncSetAttribute(k_decode_stream<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "decode stream smem")) return 0;
     attrDone.fetch_or(devBit, std::memory_order_relaxed);
   }
-  { LaunchScope scope_(ctx, "k_decode_stream<T>"); k_decode_stream<T><<<(unsigned)nChunks, DS_THREADS, smem, st>>>(sa); ctx->kernelLaunches++; }
-  if (!cudaOk(cudaMemcpyAsync(hStatus, &sa.res->status, 4, cudaMemcpyDeviceToHost, st), "D2H stream status") || !cudaOk(cudaStreamSynchronize(st), "sync")) return -1;
+  // A host-resident call is pipelined: the stream travels to the device in strips (whole chunks) on one stream, every strip is decoded
+  // as soon as it is there (exit chain and block counts carry over in the look-back state), and the block rows a strip has
+  // completed go back to the caller's array on a third stream while the next strips are decoded.
+  const size_t rowBytes = (size_t)hd.nCols * sizeof(T);
+  int nStrips = 1;
+  if (ba.pendingBlob || ba.hOut) {
+    static const int stripLog2 = [] { const char* e = std::getenv("LERC_B200_STRIP_LOG2"); const int v = e ? std::atoi(e) : 0; return (v >= 10 && v <= 30) ? v : 23; }();
+    const size_t moved = std::max(ba.pendingBlob ? streamLen : 0, ba.hOut ? rowBytes * (size_t)hd.nRows : 0);
+    nStrips = (int)std::min<size_t>(MAXSTRIPS, std::max<size_t>(1, moved >> stripLog2));
+    nStrips = std::min(nStrips, nChunks);
+    if (nStrips > 1 && !ctx->pipeStreams()) nStrips = 1;
+  }
+  const bool outPiped = nStrips > 1 && ba.hOut != nullptr;
+  if (ba.pendingBlob) {
+    uint8_t* dst = const_cast<uint8_t*>(dBlob);
+    cudaStream_t cin = nStrips > 1 ? ctx->copyIn : st;
+    size_t from = 0;
+    for (int sI = 0; sI < nStrips; sI++) {
+      const int ce = (int)((long long)nChunks * (sI + 1) / nStrips);
+      const size_t to = sI == nStrips - 1 ? ba.pendingBlob : std::min(ba.pendingBlob, streamPos + (size_t)ce * DS_CHUNK + (size_t)DecStream<T>::LA + 32);
+      if (to > from && !cudaOk(cudaMemcpyAsync(dst + from, ba.hBlob + from, to - from, cudaMemcpyHostToDevice, cin), "H2D strip")) return -1;
+      from = std::max(from, to);
+      if (nStrips > 1) cudaEventRecord(ctx->evStrip[0][sI], cin);
+    }
+    if (nStrips > 1) cudaStreamWaitEvent(st, ctx->evStrip[0][0], 0);
+  }
+  const bool inPiped = nStrips > 1 && ba.pendingBlob != 0;
+  for (int sI = 0; sI < nStrips; sI++) {
+    const int cb = (int)((long long)nChunks * sI / nStrips), ce = (int)((long long)nChunks * (sI + 1) / nStrips);
+    sa.chunkBegin = cb; sa.ticket = (unsigned int*)(dState + 64) + sI;
+    if (inPiped) cudaStreamWaitEvent(st, ctx->evStrip[0][sI], 0);
+    { LaunchScope scope_(ctx, "k_decode_stream<T>"); k_decode_stream<T><<<(unsigned)(ce - cb), DS_THREADS, smem, st>>>(sa); ctx->kernelLaunches++; }
+    if (outPiped) {
+      cudaMemcpyAsync(hEnd + sI, sa.cntState + (ce - 1), 8, cudaMemcpyDeviceToHost, st);      // inclusive block count behind this strip
+      if (sI == nStrips - 1) cudaMemcpyAsync(hStatus, &sa.res->status, 4, cudaMemcpyDeviceToHost, st);
+      cudaEventRecord(ctx->evStrip[1][sI], st);
+    }
+  }
+  ba.pendingBlob = 0;                                                 // (the whole blob is in dBlob once the call's stream has passed the last strip's event)
+  if (outPiped) {
+    int rowsSent = 0;
+    bool ok = true;
+    for (int sI = 0; sI < nStrips && ok; sI++) {
+      ok = cudaOk(cudaEventSynchronize(ctx->evStrip[1][sI]), "strip sync");
+      if (!ok) break;
+      const unsigned long long blocks = hEnd[sI] & LB_VAL;
+      const int rows = sI == nStrips - 1 ? hd.nRows : (int)std::min<unsigned long long>((unsigned long long)hd.nRows, blocks / (unsigned)sa.nTx * 8);
+      if (rows > rowsSent) { cudaMemcpyAsync(ba.hOut + (size_t)rowsSent * rowBytes, (const uint8_t*)dData + (size_t)rowsSent * rowBytes, (size_t)(rows - rowsSent) * rowBytes, cudaMemcpyDeviceToHost, ctx->copyOut); rowsSent = rows; }
+    }
+    ok = cudaOk(cudaStreamSynchronize(ctx->copyOut), "copy out sync") && ok;
+    if (!ok) return -1;
+    ba.hostCopied = true;                                             // (void if the verdict below is a fallback: the caller copies again)
+  } else if (!cudaOk(cudaMemcpyAsync(hStatus, &sa.res->status, 4, cudaMemcpyDeviceToHost, st), "D2H stream status") || !cudaOk(cudaStreamSynchronize(st), "sync")) return -1;
   if (!cudaOk(cudaGetLastError(), "k_decode_stream")) return -1;
   if (*hStatus && std::getenv("LERC_B200_VERBOSE")) std::fprintf(stderr, "[lerc_b200] stream decoder status %u\n", *hStatus);
   if (*hStatus & DSF_CHECKSUM) return -1;
-  return (*hStatus & DSF_FALLBACK) ? 0 : 1;
+  if (*hStatus & DSF_FALLBACK) { ba.hostCopied = false; return 0; }
+  return 1;
 }
 
 // Launches the speculative parallel decoder (lerc_decode_fast.cuh) on the micro-block stream.  Returns false when the
@@ -622,11 +677,21 @@ ErrCode decodeBandT(Context* ctx, DecodeBandArgs& a, BandMaskState& ms) {
   // the bit mask of an all-valid / all-invalid band is only written when something reads it
   auto bitsNow = [&]() { if (ms.pendingFill >= 0) { cudaMemsetAsync(ms.dBits, ms.pendingFill, nBits, st); ms.pendingFill = -1; } };
 
+  // a host blob that is not on the device yet: only the stream decoder below copies it itself (in strips); every other path wants it whole
+  // (they all start the checksum kernel first, which therefore stages the blob)
+  const bool mayFast = nDepth == 1 && hd.numValidPixel == nPix && hd.microBlockSize == 8 && hd.version >= 3 && hd.zMin != hd.zMax;
+  auto stageBlob = [&]() {
+    if (a.pendingBlob) cudaMemcpyAsync(const_cast<uint8_t*>(a.dBlob), a.hBlob, a.pendingBlob, cudaMemcpyHostToDevice, st);
+    a.pendingBlob = 0;
+  };
+  if (!mayFast) stageBlob();
+
   // checksum (Lerc2.cpp:592-601); the verdict is read together with the other status bits at the end.  The single-kernel stream
   // decoder sums the blob itself, so the launch waits until it is known whether that decoder applies.
   if (hd.version >= 3 && hd.blobSize < 14) return Failed;
   bool checksumLaunched = false;
   auto launchChecksum = [&]() -> bool {
+    stageBlob();
     if (hd.version < 3 || checksumLaunched) return true;
     unsigned long long* dAcc = (unsigned long long*)ctx->arena.alloc(16);
     if (!dAcc) return false;
@@ -661,7 +726,6 @@ ErrCode decodeBandT(Context* ctx, DecodeBandArgs& a, BandMaskState& ms) {
 
   // Lerc2.cpp:609 zero-fills the output; when every pixel is valid and coded by the micro-block stream each one is
   // overwritten, so the fill is deferred until the fused decoder is known not to apply.
-  const bool mayFast = nDepth == 1 && hd.numValidPixel == nPix && hd.microBlockSize == 8 && hd.version >= 3 && hd.zMin != hd.zMax;
   bool zeroFilled = false;
   auto zeroFill = [&]() { if (!zeroFilled) { cudaMemsetAsync(a.dData, 0, (size_t)nPix * nDepth * sizeof(T), st); zeroFilled = true; } };
   if (!mayFast) { bitsNow(); zeroFill(); if (!needStatus() || !launchChecksum()) return Failed; }
@@ -781,10 +845,11 @@ ErrCode decodeBandT(Context* ctx, DecodeBandArgs& a, BandMaskState& ms) {
     uint8_t pre[256];
     if (pos > 14 && pos - 14 <= sizeof pre && src.fetch(14, pos - 14, pre)) {
       fletcherHostPartial(pre, 0, (long long)pos - 14, pA, pD);
-      const int rc = decodeStreamFast<T>(ctx, hd, blob, pos, pA, pD, a.dData);
+      const int rc = decodeStreamFast<T>(ctx, hd, a, pos, pA, pD);
       if (rc < 0) return Failed;
       if (rc > 0) { globalStats().fastPathDecodes++; return Ok; }
     }
+    stageBlob();
     bitsNow();
     if (!needStatus() || !launchChecksum()) return Failed;
   }

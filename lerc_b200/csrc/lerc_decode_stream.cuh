@@ -59,6 +59,8 @@ struct StreamDecArgs {
   double invScale, zMax;                        // 2 * maxZError ; header zMax
   void* data;
   int nChunks;
+  int chunkBegin;                               // this launch: chunks chunkBegin .. chunkBegin + gridDim.x - 1 (a stream that arrives in strips is decoded strip by strip)
+  unsigned int* ticket;                         // this launch's ticket counter (zero at launch)
   unsigned long long* exitState;                // [nChunks] 0 = not yet, else (stream offset where the chunk's chain leaves it) + 1; bit 63: no chain
   unsigned long long* cntState;                 // [nChunks] look-back words over the chunks' block counts
   unsigned long long* groupState;               // [ceil(nChunks / 32)]
@@ -123,7 +125,7 @@ __global__ void __launch_bounds__(DS_THREADS, 7) k_decode_stream(StreamDecArgs a
 
   // ---- ticket, copy engine
   if (tid == 0) {
-    const int c = (int)atomicAdd(&a.res->ticket, 1u);
+    const int c = a.chunkBegin + (int)atomicAdd(a.ticket, 1u);
     sChunk = c;
     const unsigned long long start = (unsigned long long)c * DS_CHUNK;
     const long long left = (long long)(a.streamLen - start);

@@ -17,6 +17,7 @@
 #include <cstring>
 #include <cstdio>
 #include <atomic>
+#include <cstdlib>
 
 namespace lerc {
 
@@ -772,12 +773,25 @@ bool encodeBandFast(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
   if (a.outCapacity < dataStart + 1) return false;                     // let the general path report BufferTooSmall exactly
 
   const size_t nGroups = (size_t)((nTiles + 31) / 32);
-  const size_t stateBytes = sizeof(FastEncResult) + (size_t)nTiles * 8 + 2 * nGroups * 8;
+  constexpr int MAXSTRIPS = 16;
+  const size_t stateBytes = sizeof(FastEncResult) + 64 + (size_t)nTiles * 8 + 2 * nGroups * 8;      // result | ticket counters | tile states | group states
   uint8_t* dState = (uint8_t*)ctx->arena.alloc(stateBytes);
   FastEncResult* hRes = (FastEncResult*)ctx->pinnedAlloc(sizeof(FastEncResult));
-  if (!dState || !hRes) return false;
+  unsigned long long* hEnd = (unsigned long long*)ctx->pinnedAlloc(8 * MAXSTRIPS);
+  if (!dState || !hRes || !hEnd) return false;
   FastEncResult* dRes = (FastEncResult*)dState;
   cudaMemsetAsync(dState, 0, stateBytes, st);
+  // A band that still sits in host memory is coded strip by strip (whole block rows) while its later strips are on their way: host
+  // to device copies on one stream, the kernels on the call's stream, and - for a host blob buffer - the finished part of the blob
+  // back on a third one, so that the two PCIe directions and the coding overlap.  Look-back state and result block carry over.
+  int nStrips = 1;
+  if (a.hData) {
+    const size_t bandBytesIn = (size_t)nPix * sizeof(T);
+    static const int stripLog2 = [] { const char* e = std::getenv("LERC_B200_STRIP_LOG2"); const int v = e ? std::atoi(e) : 0; return (v >= 10 && v <= 30) ? v : 23; }();   // ~8 MB strips
+    nStrips = (int)std::min<size_t>(MAXSTRIPS, std::max<size_t>(1, bandBytesIn >> stripLog2));
+    nStrips = std::min(nStrips, nTy);
+    if (!ctx->pipeStreams()) nStrips = 1;
+  }
 
   FastEncArgs fa;
   fa.data = a.dData; fa.nRows = a.nRows; fa.nCols = a.nCols; fa.nTx = nTx; fa.nTy = nTy; fa.dt = PixelTraits<T>::code;
@@ -793,10 +807,12 @@ bool encodeBandFast(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
   }
   uint8_t* blob = a.dOut + a.outOffset;
   fa.stream = blob + dataStart; fa.streamCap = a.outCapacity - dataStart; fa.regionOff = (long long)dataStart - 14;
-  fa.tileState = (unsigned long long*)(dState + sizeof(FastEncResult)); fa.res = dRes;
+  fa.tileState = (unsigned long long*)(dState + sizeof(FastEncResult) + 64); fa.res = dRes;
   fa.groupState = fa.tileState + nTiles; fa.groupAcc = fa.groupState + nGroups;   // look-back level 2: groups of 32 tiles
   fa.blob = blob; fa.dataStart = (int)dataStart; fa.nBlobsMore = 0; fa.blobCap = a.outCapacity;
   fa.fillEnd = (a.nBands == 1 && a.fillEnd && a.fillEnd > blob) ? a.fillEnd : nullptr;
+  uint8_t* const fillEnd = fa.fillEnd;
+  bool outPiped = false;
   {
     // persistent CTAs, tiles taken by ticket (no co-residency assumption); shared memory opt-in and occupancy once per device
     constexpr size_t smem = (size_t)EncTile<T>::SMEM;
@@ -809,13 +825,52 @@ bool encodeBandFast(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
       ctasPerSmOf[dv].store(ctasPerSm, std::memory_order_relaxed);
     }
     int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-    const long long grid = std::min<long long>(nTiles, (long long)ctasPerSm * std::max(sms, 1));   // all CTAs resident (the zero fill at the end waits for the last tile)
-    LaunchScope scope_(ctx, "k_encode_tile<T>");
-    k_encode_tile<T, 3><<<(unsigned)grid, ENC_THREADS, smem, ctx->stream>>>(fa); ctx->kernelLaunches++;
+    const int tpr = (nTx + TW - 1) / TW;
+    const size_t rowBytes = (size_t)a.nCols * sizeof(T);
+    // all host -> device copies first (their stream runs ahead of the kernels)
+    if (a.hData) {
+      cudaStream_t cin = nStrips > 1 ? ctx->copyIn : st;
+      for (int sI = 0; sI < nStrips; sI++) {
+        const int br0 = (int)((long long)nTy * sI / nStrips), br1 = (int)((long long)nTy * (sI + 1) / nStrips);
+        const size_t r0 = (size_t)br0 * 8, r1 = std::min<size_t>((size_t)br1 * 8, (size_t)a.nRows);
+        if (!cudaOk(cudaMemcpyAsync((uint8_t*)const_cast<void*>(a.dData) + r0 * rowBytes, (const uint8_t*)a.hData + r0 * rowBytes, (r1 - r0) * rowBytes,
+                                    cudaMemcpyHostToDevice, cin), "H2D strip")) { err = Failed; return true; }
+        if (nStrips > 1) cudaEventRecord(ctx->evStrip[0][sI], cin);
+      }
+      a.hData = nullptr;                                               // (the band is on its way to dData in full, whatever happens below)
+    }
+    outPiped = nStrips > 1 && a.hOut != nullptr;
+    for (int sI = 0; sI < nStrips; sI++) {
+      const int br0 = (int)((long long)nTy * sI / nStrips), br1 = (int)((long long)nTy * (sI + 1) / nStrips);
+      fa.tileBegin = br0 * tpr; fa.tileEnd = br1 * tpr;
+      fa.ticket = (unsigned int*)(dState + sizeof(FastEncResult)) + sI;
+      fa.fillEnd = sI == nStrips - 1 ? fillEnd : nullptr;
+      if (nStrips > 1) cudaStreamWaitEvent(st, ctx->evStrip[0][sI], 0);
+      const long long grid = std::min<long long>((long long)(fa.tileEnd - fa.tileBegin), (long long)ctasPerSm * std::max(sms, 1));   // all CTAs resident (the zero fill at the end waits for the last tile)
+      { LaunchScope scope_(ctx, "k_encode_tile<T>"); k_encode_tile<T, 3><<<(unsigned)grid, ENC_THREADS, smem, st>>>(fa); ctx->kernelLaunches++; }
+      if (outPiped) {                                                  // where the stream ends after this strip: the inclusive prefix of its last tile
+        cudaMemcpyAsync(hEnd + sI, fa.tileState + (fa.tileEnd - 1), 8, cudaMemcpyDeviceToHost, st);
+        if (sI == nStrips - 1) cudaMemcpyAsync(hRes, dRes, sizeof(FastEncResult), cudaMemcpyDeviceToHost, st);
+        cudaEventRecord(ctx->evStrip[1][sI], st);
+      }
+    }
+    fa.fillEnd = fillEnd;
   }
-  if (!cudaOk(cudaMemcpyAsync(hRes, dRes, sizeof(FastEncResult), cudaMemcpyDeviceToHost, st), "D2H fast result")) { err = Failed; return true; }
-  if (!cudaOk(cudaStreamSynchronize(st), "sync")) { err = Failed; return true; }
+  if (outPiped) {
+    // the finished part of the stream goes to the caller's buffer while the next strips are coded (the prefix follows at the end)
+    unsigned long long prev = 0;
+    for (int sI = 0; sI < nStrips; sI++) {
+      if (!cudaOk(cudaEventSynchronize(ctx->evStrip[1][sI]), "strip sync")) { err = Failed; return true; }
+      const unsigned long long end = std::min<unsigned long long>(hEnd[sI] & ((1ull << 62) - 1), (unsigned long long)(a.outCapacity - dataStart));
+      if (end > prev) cudaMemcpyAsync(a.hOut + dataStart + prev, blob + dataStart + prev, (size_t)(end - prev), cudaMemcpyDeviceToHost, ctx->copyOut);
+      prev = std::max(prev, end);
+    }
+  } else {
+    if (!cudaOk(cudaMemcpyAsync(hRes, dRes, sizeof(FastEncResult), cudaMemcpyDeviceToHost, st), "D2H fast result")) { err = Failed; return true; }
+    if (!cudaOk(cudaStreamSynchronize(st), "sync")) { err = Failed; return true; }
+  }
   if (!cudaOk(cudaGetLastError(), "k_encode_tile")) { err = Failed; return true; }
+  struct DrainOut { Context* c; bool on; ~DrainOut() { if (on) cudaStreamSynchronize(c->copyOut); } } drainOut{ctx, outPiped};   // (whatever the verdict: no copy into the caller's buffer is left in flight)
 
   // ---- were the assumptions right?  (On the host: a single warp doing this at the end of the kernel runs cold code at the pace of its
   // instruction fetches, ~8 us measured; here it costs nothing and the prefix follows in stream order.)
@@ -862,7 +917,8 @@ bool encodeBandFast(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
   fletcherHostPartial(pb.b + 14, 0, (long long)p - 14, A, D);
   hd.checksum = fletcherFinish(A, D, (long long)total - 14);
   std::memcpy(pb.b + 10, &hd.checksum, 4);
-  LERC_LAUNCH(ctx, k_write_prefix, 1, 128, 0, blob, pb);
+  if (outPiped) { std::memcpy(a.hOut, pb.b, (size_t)pb.n); a.hostCopied = true; }        // (the stream's bytes are on their way on copyOut: drained on return)
+  else LERC_LAUNCH(ctx, k_write_prefix, 1, 128, 0, blob, pb);
   a.tailFilled = fa.fillEnd != nullptr;
 
   // validity bookkeeping the band loop expects (Lerc.cpp:659-741): this band is all valid
@@ -893,6 +949,10 @@ ErrCode encodeBandT(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
     if (ctx->arena.retired.empty()) ctx->arena.used = arenaMark;
     ctx->pinnedUsed = pinnedMark;
     bandBytes = 0;
+  }
+  if (a.hData) {                                                       // the band is still in host memory (the single-pass encoder did not take it)
+    if (!cudaOk(cudaMemcpyAsync(const_cast<void*>(a.dData), a.hData, (size_t)nPix * nDepth * sizeof(T), cudaMemcpyHostToDevice, st), "H2D band")) return Failed;
+    a.hData = nullptr;
   }
 
   HeaderInfo hd;

@@ -46,7 +46,10 @@ struct FastEncArgs {
   FastEncResult* res;
   unsigned long long* groupState;      // [ceil(nTiles / 32)], zero-initialised: aggregates of 32 consecutive tiles (two-round look-back); nullptr = plain chain
   unsigned long long* groupAcc;        // [ceil(nTiles / 32)], zero-initialised: atomic accumulators of the groups (lerc_lookback.cuh)
-  // k_encode_tile only: row-0 test of TryRaiseMaxZError (Lerc2.cpp:1233-1339), zero fill behind the blob
+  // k_encode_tile only: the tiles [tileBegin, tileEnd) of this launch (a band may be coded strip by strip while its rows arrive from the
+  // host; look-back state and result block carry over), their ticket counter (zero-initialised, one per launch);
+  // row-0 test of TryRaiseMaxZError (Lerc2.cpp:1233-1339), zero fill behind the blob
+  int tileBegin, tileEnd; unsigned int* ticket;
   double raiseFac[9]; int nRaise;
   uint8_t* blob; int dataStart, nBlobsMore;            // where the band blob starts; header field
   unsigned long long blobCap;                          // bytes available from `blob`

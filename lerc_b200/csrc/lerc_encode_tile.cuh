@@ -177,9 +177,9 @@ __global__ void __launch_bounds__(ENC_THREADS, MINB) k_encode_tile(FastEncArgs a
 
   if (tid == 0) {
     mbarInit(&sBarFull, 1); mbarInit(&sBarScan[0], 1); mbarInit(&sBarScan[1], 1); mbarInit(&sBarOff[0], 1); mbarInit(&sBarOff[1], 1);
-    const int t = (int)atomicAdd(&a.res->ticket, 1u);
+    const int t = a.tileBegin + (int)atomicAdd(a.ticket, 1u);
     sTileNext = t;
-    if (vecOk && t < nTiles) issueLoad(t);
+    if (vecOk && t < a.tileEnd) issueLoad(t);
   }
   for (int i = tid; i < 2 * C::STAGE_BYTES / 16; i += ENC_THREADS) ((uint4*)(tileSmem + C::IN_BYTES))[i] = make_uint4(0, 0, 0, 0);
   __syncthreads();
@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(ENC_THREADS, MINB) k_encode_tile(FastEncArgs a
   int pendK = -1; uint32_t pendBytes = 0;                          // the tile whose staging image still waits for its offset
   int tile = sTileNext;
   int k = 0;                                                        // tiles this CTA has posted to its control warp
-  for (; tile < nTiles; k++) {
+  for (; tile < a.tileEnd; k++) {
     int nextT = 0;
     const int tyT = tile / tpr, seg = tile - tyT * tpr;
     const int bx0 = seg * TW;                                      // first block column of the tile
@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(ENC_THREADS, MINB) k_encode_tile(FastEncArgs a
     }
     namedBarSync(1, ENC_COMPUTE);
     const uint32_t tileBytes = sOff[TW];
-    if (tid == 0) nextT = (int)atomicAdd(&a.res->ticket, 1u);      // ticket of tile k + 1: in flight while this tile is packed
+    if (tid == 0) nextT = a.tileBegin + (int)atomicAdd(a.ticket, 1u);      // ticket of tile k + 1: in flight while this tile is packed
     // row 0 of the image against the coarser decimal grids (block row 0 only; behind the publication, so that nobody's look-back waits for it)
     if (isFlt && a.nRaise > 0 && tyT == 0) encRaiseRow0<T>(a, (const T*)sIn, min(TW * 8, a.nCols - bx0 * 8), tid, ENC_COMPUTE);
 
@@ -418,7 +418,7 @@ __global__ void __launch_bounds__(ENC_THREADS, MINB) k_encode_tile(FastEncArgs a
       if (tid == 0) sTileNext = nextT;
       namedBarSync(1, ENC_COMPUTE);                                  // image complete, sIn free
       const int tn = sTileNext;
-      if (tid == 0 && vecOk && tn < nTiles) issueLoad(tn);
+      if (tid == 0 && vecOk && tn < a.tileEnd) issueLoad(tn);
       if (pendK >= 0) {
         mbarWait(&sBarOff[pendK & 1], (uint32_t)(pendK >> 1) & 1u);
         uint32_t* pst = (uint32_t*)(tileSmem + C::IN_BYTES + (pendK & 1) * C::STAGE_BYTES);
@@ -462,7 +462,7 @@ __global__ void __launch_bounds__(ENC_THREADS, MINB) k_encode_tile(FastEncArgs a
       if (tid == 0) sTileNext = nextT;
       namedBarSync(1, ENC_COMPUTE);                                  // image cleared, sIn free
       const int tn = sTileNext;
-      if (tid == 0 && vecOk && tn < nTiles) issueLoad(tn);
+      if (tid == 0 && vecOk && tn < a.tileEnd) issueLoad(tn);
       tile = tn;
     }
   }

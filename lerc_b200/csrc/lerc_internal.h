@@ -93,6 +93,11 @@ struct Context {
   // to it; joinSide() switches back and makes `stream` wait for the side work.
   cudaStream_t side = nullptr, mainSaved = nullptr;
   cudaEvent_t evFork = nullptr, evJoin = nullptr;
+  // host <-> device pipelines of the single-pass paths (strips of a host raster / blob move while earlier strips are coded): one stream
+  // per direction and a few events without timing, created on first use
+  cudaStream_t copyIn = nullptr, copyOut = nullptr;
+  cudaEvent_t evStrip[2][16] = {};
+  bool pipeStreams();
   bool sidePending = false;
   bool drainOnRelease = true;   // releaseContext synchronises the call's stream unless the call says its stream is idle / its results are stream-ordered
   void forkSide();
@@ -151,6 +156,10 @@ struct EncodeBandArgs {
   bool prefiltered = false, isAllInt = false, passNoData = false;
   double noDataVal = 0, noDataOrig = 0;
   bool anyMaskModified;           // in/out across bands (Lerc.cpp:714-720)
+  const void* hData = nullptr;    // in: the band's pixels in HOST memory when they have not been copied to dData yet (the single-pass encoder
+                                  //     copies strip by strip while it codes; everybody else calls stageBand first)
+  uint8_t* hOut = nullptr;        // in: host destination of this band's blob (one-band calls with a host output buffer), else nullptr
+  bool hostCopied = false;        // out: the band's blob is in hOut already
   uint8_t* dOut;                  // device output buffer (whole multi-band blob), may be nullptr for size-only
   uint8_t* fillEnd = nullptr;     // in: end of the caller's device buffer when the encoder may zero-fill behind the blob itself (one band)
   bool tailFilled = false;        // out: it did
@@ -170,6 +179,12 @@ struct DecodeBandArgs {
   const ByteSource* src = nullptr; size_t srcOff = 0;   // the caller's view of the whole blob and this band's offset in it
   void* dData;                    // device output for this band
   uint8_t* dValidBytes;           // device byte mask output for this band or nullptr
+  // host-resident calls: bytes of hBlob that are NOT yet in dBlob (decodeBand copies them itself; the stream decoder strip by strip,
+  // overlapped with the decoding) and the caller's host array for the band (the stream decoder sends finished rows there while
+  // it still decodes; hostCopied says it did)
+  size_t pendingBlob = 0;
+  uint8_t* hOut = nullptr;
+  bool hostCopied = false;
 };
 ErrCode decodeBand(Context* ctx, DecodeBandArgs& a, BandMaskState& ms);
 
