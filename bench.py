@@ -116,6 +116,10 @@ def cpu_reference_run(workload, seconds_budget=20.0, threads=None):
     rows, cols, depth, dt, mz, desc = WORKLOADS[workload]
     # bounded sample: a horizontal strip of the workload raster per thread (the library is single-threaded and
     # re-entrant: one independent call per core)
+    try:                                               # (the GPU arm may have bound this process to its GPU's NUMA node: the CPU arm uses every core)
+        os.sched_setaffinity(0, range(os.cpu_count() or 1))
+    except OSError:
+        pass
     threads = threads or os.cpu_count() or 1
     strip_rows = min(rows, 1024 if workload in ("c2", "c2l") else 512)
     if workload == "c5":                               # one 256 x 256 tile per call, as the reference's tile callers do
@@ -436,6 +440,27 @@ def main_tiles(args, lib, rank, world, local_rank, warm, peak_gbs, peak_src, sub
 
 
 # ---------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa(local_rank):
+    """pins this process to the CPUs nearest to its GPU (NVML's affinity mask), so that the pinned host buffers of the end-to-end
+    leg are allocated on the GPU's NUMA node; returns the number of CPUs in the mask or None"""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = int(vis.split(",")[local_rank]) if vis and vis.split(",")[local_rank].strip().isdigit() else local_rank
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = [w * 64 + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1]
+        cpus = [c for c in cpus if c in os.sched_getaffinity(0)]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -475,6 +500,7 @@ def main():
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device: lerc_b200 has no CPU fallback"
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa(local_rank)                               # (before any pinned allocation: first touch puts staging next to the GPU)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = product_lib()
@@ -649,9 +675,51 @@ def main():
     t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e = {"value": world * n_px / float(t.item()) / 1e9, "unit": "Gpixels/s", "ms_per_step": float(t.item()) * 1e3,
-           "h2d_bytes_per_step": raw_bytes + nb, "d2h_bytes_per_step": nb + raw_bytes, "timer": "host wall clock around the synchronous C-API calls"}
+    e2e_ms = float(t.item()) * 1e3
+    e2e = {"value": world * n_px / float(t.item()) / 1e9, "unit": "Gpixels/s", "ms_per_step": e2e_ms,
+           "h2d_bytes_per_step": raw_bytes + nb, "d2h_bytes_per_step": nb + raw_bytes, "timer": "host wall clock around the synchronous C-API calls",
+           "pcie_gbs_per_direction": (raw_bytes + nb) / (e2e_ms * 1e-3) / 1e9,
+           "pipelining": "inside each call: strips of block rows / stream chunks, H2D | kernels | D2H on three streams (LERC_B200_STRIP_LOG2, default 8 MB strips)"}
     assert np.abs(h_out.numpy().astype(np.float64) - h_in[(E2E - 1) % 2].numpy().astype(np.float64)).max() <= max(mz, 0.5 if dt < 6 else 0) * 1.1 + 1e-12
+
+    # ---- two callers: one thread encodes raster i + 1 while another decodes blob i (two library contexts; the calls are synchronous and
+    # release the GIL), so that both PCIe directions are busy all the time.  Reported beside the single-caller figure, not instead of it.
+    if not args.no_sub:
+        import threading
+        h_blob2 = [h_blob, torch.empty(cap, dtype=torch.uint8).pin_memory()]
+        nw2 = [C.c_uint(0), C.c_uint(0)]
+        errs = []
+
+        def enc_job(i):
+            if enc(h_in[i % 2].data_ptr(), dt, depth, cols, rows, 1, 0, None, mz, h_blob2[i % 2].data_ptr(), tight[0], C.addressof(nw2[i % 2])) != 0:
+                errs.append(("enc", i))
+
+        def dec_job(i):
+            if dec(h_blob2[i % 2].data_ptr(), nw2[i % 2].value, 0, None, depth, cols, rows, 1, dt, h_out.data_ptr()) != 0:
+                errs.append(("dec", i))
+
+        def run_two(n):
+            enc_job(0)
+            for i in range(n):
+                ta = threading.Thread(target=enc_job, args=(i + 1,))
+                tb = threading.Thread(target=dec_job, args=(i,))
+                ta.start(); tb.start(); ta.join(); tb.join()
+
+        run_two(2)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        run_two(E2E)
+        two_s = (time.perf_counter() - t0) / (E2E + 0.5)              # (E2E decodes + E2E + 1 encodes)
+        t2 = torch.tensor([two_s], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        assert not errs, errs
+        assert np.abs(h_out.numpy().astype(np.float64) - h_in[(E2E - 1) % 2].numpy().astype(np.float64)).max() <= max(mz, 0.5 if dt < 6 else 0) * 1.1 + 1e-12
+        e2e["two_callers"] = {"value": world * n_px / float(t2.item()) / 1e9, "unit": "Gpixels/s", "ms_per_step": float(t2.item()) * 1e3,
+                              "pcie_gbs_per_direction": (raw_bytes + nb) / float(t2.item()) / 1e9,
+                              "what": "encode of raster i + 1 and decode of blob i issued by two host threads at the same time (same C-API calls, same host buffers)"}
+    e2e["numa_bound_cpus"] = numa
 
     # ---- the other BASELINE configs as sub-records (every rank takes part: c5 gathers over NCCL, c4 is one raster per rank)
     subs = {}

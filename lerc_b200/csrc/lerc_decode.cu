@@ -426,10 +426,10 @@ int decodeStreamFast(Context* ctx, const HeaderInfo& hd, DecodeBandArgs& ba, siz
   for (int sI = 0; sI < nStrips; sI++) {
     const int cb = (int)((long long)nChunks * sI / nStrips), ce = (int)((long long)nChunks * (sI + 1) / nStrips);
     sa.chunkBegin = cb; sa.ticket = (unsigned int*)(dState + 64) + sI;
+    sa.hostEnd = outPiped ? hEnd + sI : nullptr;                      // (blocks behind this strip, written by the kernel into mapped host memory)
     if (inPiped) cudaStreamWaitEvent(st, ctx->evStrip[0][sI], 0);
     { LaunchScope scope_(ctx, "k_decode_stream<T>"); k_decode_stream<T><<<(unsigned)(ce - cb), DS_THREADS, smem, st>>>(sa); ctx->kernelLaunches++; }
     if (outPiped) {
-      cudaMemcpyAsync(hEnd + sI, sa.cntState + (ce - 1), 8, cudaMemcpyDeviceToHost, st);      // inclusive block count behind this strip
       if (sI == nStrips - 1) cudaMemcpyAsync(hStatus, &sa.res->status, 4, cudaMemcpyDeviceToHost, st);
       cudaEventRecord(ctx->evStrip[1][sI], st);
     }
@@ -441,7 +441,7 @@ int decodeStreamFast(Context* ctx, const HeaderInfo& hd, DecodeBandArgs& ba, siz
     for (int sI = 0; sI < nStrips && ok; sI++) {
       ok = cudaOk(cudaEventSynchronize(ctx->evStrip[1][sI]), "strip sync");
       if (!ok) break;
-      const unsigned long long blocks = hEnd[sI] & LB_VAL;
+      const unsigned long long blocks = hEnd[sI];
       const int rows = sI == nStrips - 1 ? hd.nRows : (int)std::min<unsigned long long>((unsigned long long)hd.nRows, blocks / (unsigned)sa.nTx * 8);
       if (rows > rowsSent) { cudaMemcpyAsync(ba.hOut + (size_t)rowsSent * rowBytes, (const uint8_t*)dData + (size_t)rowsSent * rowBytes, (size_t)(rows - rowsSent) * rowBytes, cudaMemcpyDeviceToHost, ctx->copyOut); rowsSent = rows; }
     }

@@ -60,7 +60,8 @@ struct StreamDecArgs {
   void* data;
   int nChunks;
   int chunkBegin;                               // this launch: chunks chunkBegin .. chunkBegin + gridDim.x - 1 (a stream that arrives in strips is decoded strip by strip)
-  unsigned int* ticket;                         // this launch's ticket counter (zero at launch)
+unsigned long long* hostEnd;                  // mapped host word or nullptr
+    unsigned int* ticket;                         // this launch's ticket counter (zero at launch)
   unsigned long long* exitState;                // [nChunks] 0 = not yet, else (stream offset where the chunk's chain leaves it) + 1; bit 63: no chain
   unsigned long long* cntState;                 // [nChunks] look-back words over the chunks' block counts
   unsigned long long* groupState;               // [ceil(nChunks / 32)]
@@ -320,6 +321,7 @@ __global__ void __launch_bounds__(DS_THREADS, 7) k_decode_stream(StreamDecArgs a
     const unsigned long long blk0 = lookbackExclusive(a.cntState, a.groupAcc, a.groupState, c, (unsigned long long)totalW, lane);
     if (lane == 0) {
       sBlk0 = blk0;
+      if (c == a.chunkBegin + (int)gridDim.x - 1 && a.hostEnd) *(volatile unsigned long long*)a.hostEnd = blk0 + (unsigned long long)totalW;   // (mapped host memory: blocks behind this launch)
       if (c == a.nChunks - 1 && sOk && blk0 + (unsigned long long)totalW != (unsigned long long)nBlocks) atomicOr(&a.res->status, DSF_FALLBACK | 2048);
     }
   }

@@ -845,11 +845,11 @@ bool encodeBandFast(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
       fa.tileBegin = br0 * tpr; fa.tileEnd = br1 * tpr;
       fa.ticket = (unsigned int*)(dState + sizeof(FastEncResult)) + sI;
       fa.fillEnd = sI == nStrips - 1 ? fillEnd : nullptr;
+      fa.hostEnd = outPiped ? hEnd + sI : nullptr;                     // (written by the kernel itself: a small copy would queue behind the blob pieces on the copy engine)
       if (nStrips > 1) cudaStreamWaitEvent(st, ctx->evStrip[0][sI], 0);
       const long long grid = std::min<long long>((long long)(fa.tileEnd - fa.tileBegin), (long long)ctasPerSm * std::max(sms, 1));   // all CTAs resident (the zero fill at the end waits for the last tile)
       { LaunchScope scope_(ctx, "k_encode_tile<T>"); k_encode_tile<T, 3><<<(unsigned)grid, ENC_THREADS, smem, st>>>(fa); ctx->kernelLaunches++; }
-      if (outPiped) {                                                  // where the stream ends after this strip: the inclusive prefix of its last tile
-        cudaMemcpyAsync(hEnd + sI, fa.tileState + (fa.tileEnd - 1), 8, cudaMemcpyDeviceToHost, st);
+      if (outPiped) {
         if (sI == nStrips - 1) cudaMemcpyAsync(hRes, dRes, sizeof(FastEncResult), cudaMemcpyDeviceToHost, st);
         cudaEventRecord(ctx->evStrip[1][sI], st);
       }
@@ -861,7 +861,7 @@ bool encodeBandFast(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
     unsigned long long prev = 0;
     for (int sI = 0; sI < nStrips; sI++) {
       if (!cudaOk(cudaEventSynchronize(ctx->evStrip[1][sI]), "strip sync")) { err = Failed; return true; }
-      const unsigned long long end = std::min<unsigned long long>(hEnd[sI] & ((1ull << 62) - 1), (unsigned long long)(a.outCapacity - dataStart));
+      const unsigned long long end = std::min<unsigned long long>(hEnd[sI], (unsigned long long)(a.outCapacity - dataStart));
       if (end > prev) cudaMemcpyAsync(a.hOut + dataStart + prev, blob + dataStart + prev, (size_t)(end - prev), cudaMemcpyDeviceToHost, ctx->copyOut);
       prev = std::max(prev, end);
     }

@@ -49,6 +49,7 @@ struct FastEncArgs {
   // k_encode_tile only: the tiles [tileBegin, tileEnd) of this launch (a band may be coded strip by strip while its rows arrive from the
   // host; look-back state and result block carry over), their ticket counter (zero-initialised, one per launch);
   // row-0 test of TryRaiseMaxZError (Lerc2.cpp:1233-1339), zero fill behind the blob
+  unsigned long long* hostEnd;     // mapped host word or nullptr: where the stream ends behind tile tileEnd - 1 (strip pipelining of host-resident calls)
   int tileBegin, tileEnd; unsigned int* ticket;
   double raiseFac[9]; int nRaise;
   uint8_t* blob; int dataStart, nBlobsMore;            // where the band blob starts; header field

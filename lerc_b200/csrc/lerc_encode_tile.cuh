@@ -194,6 +194,7 @@ __global__ void __launch_bounds__(ENC_THREADS, MINB) k_encode_tile(FastEncArgs a
       const unsigned long long tileBytes = sMailBytes[k & 1];
       const unsigned long long excl = lookbackExclusive(st, a.groupAcc, gs, tile, tileBytes, lane);
       if (lane == 0) {
+        if (tile == a.tileEnd - 1 && a.hostEnd) *(volatile unsigned long long*)a.hostEnd = excl + tileBytes;      // (mapped host memory: read by the host after this launch's event)
         if (tile == nTiles - 1) { a.res->totalBytes = excl + tileBytes; __threadfence(); *(volatile unsigned int*)&a.res->totalReady = 1u; }
         sOffS[k & 1] = excl;
         mbarArrive(&sBarOff[k & 1]);
