@@ -9,6 +9,7 @@
 #include "lerc_device.cuh"
 #include "lerc_kernels.h"
 #include <cstring>
+#include <chrono>
 #include <cstdio>
 #include <cmath>
 
@@ -369,8 +370,11 @@ int decodeStreamFast(Context* ctx, const HeaderInfo& hd, DecodeBandArgs& ba, siz
   const uint8_t* dBlob = ba.dBlob; void* dData = ba.dData;
   const size_t streamLen = (size_t)hd.blobSize - streamPos;
   if (streamLen == 0 || streamLen >= 0xfff00000ull || !std::isfinite(hd.zMax) || std::getenv("LERC_B200_NO_FAST")) return 0;
+  static const bool trace = std::getenv("LERC_B200_TRACE") != nullptr;
+  const auto t0 = std::chrono::steady_clock::now();
+  auto us = [&]() { return (double)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count() * 1e-3; };
   cudaStream_t st = ctx->stream;
-  constexpr int MAXSTRIPS = 16;
+  constexpr int MAXSTRIPS = kMaxStrips;
   const int nChunks = (int)((streamLen + DS_CHUNK - 1) / DS_CHUNK);
   const size_t nGroups = ((size_t)nChunks + 31) / 32;
   const size_t stateBytes = 128 + ((size_t)nChunks * 2 + nGroups * 2) * 8;         // result | ticket counters | chunk and group states
@@ -379,6 +383,7 @@ int decodeStreamFast(Context* ctx, const HeaderInfo& hd, DecodeBandArgs& ba, siz
   unsigned long long* hEnd = (unsigned long long*)ctx->pinnedAlloc(8 * MAXSTRIPS);
   if (!dState || !hStatus || !hEnd) return 0;
   cudaMemsetAsync(dState, 0, stateBytes, st);
+  *hStatus = 0;
   StreamDecArgs sa;
   sa.stream = dBlob + streamPos; sa.streamLen = streamLen;
   sa.nRows = hd.nRows; sa.nCols = hd.nCols; sa.nTx = (hd.nCols + 7) / 8; sa.nTy = (hd.nRows + 7) / 8; sa.version = hd.version;
@@ -400,13 +405,11 @@ int decodeStreamFast(Context* ctx, const HeaderInfo& hd, DecodeBandArgs& ba, siz
   // as soon as it is there (exit chain and block counts carry over in the look-back state), and the block rows a strip has
   // completed go back to the caller's array on a third stream while the next strips are decoded.
   const size_t rowBytes = (size_t)hd.nCols * sizeof(T);
-  int nStrips = 1;
+  int nStrips = 1, stripAt[kMaxStrips + 1] = {0, nChunks};
   if (ba.pendingBlob || ba.hOut) {
-    static const int stripLog2 = [] { const char* e = std::getenv("LERC_B200_STRIP_LOG2"); const int v = e ? std::atoi(e) : 0; return (v >= 10 && v <= 30) ? v : 23; }();
-    const size_t moved = std::max(ba.pendingBlob ? streamLen : 0, ba.hOut ? rowBytes * (size_t)hd.nRows : 0);
-    nStrips = (int)std::min<size_t>(MAXSTRIPS, std::max<size_t>(1, moved >> stripLog2));
-    nStrips = std::min(nStrips, nChunks);
-    if (nStrips > 1 && !ctx->pipeStreams()) nStrips = 1;
+    // (the schedule follows the larger of the two transfers: the rows going back as a rule)
+    nStrips = stripSchedule(std::max(ba.pendingBlob ? streamLen : 0, ba.hOut ? rowBytes * (size_t)hd.nRows : 0), nChunks, stripAt);
+    if (nStrips > 1 && !ctx->pipeStreams()) { nStrips = 1; stripAt[1] = nChunks; }
   }
   const bool outPiped = nStrips > 1 && ba.hOut != nullptr;
   if (ba.pendingBlob) {
@@ -414,7 +417,7 @@ int decodeStreamFast(Context* ctx, const HeaderInfo& hd, DecodeBandArgs& ba, siz
     cudaStream_t cin = nStrips > 1 ? ctx->copyIn : st;
     size_t from = 0;
     for (int sI = 0; sI < nStrips; sI++) {
-      const int ce = (int)((long long)nChunks * (sI + 1) / nStrips);
+      const int ce = stripAt[sI + 1];
       const size_t to = sI == nStrips - 1 ? ba.pendingBlob : std::min(ba.pendingBlob, streamPos + (size_t)ce * DS_CHUNK + (size_t)DecStream<T>::LA + 32);
       if (to > from && !cudaOk(cudaMemcpyAsync(dst + from, ba.hBlob + from, to - from, cudaMemcpyHostToDevice, cin), "H2D strip")) return -1;
       from = std::max(from, to);
@@ -424,17 +427,18 @@ int decodeStreamFast(Context* ctx, const HeaderInfo& hd, DecodeBandArgs& ba, siz
   }
   const bool inPiped = nStrips > 1 && ba.pendingBlob != 0;
   for (int sI = 0; sI < nStrips; sI++) {
-    const int cb = (int)((long long)nChunks * sI / nStrips), ce = (int)((long long)nChunks * (sI + 1) / nStrips);
+    const int cb = stripAt[sI], ce = stripAt[sI + 1];
     sa.chunkBegin = cb; sa.ticket = (unsigned int*)(dState + 64) + sI;
+    sa.hostStatus = outPiped ? hStatus : nullptr;
     sa.hostEnd = outPiped ? hEnd + sI : nullptr;                      // (blocks behind this strip, written by the kernel into mapped host memory)
     if (inPiped) cudaStreamWaitEvent(st, ctx->evStrip[0][sI], 0);
     { LaunchScope scope_(ctx, "k_decode_stream<T>"); k_decode_stream<T><<<(unsigned)(ce - cb), DS_THREADS, smem, st>>>(sa); ctx->kernelLaunches++; }
     if (outPiped) {
-      if (sI == nStrips - 1) cudaMemcpyAsync(hStatus, &sa.res->status, 4, cudaMemcpyDeviceToHost, st);
       cudaEventRecord(ctx->evStrip[1][sI], st);
     }
   }
   ba.pendingBlob = 0;                                                 // (the whole blob is in dBlob once the call's stream has passed the last strip's event)
+  if (trace) std::fprintf(stderr, "[trace dec] %d strips enqueued at %.1f us\n", nStrips, us());
   if (outPiped) {
     int rowsSent = 0;
     bool ok = true;
@@ -443,10 +447,14 @@ int decodeStreamFast(Context* ctx, const HeaderInfo& hd, DecodeBandArgs& ba, siz
       if (!ok) break;
       const unsigned long long blocks = hEnd[sI];
       const int rows = sI == nStrips - 1 ? hd.nRows : (int)std::min<unsigned long long>((unsigned long long)hd.nRows, blocks / (unsigned)sa.nTx * 8);
+      if (trace) std::fprintf(stderr, "[trace dec] strip %d done at %.1f us, rows %d..%d\n", sI, us(), rowsSent, rows);
       if (rows > rowsSent) { cudaMemcpyAsync(ba.hOut + (size_t)rowsSent * rowBytes, (const uint8_t*)dData + (size_t)rowsSent * rowBytes, (size_t)(rows - rowsSent) * rowBytes, cudaMemcpyDeviceToHost, ctx->copyOut); rowsSent = rows; }
     }
     ok = cudaOk(cudaStreamSynchronize(ctx->copyOut), "copy out sync") && ok;
+    if (trace) std::fprintf(stderr, "[trace dec] copies drained at %.1f us\n", us());
     if (!ok) return -1;
+    if (!(*hStatus & DSF_REPORTED)) return -1;                        // (cannot happen: the last CTA of the last launch always reports)
+    *hStatus &= ~DSF_REPORTED;
     ba.hostCopied = true;                                             // (void if the verdict below is a fallback: the caller copies again)
   } else if (!cudaOk(cudaMemcpyAsync(hStatus, &sa.res->status, 4, cudaMemcpyDeviceToHost, st), "D2H stream status") || !cudaOk(cudaStreamSynchronize(st), "sync")) return -1;
   if (!cudaOk(cudaGetLastError(), "k_decode_stream")) return -1;

@@ -45,7 +45,7 @@ constexpr int DS_LIST = 264;                    // recorded positions per sub-ch
 constexpr int DS_PATCH = 48;                    // hops the patch walk may need before it joins the recorded chain
 constexpr int DS_HOPS = 4;                      // units a head-window position must parse to become the guess (windows without a strict candidate)
 constexpr int DS_THREADS = 128;
-enum { DSF_FALLBACK = 8, DSF_CHECKSUM = 2 };
+enum : unsigned int { DSF_FALLBACK = 8, DSF_CHECKSUM = 2, DSF_REPORTED = 0x80000000u };
 
 struct StreamDecResult {                        // device, zero-initialised per call
   unsigned int ticket, done, status, pad;
@@ -61,6 +61,7 @@ struct StreamDecArgs {
   int nChunks;
   int chunkBegin;                               // this launch: chunks chunkBegin .. chunkBegin + gridDim.x - 1 (a stream that arrives in strips is decoded strip by strip)
 unsigned long long* hostEnd;                  // mapped host word or nullptr
+  unsigned int* hostStatus;                     // mapped host word or nullptr: the final status word | DSF_REPORTED, written by the last CTA of the last launch
     unsigned int* ticket;                         // this launch's ticket counter (zero at launch)
   unsigned long long* exitState;                // [nChunks] 0 = not yet, else (stream offset where the chunk's chain leaves it) + 1; bit 63: no chain
   unsigned long long* cntState;                 // [nChunks] look-back words over the chunks' block counts
@@ -428,11 +429,16 @@ __global__ void __launch_bounds__(DS_THREADS, 7) k_decode_stream(StreamDecArgs a
     if (A | D) { atomicAdd(&a.res->fletA, A); atomicAdd(&a.res->fletD, D % 65535ull); }
     __threadfence();
     const unsigned int prev = atomicAdd(&a.res->done, 1u);
-    if (prev == (unsigned int)a.nChunks - 1 && a.haveChecksum) {
+    if (prev == (unsigned int)a.nChunks - 1) {
       __threadfence();
-      const unsigned long long tA = (*(volatile unsigned long long*)&a.res->fletA + a.prefA) % 65535ull;
-      const unsigned long long tD = (*(volatile unsigned long long*)&a.res->fletD % 65535ull + a.prefD) % 65535ull;
-      if (fletcherFinishFast(tA, tD, a.regionLen) != a.expectChecksum) atomicOr(&a.res->status, DSF_CHECKSUM);
+      unsigned int bits = 0;
+      if (a.haveChecksum) {
+        const unsigned long long tA = (*(volatile unsigned long long*)&a.res->fletA + a.prefA) % 65535ull;
+        const unsigned long long tD = (*(volatile unsigned long long*)&a.res->fletD % 65535ull + a.prefD) % 65535ull;
+        if (fletcherFinishFast(tA, tD, a.regionLen) != a.expectChecksum) bits = DSF_CHECKSUM;
+      }
+      const unsigned int all = atomicOr(&a.res->status, bits) | bits;
+      if (a.hostStatus) *(volatile unsigned int*)a.hostStatus = all | DSF_REPORTED;          // (mapped host memory: no copy behind the row copies)
     }
   }
 }

@@ -18,6 +18,7 @@
 #include <cstdio>
 #include <atomic>
 #include <cstdlib>
+#include <chrono>
 
 namespace lerc {
 
@@ -773,7 +774,10 @@ bool encodeBandFast(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
   if (a.outCapacity < dataStart + 1) return false;                     // let the general path report BufferTooSmall exactly
 
   const size_t nGroups = (size_t)((nTiles + 31) / 32);
-  constexpr int MAXSTRIPS = 16;
+  static const bool trace = std::getenv("LERC_B200_TRACE") != nullptr;
+  const auto t0 = std::chrono::steady_clock::now();
+  auto us = [&]() { return (double)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count() * 1e-3; };
+  constexpr int MAXSTRIPS = kMaxStrips;
   const size_t stateBytes = sizeof(FastEncResult) + 64 + (size_t)nTiles * 8 + 2 * nGroups * 8;      // result | ticket counters | tile states | group states
   uint8_t* dState = (uint8_t*)ctx->arena.alloc(stateBytes);
   FastEncResult* hRes = (FastEncResult*)ctx->pinnedAlloc(sizeof(FastEncResult));
@@ -784,13 +788,10 @@ bool encodeBandFast(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
   // A band that still sits in host memory is coded strip by strip (whole block rows) while its later strips are on their way: host
   // to device copies on one stream, the kernels on the call's stream, and - for a host blob buffer - the finished part of the blob
   // back on a third one, so that the two PCIe directions and the coding overlap.  Look-back state and result block carry over.
-  int nStrips = 1;
+  int nStrips = 1, stripAt[kMaxStrips + 1] = {0, nTy};
   if (a.hData) {
-    const size_t bandBytesIn = (size_t)nPix * sizeof(T);
-    static const int stripLog2 = [] { const char* e = std::getenv("LERC_B200_STRIP_LOG2"); const int v = e ? std::atoi(e) : 0; return (v >= 10 && v <= 30) ? v : 23; }();   // ~8 MB strips
-    nStrips = (int)std::min<size_t>(MAXSTRIPS, std::max<size_t>(1, bandBytesIn >> stripLog2));
-    nStrips = std::min(nStrips, nTy);
-    if (!ctx->pipeStreams()) nStrips = 1;
+    nStrips = stripSchedule((size_t)nPix * sizeof(T), nTy, stripAt);
+    if (nStrips > 1 && !ctx->pipeStreams()) { nStrips = 1; stripAt[1] = nTy; }
   }
 
   FastEncArgs fa;
@@ -831,7 +832,7 @@ bool encodeBandFast(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
     if (a.hData) {
       cudaStream_t cin = nStrips > 1 ? ctx->copyIn : st;
       for (int sI = 0; sI < nStrips; sI++) {
-        const int br0 = (int)((long long)nTy * sI / nStrips), br1 = (int)((long long)nTy * (sI + 1) / nStrips);
+        const int br0 = stripAt[sI], br1 = stripAt[sI + 1];
         const size_t r0 = (size_t)br0 * 8, r1 = std::min<size_t>((size_t)br1 * 8, (size_t)a.nRows);
         if (!cudaOk(cudaMemcpyAsync((uint8_t*)const_cast<void*>(a.dData) + r0 * rowBytes, (const uint8_t*)a.hData + r0 * rowBytes, (r1 - r0) * rowBytes,
                                     cudaMemcpyHostToDevice, cin), "H2D strip")) { err = Failed; return true; }
@@ -841,7 +842,7 @@ bool encodeBandFast(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
     }
     outPiped = nStrips > 1 && a.hOut != nullptr;
     for (int sI = 0; sI < nStrips; sI++) {
-      const int br0 = (int)((long long)nTy * sI / nStrips), br1 = (int)((long long)nTy * (sI + 1) / nStrips);
+      const int br0 = stripAt[sI], br1 = stripAt[sI + 1];
       fa.tileBegin = br0 * tpr; fa.tileEnd = br1 * tpr;
       fa.ticket = (unsigned int*)(dState + sizeof(FastEncResult)) + sI;
       fa.fillEnd = sI == nStrips - 1 ? fillEnd : nullptr;
@@ -856,6 +857,7 @@ bool encodeBandFast(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
     }
     fa.fillEnd = fillEnd;
   }
+  if (trace) std::fprintf(stderr, "[trace enc] %d strips enqueued at %.1f us\n", nStrips, us());
   if (outPiped) {
     // the finished part of the stream goes to the caller's buffer while the next strips are coded (the prefix follows at the end)
     unsigned long long prev = 0;
@@ -863,6 +865,7 @@ bool encodeBandFast(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
       if (!cudaOk(cudaEventSynchronize(ctx->evStrip[1][sI]), "strip sync")) { err = Failed; return true; }
       const unsigned long long end = std::min<unsigned long long>(hEnd[sI], (unsigned long long)(a.outCapacity - dataStart));
       if (end > prev) cudaMemcpyAsync(a.hOut + dataStart + prev, blob + dataStart + prev, (size_t)(end - prev), cudaMemcpyDeviceToHost, ctx->copyOut);
+      if (trace) std::fprintf(stderr, "[trace enc] strip %d done at %.1f us, blob bytes %llu..%llu\n", sI, us(), prev, end);
       prev = std::max(prev, end);
     }
   } else {
@@ -917,6 +920,7 @@ bool encodeBandFast(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
   fletcherHostPartial(pb.b + 14, 0, (long long)p - 14, A, D);
   hd.checksum = fletcherFinish(A, D, (long long)total - 14);
   std::memcpy(pb.b + 10, &hd.checksum, 4);
+  if (trace) std::fprintf(stderr, "[trace enc] verdict at %.1f us\n", us());
   if (outPiped) { std::memcpy(a.hOut, pb.b, (size_t)pb.n); a.hostCopied = true; }        // (the stream's bytes are on their way on copyOut: drained on return)
   else LERC_LAUNCH(ctx, k_write_prefix, 1, 128, 0, blob, pb);
   a.tailFilled = fa.fillEnd != nullptr;

@@ -11,6 +11,8 @@
 //
 // Reference citations are relative to /root/reference/src/LercLib.
 #pragma once
+#include <algorithm>
+#include <cstdlib>
 #include <cstdint>
 #include <cstddef>
 #include <vector>
@@ -187,6 +189,30 @@ struct DecodeBandArgs {
   bool hostCopied = false;
 };
 ErrCode decodeBand(Context* ctx, DecodeBandArgs& a, BandMaskState& ms);
+
+// Strip schedule of a pipelined host-resident call: `bytes` of payload in `nUnits` units (block rows / stream chunks).  Small strips
+// at both ends (the first kernel starts early, the last copy back is short), strips up to 8x larger in between (fewer launches
+// and synchronisations).  bounds[0..n] are unit indices, returns n <= maxStrips (1 = not worth pipelining).
+constexpr int kMaxStrips = 16;
+inline int stripSchedule(size_t bytes, int nUnits, int bounds[kMaxStrips + 1]) {
+  static const int smallLog2 = [] { const char* e = std::getenv("LERC_B200_STRIP_LOG2"); const int v = e ? std::atoi(e) : 0; return (v >= 10 && v <= 30) ? v : 20; }();   // smallest strip ~1 MB
+  bounds[0] = 0; bounds[1] = nUnits;
+  auto weight = [](int i, int n_) { return 1ll << std::min(std::min(i, n_ - 1 - i), 3); };
+  auto weights = [&](int n_) { long long t = 0; for (int i = 0; i < n_; i++) t += weight(i, n_); return t; };
+  int n = 1;
+  for (int cand = 2; cand <= std::min(kMaxStrips, nUnits); cand++) {   // as many strips as keep the smallest one above the floor
+    if ((long long)(bytes >> smallLog2) < weights(cand)) break;
+    n = cand;
+  }
+  if (n < 2) return 1;
+  const long long total = weights(n);
+  long long acc = 0;
+  for (int i = 0; i < n; i++) { acc += weight(i, n); bounds[i + 1] = (int)((long long)nUnits * acc / total); }
+  bounds[n] = nUnits;
+  int m = 0;                                                           // drop empty strips
+  for (int i = 1; i <= n; i++) if (bounds[i] > bounds[m]) bounds[++m] = bounds[i];
+  return std::max(m, 1);
+}
 
 // Tile batch (include/lerc_b200.h, lerc_tiles_encode.cuh / lerc_tiles_decode.cuh): every tileRows x tileCols window of a
 // one-band raster is its own Lerc2 blob.  hOffsets: host array of nTiles + 1 byte offsets into dOut / dBlobs.
