@@ -684,7 +684,7 @@ def main():
 
     # ---- two callers: one thread encodes raster i + 1 while another decodes blob i (two library contexts; the calls are synchronous and
     # release the GIL), so that both PCIe directions are busy all the time.  Reported beside the single-caller figure, not instead of it.
-    if not args.no_sub:
+    if True:
         import threading
         h_blob2 = [h_blob, torch.empty(cap, dtype=torch.uint8).pin_memory()]
         nw2 = [C.c_uint(0), C.c_uint(0)]
@@ -720,6 +720,29 @@ def main():
                               "pcie_gbs_per_direction": (raw_bytes + nb) / float(t2.item()) / 1e9,
                               "what": "encode of raster i + 1 and decode of blob i issued by two host threads at the same time (same C-API calls, same host buffers)"}
     e2e["numa_bound_cpus"] = numa
+    # what the link itself does on this box: one 64 MB pinned copy per direction alone, then both directions at once
+    probe_d, probe_d2 = torch.empty_like(h_in[0], device="cuda"), torch.empty_like(h_in[0], device="cuda")
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def probe(fn, reps=3):
+        best = 1e9
+        for _ in range(reps):
+            torch.cuda.synchronize(); t0 = time.perf_counter(); fn(); torch.cuda.synchronize()
+            best = min(best, time.perf_counter() - t0)
+        return best
+
+    def both():
+        with torch.cuda.stream(s1):
+            probe_d.copy_(h_in[0], non_blocking=True)
+        with torch.cuda.stream(s2):
+            h_out.copy_(probe_d2, non_blocking=True)
+
+    t_h2d = probe(lambda: probe_d.copy_(h_in[0], non_blocking=True))
+    t_d2h = probe(lambda: h_out.copy_(probe_d2, non_blocking=True))
+    t_both = probe(both)
+    e2e["pcie_measured_gbs"] = {"h2d_alone": raw_bytes / t_h2d / 1e9, "d2h_alone": raw_bytes / t_d2h / 1e9, "each_direction_when_both_run": raw_bytes / t_both / 1e9,
+                                "what": "one pinned copy of the raster per direction (torch copy_, wall clock), best of 3"}
+    del probe_d, probe_d2
 
     # ---- the other BASELINE configs as sub-records (every rank takes part: c5 gathers over NCCL, c4 is one raster per rank)
     subs = {}
