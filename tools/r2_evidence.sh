@@ -1,0 +1,24 @@
+#!/bin/bash
+# round 2 evidence call (one GPU): whole GPU suite, the default bench line, the reference arm, the ncu launch list of the same bench
+# command, and one --set full capture per dominant kernel (DRAM traffic per launch -> profiles/dram_traffic.json by tools/r2_collect.py)
+set -u
+OUT=gpurun_out/${R2OUT:-r2ev}
+mkdir -p "$OUT"
+git rev-parse HEAD > "$OUT/commit.txt" 2>/dev/null || cp .commit_for_gpu "$OUT/commit.txt" 2>/dev/null
+timeout 1200 python -m pytest tests -q -m gpu -p no:cacheprovider > "$OUT/gpu_tests.log" 2>&1
+tail -3 "$OUT/gpu_tests.log"
+timeout 900 python bench.py --steps 20 --warmup 5 > "$OUT/bench_n1.json" 2> "$OUT/bench_n1.err"
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > "$OUT/bench_reference_arm.json" 2> "$OUT/bench_reference_arm.err"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/launches.csv" python bench.py --steps 2 --warmup 3 --no-sub --no-cpu-baseline > "$OUT/bench_under_ncu.log" 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_encode_tile|k_decode_stream" -c 2 -o "$OUT/prof_c2" python tools/big_check.py > "$OUT/ncu_c2.log" 2>&1
+tail -2 "$OUT/ncu_c2.log"
+python - <<PY
+import json
+d = json.loads([l for l in open("$OUT/bench_n1.json") if l.startswith("{")][-1])
+print("c2", round(d["value"], 2), "Gpx/s", round(d["ms_per_step"], 4), "ms step_frac", round(d["roofline"]["step_frac"], 3), "e2e", round(d["e2e"]["value"], 2), d["e2e"].get("two_callers", {}).get("value"), d["e2e"].get("pcie_measured_gbs"))
+for k in ("c5", "c4", "c3"):
+    r = d.get(k)
+    if r: print(k, json.dumps({x: r[x] for x in r if x in ("value", "ms_per_step", "error", "step_frac")}))
+print("cpu", d.get("cpu_baseline"))
+print(open("$OUT/bench_reference_arm.json").read()[:600])
+PY
