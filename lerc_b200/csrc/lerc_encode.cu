@@ -849,7 +849,7 @@ bool encodeBandFast(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
       fa.hostEnd = outPiped ? hEnd + sI : nullptr;                     // (written by the kernel itself: a small copy would queue behind the blob pieces on the copy engine)
       if (nStrips > 1) cudaStreamWaitEvent(st, ctx->evStrip[0][sI], 0);
       const long long grid = std::min<long long>((long long)(fa.tileEnd - fa.tileBegin), (long long)ctasPerSm * std::max(sms, 1));   // all CTAs resident (the zero fill at the end waits for the last tile)
-      { LaunchScope scope_(ctx, "k_encode_tile<T>"); k_encode_tile<T, 3><<<(unsigned)grid, ENC_THREADS, smem, st>>>(fa); ctx->kernelLaunches++; }
+      { LaunchScope scope_(ctx, "k_encode_tile<T>"); k_encode_tile<T, 3><<<(unsigned)grid, ENC_THREADS, smem, st>>>(fa, FastBatchArgs{}); ctx->kernelLaunches++; }
       if (outPiped) {
         if (sI == nStrips - 1) cudaMemcpyAsync(hRes, dRes, sizeof(FastEncResult), cudaMemcpyDeviceToHost, st);
         cudaEventRecord(ctx->evStrip[1][sI], st);

@@ -67,6 +67,9 @@ struct FastBatchArgs {
   unsigned long long* imgState;        // [nImg], zero-initialised: look-back over whole blobs
   TileEncResult* imgRes;               // [nImg], zero-initialised
   uint8_t* out; unsigned long long outCap;
+  // k_encode_tile<T, MINB, true>: tiles of TW consecutive micro-blocks per image
+  int tilesPerImg;
+  uint32_t* tileLen;                   // [nImg * tilesPerImg] byte count of every tile (the look-back words lose it when they turn into prefixes)
 };
 struct FastNoBatch {                   // what the one-image kernel gets instead: nothing (the names fold to constants)
   static constexpr int imgCols = 0, imgRows = 0, nImgX = 0, nImgY = 0, rasterCols = 0, rasterRows = 0, segPerImg = 1, dataStart = 0;

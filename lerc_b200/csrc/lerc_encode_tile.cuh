@@ -140,8 +140,13 @@ __device__ __noinline__ void encRaiseRow0(const FastEncArgs& a, const T* __restr
 
 constexpr int ENC_COMPUTE = 256, ENC_THREADS = ENC_COMPUTE + 32;    // 8 compute warps + the control warp
 
-template <class T, int MINB>
-__global__ void __launch_bounds__(ENC_THREADS, MINB) k_encode_tile(FastEncArgs a) {
+// BATCH (tile batch, lerc_tiles_encode.cuh): the raster is cut into equal images, every image its own blob.  A tile is then TW
+// consecutive micro-blocks of ONE image in stream order = TW / nTx whole block rows (the host guarantees nTx | TW), staged side by
+// side in shared memory so that sizing and packing see the same 8-row strip as for a single image.  All tiles of all images
+// form one look-back chain; a blob starts at (bytes of all earlier tiles) + img * dataStart.  Per-image facts and checksum partials
+// go to fb.imgRes by atomics, tile by tile.
+template <class T, int MINB, bool BATCH = false>
+__global__ void __launch_bounds__(ENC_THREADS, MINB) k_encode_tile(FastEncArgs a, FastBatchArgs fb) {
   using K = typename PixelTraits<T>::Key;
   using C = EncTile<T>;
   constexpr bool isFlt = PixelTraits<T>::isFloat;
@@ -154,18 +159,32 @@ __global__ void __launch_bounds__(ENC_THREADS, MINB) k_encode_tile(FastEncArgs a
   __shared__ __align__(8) uint64_t sBarFull, sBarScan[2], sBarOff[2];
   __shared__ int sTileNext, sMailTile[2];
   __shared__ unsigned long long sMailBytes[2], sOffS[2];
+  __shared__ long long sRegS[2];                                  // checksum-region offset of the tile's first output byte
   __shared__ unsigned long long sKMin[8], sKMax[8], sFA[8], sFD[8];
   __shared__ unsigned int sFlg[8];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const T* data = (const T*)a.data;
-  const bool vecOk = (((long long)a.nCols * (int)sizeof(T)) % 16 == 0) && (((uintptr_t)data & 15) == 0);
+  const bool vecOk = BATCH || ((((long long)a.nCols * (int)sizeof(T)) % 16 == 0) && (((uintptr_t)data & 15) == 0));
   const int tpr = (a.nTx + TW - 1) / TW;                          // tiles per block row
-  const int nTiles = tpr * a.nTy;
+  const int nTiles = BATCH ? a.tileEnd : tpr * a.nTy;
+  const int rowsPerTile = BATCH ? TW / a.nTx : 1;                 // block rows of an image in one tile (BATCH)
   volatile unsigned long long* st = a.tileState;
 
   // the copy engine brings tile t into sIn (thread 0 of the compute warps)
   auto issueLoad = [&](int t) {
+    if (BATCH) {
+      const int img = t / fb.tilesPerImg, ti = t - img * fb.tilesPerImg;
+      const int iy = img / fb.nImgX, ix = img - iy * fb.nImgX;
+      const int ry0 = ti * rowsPerTile, rows = min(rowsPerTile, a.nTy - ry0);
+      const uint32_t rowBytes = (uint32_t)a.nTx * (uint32_t)ROWB;
+      mbarExpectTx(&sBarFull, rowBytes * 8u * (uint32_t)rows);
+      const T* src = data + ((size_t)iy * fb.imgRows + (size_t)ry0 * 8) * (size_t)fb.pitch + (size_t)ix * fb.imgCols;
+      for (int ry = 0; ry < rows; ry++)
+        for (int y = 0; y < 8; y++) bulkLoad(sIn + y * PITCH + ry * (int)rowBytes, src + (size_t)(ry * 8 + y) * (size_t)fb.pitch, rowBytes, &sBarFull);
+      mbarSimCopiesDone(&sBarFull);
+      return;
+    }
     const int tyT = t / tpr, seg = t - tyT * tpr;
     const int h = min(8, a.nRows - tyT * 8), cols = min(TW * 8, a.nCols - seg * TW * 8);
     const uint32_t rowBytes = (uint32_t)cols * (uint32_t)sizeof(T);
@@ -193,10 +212,25 @@ __global__ void __launch_bounds__(ENC_THREADS, MINB) k_encode_tile(FastEncArgs a
       if (tile < 0) break;
       const unsigned long long tileBytes = sMailBytes[k & 1];
       const unsigned long long excl = lookbackExclusive(st, a.groupAcc, gs, tile, tileBytes, lane);
+      if (BATCH) {
+        // where the tile's bytes go and where they sit inside their image's blob: the image's earlier tiles have all published their lengths
+        __threadfence();
+        const int img = tile / fb.tilesPerImg, first = img * fb.tilesPerImg;
+        uint32_t inImg = 0;
+        for (int j = first + lane; j < tile; j += 32) inImg += *(volatile const uint32_t*)&fb.tileLen[j];
+        inImg = __reduce_add_sync(FULL, inImg);
+        if (lane == 0) {
+          sOffS[k & 1] = excl + (unsigned long long)(img + 1) * (unsigned long long)fb.dataStart;
+          sRegS[k & 1] = (long long)fb.dataStart - 14 + (long long)inImg;
+          mbarArrive(&sBarOff[k & 1]);
+        }
+        __syncwarp();
+        continue;
+      }
       if (lane == 0) {
         if (tile == a.tileEnd - 1 && a.hostEnd) *(volatile unsigned long long*)a.hostEnd = excl + tileBytes;      // (mapped host memory: read by the host after this launch's event)
         if (tile == nTiles - 1) { a.res->totalBytes = excl + tileBytes; __threadfence(); *(volatile unsigned int*)&a.res->totalReady = 1u; }
-        sOffS[k & 1] = excl;
+        sOffS[k & 1] = excl; sRegS[k & 1] = a.regionOff + (long long)excl;
         mbarArrive(&sBarOff[k & 1]);
       }
       __syncwarp();
@@ -205,9 +239,8 @@ __global__ void __launch_bounds__(ENC_THREADS, MINB) k_encode_tile(FastEncArgs a
   }
 
   // ================= compute warps =================
-  const unsigned int flagsSeen = *(volatile unsigned int*)&a.res->flags;
+  const unsigned int flagsSeen = BATCH ? 0u : *(volatile unsigned int*)&a.res->flags;
   const unsigned long long negMinSeen = *(volatile unsigned long long*)&a.res->negMinKey, maxSeen = *(volatile unsigned long long*)&a.res->maxKey;
-  const unsigned par = (unsigned)((a.regionOff + (long long)(uintptr_t)a.stream) & 1);    // parity of the region offset of every 16-byte aligned output byte
   // running image-global facts and checksum partials of this thread
   K gMin = keyMaxValue<K>(), gMax = 0;
   unsigned int myFlags = 0;
@@ -215,11 +248,13 @@ __global__ void __launch_bounds__(ENC_THREADS, MINB) k_encode_tile(FastEncArgs a
   bool overflow = false;
 
   // staging image -> HBM: passBytes bytes that start at stream offset passOff
-  auto flushPass = [&](const uint32_t* stage, unsigned long long passOff, uint32_t passBytes) {
+  // (regionStart: checksum-region offset of the pass's first byte; img: the image the bytes belong to, BATCH)
+  auto flushPass = [&](const uint32_t* stage, unsigned long long passOff, long long regionStart, uint32_t passBytes, int img) {
     uint8_t* gPass = a.stream + passOff;
     const bool fits = passOff + passBytes <= a.streamCap;
     if (!fits) overflow = true;
     const int pad = (int)((uintptr_t)gPass & 15);
+    const unsigned par = (unsigned)((regionStart - pad) & 1);         // parity of the region offset of the 16-byte aligned output bytes
     const int nChunks = (pad + (int)passBytes + 15) >> 4;
     const int bs8 = ((-pad) & 3) * 8;
     for (int cI = tid; cI < nChunks; cI += ENC_COMPUTE) {
@@ -238,11 +273,21 @@ __global__ void __launch_bounds__(ENC_THREADS, MINB) k_encode_tile(FastEncArgs a
           for (int j = 0; j < 16; j++) if (s0 + j >= 0 && s0 + j < (int)passBytes) gPass[s0 + j] = (uint8_t)(o[j >> 2] >> (8 * (j & 3)));
         }
       }
-      const long long r0 = a.regionOff + (long long)passOff + s0;       // region offset of the chunk's first byte; r0 & 1 == par
+      const long long r0 = regionStart + s0;                            // region offset of the chunk's first byte; r0 & 1 == par
       const uint32_t w0 = (uint32_t)((unsigned long long)(r0 - par) >> 1) % 65535u;   // word index of the chunk's first word (mod 65535)
       uint32_t S, S1;
       if (par) fletcherChunk<1>(o, S, S1); else fletcherChunk<0>(o, S, S1);
       fa += S; fd += (unsigned long long)w0 * S + S1;
+    }
+    if (BATCH) {                                                         // the image's checksum partials and overflow flag
+      uint32_t A32 = (uint32_t)fa, D32 = (uint32_t)(fd % 65535ull);      // (a thread sums at most a few chunks per pass: fa < 2^24)
+      A32 = __reduce_add_sync(FULL, A32); D32 = __reduce_add_sync(FULL, D32);
+      if (lane == 0) {
+        TileEncResult* r = &fb.imgRes[img];
+        if (A32 | D32) { atomicAdd(&r->fletA, (unsigned long long)A32); atomicAdd(&r->fletD, (unsigned long long)D32); }
+        if (!fits) atomicOr(&r->flags, (unsigned int)FASTF_OVERFLOW);
+      }
+      fa = 0; fd = 0;
     }
   };
   // headers + rows of blocks [bLo, bHi) into `stage` (pass-local byte 0 = tile byte passBase)
@@ -252,7 +297,7 @@ __global__ void __launch_bounds__(ENC_THREADS, MINB) k_encode_tile(FastEncArgs a
       const uint4 info = sInfo[b];
       if (info.y & TINFO_HOT) {
         const int nb = info.y & 31, tc = (info.y >> 5) & 3, osz = 4 >> tc;
-        const int j0 = (bx0 + b) * 8;
+        const int j0 = BATCH ? (b & (a.nTx - 1)) * 8 : (bx0 + b) * 8;
         const uint32_t flag = (uint32_t)((((j0 >> 3) & 15) << 2) & 0x38);
         const float lof = __uint_as_float(info.x);
         const unsigned long long ob = tc == 0 ? (unsigned long long)info.x : (tc == 1 ? (unsigned long long)(uint16_t)(int16_t)lof : (unsigned long long)(uint8_t)lof);
@@ -297,25 +342,27 @@ __global__ void __launch_bounds__(ENC_THREADS, MINB) k_encode_tile(FastEncArgs a
         const uint32_t x4 = __funnelshift_l(R3, 0u, sh);            // non-zero only for 15- and 16-bit values
         if (x4) smemOr(wp + 4, x4);
       } else {
-        const int w = min(8, a.nCols - (bx0 + bb) * 8);
+        const int xb = BATCH ? (bb & (a.nTx - 1)) : bx0 + bb;      // block column inside the image
+        const int w = min(8, a.nCols - xb * 8);
         const int mode = (info.y >> 7) & 3, nb = info.y & 31, tc = (info.y >> 5) & 3;
         const int dtUsed = offsetTypeFromCode(PixelTraits<T>::code, tc);
         const unsigned long long lb = (unsigned long long)info.x | ((unsigned long long)info.w << 32);
         T lo; memcpy(&lo, &lb, sizeof(T));
-        fastGenericEmit<T>(a, stage, (const T*)row, h, w, r, (bx0 + bb) * 8, byte0, mode, nb, tc, dtUsed, (info.y & TINFO_CONST) ? 0u : 1u, (double)lo, lo);
+        fastGenericEmit<T>(a, stage, (const T*)row, h, w, r, xb * 8, byte0, mode, nb, tc, dtUsed, (info.y & TINFO_CONST) ? 0u : 1u, (double)lo, lo);
       }
     }
   };
 
-  int pendK = -1; uint32_t pendBytes = 0;                          // the tile whose staging image still waits for its offset
+  int pendK = -1, pendImg = 0; uint32_t pendBytes = 0;             // the tile whose staging image still waits for its offset
   int tile = sTileNext;
   int k = 0;                                                        // tiles this CTA has posted to its control warp
   for (; tile < a.tileEnd; k++) {
     int nextT = 0;
-    const int tyT = tile / tpr, seg = tile - tyT * tpr;
-    const int bx0 = seg * TW;                                      // first block column of the tile
-    const int nbk = min(TW, a.nTx - bx0);                          // blocks in the tile
-    const int h = min(8, a.nRows - tyT * 8);
+    const int img = BATCH ? tile / fb.tilesPerImg : 0;
+    const int tyT = BATCH ? 1 : tile / tpr, seg = BATCH ? 0 : tile - tyT * tpr;
+    const int bx0 = seg * TW;                                      // first block column of the tile (BATCH: block b of the tile is column b mod nTx)
+    const int nbk = BATCH ? min(rowsPerTile, a.nTy - (tile - img * fb.tilesPerImg) * rowsPerTile) * a.nTx : min(TW, a.nTx - bx0);   // blocks in the tile
+    const int h = BATCH ? 8 : min(8, a.nRows - tyT * 8);
     uint32_t* stage = (uint32_t*)(tileSmem + C::IN_BYTES + (k & 1) * C::STAGE_BYTES) + 4;   // pass-local byte 0 of this tile's output image
     if (vecOk) mbarWait(&sBarFull, (uint32_t)k & 1u);
     else {
@@ -330,7 +377,7 @@ __global__ void __launch_bounds__(ENC_THREADS, MINB) k_encode_tile(FastEncArgs a
     for (int bb = tid >> 1; bb < TW; bb += ENC_COMPUTE / 2) {
       const int hf = tid & 1;
       const bool act = bb < nbk;
-      const int w = act ? min(8, a.nCols - (bx0 + bb) * 8) : 0;
+      const int w = act ? (BATCH ? 8 : min(8, a.nCols - (bx0 + bb) * 8)) : 0;
       const bool full = act && h == 8 && w == 8;
       bool hot = false;
       uint4 info = make_uint4(0, 0, 0, 0);
@@ -386,6 +433,21 @@ __global__ void __launch_bounds__(ENC_THREADS, MINB) k_encode_tile(FastEncArgs a
       }
       if (hf == 0) { sInfo[bb] = info; sOff[bb] = len; }
     }
+    if (BATCH) {                                                     // the image's extremes and flags, from this tile
+      K mn = gMin, mx = gMax;
+      if constexpr (sizeof(K) == 4) { mn = __reduce_min_sync(FULL, mn); mx = __reduce_max_sync(FULL, mx); }
+      else {
+#pragma unroll
+        for (int m = 1; m < 32; m <<= 1) { const K omin = shflXorK<K>(mn, m), omax = shflXorK<K>(mx, m); mn = omin < mn ? omin : mn; mx = omax > mx ? omax : mx; }
+      }
+      const unsigned int fl = __reduce_or_sync(FULL, myFlags);
+      if (lane == 0) {
+        TileEncResult* r = &fb.imgRes[img];
+        if (mx >= mn) { atomicMax(&r->negMinKey, ~(unsigned long long)mn); atomicMax(&r->maxKey, (unsigned long long)mx); }
+        if (fl) atomicOr(&r->flags, fl);
+      }
+      gMin = keyMaxValue<K>(); gMax = 0; myFlags = 0;
+    }
     namedBarSync(1, ENC_COMPUTE);
 
     // ---- scan (warp 0): block lengths -> exclusive byte offsets inside the tile, sOff[TW] = the tile's bytes; publish; post
@@ -402,6 +464,7 @@ __global__ void __launch_bounds__(ENC_THREADS, MINB) k_encode_tile(FastEncArgs a
       for (int j = 0; j < PER; j++) { sOff[lane * PER + j] = run; run += v[j]; }
       if (lane == 31) {
         sOff[TW] = inc;
+        if (BATCH) { fb.tileLen[tile] = inc; __threadfence(); }                 // (read by the control warps of the image's later tiles)
         lookbackPublish(st, a.groupAcc, tile, inc);                                     // for the other CTAs' look-backs
         sMailTile[k & 1] = tile; sMailBytes[k & 1] = inc;
         mbarArrive(&sBarScan[k & 1]);                                          // for this CTA's control warp
@@ -411,7 +474,7 @@ __global__ void __launch_bounds__(ENC_THREADS, MINB) k_encode_tile(FastEncArgs a
     const uint32_t tileBytes = sOff[TW];
     if (tid == 0) nextT = a.tileBegin + (int)atomicAdd(a.ticket, 1u);      // ticket of tile k + 1: in flight while this tile is packed
     // row 0 of the image against the coarser decimal grids (block row 0 only; behind the publication, so that nobody's look-back waits for it)
-    if (isFlt && a.nRaise > 0 && tyT == 0) encRaiseRow0<T>(a, (const T*)sIn, min(TW * 8, a.nCols - bx0 * 8), tid, ENC_COMPUTE);
+    if (!BATCH && isFlt && a.nRaise > 0 && tyT == 0) encRaiseRow0<T>(a, (const T*)sIn, min(TW * 8, a.nCols - bx0 * 8), tid, ENC_COMPUTE);
 
     if (tileBytes <= (uint32_t)C::STAGE_CAP) {
       // ---- the common case: one pass into this tile's staging image; it is flushed when the next tile has been packed
@@ -423,11 +486,11 @@ __global__ void __launch_bounds__(ENC_THREADS, MINB) k_encode_tile(FastEncArgs a
       if (pendK >= 0) {
         mbarWait(&sBarOff[pendK & 1], (uint32_t)(pendK >> 1) & 1u);
         uint32_t* pst = (uint32_t*)(tileSmem + C::IN_BYTES + (pendK & 1) * C::STAGE_BYTES);
-        flushPass(pst + 4, sOffS[pendK & 1], pendBytes);
+        flushPass(pst + 4, sOffS[pendK & 1], sRegS[pendK & 1], pendBytes, pendImg);
         namedBarSync(1, ENC_COMPUTE);
         for (int i = tid; i < (int)((pendBytes + 16 + 48 + 15) >> 4) && i < C::STAGE_BYTES / 16; i += ENC_COMPUTE) ((uint4*)pst)[i] = make_uint4(0, 0, 0, 0);
       }
-      pendK = k; pendBytes = tileBytes;
+      pendK = k; pendBytes = tileBytes; pendImg = img;
       tile = tn;
     } else {
       // ---- more than STAGE_CAP bytes (values wider than 16 bits, raw blocks): passes of at most STAGE_CAP bytes, each flushed at
@@ -435,13 +498,14 @@ __global__ void __launch_bounds__(ENC_THREADS, MINB) k_encode_tile(FastEncArgs a
       if (pendK >= 0) {                                              // first the waiting tile: its image is the other one
         mbarWait(&sBarOff[pendK & 1], (uint32_t)(pendK >> 1) & 1u);
         uint32_t* pst = (uint32_t*)(tileSmem + C::IN_BYTES + (pendK & 1) * C::STAGE_BYTES);
-        flushPass(pst + 4, sOffS[pendK & 1], pendBytes);
+        flushPass(pst + 4, sOffS[pendK & 1], sRegS[pendK & 1], pendBytes, pendImg);
         namedBarSync(1, ENC_COMPUTE);
         for (int i = tid; i < C::STAGE_BYTES / 16; i += ENC_COMPUTE) ((uint4*)pst)[i] = make_uint4(0, 0, 0, 0);
         pendK = -1;
       }
       mbarWait(&sBarOff[k & 1], (uint32_t)(k >> 1) & 1u);
       const unsigned long long tileOff = sOffS[k & 1];
+      const long long tileReg = sRegS[k & 1];
       int bLo = 0;
       uint32_t passBase = 0;
       while (bLo < nbk) {
@@ -454,7 +518,7 @@ __global__ void __launch_bounds__(ENC_THREADS, MINB) k_encode_tile(FastEncArgs a
         const uint32_t passBytes = (bHi == nbk ? tileBytes : sOff[bHi]) - passBase;
         packBlocks(stage, bx0, h, bLo, bHi, passBase);
         namedBarSync(1, ENC_COMPUTE);
-        flushPass(stage, tileOff + passBase, passBytes);
+        flushPass(stage, tileOff + passBase, tileReg + (long long)passBase, passBytes, img);
         namedBarSync(1, ENC_COMPUTE);
         for (int i = tid; i < C::STAGE_BYTES / 16; i += ENC_COMPUTE) ((uint4*)(stage - 4))[i] = make_uint4(0, 0, 0, 0);
         bLo = bHi; passBase += passBytes;
@@ -470,9 +534,10 @@ __global__ void __launch_bounds__(ENC_THREADS, MINB) k_encode_tile(FastEncArgs a
   // ---- the last tile's image; stop the control warp
   if (pendK >= 0) {
     mbarWait(&sBarOff[pendK & 1], (uint32_t)(pendK >> 1) & 1u);
-    flushPass((uint32_t*)(tileSmem + C::IN_BYTES + (pendK & 1) * C::STAGE_BYTES) + 4, sOffS[pendK & 1], pendBytes);
+    flushPass((uint32_t*)(tileSmem + C::IN_BYTES + (pendK & 1) * C::STAGE_BYTES) + 4, sOffS[pendK & 1], sRegS[pendK & 1], pendBytes, pendImg);
   }
   if (tid == 0) { sMailTile[k & 1] = -1; mbarArrive(&sBarScan[k & 1]); }
+  if (BATCH) return;                                               // (per-image facts went out tile by tile)
 
   // ---- image-global facts and checksum partials of this CTA
 #pragma unroll

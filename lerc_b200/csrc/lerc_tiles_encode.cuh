@@ -62,6 +62,9 @@ struct TileFinishArgs {
   double maxZErr;
   uint8_t* out; unsigned long long outCap;
   uint32_t* status;
+  // after k_encode_tile<T, MINB, true>: the look-back words of all tiles (inclusive byte prefixes by then), tilesPerImg of them per image;
+  // the end offset of every blob is written to imgStateOut.  nullptr after k_encode_fused (imgState holds the end offsets already).
+  const unsigned long long* tileState; int tilesPerImg; unsigned long long* imgStateOut;
 };
 
 template <class T>
@@ -70,12 +73,19 @@ __global__ void k_tiles_finish(TileFinishArgs a) {
   using K = typename PixelTraits<T>::Key;
   const int img = blockIdx.x * blockDim.x + threadIdx.x;
   if (img >= a.nImg) return;
-  const TileEncResult r = a.res[img];
+  TileEncResult r = a.res[img];
   const int iy = img / a.nImgX, ix = img - iy * a.nImgX;
   const int rows = min(a.imgRows, a.rasterRows - iy * a.imgRows), cols = min(a.imgCols, a.rasterCols - ix * a.imgCols);
   const long long nPix = (long long)rows * cols;
   constexpr unsigned long long VAL = (1ull << 62) - 1;
-  const unsigned long long start = img == 0 ? 0ull : (a.imgState[img - 1] & VAL);
+  unsigned long long start;
+  if (a.tileState) {
+    const long long first = (long long)img * a.tilesPerImg;
+    const unsigned long long before = first == 0 ? 0ull : (a.tileState[first - 1] & VAL), behind = a.tileState[first + a.tilesPerImg - 1] & VAL;
+    r.streamBytes = behind - before;
+    start = before + (unsigned long long)img * (unsigned long long)a.dataStart;
+    a.imgStateOut[img] = behind + (unsigned long long)(img + 1) * (unsigned long long)a.dataStart;
+  } else start = img == 0 ? 0ull : (a.imgState[img - 1] & VAL);
   uint32_t st = TILEST_OK;
   // ---- the tests of encodeBandFast (lerc_encode.cu), per image
   if (r.flags & (FASTF_NAN | FASTF_LUT)) st = TILEST_GENERAL;
@@ -194,12 +204,21 @@ ErrCode encodeTilesFast(Context* ctx, const TilesGeom& g, const void* dData, dou
   const long long nImg = g.nImg();
   cudaStream_t st = ctx->stream;
   const int nTxF = (g.tileCols + 7) / 8, nTyF = (g.tileRows + 7) / 8;
-  const int segPerImg = ((nTxF + FAST_TB - 1) / FAST_TB) * nTyF;
+  // the TMA-staged persistent encoder (lerc_encode_tile.cuh, BATCH) when all images are equal, made of whole micro-blocks, and a tile of
+  // TW blocks is a whole number of an image's block rows; else the older fused kernel
+  constexpr int TWt = EncTile<T>::TW;
+  const bool tma = g.nCols % g.tileCols == 0 && g.nRows % g.tileRows == 0 && g.tileCols % 8 == 0 && g.tileRows % 8 == 0 && nTxF <= TWt && TWt % nTxF == 0 &&
+                   ((uintptr_t)dData & 15) == 0 && ((size_t)g.nCols * sizeof(T)) % 16 == 0 && !std::getenv("LERC_B200_TILES_OLD");
+  if (std::getenv("LERC_B200_VERBOSE")) std::fprintf(stderr, "[lerc_b200] tile batch encoder: %s\n", tma ? "k_encode_tile (TMA, persistent)" : "k_encode_fused");
+  const int rowsPerTile = tma ? TWt / nTxF : 1;
+  const int segPerImg = tma ? (nTyF + rowsPerTile - 1) / rowsPerTile : ((nTxF + FAST_TB - 1) / FAST_TB) * nTyF;
   const long long nSeg = (long long)segPerImg * nImg;
   const int dataStart = headerBytes(6) + 4 + 2 * (int)sizeof(T) + 1;
 
   const size_t offRes = (size_t)nSeg * 8, offImg = offRes + (size_t)nImg * sizeof(TileEncResult), offRaise = offImg + (size_t)nImg * 8;
-  const size_t offStatus = offRaise + (size_t)nImg * 9 * 8, stateBytes = offStatus + (size_t)nImg * 4;
+  const size_t nGroups = ((size_t)nSeg + 31) / 32;
+  const size_t offStatus = offRaise + (size_t)nImg * 9 * 8, offGroups = (offStatus + (size_t)nImg * 4 + 15) / 16 * 16, offLen = offGroups + 2 * nGroups * 8;
+  const size_t offMisc = offLen + (size_t)nSeg * 4, stateBytes = (offMisc + 15) / 16 * 16 + sizeof(FastEncResult) + 16;
   uint8_t* dState = (uint8_t*)ctx->arena.alloc(stateBytes);
   if (!dState) return Failed;
   cudaMemsetAsync(dState, 0, stateBytes, st);
@@ -232,7 +251,27 @@ ErrCode encodeTilesFast(Context* ctx, const TilesGeom& g, const void* dData, dou
   fb.imgCols = g.tileCols; fb.imgRows = g.tileRows; fb.nImgX = g.nImgX; fb.nImgY = g.nImgY; fb.rasterCols = g.nCols; fb.rasterRows = g.nRows;
   fb.segPerImg = segPerImg; fb.dataStart = dataStart; fb.pitch = g.nCols;
   fb.imgState = dImgState; fb.imgRes = dRes; fb.out = dOut; fb.outCap = outCap;
-  {
+  fb.tilesPerImg = segPerImg; fb.tileLen = (uint32_t*)(dState + offLen);
+  if (tma) {
+    if (nSeg >= (1ll << 31) - 1) return Failed;
+    FastEncResult* dMisc = (FastEncResult*)(dState + (offMisc + 15) / 16 * 16);
+    fa.stream = dOut; fa.streamCap = outCap; fa.res = dMisc;
+    fa.groupState = (unsigned long long*)(dState + offGroups); fa.groupAcc = fa.groupState + nGroups;
+    fa.tileBegin = 0; fa.tileEnd = (int)nSeg; fa.ticket = &dMisc->ticket;
+    constexpr size_t smem = (size_t)EncTile<T>::SMEM;
+    static std::atomic<int> ctasPerSmOf[64];
+    const int dv = ctx->device & 63;
+    int ctasPerSm = ctasPerSmOf[dv].load(std::memory_order_relaxed);
+    auto kernel = k_encode_tile<T, 3, true>;
+    if (!ctasPerSm) {
+      if (!cudaOk(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "encode tile smem")) return Failed;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSm, kernel, ENC_THREADS, smem) != cudaSuccess || ctasPerSm < 1) ctasPerSm = 1;
+      ctasPerSmOf[dv].store(ctasPerSm, std::memory_order_relaxed);
+    }
+    int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+    const long long grid = std::min<long long>(nSeg, (long long)ctasPerSm * std::max(sms, 1));        // persistent CTAs, tiles by ticket
+    { LaunchScope scope_(ctx, "k_encode_tile<T, tiles>"); kernel<<<(unsigned)grid, ENC_THREADS, smem, st>>>(fa, fb); ctx->kernelLaunches++; }
+  } else {
     constexpr int MAXB = 1 + 64 * (int)sizeof(T);
     const size_t smem = (size_t)((FAST_TB * MAXB + 15) / 16 + 3) * 16 * 2 + 256 * 8 * sizeof(T);
     int dev = 0, sms = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -251,6 +290,7 @@ ErrCode encodeTilesFast(Context* ctx, const TilesGeom& g, const void* dData, dou
   for (int i = 0; i < 9; i++) ta.raiseErr[i] = raiseErr[i];
   ta.nImg = (int)nImg; ta.nImgX = g.nImgX; ta.imgCols = g.tileCols; ta.imgRows = g.tileRows; ta.rasterCols = g.nCols; ta.rasterRows = g.nRows;
   ta.dataStart = dataStart; ta.maxZErr = maxZErr; ta.out = dOut; ta.outCap = outCap; ta.status = dStatus;
+  ta.tileState = tma ? dSegState : nullptr; ta.tilesPerImg = segPerImg; ta.imgStateOut = dImgState;
   LERC_LAUNCH(ctx, k_tiles_finish<T>, (unsigned)((nImg + 127) / 128), 128, 0, ta);
 
   hStatus.resize((size_t)nImg); hEnd.resize((size_t)nImg);

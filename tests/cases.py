@@ -147,6 +147,31 @@ def tile_cases(seed=5):
     ci[64:128, 192:200] = 5
     cases.append(("i16_const_tiles_lossless", ci, 64, 64, 0))
     cases.append(("i32_const_tiles_lossy3", ci.astype(np.int32) * 5, 64, 64, 3))
+    # rasters that are whole multiples of the tile size with tiles made of whole micro-blocks: the TMA-staged persistent encoder
+    # (lerc_encode_tile.cuh, BATCH): several block rows per encoder tile, every pixel type, tiles as wide as an encoder tile, values
+    # wider than 16 bits (several packing passes), decisions flipped per image
+    g = c2_raster(512, 768)
+    cases.append(("f32_256x256_config5_shape", g, 256, 256, 0.01))
+    cases.append(("f32_128x256_0.1", g, 128, 256, 0.1))
+    cases.append(("f32_16x16_tiles", g[:64, :96].copy(), 16, 16, 0.01))
+    cases.append(("f32_8x1024_wide_tiles", c2_raster(24, 2048), 8, 1024, 0.01))
+    cases.append(("f32_264x512_partial_last_encoder_tile", c2_raster(264, 1024), 264, 512, 0.01))
+    cases.append(("f32_wide_values_1e-5", (g[:256, :256] * 37.0 + rng.normal(0, 30, (256, 256))).astype(np.float32), 128, 128, 1e-5))
+    cases.append(("f64_64x64_exact", g[:192, :256].astype(np.float64) + 1e-9, 64, 64, 0.001))
+    cases.append(("f64_64x512_wide", g[:128, :1024 - 256].astype(np.float64) * 1.0000001, 64, 512, 1e-6))
+    gi = np.clip(smooth_field(256, 384) * 3 + rng.normal(0, 4, (256, 384)), -3e4, 3e4)
+    cases.append(("i16_128x128_exact", gi.astype(np.int16), 128, 128, 0))
+    cases.append(("u16_64x128_exact_lossy", (gi + 32768).astype(np.uint16), 64, 128, 3))
+    cases.append(("i32_128x64_exact", (gi * 1000).astype(np.int32), 128, 64, 0))
+    cases.append(("u32_64x64_exact_lossy", (gi * 100 + 4e6).astype(np.uint32), 64, 64, 2))
+    mix2 = c2_raster(256, 512)
+    mix2[0:128, 0:128] = -7.5                                   # constant
+    mix2[0:128, 128:256] = np.round(mix2[0:128, 128:256])       # all-integer
+    mix2[128:256, 0:128] = np.floor(mix2[128:256, 0:128] / 40) * 40      # LUT friendly
+    mix2[130:140, 300:310] = np.nan
+    mix2[128:256, 384:512] = rng.random((128, 128)).astype(np.float32) * 1e30
+    cases.append(("f32_exact_mixed_decisions", mix2, 128, 128, 0.01))
+    cases.append(("f32_exact_all_integer", np.round(g[:256, :256]), 128, 128, 0.01))
     cases.append(("f32_every_tile_const", np.repeat(np.repeat(rng.integers(0, 4, (3, 5)).astype(np.float32) * np.float32(1.5), 32, 0), 32, 1), 32, 32, 0.01))
     return cases
 
