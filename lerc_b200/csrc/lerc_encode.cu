@@ -602,6 +602,11 @@ __global__ void __launch_bounds__(256) k_huffman_segments(HuffArgs a, unsigned l
   // first and last word of the segment are shared with the neighbouring segments and go through global atomics.
   constexpr int NW = 640;                                  // window words per warp (a 1024-pixel segment at 20 bits/pixel)
   __shared__ uint32_t sWin[WRITE ? 8 * NW : 1];
+  // the code table in shared memory (indexing the kernel parameter by a per-thread symbol would put a private copy of it in local memory)
+  __shared__ uint32_t sCode[256];
+  __shared__ uint16_t sLen[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) { sCode[i] = a.code[i]; sLen[i] = a.len[i]; }
+  __syncthreads();
   const T* data = (const T*)a.data;
   const int lane = threadIdx.x & 31, warpsPerCta = blockDim.x >> 5, warp = threadIdx.x >> 5;
   const long long nPix = (long long)a.H * a.W;
@@ -630,7 +635,7 @@ __global__ void __launch_bounds__(256) k_huffman_segments(HuffArgs a, unsigned l
         for (int d = dFirst; d < dLast; d++) {
           const T val = data[k * a.D + d];
           const int sym = off + (int)(a.delta ? (T)(val - deltaPredictor(data, a.bits, k, i, j, a.W, a.D, d)) : val);
-          myBits += a.len[sym];
+          myBits += sLen[sym];
           if (nd < 4) syms[nd] = sym;
           nd++;
         }
@@ -645,7 +650,7 @@ __global__ void __launch_bounds__(256) k_huffman_segments(HuffArgs a, unsigned l
           int sym;
           if (q < 4) sym = syms[q];
           else { const T val = data[k * a.D + d]; sym = off + (int)(a.delta ? (T)(val - deltaPredictor(data, a.bits, k, i, j, a.W, a.D, d)) : val); }
-          const int len = a.len[sym]; const uint32_t code = a.code[sym];
+          const int len = sLen[sym]; const uint32_t code = sCode[sym];
           const unsigned long long wi = bp >> 5; const int used = (int)(bp & 31);
           if (staged) {
             if (32 - used >= len) atomicOr(&win[wi - w0], code << (32 - used - len));
