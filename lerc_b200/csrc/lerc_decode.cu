@@ -639,7 +639,10 @@ int decodeHuffmanFast(Context* ctx, const HuffmanTable& t, const uint8_t* dStrea
     uint8_t* dCol0 = (uint8_t*)ctx->arena.alloc((size_t)H * D + 16);
     if (!dCol0) return 0;
     LERC_LAUNCH(ctx, k_huff_col0, D, 256, 0, dPlanes, H, W, D, off, dCol0);
-    LERC_LAUNCH(ctx, k_huff_rows<T>, H, 256, 0, dPlanes, dCol0, H, W, D, off, (T*)dData);
+    const bool vec = (D == 1 || D == 3) && W % 16 == 0 && (((uintptr_t)dPlanes | (uintptr_t)dData) & 15) == 0;
+    if (vec && D == 3) LERC_LAUNCH(ctx, k_huff_rows_vec<3>, H, 256, 0, dPlanes, dCol0, H, W, off, (uint8_t*)dData);
+    else if (vec) LERC_LAUNCH(ctx, k_huff_rows_vec<1>, H, 256, 0, dPlanes, dCol0, H, W, off, (uint8_t*)dData);
+    else LERC_LAUNCH(ctx, k_huff_rows<T>, H, 256, 0, dPlanes, dCol0, H, W, D, off, (T*)dData);
   }
   if (!cudaOk(cudaMemcpyAsync(hFlags, dFlags, 32, cudaMemcpyDeviceToHost, st), "D2H") || !cudaOk(cudaStreamSynchronize(st), "sync")) return -1;
   if (hFlags[1]) return 0;

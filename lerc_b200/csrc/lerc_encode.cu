@@ -678,6 +678,122 @@ __global__ void __launch_bounds__(256) k_huffman_segments(HuffArgs a, unsigned l
   }
 }
 
+// The same two passes for rasters where every pixel is valid, DD = 1 or 3 values per pixel (BASELINE config 4: RGB): a warp takes a
+// segment of 1024 pixels, every lane 32 CONSECUTIVE pixels of it (96 bytes: six 16-byte loads, held in registers).  Per bit string
+// (one per depth plane in delta mode, one for all depths otherwise) a lane sums its code lengths, one warp scan gives its first
+// bit, and the WRITE pass appends its codes in a 64-bit register window that leaves word by word: whole words by plain stores, the
+// two words a lane shares with its neighbours by shared-memory atomics (Huffman.h:218-255: MSB first in little-endian words).
+template <class T, int DD, bool WRITE>
+__global__ void __launch_bounds__(256) k_huffman_runs(HuffArgs a, unsigned long long* __restrict__ segBits, const unsigned long long* __restrict__ segOff,
+                                                      uint32_t* __restrict__ words) {
+  constexpr int NW = 640;                                  // window words per warp (a 1024-symbol string at 20 bits/symbol)
+  __shared__ uint32_t sWin[WRITE ? 8 * NW : 1];
+  __shared__ uint32_t sCode[256];
+  __shared__ uint8_t sLen[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) { sCode[i] = a.code[i]; sLen[i] = (uint8_t)a.len[i]; }
+  __syncthreads();
+  const uint8_t* data = (const uint8_t*)a.data;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long nPix = (long long)a.H * a.W;
+  const int nChunks = (int)((nPix + 1023) >> 10);
+  const uint32_t flip = PixelTraits<T>::code == DT_Char ? 0x80u : 0u;      // symbol = value (or delta) + 128 for signed char (Lerc2.cpp:2320)
+  const bool delta = a.delta != 0;
+  uint32_t* win = sWin + (WRITE ? warp * NW : 0);
+  for (int chunk = blockIdx.x * 8 + warp; chunk < nChunks; chunk += gridDim.x * 8) {
+    const long long k0 = (long long)chunk * 1024 + lane * 32;
+    const int nMine = (int)max(0ll, min(32ll, nPix - k0));
+    uint32_t v[8 * DD];
+    if (nMine == 32) {
+      const uint4* src = (const uint4*)(data + k0 * DD);
+#pragma unroll
+      for (int q = 0; q < 2 * DD; q++) { const uint4 x = __ldg(src + q); v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w; }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 8 * DD; q++) {
+        uint32_t w = 0;
+#pragma unroll
+        for (int b = 0; b < 4; b++) if ((q * 4 + b) < nMine * DD) w |= (uint32_t)data[k0 * DD + q * 4 + b] << (8 * b);
+        v[q] = w;
+      }
+    }
+    const int j0 = nMine > 0 ? (int)(k0 % a.W) : 0;
+    // value of byte m of the lane's 32 * DD bytes (m is a compile-time constant wherever this is called)
+    auto byteAt = [&](int m) -> uint32_t { return (v[m >> 2] >> (8 * (m & 3))) & 0xffu; };
+    // the strings: delta mode DD strings (plane d: segment d * nChunks + chunk), else one (segment chunk)
+    const int nStr = delta ? DD : 1;
+    for (int sI = 0; sI < nStr; sI++) {
+      const long long seg = delta ? (long long)sI * nChunks + chunk : chunk;
+      // ---- one sweep over the lane's symbols of string sI; f(sym) is called in stream order
+      auto sweep = [&](auto&& f) {
+        if (delta) {
+          uint32_t prev = 0;
+          if (nMine > 0 && k0 > 0) prev = j0 > 0 ? data[(k0 - 1) * DD + sI] : data[(k0 - a.W) * DD + sI];
+          int j = j0;
+#pragma unroll
+          for (int px = 0; px < 32; px++) {
+            if (px < nMine) {
+              uint32_t val = 0;
+#pragma unroll
+              for (int d = 0; d < DD; d++) if (d == sI) val = byteAt(px * DD + d);
+              if (px > 0 && j == 0) prev = data[(k0 + px - a.W) * DD + sI];      // first pixel of a row: the pixel above
+              f(((val - prev) & 0xffu) ^ flip);
+              prev = val;
+              if (++j == a.W) j = 0;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int px = 0; px < 32; px++)
+            if (px < nMine) {
+#pragma unroll
+              for (int d = 0; d < DD; d++) f(byteAt(px * DD + d) ^ flip);
+            }
+        }
+      };
+      uint32_t myBits = 0;
+      sweep([&](uint32_t sym) { myBits += sLen[sym]; });
+      uint32_t incl = myBits;
+#pragma unroll
+      for (int m = 1; m < 32; m <<= 1) { const uint32_t o = __shfl_up_sync(FULL, incl, m); if (lane >= m) incl += o; }
+      const uint32_t total = __shfl_sync(FULL, incl, 31);
+      if (!WRITE) { if (lane == 0) segBits[seg] = total; continue; }
+      const unsigned long long bit0 = segOff[seg], bitEnd = bit0 + total;
+      const unsigned long long w0 = bit0 >> 5, w1 = bitEnd > bit0 ? ((bitEnd - 1) >> 5) : w0;
+      const int nw = (int)(w1 - w0) + 1;
+      const bool staged = nw <= NW;
+      if (staged) { for (int i = lane; i < nw; i += 32) win[i] = 0; }
+      __syncwarp();
+      if (myBits) {
+        const unsigned long long myBit = bit0 + (incl - myBits);
+        uint32_t* dst = staged ? win + (int)((myBit >> 5) - w0) : words + (myBit >> 5);
+        unsigned long long acc = 0;
+        int fill = (int)(myBit & 31);                       // leading bits of the first word belong to the predecessor: zero here, OR-ed
+        bool first = true;
+        sweep([&](uint32_t sym) {
+          const int len = sLen[sym];
+          acc |= (unsigned long long)sCode[sym] << (64 - fill - len);
+          fill += len;
+          if (fill >= 32) {
+            const uint32_t w = (uint32_t)(acc >> 32);
+            if (first) { atomicOr(dst, w); first = false; } else *dst = w;
+            dst++; acc <<= 32; fill -= 32;
+          }
+        });
+        if (fill > 0) atomicOr(dst, (uint32_t)(acc >> 32));
+      }
+      __syncwarp();
+      if (staged) {
+        for (int i = lane; i < nw; i += 32) {
+          const uint32_t x = win[i];
+          if (i == 0 || i == nw - 1) { if (x) atomicOr(&words[w0 + i], x); }      // shared with the neighbouring segment
+          else words[w0 + i] = x;
+        }
+        __syncwarp();
+      }
+    }
+  }
+}
+
 // raw valid pixels, all depths, in scan order                                    Lerc2.cpp:1343-1364
 template <class T>
 __global__ void k_one_sweep_gather(const T* __restrict__ data, const uint8_t* __restrict__ bits, const uint32_t* __restrict__ chunkBase,
@@ -1288,7 +1404,12 @@ ErrCode encodeBandT(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
           if (!dSegBits || !dSegOff) return Failed;
           cudaMemsetAsync(dSegBits + nSeg, 0, 8, st);
           int grid = (int)std::min<size_t>((nSeg + 7) / 8, 148 * 16);
-          LERC_LAUNCH(ctx, (k_huffman_segments<T, false>), grid, 256, 0, ha, dSegBits, nullptr, nullptr);
+          // all pixels valid, 1 or 3 values per pixel, 16-byte aligned: the register-window kernels
+          const int runsD = (!dBitsOrNull && ((uintptr_t)a.dData & 15) == 0 && nPix < (1ll << 31)) ? (nDepth == 1 ? 1 : (nDepth == 3 ? 3 : 0)) : 0;
+          const int gridRuns = (int)std::min<size_t>(((size_t)nChunks + 7) / 8, 148 * 16);
+          if (runsD == 3) LERC_LAUNCH(ctx, (k_huffman_runs<T, 3, false>), gridRuns, 256, 0, ha, dSegBits, nullptr, nullptr);
+          else if (runsD == 1) LERC_LAUNCH(ctx, (k_huffman_runs<T, 1, false>), gridRuns, 256, 0, ha, dSegBits, nullptr, nullptr);
+          else LERC_LAUNCH(ctx, (k_huffman_segments<T, false>), grid, 256, 0, ha, dSegBits, nullptr, nullptr);
           exclusiveScanU64(ctx, dSegBits, dSegOff, nSeg);
           // The masked delta mode codes valid pixels only, so segment order == stream order holds in both modes
           // as long as the delta planes are laid out depth after depth, which the segment numbering does.
@@ -1296,7 +1417,9 @@ ErrCode encodeBandT(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
           uint32_t* dWords = (uint32_t*)ctx->arena.alloc(dataBytes + 16);
           if (!dWords) return Failed;
           cudaMemsetAsync(dWords, 0, dataBytes + 16, st);
-          LERC_LAUNCH(ctx, (k_huffman_segments<T, true>), grid, 256, 0, ha, nullptr, dSegOff, dWords);
+          if (runsD == 3) LERC_LAUNCH(ctx, (k_huffman_runs<T, 3, true>), gridRuns, 256, 0, ha, nullptr, dSegOff, dWords);
+          else if (runsD == 1) LERC_LAUNCH(ctx, (k_huffman_runs<T, 1, true>), gridRuns, 256, 0, ha, nullptr, dSegOff, dWords);
+          else LERC_LAUNCH(ctx, (k_huffman_segments<T, true>), grid, 256, 0, ha, nullptr, dSegOff, dWords);
           cudaMemcpyAsync(blob + pos, dWords, dataBytes, cudaMemcpyDeviceToDevice, st);
           pos += dataBytes;
         } else return Failed;

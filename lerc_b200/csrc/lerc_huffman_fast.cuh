@@ -146,13 +146,26 @@ __global__ void __launch_bounds__(256) k_huff_emit(HuffFastArgs a, const unsigne
   unsigned long long p = t == 0 ? 0ull : endFinal[t - 1];
   unsigned long long n = symBase[t];
   bool stop = false;
+  // symbols leave four at a time: a word is stored whole once all of its bytes came from this thread, else byte by byte
+  const unsigned al = (unsigned)((uintptr_t)out & 3);
+  uint32_t wAcc = 0; int have = 0;
+  auto put = [&](int sym) {
+    const unsigned c = ((unsigned)n + al) & 3u;
+    wAcc |= (uint32_t)(sym & 0xff) << (8 * c);
+    have++; n++;
+    if (c == 3u) {
+      if (have == 4) *(uint32_t*)(out + n - 4) = wAcc;
+      else for (int q = 0; q < have; q++) out[n - have + q] = (uint8_t)(wAcc >> (8 * (4 - have + q)));
+      wAcc = 0; have = 0;
+    }
+  };
   if (p < chunkEnd && p + 192 <= a.nBits) {
     HfReader rd; rd.init(a.stream, p);
     const unsigned long long safeEnd = a.nBits - 192;
     while (p < chunkEnd && n < a.nSym && p <= safeEnd) {
       int sym; const int len = hfDecodeOne(a.tab, sLut, rd.peek32(), sym);
       if (!len) { atomicOr(a.bad, 1); stop = true; break; }                // no code on the true chain: the serial decoder decides
-      out[n++] = (uint8_t)sym;
+      put(sym);
       rd.consume(len); p += len;
       if (n == a.nSym) *a.endBit = p;
     }
@@ -161,9 +174,14 @@ __global__ void __launch_bounds__(256) k_huff_emit(HuffFastArgs a, const unsigne
     if (p + 32 > a.nBits) { atomicOr(a.bad, 1); break; }
     int sym; const int len = hfDecodeOne(a.tab, sLut, hfPeek(a.stream, p), sym);
     if (!len) { atomicOr(a.bad, 1); break; }
-    out[n++] = (uint8_t)sym;
+    put(sym);
     p += len;
     if (n == a.nSym) *a.endBit = p;
+  }
+  // the bytes of the last, incomplete word: they sit at byte positions c - have + 1 .. c of wAcc, c = class of the last symbol
+  for (int q = 0; q < have; q++) {
+    const unsigned c = ((unsigned)(n - have + q) + al) & 3u;
+    out[n - have + q] = (uint8_t)(wAcc >> (8 * c));
   }
 }
 
@@ -219,6 +237,82 @@ __global__ void __launch_bounds__(256) k_huff_rows(const uint8_t* __restrict__ p
       }
       __syncthreads();
     }
+  }
+}
+
+// The same for D = 1 or 3 planes, rows of a multiple of 16 pixels and 16-byte aligned buffers (BASELINE config 4: RGB): every thread
+// takes 16 pixels of ALL planes (one 16-byte load per plane), sums them as packed bytes (the running sum is modulo 256 anyway),
+// the totals go through a warp scan and one shared-memory hop per 4096-pixel pass, and the pixel-interleaved result leaves as
+// 16-byte stores.
+template <int DD>
+__global__ void __launch_bounds__(256) k_huff_rows_vec(const uint8_t* __restrict__ planes, const uint8_t* __restrict__ col0, int H, int W, int off, uint8_t* __restrict__ data) {
+  __shared__ uint32_t sWarp[8][DD];
+  __shared__ uint32_t sCarry[DD];
+  const int i = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t off4 = (uint32_t)off * 0x01010101u;
+  if (tid < DD) sCarry[tid] = 0;
+  __syncthreads();
+  for (int j0 = 0; j0 < W; j0 += 4096) {
+    const int a0 = j0 + tid * 16;
+    const bool act = a0 < W;
+    uint32_t x[DD][4], tot[DD];
+#pragma unroll
+    for (int d = 0; d < DD; d++) {
+      uint4 v = make_uint4(off4, off4, off4, off4);
+      if (act) v = __ldg((const uint4*)(planes + ((size_t)d * H + i) * W + a0));
+      x[d][0] = __vsub4(v.x, off4); x[d][1] = __vsub4(v.y, off4); x[d][2] = __vsub4(v.z, off4); x[d][3] = __vsub4(v.w, off4);
+      if (a0 == 0) x[d][0] = (x[d][0] & 0xffffff00u) | (uint32_t)col0[(size_t)d * H + i];      // pixel (i, 0): its value, not a delta (predictor = pixel above)
+      uint32_t run = 0;
+#pragma unroll
+      for (int k = 0; k < 4; k++) {                                       // running sums of the 16 bytes
+        uint32_t w = x[d][k];
+        w = __vadd4(w, w << 8); w = __vadd4(w, w << 16);
+        w = __vadd4(w, run * 0x01010101u);
+        run = w >> 24;
+        x[d][k] = w;
+      }
+      tot[d] = run;
+    }
+    // exclusive prefix of the threads' totals (mod 256) inside the warp, then across the warps and the passes
+#pragma unroll
+    for (int d = 0; d < DD; d++) {
+      uint32_t inc = tot[d];
+#pragma unroll
+      for (int m = 1; m < 32; m <<= 1) { const uint32_t o = __shfl_up_sync(FULL, inc, m); if (lane >= m) inc += o; }
+      if (lane == 31) sWarp[warp][d] = inc;
+      tot[d] = inc - tot[d];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int d = 0; d < DD; d++) {
+      uint32_t base = sCarry[d];
+      for (int w = 0; w < warp; w++) base += sWarp[w][d];
+      const uint32_t add = ((base + tot[d]) & 0xffu) * 0x01010101u;
+#pragma unroll
+      for (int k = 0; k < 4; k++) x[d][k] = __vadd4(x[d][k], add);
+    }
+    if (act) {
+      uint8_t* dst = data + ((size_t)i * W + a0) * DD;
+      if (DD == 1) *(uint4*)dst = make_uint4(x[0][0], x[0][1], x[0][2], x[0][3]);
+      else {
+        uint32_t o[12];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {                                     // 4 pixels of 3 planes -> 3 interleaved words
+          const uint32_t A = x[0][k], B = x[1 % DD][k], C = x[2 % DD][k];
+          o[3 * k + 0] = __byte_perm(__byte_perm(A, B, 0x1040), C, 0x3410);      // A0 B0 C0 A1
+          o[3 * k + 1] = __byte_perm(__byte_perm(B, C, 0x2051), A, 0x3610);      // B1 C1 A2 B2
+          o[3 * k + 2] = __byte_perm(__byte_perm(C, A, 0x3072), B, 0x3710);      // C2 A3 B3 C3
+        }
+        uint4* d4 = (uint4*)dst;
+        d4[0] = make_uint4(o[0], o[1], o[2], o[3]); d4[1] = make_uint4(o[4], o[5], o[6], o[7]); d4[2] = make_uint4(o[8], o[9], o[10], o[11]);
+      }
+    }
+    __syncthreads();
+    if (tid == 255) {
+#pragma unroll
+      for (int d = 0; d < DD; d++) { uint32_t base = sCarry[d]; for (int w = 0; w < 8; w++) base += sWarp[w][d]; sCarry[d] = base & 0xffu; }
+    }
+    __syncthreads();
   }
 }
 

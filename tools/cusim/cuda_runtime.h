@@ -228,6 +228,8 @@ static inline unsigned __byte_perm(unsigned x, unsigned y, unsigned s) {
   }
   return r;
 }
+static inline unsigned __vadd4(unsigned a, unsigned b) { unsigned r = 0; for (int i = 0; i < 4; i++) r |= (((a >> (8 * i)) + (b >> (8 * i))) & 0xffu) << (8 * i); return r; }
+static inline unsigned __vsub4(unsigned a, unsigned b) { unsigned r = 0; for (int i = 0; i < 4; i++) r |= (((a >> (8 * i)) - (b >> (8 * i))) & 0xffu) << (8 * i); return r; }
 static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
 static inline unsigned long long __umul64hi(unsigned long long a, unsigned long long b) { return (unsigned long long)(((unsigned __int128)a * b) >> 64); }
 // fp intrinsics: the sim build is compiled with -ffp-contract=off, so plain operators are round-to-nearest, unfused
