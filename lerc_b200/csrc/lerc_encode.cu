@@ -240,6 +240,7 @@ struct TileArgs {
   int nRows, nCols, nDepth, mb, nTx, nTy, dt, version;
   double maxZErr; uint32_t maxQ;
   int tryDiff, checkOverflow, allValidImage;
+  int onlyFlagged;                                // count pass: only the blocks whose blockBytes entry is 0xffffffff (left over by k_tiles_count8)
   uint32_t* blockBytes;                           // count pass: out [nBlocks]
   const uint32_t* blockOff;                       // write pass: in  [nBlocks], exclusive prefix of blockBytes
   uint8_t* out;                                   // write pass: start of the block stream
@@ -413,6 +414,7 @@ __global__ void k_tiles(TileArgs a) {
   const double scale = a.maxZErr > 0 ? __ddiv_rn(1.0, __dmul_rn(2.0, a.maxZErr)) : 0;
 
   for (int blk = blockIdx.x * warpsPerCta + warp; blk < nBlocks; blk += gridDim.x * warpsPerCta) {
+    if (!WRITE && a.onlyFlagged && a.blockBytes[blk] != 0xffffffffu) continue;
     const int ty = blk / a.nTx, tx = blk - ty * a.nTx;
     const int i0 = ty * a.mb, j0 = tx * a.mb;
     const int h = (i0 + a.mb > a.nRows) ? a.nRows - i0 : a.mb, w = (j0 + a.mb > a.nCols) ? a.nCols - j0 : a.mb;
@@ -516,6 +518,82 @@ __global__ void k_tiles(TileArgs a) {
     }
     if (!WRITE && lane == 0) a.blockBytes[blk] = total;
   }
+}
+
+// Count pass for 8-bit lossless rasters where every pixel is valid (the size of the tiling the Huffman modes compete with,
+// Lerc2.cpp:261-330): ONE THREAD per 8x8 block position, all DD depths in one sweep over the block's bytes -- minimum, maximum and
+// equal-neighbour count of every depth and of every depth-delta block (Lerc2.cpp:1558-1583, :1717-1874), then NumBytesTile
+// (Lerc2.h:416-453) for both and the smaller one.  Blocks in which a lookup table has to be tried (more than half of the values
+// repeat their predecessor) are left to the general kernel: their entry is 0xffffffff.
+template <class T, int DD>
+__global__ void __launch_bounds__(128) k_tiles_count8(TileArgs a) {
+  const int nBlocks = a.nTx * a.nTy;
+  const int blk = blockIdx.x * 128 + threadIdx.x;
+  if (blk >= nBlocks) return;
+  const uint8_t* data = (const uint8_t*)a.data;
+  const int ty = blk / a.nTx, tx = blk - ty * a.nTx;
+  const int i0 = ty * 8, j0 = tx * 8;
+  const int h = min(8, a.nRows - i0), w = min(8, a.nCols - j0), n = h * w;
+  int lo[DD], hi[DD], pv[DD], same[DD], l2[DD], h2[DD], pd[DD], same2[DD];
+#pragma unroll
+  for (int d = 0; d < DD; d++) { lo[d] = 1 << 20; hi[d] = -(1 << 20); pv[d] = 0; same[d] = 0; l2[d] = 1 << 20; h2[d] = -(1 << 20); pd[d] = 0; same2[d] = 0; }
+  bool firstPix = true;
+  for (int r = 0; r < h; r++) {
+    const uint8_t* row = data + ((size_t)(i0 + r) * a.nCols + j0) * DD;
+    uint32_t wds[2 * DD];
+    if (w == 8 && ((uintptr_t)row & 7) == 0) {
+#pragma unroll
+      for (int q = 0; q < DD; q++) { const uint2 x = __ldg((const uint2*)row + q); wds[2 * q] = x.x; wds[2 * q + 1] = x.y; }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 2 * DD; q++) {
+        uint32_t x = 0;
+#pragma unroll
+        for (int b = 0; b < 4; b++) if (q * 4 + b < w * DD) x |= (uint32_t)row[q * 4 + b] << (8 * b);
+        wds[q] = x;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+      if (c < w) {
+        int vPrevDepth = 0;
+#pragma unroll
+        for (int d = 0; d < DD; d++) {
+          const int m = c * DD + d;
+          const uint32_t b8 = (wds[m >> 2] >> (8 * (m & 3))) & 0xffu;
+          const int v = PixelTraits<T>::code == DT_Char ? (int)(int8_t)b8 : (int)b8;
+          lo[d] = min(lo[d], v); hi[d] = max(hi[d], v);
+          if (!firstPix || a.allValidImage) same[d] += (v == pv[d]) ? 1 : 0;        // Lerc2.cpp:1729, :1754
+          pv[d] = v;
+          if (d > 0) {
+            const int df = v - vPrevDepth;
+            l2[d] = min(l2[d], df); h2[d] = max(h2[d], df);
+            same2[d] += (df == pd[d]) ? 1 : 0;
+            pd[d] = df;
+          }
+          vPrevDepth = v;
+        }
+        firstPix = false;
+      }
+    }
+  }
+  uint32_t total = 0;
+  bool flagged = false;
+#pragma unroll
+  for (int d = 0; d < DD; d++) {
+    const double zMin = (double)lo[d], zMax = (double)hi[d];
+    if (n > 4 && (zMax > __dadd_rn(zMin, __dmul_rn(3.0, a.maxZErr))) && (2 * same[d] > n)) flagged = true;
+    const BlockChoice ca = sizeBlock(a, n, zMin, zMax, 1, a.dt, false, nullptr, nullptr, nullptr, 0);
+    int nbAbs = ca.nBytes, nbDiff = nbAbs + 1;
+    if (a.tryDiff && d > 0) {
+      const double dMin = (double)l2[d], dMax = (double)h2[d];
+      if (n > 4 && (dMax > __dadd_rn(dMin, __dmul_rn(3.0, a.maxZErr))) && (2 * same2[d] > n)) flagged = true;
+      const BlockChoice cd = sizeBlock(a, n, dMin, dMax, 4, DT_Int, false, nullptr, nullptr, nullptr, 0);
+      if (cd.nBytes > 0) nbDiff = cd.nBytes;
+    }
+    total += (uint32_t)((d == 0 || nbAbs <= nbDiff) ? nbAbs : nbDiff);
+  }
+  a.blockBytes[blk] = flagged ? 0xffffffffu : total;
 }
 
 template <class T>
@@ -684,7 +762,7 @@ __global__ void __launch_bounds__(256) k_huffman_segments(HuffArgs a, unsigned l
 // bit, and the WRITE pass appends its codes in a 64-bit register window that leaves word by word: whole words by plain stores, the
 // two words a lane shares with its neighbours by shared-memory atomics (Huffman.h:218-255: MSB first in little-endian words).
 template <class T, int DD, bool WRITE>
-__global__ void __launch_bounds__(256) k_huffman_runs(HuffArgs a, unsigned long long* __restrict__ segBits, const unsigned long long* __restrict__ segOff,
+__global__ void __launch_bounds__(256, 2) k_huffman_runs(HuffArgs a, unsigned long long* __restrict__ segBits, const unsigned long long* __restrict__ segOff,
                                                       uint32_t* __restrict__ words) {
   constexpr int NW = 640;                                  // window words per warp (a 1024-symbol string at 20 bits/symbol)
   __shared__ uint32_t sWin[WRITE ? 8 * NW : 1];
@@ -721,7 +799,9 @@ __global__ void __launch_bounds__(256) k_huffman_runs(HuffArgs a, unsigned long 
     auto byteAt = [&](int m) -> uint32_t { return (v[m >> 2] >> (8 * (m & 3))) & 0xffu; };
     // the strings: delta mode DD strings (plane d: segment d * nChunks + chunk), else one (segment chunk)
     const int nStr = delta ? DD : 1;
-    for (int sI = 0; sI < nStr; sI++) {
+#pragma unroll
+    for (int sI = 0; sI < DD; sI++) {
+      if (sI >= nStr) break;
       const long long seg = delta ? (long long)sI * nChunks + chunk : chunk;
       // ---- one sweep over the lane's symbols of string sI; f(sym) is called in stream order
       auto sweep = [&](auto&& f) {
@@ -732,9 +812,7 @@ __global__ void __launch_bounds__(256) k_huffman_runs(HuffArgs a, unsigned long 
 #pragma unroll
           for (int px = 0; px < 32; px++) {
             if (px < nMine) {
-              uint32_t val = 0;
-#pragma unroll
-              for (int d = 0; d < DD; d++) if (d == sI) val = byteAt(px * DD + d);
+              const uint32_t val = byteAt(px * DD + sI);
               if (px > 0 && j == 0) prev = data[(k0 + px - a.W) * DD + sI];      // first pixel of a row: the pixel above
               f(((val - prev) & 0xffu) ^ flip);
               prev = val;
@@ -1283,8 +1361,20 @@ ErrCode encodeBandT(Context* ctx, EncodeBandArgs& a, BandMaskState& ms, uint32_t
       dOff = (uint32_t*)ctx->arena.alloc(4 * (nBlocks + 1));
       if (!dLen || !dOff) return false;
       cudaMemsetAsync(dLen + nBlocks, 0, 4, st);
-      ta.blockBytes = dLen; ta.blockOff = nullptr; ta.out = nullptr;
-      launchTiles<T>(ctx, ta, false);
+      ta.blockBytes = dLen; ta.blockOff = nullptr; ta.out = nullptr; ta.onlyFlagged = 0;
+      bool counted = false;
+      if constexpr (sizeof(T) == 1) {
+        if (mb == 8 && !dBitsOrNull && maxZErr == 0.5 && (nDepth == 1 || nDepth == 3) && !std::getenv("LERC_B200_NO_FAST")) {
+          const unsigned grid8 = (unsigned)((nBlocks + 127) / 128);
+          if (nDepth == 3) LERC_LAUNCH(ctx, (k_tiles_count8<T, 3>), grid8, 128, 0, ta);
+          else LERC_LAUNCH(ctx, (k_tiles_count8<T, 1>), grid8, 128, 0, ta);
+          ta.onlyFlagged = 1;                                         // the general kernel finishes the blocks that want a lookup table tried
+          launchTiles<T>(ctx, ta, false);
+          ta.onlyFlagged = 0;
+          counted = true;
+        }
+      }
+      if (!counted) launchTiles<T>(ctx, ta, false);
       exclusiveScanU32(ctx, dLen, dOff, nBlocks);
       uint32_t t = 0;
       if (!d2h(ctx, &t, dOff + nBlocks, 1)) return false;
