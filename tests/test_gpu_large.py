@@ -8,7 +8,7 @@ import sys
 import numpy as np
 import pytest
 
-from cases import c2_raster
+from cases import c2_raster, c4_raster
 from lercapi import ROOT, oracle_lib, product_lib, ref_lib
 
 sys.path.insert(0, ROOT)
@@ -40,6 +40,26 @@ def test_c2_full_size_bit_exact(libs):
     assert st == 0 and np.array_equal(d_p.view(np.uint8), d_r.view(np.uint8))
     assert s1[3] == s0[3] + 1 and s1[4] == s0[4] + 1, "fused paths were not taken"
     assert float(np.abs(d_p[0, :, :, 0].astype(np.float64) - img).max()) <= 0.01 * 1.1     # reference slack (Lerc.cpp:1137)
+
+
+def test_c4_full_size_bit_exact(libs):
+    """BASELINE configs[3]: 8192 x 8192 uint8 RGB (nDepth = 3), lossless -- the 8-bit Huffman path: blob byte-exact vs the
+    reference library (oracle/_ref, else the oracle), decode of the reference's blob bit-exact and lossless"""
+    prod, orc = libs
+    chk = ref_lib() or orc
+    img = c4_raster(8192, 8192)
+    s_r, b_r, _ = chk.encode(img, 0, n_depth=3)
+    s_p, b_p, _ = prod.encode(img, 0, n_depth=3)
+    assert s_r == 0 and s_p == 0
+    assert len(b_p) == len(b_r) and b_p == b_r
+    mode_at = 90 + 4 + 2 * 3 + 1                                  # header | mask byte count | ranges | one-sweep flag
+    assert b_r[mode_at] in (1, 2), "expected a Huffman image mode for this raster"
+    st, n = prod.compute_size(img, 0, n_depth=3)
+    assert st == 0 and n == len(b_r)
+    st, d_p, _ = prod.decode(b_r)
+    assert st == 0 and np.array_equal(d_p[0], img)
+    bad = bytearray(b_r); bad[len(bad) // 2] ^= 0x10
+    assert prod.decode(bytes(bad))[0] != 0
 
 
 def test_c3_band_properties_device_resident(libs):
