@@ -343,11 +343,6 @@ namespace lerc {
 // band orchestration (host)
 namespace {
 
-int smCount() {
-  static int n = 0;
-  if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 1; }
-  return n;
-}
 
 // k_dec_resolve: the region tables stay in global memory (default) or are staged in shared memory when they fit (experimental,
 // LERC_B200_DEC_RESOLVE=smem)
@@ -355,8 +350,8 @@ inline void launchResolve(Context* ctx, const FastDecArgs& fa) {
   static const bool smemResolve = [] { const char* e = std::getenv("LERC_B200_DEC_RESOLVE"); return e && std::strcmp(e, "smem") == 0; }();
   const size_t bytes = (size_t)fa.nReg * FD_CAND * sizeof(FdEntry);
   if (smemResolve && bytes <= 160 * 1024) {
-    static bool attrSet = false;
-    if (!attrSet) { cudaFuncSetAttribute(k_dec_resolve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attrSet = true; }
+    static DeviceOnce attrSet;
+    if (attrSet.need(ctx->device)) { cudaFuncSetAttribute(k_dec_resolve<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); attrSet.done(ctx->device); }
     LERC_LAUNCH(ctx, k_dec_resolve<true>, 1, 1024, bytes, fa, fa.nTx * fa.nTy);
   } else LERC_LAUNCH(ctx, k_dec_resolve<false>, 1, 1024, 0, fa, fa.nTx * fa.nTy);
 }
@@ -498,11 +493,11 @@ bool launchDecodeFast(Context* ctx, const HeaderInfo& hd, const uint8_t* dStream
   static const bool closureDec = [] { const char* e = std::getenv("LERC_B200_DEC"); return e && std::strcmp(e, "closure") == 0; }();
   fa.firstOnly = closureDec ? 1 : 0;
   if (faOut) *faOut = fa;
-  static bool attrSet = false;
-  if (!attrSet) {
+  static DeviceOnce attrSet;
+  if (attrSet.need(ctx->device)) {
     if (!cudaOk(cudaFuncSetAttribute(k_dec_blocks<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB), "smem attribute")) return false;
     if (!cudaOk(cudaFuncSetAttribute(k_dec_walk<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemW), "smem attribute")) return false;
-    attrSet = true;
+    attrSet.done(ctx->device);
   }
   LERC_LAUNCH(ctx, k_dec_candidates<T>, (nSub + 7) / 8, 256, 0, fa);
   LERC_LAUNCH(ctx, k_dec_walk<T>, nReg, 256, smemW, fa);

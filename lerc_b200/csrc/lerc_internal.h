@@ -12,6 +12,7 @@
 // Reference citations are relative to /root/reference/src/LercLib.
 #pragma once
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <cstdint>
 #include <cstddef>
@@ -189,6 +190,19 @@ struct DecodeBandArgs {
   bool hostCopied = false;
 };
 ErrCode decodeBand(Context* ctx, DecodeBandArgs& a, BandMaskState& ms);
+
+// Per-device "done once" flags and cached integers (function attributes and occupancy are per device; contexts are pooled per device)
+struct DeviceOnce {
+  std::atomic<unsigned long long> mask{0};
+  bool need(int dev) const { return !((mask.load(std::memory_order_relaxed) >> (dev & 63)) & 1ull); }
+  void done(int dev) { mask.fetch_or(1ull << (dev & 63), std::memory_order_relaxed); }
+};
+struct DeviceInt {
+  std::atomic<int> v[64];
+  int get(int dev) const { return v[dev & 63].load(std::memory_order_relaxed); }
+  void set(int dev, int x) { v[dev & 63].store(x, std::memory_order_relaxed); }
+};
+inline int smCountOf(int dev) { int n = 0; cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n > 0 ? n : 1; }
 
 // Strip schedule of a pipelined host-resident call: `bytes` of payload in `nUnits` units (block rows / stream chunks).  Small strips
 // at both ends (the first kernel starts early, the last copy back is short), strips up to 8x larger in between (fewer launches

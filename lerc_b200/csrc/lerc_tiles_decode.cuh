@@ -309,9 +309,13 @@ ErrCode decodeTilesT(Context* ctx, const TilesGeom& g, const uint8_t* dBlobs, si
     // CTA size: fewer threads per CTA = more CTAs (and header walkers) per SM; LERC_B200_TILES_NT = 32 (default: one warp per blob, no CTA-wide waiting on the header walk; measured 0.94 ms on 4096 tiles) | 64 (1.28 ms) | 128 (1.33 ms) | 256 (1.77 ms)
     static const int nt = [] { const char* e = std::getenv("LERC_B200_TILES_NT"); const int v = e ? std::atoi(e) : 32; return (v == 64 || v == 128 || v == 256) ? v : 32; }();
     auto launch = [&](auto kernel, int NT) {
-      static int ctasPerSm = 0;                     // all CTAs resident, each strides over the blobs: no tail wave
-      if (!ctasPerSm && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSm, kernel, NT, 0) != cudaSuccess || ctasPerSm < 1)) ctasPerSm = 1;
-      const long long grid = std::min<long long>(nImg, (long long)smCount() * ctasPerSm);
+      static DeviceInt occ;                         // all CTAs resident, each strides over the blobs: no tail wave
+      int ctasPerSm = occ.get(ctx->device);
+      if (!ctasPerSm) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSm, kernel, NT, 0) != cudaSuccess || ctasPerSm < 1) ctasPerSm = 1;
+        occ.set(ctx->device, ctasPerSm);
+      }
+      const long long grid = std::min<long long>(nImg, (long long)smCountOf(ctx->device) * ctasPerSm);
       LaunchScope scope_(ctx, "k_tiles_blocks<T>");
       kernel<<<(unsigned)grid, NT, 0, ctx->stream>>>(a); ctx->kernelLaunches++;
     };

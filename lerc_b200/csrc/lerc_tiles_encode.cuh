@@ -274,12 +274,14 @@ ErrCode encodeTilesFast(Context* ctx, const TilesGeom& g, const void* dData, dou
   } else {
     constexpr int MAXB = 1 + 64 * (int)sizeof(T);
     const size_t smem = (size_t)((FAST_TB * MAXB + 15) / 16 + 3) * 16 * 2 + 256 * 8 * sizeof(T);
-    int dev = 0, sms = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    static int ctasPerSm = 0;
+    const int sms = smCountOf(ctx->device);
+    static DeviceInt occ;
+    int ctasPerSm = occ.get(ctx->device);
     auto kernel = k_encode_fused<T, 4, true>;
     if (!ctasPerSm) {
       cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctasPerSm, kernel, 256, smem) != cudaSuccess || ctasPerSm < 1) ctasPerSm = 1;
+      occ.set(ctx->device, ctasPerSm);
     }
     const long long grid = std::min<long long>(nSeg, (long long)ctasPerSm * std::max(sms, 1));       // all CTAs co-resident (look-back)
     { LaunchScope scope_(ctx, "k_encode_fused<T, tiles>"); kernel<<<(unsigned)grid, 256, smem, ctx->stream>>>(fa, fb); ctx->kernelLaunches++; }
