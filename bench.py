@@ -679,7 +679,7 @@ def main():
     e2e = {"value": world * n_px / float(t.item()) / 1e9, "unit": "Gpixels/s", "ms_per_step": e2e_ms,
            "h2d_bytes_per_step": raw_bytes + nb, "d2h_bytes_per_step": nb + raw_bytes, "timer": "host wall clock around the synchronous C-API calls",
            "pcie_gbs_per_direction": (raw_bytes + nb) / (e2e_ms * 1e-3) / 1e9,
-           "pipelining": "inside each call: strips of block rows / stream chunks, H2D | kernels | D2H on three streams (LERC_B200_STRIP_LOG2, default 8 MB strips)"}
+           "pipelining": "inside each call: strips of block rows / stream chunks, H2D | kernels | D2H on three streams (graded schedule: ~1 MB strips at both ends, up to 8x larger in between; LERC_B200_STRIP_LOG2)"}
     assert np.abs(h_out.numpy().astype(np.float64) - h_in[(E2E - 1) % 2].numpy().astype(np.float64)).max() <= max(mz, 0.5 if dt < 6 else 0) * 1.1 + 1e-12
 
     # ---- two callers: one thread encodes raster i + 1 while another decodes blob i (two library contexts; the calls are synchronous and
