@@ -53,7 +53,7 @@ out, fn = [], None
 for line in sass:
     if "Function :" in line:
         fn = line.strip()
-    if any(m in line for m in ("UBLKCP", "SYNCS", "ATOMS.OR", "REDUX")) and fn and ("k_encode_tile" in fn or "k_decode_stream" in fn):
+    if any(m in line for m in ("UBLKCP", "SYNCS", "ATOMS.OR", "REDUX")) and fn and ("k_encode_tileIfLi3ELb0" in fn or "k_decode_streamIf" in fn):      # the float instantiations of the headline kernels
         out.append(f"{fn[:90]:90s} {line.strip()[:110]}")
 open(os.path.join(P, f"{tag}_sass_tma_mbarrier.txt"), "w").write("\n".join(out[:400]) + "\n")
 print(len(out), "SASS lines with UBLKCP / SYNCS / ATOMS.OR / REDUX")
