@@ -2,6 +2,8 @@
 // Fletcher-32 and a few small utilities.  Reference citations relative to /root/reference/src/LercLib.
 #include "lerc_device.cuh"
 #include "lerc_kernels.h"
+#include <cub/device/device_scan.cuh>
+#include <algorithm>
 
 namespace lerc {
 
@@ -174,8 +176,100 @@ __global__ void __launch_bounds__(32) k_rle_encode(const uint8_t* __restrict__ s
   putCount(-32768);
   if (lane == 0) *sizeOut = (uint32_t)out;
 }
+// ---- the same token stream in parallel (masks of more than a few KB): run starts, literal-span starts and the ends of both are
+// found with prefix scans instead of a walk.
+//   k_rle_runs    every byte that starts a maximal run of equal bytes gets a marker {position, "repeat" bit}; the repeat rule
+//                 (run >= 5 and more than 5 bytes before the end, RLE.cpp:74-79) needs only the four bytes behind the run start
+//   (max-scan)    -> every byte knows its run's start and repeat bit
+//   k_rle_spans   start markers of repeat runs / literal spans (maximal stretches of non-repeat bytes) in stream order and end
+//                 markers in REVERSED order, packed into one 64-bit element
+//   (max-scan of both halves at once) -> every byte knows where its repeat run / literal span starts and ends
+//   k_rle_sizes   output bytes contributed by every byte: a piece of at most 32767 (RLE.cpp:98-107) starts every 32767 bytes of a
+//                 repeat run (3 bytes) or literal span (2 bytes + the literals themselves)
+//   (sum-scan)    -> output offsets
+//   k_rle_write   headers with the piece's count (what is left of the run / span, capped), bytes, terminator
+struct U32Max { __host__ __device__ uint32_t operator()(uint32_t a, uint32_t b) const { return a > b ? a : b; } };
+struct U32x2 { uint32_t a, b; };
+struct U32x2Max { __host__ __device__ U32x2 operator()(const U32x2& x, const U32x2& y) const { U32x2 r; r.a = x.a > y.a ? x.a : y.a; r.b = x.b > y.b ? x.b : y.b; return r; } };
+
+__global__ void k_rle_runs(const uint8_t* __restrict__ src, uint32_t n, uint32_t* __restrict__ mark) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint8_t v = src[i];
+    uint32_t m = 0;
+    if (i == 0 || src[i - 1] != v) {
+      const bool rep = i + 5 < n && src[i + 1] == v && src[i + 2] == v && src[i + 3] == v && src[i + 4] == v;
+      m = ((i + 1) << 1) | (rep ? 1u : 0u);
+    }
+    mark[i] = m;
+  }
+}
+__global__ void k_rle_spans(const uint8_t* __restrict__ src, uint32_t n, const uint32_t* __restrict__ run, U32x2* __restrict__ se) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t r = run[i], p = (r >> 1) - 1;
+    const bool rep = r & 1u;
+    const bool runEnd = i == n - 1 || src[i + 1] != src[i];
+    bool start, end;
+    if (rep) { start = i == p; end = runEnd; }
+    else {
+      start = i == 0 || (i == p && (run[i - 1] & 1u));                    // the byte before belongs to a repeat run
+      end = i == n - 1 || (runEnd && (run[i + 1] & 1u));                  // the next run is a repeat run
+    }
+    se[i].a = start ? i + 1 : 0;
+    se[n - 1 - i].b = end ? (n - 1 - i) + 1 : 0;
+  }
+}
+__global__ void k_rle_sizes(uint32_t n, const uint32_t* __restrict__ run, const U32x2* __restrict__ se, uint32_t* __restrict__ contrib) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const bool rep = run[i] & 1u;
+    const uint32_t k = i - (se[i].a - 1);
+    const bool piece = k % 32767u == 0;
+    contrib[i] = rep ? (piece ? 3u : 0u) : (piece ? 3u : 1u);
+  }
+}
+__global__ void k_rle_write(const uint8_t* __restrict__ src, uint32_t n, const uint32_t* __restrict__ run, const U32x2* __restrict__ se,
+                            const uint32_t* __restrict__ off, uint8_t* __restrict__ dst, uint32_t* __restrict__ sizeOut) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const bool rep = run[i] & 1u;
+    const uint32_t st = se[i].a - 1, en = n - 1 - (se[n - 1 - i].b - 1);
+    const uint32_t k = i - st;
+    const bool piece = k % 32767u == 0;
+    const uint32_t o = off[i];
+    if (dst) {
+      if (piece) {
+        const uint32_t left = en - i + 1, c = left > 32767u ? 32767u : left;
+        const uint32_t cnt = rep ? (0x10000u - c) & 0xffffu : c;            // int16 count, little endian; negative = repeat
+        dst[o] = (uint8_t)cnt; dst[o + 1] = (uint8_t)(cnt >> 8); dst[o + 2] = src[i];
+      } else if (!rep) dst[o] = src[i];
+    }
+    if (i == n - 1) {
+      const uint32_t total = o + (rep ? (piece ? 3u : 0u) : (piece ? 3u : 1u));
+      if (dst) { dst[total] = 0x00; dst[total + 1] = 0x80; }               // -32768 ends the stream (RLE.cpp:250)
+      *sizeOut = total + 2;
+    }
+  }
+}
+
 void launchRleEncode(Context* ctx, const uint8_t* dSrc, long long n, uint8_t* dDst, uint32_t* dSize) {
-  LERC_LAUNCH(ctx, k_rle_encode, 1, 32, 0, dSrc, n, dDst, dSize);
+  if (n < 4096 || n >= (1ll << 30)) { LERC_LAUNCH(ctx, k_rle_encode, 1, 32, 0, dSrc, n, dDst, dSize); return; }
+  const uint32_t nn = (uint32_t)n;
+  uint32_t* dRun = (uint32_t*)ctx->arena.alloc(4 * (size_t)nn);
+  uint32_t* dOff = (uint32_t*)ctx->arena.alloc(4 * (size_t)nn);
+  U32x2* dSe = (U32x2*)ctx->arena.alloc(8 * (size_t)nn);
+  size_t t1 = 0, t2 = 0, t3 = 0;
+  cub::DeviceScan::InclusiveScan(nullptr, t1, dRun, dRun, U32Max(), (int)nn, ctx->stream);
+  cub::DeviceScan::InclusiveScan(nullptr, t2, dSe, dSe, U32x2Max(), (int)nn, ctx->stream);
+  cub::DeviceScan::ExclusiveSum(nullptr, t3, dOff, dOff, (int)nn, ctx->stream);
+  const size_t tb = std::max(std::max(t1, t2), std::max(t3, (size_t)16));
+  void* tmp = ctx->arena.alloc(tb);
+  if (!dRun || !dOff || !dSe || !tmp) { LERC_LAUNCH(ctx, k_rle_encode, 1, 32, 0, dSrc, n, dDst, dSize); return; }
+  const int grid = (int)std::min<long long>((n + 255) / 256, 148 * 16);
+  LERC_LAUNCH(ctx, k_rle_runs, grid, 256, 0, dSrc, nn, dRun);
+  { LaunchScope scope(ctx, "cub::InclusiveScan<max>"); size_t b = tb; cub::DeviceScan::InclusiveScan(tmp, b, dRun, dRun, U32Max(), (int)nn, ctx->stream); ctx->kernelLaunches += 2; }
+  LERC_LAUNCH(ctx, k_rle_spans, grid, 256, 0, dSrc, nn, dRun, dSe);
+  { LaunchScope scope(ctx, "cub::InclusiveScan<max2>"); size_t b = tb; cub::DeviceScan::InclusiveScan(tmp, b, dSe, dSe, U32x2Max(), (int)nn, ctx->stream); ctx->kernelLaunches += 2; }
+  LERC_LAUNCH(ctx, k_rle_sizes, grid, 256, 0, nn, dRun, dSe, dOff);
+  { LaunchScope scope(ctx, "cub::ExclusiveSum<u32>"); size_t b = tb; cub::DeviceScan::ExclusiveSum(tmp, b, dOff, dOff, (int)nn, ctx->stream); ctx->kernelLaunches += 2; }
+  LERC_LAUNCH(ctx, k_rle_write, grid, 256, 0, dSrc, nn, dRun, dSe, dOff, dDst, dSize);
 }
 
 // RLE.cpp:298-331.  status[0] = 1 on success, 0 on malformed input.

@@ -23,7 +23,7 @@ struct DeviceScan {
   static cudaError_t InclusiveScan(void* tmp, size_t& tmpBytes, In in, Out out, Op op, int n, cudaStream_t = nullptr) {
     if (!tmp) { tmpBytes = 16; return cudaSuccess; }
     using V = std::remove_reference_t<decltype(out[0])>;
-    V run = 0;
+    V run{};
     for (int i = 0; i < n; i++) { run = i ? (V)op(run, (V)in[i]) : (V)in[i]; out[i] = run; }
     return cudaSuccess;
   }
