@@ -106,6 +106,32 @@ __global__ void k_walk_units(DecTileArgs a) {
   if (threadIdx.x == 0 && sBad) atomicOr(a.status, DECF_BAD_STREAM);
 }
 
+// The walk's checks, block-parallel, for offsets found speculatively (k_decode_stream<T, true>): every block's units, parsed with the
+// block's true size and valid count, must carry the right integrity bits and end exactly where the next block starts.  status[2] != 0:
+// the offsets are not the serial parse (the serial walk then decides).
+__global__ void k_verify_offsets(DecTileArgs a) {
+  const int nBlocks = a.nTx * a.nTy;
+  const int pattern = a.version >= 5 ? 14 : 15;
+  for (int blk = blockIdx.x * blockDim.x + threadIdx.x; blk < nBlocks; blk += gridDim.x * blockDim.x) {
+    const int ty = blk / a.nTx, tx = blk - ty * a.nTx, i0 = ty * a.mb, j0 = tx * a.mb;
+    const int h = (i0 + a.mb > a.nRows) ? a.nRows - i0 : a.mb, w = (j0 + a.mb > a.nCols) ? a.nCols - j0 : a.mb;
+    unsigned long long cur = a.blockOff[blk];
+    bool bad = blk == 0 && cur != 0;
+    for (int d = 0; d < a.nDepth && !bad; d++) {
+      if (cur >= a.streamLen) { bad = true; break; }
+      uint8_t hb[16];
+      for (int k = 0; k < 16; k++) hb[k] = cur + k < a.streamLen ? a.stream[cur + k] : 0;
+      if ((((hb[0] >> 2) & pattern) != ((j0 >> 3) & pattern)) || (a.version >= 5 && (hb[0] & 4) && d == 0)) { bad = true; break; }
+      const int rawCount = ((hb[0] & 3) == 0) ? blockValidCount(a, i0, j0, h, w) : 0;
+      const unsigned len = unitLength(hb, a.dt, a.version, rawCount, h * w);
+      if (!len || cur + len > a.streamLen) { bad = true; break; }
+      cur += len;
+    }
+    if (!bad && blk + 1 < nBlocks && cur != (unsigned long long)a.blockOff[blk + 1]) bad = true;
+    if (bad) atomicOr(a.status + 2, 1);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // micro-block decoder: one warp per block position, all depths               Lerc2.cpp:2025-2230
 template <class T> __device__ __forceinline__ T castClamped(double z, double zMax) {
@@ -457,6 +483,48 @@ int decodeStreamFast(Context* ctx, const HeaderInfo& hd, DecodeBandArgs& ba, siz
   if (*hStatus & DSF_CHECKSUM) return -1;
   if (*hStatus & DSF_FALLBACK) { ba.hostCopied = false; return 0; }
   return 1;
+}
+
+// Block offsets of a masked band's stream with the stream decoder's boundary discovery (k_decode_stream<T, true>) + k_verify_offsets.
+// 1 = dOff holds the serial parse's offsets, 0 = not established (other ways must find them), -1 = CUDA error.
+template <class T>
+int streamBlockOffsets(Context* ctx, const HeaderInfo& hd, const DecTileArgs& ta, int* dStatus) {
+  const size_t streamLen = (size_t)ta.streamLen;
+  if (streamLen == 0 || streamLen >= 0xfff00000ull || hd.nDepth != 1 || hd.microBlockSize != 8 || hd.version < 3 || std::getenv("LERC_B200_NO_FAST")) return 0;
+  cudaStream_t st = ctx->stream;
+  const int nChunks = (int)((streamLen + DS_CHUNK - 1) / DS_CHUNK);
+  const size_t nGroups = ((size_t)nChunks + 31) / 32;
+  const size_t stateBytes = 128 + ((size_t)nChunks * 2 + nGroups * 2) * 8;
+  uint8_t* dState = (uint8_t*)ctx->arena.alloc(stateBytes);
+  unsigned int* hStatus = (unsigned int*)ctx->pinnedAlloc(16);
+  if (!dState || !hStatus) return 0;
+  cudaMemsetAsync(dState, 0, stateBytes, st);
+  cudaMemsetAsync(dStatus + 2, 0, 4, st);
+  StreamDecArgs sa;
+  std::memset(&sa, 0, sizeof sa);
+  sa.stream = ta.stream; sa.streamLen = streamLen;
+  sa.nRows = hd.nRows; sa.nCols = hd.nCols; sa.nTx = ta.nTx; sa.nTy = ta.nTy; sa.version = hd.version;
+  sa.nTxMagic = sa.nTx >= 2 ? (uint32_t)((1ull << 32) / (unsigned)sa.nTx) + 1u : 0u;
+  sa.invScale = 2 * hd.maxZError; sa.zMax = hd.zMax; sa.data = nullptr; sa.nChunks = nChunks;
+  sa.res = (StreamDecResult*)dState;
+  sa.exitState = (unsigned long long*)(dState + 128); sa.cntState = sa.exitState + nChunks;
+  sa.groupState = sa.cntState + nChunks; sa.groupAcc = sa.groupState + nGroups;
+  sa.haveChecksum = 0; sa.blockOff = ta.blockOff;
+  sa.chunkBegin = 0; sa.ticket = (unsigned int*)(dState + 64);
+  constexpr size_t smem = (size_t)DecStream<T>::SMEM_OFFS;
+  static DeviceOnce attrDone;
+  if (attrDone.need(ctx->device)) {
+    if (!cudaOk(cudaFuncSetAttribute(k_decode_stream<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "stream offsets smem")) return 0;
+    attrDone.done(ctx->device);
+  }
+  { LaunchScope scope_(ctx, "k_decode_stream<T, offsets>"); k_decode_stream<T, true><<<(unsigned)nChunks, DS_THREADS, smem, st>>>(sa); ctx->kernelLaunches++; }
+  const int nBlocks = ta.nTx * ta.nTy;
+  LERC_LAUNCH(ctx, k_verify_offsets, (unsigned)std::min((nBlocks + 127) / 128, 148 * 16), 128, 0, ta);
+  if (!cudaOk(cudaMemcpyAsync(hStatus, &sa.res->status, 4, cudaMemcpyDeviceToHost, st), "D2H") ||
+      !cudaOk(cudaMemcpyAsync(hStatus + 1, dStatus + 2, 4, cudaMemcpyDeviceToHost, st), "D2H") || !cudaOk(cudaStreamSynchronize(st), "sync")) return -1;
+  if (!cudaOk(cudaGetLastError(), "k_decode_stream<offsets>")) return -1;
+  if ((hStatus[0] || hStatus[1]) && std::getenv("LERC_B200_VERBOSE")) std::fprintf(stderr, "[lerc_b200] stream offsets status %u, verification %u\n", hStatus[0], hStatus[1]);
+  return (hStatus[0] == 0 && hStatus[1] == 0) ? 1 : 0;
 }
 
 // Launches the speculative parallel decoder (lerc_decode_fast.cuh) on the micro-block stream.  Returns false when the
@@ -890,7 +958,12 @@ ErrCode decodeBandT(Context* ctx, DecodeBandArgs& a, BandMaskState& ms) {
   // block boundaries: speculative parallel discovery for masked nDepth == 1 rasters (lerc_decode_fast.cuh), else / on
   // any inconsistency the exact serial walk
   bool haveOffsets = false;
-  if (hd.numValidPixel != nPix && !ta.allValidImage && nDepth == 1 &&
+  if (hd.numValidPixel != nPix && !ta.allValidImage && nDepth == 1) {
+    const int rc = streamBlockOffsets<T>(ctx, hd, ta, dStatus);
+    if (rc < 0) return Failed;
+    if (rc > 0) { haveOffsets = true; globalStats().fastPathDecodes++; }
+  }
+  if (!haveOffsets && hd.numValidPixel != nPix && !ta.allValidImage && nDepth == 1 &&
       launchDecodeFast<T>(ctx, hd, ta.stream, (size_t)ta.streamLen, nullptr, dStatus, ms.dBits, ta.blockOff, &fdArgs)) {
     int hs = 0;
     ctx->joinSide();

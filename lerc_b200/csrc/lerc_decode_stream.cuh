@@ -41,6 +41,7 @@ namespace lerc {
 constexpr int DS_CHUNK = 16384;                 // stream bytes per CTA
 constexpr int DS_SUBS = 16;                     // sub-chunks per chunk, one lane of warp 0 each
 constexpr int DS_SUB = DS_CHUNK / DS_SUBS;
+constexpr int DS_LIST_OFFS = 1032;              // ... in the offsets-only instantiation (masked rasters: runs of one-byte units of empty blocks)
 constexpr int DS_LIST = 264;                    // recorded positions per sub-chunk; more units than that in 1 KB (flat regions: 1..3-byte blocks) -> DSF_FALLBACK
 constexpr int DS_PATCH = 48;                    // hops the patch walk may need before it joins the recorded chain
 constexpr int DS_HOPS = 4;                      // units a head-window position must parse to become the guess (windows without a strict candidate)
@@ -62,7 +63,8 @@ struct StreamDecArgs {
   int chunkBegin;                               // this launch: chunks chunkBegin .. chunkBegin + gridDim.x - 1 (a stream that arrives in strips is decoded strip by strip)
 unsigned long long* hostEnd;                  // mapped host word or nullptr
   unsigned int* hostStatus;                     // mapped host word or nullptr: the final status word | DSF_REPORTED, written by the last CTA of the last launch
-    unsigned int* ticket;                         // this launch's ticket counter (zero at launch)
+    uint32_t* blockOff;                           // OFFS instantiation: [nBlocks] stream offset of every block
+  unsigned int* ticket;                         // this launch's ticket counter (zero at launch)
   unsigned long long* exitState;                // [nChunks] 0 = not yet, else (stream offset where the chunk's chain leaves it) + 1; bit 63: no chain
   unsigned long long* cntState;                 // [nChunks] look-back words over the chunks' block counts
   unsigned long long* groupState;               // [ceil(nChunks / 32)]
@@ -78,6 +80,7 @@ template <class T> struct DecStream {
   static constexpr int LA = ((MAXU + 64 + 15) / 16) * 16;               // look-ahead behind the chunk
   static constexpr int BUFB = 16 + DS_CHUNK + LA;                       // alignment slack | chunk | look-ahead
   static constexpr int SMEM = BUFB + DS_SUBS * DS_LIST * 2;
+  static constexpr int SMEM_OFFS = BUFB + DS_SUBS * DS_LIST_OFFS * 2;
 };
 
 // b / nTx and b % nTx for b < 2^32 with the precomputed magic (exact: the estimate is never more than one too high)
@@ -105,14 +108,19 @@ __device__ __forceinline__ bool dsStrict(const uint8_t* __restrict__ q, int vers
   return (flag & 3) == 1 && !(version >= 5 && (flag & 4)) && osz != 0 && (b & 0xe0) == 0x80 && (b & 31) != 0 && n == 64;
 }
 
-template <class T>
-__global__ void __launch_bounds__(DS_THREADS, 7) k_decode_stream(StreamDecArgs a) {
+// OFFS: the same boundary discovery for rasters with a mask (nDepth == 1): no pixels, no checksum; the stream offset of every block goes to
+// a.blockOff and the general block decoder (k_tiles_decode) does the rest, after k_verify_offsets has checked every unit with
+// its true valid count against the chain.  Empty blocks are one-byte units, hence the longer position lists.
+template <class T, bool OFFS = false>
+__global__ void __launch_bounds__(DS_THREADS, OFFS ? 4 : 7) k_decode_stream(StreamDecArgs a) {
   using C = DecStream<T>;
+  constexpr int LIST = OFFS ? DS_LIST_OFFS : DS_LIST;
+  constexpr int PATCH = OFFS ? C::MAXU + 7 : DS_PATCH;           // (offsets: a run of one-byte units may fill the whole head window in front of the guess)
   constexpr int MAXU = C::MAXU;
   extern __shared__ __align__(16) uint8_t dsSmem[];
   uint8_t* buf = dsSmem;                                   // buf[d + i] = stream[start + i]
-  uint16_t* sListAll = (uint16_t*)(dsSmem + C::BUFB);      // [DS_SUBS][DS_LIST] recorded positions (relative to the chunk start)
-  __shared__ uint16_t sPatch[DS_SUBS][DS_PATCH];
+  uint16_t* sListAll = (uint16_t*)(dsSmem + C::BUFB);      // [DS_SUBS][LIST] recorded positions (relative to the chunk start)
+  __shared__ uint16_t sPatch[DS_SUBS][PATCH];
   __shared__ int sGuess[DS_SUBS], sCnt[DS_SUBS], sExit[DS_SUBS], sDead[DS_SUBS];
   __shared__ int sFirst[DS_SUBS], sNPatch[DS_SUBS], sPre[DS_SUBS + 1], sTrueExit[DS_SUBS];
   __shared__ __align__(8) uint64_t sBar;
@@ -213,7 +221,7 @@ __global__ void __launch_bounds__(DS_THREADS, 7) k_decode_stream(StreamDecArgs a
     // ---- walk: lane s hops through sub-chunk s from its guess, recording the positions
     {
       const int s = lane, subEnd = min((s + 1) * DS_SUB, chunkLen);
-      uint16_t* list = sListAll + s * DS_LIST;
+      uint16_t* list = sListAll + s * LIST;
       int n = 0, dead = 0;
       int guess = s < nSubs ? sGuess[s] : -1, p = guess;
       const int headEnd = min(s * DS_SUB + MAXU, testable);
@@ -221,7 +229,7 @@ __global__ void __launch_bounds__(DS_THREADS, 7) k_decode_stream(StreamDecArgs a
         n = 0; dead = 0; p = guess;
         int pat = 0;
         while (p < subEnd) {
-          if (n >= DS_LIST) { dead = 1; break; }
+          if (n >= LIST) { dead = 1; break; }
           int np;
           const int len = hopLen(p, np);
           if (len <= 0 || (n > 0 && !fdFollows(pat, np, version))) { dead = 1; break; }
@@ -277,7 +285,7 @@ __global__ void __launch_bounds__(DS_THREADS, 7) k_decode_stream(StreamDecArgs a
           while (q < subEnd) {
             while (cursor < n && (int)list[cursor] < q) cursor++;
             if (cursor < n && (int)list[cursor] == q) { joined = true; break; }
-            if (npatch == DS_PATCH || q >= testable) { bad = true; break; }
+            if (npatch == PATCH || q >= testable) { bad = true; break; }
             int pat;
             const int len = hopLen(q, pat);
             if (len <= 0) { bad = true; break; }
@@ -351,7 +359,23 @@ __global__ void __launch_bounds__(DS_THREADS, 7) k_decode_stream(StreamDecArgs a
   const bool ok = sOk != 0;
 
   // ---- decode: 8 lanes per block (lane r = block row r); lane group j takes the blocks of sub-chunk j one after the other
-  if (ok) {
+  if (ok && OFFS) {
+    // ---- offsets only: every recorded unit is one block (nDepth == 1)
+    const unsigned long long blk0 = sBlk0;
+    bool fallback = false;
+    for (int s = tid >> 3; s < nSubs; s += DS_THREADS / 8) {
+      const int npS = sNPatch[s], firstS = sFirst[s], cs = sPre[s + 1] - sPre[s];
+      const uint16_t* list = sListAll + s * LIST;
+      const unsigned long long b0 = blk0 + (unsigned long long)sPre[s];
+      if (cs > 0 && b0 + (unsigned long long)cs > (unsigned long long)nBlocks) { fallback = true; continue; }
+      for (int i = tid & 7; i < cs; i += 8) {
+        const int pos = i < npS ? (int)sPatch[s][i] : (int)list[firstS + i - npS];
+        a.blockOff[b0 + (unsigned long long)i] = (uint32_t)(start + (unsigned long long)pos);
+      }
+    }
+    if (fallback) atomicOr(&a.res->status, DSF_FALLBACK | 4096);
+  }
+  if (ok && !OFFS) {
     T* data = (T*)a.data;
     const bool vecOk = ((a.nCols * (int)sizeof(T)) % 16 == 0) && (((uintptr_t)data & 15) == 0);
     const unsigned long long blk0 = sBlk0;
@@ -360,7 +384,7 @@ __global__ void __launch_bounds__(DS_THREADS, 7) k_decode_stream(StreamDecArgs a
     bool fallback = false; unsigned why = 0;
     for (int s = tid >> 3; s < nSubs && !fallback; s += DS_THREADS / 8) {
     const int npS = sNPatch[s], firstS = sFirst[s], cs = sPre[s + 1] - sPre[s];
-    const uint16_t* list = sListAll + s * DS_LIST;
+    const uint16_t* list = sListAll + s * LIST;
     int p = cs > 0 ? (npS > 0 ? (int)sPatch[s][0] : (int)list[firstS]) : 0;
     int ty = 0, tx = 0;
     if (cs > 0) {
