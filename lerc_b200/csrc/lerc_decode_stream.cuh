@@ -163,10 +163,39 @@ __global__ void __launch_bounds__(DS_THREADS, OFFS ? 4 : 7) k_decode_stream(Stre
   const int testable = (int)min((long long)(DS_CHUNK + C::LA - 32), left);   // positions below it have a full window staged
 
   // one unit at chunk-relative position p (speculative: an 8x8 block is assumed); 0 = does not parse
-  auto hopLen = [&](int p, int& pat) -> int {
+  auto hopPlain = [&](int p, int& pat) -> int {
     int len;
     if (dsStrict<T>(sb + p, version, len, pat) && (long long)len <= left - p) return len;      // the common unit, three byte loads
     return fdHopLen<T>(fdWindow(words, (uint32_t)(d + p)), sb + p, version, left - p, tailRaw, pat);
+  };
+  auto hopLen = [&](int p, int& pat) -> int {
+    if constexpr (OFFS) {
+      // A raw unit of a partly valid block is 1 + n * sizeof(T) bytes for the block's n valid pixels, which only the block's index would
+      // tell.  The smallest n after which two more units parse with consecutive integrity bits is taken (raw wins for small n only);
+      // k_verify_offsets checks the result against the mask.
+      const uint32_t flag = sb[p];
+      if ((flag & 3) == 0 && !(version >= 5 && (flag & 4))) {
+        pat = fdPattern(flag, version);
+        for (int n = 1; n <= 64; n++) {
+          const int len = 1 + n * (int)sizeof(T);
+          if ((long long)len > left - p) break;
+          const int q = p + len;
+          if ((long long)q == left) return len;                        // ends the stream
+          if (q >= testable) break;
+          int pat2, pat3;
+          const bool raw2 = (sb[q] & 3) == 0 && !(version >= 5 && (sb[q] & 4));
+          const int len2 = raw2 ? -1 : hopPlain(q, pat2);
+          if (raw2) { if (fdFollows(pat, fdPattern(sb[q], version), version)) return len; continue; }
+          if (len2 <= 0 || !fdFollows(pat, pat2, version)) continue;
+          const int q2 = q + len2;
+          if ((long long)q2 == left || q2 >= testable) return len;
+          const bool raw3 = (sb[q2] & 3) == 0 && !(version >= 5 && (sb[q2] & 4));
+          if (raw3 ? fdFollows(pat2, fdPattern(sb[q2], version), version) : (hopPlain(q2, pat3) > 0 && fdFollows(pat2, pat3, version))) return len;
+        }
+        return 0;
+      }
+    }
+    return hopPlain(p, pat);
   };
 
   // ---- guess: every warp scans the head windows of four sub-chunks
@@ -201,7 +230,7 @@ __global__ void __launch_bounds__(DS_THREADS, OFFS ? 4 : 7) k_decode_stream(Stre
           for (int hop = 0; hop < DS_HOPS; hop++) {
             if (alive && q < testable) {
               int np;
-              const int len = hopLen(q, np);
+              const int len = hopPlain(q, np);                            // (guessing never resolves raw units by trial: too many bytes look like one)
               if (len <= 0 || (hop > 0 && !fdFollows(pat, np, version))) alive = false;
               else { if (hop == 0) firstRaw = len == MAXU; q += len; pat = np; }
             }
@@ -240,7 +269,7 @@ __global__ void __launch_bounds__(DS_THREADS, OFFS ? 4 : 7) k_decode_stream(Stre
         // window from which a unit parses is tried (rare; the other lanes wait)
         if (!dead || (c == 0 && s == 0)) break;
         int q = guess + 1;
-        for (; q < headEnd; q++) { int np; if (hopLen(q, np) > 0) break; }
+        for (; q < headEnd; q++) { int np; if (hopPlain(q, np) > 0) break; }
         if (q >= headEnd) break;
         guess = q;
       }
