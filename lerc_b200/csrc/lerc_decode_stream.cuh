@@ -168,29 +168,52 @@ __global__ void __launch_bounds__(DS_THREADS, OFFS ? 4 : 7) k_decode_stream(Stre
     if (dsStrict<T>(sb + p, version, len, pat) && (long long)len <= left - p) return len;      // the common unit, three byte loads
     return fdHopLen<T>(fdWindow(words, (uint32_t)(d + p)), sb + p, version, left - p, tailRaw, pat);
   };
+  // `hops` more units parse from q with consecutive integrity bits (a raw unit on the way is taken on its integrity bits alone)
+  auto plainChain = [&](int q, int patPrev, int hops) -> bool {
+    for (int hI = 0; hI < hops; hI++) {
+      if ((long long)q >= left || q >= testable) return true;
+      const uint32_t f = sb[q];
+      if ((f & 3) == 0 && !(version >= 5 && (f & 4))) return fdFollows(patPrev, fdPattern(f, version), version);
+      int pt; const int len = hopPlain(q, pt);
+      if (len <= 0 || !fdFollows(patPrev, pt, version)) return false;
+      q += len; patPrev = pt;
+    }
+    return true;
+  };
   auto hopLen = [&](int p, int& pat) -> int {
     if constexpr (OFFS) {
       // A raw unit of a partly valid block is 1 + n * sizeof(T) bytes for the block's n valid pixels, which only the block's index would
-      // tell.  The smallest n after which two more units parse with consecutive integrity bits is taken (raw wins for small n only);
-      // k_verify_offsets checks the result against the mask.
+      // tell.  The smallest n behind which five more units parse with consecutive integrity bits is taken (raw wins for small n only; a
+      // raw unit among the five is resolved the same way, one level deep); k_verify_offsets checks the result against the mask.
       const uint32_t flag = sb[p];
       if ((flag & 3) == 0 && !(version >= 5 && (flag & 4))) {
         pat = fdPattern(flag, version);
         for (int n = 1; n <= 64; n++) {
           const int len = 1 + n * (int)sizeof(T);
           if ((long long)len > left - p) break;
-          const int q = p + len;
-          if ((long long)q == left) return len;                        // ends the stream
-          if (q >= testable) break;
-          int pat2, pat3;
-          const bool raw2 = (sb[q] & 3) == 0 && !(version >= 5 && (sb[q] & 4));
-          const int len2 = raw2 ? -1 : hopPlain(q, pat2);
-          if (raw2) { if (fdFollows(pat, fdPattern(sb[q], version), version)) return len; continue; }
-          if (len2 <= 0 || !fdFollows(pat, pat2, version)) continue;
-          const int q2 = q + len2;
-          if ((long long)q2 == left || q2 >= testable) return len;
-          const bool raw3 = (sb[q2] & 3) == 0 && !(version >= 5 && (sb[q2] & 4));
-          if (raw3 ? fdFollows(pat2, fdPattern(sb[q2], version), version) : (hopPlain(q2, pat3) > 0 && fdFollows(pat2, pat3, version))) return len;
+          if ((long long)(p + len) == left) return len;                // ends the stream
+          if (p + len >= testable) break;
+          bool okc = true;
+          int qq = p + len, pp = pat;
+          for (int hI = 0; hI < 5 && okc; hI++) {
+            if ((long long)qq >= left || qq >= testable) break;
+            const uint32_t f = sb[qq];
+            if ((f & 3) == 0 && !(version >= 5 && (f & 4))) {
+              const int pf = fdPattern(f, version);
+              okc = false;
+              if (fdFollows(pp, pf, version))
+                for (int n2 = 1; n2 <= 64 && !okc; n2++) {
+                  const long long q2 = (long long)qq + 1 + (long long)n2 * (int)sizeof(T);
+                  if (q2 > left) break;
+                  okc = q2 == left || q2 >= testable || plainChain((int)q2, pf, 4);
+                }
+              break;
+            }
+            int pt; const int len2 = hopPlain(qq, pt);
+            if (len2 <= 0 || !fdFollows(pp, pt, version)) okc = false;
+            else { qq += len2; pp = pt; }
+          }
+          if (okc) return len;
         }
         return 0;
       }
@@ -317,6 +340,9 @@ __global__ void __launch_bounds__(DS_THREADS, OFFS ? 4 : 7) k_decode_stream(Stre
             if (npatch == PATCH || q >= testable) { bad = true; break; }
             int pat;
             const int len = hopLen(q, pat);
+#ifdef LERC_CUSIM
+            if (len <= 0 && std::getenv("DS_DEBUG3")) { std::fprintf(stderr, "      patch hop failed: chunk %d sub %d q %d npatch %d bytes", c, s, q, npatch); for (int k = 0; k < 24; k++) std::fprintf(stderr, " %02x", sb[q + k]); std::fprintf(stderr, "\n"); }
+#endif
             if (len <= 0) { bad = true; break; }
             sPatch[s][npatch++] = (uint16_t)q;
             q += len;
