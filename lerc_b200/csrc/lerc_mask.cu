@@ -307,8 +307,74 @@ __global__ void __launch_bounds__(32) k_rle_decode(const uint8_t* __restrict__ s
   }
   if (lane == 0) *status = ok;
 }
+// ---- the same in two steps for masks of more than a few KB: one warp hops over the token HEADERS only (the chain is serial, but a
+// hop is a few shared-memory reads, whatever the token's length) and lists the tokens; then every thread fills 16 output bytes, finding
+// its token by binary search.  Verdict and bytes written are those of k_rle_decode (RLE.cpp:298-331).
+struct RleTok { uint32_t ip, op; int32_t c; };        // payload position, output position, count (> 0 literal bytes, <= 0 one byte repeated)
+
+__global__ void __launch_bounds__(32) k_rle_tokens(const uint8_t* __restrict__ src, long long srcLen, long long dstLen, RleTok* __restrict__ tok, uint32_t maxTok,
+                                                   uint32_t* __restrict__ nTokOut, int* __restrict__ status) {
+  constexpr int WIN = 8192;
+  __shared__ __align__(16) uint8_t win[WIN + 16];
+  const int lane = threadIdx.x;
+  long long wBase = 0; bool haveWin = false;
+  const int mis = (int)((uintptr_t)src & 15);
+  auto fill = [&](long long i) {
+    const long long a0 = ((i + mis) & ~15ll) - mis;
+    for (int c = lane; c < WIN / 16; c += 32) {
+      const long long s0 = a0 + (long long)c * 16;
+      uint4 x = make_uint4(0, 0, 0, 0);
+      if (s0 < srcLen && s0 + 16 > 0) x = *(const uint4*)(src + s0);
+      ((uint4*)win)[c] = x;
+    }
+    wBase = a0; haveWin = true;
+    __syncwarp();
+  };
+  long long ip = 0, op = 0;
+  uint32_t n = 0;
+  int ok = 1;
+  for (;;) {
+    if (ip + 2 > srcLen) { ok = 0; break; }
+    if (!haveWin || ip < wBase || ip + 4 > wBase + WIN) { __syncwarp(); fill(ip); }
+    const int c = (int)(int16_t)(win[ip - wBase] | (win[ip + 1 - wBase] << 8));
+    ip += 2;
+    if (c == -32768) break;
+    const long long cnt = c <= 0 ? -c : c, take = c > 0 ? cnt : 1;
+    if (ip + take + 2 > srcLen || op + cnt > dstLen || n >= maxTok) { ok = 0; break; }
+    if (lane == 0) { RleTok t; t.ip = (uint32_t)ip; t.op = (uint32_t)op; t.c = c; tok[n] = t; }
+    n++;
+    ip += take; op += cnt;
+  }
+  if (lane == 0) { RleTok t; t.ip = 0; t.op = (uint32_t)op; t.c = 0; tok[n] = t; *nTokOut = n; *status = ok; }   // (sentinel: where the output ends)
+}
+
+__global__ void k_rle_expand(const uint8_t* __restrict__ src, const RleTok* __restrict__ tok, const uint32_t* __restrict__ nTokIn, uint8_t* __restrict__ dst) {
+  const uint32_t nTok = *nTokIn;
+  if (nTok == 0) return;
+  const uint32_t total = tok[nTok].op;
+  for (uint32_t o0 = (blockIdx.x * blockDim.x + threadIdx.x) * 16u; o0 < total; o0 += gridDim.x * blockDim.x * 16u) {
+    uint32_t lo = 0, hi = nTok - 1;                                   // last token with op <= o0
+    while (lo < hi) { const uint32_t mid = (lo + hi + 1) >> 1; if (tok[mid].op <= o0) lo = mid; else hi = mid - 1; }
+    uint32_t t = lo;
+    RleTok cur = tok[t];
+    uint32_t end = tok[t + 1].op;
+    const uint32_t oEnd = min(o0 + 16u, total);
+    for (uint32_t o = o0; o < oEnd; o++) {
+      while (o >= end) { t++; cur = tok[t]; end = tok[t + 1].op; }
+      dst[o] = cur.c > 0 ? src[cur.ip + (o - cur.op)] : src[cur.ip];
+    }
+  }
+}
+
 void launchRleDecode(Context* ctx, const uint8_t* dSrc, long long srcLen, uint8_t* dDst, long long dstLen, int* dStatus) {
-  LERC_LAUNCH(ctx, k_rle_decode, 1, 32, 0, dSrc, srcLen, dDst, dstLen, dStatus);
+  if (srcLen < 2048 || srcLen >= (1ll << 31) || dstLen >= (1ll << 31)) { LERC_LAUNCH(ctx, k_rle_decode, 1, 32, 0, dSrc, srcLen, dDst, dstLen, dStatus); return; }
+  const uint32_t maxTok = (uint32_t)(srcLen / 3 + 2);
+  RleTok* dTok = (RleTok*)ctx->arena.alloc(sizeof(RleTok) * ((size_t)maxTok + 2));
+  uint32_t* dN = (uint32_t*)ctx->arena.alloc(16);
+  if (!dTok || !dN) { LERC_LAUNCH(ctx, k_rle_decode, 1, 32, 0, dSrc, srcLen, dDst, dstLen, dStatus); return; }
+  LERC_LAUNCH(ctx, k_rle_tokens, 1, 32, 0, dSrc, srcLen, dstLen, dTok, maxTok, dN, dStatus);
+  const int grid = (int)std::min<long long>((dstLen / 16 + 255) / 256 + 1, 148 * 16);
+  LERC_LAUNCH(ctx, k_rle_expand, grid, 256, 0, dSrc, dTok, dN, dDst);
 }
 
 // ------------------------------------------------------------------------------------------------
