@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(DS_THREADS, OFFS ? 4 : 7) k_decode_stream(Stre
   auto hopLen = [&](int p, int& pat) -> int {
     if constexpr (OFFS) {
       // A raw unit of a partly valid block is 1 + n * sizeof(T) bytes for the block's n valid pixels, which only the block's index would
-      // tell.  The smallest n behind which five more units parse with consecutive integrity bits is taken (raw wins for small n only; a
+      // tell.  The smallest n behind which eight more units parse with consecutive integrity bits is taken (raw wins for small n only; a
       // raw unit among the five is resolved the same way, one level deep); k_verify_offsets checks the result against the mask.
       const uint32_t flag = sb[p];
       if ((flag & 3) == 0 && !(version >= 5 && (flag & 4))) {
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(DS_THREADS, OFFS ? 4 : 7) k_decode_stream(Stre
           if (p + len >= testable) break;
           bool okc = true;
           int qq = p + len, pp = pat;
-          for (int hI = 0; hI < 5 && okc; hI++) {
+          for (int hI = 0; hI < 8 && okc; hI++) {
             if ((long long)qq >= left || qq >= testable) break;
             const uint32_t f = sb[qq];
             if ((f & 3) == 0 && !(version >= 5 && (f & 4))) {
@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(DS_THREADS, OFFS ? 4 : 7) k_decode_stream(Stre
                 for (int n2 = 1; n2 <= 64 && !okc; n2++) {
                   const long long q2 = (long long)qq + 1 + (long long)n2 * (int)sizeof(T);
                   if (q2 > left) break;
-                  okc = q2 == left || q2 >= testable || plainChain((int)q2, pf, 4);
+                  okc = q2 == left || q2 >= testable || plainChain((int)q2, pf, 6);
                 }
               break;
             }
