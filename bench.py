@@ -47,6 +47,8 @@ WORKLOADS = {
     "c4": (8192, 8192, 3, 1, 0.0, "8192x8192 nDepth=3 uint8 lossless (Huffman path)"),
     # not a BASELINE config: configs[1]'s raster at maxZError 0 = the lossless float (FPL) codec, for profiling that path
     "c2l": (4096, 4096, 1, 6, 0.0, "4096x4096 float32 1-band encode+decode maxZError=0 (lossless float codec)"),
+    # not a BASELINE config either: configs[1]'s raster under a california-shaped validity mask (ragged coast, one third invalid): the masked paths
+    "c2m": (4096, 4096, 1, 6, 0.01, "4096x4096 float32 1-band, coast-shaped validity mask (one third invalid), encode+decode maxZError=0.01"),
     # per-rank strip of the 65536^2 raster; rows can be lowered with --strip-rows for a quick run
     "c5": (8192, 65536, 1, 6, 0.01, "65536x65536 float32 as 256x256 tiles, 8192-row strip (8192 tiles) per GPU, encodeTiles+decodeTiles maxZError=0.01"),
 }
@@ -55,7 +57,7 @@ BANDS = {"c3": 4}                      # bands per call (default 1)
 NVLINK_PEER_GBS = 770.0                # measured peer copy per direction (B200_PROFILING.md)
 
 
-METRIC = {"c2": "Gpixels/s encode+decode float32 @ maxZError=0.01; achieved HBM GB/s vs peak", "c3": "Gpixels/s (pixels x bands) encode+decode float32 4 bands @ maxZError=0.001", "c2l": "Gpixels/s encode+decode float32 lossless", "c4": "Gpixels/s encode+decode uint8 nDepth=3 lossless",
+METRIC = {"c2": "Gpixels/s encode+decode float32 @ maxZError=0.01; achieved HBM GB/s vs peak", "c3": "Gpixels/s (pixels x bands) encode+decode float32 4 bands @ maxZError=0.001", "c2l": "Gpixels/s encode+decode float32 lossless", "c2m": "Gpixels/s encode+decode float32 @ maxZError=0.01 with a validity mask", "c4": "Gpixels/s encode+decode uint8 nDepth=3 lossless",
           "c5": "Gpixels/s encode+decode float32 @ maxZError=0.01, 256x256 tiles (one blob per tile); achieved HBM GB/s vs peak"}
 
 
@@ -202,6 +204,15 @@ def bench_raster_sub(lib, workload, steps, rank, world, peak_gbs):
         d_img = device_c4_raster(torch, rows, cols, 7 + rank)
     else:
         d_img = torch.stack([device_c2_strip(torch, rows, cols, 0, 1234 + b + 16 * rank) for b in range(bands)])
+    d_mask = d_dmask = None
+    if workload == "c2m":                                                      # valid to the right of a ragged coast line
+        yy = torch.arange(rows, device="cuda", dtype=torch.float32)[:, None]
+        xx = torch.arange(cols, device="cuda", dtype=torch.float32)[None, :]
+        coast = 0.34 * cols + 0.12 * cols * torch.sin(yy / 300.0) + 120 * torch.sin(yy / 37.0) + 25 * torch.sin(yy / 5.0)
+        d_mask = (xx > coast).to(torch.uint8).contiguous()
+        d_dmask = torch.empty_like(d_mask)
+    n_masks = 1 if d_mask is not None else 0
+    p_mask, p_dmask = (d_mask.data_ptr(), d_dmask.data_ptr()) if n_masks else (None, None)
     raw_bytes = d_img.numel() * d_img.element_size()
     cap = min(raw_bytes + raw_bytes // 8 + 4096, 0xF0000000)                  # (outBufferSize is a 32-bit count)
     d_blob = torch.empty(cap, dtype=torch.uint8, device="cuda")
@@ -212,9 +223,9 @@ def bench_raster_sub(lib, workload, steps, rank, world, peak_gbs):
     tight = [cap]
 
     def step():
-        st = enc(d_img.data_ptr(), dt, depth, cols, rows, bands, 0, None, mz, d_blob.data_ptr(), tight[0], C.addressof(n_written))
+        st = enc(d_img.data_ptr(), dt, depth, cols, rows, bands, n_masks, p_mask, mz, d_blob.data_ptr(), tight[0], C.addressof(n_written))
         assert st == 0, f"{workload}: lerc_encode status {st}"
-        st = dec(d_blob.data_ptr(), n_written.value, 0, None, depth, cols, rows, bands, dt, d_dec.data_ptr())
+        st = dec(d_blob.data_ptr(), n_written.value, n_masks, p_dmask, depth, cols, rows, bands, dt, d_dec.data_ptr())
         assert st == 0, f"{workload}: lerc_decode status {st}"
         return n_written.value
 
@@ -239,7 +250,11 @@ def bench_raster_sub(lib, workload, steps, rank, world, peak_gbs):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item()) / steps
-    err = float((d_dec.double() - d_img.double()).abs().max().item())
+    if n_masks:
+        assert bool((d_dmask == d_mask).all()), f"{workload}: mask round trip"
+        err = float(((d_dec.double() - d_img.double()).abs() * d_mask.double()).max().item())
+    else:
+        err = float((d_dec.double() - d_img.double()).abs().max().item())
     assert err <= max(mz, 0.5 if dt < 6 else 0) * 1.1 + 1e-12, f"{workload}: round trip error {err} exceeds maxZError {mz}"
     lerc_b200.kernel_times(reset=True)
     lerc_b200.profile(True)
@@ -507,7 +522,7 @@ def main():
     assert lib is not None, "lerc_b200/libLerc.so.4 missing: run python __graft_entry__.py"
     if args.workload == "c5":
         return main_tiles(args, lib, rank, world, local_rank, warm, peak_gbs, peak_src)
-    if args.workload in ("c3", "c4"):                                   # the big rasters: device-generated, one buffer set (far larger than L2)
+    if args.workload in ("c3", "c4", "c2m"):                                   # the big rasters: device-generated, one buffer set (far larger than L2)
         rec = bench_raster_sub(lib, args.workload, max(3, min(args.steps, 10)), rank, world, peak_gbs)
         if rank == 0:
             print(json.dumps({"metric": METRIC[args.workload], "value": rec["value"], "unit": "Gpixels/s", "n_gpus": world, "steps": rec["steps"], "warmup": 3,
@@ -750,12 +765,12 @@ def main():
         import copy
         sub_args = copy.copy(args)
         sub_args.steps, sub_args.gather = 5, True
-        for name in ("c5", "c4", "c3"):
+        for name in ("c5", "c4", "c3", "c2m"):
             try:
                 if name == "c5":
                     subs[name] = main_tiles(sub_args, lib, rank, world, local_rank, warm, peak_gbs, peak_src, sub=True)
                 elif name == "c4" or world == 1:
-                    subs[name] = bench_raster_sub(lib, name, 5 if name == "c4" else 3, rank, world, peak_gbs)
+                    subs[name] = bench_raster_sub(lib, name, 5 if name in ("c4", "c2m") else 3, rank, world, peak_gbs)
             except Exception as ex:                                      # a sub-record must not take the headline down with it
                 subs[name] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
                 torch.cuda.empty_cache()
