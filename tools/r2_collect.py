@@ -11,7 +11,7 @@ P = os.path.join(ROOT, "profiles")
 UNIT = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 
 for name, dst in [("bench_n1.json", f"{tag}_bench_c2.json"), ("bench_reference_arm.json", f"{tag}_bench_c2_reference_arm.json"), ("bench_c3.json", f"{tag}_bench_c3.json"),
-                  ("bench_c4.json", f"{tag}_bench_c4.json"), ("bench_c5.json", f"{tag}_bench_c5.json"), ("launches.csv", f"{tag}_launches.csv"),
+                  ("bench_c4.json", f"{tag}_bench_c4.json"), ("bench_c5.json", f"{tag}_bench_c5.json"), ("bench_c2m.json", f"{tag}_bench_c2m.json"), ("launches.csv", f"{tag}_launches.csv"),
                   ("gpu_tests.log", f"{tag}_gpu_tests.log")]:
     f = os.path.join(src, name)
     if os.path.exists(f):

@@ -35,4 +35,4 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_h
 tail -1 "$OUT/ncu_c4.log"
 export_rep prof_c4; rm -f "$OUT/prof_c4.ncu-rep"
 du -sh "$OUT"
-for w in c4 c5 c3; do timeout 600 python bench.py --workload $w --steps 5 --no-cpu-baseline > "$OUT/bench_$w.json" 2> "$OUT/bench_$w.err"; done
+for w in c4 c5 c3 c2m; do timeout 600 python bench.py --workload $w --steps 5 --no-cpu-baseline > "$OUT/bench_$w.json" 2> "$OUT/bench_$w.err"; done
