@@ -24,6 +24,9 @@ extern "C" {
 /* Device pointers and ordering: without lerc_b200_set_stream the library works on a private NON-BLOCKING stream, so
  * device buffers handed to lerc_* must be complete (synchronise the producing stream first); results are complete
  * when the call returns.  With lerc_b200_set_stream the calls are ordered on the given stream like any other work.
+ * Device buffers are read in aligned 16-byte chunks: a chunk holding the first or last bytes of a buffer may include up to 15
+ * bytes outside it (never across a page, never used); pad device blobs to a multiple of 16 bytes if a memory checker objects.
+ * Host buffers: pass pinned memory to get the copy / compute overlap inside the call (strips; LERC_B200_STRIP_LOG2).
  *
  * Use `cudaStream` (a cudaStream_t passed as void*) for all work issued by the calling thread's next
  * lerc_* calls when enable != 0; enable == 0 returns to the library's private non-blocking stream.
