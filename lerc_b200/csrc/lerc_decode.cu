@@ -128,6 +128,13 @@ __global__ void k_verify_offsets(DecTileArgs a) {
       cur += len;
     }
     if (!bad && blk + 1 < nBlocks && cur != (unsigned long long)a.blockOff[blk + 1]) bad = true;
+#ifdef LERC_CUSIM
+    if (bad && std::getenv("DS_DEBUG3")) {
+      std::fprintf(stderr, "      verify: block %d (ty %d tx %d) off %u next %u parsed end %llu valid %d bytes", blk, ty, tx, a.blockOff[blk], blk + 1 < nBlocks ? a.blockOff[blk + 1] : 0u, cur, blockValidCount(a, i0, j0, h, w));
+      for (int k = 0; k < 20; k++) std::fprintf(stderr, " %02x", a.stream[a.blockOff[blk] + k]);
+      std::fprintf(stderr, "\n");
+    }
+#endif
     if (bad) atomicOr(a.status + 2, 1);
   }
 }

@@ -168,12 +168,36 @@ __global__ void __launch_bounds__(DS_THREADS, OFFS ? 4 : 7) k_decode_stream(Stre
     if (dsStrict<T>(sb + p, version, len, pat) && (long long)len <= left - p) return len;      // the common unit, three byte loads
     return fdHopLen<T>(fdWindow(words, (uint32_t)(d + p)), sb + p, version, left - p, tailRaw, pat);
   };
-  // `hops` more units parse from q with consecutive integrity bits (a raw unit on the way is taken on its integrity bits alone)
-  auto plainChain = [&](int q, int patPrev, int hops) -> bool {
+  // `hops` more units parse from q with consecutive integrity bits.  level 0: none of them may look like a raw unit; level 1: one raw
+  // unit on the way is resolved by trying its sizes with a level-0 look-ahead behind it; level 2: a raw unit is taken on its
+  // integrity bits alone.  (The bytes of raw pixels often look like short units; an encoder's empty-block byte has zero top bits.)
+  auto looksRaw = [&](uint32_t f) { return (f & 3) == 0 && !(version >= 5 && (f & 4)); };
+  auto chainFrom = [&](int q, int patPrev, int hops, int level) -> bool {
     for (int hI = 0; hI < hops; hI++) {
       if ((long long)q >= left || q >= testable) return true;
       const uint32_t f = sb[q];
-      if ((f & 3) == 0 && !(version >= 5 && (f & 4))) return fdFollows(patPrev, fdPattern(f, version), version);
+      if (looksRaw(f)) {
+        const int pf = fdPattern(f, version);
+        if (level == 0 || !fdFollows(patPrev, pf, version)) return false;
+        if (level == 2) return true;
+        for (int n2 = 1; n2 <= 64; n2++) {                              // level 1: sizes of the nested raw unit
+          const long long q2 = (long long)q + 1 + (long long)n2 * (int)sizeof(T);
+          if (q2 > left) return false;
+          if (q2 == left || q2 >= testable) return true;
+          // (inlined level-0 look-ahead, 6 units)
+          int qq = (int)q2, pp = pf; bool ok0 = true;
+          for (int h2 = 0; h2 < 6 && ok0; h2++) {
+            if ((long long)qq >= left || qq >= testable) break;
+            const uint32_t f2 = sb[qq];
+            if (looksRaw(f2) || ((f2 & 3) == 2 && (f2 & 0xc0))) { ok0 = false; break; }
+            int pt; const int l2 = hopPlain(qq, pt);
+            if (l2 <= 0 || !fdFollows(pp, pt, version)) ok0 = false; else { qq += l2; pp = pt; }
+          }
+          if (ok0) return true;
+        }
+        return false;
+      }
+      if ((f & 3) == 2 && (f & 0xc0)) return false;
       int pt; const int len = hopPlain(q, pt);
       if (len <= 0 || !fdFollows(patPrev, pt, version)) return false;
       q += len; patPrev = pt;
@@ -183,38 +207,22 @@ __global__ void __launch_bounds__(DS_THREADS, OFFS ? 4 : 7) k_decode_stream(Stre
   auto hopLen = [&](int p, int& pat) -> int {
     if constexpr (OFFS) {
       // A raw unit of a partly valid block is 1 + n * sizeof(T) bytes for the block's n valid pixels, which only the block's index would
-      // tell.  The smallest n behind which eight more units parse with consecutive integrity bits is taken (raw wins for small n only; a
-      // raw unit among the five is resolved the same way, one level deep); k_verify_offsets checks the result against the mask.
+      // tell.  The smallest n behind which eight more units parse with consecutive integrity bits is taken (raw wins for small n only),
+      // strictest look-ahead first; k_verify_offsets checks the result against the mask.
       const uint32_t flag = sb[p];
-      if ((flag & 3) == 0 && !(version >= 5 && (flag & 4))) {
+      if (looksRaw(flag)) {
         pat = fdPattern(flag, version);
-        for (int n = 1; n <= 64; n++) {
-          const int len = 1 + n * (int)sizeof(T);
-          if ((long long)len > left - p) break;
-          if ((long long)(p + len) == left) return len;                // ends the stream
-          if (p + len >= testable) break;
-          bool okc = true;
-          int qq = p + len, pp = pat;
-          for (int hI = 0; hI < 8 && okc; hI++) {
-            if ((long long)qq >= left || qq >= testable) break;
-            const uint32_t f = sb[qq];
-            if ((f & 3) == 0 && !(version >= 5 && (f & 4))) {
-              const int pf = fdPattern(f, version);
-              okc = false;
-              if (fdFollows(pp, pf, version))
-                for (int n2 = 1; n2 <= 64 && !okc; n2++) {
-                  const long long q2 = (long long)qq + 1 + (long long)n2 * (int)sizeof(T);
-                  if (q2 > left) break;
-                  okc = q2 == left || q2 >= testable || plainChain((int)q2, pf, 6);
-                }
-              break;
-            }
-            int pt; const int len2 = hopPlain(qq, pt);
-            if (len2 <= 0 || !fdFollows(pp, pt, version)) okc = false;
-            else { qq += len2; pp = pt; }
+        for (int level = 0; level < 3; level++)
+          for (int n = 1; n <= 64; n++) {
+            const int len = 1 + n * (int)sizeof(T);
+            if ((long long)len > left - p) break;
+            if ((long long)(p + len) == left) return len;              // ends the stream
+            if (p + len >= testable) break;
+            if (chainFrom(p + len, pat, 8, level)) return len;
           }
-          if (okc) return len;
-        }
+#ifdef LERC_CUSIM
+        if (std::getenv("DS_DEBUG3")) { std::fprintf(stderr, "      raw trial failed: chunk %d p %d bytes", c, p); for (int k = 0; k < 24; k++) std::fprintf(stderr, " %02x", sb[p + k]); std::fprintf(stderr, "\n"); }
+#endif
         return 0;
       }
     }
