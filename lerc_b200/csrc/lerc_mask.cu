@@ -314,8 +314,12 @@ struct RleTok { uint32_t ip, op; int32_t c; };        // payload position, outpu
 
 __global__ void __launch_bounds__(32) k_rle_tokens(const uint8_t* __restrict__ src, long long srcLen, long long dstLen, RleTok* __restrict__ tok, uint32_t maxTok,
                                                    uint32_t* __restrict__ nTokOut, int* __restrict__ status) {
+  // The header chain is serial.  Per 8 KB window all lanes first work out, for EVERY byte position, the token that would start there
+  // (its length in the stream and its count), so that the hop itself is two shared-memory reads and an add.
   constexpr int WIN = 8192;
   __shared__ __align__(16) uint8_t win[WIN + 16];
+  __shared__ uint16_t sLen[WIN];                   // 0: terminator, or a header that does not lie wholly inside the window
+  __shared__ int16_t sCnt[WIN];
   const int lane = threadIdx.x;
   long long wBase = 0; bool haveWin = false;
   const int mis = (int)((uintptr_t)src & 15);
@@ -329,6 +333,15 @@ __global__ void __launch_bounds__(32) k_rle_tokens(const uint8_t* __restrict__ s
     }
     wBase = a0; haveWin = true;
     __syncwarp();
+    for (int p = lane; p < WIN; p += 32) {
+      int len = 0, c = 0;
+      if (p + 2 <= WIN) {
+        c = (int)(int16_t)(win[p] | (win[p + 1] << 8));
+        if (c != -32768) len = 2 + (c > 0 ? c : 1);
+      }
+      sLen[p] = (uint16_t)len; sCnt[p] = (int16_t)c;
+    }
+    __syncwarp();
   };
   long long ip = 0, op = 0;
   uint32_t n = 0;
@@ -336,6 +349,21 @@ __global__ void __launch_bounds__(32) k_rle_tokens(const uint8_t* __restrict__ s
   for (;;) {
     if (ip + 2 > srcLen) { ok = 0; break; }
     if (!haveWin || ip < wBase || ip + 4 > wBase + WIN) { __syncwarp(); fill(ip); }
+    // ---- fast hops inside the window
+    {
+      int rel = (int)(ip - wBase);
+      const long long ipLimit = srcLen - 2;                              // a token and the next header must fit: ip + len + 2 <= srcLen
+      while (rel + 4 <= WIN) {
+        const int len = sLen[rel], c = sCnt[rel];
+        const int cnt = c <= 0 ? -c : c;
+        if (len == 0 || ip + len > ipLimit || op + cnt > dstLen || n >= maxTok) break;
+        if (lane == 0) { RleTok t; t.ip = (uint32_t)(ip + 2); t.op = (uint32_t)op; t.c = c; tok[n] = t; }
+        n++; ip += len; op += cnt; rel += len;
+      }
+      if (ip + 2 > srcLen) { ok = 0; break; }
+      if (ip < wBase || ip + 4 > wBase + WIN) { __syncwarp(); fill(ip); }
+    }
+    // ---- one token the exact way (terminator, bounds, list full)
     const int c = (int)(int16_t)(win[ip - wBase] | (win[ip + 1 - wBase] << 8));
     ip += 2;
     if (c == -32768) break;
