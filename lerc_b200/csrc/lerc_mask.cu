@@ -320,6 +320,8 @@ __global__ void __launch_bounds__(32) k_rle_tokens(const uint8_t* __restrict__ s
   __shared__ __align__(16) uint8_t win[WIN + 16];
   __shared__ uint16_t sLen[WIN];                   // 0: terminator, or a header that does not lie wholly inside the window
   __shared__ int16_t sCnt[WIN];
+  constexpr int LISTCAP = WIN / 3 + 1;
+  __shared__ uint16_t sList[LISTCAP];              // positions of the window's tokens
   const int lane = threadIdx.x;
   long long wBase = 0; bool haveWin = false;
   const int mis = (int)((uintptr_t)src & 15);
@@ -349,16 +351,37 @@ __global__ void __launch_bounds__(32) k_rle_tokens(const uint8_t* __restrict__ s
   for (;;) {
     if (ip + 2 > srcLen) { ok = 0; break; }
     if (!haveWin || ip < wBase || ip + 4 > wBase + WIN) { __syncwarp(); fill(ip); }
-    // ---- fast hops inside the window
+    // ---- the window's tokens: positions by a bare hop loop (two shared-memory reads and an add per token), then counts, output
+    // positions (warp scan), bounds and records for 32 tokens at a time
     {
-      int rel = (int)(ip - wBase);
-      const long long ipLimit = srcLen - 2;                              // a token and the next header must fit: ip + len + 2 <= srcLen
-      while (rel + 4 <= WIN) {
-        const int len = sLen[rel], c = sCnt[rel];
-        const int cnt = c <= 0 ? -c : c;
-        if (len == 0 || ip + len > ipLimit || op + cnt > dstLen || n >= maxTok) break;
-        if (lane == 0) { RleTok t; t.ip = (uint32_t)(ip + 2); t.op = (uint32_t)op; t.c = c; tok[n] = t; }
-        n++; ip += len; op += cnt; rel += len;
+      int rel = (int)(ip - wBase), k = 0;
+      while (rel + 4 <= WIN && k < LISTCAP) {
+        const int len = sLen[rel];
+        if (len == 0) break;
+        if (lane == 0) sList[k] = (uint16_t)rel;
+        k++; rel += len;
+      }
+      __syncwarp();
+      bool stop = false;
+      for (int base = 0; base < k && !stop; base += 32) {
+        const int i = base + lane;
+        const bool have = i < k;
+        const int r = have ? (int)sList[i] : 0;
+        const int c = have ? (int)sCnt[r] : 0, len = have ? (int)sLen[r] : 0;
+        const long long cnt = c <= 0 ? -c : c;
+        long long inc = cnt;
+#pragma unroll
+        for (int m = 1; m < 32; m <<= 1) { const long long o = __shfl_up_sync(FULL, inc, m); if (lane >= m) inc += o; }
+        const long long myOp = op + inc - cnt, myIp = wBase + r;
+        const bool bad = have && (myIp + len + 2 > srcLen || myOp + cnt > dstLen || (unsigned long long)n + (unsigned)(i - base) >= maxTok);
+        const unsigned mb = __ballot_sync(FULL, bad), mh = __ballot_sync(FULL, have);
+        const int nGood = mb ? __ffs(mb) - 1 : __popc(mh);                 // tokens of this batch before the first one that needs the exact path
+        if (lane < nGood) { RleTok t; t.ip = (uint32_t)(myIp + 2); t.op = (uint32_t)myOp; t.c = c; tok[n + lane] = t; }
+        if (nGood > 0) {
+          const long long endIp = __shfl_sync(FULL, myIp + len, nGood - 1), endOp = __shfl_sync(FULL, myOp + cnt, nGood - 1);
+          ip = endIp; op = endOp; n += (uint32_t)nGood;
+        }
+        if (mb) stop = true;
       }
       if (ip + 2 > srcLen) { ok = 0; break; }
       if (ip < wBase || ip + 4 > wBase + WIN) { __syncwarp(); fill(ip); }
