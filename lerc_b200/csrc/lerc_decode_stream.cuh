@@ -112,7 +112,7 @@ __device__ __forceinline__ bool dsStrict(const uint8_t* __restrict__ q, int vers
 // a.blockOff and the general block decoder (k_tiles_decode) does the rest, after k_verify_offsets has checked every unit with
 // its true valid count against the chain.  Empty blocks are one-byte units, hence the longer position lists.
 template <class T, bool OFFS = false>
-__global__ void __launch_bounds__(DS_THREADS, OFFS ? 4 : 7) k_decode_stream(StreamDecArgs a) {
+__global__ void __launch_bounds__(DS_THREADS, OFFS ? 4 : 6) k_decode_stream(StreamDecArgs a) {
   using C = DecStream<T>;
   constexpr int LIST = OFFS ? DS_LIST_OFFS : DS_LIST;
   constexpr int PATCH = OFFS ? C::MAXU + 7 : DS_PATCH;           // (offsets: a run of one-byte units may fill the whole head window in front of the guess)
