@@ -252,3 +252,38 @@ def test_concurrent_callers(libs):
     stop.set()
     f.join()
     assert not errors, errors
+
+
+def test_concurrent_pipelined_host_calls(libs):
+    """three host threads with HOST rasters large enough for the strip pipeline (copy-in / kernels / copy-out streams per pooled context;
+    lerc_encode.cu encodeBandFast, lerc_decode.cu decodeStreamFast), pageable memory, different sizes: blobs and pixels equal the oracle's"""
+    prod, orc = libs
+    rng = np.random.default_rng(23)
+    jobs, want = [], []
+    for k in range(3):
+        h, w = 1536 + 256 * k, 2048 + 8 * k                      # 12-17 MB: 8-11 strips
+        arr = (smooth_field(h, w) + rng.normal(0, 0.5, (h, w))).astype(np.float32)
+        s, b, _ = orc.encode(arr, 0.01)
+        assert s == 0
+        s, d, _ = orc.decode(b)
+        jobs.append(arr); want.append((b, d))
+    errors = []
+
+    def worker(k):
+        try:
+            for _ in range(6):
+                s, b, _ = prod.encode(jobs[k], 0.01)
+                if s != 0 or b != want[k][0]:
+                    errors.append(f"thread {k}: encode status {s}, blob equal {b == want[k][0]}")
+                    return
+                s, d, _ = prod.decode(b)
+                if s != 0 or not np.array_equal(d.view(np.uint8), want[k][1].view(np.uint8)):
+                    errors.append(f"thread {k}: decode status {s} or pixels differ")
+                    return
+        except Exception as ex:   # noqa: BLE001
+            errors.append(f"thread {k}: {type(ex).__name__}: {ex}")
+
+    th = [threading.Thread(target=worker, args=(k,)) for k in range(3)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errors, errors
