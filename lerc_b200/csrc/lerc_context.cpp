@@ -152,7 +152,10 @@ void releaseContext(Context* c) {
   if (c->sidePending) { cudaStreamSynchronize(c->side); c->sidePending = false; }
   // early error returns can leave kernels / copies in flight that use the arena or the pinned staging: drain the call's stream before
   // they go back to the pool (free on the success paths, which have synchronised already)
-  if (c->drainOnRelease) cudaStreamSynchronize(c->stream);
+  if (c->drainOnRelease) {
+    cudaStreamSynchronize(c->stream);
+    if (c->copyIn) { cudaStreamSynchronize(c->copyIn); cudaStreamSynchronize(c->copyOut); }     // (strip copies of a pipelined host-resident call)
+  }
   c->drainOnRelease = true;
   c->arena.reset();
   c->pinnedUsed = 0;
